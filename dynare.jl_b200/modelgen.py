@@ -1,0 +1,573 @@
+"""Model set-up: ``.mod`` text -> index bookkeeping + symbolic first-order model -> generated
+CUDA / C model functions.
+
+This replaces, for the likelihood path only, what the reference obtains from its external
+preprocessor and loads as ``RuntimeGeneratedFunction``s (reference
+``src/dynare_functions.jl:10-47, 145-157``; ``src/model.jl:120-139``) and the index sets built
+by ``Model`` (``src/dynare_containers.jl:258-390, 557-602``).  It runs once per model on the
+host; its output is compiled into ``libdynare_b200.so`` (the same idea as Dynare's ``use_dll``).
+
+Conventions reproduced:
+  * variable order = declaration order, then auxiliary variables for leads/lags beyond one period;
+  * dynamic Jacobian column blocks ``[y(-1) | y | y(+1) | u]`` evaluated at the steady state
+    with ``u = 0`` (``src/perturbations.jl:526-531``);
+  * compressed Jacobian = columns with a positive lead/lag incidence, block by block, then the
+    shock columns (``src/perturbations.jl:616-635``);
+  * ``i_bkwrd_b`` (has a lag), ``i_fwrd_b`` (has a lead), ``i_static`` (current only);
+  * Kalman state = ``sort(union(obs_idx, i_bkwrd_b))`` (``src/estimation/estimation.jl:384-390``).
+"""
+from __future__ import annotations
+
+import json
+import keyword
+import re
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import sympy as sp
+
+from .modfile import ModFile, EstimatedParam, parse_mod
+
+# estimated-parameter type codes shared with the C ABI (include/dynare_b200.h)
+EST_PARAM, EST_SD_SHOCK, EST_VAR_SHOCK, EST_CORR_SHOCK, EST_SD_MEAS, EST_VAR_MEAS, EST_CORR_MEAS = range(7)
+
+_FUNCS = {"exp": sp.exp, "log": sp.log, "ln": sp.log, "sqrt": sp.sqrt, "abs": sp.Abs,
+          "sin": sp.sin, "cos": sp.cos, "tan": sp.tan}
+
+
+def _tname(v: str, shift: int) -> str:
+    if shift == 0:
+        return v
+    return f"{v}__{'p' if shift > 0 else 'm'}{abs(shift)}"
+
+
+def _time_subst(expr: str, names: List[str]) -> str:
+    """``x(+1)`` -> ``x__p1`` for every declared variable name."""
+    if not names:
+        return expr
+    alt = "|".join(sorted(map(re.escape, names), key=len, reverse=True))
+    pat = re.compile(rf"\b({alt})\s*\(\s*([+-]?\s*\d+)\s*\)")
+    return pat.sub(lambda m: _tname(m.group(1), int(m.group(2).replace(" ", ""))), expr)
+
+
+@dataclass
+class ModelSpec:
+    name: str
+    endo: List[str]
+    n_orig: int
+    exo: List[str]
+    params: List[str]
+    param_values: np.ndarray
+    linear: bool
+    lli: np.ndarray                      # 3 x n bool: lag / current / lead incidence
+    i_bkwrd_b: List[int]
+    i_fwrd_b: List[int]
+    i_both: List[int]
+    i_static: List[int]
+    i_dyn: List[int]                     # non-static, declaration order
+    sigma_e0: np.ndarray
+    sigma_m0: np.ndarray
+    varobs: List[str]
+    obs_idx: List[int]
+    state_ids: List[int]
+    obs_idx_state: List[int]
+    lagged_state_ids: List[int]
+    est: List[EstimatedParam]
+    est_type: List[int]
+    est_i: List[int]
+    est_j: List[int]
+    estimation_options: Dict[str, str]
+    # symbolic content
+    psym: List[sp.Symbol] = field(default_factory=list)
+    ysym: List[sp.Symbol] = field(default_factory=list)
+    ss_assign: List[Tuple[sp.Symbol, sp.Expr]] = field(default_factory=list)
+    static_resid: List[sp.Expr] = field(default_factory=list)
+    jac: Dict[Tuple[int, int], sp.Expr] = field(default_factory=dict)   # (row, compressed col) -> expr
+
+    # sizes ------------------------------------------------------------------------------
+    @property
+    def n(self): return len(self.endo)
+    @property
+    def nx(self): return len(self.exo)
+    @property
+    def k(self): return len(self.i_bkwrd_b)
+    @property
+    def nf(self): return len(self.i_fwrd_b)
+    @property
+    def s(self): return len(self.i_static)
+    @property
+    def m(self): return self.n - self.s
+    @property
+    def ncol(self): return self.k + self.n + self.nf + self.nx
+    @property
+    def ns(self): return len(self.state_ids)
+    @property
+    def ny(self): return len(self.varobs)
+    @property
+    def nl(self): return len(self.lagged_state_ids)
+    @property
+    def np_est(self): return len(self.est)
+
+    def theta_init(self) -> np.ndarray:
+        """Initial / calibrated value of every estimated parameter, in ``estimated_params`` order."""
+        out = []
+        for e, t, i, j in zip(self.est, self.est_type, self.est_i, self.est_j):
+            if e.init is not None:
+                out.append(e.init)
+            elif t == EST_PARAM:
+                out.append(self.param_values[i])
+            elif t == EST_SD_SHOCK:
+                out.append(np.sqrt(self.sigma_e0[i, i]))
+            elif t == EST_SD_MEAS:
+                out.append(np.sqrt(self.sigma_m0[i, i]))
+            else:
+                out.append(e.mean)
+        return np.array(out, dtype=np.float64)
+
+    def describe(self) -> dict:
+        """Plain-data description (what ``dyb_model_desc`` carries; also stored as JSON)."""
+        return dict(
+            name=self.name, n=self.n, n_orig=self.n_orig, nx=self.nx, npar=len(self.params),
+            k=self.k, nf=self.nf, s=self.s, m=self.m, ncol=self.ncol, ns=self.ns, ny=self.ny,
+            nl=self.nl, np_est=self.np_est, linear=self.linear,
+            endo=self.endo, exo=self.exo, params=self.params,
+            param_values=[float(v) for v in self.param_values],
+            lead_lag_incidence=self.lli.astype(int).tolist(),
+            i_bkwrd_b=self.i_bkwrd_b, i_fwrd_b=self.i_fwrd_b, i_both=self.i_both,
+            i_static=self.i_static, i_dyn=self.i_dyn,
+            sigma_e0=self.sigma_e0.tolist(), sigma_m0=self.sigma_m0.tolist(),
+            varobs=self.varobs, obs_idx=self.obs_idx, state_ids=self.state_ids,
+            obs_idx_state=self.obs_idx_state, lagged_state_ids=self.lagged_state_ids,
+            est_type=self.est_type, est_i=self.est_i, est_j=self.est_j,
+            est_names=[(e.name1 if e.name2 is None else f"{e.name1}:{e.name2}") for e in self.est],
+            priors=[dict(kind=e.kind, shape=e.shape, mean=e.mean,
+                         stdev=(e.stdev if np.isfinite(e.stdev) else "inf")) for e in self.est],
+            theta_init=[float(v) for v in self.theta_init()],
+            estimation_options=self.estimation_options,
+        )
+
+
+def build_spec(name: str, mf: ModFile) -> ModelSpec:
+    endo = list(mf.endo)
+    exo = list(mf.exo)
+    n_orig = len(endo)
+    names = endo + exo
+
+    eq_txt = [_time_subst(f"({lhs}) - ({rhs})", names) for lhs, rhs in mf.equations]
+
+    # --- auxiliary variables for leads / lags beyond one period (encounter order) ------------
+    aux_src: Dict[str, Tuple[str, int]] = {}     # aux name -> (source name, +1/-1)
+    aux_defs: List[str] = []
+    tok = re.compile(r"\b(\w+?)__([pm])(\d+)\b")
+    for _ in range(8):
+        changed = False
+        new_eqs = []
+        for e in eq_txt:
+            def repl(m):
+                nonlocal changed
+                v, d, h = m.group(1), m.group(2), int(m.group(3))
+                if h < 2 or v not in endo:
+                    return m.group(0)
+                if v in exo:
+                    raise NotImplementedError("leads/lags on exogenous variables")
+                sgn = 1 if d == "p" else -1
+                kind = "LEAD" if sgn > 0 else "LAG"
+                cur = v
+                for j in range(1, h):
+                    aux = f"AUX_ENDO_{kind}_{v}_{j}"
+                    if aux not in aux_src:
+                        aux_src[aux] = (cur, sgn)
+                        endo.append(aux)
+                        aux_defs.append(f"({aux}) - ({_tname(cur, sgn)})")
+                    cur = aux
+                changed = True
+                return _tname(cur, sgn)
+            new_eqs.append(tok.sub(repl, e))
+        eq_txt = new_eqs
+        if not changed:
+            break
+    eq_txt += aux_defs
+    n = len(endo)
+    nx = len(exo)
+    if len(eq_txt) != n:
+        raise ValueError(f"{name}: {len(eq_txt)} equations for {n} endogenous variables")
+
+    # --- symbols ---------------------------------------------------------------------------
+    psym = [sp.Symbol(p, real=True) for p in mf.params]
+    ysym = [sp.Symbol(v, real=True) for v in endo]
+    ym = [sp.Symbol(_tname(v, -1), real=True) for v in endo]
+    yp = [sp.Symbol(_tname(v, +1), real=True) for v in endo]
+    usym = [sp.Symbol(u, real=True) for u in exo]
+    local = dict(_FUNCS)
+    for s_ in psym + ysym + ym + yp + usym:
+        local[s_.name] = s_
+
+    # names that are Python keywords (fs2000 has a parameter called ``del``) cannot go through
+    # sympify as they are; they are spelled ``<name>__kw`` in the text handed to the parser
+    kw = [s_ for s_ in local if keyword.iskeyword(s_)]
+    for s_ in kw:
+        local[s_ + "__kw"] = local[s_]
+    kw_pat = re.compile(r"\b(" + "|".join(map(re.escape, kw)) + r")\b") if kw else None
+
+    def parse(txt: str, extra=None) -> sp.Expr:
+        d = dict(local)
+        if extra:
+            d.update(extra)
+        if kw_pat is not None:
+            txt = kw_pat.sub(lambda m: m.group(1) + "__kw", txt)
+        return sp.sympify(txt.replace("^", "**"), locals=d)
+
+    resid = [parse(e) for e in eq_txt]
+    for r in resid:
+        bad = [s_ for s_ in r.free_symbols if s_.name not in local]
+        if bad:
+            raise ValueError(f"{name}: unknown symbols {bad}")
+
+    # --- calibration -----------------------------------------------------------------------
+    pval: Dict[sp.Symbol, float] = {}
+    for pname, expr in mf.calibration:
+        pval[local[pname]] = float(parse(expr).subs(pval))
+    param_values = np.array([pval.get(p, np.nan) for p in psym], dtype=np.float64)
+
+    # --- incidence and index sets ------------------------------------------------------------
+    lli = np.zeros((3, n), dtype=bool)
+    for r in resid:
+        fs = r.free_symbols
+        for j in range(n):
+            lli[0, j] |= ym[j] in fs
+            lli[1, j] |= ysym[j] in fs
+            lli[2, j] |= yp[j] in fs
+    i_bkwrd_b = [j for j in range(n) if lli[0, j]]
+    i_fwrd_b = [j for j in range(n) if lli[2, j]]
+    i_both = [j for j in range(n) if lli[0, j] and lli[2, j]]
+    i_static = [j for j in range(n) if not lli[0, j] and not lli[2, j]]
+    i_dyn = [j for j in range(n) if lli[0, j] or lli[2, j]]
+    if not lli[1].all():
+        raise NotImplementedError(f"{name}: a variable never appears at the current period")
+
+    # --- steady state ----------------------------------------------------------------------
+    ss_assign: List[Tuple[sp.Symbol, sp.Expr]] = []
+    assigned = set()
+    temps: Dict[str, sp.Symbol] = {}
+    for lhs, rhs in mf.steady_state_model:
+        if lhs in endo:
+            target = local[lhs]
+        else:
+            target = temps.setdefault(lhs, sp.Symbol(f"ss_{lhs}", real=True))
+        ss_assign.append((target, parse(rhs, temps)))
+        assigned.add(lhs)
+    for v in endo[:n_orig]:
+        if v not in assigned:
+            if mf.linear or not mf.steady_state_model:
+                ss_assign.append((local[v], sp.Float(0.0)))
+            else:
+                raise ValueError(f"{name}: steady_state_model does not define {v}")
+    for aux in endo[n_orig:]:
+        ss_assign.append((local[aux], local[aux_src[aux][0]]))
+
+    # --- static residuals and Jacobian at the steady state -----------------------------------
+    to_ss = {}
+    for j in range(n):
+        to_ss[ym[j]] = ysym[j]
+        to_ss[yp[j]] = ysym[j]
+    for u in usym:
+        to_ss[u] = sp.Integer(0)
+    static_resid = [r.subs(to_ss) for r in resid]
+
+    k, nf = len(i_bkwrd_b), len(i_fwrd_b)
+    cols: List[sp.Symbol] = [ym[j] for j in i_bkwrd_b] + list(ysym) + [yp[j] for j in i_fwrd_b] + usym
+    jac: Dict[Tuple[int, int], sp.Expr] = {}
+    for i, r in enumerate(resid):
+        fs = r.free_symbols
+        for c, sym in enumerate(cols):
+            if sym in fs:
+                d = sp.diff(r, sym).subs(to_ss)
+                if d != 0:
+                    jac[(i, c)] = d
+
+    # --- shocks / measurement errors --------------------------------------------------------
+    sigma_e0 = np.zeros((nx, nx))
+    for u, expr in mf.shock_stderr.items():
+        if u in exo:
+            sigma_e0[exo.index(u), exo.index(u)] = float(parse(expr).subs(pval)) ** 2
+    for u, expr in mf.shock_var.items():
+        if u in exo:
+            sigma_e0[exo.index(u), exo.index(u)] = float(parse(expr).subs(pval))
+    for (a, b), expr in mf.shock_corr.items():
+        ia, ib = exo.index(a), exo.index(b)
+        c = float(parse(expr).subs(pval)) * np.sqrt(sigma_e0[ia, ia] * sigma_e0[ib, ib])
+        sigma_e0[ia, ib] = sigma_e0[ib, ia] = c
+    ny = len(mf.varobs)
+    sigma_m0 = np.zeros((ny, ny))
+
+    # --- observation / state bookkeeping (estimation.jl:384-390) ---------------------------
+    obs_idx = [endo.index(v) for v in mf.varobs]
+    state_ids = sorted(set(obs_idx) | set(i_bkwrd_b))
+    obs_idx_state = [state_ids.index(i) for i in obs_idx]
+    lagged_state_ids = [p for p, i in enumerate(state_ids) if i in i_bkwrd_b]
+
+    # --- estimated parameters (estimation.jl:517-601 ; dynare_containers.jl:800-841) ----------
+    est_type, est_i, est_j = [], [], []
+    for e in mf.estimated_params:
+        if e.kind == "param":
+            est_type.append(EST_PARAM); est_i.append(mf.params.index(e.name1)); est_j.append(0)
+        elif e.kind == "stderr":
+            if e.name1 in exo:
+                est_type.append(EST_SD_SHOCK); est_i.append(exo.index(e.name1)); est_j.append(exo.index(e.name1))
+            else:
+                o = mf.varobs.index(e.name1)
+                est_type.append(EST_SD_MEAS); est_i.append(o); est_j.append(o)
+        elif e.kind == "corr":
+            if e.name1 in exo:
+                est_type.append(EST_CORR_SHOCK); est_i.append(exo.index(e.name1)); est_j.append(exo.index(e.name2))
+            else:
+                est_type.append(EST_CORR_MEAS); est_i.append(mf.varobs.index(e.name1)); est_j.append(mf.varobs.index(e.name2))
+
+    return ModelSpec(
+        name=name, endo=endo, n_orig=n_orig, exo=exo, params=list(mf.params),
+        param_values=param_values, linear=mf.linear, lli=lli,
+        i_bkwrd_b=i_bkwrd_b, i_fwrd_b=i_fwrd_b, i_both=i_both, i_static=i_static, i_dyn=i_dyn,
+        sigma_e0=sigma_e0, sigma_m0=sigma_m0, varobs=list(mf.varobs), obs_idx=obs_idx,
+        state_ids=state_ids, obs_idx_state=obs_idx_state, lagged_state_ids=lagged_state_ids,
+        est=list(mf.estimated_params), est_type=est_type, est_i=est_i, est_j=est_j,
+        estimation_options=dict(mf.estimation_options),
+        psym=psym, ysym=ysym, ss_assign=ss_assign, static_resid=static_resid, jac=jac,
+    )
+
+
+def spec_from_file(name: str, path: str) -> ModelSpec:
+    with open(path) as f:
+        return build_spec(name, parse_mod(f.read()))
+
+
+# =========================================================================================
+# numeric evaluation on the host (used by tests and by the host-evaluated-Jacobian entry point)
+# =========================================================================================
+class HostModel:
+    """Lambdified steady state / static residuals / compressed Jacobian of a ``ModelSpec``."""
+
+    def __init__(self, spec: ModelSpec):
+        self.spec = spec
+        p, y = spec.psym, spec.ysym
+        # steady state: sequential substitution -> closed form in the parameters
+        env: Dict[sp.Symbol, sp.Expr] = {}
+        for tgt, expr in spec.ss_assign:
+            env[tgt] = expr.subs(env)
+        self._ss = sp.lambdify([p], [env[s_] for s_ in y], modules="numpy")
+        self._res = sp.lambdify([p, y], spec.static_resid, modules="numpy")
+        keys = sorted(spec.jac.keys(), key=lambda rc: (rc[1], rc[0]))
+        self._jkeys = keys
+        self._jac = sp.lambdify([p, y], [spec.jac[kx] for kx in keys], modules="numpy")
+
+    def steady_state(self, params) -> np.ndarray:
+        with np.errstate(all="ignore"):
+            return np.array(self._ss(list(params)), dtype=np.float64)
+
+    def static_residuals(self, params, ybar) -> np.ndarray:
+        with np.errstate(all="ignore"):
+            return np.array(self._res(list(params), list(ybar)), dtype=np.float64)
+
+    def jacobian(self, params, ybar) -> np.ndarray:
+        """Compressed Jacobian, ``n x ncol`` (column blocks lags | current | leads | shocks)."""
+        sp_ = self.spec
+        J = np.zeros((sp_.n, sp_.ncol))
+        with np.errstate(all="ignore"):
+            vals = self._jac(list(params), list(ybar))
+        for (r, c), v in zip(self._jkeys, vals):
+            J[r, c] = v
+        return J
+
+
+# =========================================================================================
+# code generation
+# =========================================================================================
+def _pow_opt(expr):
+    from sympy.codegen.rewriting import create_expand_pow_optimization, optimize
+    return optimize(expr, [create_expand_pow_optimization(4)])
+
+
+class _Printer:
+    def __init__(self):
+        from sympy.printing.c import C99CodePrinter
+
+        class P(C99CodePrinter):
+            def _print_Rational(self, e):
+                return f"({float(e.p)!r}/{float(e.q)!r})"
+
+            def _print_Integer(self, e):
+                return f"{float(int(e))!r}"
+
+            def _print_Pow(self, e):
+                b, ex = e.base, e.exp
+                if ex.is_Integer and 2 <= int(ex) <= 4:
+                    s_ = self._print(b)
+                    if not (b.is_Symbol or b.is_Number):
+                        s_ = f"({s_})"
+                    return "(" + "*".join([s_] * int(ex)) + ")"
+                if ex.is_Integer and -4 <= int(ex) <= -1:
+                    return f"(1.0/{self._print(b ** (-ex))})"
+                if ex == sp.Rational(1, 2):
+                    return f"sqrt({self._print(b)})"
+                return f"pow({self._print(b)}, {self._print(ex)})"
+
+        self.p = P()
+
+    def __call__(self, e) -> str:
+        return self.p.doprint(e)
+
+
+def _lower(spec: ModelSpec):
+    """Lower the symbolic model to three straight-line blocks of (name, C expression)."""
+    pr = _Printer()
+    psub = {s_: sp.Symbol(f"p[{i}]") for i, s_ in enumerate(spec.psym)}
+    ysub = {s_: sp.Symbol(f"y[{i}]") for i, s_ in enumerate(spec.ysym)}
+    sub = {**psub, **ysub}
+
+    # steady state: keep the user's temporaries as locals
+    ss_lines = []
+    for tgt, expr in spec.ss_assign:
+        e = expr.subs(sub)
+        if tgt in ysub:
+            ss_lines.append((str(ysub[tgt]), pr(e), False))
+        else:
+            sub[tgt] = sp.Symbol(tgt.name)
+            ss_lines.append((tgt.name, pr(e), True))
+
+    res_exprs = [r.subs(sub) for r in spec.static_resid]
+    rrep, rred = sp.cse(res_exprs, symbols=sp.numbered_symbols("r_"), optimizations="basic")
+    res_lines = [(str(a), pr(b), True) for a, b in rrep]
+    res_out = [pr(e) for e in rred]
+
+    keys = sorted(spec.jac.keys(), key=lambda rc: (rc[1], rc[0]))
+    jexprs = [spec.jac[kx].subs(sub) for kx in keys]
+    jrep, jred = sp.cse(jexprs, symbols=sp.numbered_symbols("t_"), optimizations="basic")
+    jac_lines = [(str(a), pr(b), True) for a, b in jrep]
+    jac_out = [(r, c, pr(e)) for (r, c), e in zip(keys, jred)]
+    return ss_lines, res_lines, res_out, jac_lines, jac_out
+
+
+def _int_list(v) -> str:
+    v = list(v)
+    return "{" + ", ".join(str(int(x)) for x in v) + "}" if v else "{0}"
+
+
+def _dbl_list(v) -> str:
+    v = [float(x) for x in np.asarray(v).ravel()]
+    return "{" + ", ".join(repr(x) if np.isfinite(x) else "0.0" for x in v) + "}" if v else "{0.0}"
+
+
+def emit_cuda(spec: ModelSpec) -> str:
+    """CUDA header: a traits struct with compile-time sizes/index sets and the device model function."""
+    ss_lines, res_lines, res_out, jac_lines, jac_out = _lower(spec)
+    S = spec
+    pos_in_dyn = {v: i for i, v in enumerate(S.i_dyn)}
+    L = []
+    A = L.append
+    A(f"// GENERATED by dynare_jl_b200.modelgen from model '{S.name}' -- do not edit.")
+    A("// Replaces the preprocessor-generated SparseDynamicG1!/SteadyState2 functions the reference loads")
+    A("// in src/dynare_functions.jl:10-47 and calls from src/model.jl:120-139.")
+    A("#pragma once")
+    A("#include \"../model_traits.cuh\"")
+    A("namespace dyb {")
+    A(f"struct Model_{S.name} {{")
+    A(f"  static constexpr const char* name = \"{S.name}\";")
+    for nm, val in [("N", S.n), ("NX", S.nx), ("NPAR", len(S.params)), ("K", S.k), ("NF", S.nf),
+                    ("S", S.s), ("M", S.m), ("NCOL", S.ncol), ("NS", S.ns), ("NY", S.ny),
+                    ("NL", S.nl), ("NP_DEFAULT", S.np_est)]:
+        A(f"  static constexpr int {nm} = {val};")
+    A(f"  static constexpr bool LINEAR = {'true' if S.linear else 'false'};")
+
+    def arr(nm, v):
+        v = list(v)
+        A(f"  DYB_HD static constexpr int {nm}(int i) {{ constexpr int a[{max(len(v), 1)}] = {_int_list(v)}; return a[i]; }}")
+    arr("i_bkwrd_b", S.i_bkwrd_b)
+    arr("i_fwrd_b", S.i_fwrd_b)
+    arr("i_static", S.i_static)
+    arr("i_dyn", S.i_dyn)
+    arr("bkwrd_in_dyn", [pos_in_dyn[v] for v in S.i_bkwrd_b])
+    arr("fwrd_in_dyn", [pos_in_dyn[v] for v in S.i_fwrd_b])
+    arr("state_ids", S.state_ids)
+    arr("obs_idx_state", S.obs_idx_state)
+    arr("lagged_state_ids", S.lagged_state_ids)
+    # position of each lagged state inside i_bkwrd_b (column of g1_1)
+    arr("lagged_in_bkwrd", [S.i_bkwrd_b.index(S.state_ids[p]) for p in S.lagged_state_ids])
+    A("")
+    A("  // closed-form steady state (reference: generated steady_state!, src/dynare_functions.jl:39-41)")
+    A("  DYB_HD static void steady_state(const double* __restrict__ p, double* __restrict__ y) {")
+    for nm, ex, is_local in ss_lines:
+        A(f"    {'const double ' if is_local else ''}{nm} = {ex};")
+    A("  }")
+    A("  // sum of squared static residuals at y (reference: check_steady_state, src/steady_state/SteadyState.jl:476-482)")
+    A("  DYB_HD static double static_resid_ss(const double* __restrict__ p, const double* __restrict__ y) {")
+    for nm, ex, _ in res_lines:
+        A(f"    const double {nm} = {ex};")
+    A("    double acc = 0.0, r;")
+    for ex in res_out:
+        A(f"    r = {ex}; acc += r*r;")
+    A("    return acc;")
+    A("  }")
+    A("  // non-zeros of the compressed dynamic Jacobian, n x NCOL column-major, at the steady state, u = 0")
+    A("  // (reference: get_dynamic_jacobian! + set_compressed_jacobian!, src/model.jl:120-139, src/perturbations.jl:616-635)")
+    A("  // J must be zero-initialised by the caller; JT is any type with operator[](int).")
+    A("  template <class JT>")
+    A("  DYB_HD static void jacobian(const double* __restrict__ p, const double* __restrict__ y, JT& J) {")
+    for nm, ex, _ in jac_lines:
+        A(f"    const double {nm} = {ex};")
+    for r, c, ex in jac_out:
+        A(f"    J[{r + S.n * c}] = {ex};")
+    A("  }")
+    A(f"  static constexpr int JAC_NNZ = {len(jac_out)};")
+    A("};")
+    A("}  // namespace dyb")
+    return "\n".join(L) + "\n"
+
+
+def emit_c(spec: ModelSpec) -> str:
+    """Plain-C model functions + descriptor for the CPU oracle port (oracle/c)."""
+    ss_lines, res_lines, res_out, jac_lines, jac_out = _lower(spec)
+    S = spec
+    nm = S.name
+    L = []
+    A = L.append
+    A(f"/* GENERATED by dynare_jl_b200.modelgen from model '{nm}' -- do not edit. Test infrastructure (CPU oracle). */")
+    A("#include <math.h>")
+    A("#include \"oracle_model.h\"")
+    A(f"static void {nm}_steady_state(const double* p, double* y) {{")
+    for n_, ex, is_local in ss_lines:
+        A(f"  {'const double ' if is_local else ''}{n_} = {ex};")
+    A("}")
+    A(f"static double {nm}_static_resid_ss(const double* p, const double* y) {{")
+    for n_, ex, _ in res_lines:
+        A(f"  const double {n_} = {ex};")
+    A("  double acc = 0.0, r;")
+    for ex in res_out:
+        A(f"  r = {ex}; acc += r*r;")
+    A("  return acc;")
+    A("}")
+    A(f"static void {nm}_jacobian(const double* p, const double* y, double* J) {{")
+    for n_, ex, _ in jac_lines:
+        A(f"  const double {n_} = {ex};")
+    for r, c, ex in jac_out:
+        A(f"  J[{r + S.n * c}] = {ex};")
+    A("}")
+    for an, v in [("i_bkwrd_b", S.i_bkwrd_b), ("i_fwrd_b", S.i_fwrd_b), ("i_static", S.i_static),
+                  ("i_dyn", S.i_dyn), ("state_ids", S.state_ids), ("obs_idx_state", S.obs_idx_state),
+                  ("lagged_state_ids", S.lagged_state_ids), ("est_type", S.est_type),
+                  ("est_i", S.est_i), ("est_j", S.est_j)]:
+        A(f"static const int {nm}_{an}[] = {_int_list(v)};")
+    A(f"static const double {nm}_params0[] = {_dbl_list(S.param_values)};")
+    A(f"static const double {nm}_sigma_e0[] = {_dbl_list(S.sigma_e0.T)};")
+    A(f"static const double {nm}_sigma_m0[] = {_dbl_list(S.sigma_m0.T)};")
+    A(f"const oracle_model oracle_model_{nm} = {{")
+    A(f"  \"{nm}\", {S.n}, {S.nx}, {len(S.params)}, {S.k}, {S.nf}, {S.s}, {S.ncol}, {S.ns}, {S.ny}, {S.nl}, {S.np_est},")
+    A(f"  {nm}_i_bkwrd_b, {nm}_i_fwrd_b, {nm}_i_static, {nm}_i_dyn, {nm}_state_ids, {nm}_obs_idx_state, {nm}_lagged_state_ids,")
+    A(f"  {nm}_est_type, {nm}_est_i, {nm}_est_j, {nm}_params0, {nm}_sigma_e0, {nm}_sigma_m0,")
+    A(f"  {nm}_steady_state, {nm}_static_resid_ss, {nm}_jacobian")
+    A("};")
+    return "\n".join(L) + "\n"
+
+
+def write_json(spec: ModelSpec, path: str) -> None:
+    with open(path, "w") as f:
+        json.dump(spec.describe(), f, indent=1)

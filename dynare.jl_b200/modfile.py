@@ -1,0 +1,229 @@
+"""Reader for the subset of the Dynare ``.mod`` language the likelihood path needs.
+
+The reference hands ``.mod`` files to an external C++ preprocessor binary
+(``DynarePreprocessor_jll``; reference ``src/DynarePreprocessor.jl:4-40``) and reads
+the JSON it produces (``src/DynareParser.jl:169-218``).  That binary is not part of
+the reference tree and is not available here, so this module reads the declarative
+blocks directly.  It is a host-side set-up tool (runs once per model, never per draw).
+
+Supported: ``var``, ``varexo``, ``parameters``, parameter calibration statements,
+``model;`` / ``model(linear);``, ``steady_state_model;``, ``shocks;`` (``var x; stderr s;``,
+``var x = v;``, ``corr a, b = r;``), ``varobs``, ``estimated_params;``,
+``estimated_params_init;``, ``x.prior(shape=..., mean=..., stdev=...)`` statements and the
+``nobs`` / ``first_obs`` / ``datafile`` options of ``estimation(...)`` (also when the
+statement is commented out with ``//``, which is how the reference's fixtures carry it:
+``test/models/ls2003/ls2003.mod:85``).
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+
+@dataclass
+class EstimatedParam:
+    """One row of ``estimated_params`` (reference ``src/estimation/priors.jl:370-433``)."""
+    kind: str                 # 'param' | 'stderr' | 'corr'
+    name1: str
+    name2: Optional[str]
+    shape: str                # 'beta' 'gamma' 'normal' 'inv_gamma' 'uniform' 'inv_gamma2' 'weibull'
+    mean: float
+    stdev: float
+    init: Optional[float] = None
+    domain: Optional[Tuple[float, float]] = None
+
+
+@dataclass
+class ModFile:
+    endo: List[str] = field(default_factory=list)
+    exo: List[str] = field(default_factory=list)
+    params: List[str] = field(default_factory=list)
+    calibration: List[Tuple[str, str]] = field(default_factory=list)   # (name, expr) in file order
+    equations: List[Tuple[str, str]] = field(default_factory=list)     # (lhs, rhs); rhs '0' if none
+    linear: bool = False
+    steady_state_model: List[Tuple[str, str]] = field(default_factory=list)
+    shock_stderr: Dict[str, str] = field(default_factory=dict)
+    shock_var: Dict[str, str] = field(default_factory=dict)
+    shock_corr: Dict[Tuple[str, str], str] = field(default_factory=dict)
+    varobs: List[str] = field(default_factory=list)
+    estimated_params: List[EstimatedParam] = field(default_factory=list)
+    estimation_options: Dict[str, str] = field(default_factory=dict)
+
+
+_SHAPES = {
+    "beta_pdf": "beta", "beta": "beta",
+    "gamma_pdf": "gamma", "gamma": "gamma",
+    "normal_pdf": "normal", "normal": "normal",
+    "inv_gamma_pdf": "inv_gamma", "inv_gamma1_pdf": "inv_gamma", "inv_gamma": "inv_gamma",
+    "inv_gamma1": "inv_gamma",
+    "uniform_pdf": "uniform", "uniform": "uniform",
+    "inv_gamma2_pdf": "inv_gamma2", "inv_gamma2": "inv_gamma2",
+    "weibull_pdf": "weibull", "weibull": "weibull",
+}
+
+
+def _num(s: str) -> float:
+    s = s.strip().lower()
+    if s in ("inf", "+inf"):
+        return float("inf")
+    if s == "-inf":
+        return float("-inf")
+    return float(eval(s.replace("^", "**"), {"__builtins__": {}}, {}))
+
+
+def _strip_comments(text: str) -> Tuple[str, List[str]]:
+    """Return the text without comments and the list of ``//`` comment bodies."""
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    comments = []
+    out = []
+    for line in text.splitlines():
+        m = re.search(r"//|%", line)
+        if m:
+            comments.append(line[m.end():])
+            line = line[: m.start()]
+        out.append(line)
+    return "\n".join(out), comments
+
+
+def _names(body: str) -> List[str]:
+    body = re.sub(r"\$[^$]*\$", " ", body)
+    body = re.sub(r"\([^)]*\)", " ", body)
+    return [t for t in re.split(r"[\s,]+", body.strip()) if t]
+
+
+def _parse_estimation_options(stmt: str, opts: Dict[str, str]) -> None:
+    m = re.match(r"\s*estimation\s*\((.*)\)", stmt, flags=re.S)
+    if not m:
+        return
+    for item in re.split(r",(?![^()]*\))", m.group(1)):
+        if "=" in item:
+            k, v = item.split("=", 1)
+            opts[k.strip()] = v.strip().strip("'\"")
+        elif item.strip():
+            opts[item.strip()] = "true"
+
+
+def parse_mod(text: str) -> ModFile:
+    mf = ModFile()
+    clean, comments = _strip_comments(text)
+    # an estimation statement that only exists as a comment still defines the sample
+    for c in comments:
+        if re.match(r"\s*estimation\s*\(", c):
+            _parse_estimation_options(c.strip().rstrip(";"), mf.estimation_options)
+    stmts = [s.strip() for s in clean.split(";")]
+    block = None
+    pending_shock: Optional[str] = None
+    for s in stmts:
+        if not s:
+            continue
+        flat = " ".join(s.split())
+        if block is not None:
+            if flat == "end":
+                block = None
+                pending_shock = None
+                continue
+            if block == "model":
+                if "=" in flat:
+                    lhs, rhs = flat.split("=", 1)
+                else:
+                    lhs, rhs = flat, "0"
+                # drop equation tags  [name='...']
+                lhs = re.sub(r"^\[[^\]]*\]\s*", "", lhs)
+                mf.equations.append((lhs.strip(), rhs.strip()))
+            elif block == "steady_state_model":
+                lhs, rhs = flat.split("=", 1)
+                mf.steady_state_model.append((lhs.strip(), rhs.strip()))
+            elif block == "shocks":
+                m = re.match(r"var\s+(\w+)\s*=\s*(.+)$", flat)
+                if m:
+                    mf.shock_var[m.group(1)] = m.group(2)
+                    continue
+                m = re.match(r"var\s+(\w+)$", flat)
+                if m:
+                    pending_shock = m.group(1)
+                    continue
+                m = re.match(r"stderr\s+(.+)$", flat)
+                if m and pending_shock:
+                    mf.shock_stderr[pending_shock] = m.group(1)
+                    pending_shock = None
+                    continue
+                m = re.match(r"corr\s+(\w+)\s*,\s*(\w+)\s*=\s*(.+)$", flat)
+                if m:
+                    mf.shock_corr[(m.group(1), m.group(2))] = m.group(3)
+                    continue
+                raise ValueError(f"unsupported shocks statement: {flat!r}")
+            elif block == "estimated_params":
+                parts = [p.strip() for p in flat.split(",")]
+                head = parts[0].split()
+                if head[0] == "stderr":
+                    kind, n1, n2 = "stderr", head[1], None
+                    rest = parts[1:]
+                elif head[0] == "corr":
+                    kind, n1, n2 = "corr", head[1], parts[1]
+                    rest = parts[2:]
+                else:
+                    kind, n1, n2 = "param", head[0], None
+                    rest = parts[1:]
+                # forms:  shape, mean, std   |   init, shape, mean, std  |  init, lb, ub, shape, mean, std
+                si = next(i for i, p in enumerate(rest) if p.lower() in _SHAPES)
+                init = _num(rest[0]) if si >= 1 and rest[0] else None
+                shape = _SHAPES[rest[si].lower()]
+                mean = _num(rest[si + 1])
+                std = _num(rest[si + 2])
+                mf.estimated_params.append(EstimatedParam(kind, n1, n2, shape, mean, std, init))
+            elif block == "estimated_params_init":
+                parts = [p.strip() for p in flat.split(",")]
+                head = parts[0].split()
+                if head[0] == "stderr":
+                    key = ("stderr", head[1], None)
+                elif head[0] == "corr":
+                    key = ("corr", head[1], parts[1])
+                    parts = parts[1:]
+                else:
+                    key = ("param", head[0], None)
+                for ep in mf.estimated_params:
+                    if (ep.kind, ep.name1, ep.name2) == key:
+                        ep.init = _num(parts[1])
+            # other blocks (initval, histval, ...) are ignored
+            continue
+
+        m = re.match(r"(model|steady_state_model|shocks|estimated_params|estimated_params_init|"
+                     r"initval|endval|histval|observation_trends|estimated_params_bounds)"
+                     r"\s*(\(([^)]*)\))?$", flat)
+        if m:
+            block = m.group(1)
+            if block == "model" and m.group(3) and "linear" in m.group(3):
+                mf.linear = True
+            continue
+        m = re.match(r"(var|varexo|parameters|varobs)\s+(.*)$", flat, flags=re.S)
+        if m:
+            target = {"var": mf.endo, "varexo": mf.exo, "parameters": mf.params,
+                      "varobs": mf.varobs}[m.group(1)]
+            target.extend(_names(m.group(2)))
+            continue
+        m = re.match(r"(std\s*\(\s*(\w+)\s*\)|corr\s*\(\s*(\w+)\s*,\s*(\w+)\s*\)|(\w+))\.prior\s*\((.*)\)$", flat)
+        if m:
+            kw = {}
+            for item in m.group(6).split(","):
+                k, v = item.split("=", 1)
+                kw[k.strip()] = v.strip()
+            if m.group(2):
+                kind, n1, n2 = "stderr", m.group(2), None
+            elif m.group(3):
+                kind, n1, n2 = "corr", m.group(3), m.group(4)
+            else:
+                kind, n1, n2 = "param", m.group(5), None
+            stdev = _num(kw["stdev"]) if "stdev" in kw else _num(kw["variance"]) ** 0.5
+            mf.estimated_params.append(
+                EstimatedParam(kind, n1, n2, _SHAPES[kw["shape"].lower()], _num(kw["mean"]), stdev))
+            continue
+        m = re.match(r"(\w+)\s*=\s*(.+)$", flat)
+        if m and m.group(1) in mf.params:
+            mf.calibration.append((m.group(1), m.group(2)))
+            continue
+        if flat.startswith("estimation"):
+            _parse_estimation_options(flat, mf.estimation_options)
+            continue
+        # steady, check, stoch_simul, ... : statements of the reference front end, not needed
+    return mf

@@ -1,0 +1,570 @@
+// C ABI of libdynare_b200.so (declared in include/dynare_b200.h).
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "registry.h"
+#include "kalman_generic.cuh"
+#include "smc_kernels.cuh"
+
+namespace dyb {
+
+static std::vector<const ModelOps*>& reg_mut() {
+  static std::vector<const ModelOps*> r;
+  return r;
+}
+const std::vector<const ModelOps*>& registry() { return reg_mut(); }
+void register_model(const ModelOps* m) { reg_mut().push_back(m); }
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define DYB_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(DYB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+static const ModelOps* find_model(const char* name) {
+  if (!name) return nullptr;
+  for (auto* m : registry()) if (std::strcmp(m->name, name) == 0) return m;
+  return nullptr;
+}
+
+static bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+static bool is_pinned_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// growable device / pinned buffers
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Per-call staging of arguments that may live on the host or on the device.
+struct Stager {
+  cudaStream_t st;
+  struct Back { void* host; void* dev; size_t bytes; };
+  std::vector<void*> temps;
+  std::vector<Back> backs;
+  cudaError_t err = cudaSuccess;
+  explicit Stager(cudaStream_t s) : st(s) {}
+  template <class T> const T* in(const T* p, size_t count) {
+    if (!p || is_device_ptr(p)) return p;
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, count * sizeof(T) + 8);
+    if (e != cudaSuccess) { err = e; return nullptr; }
+    temps.push_back(d);
+    e = cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) err = e;
+    return static_cast<const T*>(d);
+  }
+  template <class T> T* out(T* p, size_t count) {
+    if (!p || is_device_ptr(p)) return p;
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, count * sizeof(T) + 8);
+    if (e != cudaSuccess) { err = e; return nullptr; }
+    temps.push_back(d);
+    backs.push_back({p, d, count * sizeof(T)});
+    return static_cast<T*>(d);
+  }
+  template <class T> T* temp(size_t count) {
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, count * sizeof(T) + 8);
+    if (e != cudaSuccess) { err = e; return nullptr; }
+    temps.push_back(d);
+    return static_cast<T*>(d);
+  }
+  cudaError_t finish() {
+    cudaError_t e = err;
+    for (auto& b : backs) {
+      cudaError_t e2 = cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = e2;
+    }
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = e3;
+    for (void* t : temps) cudaFree(t);
+    temps.clear(); backs.clear();
+    return e;
+  }
+  ~Stager() { for (void* t : temps) cudaFree(t); }
+};
+
+static cudaStream_t device_stream(int device) {
+  static std::mutex mu;
+  static std::vector<cudaStream_t> streams;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)streams.size() <= device) streams.resize(device + 1, nullptr);
+  if (!streams[device]) cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking);
+  return streams[device];
+}
+
+}  // namespace dyb
+
+using namespace dyb;
+
+struct dyb_handle {
+  const ModelOps* ops = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+  HostState hs;
+  DevBuf d_theta, d_ss, d_st1, d_ll, d_st2, d_Y;
+  PinBuf h_in, h_out;
+  int ny_obs = 0, nobs = 0;
+  int64_t launches = 0;
+};
+
+static void default_options(dyb_options* o) {
+  o->cr_tol = 1e-8;
+  o->cr_maxit = 100;
+  o->steady_tol = std::cbrt(2.220446049250313e-16);
+  o->lyap_tol = 1e-16;
+  o->lyap_maxit = 60;
+  o->presample = 0;
+}
+
+extern "C" {
+
+int dyb_version(void) { return DYB_VERSION; }
+const char* dyb_last_error(void) { return g_err.c_str(); }
+
+int dyb_device_count(int* count) {
+  if (!count) return fail(DYB_ERR_ARG, "count is null");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { cudaGetLastError(); *count = 0; return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
+  *count = c;
+  return DYB_OK;
+}
+
+int dyb_model_count(void) { return (int)registry().size(); }
+const char* dyb_model_name(int index) {
+  if (index < 0 || index >= (int)registry().size()) return nullptr;
+  return registry()[index]->name;
+}
+int dyb_model_get_dims(const char* model, dyb_model_dims* dims) {
+  const ModelOps* m = find_model(model);
+  if (!m || !dims) return fail(DYB_ERR_ARG, "unknown model or null dims");
+  *dims = m->dims;
+  return DYB_OK;
+}
+
+int dyb_create(const char* model, int device, dyb_handle** out) {
+  if (!out) return fail(DYB_ERR_ARG, "out is null");
+  *out = nullptr;
+  const ModelOps* m = find_model(model);
+  if (!m) return fail(DYB_ERR_ARG, std::string("unknown model: ") + (model ? model : "(null)"));
+  int ndev = 0;
+  DYB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(DYB_ERR_ARG, "no such CUDA device");
+  DYB_CUDA(cudaSetDevice(device));
+  dyb_handle* h = new dyb_handle();
+  h->ops = m;
+  h->device = device;
+  m->defaults(h->hs);
+  default_options(&h->hs.opt);
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  if (e != cudaSuccess) { delete h; return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
+  *out = h;
+  return DYB_OK;
+}
+
+int dyb_destroy(dyb_handle* h) {
+  if (!h) return DYB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->d_theta.release(); h->d_ss.release(); h->d_st1.release(); h->d_ll.release(); h->d_st2.release(); h->d_Y.release();
+  h->h_in.release(); h->h_out.release();
+  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return DYB_OK;
+}
+
+int dyb_get_dims(const dyb_handle* h, dyb_model_dims* dims) {
+  if (!h || !dims) return fail(DYB_ERR_ARG, "null argument");
+  *dims = h->ops->dims;
+  return DYB_OK;
+}
+int dyb_get_options(const dyb_handle* h, dyb_options* opt) {
+  if (!h || !opt) return fail(DYB_ERR_ARG, "null argument");
+  *opt = h->hs.opt;
+  return DYB_OK;
+}
+int dyb_set_options(dyb_handle* h, const dyb_options* opt) {
+  if (!h || !opt) return fail(DYB_ERR_ARG, "null argument");
+  if (!(opt->cr_tol > 0) || opt->cr_maxit < 1 || !(opt->steady_tol > 0) || !(opt->lyap_tol >= 0) ||
+      opt->lyap_maxit < 1 || opt->presample < 0)
+    return fail(DYB_ERR_ARG, "invalid option value");
+  h->hs.opt = *opt;
+  return DYB_OK;
+}
+
+int dyb_set_calibration(dyb_handle* h, const double* params, const double* sigma_e, const double* sigma_m) {
+  if (!h) return fail(DYB_ERR_ARG, "null handle");
+  const dyb_model_dims& d = h->ops->dims;
+  if (params) h->hs.params.assign(params, params + d.npar);
+  if (sigma_e) h->hs.sigma_e.assign(sigma_e, sigma_e + d.nx * d.nx);
+  if (sigma_m) h->hs.sigma_m.assign(sigma_m, sigma_m + d.ny * d.ny);
+  return DYB_OK;
+}
+
+int dyb_set_estimated_params(dyb_handle* h, int32_t np, const int32_t* kind, const int32_t* i1, const int32_t* i2) {
+  if (!h || np < 0 || np > MAX_EST || (np > 0 && (!kind || !i1 || !i2))) return fail(DYB_ERR_ARG, "bad estimated-parameter map");
+  const dyb_model_dims& d = h->ops->dims;
+  for (int q = 0; q < np; ++q) {
+    int lim1, lim2;
+    switch (kind[q]) {
+      case DYB_EST_PARAM: lim1 = d.npar; lim2 = 1 << 30; break;
+      case DYB_EST_SD_SHOCK: case DYB_EST_VAR_SHOCK: case DYB_EST_CORR_SHOCK: lim1 = lim2 = d.nx; break;
+      case DYB_EST_SD_MEAS: case DYB_EST_VAR_MEAS: case DYB_EST_CORR_MEAS: lim1 = lim2 = d.ny; break;
+      default: return fail(DYB_ERR_ARG, "unknown estimated-parameter kind");
+    }
+    if (i1[q] < 0 || i1[q] >= lim1 || i2[q] < 0 || i2[q] >= lim2) return fail(DYB_ERR_ARG, "estimated-parameter index out of range");
+  }
+  h->hs.np = np;
+  for (int q = 0; q < np; ++q) { h->hs.est_type[q] = kind[q]; h->hs.est_i[q] = i1[q]; h->hs.est_j[q] = i2[q]; }
+  return DYB_OK;
+}
+
+int dyb_set_observations(dyb_handle* h, const double* Y, int32_t ny, int32_t nobs) {
+  if (!h || !Y) return fail(DYB_ERR_ARG, "null argument");
+  if (ny != h->ops->dims.ny) return fail(DYB_ERR_ARG, "observations must have ny rows");
+  if (nobs < 0) return fail(DYB_ERR_ARG, "nobs < 0");
+  if ((size_t)ny * nobs * sizeof(double) > 200 * 1024) return fail(DYB_ERR_UNSUPPORTED, "observation matrix larger than 200 KB");
+  DYB_CUDA(cudaSetDevice(h->device));
+  DYB_CUDA(h->d_Y.reserve(sizeof(double) * (size_t)ny * (nobs > 0 ? nobs : 1)));
+  if (nobs > 0) DYB_CUDA(cudaMemcpyAsync(h->d_Y.p, Y, sizeof(double) * (size_t)ny * nobs,
+                                         is_device_ptr(Y) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  h->ny_obs = ny; h->nobs = nobs;
+  return DYB_OK;
+}
+
+static int reserve_batch(dyb_handle* h, int64_t n) {
+  const dyb_model_dims& d = h->ops->dims;
+  const size_t N = (size_t)(n > 0 ? n : 1);
+  DYB_CUDA(h->d_ss.reserve(sizeof(double) * d.ss_doubles * N));
+  DYB_CUDA(h->d_st1.reserve(sizeof(int) * N));
+  return DYB_OK;
+}
+
+int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, double* d_loglik, int32_t* d_status) {
+  if (!h || n < 0 || (n > 0 && (!d_theta || !d_loglik || !d_status))) return fail(DYB_ERR_ARG, "null argument");
+  if (h->nobs <= 0 && h->d_Y.p == nullptr) return fail(DYB_ERR_STATE, "dyb_set_observations has not been called");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  int rc = reserve_batch(h, n);
+  if (rc) return rc;
+  SolveOut so{h->d_ss.as<double>(), h->d_st1.as<int>(), nullptr, nullptr, nullptr};
+  DYB_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  DYB_CUDA(h->ops->solve(h->hs, d_theta, n, so, h->stream));
+  DYB_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  DYB_CUDA(h->ops->kalman(h->d_ss.as<double>(), n, h->d_Y.as<double>(), h->nobs, h->hs.opt.presample,
+                          h->d_st1.as<int>(), d_loglik, d_status, h->stream));
+  DYB_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  h->ev_valid = true;
+  h->launches += 2;
+  return DYB_OK;
+}
+
+int dyb_loglik_batch(dyb_handle* h, const double* theta, int64_t n, double* loglik, int32_t* status) {
+  if (!h || n < 0 || (n > 0 && (!theta || !loglik || !status))) return fail(DYB_ERR_ARG, "null argument");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  const int np = h->hs.np;
+  const size_t N = (size_t)n;
+  DYB_CUDA(h->d_theta.reserve(sizeof(double) * np * N + 8));
+  DYB_CUDA(h->d_ll.reserve(sizeof(double) * N));
+  DYB_CUDA(h->d_st2.reserve(sizeof(int) * N));
+  const bool dev_in = is_device_ptr(theta);
+  const void* src = theta;
+  if (!dev_in && !is_pinned_ptr(theta)) {
+    DYB_CUDA(h->h_in.reserve(sizeof(double) * np * N + 8));
+    std::memcpy(h->h_in.p, theta, sizeof(double) * np * N);
+    src = h->h_in.p;
+  }
+  DYB_CUDA(cudaMemcpyAsync(h->d_theta.p, src, sizeof(double) * np * N,
+                           dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  int rc = dyb_loglik_batch_device(h, h->d_theta.as<double>(), n, h->d_ll.as<double>(), h->d_st2.as<int>());
+  if (rc) return rc;
+  const bool pin_ll = is_pinned_ptr(loglik) || is_device_ptr(loglik);
+  const bool pin_st = is_pinned_ptr(status) || is_device_ptr(status);
+  DYB_CUDA(h->h_out.reserve((sizeof(double) + sizeof(int)) * N + 16));
+  double* ll_stage = h->h_out.as<double>();
+  int* st_stage = reinterpret_cast<int*>(ll_stage + N);
+  DYB_CUDA(cudaMemcpyAsync(pin_ll ? (void*)loglik : (void*)ll_stage, h->d_ll.p, sizeof(double) * N, cudaMemcpyDefault, h->stream));
+  DYB_CUDA(cudaMemcpyAsync(pin_st ? (void*)status : (void*)st_stage, h->d_st2.p, sizeof(int) * N, cudaMemcpyDefault, h->stream));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  if (!pin_ll) std::memcpy(loglik, ll_stage, sizeof(double) * N);
+  if (!pin_st) std::memcpy(status, st_stage, sizeof(int) * N);
+  return DYB_OK;
+}
+
+int dyb_sync(dyb_handle* h) {
+  if (!h) return fail(DYB_ERR_ARG, "null handle");
+  DYB_CUDA(cudaSetDevice(h->device));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  return DYB_OK;
+}
+
+int64_t dyb_kernel_launches(const dyb_handle* h) { return h ? h->launches : 0; }
+
+int dyb_last_kernel_ms(dyb_handle* h, float* solve_ms, float* filter_ms) {
+  if (!h) return fail(DYB_ERR_ARG, "null handle");
+  if (!h->ev_valid) return fail(DYB_ERR_STATE, "no likelihood batch has run");
+  DYB_CUDA(cudaSetDevice(h->device));
+  DYB_CUDA(cudaEventSynchronize(h->ev[2]));
+  float a = 0, b = 0;
+  DYB_CUDA(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+  DYB_CUDA(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+  if (solve_ms) *solve_ms = a;
+  if (filter_ms) *filter_ms = b;
+  return DYB_OK;
+}
+
+int dyb_first_order_batch(dyb_handle* h, const double* theta, int64_t n, double* g1, double* ybar,
+                          int32_t* cr_iters, int32_t* status) {
+  if (!h || n < 0 || (n > 0 && (!theta || !status))) return fail(DYB_ERR_ARG, "null argument");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  const dyb_model_dims& d = h->ops->dims;
+  int rc = reserve_batch(h, n);
+  if (rc) return rc;
+  Stager sg(h->stream);
+  const size_t N = (size_t)n;
+  const double* dth = sg.in(theta, (size_t)h->hs.np * N);
+  SolveOut so;
+  so.ss = h->d_ss.as<double>();
+  so.status = sg.out(status, N);
+  so.g1 = sg.out(g1, (size_t)d.n * (d.k + d.nx) * N);
+  so.ybar = sg.out(ybar, (size_t)d.n * N);
+  so.cr_iters = sg.out(cr_iters, N);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  if (so.g1) DYB_CUDA(cudaMemsetAsync(so.g1, 0, sizeof(double) * (size_t)d.n * (d.k + d.nx) * N, h->stream));
+  if (so.cr_iters) DYB_CUDA(cudaMemsetAsync(so.cr_iters, 0, sizeof(int) * N, h->stream));
+  DYB_CUDA(h->ops->solve(h->hs, dth, n, so, h->stream));
+  h->launches += 1;
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int dyb_state_space_batch(dyb_handle* h, const double* theta, int64_t n, double* T, double* RQR, double* P0,
+                          double* ybar_obs, double* H, int32_t* status) {
+  if (!h || n < 0 || (n > 0 && (!theta || !status))) return fail(DYB_ERR_ARG, "null argument");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  const dyb_model_dims& d = h->ops->dims;
+  int rc = reserve_batch(h, n);
+  if (rc) return rc;
+  Stager sg(h->stream);
+  const size_t N = (size_t)n, ns2 = (size_t)d.ns * d.ns;
+  const double* dth = sg.in(theta, (size_t)h->hs.np * N);
+  SolveOut so{h->d_ss.as<double>(), sg.out(status, N), nullptr, nullptr, nullptr};
+  double* dT = sg.out(T, ns2 * N);
+  double* dQ = sg.out(RQR, ns2 * N);
+  double* dP = sg.out(P0, ns2 * N);
+  double* dy = sg.out(ybar_obs, (size_t)d.ny * N);
+  double* dH = sg.out(H, (size_t)d.ny * d.ny * N);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  DYB_CUDA(cudaMemsetAsync(h->d_ss.p, 0, sizeof(double) * d.ss_doubles * N, h->stream));
+  DYB_CUDA(h->ops->solve(h->hs, dth, n, so, h->stream));
+  DYB_CUDA(h->ops->unpack(h->d_ss.as<double>(), n, dT, dQ, dP, dy, dH, h->stream));
+  h->launches += 2;
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t presample,
+                     const int32_t* z_idx, const double* Y, const double* T, const double* RQR,
+                     const double* P0, const double* a0, const double* H, int64_t n,
+                     double* loglik, int32_t* status) {
+  if (ns <= 0 || ny <= 0 || ny > 64 || ny > ns || nobs < 0 || presample < 0 || n < 0)
+    return fail(DYB_ERR_ARG, "bad sizes (need 0 < ny <= min(ns, 64))");
+  if (n == 0) return DYB_OK;
+  if (!z_idx || !Y || !T || !RQR || !P0 || !loglik || !status) return fail(DYB_ERR_ARG, "null argument");
+  DYB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = device_stream(device);
+  Stager sg(st);
+  const size_t N = (size_t)n, ns2 = (size_t)ns * ns;
+  KalmanGenericArgs g;
+  g.ns = ns; g.ny = ny; g.nobs = nobs; g.presample = presample;
+  g.z_idx = sg.in(z_idx, (size_t)ny);
+  g.Y = sg.in(Y, (size_t)ny * (nobs > 0 ? nobs : 1));
+  g.T = sg.in(T, ns2 * N);
+  g.RQR = sg.in(RQR, ns2 * N);
+  g.P0 = sg.in(P0, ns2 * N);
+  g.a0 = sg.in(a0, (size_t)ns * N);
+  g.H = sg.in(H, (size_t)ny * ny * N);
+  g.n_draws = n;
+  g.loglik = sg.out(loglik, N);
+  g.status = sg.out(status, N);
+  if (!is_device_ptr(z_idx)) for (int i = 0; i < ny; ++i) if (z_idx[i] < 0 || z_idx[i] >= ns) return fail(DYB_ERR_ARG, "z_idx out of range");
+  int dev_sms = 148, max_smem = 0;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const size_t small = sizeof(double) * ((size_t)ny * ns + (size_t)ny * ny + 2 * (size_t)ns + 2 * (size_t)ny + 32);
+  const size_t full = small + sizeof(double) * 2 * ns2;
+  size_t smem;
+  long long grid;
+  if (full + 1024 <= (size_t)max_smem) {
+    smem = full; g.scratch = nullptr;
+    grid = n;
+    if (grid > 65535LL * 16) grid = 65535LL * 16;
+  } else {
+    smem = small;
+    grid = (long long)dev_sms * 2 < n ? (long long)dev_sms * 2 : n;
+    g.scratch = sg.temp<double>(2 * ns2 * (size_t)grid);
+  }
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  if (smem > 48 * 1024) DYB_CUDA(cudaFuncSetAttribute(kalman_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kalman_generic_kernel<<<(unsigned)grid, 256, smem, st>>>(g);
+  DYB_CUDA(cudaGetLastError());
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+// ---- SMC -------------------------------------------------------------------------------------
+static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
+
+int dyb_smc_reweight(int device, const double* w, const double* loglh, double dphi, int64_t n,
+                     double* w_out, double* zhat, double* ess) {
+  if (n <= 0 || !w || !loglh || !w_out) return fail(DYB_ERR_ARG, "bad argument");
+  DYB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = device_stream(device);
+  Stager sg(st);
+  const size_t N = (size_t)n;
+  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
+  const double* dw = sg.in(w, N);
+  const double* dl = sg.in(loglh, N);
+  double* dwo = sg.out(w_out, N);
+  double* wt = sg.temp<double>(N);
+  double* bt = sg.temp<double>((size_t)nb);
+  double* scal = sg.temp<double>(2);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  smc_incweight_kernel<<<nblk(n, 256), 256, 0, st>>>(dw, dl, dphi, n, wt);
+  smc_block_sum_kernel<<<nblk(nb, 64), 64, 0, st>>>(wt, n, 0, bt);
+  smc_total_kernel<<<1, 32, 0, st>>>(bt, nb, scal);
+  smc_normalise_kernel<<<nblk(n, 256), 256, 0, st>>>(wt, scal, n, dwo);
+  smc_block_sum_kernel<<<nblk(nb, 64), 64, 0, st>>>(dwo, n, 1, bt);
+  smc_total_kernel<<<1, 32, 0, st>>>(bt, nb, scal + 1);
+  DYB_CUDA(cudaGetLastError());
+  double hs[2];
+  DYB_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  DYB_CUDA(sg.finish());
+  if (zhat) *zhat = hs[0];
+  if (ess) *ess = 1.0 / hs[1];
+  return DYB_OK;
+}
+
+static int resample_impl(int device, const double* w, const double* u, double u0, int systematic, int64_t n,
+                         int64_t* idx, int64_t* n_clamped) {
+  if (n <= 0 || !w || !idx || (!systematic && !u)) return fail(DYB_ERR_ARG, "bad argument");
+  DYB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = device_stream(device);
+  Stager sg(st);
+  const size_t N = (size_t)n;
+  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
+  const double* dw = sg.in(w, N);
+  const double* du = systematic ? nullptr : sg.in(u, N);
+  long long* didx = reinterpret_cast<long long*>(sg.out(idx, N));
+  double* cw = sg.temp<double>(N);
+  double* bt = sg.temp<double>((size_t)nb);
+  double* offs = sg.temp<double>((size_t)nb);
+  unsigned long long* dcl = sg.temp<unsigned long long>(1);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  DYB_CUDA(cudaMemsetAsync(dcl, 0, sizeof(unsigned long long), st));
+  smc_block_scan_kernel<<<nblk(nb, 64), 64, 0, st>>>(dw, n, cw, bt);
+  smc_offsets_kernel<<<1, 32, 0, st>>>(bt, nb, offs);
+  smc_add_offsets_kernel<<<nblk(n, 256), 256, 0, st>>>(cw, offs, n);
+  smc_search_kernel<<<nblk(n, 256), 256, 0, st>>>(cw, n, du, u0, systematic, 0, n, didx, dcl);
+  DYB_CUDA(cudaGetLastError());
+  unsigned long long hcl = 0;
+  DYB_CUDA(cudaMemcpyAsync(&hcl, dcl, sizeof(hcl), cudaMemcpyDeviceToHost, st));
+  DYB_CUDA(sg.finish());
+  if (n_clamped) *n_clamped = (int64_t)hcl;
+  return DYB_OK;
+}
+
+int dyb_smc_resample_multinomial(int device, const double* w, const double* u, int64_t n, int64_t* idx, int64_t* n_clamped) {
+  return resample_impl(device, w, u, 0.0, 0, n, idx, n_clamped);
+}
+int dyb_smc_resample_systematic(int device, const double* w, double u0, int64_t n, int64_t* idx, int64_t* n_clamped) {
+  return resample_impl(device, w, nullptr, u0, 1, n, idx, n_clamped);
+}
+
+int dyb_smc_moments(int device, const double* para, const double* w, int64_t n, int32_t np, double* mu, double* R) {
+  if (n <= 0 || np <= 0 || np > MAX_EST || !para || !w || !mu || !R) return fail(DYB_ERR_ARG, "bad argument");
+  DYB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = device_stream(device);
+  Stager sg(st);
+  const size_t N = (size_t)n;
+  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
+  const double* dp = sg.in(para, N * np);
+  const double* dw = sg.in(w, N);
+  double* dmu = sg.out(mu, (size_t)np);
+  double* dR = sg.out(R, (size_t)np * np);
+  double* part = sg.temp<double>((size_t)nb * np * np);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  smc_moment1_kernel<<<nblk(nb * np, 64), 64, 0, st>>>(dp, dw, n, np, part);
+  smc_reduce_partials_kernel<<<nblk(np, 64), 64, 0, st>>>(part, nb, np, dmu);
+  smc_moment2_kernel<<<nblk(nb * np * np, 64), 64, 0, st>>>(dp, dw, dmu, n, np, part);
+  smc_reduce_partials_kernel<<<nblk(np * np, 64), 64, 0, st>>>(part, nb, np * np, dR);
+  DYB_CUDA(cudaGetLastError());
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int dyb_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return fail(DYB_ERR_ARG, "bad argument");
+  DYB_CUDA(cudaMallocHost(ptr, (size_t)bytes));
+  return DYB_OK;
+}
+int dyb_host_free(void* ptr) {
+  if (!ptr) return DYB_OK;
+  DYB_CUDA(cudaFreeHost(ptr));
+  return DYB_OK;
+}
+
+}  // extern "C"

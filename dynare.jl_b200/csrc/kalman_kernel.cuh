@@ -1,0 +1,185 @@
+// Fused Kalman-filter log-likelihood, model-specialised: one thread per draw, the whole
+// T-step recursion in one launch, state (a, P) and the draw's transition data in registers.
+//
+// Replaces the reference's `kalman_likelihood(Y,Z,H,T,R,Q,a0,P,start,last,presample,ws[,data_pattern])`
+// call (src/estimation/estimation.jl:665-701; KalmanFilterTools 0.1.x, not vendored):
+//     v = y - Z a ; F = Z P Z' + H ; lik_t = log det F + v' F^-1 v ; K = P Z' F^-1
+//     a <- T (a + K v) ; P <- T (P - K Z P) T' + R Q R'
+//     loglik = -1/2 ( n_observed * log 2pi + sum_{t >= presample} lik_t )
+// Structure exploited (none of it changes the result beyond rounding):
+//   * Z is a selection (estimation.jl:644-646): Z a and Z P Z' are gathers;
+//   * T has non-zero columns only at the K lagged states (estimation.jl:648-649): the time update
+//     only needs the updated mean / covariance on those K states:  a <- Tl a_l,  P <- Tl P_ll Tl' + RQR';
+//   * P is symmetric: packed lower storage, half of the products.
+//   * the observations (and therefore the missing-data pattern) are shared by every draw, so the
+//     `data_pattern` variant costs no divergence: a missing row i gets v_i = 0, F_ii = 1, F_ij = 0 and
+//     a zero column in P Z', which removes it from the likelihood and from the update exactly.
+#pragma once
+#include "model_traits.cuh"
+#include "solve_kernel.cuh"
+
+namespace dyb {
+
+template <class M>
+__global__ void __launch_bounds__(128)
+kalman_kernel(const double* __restrict__ ss, long long n_draws,
+              const double* __restrict__ Y,            // NY x nobs, column-major, NaN = missing
+              int nobs, int presample,
+              const int* __restrict__ status_in,
+              double* __restrict__ loglik, int* __restrict__ status_out) {
+  constexpr int NS = M::NS, K = M::K, NY = M::NY;
+  using L = SSLayout<M>;
+  extern __shared__ double ysh[];                      // NY * nobs
+  for (int i = threadIdx.x; i < NY * nobs; i += blockDim.x) ysh[i] = Y[i];
+  __syncthreads();
+
+  const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_draws) return;
+  if (status_in[d] != ST_OK) {
+    loglik[d] = -INFINITY;
+    status_out[d] = status_in[d];
+    return;
+  }
+  const double* s_ = ss + d;
+  const long long st = n_draws;
+
+  double Tl[NS * K];                      // row-major
+  double QQ[NS * (NS + 1) / 2];
+  double P[NS * (NS + 1) / 2];
+  double a[NS];
+  double yb[NY];
+  double H[NY * (NY + 1) / 2];
+#pragma unroll
+  for (int i = 0; i < NS * K; ++i) Tl[i] = s_[(L::OFF_T + i) * st];
+#pragma unroll
+  for (int i = 0; i < NS * (NS + 1) / 2; ++i) { QQ[i] = s_[(L::OFF_QQ + i) * st]; P[i] = s_[(L::OFF_P0 + i) * st]; }
+#pragma unroll
+  for (int i = 0; i < NY; ++i) yb[i] = s_[(L::OFF_YB + i) * st];
+#pragma unroll
+  for (int i = 0; i < NY * (NY + 1) / 2; ++i) H[i] = s_[(L::OFF_H + i) * st];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) a[i] = 0.0;
+
+  double acc = 0.0;
+  int nseen = 0;
+  bool bad = false;
+
+  for (int t = 0; t < nobs; ++t) {
+    // ---- measurement update ----------------------------------------------------------------
+    double v[NY], F[NY * (NY + 1) / 2];
+    bool miss[NY];
+    int nobs_t = 0;
+#pragma unroll
+    for (int i = 0; i < NY; ++i) {
+      const double yi = ysh[i + NY * t];
+      miss[i] = isnan(yi);
+      nobs_t += miss[i] ? 0 : 1;
+      v[i] = miss[i] ? 0.0 : (yi - yb[i] - a[M::obs_idx_state(i)]);
+    }
+#pragma unroll
+    for (int i = 0; i < NY; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        double f = P[sym(M::obs_idx_state(i), M::obs_idx_state(j))] + H[tri(i, j)];
+        if (miss[i] || miss[j]) f = (i == j) ? 1.0 : 0.0;
+        F[tri(i, j)] = f;
+      }
+    // Cholesky F = L L' in place (packed lower); rdiag = 1 / L_ii
+    double rdiag[NY];
+    double det = 1.0;
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+      double djj = F[tri(j, j)];
+#pragma unroll
+      for (int q = 0; q < j; ++q) djj = fma(-F[tri(j, q)], F[tri(j, q)], djj);
+      if (!(djj > 0.0)) bad = true;
+      det *= djj;
+      const double ljj = sqrt(djj);
+      const double r = 1.0 / ljj;
+      rdiag[j] = r;
+      F[tri(j, j)] = ljj;
+#pragma unroll
+      for (int i = j + 1; i < NY; ++i) {
+        double x = F[tri(i, j)];
+#pragma unroll
+        for (int q = 0; q < j; ++q) x = fma(-F[tri(i, q)], F[tri(j, q)], x);
+        F[tri(i, j)] = x * r;
+      }
+    }
+    // w = L^-1 v
+    double w[NY];
+    double quad = 0.0;
+#pragma unroll
+    for (int i = 0; i < NY; ++i) {
+      double x = v[i];
+#pragma unroll
+      for (int q = 0; q < i; ++q) x = fma(-F[tri(i, q)], w[q], x);
+      w[i] = x * rdiag[i];
+      quad = fma(w[i], w[i], quad);
+    }
+    if (t >= presample) { acc += log(det) + quad; nseen += nobs_t; }
+    if (t == nobs - 1) break;
+
+    // U = L^-1 (Z P)[:, lagged]   (NY x K)
+    double U[NY * K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+#pragma unroll
+      for (int i = 0; i < NY; ++i) {
+        double x = miss[i] ? 0.0 : P[sym(M::obs_idx_state(i), M::lagged_state_ids(j))];
+#pragma unroll
+        for (int q = 0; q < i; ++q) x = fma(-F[tri(i, q)], U[q + NY * j], x);
+        U[i + NY * j] = x * rdiag[i];
+      }
+    }
+    // updated mean / covariance on the lagged states only
+    double al[K], Pll[K * (K + 1) / 2];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      double x = a[M::lagged_state_ids(j)];
+#pragma unroll
+      for (int i = 0; i < NY; ++i) x = fma(U[i + NY * j], w[i], x);
+      al[j] = x;
+#pragma unroll
+      for (int q = 0; q <= j; ++q) {
+        double pjq = P[sym(M::lagged_state_ids(j), M::lagged_state_ids(q))];
+#pragma unroll
+        for (int i = 0; i < NY; ++i) pjq = fma(-U[i + NY * j], U[i + NY * q], pjq);
+        Pll[tri(j, q)] = pjq;
+      }
+    }
+    // ---- time update ---------------------------------------------------------------------------
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      double x = 0.0;
+      double mrow[K];                                    // row s of Tl * Pll
+#pragma unroll
+      for (int j = 0; j < K; ++j) x = fma(Tl[s * K + j], al[j], x);
+      a[s] = x;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        double m = 0.0;
+#pragma unroll
+        for (int q = 0; q < K; ++q) m = fma(Tl[s * K + q], Pll[sym(q, j)], m);
+        mrow[j] = m;
+      }
+#pragma unroll
+      for (int t2 = 0; t2 <= s; ++t2) {
+        double x2 = QQ[tri(s, t2)];
+#pragma unroll
+        for (int j = 0; j < K; ++j) x2 = fma(mrow[j], Tl[t2 * K + j], x2);
+        P[tri(s, t2)] = x2;
+      }
+    }
+  }
+  const double ll = -0.5 * (nseen * 1.8378770664093453 + acc);     // log(2 pi)
+  if (bad || !isfinite(ll)) {
+    loglik[d] = -INFINITY;
+    status_out[d] = ST_F_NOT_PD;
+  } else {
+    loglik[d] = ll;
+    status_out[d] = ST_OK;
+  }
+}
+
+}  // namespace dyb

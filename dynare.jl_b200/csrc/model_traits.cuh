@@ -1,0 +1,35 @@
+// Common definitions for generated model headers and the kernels that consume them.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define DYB_HD __host__ __device__ __forceinline__
+#define DYB_D __device__ __forceinline__
+#else
+#define DYB_HD inline
+#define DYB_D inline
+#endif
+
+namespace dyb {
+
+// estimated-parameter kinds (reference src/dynare_containers.jl:16 `EstimatedParameterType`,
+// scattered by set_estimated_parameters!, src/estimation/estimation.jl:517-601)
+enum EstKind : int {
+  EST_PARAM = 0, EST_SD_SHOCK = 1, EST_VAR_SHOCK = 2, EST_CORR_SHOCK = 3,
+  EST_SD_MEAS = 4, EST_VAR_MEAS = 5, EST_CORR_MEAS = 6
+};
+
+// per-draw status (include/dynare_b200.h DYB_ST_*)
+enum DrawStatus : int {
+  ST_OK = 0, ST_STEADY = 1, ST_INDETERMINATE = 2, ST_UNSTABLE = 3, ST_SOLVER = 4,
+  ST_NONSTATIONARY = 5, ST_F_NOT_PD = 6
+};
+
+constexpr int MAX_EST = 64;
+
+DYB_HD constexpr int tri(int i, int j) {            // packed lower-triangular index, i >= j
+  return i * (i + 1) / 2 + j;
+}
+DYB_HD constexpr int sym(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
+
+}  // namespace dyb

@@ -1,0 +1,93 @@
+// Included by each generated model translation unit after its model header:
+//   #include "generated/model_<name>.cuh"
+//   #define DYB_MODEL dyb::Model_<name>
+//   #include "model_tu.cuh"
+// Instantiates the solve / filter kernels for the model and registers its launchers.
+#include "registry.h"
+#include "solve_kernel.cuh"
+#include "kalman_kernel.cuh"
+
+namespace dyb {
+namespace {
+
+using MT = DYB_MODEL;
+
+void mt_defaults(HostState& hs) {
+  hs.params.resize(MT::NPAR);
+  for (int i = 0; i < MT::NPAR; ++i) hs.params[i] = MT::param0(i);
+  hs.sigma_e.resize(MT::NX * MT::NX);
+  for (int i = 0; i < MT::NX * MT::NX; ++i) hs.sigma_e[i] = MT::sigma_e0(i);
+  hs.sigma_m.resize(MT::NY * MT::NY);
+  for (int i = 0; i < MT::NY * MT::NY; ++i) hs.sigma_m[i] = MT::sigma_m0(i);
+  hs.np = MT::NP_DEFAULT;
+  for (int i = 0; i < MT::NP_DEFAULT && i < MAX_EST; ++i) {
+    hs.est_type[i] = MT::est_type0(i); hs.est_i[i] = MT::est_i0(i); hs.est_j[i] = MT::est_j0(i);
+  }
+}
+
+cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, SolveOut out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  SolveParams<MT> prm;
+  for (int i = 0; i < MT::NPAR; ++i) prm.params0[i] = hs.params[i];
+  for (int i = 0; i < MT::NX * MT::NX; ++i) prm.sigma_e0[i] = hs.sigma_e[i];
+  for (int i = 0; i < MT::NY * MT::NY; ++i) prm.sigma_m0[i] = hs.sigma_m[i];
+  prm.np = hs.np;
+  for (int i = 0; i < MAX_EST; ++i) { prm.est_type[i] = hs.est_type[i]; prm.est_i[i] = hs.est_i[i]; prm.est_j[i] = hs.est_j[i]; }
+  prm.cr_tol = hs.opt.cr_tol; prm.cr_maxit = hs.opt.cr_maxit; prm.steady_tol = hs.opt.steady_tol;
+  prm.lyap_tol = hs.opt.lyap_tol; prm.lyap_maxit = hs.opt.lyap_maxit;
+  SolveExtra ex{out.g1, out.ybar, out.cr_iters};
+  const int block = 128;
+  const long long grid = (n + block - 1) / block;
+  solve_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.ss, out.status, ex);
+  return cudaGetLastError();
+}
+
+cudaError_t mt_kalman(const double* d_ss, long long n, const double* d_Y, int nobs, int presample,
+                      const int* d_status_in, double* d_loglik, int* d_status_out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int block = 128;
+  const long long grid = (n + block - 1) / block;
+  const size_t smem = sizeof(double) * (size_t)MT::NY * (size_t)nobs;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kalman_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kalman_kernel<MT><<<(unsigned)grid, block, smem, st>>>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out);
+  return cudaGetLastError();
+}
+
+__global__ void mt_unpack_kernel(const double* __restrict__ ss, long long n, double* T, double* RQR, double* P0,
+                                 double* yb, double* H) {
+  using L = SSLayout<MT>;
+  constexpr int NS = MT::NS, K = MT::K, NY = MT::NY;
+  const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n) return;
+  const double* s = ss + d;
+  if (T) {
+    double* t = T + d * NS * NS;
+    for (int i = 0; i < NS * NS; ++i) t[i] = 0.0;
+    for (int r = 0; r < NS; ++r) for (int j = 0; j < K; ++j) t[r + NS * MT::lagged_state_ids(j)] = s[(L::OFF_T + r * K + j) * n];
+  }
+  if (RQR) for (int r = 0; r < NS; ++r) for (int c = 0; c < NS; ++c) RQR[d * NS * NS + r + NS * c] = s[(L::OFF_QQ + sym(r, c)) * n];
+  if (P0) for (int r = 0; r < NS; ++r) for (int c = 0; c < NS; ++c) P0[d * NS * NS + r + NS * c] = s[(L::OFF_P0 + sym(r, c)) * n];
+  if (yb) for (int i = 0; i < NY; ++i) yb[d * NY + i] = s[(L::OFF_YB + i) * n];
+  if (H) for (int r = 0; r < NY; ++r) for (int c = 0; c < NY; ++c) H[d * NY * NY + r + NY * c] = s[(L::OFF_H + sym(r, c)) * n];
+}
+
+cudaError_t mt_unpack(const double* d_ss, long long n, double* T, double* RQR, double* P0, double* yb, double* H, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int block = 128;
+  mt_unpack_kernel<<<(unsigned)((n + block - 1) / block), block, 0, st>>>(d_ss, n, T, RQR, P0, yb, H);
+  return cudaGetLastError();
+}
+
+const ModelOps mt_ops = {
+  MT::name,
+  {MT::N, MT::NX, MT::NPAR, MT::K, MT::NF, MT::S, MT::NCOL, MT::NS, MT::NY, MT::NP_DEFAULT, SSLayout<MT>::SIZE},
+  mt_defaults, mt_solve, mt_kalman, mt_unpack
+};
+
+struct Registrar { Registrar() { register_model(&mt_ops); } } mt_registrar;
+
+}  // namespace
+}  // namespace dyb

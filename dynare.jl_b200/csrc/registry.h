@@ -1,0 +1,42 @@
+// Host-side registry of compiled models: one ModelOps per generated model header.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+#include "../../include/dynare_b200.h"
+#include "model_traits.cuh"
+
+namespace dyb {
+
+// everything the solve kernel needs from the host besides theta
+struct HostState {
+  std::vector<double> params, sigma_e, sigma_m;
+  int np = 0;
+  int est_type[MAX_EST], est_i[MAX_EST], est_j[MAX_EST];
+  dyb_options opt;
+};
+
+struct SolveOut {
+  double* ss;        // SoA hand-off buffer, ss_doubles x N
+  int* status;
+  double* g1;        // optional AoS outputs (device), may be null
+  double* ybar;
+  int* cr_iters;
+};
+
+struct ModelOps {
+  const char* name;
+  dyb_model_dims dims;
+  void (*defaults)(HostState&);
+  cudaError_t (*solve)(const HostState&, const double* d_theta, long long n, SolveOut out, cudaStream_t);
+  cudaError_t (*kalman)(const double* d_ss, long long n, const double* d_Y, int nobs, int presample,
+                        const int* d_status_in, double* d_loglik, int* d_status_out, cudaStream_t);
+  // expand the SoA hand-off buffer into dense per-draw matrices (any output may be null)
+  cudaError_t (*unpack)(const double* d_ss, long long n, double* T, double* RQR, double* P0,
+                        double* ybar_obs, double* H, cudaStream_t);
+};
+
+const std::vector<const ModelOps*>& registry();
+void register_model(const ModelOps*);
+
+}  // namespace dyb

@@ -1,0 +1,154 @@
+// SMC particle-weight primitives on device (reference src/estimation/smc.jl:118-167, 340-361).
+//
+// Every sum over particles uses ONE canonical association order, independent of launch geometry and
+// of how particles are sharded over GPUs:  sequential fp64 sum inside each block of SMC_BLOCK = 1024
+// consecutive particles, then a sequential sum over block totals.  The cumulative weight used for
+// resampling is  cw[b*1024 + i] = offset_b + local_b[i]  with local_b the sequential inclusive scan
+// of block b and offset_b the sequential sum of the previous block totals.  The CPU oracle
+// (oracle/smc.py) uses the same order, which is what makes resampling indices bit-exact.
+#pragma once
+#include "model_traits.cuh"
+
+namespace dyb {
+
+constexpr int SMC_BLOCK = 1024;
+
+// phase 1 of reweight: wt[i] = w[i] * exp(dphi * loglh[i]); block totals of wt (canonical order)
+__global__ void smc_incweight_kernel(const double* __restrict__ w, const double* __restrict__ loglh,
+                                     double dphi, long long n, double* __restrict__ wt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) wt[i] = w[i] * exp(dphi * loglh[i]);
+}
+
+// sequential sum of f(x) inside each 1024-block: one thread per block. mode 0: x ; 1: x*x
+__global__ void smc_block_sum_kernel(const double* __restrict__ x, long long n, int mode,
+                                     double* __restrict__ block_tot) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
+  if (b >= nb) return;
+  const long long lo = b * SMC_BLOCK;
+  const long long hi = (lo + SMC_BLOCK < n) ? lo + SMC_BLOCK : n;
+  double s = 0.0;
+  if (mode == 0) for (long long i = lo; i < hi; ++i) s += x[i];
+  else for (long long i = lo; i < hi; ++i) s = __dadd_rn(s, __dmul_rn(x[i], x[i]));   // no FMA contraction: same bits as the CPU order
+  block_tot[b] = s;
+}
+
+// sequential sum over block totals (single thread); out[0] = total
+__global__ void smc_total_kernel(const double* __restrict__ block_tot, long long nb, double* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (long long b = 0; b < nb; ++b) s += block_tot[b];
+    out[0] = s;
+  }
+}
+
+// w_out = wt / zhat
+__global__ void smc_normalise_kernel(const double* __restrict__ wt, const double* __restrict__ zhat,
+                                     long long n, double* __restrict__ w_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w_out[i] = wt[i] / zhat[0];
+}
+
+// local inclusive scan inside each 1024-block (one thread per block) + block totals
+__global__ void smc_block_scan_kernel(const double* __restrict__ w, long long n,
+                                      double* __restrict__ local, double* __restrict__ block_tot) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
+  if (b >= nb) return;
+  const long long lo = b * SMC_BLOCK;
+  const long long hi = (lo + SMC_BLOCK < n) ? lo + SMC_BLOCK : n;
+  double s = 0.0;
+  for (long long i = lo; i < hi; ++i) { s += w[i]; local[i] = s; }
+  block_tot[b] = s;
+}
+
+// exclusive sequential scan of block totals (single thread): offs[b] = sum_{b' < b} tot[b']
+__global__ void smc_offsets_kernel(const double* __restrict__ block_tot, long long nb, double* __restrict__ offs) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (long long b = 0; b < nb; ++b) { offs[b] = s; s += block_tot[b]; }
+  }
+}
+
+__global__ void smc_add_offsets_kernel(double* __restrict__ cw, const double* __restrict__ offs, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cw[i] = offs[i / SMC_BLOCK] + cw[i];
+}
+
+// idx[i] = #{ j : cw[j] <= u_i }  (= first j with u_i < cw[j], 0-based), clamped to n-1.
+// systematic != 0: u_i = (i + u0) / n, else u_i = u[i].  Output rows [lo, hi).
+__global__ void smc_search_kernel(const double* __restrict__ cw, long long n,
+                                  const double* __restrict__ u, double u0, int systematic,
+                                  long long lo, long long hi,
+                                  long long* __restrict__ idx, unsigned long long* __restrict__ n_clamped) {
+  const long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  const double ui = systematic ? ((double)i + u0) / (double)n : u[i];
+  long long a = 0, b = n;                 // first position with cw[pos] > ui
+  while (a < b) {
+    const long long mid = (a + b) >> 1;
+    if (cw[mid] <= ui) a = mid + 1; else b = mid;
+  }
+  if (a >= n) { a = n - 1; atomicAdd(n_clamped, 1ULL); }
+  idx[i - lo] = a;
+}
+
+// weighted first moment: partial[b*np + p] = sum_{i in block b} w[i] * para[p + np*i]  (sequential)
+__global__ void smc_moment1_kernel(const double* __restrict__ para, const double* __restrict__ w,
+                                   long long n, int np, double* __restrict__ partial) {
+  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nb * np) return;
+  const long long b = e / np;
+  const int p = (int)(e % np);
+  const long long lo = b * SMC_BLOCK;
+  const long long hi = (lo + SMC_BLOCK < n) ? lo + SMC_BLOCK : n;
+  double s = 0.0;
+  for (long long i = lo; i < hi; ++i) s = __dadd_rn(s, __dmul_rn(w[i], para[p + (long long)np * i]));
+  partial[e] = s;
+}
+
+// weighted second central moment: partial[b*np*np + p + np*q] = sum_i w_i (x_ip - mu_p)(x_iq - mu_q)
+__global__ void smc_moment2_kernel(const double* __restrict__ para, const double* __restrict__ w,
+                                   const double* __restrict__ mu, long long n, int np,
+                                   double* __restrict__ partial) {
+  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int np2 = np * np;
+  if (e >= nb * np2) return;
+  const long long b = e / np2;
+  const int pq = (int)(e % np2);
+  const int p = pq % np, q = pq / np;
+  const long long lo = b * SMC_BLOCK;
+  const long long hi = (lo + SMC_BLOCK < n) ? lo + SMC_BLOCK : n;
+  const double mp = mu[p], mq = mu[q];
+  double s = 0.0;
+  for (long long i = lo; i < hi; ++i) {
+    const double* x = para + (long long)np * i;
+    s = __dadd_rn(s, __dmul_rn(__dmul_rn(w[i], x[p] - mp), x[q] - mq));
+  }
+  partial[e] = s;
+}
+
+// out[c] = sequential sum over blocks of partial[b*ncomp + c]
+__global__ void smc_reduce_partials_kernel(const double* __restrict__ partial, long long nb, int ncomp,
+                                           double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncomp) return;
+  double s = 0.0;
+  for (long long b = 0; b < nb; ++b) s += partial[b * ncomp + c];
+  out[c] = s;
+}
+
+// gather particle payload rows: dst[:, i] = src[:, idx[i]]  (ncomp doubles per particle)
+__global__ void smc_gather_kernel(const double* __restrict__ src, const long long* __restrict__ idx,
+                                  long long n_out, int ncomp, double* __restrict__ dst) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_out * ncomp) return;
+  const long long i = e / ncomp;
+  const int c = (int)(e % ncomp);
+  dst[e] = src[idx[i] * ncomp + c];
+}
+
+}  // namespace dyb

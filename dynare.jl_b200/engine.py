@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's per-draw likelihood interface, batched.
+
+Reference interface                                   -> here
+  SSWs(context, observations, varobs)                 -> BatchSSWs(model, observations)
+     (src/estimation/estimation.jl:358-429)
+  loglikelihood(theta, context, observations, ssws)   -> BatchSSWs.loglikelihood(Theta)  (N draws at once)
+     (src/estimation/estimation.jl:603-702)
+  DSGELogPosteriorDensity (callable, -Inf on failure) -> DSGELogPosteriorDensity(ssws, priors)(Theta)
+     (src/estimation/estimation.jl:439-453, 503-515)
+  LRE.first_order_solver! results g1_1 / g1_2         -> BatchSSWs.first_order(Theta)
+     (src/perturbations.jl:663-664)
+
+``Theta`` is an ``(N, np)`` C-contiguous float64 array, i.e. the ``np x N`` column-major matrix of the
+C ABI.  Everything is computed by libdynare_b200.so on the GPU; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import PACKAGE_DIR
+from . import _lib as L
+from .priors import PriorSet
+
+STATUS_NAMES = {0: "ok", 1: "steady_state", 2: "indeterminate", 3: "unstable", 4: "solver",
+                5: "nonstationary", 6: "F_not_pd"}
+
+
+def available_models():
+    lib = L.load()
+    return [lib.dyb_model_name(i).decode() for i in range(lib.dyb_model_count())]
+
+
+def model_description(name: str) -> dict:
+    """Plain-data description written by the model set-up (names, index sets, priors, defaults)."""
+    with open(os.path.join(PACKAGE_DIR, "models", f"{name}.json")) as f:
+        return json.load(f)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+class PinnedArray:
+    """A numpy view of page-locked host memory obtained from ``dyb_host_alloc``."""
+
+    def __init__(self, shape, dtype=np.float64):
+        lib = L.load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        L.check(lib.dyb_host_alloc(C.byref(p), max(self.nbytes, 8)))
+        self._ptr = p
+        buf = (C.c_char * max(self.nbytes, 8)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._ptr is not None:
+            self.array = None
+            L.load().dyb_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class BatchSSWs:
+    """State-space workspace of a compiled model on one GPU (the batched ``SSWs``)."""
+
+    def __init__(self, model: str, observations: Optional[np.ndarray] = None, device: int = 0):
+        self.lib = L.load()
+        self.model = model
+        self.device = device
+        h = C.c_void_p()
+        L.check(self.lib.dyb_create(model.encode(), device, C.byref(h)))
+        self._h = h
+        d = L.ModelDims()
+        L.check(self.lib.dyb_get_dims(self._h, C.byref(d)))
+        self.dims = d.asdict()
+        self.np = self.dims["np_default"]
+        self.nobs = 0
+        if observations is not None:
+            self.set_observations(observations)
+
+    # -- configuration --------------------------------------------------------------------------
+    def set_observations(self, Y):
+        """Y: ny x nobs (rows in varobs order), NaN = missing."""
+        Y = np.asarray(Y, dtype=np.float64)
+        if Y.ndim != 2 or Y.shape[0] != self.dims["ny"]:
+            raise ValueError(f"observations must be ny x nobs with ny = {self.dims['ny']}")
+        Yf = np.asfortranarray(Y)
+        L.check(self.lib.dyb_set_observations(self._h, L.ptr(Yf), Y.shape[0], Y.shape[1]))
+        self.nobs = Y.shape[1]
+
+    def set_calibration(self, params=None, sigma_e=None, sigma_m=None):
+        d = self.dims
+        p = None if params is None else _f64(params, (d["npar"],))
+        se = None if sigma_e is None else np.asfortranarray(_f64(sigma_e, (d["nx"], d["nx"])))
+        sm = None if sigma_m is None else np.asfortranarray(_f64(sigma_m, (d["ny"], d["ny"])))
+        L.check(self.lib.dyb_set_calibration(self._h, L.ptr(p), L.ptr(se), L.ptr(sm)))
+
+    def set_estimated_params(self, kinds, index1, index2):
+        k = np.ascontiguousarray(kinds, dtype=np.int32)
+        i = np.ascontiguousarray(index1, dtype=np.int32)
+        j = np.ascontiguousarray(index2, dtype=np.int32)
+        if not (k.shape == i.shape == j.shape and k.ndim == 1):
+            raise ValueError("kinds / index1 / index2 must be 1-d arrays of equal length")
+        L.check(self.lib.dyb_set_estimated_params(self._h, k.size, L.ptr(k), L.ptr(i), L.ptr(j)))
+        self.np = int(k.size)
+
+    def options(self) -> L.Options:
+        o = L.Options()
+        L.check(self.lib.dyb_get_options(self._h, C.byref(o)))
+        return o
+
+    def set_options(self, **kw):
+        o = self.options()
+        for k, v in kw.items():
+            if not hasattr(o, k):
+                raise KeyError(k)
+            setattr(o, k, v)
+        L.check(self.lib.dyb_set_options(self._h, C.byref(o)))
+
+    # -- the hot path -------------------------------------------------------------------------------
+    def _theta(self, Theta):
+        Theta = np.asarray(Theta, dtype=np.float64)
+        if Theta.ndim == 1:
+            Theta = Theta[None, :]
+        if Theta.ndim != 2 or Theta.shape[1] != self.np:
+            raise ValueError(f"Theta must be (N, {self.np})")
+        return np.ascontiguousarray(Theta)
+
+    def loglikelihood(self, Theta, out=None, status=None):
+        """Log-likelihood of N draws: returns (loglik[N], status[N]); loglik = -inf where status != 0."""
+        Theta = self._theta(Theta)
+        n = Theta.shape[0]
+        ll = np.empty(n, dtype=np.float64) if out is None else out
+        st = np.empty(n, dtype=np.int32) if status is None else status
+        L.check(self.lib.dyb_loglik_batch(self._h, L.ptr(Theta), n, L.ptr(ll), L.ptr(st)))
+        return ll, st
+
+    def loglikelihood_device(self, d_theta: int, n: int, d_loglik: int, d_status: int):
+        """Device-pointer variant (addresses as ints); asynchronous, call ``sync()``."""
+        L.check(self.lib.dyb_loglik_batch_device(self._h, L.ptr(d_theta), n, L.ptr(d_loglik), L.ptr(d_status)))
+
+    def sync(self):
+        L.check(self.lib.dyb_sync(self._h))
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.dyb_kernel_launches(self._h))
+
+    def last_kernel_ms(self):
+        a, b = C.c_float(), C.c_float()
+        L.check(self.lib.dyb_last_kernel_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # -- stage-level ----------------------------------------------------------------------------------
+    def first_order(self, Theta):
+        """Returns dict(g1_1 (N,n,k), g1_2 (N,n,nx), ybar (N,n), cr_iters (N,), status (N,))."""
+        Theta = self._theta(Theta)
+        n = Theta.shape[0]
+        d = self.dims
+        g1 = np.zeros((n, d["k"] + d["nx"], d["n"]))          # per draw column-major n x (k+nx)
+        yb = np.zeros((n, d["n"]))
+        it = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        L.check(self.lib.dyb_first_order_batch(self._h, L.ptr(Theta), n, L.ptr(g1), L.ptr(yb), L.ptr(it), L.ptr(st)))
+        g1 = g1.transpose(0, 2, 1)
+        return dict(g1_1=g1[:, :, :d["k"]], g1_2=g1[:, :, d["k"]:], ybar=yb, cr_iters=it, status=st)
+
+    def state_space(self, Theta):
+        """Returns dict(T, RQR, P0 (N,ns,ns), ybar_obs (N,ny), H (N,ny,ny), status)."""
+        Theta = self._theta(Theta)
+        n = Theta.shape[0]
+        ns, ny = self.dims["ns"], self.dims["ny"]
+        T = np.zeros((n, ns, ns)); Q = np.zeros((n, ns, ns)); P = np.zeros((n, ns, ns))
+        yb = np.zeros((n, ny)); H = np.zeros((n, ny, ny)); st = np.zeros(n, dtype=np.int32)
+        L.check(self.lib.dyb_state_space_batch(self._h, L.ptr(Theta), n, L.ptr(T), L.ptr(Q), L.ptr(P),
+                                               L.ptr(yb), L.ptr(H), L.ptr(st)))
+        tr = lambda a: a.transpose(0, 2, 1)                  # column-major per draw -> numpy row-major
+        return dict(T=tr(T), RQR=tr(Q), P0=tr(P), ybar_obs=yb, H=tr(H), status=st)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.dyb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DSGELogPosteriorDensity:
+    """Batched analogue of the reference callable (estimation.jl:439-453, 503-515):
+    ``logprior(theta) + loglikelihood(theta)``, ``-inf`` for any failed draw."""
+
+    def __init__(self, ssws: BatchSSWs, priors: PriorSet):
+        if len(priors) != ssws.np:
+            raise ValueError("one prior per estimated parameter is required")
+        self.ssws = ssws
+        self.priors = priors
+
+    def dimension(self):
+        return self.ssws.np
+
+    def __call__(self, Theta):
+        Theta = self.ssws._theta(Theta)
+        ll, st = self.ssws.loglikelihood(Theta)
+        lp = self.priors.logpriordensity(Theta)
+        out = lp + ll
+        out[(st != 0) | ~np.isfinite(out)] = -np.inf
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# model-free entry points
+# ---------------------------------------------------------------------------------------------------
+def kalman_batch(Y, z_idx, T, RQR, P0, a0=None, H=None, presample=0, device=0):
+    """Generic batched Kalman log-likelihood.  T, RQR, P0: (N, ns, ns) numpy (row-major per draw);
+    Y: ny x nobs; z_idx: state observed by each row.  Returns (loglik[N], status[N])."""
+    lib = L.load()
+    T = np.asarray(T, dtype=np.float64)
+    n, ns, _ = T.shape
+    Y = np.asarray(Y, dtype=np.float64)
+    ny, nobs = Y.shape
+    cm = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).transpose(0, 2, 1))
+    Tc, Qc, Pc = cm(T), cm(RQR), cm(P0)
+    Hc = None if H is None else cm(H)
+    a0c = None if a0 is None else _f64(a0, (n, ns))
+    z = np.ascontiguousarray(z_idx, dtype=np.int32)
+    Yf = np.asfortranarray(Y)
+    ll = np.empty(n); st = np.empty(n, dtype=np.int32)
+    L.check(lib.dyb_kalman_batch(device, ns, ny, nobs, presample, L.ptr(z), L.ptr(Yf), L.ptr(Tc), L.ptr(Qc),
+                                 L.ptr(Pc), L.ptr(a0c), L.ptr(Hc), n, L.ptr(ll), L.ptr(st)))
+    return ll, st
+
+
+def smc_reweight(w, loglh, dphi, device=0):
+    lib = L.load()
+    w = _f64(w); loglh = _f64(loglh)
+    out = np.empty_like(w)
+    z, e = C.c_double(), C.c_double()
+    L.check(lib.dyb_smc_reweight(device, L.ptr(w), L.ptr(loglh), float(dphi), w.size, L.ptr(out), C.byref(z), C.byref(e)))
+    return out, z.value, e.value
+
+
+def smc_resample_multinomial(w, u, device=0):
+    lib = L.load()
+    w = _f64(w); u = _f64(u)
+    idx = np.empty(w.size, dtype=np.int64)
+    nc = C.c_int64()
+    L.check(lib.dyb_smc_resample_multinomial(device, L.ptr(w), L.ptr(u), w.size, L.ptr(idx), C.byref(nc)))
+    return idx, nc.value
+
+
+def smc_resample_systematic(w, u0, device=0):
+    lib = L.load()
+    w = _f64(w)
+    idx = np.empty(w.size, dtype=np.int64)
+    nc = C.c_int64()
+    L.check(lib.dyb_smc_resample_systematic(device, L.ptr(w), float(u0), w.size, L.ptr(idx), C.byref(nc)))
+    return idx, nc.value
+
+
+def smc_moments(para, w, device=0):
+    lib = L.load()
+    para = _f64(para); w = _f64(w)
+    n, np_ = para.shape
+    mu = np.empty(np_); R = np.empty((np_, np_))
+    L.check(lib.dyb_smc_moments(device, L.ptr(para), L.ptr(w), n, np_, L.ptr(mu), L.ptr(R)))
+    return mu, R.T.copy()      # library writes column-major

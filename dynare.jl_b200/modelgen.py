@@ -492,6 +492,27 @@ def emit_cuda(spec: ModelSpec) -> str:
     arr("lagged_state_ids", S.lagged_state_ids)
     # position of each lagged state inside i_bkwrd_b (column of g1_1)
     arr("lagged_in_bkwrd", [S.i_bkwrd_b.index(S.state_ids[p]) for p in S.lagged_state_ids])
+    # variable -> (is static, position inside i_static / i_dyn)
+    pos_in_static = {v: i for i, v in enumerate(S.i_static)}
+    arr("var_static", [1 if v in pos_in_static else 0 for v in range(S.n)])
+    arr("var_pos", [pos_in_static[v] if v in pos_in_static else pos_in_dyn[v] for v in range(S.n)])
+    # compressed-Jacobian column -> working-matrix column [static | lags | dynamic current | leads | shocks]
+    jperm = [S.s + j for j in range(S.k)]
+    jperm += [pos_in_static[v] if v in pos_in_static else S.s + S.k + pos_in_dyn[v] for v in range(S.n)]
+    jperm += [S.s + S.k + S.m + j for j in range(S.nf)]
+    jperm += [S.s + S.k + S.m + S.nf + j for j in range(S.nx)]
+    arr("jperm", jperm)
+    # defaults taken from the model file (calibration, shocks block, estimated_params block)
+    arr("est_type0", S.est_type)
+    arr("est_i0", S.est_i)
+    arr("est_j0", S.est_j)
+
+    def darr(nm, v):
+        v = [float(x) for x in np.asarray(v).ravel()]
+        A(f"  DYB_HD static constexpr double {nm}(int i) {{ constexpr double a[{max(len(v), 1)}] = {_dbl_list(v)}; return a[i]; }}")
+    darr("param0", S.param_values)
+    darr("sigma_e0", S.sigma_e0.T)
+    darr("sigma_m0", S.sigma_m0.T)
     A("")
     A("  // closed-form steady state (reference: generated steady_state!, src/dynare_functions.jl:39-41)")
     A("  DYB_HD static void steady_state(const double* __restrict__ p, double* __restrict__ y) {")

@@ -1,0 +1,82 @@
+"""Model-free entry points: generic batched Kalman filter and the SMC weight primitives."""
+import numpy as np
+import pytest
+
+from oracle import pipeline as pl
+from oracle import smc as osmc
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_state_space(rng, n, ns, ny, nx):
+    T = np.empty((n, ns, ns)); RQR = np.empty((n, ns, ns)); P0 = np.empty((n, ns, ns)); H = np.empty((n, ny, ny))
+    for i in range(n):
+        Qo, _ = np.linalg.qr(rng.standard_normal((ns, ns)))
+        lam = rng.uniform(0.3, 0.97, ns)
+        T[i] = Qo @ np.diag(lam) @ Qo.T
+        R = 0.1 * rng.standard_normal((ns, nx))
+        RQR[i] = R @ R.T
+        import scipy.linalg as sla
+        P0[i] = sla.solve_discrete_lyapunov(T[i], RQR[i])
+        H[i] = 0.01 * np.eye(ny)
+    return T, RQR, P0, H
+
+
+@pytest.mark.parametrize("ns,ny,nobs,n", [(6, 2, 50, 40), (40, 7, 60, 12), (110, 20, 12, 3)])
+def test_generic_kalman_matches_oracle(ns, ny, nobs, n):
+    from dynare_jl_b200.engine import kalman_batch
+    rng = np.random.default_rng(ns)
+    T, RQR, P0, H = _random_state_space(rng, n, ns, ny, ny)
+    z = np.arange(ny)[::-1].copy() if ns < 20 else np.arange(ny)
+    Y = rng.standard_normal((ny, nobs))
+    Y[0, 3] = np.nan
+    ll, st = kalman_batch(Y, z, T, RQR, P0, H=H)
+    Z = np.zeros((ny, ns)); Z[np.arange(ny), z] = 1
+    for i in range(n):
+        ref = pl.kalman_likelihood(Y, Z, H[i], T[i], np.eye(ns), RQR[i], np.zeros(ns), P0[i])
+        assert st[i] == 0
+        assert abs(ll[i] - ref) <= 1e-8 * abs(ref), (i, ll[i], ref)
+
+
+def test_generic_kalman_flags_non_pd():
+    from dynare_jl_b200.engine import kalman_batch
+    ns, ny = 4, 2
+    T = 0.5 * np.eye(ns)[None]; RQR = np.zeros((1, ns, ns)); P0 = -np.eye(ns)[None]
+    ll, st = kalman_batch(np.ones((ny, 5)), [0, 1], T, RQR, P0)
+    assert st[0] == pl.ST_F_NOT_PD and ll[0] == -np.inf
+
+
+@pytest.mark.parametrize("n", [1, 777, 1024, 16384, 100000])
+def test_resampling_indices_bit_exact(n):
+    from dynare_jl_b200.engine import smc_resample_multinomial, smc_resample_systematic
+    rng = np.random.default_rng(n)
+    w = rng.random(n) ** 3
+    w /= w.sum()
+    u = rng.random(n)
+    if n > 10:
+        cw = osmc.canonical_cumsum(w)
+        u[0] = cw[5]; u[1] = 0.0; u[2] = np.nextafter(cw[-1], 2.0); u[3] = cw[-1]
+    idx, ncl = smc_resample_multinomial(w, u)
+    ref, rcl = osmc.resample_indices(w, u)
+    assert np.array_equal(idx, ref) and ncl == rcl
+    idx, ncl = smc_resample_systematic(w, 0.37)
+    ref, rcl = osmc.resample_indices(w, osmc.systematic_uniforms(n, 0.37))
+    assert np.array_equal(idx, ref) and ncl == rcl
+
+
+def test_reweight_ess_and_moments():
+    from dynare_jl_b200.engine import smc_reweight, smc_moments
+    rng = np.random.default_rng(9)
+    n = 16384
+    w = rng.random(n); w /= w.sum()
+    ll = rng.normal(-820, 4, n)
+    wn, zhat, ess = smc_reweight(w, ll, 0.0123)
+    rw, rz, re = osmc.reweight(w, ll, 0.0123)
+    assert abs(zhat - rz) <= 1e-13 * abs(rz) and abs(ess - re) <= 1e-12 * re
+    assert np.allclose(wn, rw, rtol=1e-13, atol=0)
+    # with identical (oracle) weights the canonical sums are bit-exact
+    para = rng.normal(size=(n, 17))
+    mu, R = smc_moments(para, rw)
+    rmu, rR = osmc.moments(para, rw)
+    assert np.array_equal(mu, rmu)
+    assert np.array_equal(R, rR)

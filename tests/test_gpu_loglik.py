@@ -1,0 +1,204 @@
+"""Parity of the CUDA likelihood path with the CPU oracle, through the C ABI (ctypes)."""
+import numpy as np
+import pytest
+
+from oracle import models, pipeline as pl
+
+pytestmark = pytest.mark.gpu
+
+RTOL_LOGLIK = 1e-8       # north-star tolerance: log-likelihood within 1e-8 relative (fp64)
+ATOL_POLICY = 1e-10      # north-star tolerance: policy matrices within 1e-10
+
+
+@pytest.fixture(scope="module")
+def ws_factory():
+    from dynare_jl_b200.engine import BatchSSWs
+    made = []
+
+    def make(name, Y):
+        w = BatchSSWs(name, Y)
+        made.append(w)
+        return w
+    yield make
+    for w in made:
+        w.close()
+
+
+@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+def test_loglik_matches_golden(name, golden, ws_factory):
+    g = golden(name)
+    ws = ws_factory(name, g["Y"])
+    ll, st = ws.loglikelihood(g["theta"])
+    assert np.array_equal(st, g["status"])
+    ok = g["status"] == 0
+    rel = np.abs(ll[ok] - g["loglik"][ok]) / np.abs(g["loglik"][ok])
+    assert rel.max() <= RTOL_LOGLIK, rel.max()
+    assert np.all(np.isneginf(ll[~ok]))
+
+
+@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+def test_loglik_matches_live_oracle_on_fresh_draws(name, golden, ws_factory):
+    from dynare_jl_b200.engine import model_description
+    from dynare_jl_b200.priors import PriorSet
+    g = golden(name)
+    m = models.get_model(name)
+    pri = PriorSet.from_description(model_description(name)["priors"])
+    theta = pri.sample(np.random.default_rng(12345), 200)
+    ws = ws_factory(name, g["Y"])
+    ll, st = ws.loglikelihood(theta)
+    for i in range(theta.shape[0]):
+        ref, rst = pl.loglikelihood(m, theta[i], g["Y"])
+        assert st[i] == rst, (i, st[i], rst)
+        if rst == 0:
+            assert abs(ll[i] - ref) <= RTOL_LOGLIK * abs(ref), (i, ll[i], ref)
+        else:
+            assert ll[i] == -np.inf
+
+
+@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+def test_policy_matrices(name, golden, ws_factory):
+    """g1 = [g1_1 | g1_2] against the generalised-Schur oracle (the reference's default dr_algo 'GS')."""
+    g = golden(name)
+    ws = ws_factory(name, g["Y"])
+    out = ws.first_order(g["theta"])
+    assert np.array_equal(out["status"], g["status"])
+    m = models.get_model(name)
+    g1 = np.concatenate([out["g1_1"], out["g1_2"]], axis=2)
+    err = np.abs(g1 - g["g1"]).max()
+    assert err <= ATOL_POLICY, err
+    assert np.all(out["cr_iters"] > 0) and np.all(out["cr_iters"] < 60)
+    p, se, sm = pl.set_estimated_parameters(m, g["theta"][3])
+    assert np.allclose(out["ybar"][3], m.steady_state(p), rtol=1e-13, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+def test_state_space_assembly(name, golden, ws_factory):
+    g = golden(name)
+    m = models.get_model(name)
+    ws = ws_factory(name, g["Y"])
+    theta = g["theta"][:16]
+    out = ws.state_space(theta)
+    for i in range(theta.shape[0]):
+        d = pl.solve_draw(m, theta[i])
+        ss = d["ss"]
+        sc = max(1.0, np.abs(ss["P0"]).max())
+        assert np.abs(out["T"][i] - ss["T"]).max() <= 1e-10
+        assert np.abs(out["RQR"][i] - ss["R"] @ ss["Q"] @ ss["R"].T).max() <= 1e-12 * sc
+        assert np.abs(out["P0"][i] - ss["P0"]).max() <= 1e-9 * sc
+        assert np.allclose(out["ybar_obs"][i], d["ybar"][m.obs_idx], rtol=1e-13, atol=1e-15)
+        assert np.abs(out["H"][i] - ss["H"]).max() == 0.0
+        # Lyapunov identity on the device result (reference test/test_smc.jl:41-42 pattern)
+        P0, T = out["P0"][i], out["T"][i]
+        assert np.abs(P0 - (T @ P0 @ T.T + out["RQR"][i])).max() <= 1e-9 * sc
+
+
+def test_status_classification_matches_oracle(golden, ws_factory):
+    gl, gf = golden("ls2003"), golden("fs2000")
+    ls, fs = models.get_model("ls2003"), models.get_model("fs2000")
+    cases_ls = []
+    for k, v in [(0, -1.5), (8, 1.2), (10, 1.05), (3, 1.5), (0, -1.01)]:
+        th = ls.theta_mode.copy(); th[k] = v; cases_ls.append(th)
+    cases_ls.append(ls.theta_mode.copy())
+    th = np.array(cases_ls)
+    ll, st = ws_factory("ls2003", gl["Y"]).loglikelihood(th)
+    for i in range(th.shape[0]):
+        ref, rst = pl.loglikelihood(ls, th[i], gl["Y"])
+        assert st[i] == rst, (i, th[i], st[i], rst)
+        assert (ll[i] == -np.inf) if rst else abs(ll[i] - ref) <= RTOL_LOGLIK * abs(ref)
+    cases_fs = []
+    for k, v in [(0, 1.5), (1, 1.2), (5, 1.3), (4, 1.01), (2, np.nan), (7, 0.0)]:
+        th = fs.theta_mode.copy(); th[k] = v; cases_fs.append(th)
+    th = np.array(cases_fs)
+    ll, st = ws_factory("fs2000", gf["Y"]).loglikelihood(th)
+    for i in range(th.shape[0]):
+        ref, rst = pl.loglikelihood(fs, th[i], gf["Y"])
+        assert (st[i] != 0) == (rst != 0), (i, th[i], st[i], rst)
+        if rst in (pl.ST_STEADY, pl.ST_INDETERMINATE, pl.ST_UNSTABLE):
+            assert st[i] == rst, (i, th[i], st[i], rst)
+        assert (ll[i] == -np.inf) if rst else abs(ll[i] - ref) <= RTOL_LOGLIK * abs(ref)
+
+
+def test_missing_observations_and_presample(golden, ws_factory):
+    g = golden("ls2003")
+    m = models.get_model("ls2003")
+    Y = g["Y"].copy()
+    Y[1, 5] = np.nan
+    Y[:, 20] = np.nan
+    Y[[0, 3], 40] = np.nan
+    ws = ws_factory("ls2003", Y)
+    theta = g["theta"][:24]
+    ll, st = ws.loglikelihood(theta)
+    for i in range(theta.shape[0]):
+        ref, rst = pl.loglikelihood(m, theta[i], Y)
+        assert st[i] == rst
+        assert abs(ll[i] - ref) <= RTOL_LOGLIK * abs(ref)
+    # presample: the first periods update the state but are excluded from the sum (estimation.jl:659-661)
+    ws.set_options(presample=4)
+    ll2, st2 = ws.loglikelihood(theta[:4])
+    for i in range(4):
+        d = pl.solve_draw(m, theta[i])
+        ss = d["ss"]
+        Yd = Y - d["ybar"][m.obs_idx][:, None]
+        ref = pl.kalman_likelihood(Yd, ss["Z"], ss["H"], ss["T"], ss["R"], ss["Q"], ss["a0"], ss["P0"], presample=4)
+        assert abs(ll2[i] - ref) <= RTOL_LOGLIK * abs(ref)
+    ws.set_options(presample=0)
+
+
+def test_measurement_error_and_custom_estimated_parameter_map(golden, ws_factory):
+    """stderr of a measurement error and a shock correlation in the estimated-parameter map
+    (set_estimated_parameters!, estimation.jl:517-601, incl. corr -> cov with current variances)."""
+    g = golden("fs2000")
+    m = models.get_model("fs2000")
+    ws = ws_factory("fs2000", g["Y"])
+    from dynare_jl_b200 import modelgen as mg
+    kinds = [mg.EST_PARAM, mg.EST_PARAM, mg.EST_SD_SHOCK, mg.EST_SD_SHOCK, mg.EST_CORR_SHOCK, mg.EST_SD_MEAS, mg.EST_VAR_MEAS]
+    i1 = [0, 4, 0, 1, 0, 0, 1]
+    i2 = [0, 0, 0, 1, 1, 0, 1]
+    ws.set_estimated_params(kinds, i1, i2)
+    m.est = [("param", "alp"), ("param", "rho"), ("stderr", "e_a"), ("stderr", "e_m"),
+             ("corr", "e_a", "e_m"), ("stderr", "gp_obs"), ("var", "gy_obs")]
+    rng = np.random.default_rng(5)
+    th = np.column_stack([rng.uniform(0.3, 0.45, 20), rng.uniform(0.1, 0.9, 20), rng.uniform(0.005, 0.03, 20),
+                          rng.uniform(0.002, 0.01, 20), rng.uniform(-0.6, 0.6, 20), rng.uniform(0.0005, 0.004, 20),
+                          rng.uniform(1e-7, 1e-5, 20)])
+    ll, st = ws.loglikelihood(th)
+    for i in range(20):
+        ref, rst = pl.loglikelihood(m, th[i], g["Y"])
+        assert st[i] == rst == 0
+        assert abs(ll[i] - ref) <= RTOL_LOGLIK * abs(ref)
+
+
+def test_full_size_batch_properties(golden, ws_factory):
+    """BASELINE config 2 size (65 536 draws): the batch result does not depend on batch position or
+    batch size, and repeated draws give bit-identical values."""
+    g = golden("fs2000")
+    ws = ws_factory("fs2000", g["Y"])
+    n = 65536
+    base = g["theta"]
+    reps = n // base.shape[0]
+    theta = np.tile(base, (reps, 1))
+    ll, st = ws.loglikelihood(theta)
+    assert np.all(st == 0)
+    llr = ll.reshape(reps, base.shape[0])
+    assert np.all(llr == llr[0][None, :])                 # bit-identical across positions
+    rel = np.abs(llr[0] - g["loglik"]) / np.abs(g["loglik"])
+    assert rel.max() <= RTOL_LOGLIK
+    perm = np.random.default_rng(0).permutation(n)[:5000]
+    ll2, _ = ws.loglikelihood(theta[perm])
+    assert np.array_equal(ll2, ll[perm])
+    ll3, _ = ws.loglikelihood(theta[:1])                  # N = 1 is the reference's scalar call
+    assert ll3[0] == ll[0]
+    ll0, st0 = ws.loglikelihood(np.zeros((0, 9)))
+    assert ll0.size == 0 and st0.size == 0
+
+
+def test_pinned_host_buffers(golden, ws_factory):
+    from dynare_jl_b200.engine import PinnedArray
+    g = golden("fs2000")
+    ws = ws_factory("fs2000", g["Y"])
+    n = 256
+    pth = PinnedArray((n, 9)); pll = PinnedArray((n,)); pst = PinnedArray((n,), np.int32)
+    pth.array[:] = g["theta"]
+    ll, st = ws.loglikelihood(pth.array, out=pll.array, status=pst.array)
+    assert np.allclose(pll.array, g["loglik"], rtol=RTOL_LOGLIK, atol=0) and np.all(pst.array == 0)
+    pth.free(); pll.free(); pst.free()

@@ -1,6 +1,7 @@
 // Common definitions for generated model headers and the kernels that consume them.
 #pragma once
 #include <cstdint>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define DYB_HD __host__ __device__ __forceinline__

@@ -406,7 +406,7 @@ class _Printer:
                         s_ = f"({s_})"
                     return "(" + "*".join([s_] * int(ex)) + ")"
                 if ex.is_Integer and -4 <= int(ex) <= -1:
-                    return f"(1.0/{self._print(b ** (-ex))})"
+                    return f"(1.0/({self._print(b ** (-ex))}))"
                 if ex == sp.Rational(1, 2):
                     return f"sqrt({self._print(b)})"
                 return f"pow({self._print(b)}, {self._print(ex)})"

@@ -200,11 +200,11 @@ __device__ int solve_draw(const SolveParams<M>& prm, const double* __restrict__ 
 
   int it = 0;
   int status = ST_OK;
-  bool conv = false;
-  double n0 = 0.0, n2 = 0.0;
+  bool conv = false, stalled = false;
+  double n0 = 0.0, n2 = 0.0;          // ||A0||_1, ||A2||_1 of the last iteration that stayed finite
   for (it = 1; it <= prm.cr_maxit; ++it) {
     for (int i = 0; i < MM * MM; ++i) LU[i] = A1[i];
-    if (!lu_factor<MM>(LU, piv)) { status = ST_SOLVER; break; }
+    if (!lu_factor<MM>(LU, piv)) { if (it == 1) status = ST_SOLVER; else stalled = true; break; }
     for (int i = 0; i < MM * K; ++i) X[i] = A0[i];
     for (int i = 0; i < MM * NF; ++i) X[MM * K + i] = A2[i];
     lu_solve<MM>(LU, piv, X, K + NF);
@@ -225,7 +225,7 @@ __device__ int solve_draw(const SolveParams<M>& prm, const double* __restrict__ 
         acc_hat[r + MM * j] += s;
       }
     // A0 <- -A0 X0[bk,:] ; A2 <- -A2 X2[fw,:]   (row by row so the update can be done in place)
-    n0 = 0.0; n2 = 0.0;
+    double m0 = 0.0, m2 = 0.0;
     {
       double coln[K > NF ? K : NF];
       for (int j = 0; j < K; ++j) coln[j] = 0.0;
@@ -238,7 +238,7 @@ __device__ int solve_draw(const SolveParams<M>& prm, const double* __restrict__ 
         }
         for (int j = 0; j < K; ++j) { A0[r + MM * j] = row[j]; coln[j] += fabs(row[j]); }
       }
-      for (int j = 0; j < K; ++j) n0 = fmax(n0, coln[j]);
+      for (int j = 0; j < K; ++j) m0 = fmax(m0, coln[j]);
       for (int j = 0; j < NF; ++j) coln[j] = 0.0;
       for (int r = 0; r < MM; ++r) {
         double row[NF];
@@ -249,17 +249,23 @@ __device__ int solve_draw(const SolveParams<M>& prm, const double* __restrict__ 
         }
         for (int j = 0; j < NF; ++j) { A2[r + MM * j] = row[j]; coln[j] += fabs(row[j]); }
       }
-      for (int j = 0; j < NF; ++j) n2 = fmax(n2, coln[j]);
+      for (int j = 0; j < NF; ++j) m2 = fmax(m2, coln[j]);
     }
-    if (!isfinite(n0) || !isfinite(n2)) { status = ST_SOLVER; break; }
+    if (!(m0 <= 1e150) || !(m2 <= 1e150)) {          // NaN / overflow: one of the two sequences diverges
+      if (it == 1) status = ST_SOLVER; else stalled = true;
+      break;
+    }
+    n0 = m0; n2 = m2;
     if (n0 < prm.cr_tol && n2 < prm.cr_tol) { conv = true; break; }
   }
   if (cr_it_out) *cr_it_out = it;
   if (status == ST_OK && !conv) {
-    // Blanchard-Kahn reading of a stalled reduction: A0(j) ~ lambda_m^(2^j) does not vanish when fewer
-    // than MM roots are inside the unit circle (no stable solution); A2(j) ~ lambda_(m+1)^-(2^j) does
-    // not vanish when more than MM are (indeterminacy).
-    status = (n0 >= prm.cr_tol) ? ST_UNSTABLE : ST_INDETERMINATE;
+    // Blanchard-Kahn reading of a reduction that does not converge: A0(j) ~ lambda_m^(2^j) fails to vanish
+    // when fewer than MM roots lie inside the unit circle (no stable solution: UnstableSystemException);
+    // A2(j) ~ lambda_(m+1)^-(2^j) fails to vanish when more than MM do (UndeterminateSystemException).
+    // When the iteration blows up the sequence that was still large decides; at maxit the tolerance does.
+    if (stalled) status = (n0 < n2) ? ST_INDETERMINATE : ST_UNSTABLE;
+    else status = (n0 >= prm.cr_tol) ? ST_UNSTABLE : ST_INDETERMINATE;
   }
   if (status != ST_OK) return status;
 

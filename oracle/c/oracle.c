@@ -171,10 +171,10 @@ static int solve_draw(const oracle_model* M, const opts_t* o, int np, const int*
   memcpy(A00, A0, sizeof(double) * m * m);
   double* A20 = w->tmp2; memcpy(A20, A2, sizeof(double) * m * m);
   double* B0 = w->M1; memcpy(B0, A1, sizeof(double) * m * m);
-  int conv = 0; double n0 = 0, n2 = 0;
+  int conv = 0, stalled = 0; double n0 = 0, n2 = 0;
   for (int it = 1; it <= o->cr_maxit; ++it) {
     memcpy(w->LU, A1, sizeof(double) * m * m);
-    if (lu_factor(m, w->LU, w->piv)) { status = ST_SOLVER; break; }
+    if (lu_factor(m, w->LU, w->piv)) { if (it == 1) status = ST_SOLVER; else stalled = 1; break; }
     memcpy(w->X, A0, sizeof(double) * m * m); memcpy(w->X + (size_t)m * m, A2, sizeof(double) * m * m);
     lu_solve(m, w->LU, w->piv, w->X, 2 * m);
     double *W00 = w->Wk, *W01 = w->Wk + m * m, *W10 = w->Wk + 2 * m * m, *W11 = w->Wk + 3 * m * m;
@@ -182,7 +182,7 @@ static int solve_draw(const oracle_model* M, const opts_t* o, int np, const int*
     gemm(m, m, m, 1.0, A0, m, w->X + (size_t)m * m, m, 0, 0.0, W01, m);
     gemm(m, m, m, 1.0, A2, m, w->X, m, 0, 0.0, W10, m);
     gemm(m, m, m, 1.0, A2, m, w->X + (size_t)m * m, m, 0, 0.0, W11, m);
-    n0 = 0; n2 = 0;
+    double m0 = 0, m2 = 0;
     for (int c = 0; c < m; ++c) {
       double c0 = 0, c2 = 0;
       for (int r = 0; r < m; ++r) {
@@ -191,12 +191,19 @@ static int solve_draw(const oracle_model* M, const opts_t* o, int np, const int*
         A_(A0, m, r, c) = -A_(W00, m, r, c); A_(A2, m, r, c) = -A_(W11, m, r, c);
         c0 += fabs(A_(A0, m, r, c)); c2 += fabs(A_(A2, m, r, c));
       }
-      if (c0 > n0) n0 = c0; if (c2 > n2) n2 = c2;
+      if (!(c0 <= m0)) m0 = c0;
+      if (!(c2 <= m2)) m2 = c2;
     }
-    if (!isfinite(n0) || !isfinite(n2)) { status = ST_SOLVER; break; }
+    if (!(m0 <= 1e150) || !(m2 <= 1e150)) { if (it == 1) status = ST_SOLVER; else stalled = 1; break; }
+    n0 = m0; n2 = m2;
     if (n0 < o->cr_tol && n2 < o->cr_tol) { conv = 1; break; }
   }
-  if (status == ST_OK && !conv) status = (n0 >= o->cr_tol) ? ST_UNSTABLE : ST_INDETERMINATE;
+  /* Blanchard-Kahn reading of a non-converging reduction: A0(j) not vanishing = too few stable roots
+   * (UnstableSystemException); A2(j) not vanishing = too many (UndeterminateSystemException) */
+  if (status == ST_OK && !conv) {
+    if (stalled) status = (n0 < n2) ? ST_INDETERMINATE : ST_UNSTABLE;
+    else status = (n0 >= o->cr_tol) ? ST_UNSTABLE : ST_INDETERMINATE;
+  }
   if (status != ST_OK) { free(dynpos); free(statpos); return status; }
   /* Gd = -A1h^-1 A0(0)  (m x m, non-zero columns at the backward positions) */
   double* Gd = w->G;

@@ -104,23 +104,39 @@ def solve_cr(A0, A1, A2, tol=1e-13, maxit=100):
     A0_0, A2_0 = A0.copy(), A2.copy()
     A0, A1, A2 = A0.copy(), A1.copy(), A2.copy()
     A1hat, A1chk = A1.copy(), A1.copy()
+    n0 = n2 = np.inf
+    stalled = False
     for it in range(1, maxit + 1):
         try:
-            X = np.linalg.solve(A1, np.hstack([A0, A2]))
+            with np.errstate(all="ignore"):
+                X = np.linalg.solve(A1, np.hstack([A0, A2]))
+                W = np.vstack([A0, A2]) @ X
         except np.linalg.LinAlgError:
-            raise DrawFailure(ST_SOLVER, "singular A1 in cyclic reduction")
-        W = np.vstack([A0, A2]) @ X
+            if it == 1:
+                raise DrawFailure(ST_SOLVER, "singular A1 in cyclic reduction")
+            stalled = True
+            break
+        with np.errstate(all="ignore"):
+            m0 = np.abs(W[:m, :m]).sum(0).max()
+            m2 = np.abs(W[m:, m:]).sum(0).max()
+        if not (m0 <= 1e150) or not (m2 <= 1e150):
+            if it == 1:
+                raise DrawFailure(ST_SOLVER, "NaN in cyclic reduction")
+            stalled = True
+            break
         A1 = A1 - W[:m, m:] - W[m:, :m]
         A1hat = A1hat - W[m:, :m]
         A1chk = A1chk - W[:m, m:]
         A0 = -W[:m, :m]
         A2 = -W[m:, m:]
-        if not np.all(np.isfinite(A1)):
-            raise DrawFailure(ST_SOLVER, "NaN in cyclic reduction")
-        if np.abs(A0).sum(0).max() < tol and np.abs(A2).sum(0).max() < tol:
+        n0, n2 = m0, m2
+        if n0 < tol and n2 < tol:
             break
     else:
-        raise DrawFailure(ST_SOLVER, "cyclic reduction did not converge")
+        # A0(j) ~ lambda_m^(2^j) not vanishing: too few stable roots; A2(j) not vanishing: too many
+        raise DrawFailure(ST_UNSTABLE if n0 >= tol else ST_INDETERMINATE, "cyclic reduction did not converge")
+    if stalled:
+        raise DrawFailure(ST_INDETERMINATE if n0 < n2 else ST_UNSTABLE, "cyclic reduction diverged")
     return -np.linalg.solve(A1hat, A0_0), -np.linalg.solve(A1chk, A2_0), it
 
 

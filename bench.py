@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- log-likelihood evaluations / second, fs2000 (T = 192), batched over prior draws.
+
+  python bench.py --gpus N --steps K --warmup W             our arm (CUDA library through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...   reference arm: the reference's CPU likelihood
+                                                            loop (C restatement oracle/c, all host threads)
+
+A "step" is one pass of the hot path (theta -> steady state -> Jacobian -> static elimination -> cyclic
+reduction -> g_u -> Lyapunov -> state space -> Kalman filter over T = 192) over one batch of 65 536
+draws per GPU (BASELINE.json configs[1]).  Draws are independent, so at N GPUs every rank evaluates its
+own shard of 65 536 draws with no data-path collective (weak scaling); NCCL is only used for the barrier
+and the max-over-ranks of the device time.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "fs2000"
+DRAWS_PER_GPU = 65536
+WORKLOAD = "fs2000 batched log-likelihood, 65536 prior draws per GPU, T=192 (BASELINE configs[1])"
+METRIC = "loglik evals/sec (fs2000, T=192)"
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work (SURVEY.md section 8d / BASELINE.md section 3): flop per evaluation
+# ------------------------------------------------------------------------------------------------
+def kalman_flops_per_eval(ns, ny, nx, nobs):
+    w_kf = 4 * ns ** 3 + 2 * ny * ns ** 2 + 3 * ns ** 2 + 2 * ny ** 2 * ns + 2 * ny * ns + ny ** 3 / 3 + 3 * ny ** 2 + 4 * ny
+    w_qq = 2 * ns * nx ** 2 + 2 * ns ** 2 * nx
+    return w_kf * nobs + w_qq
+
+
+def solve_flops_per_eval(d, cr_it, lyap_it):
+    n, k, s, nx, nf, ns = d["n"], d["k"], d["s"], d["nx"], d["nf"], d["ns"]
+    m = n - s
+    ncol = d["ncol"]
+    w_cr = cr_it * (38.0 / 3.0) * m ** 3 + (8.0 / 3.0) * m ** 3
+    w_static = 2 * n * s ** 2 - (2.0 / 3.0) * s ** 3 + 4 * n * s * (ncol - s)
+    w_gu = 2 * n ** 2 * nf + (2.0 / 3.0) * n ** 3 + 2 * n ** 2 * nx
+    w_lyap = 6 * k ** 3 * lyap_it + 2 * ns * k * (k + ns) + 2 * ns * nx * (nx + ns)
+    return w_cr + w_static + w_gu + w_lyap
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        allsm = []
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk = float(f[1]); mx = float(f[2])
+            except ValueError:
+                continue
+            allsm.append(clk)
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        use = sm if sm else allsm
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def load_problem():
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{MODEL}_golden.npz")))
+    return g["Y"]
+
+
+def prior_draws(n, seed):
+    import dynare_jl_b200  # noqa: F401
+    from dynare_jl_b200.engine import model_description
+    from dynare_jl_b200.priors import PriorSet
+    pri = PriorSet.from_description(model_description(MODEL)["priors"])
+    return np.ascontiguousarray(pri.sample(np.random.default_rng(seed), n))
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_port_rate(Y, budget_s, seed=1):
+    """evals/s of the C restatement on all host threads over a bounded sample of the same workload."""
+    from oracle import cbuild
+    theta = prior_draws(DRAWS_PER_GPU, seed)
+    cbuild.loglik_batch(MODEL, theta[:2048], Y)                  # warm-up + calibration
+    t = time.perf_counter(); _, _, used = cbuild.loglik_batch(MODEL, theta[:8192], Y); dt = time.perf_counter() - t
+    rate = 8192 / dt
+    n = int(min(max(rate * budget_s, 8192), 64 * DRAWS_PER_GPU))
+    reps = max(1, int(np.ceil(n / DRAWS_PER_GPU)))
+    done, t = 0, time.perf_counter()
+    for r in range(reps):
+        m = min(DRAWS_PER_GPU, n - done)
+        cbuild.loglik_batch(MODEL, theta[:m], Y)
+        done += m
+    dt = time.perf_counter() - t
+    return done / dt, used, done
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path on the host cores.  The reference is
+    pure Julia and cannot be installed here (no julia, dependencies un-vendored), so this times the C
+    restatement of its likelihood loop (oracle/c, `kind: port`) with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cbuild
+    Y = load_problem()
+    sample = 32768
+    theta = prior_draws(sample, 1)
+    for _ in range(max(args.warmup, 1)):
+        cbuild.loglik_batch(MODEL, theta[:4096], Y)
+    t = time.perf_counter()
+    used = 1
+    for _ in range(args.steps):
+        _, _, used = cbuild.loglik_batch(MODEL, theta, Y)
+    dt = time.perf_counter() - t
+    val = args.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "draws_per_step": sample},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": used, "kind": "port",
+                         "sample": f"{sample} prior draws per step x {args.steps} steps, C restatement of the "
+                                   f"reference likelihood loop (oracle/c), OpenMP, {used} threads"},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is Julia (not installable offline); timed: its CPU likelihood loop restated in C",
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import dynare_jl_b200  # noqa: F401
+    from dynare_jl_b200.engine import BatchSSWs, PinnedArray, fp64_peak
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    Y = load_problem()
+    ws = BatchSSWs(MODEL, Y, device=local)
+    stream = torch.cuda.Stream(device=dev)
+    ws.set_stream(stream.cuda_stream)
+    n = DRAWS_PER_GPU
+    npar = ws.np
+    # distinct batches of draws rotate through a pool larger than L2 (126 MB) so no step re-reads warm inputs
+    pool = 32
+    host_pool = prior_draws(n * pool, seed=1 + rank).reshape(pool, n, npar)
+    d_pool = torch.from_numpy(host_pool).to(dev)
+    d_ll = torch.empty(n, dtype=torch.float64, device=dev)
+    d_st = torch.empty(n, dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(i):
+        th = d_pool[i % pool]
+        ws.loglikelihood_device(th.data_ptr(), n, d_ll.data_ptr(), d_st.data_ptr())
+
+    # ---- device-resident throughput ---------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        launches0 = ws.kernel_launches()
+        ws.timers_reset()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        e0.record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+        e1.record(stream)
+        barrier()
+        t1 = time.time()
+        dev_ms = e0.elapsed_time(e1)
+        nb, solve_ms, filter_ms = ws.timers_read()
+        launches = ws.kernel_launches() - launches0
+        clocks = sampler.stop(t0, t1) if rank == 0 else None
+    n_ok = int((d_st == 0).sum().item())
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    step_ms = tmax.item() / args.steps
+    value = world * n * args.steps / (tmax.item() * 1e-3)
+
+    # ---- end to end through the public API with (pinned) host buffers --------------------------------
+    pth = PinnedArray((n, npar)); pll = PinnedArray((n,)); pst = PinnedArray((n,), np.int32)
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(2):
+        pth.array[:] = host_pool[i % pool]
+        ws.loglikelihood(pth.array, out=pll.array, status=pst.array)
+    barrier()
+    e2e_t = 0.0
+    for i in range(e2e_steps):
+        pth.array[:] = host_pool[(i + 2) % pool]          # a fresh batch lands in pinned memory (not timed)
+        barrier()
+        t = time.perf_counter()
+        ws.loglikelihood(pth.array, out=pll.array, status=pst.array)   # H2D + kernels + D2H, synchronous
+        e2e_t += time.perf_counter() - t
+    te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / te.item()
+
+    if rank == 0:
+        d = ws.dims
+        # iterations actually taken (batch means) for the algorithmic flop count of the solve
+        fo = ws.first_order(host_pool[0][:8192])
+        okm = fo["status"] == 0
+        cr_it = float(fo["cr_iters"][okm].mean()); ly_it = float(fo["lyap_iters"][okm].mean())
+        fl_kal = kalman_flops_per_eval(d["ns"], d["ny"], d["nx"], Y.shape[1])
+        fl_sol = solve_flops_per_eval(d, cr_it, ly_it)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+            hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        fp64 = fp64_peak(local)
+        k_solve = solve_ms / max(nb, 1); k_filt = filter_ms / max(nb, 1)
+        kernels = [
+            {"name": "solve_kernel<fs2000>", "ms_per_launch": k_solve, "flop_per_launch": fl_sol * n,
+             "tflops": fl_sol * n / (k_solve * 1e-3) / 1e12 if k_solve > 0 else None,
+             "hbm_bytes_per_launch": n * (npar * 8 + d["ss_doubles"] * 8 + 4)},
+            {"name": "kalman_kernel<fs2000>", "ms_per_launch": k_filt, "flop_per_launch": fl_kal * n,
+             "tflops": fl_kal * n / (k_filt * 1e-3) / 1e12 if k_filt > 0 else None,
+             "hbm_bytes_per_launch": n * (d["ss_doubles"] * 8 + 4 + 12)},
+        ]
+        dom = max(kernels, key=lambda kx: kx["ms_per_launch"])
+        roofline = {
+            "kernel": dom["name"], "bound": "fp64", "achieved": dom["tflops"], "peak": fp64, "unit": "TFLOP/s",
+            "frac": dom["tflops"] / fp64 if fp64 > 0 else None, "traffic": None,
+            "peak_source": "measured live: dyb_fp64_peak DFMA microbenchmark (MEASURED_PEAKS.json has no fp64 figure)",
+            "algorithmic_flop_per_eval": {"kalman": fl_kal, "solve": fl_sol, "cr_iters_mean": cr_it, "lyap_iters_mean": ly_it},
+            "hbm": {"achieved": dom["hbm_bytes_per_launch"] / (dom["ms_per_launch"] * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+                    "frac": dom["hbm_bytes_per_launch"] / (dom["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak},
+            "kernels": kernels,
+            "kernel_share_of_step": {"solve": k_solve / step_ms, "filter": k_filt / step_ms},
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "draws_per_gpu": n, "global_draws": n * world, "np": npar,
+                       "l2": f"inputs rotate through a pool of {pool} distinct batches "
+                             f"({pool * n * (npar * 8 + d['ss_doubles'] * 8) / 1e6:.0f} MB touched per cycle incl. the "
+                             f"hand-off buffer > 126 MB L2)",
+                       "parallelism": f"draws sharded over {world} GPU(s), no data-path collective",
+                       "ok_draws_last_step": n_ok},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": n * npar * 8,
+                    "d2h_bytes_per_step": n * 12, "steps": e2e_steps,
+                    "how": "BatchSSWs.loglikelihood (dyb_loglik_batch) with pinned host buffers; host wall clock "
+                           "around the synchronous call, max over ranks"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            rate, used, done = cpu_port_rate(Y, args.cpu_budget)
+            line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": used, "kind": "port",
+                                    "sample": f"{done} prior draws of the same workload, C restatement of the reference "
+                                              f"likelihood loop (oracle/c), OpenMP on {used} of {host_cores()} host cores"}
+        print(json.dumps(line))
+    pth.free(); pll.free(); pst.free()
+    ws.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -60,7 +60,11 @@ SIGNATURES = {
     "dyb_sync": (C.c_int, [_P]),
     "dyb_kernel_launches": (C.c_int64, [_P]),
     "dyb_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
-    "dyb_first_order_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D, _I32, _I32]),
+    "dyb_first_order_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D, _I32, _I32, _I32]),
+    "dyb_set_stream": (C.c_int, [_P, C.c_void_p]),
+    "dyb_kernel_timers_reset": (C.c_int, [_P]),
+    "dyb_kernel_timers_read": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "dyb_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "dyb_state_space_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D, _D, _D, _D, _I32]),
     "dyb_kalman_batch": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _D,
                                    _D, _D, _D, _D, _D, C.c_int64, _D, _I32]),

@@ -144,9 +144,13 @@ using namespace dyb;
 struct dyb_handle {
   const ModelOps* ops = nullptr;
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;        // stream in use
+  cudaStream_t own_stream = nullptr;    // the handle's private stream
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
+  std::vector<cudaEvent_t> timer_ev;    // triples (start, after solve, after filter)
+  int timer_n = 0;
+  bool timers_armed = false;
   HostState hs;
   DevBuf d_theta, d_ss, d_st1, d_ll, d_st2, d_Y;
   PinBuf h_in, h_out;
@@ -203,7 +207,8 @@ int dyb_create(const char* model, int device, dyb_handle** out) {
   h->device = device;
   m->defaults(h->hs);
   default_options(&h->hs.opt);
-  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  h->stream = h->own_stream;
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
   if (e != cudaSuccess) { delete h; return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
   *out = h;
@@ -217,7 +222,8 @@ int dyb_destroy(dyb_handle* h) {
   h->d_theta.release(); h->d_ss.release(); h->d_st1.release(); h->d_ll.release(); h->d_st2.release(); h->d_Y.release();
   h->h_in.release(); h->h_out.release();
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  for (cudaEvent_t e : h->timer_ev) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return DYB_OK;
 }
@@ -282,6 +288,7 @@ int dyb_set_observations(dyb_handle* h, const double* Y, int32_t ny, int32_t nob
   return DYB_OK;
 }
 
+static cudaEvent_t* timer_slot(dyb_handle* h);
 static int reserve_batch(dyb_handle* h, int64_t n) {
   const dyb_model_dims& d = h->ops->dims;
   const size_t N = (size_t)(n > 0 ? n : 1);
@@ -297,16 +304,29 @@ int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, dou
   DYB_CUDA(cudaSetDevice(h->device));
   int rc = reserve_batch(h, n);
   if (rc) return rc;
-  SolveOut so{h->d_ss.as<double>(), h->d_st1.as<int>(), nullptr, nullptr, nullptr};
-  DYB_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  SolveOut so{h->d_ss.as<double>(), h->d_st1.as<int>(), nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t* ev = h->timers_armed ? timer_slot(h) : nullptr;
+  if (ev) h->timer_n += 1; else ev = h->ev;
+  DYB_CUDA(cudaEventRecord(ev[0], h->stream));
   DYB_CUDA(h->ops->solve(h->hs, d_theta, n, so, h->stream));
-  DYB_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  DYB_CUDA(cudaEventRecord(ev[1], h->stream));
   DYB_CUDA(h->ops->kalman(h->d_ss.as<double>(), n, h->d_Y.as<double>(), h->nobs, h->hs.opt.presample,
                           h->d_st1.as<int>(), d_loglik, d_status, h->stream));
-  DYB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-  h->ev_valid = true;
+  DYB_CUDA(cudaEventRecord(ev[2], h->stream));
+  h->ev_valid = (ev == h->ev);
   h->launches += 2;
   return DYB_OK;
+}
+
+// timed variant used when the accumulating timers are armed: records into the timer ring instead
+static cudaEvent_t* timer_slot(dyb_handle* h) {
+  if (h->timer_n >= 4096) return nullptr;
+  while ((int)h->timer_ev.size() < 3 * (h->timer_n + 1)) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    h->timer_ev.push_back(e);
+  }
+  return &h->timer_ev[3 * h->timer_n];
 }
 
 int dyb_loglik_batch(dyb_handle* h, const double* theta, int64_t n, double* loglik, int32_t* status) {
@@ -364,8 +384,85 @@ int dyb_last_kernel_ms(dyb_handle* h, float* solve_ms, float* filter_ms) {
   return DYB_OK;
 }
 
+int dyb_set_stream(dyb_handle* h, void* cuda_stream) {
+  if (!h) return fail(DYB_ERR_ARG, "null handle");
+  DYB_CUDA(cudaSetDevice(h->device));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return DYB_OK;
+}
+
+int dyb_kernel_timers_reset(dyb_handle* h) {
+  if (!h) return fail(DYB_ERR_ARG, "null handle");
+  DYB_CUDA(cudaSetDevice(h->device));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  h->timer_n = 0;
+  h->timers_armed = true;
+  return DYB_OK;
+}
+
+int dyb_kernel_timers_read(dyb_handle* h, int32_t* n_batches, float* solve_ms_total, float* filter_ms_total) {
+  if (!h) return fail(DYB_ERR_ARG, "null handle");
+  DYB_CUDA(cudaSetDevice(h->device));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  float a = 0, b = 0;
+  for (int i = 0; i < h->timer_n; ++i) {
+    float x = 0, y = 0;
+    DYB_CUDA(cudaEventElapsedTime(&x, h->timer_ev[3 * i], h->timer_ev[3 * i + 1]));
+    DYB_CUDA(cudaEventElapsedTime(&y, h->timer_ev[3 * i + 1], h->timer_ev[3 * i + 2]));
+    a += x; b += y;
+  }
+  if (n_batches) *n_batches = h->timer_n;
+  if (solve_ms_total) *solve_ms_total = a;
+  if (filter_ms_total) *filter_ms_total = b;
+  h->timers_armed = false;
+  return DYB_OK;
+}
+
+namespace dyb {
+// 8 independent DFMA chains per thread, 4096 iterations: register-resident, saturates the fp64 pipe
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+}  // namespace dyb
+
+int dyb_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(DYB_ERR_ARG, "null argument");
+  DYB_CUDA(cudaSetDevice(device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sms * 8, threads = 256, iters = 8192;
+  double* out = nullptr;
+  DYB_CUDA(cudaMalloc(&out, sizeof(double) * blocks * threads));
+  cudaStream_t st = device_stream(device);
+  cudaEvent_t e0, e1;
+  DYB_CUDA(cudaEventCreate(&e0)); DYB_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    DYB_CUDA(cudaEventRecord(e0, st));
+    fp64_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 1.0 + rep);
+    DYB_CUDA(cudaEventRecord(e1, st));
+    DYB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    DYB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops = best;
+  return DYB_OK;
+}
+
 int dyb_first_order_batch(dyb_handle* h, const double* theta, int64_t n, double* g1, double* ybar,
-                          int32_t* cr_iters, int32_t* status) {
+                          int32_t* cr_iters, int32_t* lyap_iters, int32_t* status) {
   if (!h || n < 0 || (n > 0 && (!theta || !status))) return fail(DYB_ERR_ARG, "null argument");
   if (n == 0) return DYB_OK;
   DYB_CUDA(cudaSetDevice(h->device));
@@ -381,9 +478,11 @@ int dyb_first_order_batch(dyb_handle* h, const double* theta, int64_t n, double*
   so.g1 = sg.out(g1, (size_t)d.n * (d.k + d.nx) * N);
   so.ybar = sg.out(ybar, (size_t)d.n * N);
   so.cr_iters = sg.out(cr_iters, N);
+  so.lyap_iters = sg.out(lyap_iters, N);
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   if (so.g1) DYB_CUDA(cudaMemsetAsync(so.g1, 0, sizeof(double) * (size_t)d.n * (d.k + d.nx) * N, h->stream));
   if (so.cr_iters) DYB_CUDA(cudaMemsetAsync(so.cr_iters, 0, sizeof(int) * N, h->stream));
+  if (so.lyap_iters) DYB_CUDA(cudaMemsetAsync(so.lyap_iters, 0, sizeof(int) * N, h->stream));
   DYB_CUDA(h->ops->solve(h->hs, dth, n, so, h->stream));
   h->launches += 1;
   DYB_CUDA(sg.finish());
@@ -401,7 +500,7 @@ int dyb_state_space_batch(dyb_handle* h, const double* theta, int64_t n, double*
   Stager sg(h->stream);
   const size_t N = (size_t)n, ns2 = (size_t)d.ns * d.ns;
   const double* dth = sg.in(theta, (size_t)h->hs.np * N);
-  SolveOut so{h->d_ss.as<double>(), sg.out(status, N), nullptr, nullptr, nullptr};
+  SolveOut so{h->d_ss.as<double>(), sg.out(status, N), nullptr, nullptr, nullptr, nullptr};
   double* dT = sg.out(T, ns2 * N);
   double* dQ = sg.out(RQR, ns2 * N);
   double* dP = sg.out(P0, ns2 * N);

@@ -35,7 +35,7 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
   for (int i = 0; i < MAX_EST; ++i) { prm.est_type[i] = hs.est_type[i]; prm.est_i[i] = hs.est_i[i]; prm.est_j[i] = hs.est_j[i]; }
   prm.cr_tol = hs.opt.cr_tol; prm.cr_maxit = hs.opt.cr_maxit; prm.steady_tol = hs.opt.steady_tol;
   prm.lyap_tol = hs.opt.lyap_tol; prm.lyap_maxit = hs.opt.lyap_maxit;
-  SolveExtra ex{out.g1, out.ybar, out.cr_iters};
+  SolveExtra ex{out.g1, out.ybar, out.cr_iters, out.lyap_iters};
   const int block = 128;
   const long long grid = (n + block - 1) / block;
   solve_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.ss, out.status, ex);

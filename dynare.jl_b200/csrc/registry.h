@@ -22,6 +22,7 @@ struct SolveOut {
   double* g1;        // optional AoS outputs (device), may be null
   double* ybar;
   int* cr_iters;
+  int* lyap_iters;
 };
 
 struct ModelOps {

@@ -107,12 +107,13 @@ struct SolveExtra {
   double* g1;        // n x (k+nx) column-major per draw (AoS), or nullptr
   double* ybar;      // n per draw, or nullptr
   int* cr_iters;     // per draw, or nullptr
+  int* lyap_iters;   // per draw, or nullptr
 };
 
 template <class M>
 __device__ int solve_draw(const SolveParams<M>& prm, const double* __restrict__ theta,
                           double* __restrict__ ss, long long stride,   // ss[e * stride]
-                          double* g1_out, double* ybar_out, int* cr_it_out) {
+                          double* g1_out, double* ybar_out, int* cr_it_out, int* lyap_it_out) {
   constexpr int N = M::N, NX = M::NX, K = M::K, NF = M::NF, S = M::S, MM = M::M, NCOL = M::NCOL;
   constexpr int NS = M::NS, NY = M::NY;
   constexpr int cC = S, cB = S + K, cA = S + K + MM, cU = S + K + MM + NF;
@@ -354,7 +355,9 @@ __device__ int solve_draw(const SolveParams<M>& prm, const double* __restrict__ 
     }
   }
   bool lconv = false;
+  int li_done = 0;
   for (int li = 0; li < prm.lyap_maxit; ++li) {
+    li_done = li + 1;
     // Tm = Ak Sg ; Sg += Tm Ak' ; Ak = Ak Ak
     for (int j = 0; j < K; ++j) for (int i = 0; i < K; ++i) {
       double s = 0.0;
@@ -381,6 +384,7 @@ __device__ int solve_draw(const SolveParams<M>& prm, const double* __restrict__ 
     if (dmax <= prm.lyap_tol * smax && amax < 1.0) { lconv = true; break; }
     if (!isfinite(amax)) break;
   }
+  if (lyap_it_out) *lyap_it_out = li_done;
   if (!lconv) return ST_NONSTATIONARY;
   // symmetrise
   for (int j = 0; j < K; ++j) for (int i = j + 1; i < K; ++i) {
@@ -438,7 +442,8 @@ solve_kernel(const SolveParams<M> prm, const double* __restrict__ theta, long lo
   double* g1 = ex.g1 ? ex.g1 + d * (long long)(M::N * (M::K + M::NX)) : nullptr;
   double* yb = ex.ybar ? ex.ybar + d * (long long)M::N : nullptr;
   int* ci = ex.cr_iters ? ex.cr_iters + d : nullptr;
-  const int st = solve_draw<M>(prm, theta + d * (long long)prm.np, ss + d, n_draws, g1, yb, ci);
+  int* li = ex.lyap_iters ? ex.lyap_iters + d : nullptr;
+  const int st = solve_draw<M>(prm, theta + d * (long long)prm.np, ss + d, n_draws, g1, yb, ci, li);
   status[d] = st;
 }
 

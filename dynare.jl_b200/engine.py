@@ -155,6 +155,19 @@ class BatchSSWs:
     def sync(self):
         L.check(self.lib.dyb_sync(self._h))
 
+    def set_stream(self, cuda_stream: Optional[int]):
+        """Run on a caller-owned CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        L.check(self.lib.dyb_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def timers_reset(self):
+        L.check(self.lib.dyb_kernel_timers_reset(self._h))
+
+    def timers_read(self):
+        """(number of batches, total solve-kernel ms, total filter-kernel ms) since ``timers_reset``."""
+        n, a, b = C.c_int32(), C.c_float(), C.c_float()
+        L.check(self.lib.dyb_kernel_timers_read(self._h, C.byref(n), C.byref(a), C.byref(b)))
+        return n.value, a.value, b.value
+
     def kernel_launches(self) -> int:
         return int(self.lib.dyb_kernel_launches(self._h))
 
@@ -172,10 +185,11 @@ class BatchSSWs:
         g1 = np.zeros((n, d["k"] + d["nx"], d["n"]))          # per draw column-major n x (k+nx)
         yb = np.zeros((n, d["n"]))
         it = np.zeros(n, dtype=np.int32)
+        li = np.zeros(n, dtype=np.int32)
         st = np.zeros(n, dtype=np.int32)
-        L.check(self.lib.dyb_first_order_batch(self._h, L.ptr(Theta), n, L.ptr(g1), L.ptr(yb), L.ptr(it), L.ptr(st)))
+        L.check(self.lib.dyb_first_order_batch(self._h, L.ptr(Theta), n, L.ptr(g1), L.ptr(yb), L.ptr(it), L.ptr(li), L.ptr(st)))
         g1 = g1.transpose(0, 2, 1)
-        return dict(g1_1=g1[:, :, :d["k"]], g1_2=g1[:, :, d["k"]:], ybar=yb, cr_iters=it, status=st)
+        return dict(g1_1=g1[:, :, :d["k"]], g1_2=g1[:, :, d["k"]:], ybar=yb, cr_iters=it, lyap_iters=li, status=st)
 
     def state_space(self, Theta):
         """Returns dict(T, RQR, P0 (N,ns,ns), ybar_obs (N,ny), H (N,ny,ny), status)."""
@@ -226,6 +240,13 @@ class DSGELogPosteriorDensity:
 # ---------------------------------------------------------------------------------------------------
 # model-free entry points
 # ---------------------------------------------------------------------------------------------------
+def fp64_peak(device=0) -> float:
+    """Measured fp64 FMA peak of the device in TFLOP/s (register-resident DFMA loop)."""
+    t = C.c_double()
+    L.check(L.load().dyb_fp64_peak(device, C.byref(t)))
+    return t.value
+
+
 def kalman_batch(Y, z_idx, T, RQR, P0, a0=None, H=None, presample=0, device=0):
     """Generic batched Kalman log-likelihood.  T, RQR, P0: (N, ns, ns) numpy (row-major per draw);
     Y: ny x nobs; z_idx: state observed by each row.  Returns (loglik[N], status[N])."""

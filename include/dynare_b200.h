@@ -116,17 +116,29 @@ int dyb_loglik_batch(dyb_handle* h, const double* theta, int64_t n_draws,
 int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n_draws,
                             double* d_loglik, int32_t* d_status);
 int dyb_sync(dyb_handle* h);
+/* run the handle's work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores the
+ * handle's private stream) -- lets a host framework order and time the engine with its own events */
+int dyb_set_stream(dyb_handle* h, void* cuda_stream);
 /* number of kernels launched by this handle so far (for the bench's gpu_launches claim) */
 int64_t dyb_kernel_launches(const dyb_handle* h);
 /* elapsed device time (ms) of the last dyb_loglik_batch[_device] call's solve and filter kernels,
  * from CUDA events on the handle's stream; valid after dyb_sync */
 int dyb_last_kernel_ms(dyb_handle* h, float* solve_ms, float* filter_ms);
+/* accumulated CUDA-event timings of the solve / filter kernels over every likelihood batch since the last
+ * reset (up to 4096 batches); read synchronises the stream */
+int dyb_kernel_timers_reset(dyb_handle* h);
+int dyb_kernel_timers_read(dyb_handle* h, int32_t* n_batches, float* solve_ms_total, float* filter_ms_total);
+/* measured fp64 FMA throughput of the device (TFLOP/s) from a register-resident DFMA loop on all SMs:
+ * the roofline denominator for this path, which MEASURED_PEAKS.json does not carry */
+int dyb_fp64_peak(int device, double* tflops);
 
 /* ---- stage-level entry points (host pointers) ---------------------------------------------------- */
 /* LRE.first_order_solver! (src/perturbations.jl:663-664): g1 = [g1_1 | g1_2], n x (k+nx) per draw,
- * rows in declaration order (src/perturbations.jl:82-107); ybar n per draw; cr_iters may be NULL. */
+ * rows in declaration order (src/perturbations.jl:82-107); ybar n per draw; cr_iters / lyap_iters (iterations
+ * taken by cyclic reduction and by the doubling Lyapunov solve) may be NULL. */
 int dyb_first_order_batch(dyb_handle* h, const double* theta, int64_t n_draws,
-                          double* g1, double* ybar, int32_t* cr_iters, int32_t* status);
+                          double* g1, double* ybar, int32_t* cr_iters, int32_t* lyap_iters,
+                          int32_t* status);
 /* state space handed to the filter (src/estimation/estimation.jl:640-658), per draw:
  *   T ns x ns, RQR ns x ns (= R Q R'), P0 ns x ns, ybar_obs ny, H ny x ny; any output may be NULL */
 int dyb_state_space_batch(dyb_handle* h, const double* theta, int64_t n_draws,

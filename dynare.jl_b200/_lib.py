@@ -31,7 +31,8 @@ class ModelDims(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("cr_tol", C.c_double), ("cr_maxit", C.c_int32), ("steady_tol", C.c_double),
-                ("lyap_tol", C.c_double), ("lyap_maxit", C.c_int32), ("presample", C.c_int32)]
+                ("lyap_tol", C.c_double), ("lyap_maxit", C.c_int32), ("presample", C.c_int32),
+                ("solver", C.c_int32)]
 
 
 _P = C.c_void_p

@@ -152,7 +152,7 @@ struct dyb_handle {
   int timer_n = 0;
   bool timers_armed = false;
   HostState hs;
-  DevBuf d_theta, d_ss, d_st1, d_ll, d_st2, d_Y;
+  DevBuf d_theta, d_ss, d_st1, d_ll, d_st2, d_Y, d_mid;
   PinBuf h_in, h_out;
   int ny_obs = 0, nobs = 0;
   int64_t launches = 0;
@@ -165,6 +165,7 @@ static void default_options(dyb_options* o) {
   o->lyap_tol = 1e-16;
   o->lyap_maxit = 60;
   o->presample = 0;
+  o->solver = 0;
 }
 
 extern "C" {
@@ -219,7 +220,7 @@ int dyb_destroy(dyb_handle* h) {
   if (!h) return DYB_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  h->d_theta.release(); h->d_ss.release(); h->d_st1.release(); h->d_ll.release(); h->d_st2.release(); h->d_Y.release();
+  h->d_theta.release(); h->d_ss.release(); h->d_st1.release(); h->d_ll.release(); h->d_st2.release(); h->d_Y.release(); h->d_mid.release();
   h->h_in.release(); h->h_out.release();
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->timer_ev) cudaEventDestroy(e);
@@ -241,7 +242,7 @@ int dyb_get_options(const dyb_handle* h, dyb_options* opt) {
 int dyb_set_options(dyb_handle* h, const dyb_options* opt) {
   if (!h || !opt) return fail(DYB_ERR_ARG, "null argument");
   if (!(opt->cr_tol > 0) || opt->cr_maxit < 1 || !(opt->steady_tol > 0) || !(opt->lyap_tol >= 0) ||
-      opt->lyap_maxit < 1 || opt->presample < 0)
+      opt->lyap_maxit < 1 || opt->presample < 0 || opt->solver < 0 || opt->solver > 2)
     return fail(DYB_ERR_ARG, "invalid option value");
   h->hs.opt = *opt;
   return DYB_OK;
@@ -294,6 +295,7 @@ static int reserve_batch(dyb_handle* h, int64_t n) {
   const size_t N = (size_t)(n > 0 ? n : 1);
   DYB_CUDA(h->d_ss.reserve(sizeof(double) * d.ss_doubles * N));
   DYB_CUDA(h->d_st1.reserve(sizeof(int) * N));
+  DYB_CUDA(h->d_mid.reserve(sizeof(double) * (size_t)h->ops->mid_doubles * N));
   return DYB_OK;
 }
 
@@ -304,7 +306,7 @@ int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, dou
   DYB_CUDA(cudaSetDevice(h->device));
   int rc = reserve_batch(h, n);
   if (rc) return rc;
-  SolveOut so{h->d_ss.as<double>(), h->d_st1.as<int>(), nullptr, nullptr, nullptr, nullptr};
+  SolveOut so{h->d_ss.as<double>(), h->d_st1.as<int>(), nullptr, nullptr, nullptr, nullptr, h->d_mid.as<double>()};
   cudaEvent_t* ev = h->timers_armed ? timer_slot(h) : nullptr;
   if (ev) h->timer_n += 1; else ev = h->ev;
   DYB_CUDA(cudaEventRecord(ev[0], h->stream));
@@ -314,7 +316,7 @@ int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, dou
                           h->d_st1.as<int>(), d_loglik, d_status, h->stream));
   DYB_CUDA(cudaEventRecord(ev[2], h->stream));
   h->ev_valid = (ev == h->ev);
-  h->launches += 2;
+  h->launches += 1 + h->ops->solve_launches(h->hs);
   return DYB_OK;
 }
 
@@ -479,12 +481,13 @@ int dyb_first_order_batch(dyb_handle* h, const double* theta, int64_t n, double*
   so.ybar = sg.out(ybar, (size_t)d.n * N);
   so.cr_iters = sg.out(cr_iters, N);
   so.lyap_iters = sg.out(lyap_iters, N);
+  so.mid = h->d_mid.as<double>();
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   if (so.g1) DYB_CUDA(cudaMemsetAsync(so.g1, 0, sizeof(double) * (size_t)d.n * (d.k + d.nx) * N, h->stream));
   if (so.cr_iters) DYB_CUDA(cudaMemsetAsync(so.cr_iters, 0, sizeof(int) * N, h->stream));
   if (so.lyap_iters) DYB_CUDA(cudaMemsetAsync(so.lyap_iters, 0, sizeof(int) * N, h->stream));
   DYB_CUDA(h->ops->solve(h->hs, dth, n, so, h->stream));
-  h->launches += 1;
+  h->launches += h->ops->solve_launches(h->hs);
   DYB_CUDA(sg.finish());
   return DYB_OK;
 }
@@ -500,7 +503,7 @@ int dyb_state_space_batch(dyb_handle* h, const double* theta, int64_t n, double*
   Stager sg(h->stream);
   const size_t N = (size_t)n, ns2 = (size_t)d.ns * d.ns;
   const double* dth = sg.in(theta, (size_t)h->hs.np * N);
-  SolveOut so{h->d_ss.as<double>(), sg.out(status, N), nullptr, nullptr, nullptr, nullptr};
+  SolveOut so{h->d_ss.as<double>(), sg.out(status, N), nullptr, nullptr, nullptr, nullptr, h->d_mid.as<double>()};
   double* dT = sg.out(T, ns2 * N);
   double* dQ = sg.out(RQR, ns2 * N);
   double* dP = sg.out(P0, ns2 * N);
@@ -510,7 +513,7 @@ int dyb_state_space_batch(dyb_handle* h, const double* theta, int64_t n, double*
   DYB_CUDA(cudaMemsetAsync(h->d_ss.p, 0, sizeof(double) * d.ss_doubles * N, h->stream));
   DYB_CUDA(h->ops->solve(h->hs, dth, n, so, h->stream));
   DYB_CUDA(h->ops->unpack(h->d_ss.as<double>(), n, dT, dQ, dP, dy, dH, h->stream));
-  h->launches += 2;
+  h->launches += 1 + h->ops->solve_launches(h->hs);
   DYB_CUDA(sg.finish());
   return DYB_OK;
 }

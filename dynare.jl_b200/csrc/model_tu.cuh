@@ -5,6 +5,7 @@
 // Instantiates the solve / filter kernels for the model and registers its launchers.
 #include "registry.h"
 #include "solve_kernel.cuh"
+#include "solve_coop.cuh"
 #include "kalman_kernel.cuh"
 
 namespace dyb {
@@ -25,6 +26,9 @@ void mt_defaults(HostState& hs) {
   }
 }
 
+constexpr bool mt_coop_fits = (MT::M <= 12) && (MT::K >= 1) && (MT::NF >= 1);
+int mt_solve_launches(const HostState& hs) { return (mt_coop_fits && hs.opt.solver != 1) ? 3 : 1; }
+
 cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, SolveOut out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   SolveParams<MT> prm;
@@ -35,10 +39,21 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
   for (int i = 0; i < MAX_EST; ++i) { prm.est_type[i] = hs.est_type[i]; prm.est_i[i] = hs.est_i[i]; prm.est_j[i] = hs.est_j[i]; }
   prm.cr_tol = hs.opt.cr_tol; prm.cr_maxit = hs.opt.cr_maxit; prm.steady_tol = hs.opt.steady_tol;
   prm.lyap_tol = hs.opt.lyap_tol; prm.lyap_maxit = hs.opt.lyap_maxit;
-  SolveExtra ex{out.g1, out.ybar, out.cr_iters, out.lyap_iters};
   const int block = 128;
   const long long grid = (n + block - 1) / block;
-  solve_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.ss, out.status, ex);
+  constexpr int G = 4;
+  const bool coop = mt_coop_fits && hs.opt.solver != 1;
+  if (coop) {
+    model_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.mid, out.status, out.ybar);
+    const long long gridc = (n * G + block - 1) / block;
+    CrOptions co{hs.opt.cr_tol, hs.opt.cr_maxit};
+    cr_kernel<MT, G><<<(unsigned)gridc, block, 0, st>>>(out.mid, n, co, out.status, out.cr_iters);
+    assemble_kernel<MT><<<(unsigned)grid, block, 0, st>>>(out.mid, n, hs.opt.lyap_tol, hs.opt.lyap_maxit, out.ss,
+                                                          out.status, out.g1, out.lyap_iters);
+  } else {
+    SolveExtra ex{out.g1, out.ybar, out.cr_iters, out.lyap_iters};
+    solve_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.ss, out.status, ex);
+  }
   return cudaGetLastError();
 }
 
@@ -84,7 +99,8 @@ cudaError_t mt_unpack(const double* d_ss, long long n, double* T, double* RQR, d
 const ModelOps mt_ops = {
   MT::name,
   {MT::N, MT::NX, MT::NPAR, MT::K, MT::NF, MT::S, MT::NCOL, MT::NS, MT::NY, MT::NP_DEFAULT, SSLayout<MT>::SIZE},
-  mt_defaults, mt_solve, mt_kalman, mt_unpack
+  MidLayout<MT>::SIZE,
+  mt_defaults, mt_solve_launches, mt_solve, mt_kalman, mt_unpack
 };
 
 struct Registrar { Registrar() { register_model(&mt_ops); } } mt_registrar;

@@ -23,12 +23,15 @@ struct SolveOut {
   double* ybar;
   int* cr_iters;
   int* lyap_iters;
+  double* mid;       // scratch for the cooperative solver, mid_doubles x N (device)
 };
 
 struct ModelOps {
   const char* name;
   dyb_model_dims dims;
+  int mid_doubles;   // doubles per draw of scratch between the kernels of the cooperative solver
   void (*defaults)(HostState&);
+  int (*solve_launches)(const HostState&);   // kernels one solve() call launches
   cudaError_t (*solve)(const HostState&, const double* d_theta, long long n, SolveOut out, cudaStream_t);
   cudaError_t (*kalman)(const double* d_ss, long long n, const double* d_Y, int nobs, int presample,
                         const int* d_status_in, double* d_loglik, int* d_status_out, cudaStream_t);

@@ -1,0 +1,741 @@
+// Register-resident first-order solve in three kernels (the production path for models whose dynamic
+// block fits the register file; solve_kernel.cuh keeps the size-agnostic one-thread-per-draw variant).
+//
+//   model_kernel<M>      one thread per draw: parameter scatter, steady state + residual check, Jacobian
+//                        and the structure-aware static elimination generated at model set-up
+//                        (M::static_elim).  Writes the non-zeros of the reduced system and of the pivot rows.
+//   cr_kernel<M,G>       G lanes per draw, matrices distributed by COLUMN over the lanes and held in
+//                        registers with compile-time indices only: cyclic reduction where the m x m solve
+//                        is a Householder QR (no pivoting => no dynamic register indexing) followed by a
+//                        backward elimination; columns are exchanged with warp shuffles.  A1 and the
+//                        accumulated correction live in a small per-group shared-memory tile.  Then
+//                        G = -A1hat^-1 A0 and g_u = -(A2 G + A1)^-1 F_u with the same solver.
+//   assemble_kernel<M>   one thread per draw: static rows by sparse back-substitution, Lyapunov doubling,
+//                        state-space assembly into the hand-off buffer of the filter kernel.
+//
+// Reference stages replaced: LRE.first_order_solver! (src/perturbations.jl:663-664), compute_variance!
+// (src/estimation/estimation.jl:630), state-space assembly (estimation.jl:640-658).
+#pragma once
+#include "model_traits.cuh"
+#include "solve_kernel.cuh"
+
+namespace dyb {
+
+template <class M>
+struct MidLayout {
+  static constexpr int OFF_RED = 0;
+  static constexpr int OFF_TOP = OFF_RED + M::RED_NNZ;
+  static constexpr int OFF_YB = OFF_TOP + M::TOP_NNZ;                 // NY
+  static constexpr int OFF_SE = OFF_YB + M::NY;                       // NX*NX
+  static constexpr int OFF_H = OFF_SE + M::NX * M::NX;                // packed lower NY(NY+1)/2
+  static constexpr int OFF_G = OFF_H + M::NY * (M::NY + 1) / 2;       // MM x K  (written by cr_kernel)
+  static constexpr int OFF_GU = OFF_G + M::M * M::K;                  // MM x NX
+  static constexpr int SIZE = OFF_GU + M::M * M::NX;
+};
+
+struct StridedOut {
+  double* p; long long stride;
+  DYB_D double& operator[](int e) const { return p[(long long)e * stride]; }
+};
+
+// ------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void __launch_bounds__(128)
+model_kernel(const SolveParams<M> prm, const double* __restrict__ theta, long long n_draws,
+             double* __restrict__ mid, int* __restrict__ status, double* __restrict__ ybar_out) {
+  constexpr int N = M::N, NX = M::NX, NY = M::NY;
+  using L = MidLayout<M>;
+  const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_draws) return;
+  const double* th = theta + d * (long long)prm.np;
+  double p[M::NPAR > 0 ? M::NPAR : 1];
+  double Se[NX * NX];
+  double Sm[NY * NY];
+#pragma unroll
+  for (int i = 0; i < M::NPAR; ++i) p[i] = prm.params0[i];
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) Se[i] = prm.sigma_e0[i];
+#pragma unroll
+  for (int i = 0; i < NY * NY; ++i) Sm[i] = prm.sigma_m0[i];
+  for (int q = 0; q < prm.np; ++q) {
+    const double v = th[q];
+    const int ty = prm.est_type[q], i = prm.est_i[q], j = prm.est_j[q];
+    // compile-time indexed stores (keeps p / Se / Sm in registers)
+    if (ty == EST_PARAM) {
+#pragma unroll
+      for (int a = 0; a < M::NPAR; ++a) if (a == i) p[a] = v;
+    } else if (ty == EST_SD_SHOCK || ty == EST_VAR_SHOCK) {
+      const double x = (ty == EST_SD_SHOCK) ? v * v : v;
+#pragma unroll
+      for (int a = 0; a < NX * NX; ++a) if (a == i + NX * j) Se[a] = x;
+    } else if (ty == EST_CORR_SHOCK) {
+      double vi = 0.0, vj = 0.0;
+#pragma unroll
+      for (int a = 0; a < NX; ++a) { if (a == i) vi = Se[a + NX * a]; if (a == j) vj = Se[a + NX * a]; }
+      const double c = v * sqrt(vi * vj);
+#pragma unroll
+      for (int a = 0; a < NX * NX; ++a) if (a == i + NX * j || a == j + NX * i) Se[a] = c;
+    } else if (ty == EST_SD_MEAS || ty == EST_VAR_MEAS) {
+      const double x = (ty == EST_SD_MEAS) ? v * v : v;
+#pragma unroll
+      for (int a = 0; a < NY * NY; ++a) if (a == i + NY * j) Sm[a] = x;
+    } else if (ty == EST_CORR_MEAS) {
+      double vi = 0.0, vj = 0.0;
+#pragma unroll
+      for (int a = 0; a < NY; ++a) { if (a == i) vi = Sm[a + NY * a]; if (a == j) vj = Sm[a + NY * a]; }
+      const double c = v * sqrt(vi * vj);
+#pragma unroll
+      for (int a = 0; a < NY * NY; ++a) if (a == i + NY * j || a == j + NY * i) Sm[a] = c;
+    }
+  }
+  double y[N];
+  M::steady_state(p, y);
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < N; ++i) ok = ok && isfinite(y[i]);
+  if (ybar_out) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) ybar_out[d * N + i] = y[i];
+  }
+  if (ok) {
+    const double r2 = M::static_resid_ss(p, y);
+    ok = (r2 <= prm.steady_tol * prm.steady_tol);
+  }
+  int st = ok ? ST_OK : ST_STEADY;
+  StridedOut out{mid + d, n_draws};
+  if (ok) {
+    double buf[M::RED_NNZ + M::TOP_NNZ];
+    const bool nonsing = M::static_elim(p, y, buf);
+    double chk = 0.0;
+#pragma unroll
+    for (int e = 0; e < M::RED_NNZ + M::TOP_NNZ; ++e) { chk = fma(buf[e], 0.0, chk); out[L::OFF_RED + e] = buf[e]; }
+    if (!(chk == 0.0)) st = ST_STEADY;            // NaN / Inf in the Jacobian
+    else if (!nonsing) st = ST_SOLVER;
+  }
+#pragma unroll
+  for (int i = 0; i < NY; ++i) out[L::OFF_YB + i] = y[M::state_ids(M::obs_idx_state(i))];
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) out[L::OFF_SE + i] = Se[i];
+#pragma unroll
+  for (int i = 0; i < NY; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) out[L::OFF_H + tri(i, j)] = Sm[i + NY * j];
+  status[d] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cyclic reduction, G lanes per draw
+// ------------------------------------------------------------------------------------------------
+template <int G>
+DYB_D double gshfl(unsigned mask, double v, int src) { return __shfl_sync(mask, v, src, G); }
+
+template <int G>
+DYB_D double gmax(unsigned mask, double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o, G));
+  return v;
+}
+
+// Householder QR of the MM x MM matrix distributed in A (column c in lane c % G, slot c / G) applied on
+// the fly to NR slots of right-hand-side columns B, followed by backward elimination:  B <- A^-1 B.
+// Every register index is a compile-time constant.  Returns false on an exactly singular / non-finite column.
+template <int MM, int G, int NR>
+DYB_D bool qr_solve(double (&A)[(MM + G - 1) / G][MM], double (&B)[NR][MM], int lg, unsigned mask) {
+  constexpr int SL = (MM + G - 1) / G;
+  double rinv[MM];
+  bool ok = true;
+#pragma unroll
+  for (int p = 0; p < MM; ++p) {
+    double x[MM];
+#pragma unroll
+    for (int r = p; r < MM; ++r) x[r] = gshfl<G>(mask, A[p / G][r], p % G);
+    double sg = 0.0;
+#pragma unroll
+    for (int r = p + 1; r < MM; ++r) sg = fma(x[r], x[r], sg);
+    const double s = fma(x[p], x[p], sg);
+    ok = ok && (s > 0.0) && (s < 1e300);
+    const double rn = rsqrt(s);
+    const double nrm = s * rn;
+    const double alpha = x[p] >= 0.0 ? -nrm : nrm;
+    const double vp = x[p] - alpha;
+    const double beta = 1.0 / (-alpha * vp);
+    rinv[p] = x[p] >= 0.0 ? -rn : rn;
+#pragma unroll
+    for (int sl = p / G; sl < SL; ++sl) {
+      const int col = sl * G + lg;
+      if (col > p) {
+        double dt = vp * A[sl][p];
+#pragma unroll
+        for (int r = p + 1; r < MM; ++r) dt = fma(x[r], A[sl][r], dt);
+        dt *= beta;
+        A[sl][p] = fma(-dt, vp, A[sl][p]);
+#pragma unroll
+        for (int r = p + 1; r < MM; ++r) A[sl][r] = fma(-dt, x[r], A[sl][r]);
+      }
+    }
+#pragma unroll
+    for (int sl = 0; sl < NR; ++sl) {
+      double dt = vp * B[sl][p];
+#pragma unroll
+      for (int r = p + 1; r < MM; ++r) dt = fma(x[r], B[sl][r], dt);
+      dt *= beta;
+      B[sl][p] = fma(-dt, vp, B[sl][p]);
+#pragma unroll
+      for (int r = p + 1; r < MM; ++r) B[sl][r] = fma(-dt, x[r], B[sl][r]);
+    }
+  }
+#pragma unroll
+  for (int p = MM - 1; p >= 0; --p) {
+    double rc[MM];
+#pragma unroll
+    for (int r = 0; r < p; ++r) rc[r] = gshfl<G>(mask, A[p / G][r], p % G);
+#pragma unroll
+    for (int sl = 0; sl < NR; ++sl) {
+      const double yp = B[sl][p] * rinv[p];
+      B[sl][p] = yp;
+#pragma unroll
+      for (int r = 0; r < p; ++r) B[sl][r] = fma(-rc[r], yp, B[sl][r]);
+    }
+  }
+  return ok;
+}
+
+struct CrOptions { double cr_tol; int cr_maxit; };
+
+template <class M, int G>
+__global__ void __launch_bounds__(128)
+cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
+          int* __restrict__ status, int* __restrict__ cr_iters) {
+  constexpr int MM = M::M, K = M::K, NF = M::NF, NX = M::NX;
+  constexpr int SL1 = (MM + G - 1) / G, SL0 = (K + G - 1) / G, SL2 = (NF + G - 1) / G, SLU = (NX + G - 1) / G;
+  constexpr int NR = SL0 + SL2;
+  constexpr int GROUPS = 128 / G;
+  constexpr int TILE = MM * MM + MM * K;          // per group: A1 (current) | acc_hat
+  using L = MidLayout<M>;
+  __shared__ double tile[GROUPS * TILE];
+
+  const int lane = threadIdx.x & 31;
+  const int lg = threadIdx.x % G;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const bool real = d < n_draws;
+  if (!real) d = n_draws - 1;                       // tail groups recompute the last draw and store nothing
+  double* A1s = tile + (threadIdx.x / G) * TILE;
+  double* accs = A1s + MM * MM;
+  const double* md = mid + d;
+  const long long st = n_draws;
+  const int st_in = status[d];
+
+  // distributed registers
+  double A1w[SL1][MM], A0[SL0][MM], A2[SL2][MM], XB[NR][MM];
+#pragma unroll
+  for (int s = 0; s < SL1; ++s)
+#pragma unroll
+    for (int r = 0; r < MM; ++r) A1w[s][r] = 0.0;
+#pragma unroll
+  for (int s = 0; s < SL0; ++s)
+#pragma unroll
+    for (int r = 0; r < MM; ++r) A0[s][r] = 0.0;
+#pragma unroll
+  for (int s = 0; s < SL2; ++s)
+#pragma unroll
+    for (int r = 0; r < MM; ++r) A2[s][r] = 0.0;
+
+  auto load_blocks = [&](bool neg_a0) {
+#pragma unroll
+    for (int e = 0; e < M::RED_NNZ; ++e) {
+      const int rr = M::red_row(e), c = M::red_col(e);
+      if (c < K) {
+        if (lg == c % G) A0[c / G][rr] = neg_a0 ? -md[(L::OFF_RED + e) * st] : md[(L::OFF_RED + e) * st];
+      } else if (c < K + MM) {
+        if (lg == (c - K) % G) A1w[(c - K) / G][rr] = md[(L::OFF_RED + e) * st];
+      } else if (c < K + MM + NF) {
+        if (lg == (c - K - MM) % G) A2[(c - K - MM) / G][rr] = md[(L::OFF_RED + e) * st];
+      }
+    }
+  };
+  load_blocks(false);
+
+  // own columns of A1 into the shared tile; acc_hat = 0
+  auto store_a1 = [&]() {
+#pragma unroll
+    for (int s = 0; s < SL1; ++s) {
+      const int col = s * G + lg;
+      if (col < MM) {
+#pragma unroll
+        for (int r = 0; r < MM; ++r) A1s[r + MM * col] = A1w[s][r];
+      }
+    }
+  };
+  store_a1();
+#pragma unroll
+  for (int s = 0; s < SL0; ++s) {
+    const int col = s * G + lg;
+    if (col < K) {
+#pragma unroll
+      for (int r = 0; r < MM; ++r) accs[r + MM * col] = 0.0;
+    }
+  }
+  __syncwarp(mask);
+
+  int it = 0;
+  int result = st_in;                 // draws that already failed skip the iteration
+  bool conv = false, stalled = false;
+  double n0 = 0.0, n2 = 0.0;
+  if (st_in == ST_OK) {
+    for (it = 1; it <= opt.cr_maxit; ++it) {
+      // [X0 | X2] = A1^-1 [A0 | A2]
+#pragma unroll
+      for (int s = 0; s < SL0; ++s)
+#pragma unroll
+        for (int r = 0; r < MM; ++r) XB[s][r] = A0[s][r];
+#pragma unroll
+      for (int s = 0; s < SL2; ++s)
+#pragma unroll
+        for (int r = 0; r < MM; ++r) XB[SL0 + s][r] = A2[s][r];
+      const bool okq = qr_solve<MM, G, NR>(A1w, XB, lg, mask);
+      if (!okq) { if (it == 1) result = ST_SOLVER; else stalled = true; break; }
+
+      // pass 1: columns of A0 broadcast; own columns j of [W00 | W01] = A0 * X[bk, j]
+      double acc[NR][MM];
+#pragma unroll
+      for (int s = 0; s < NR; ++s)
+#pragma unroll
+        for (int r = 0; r < MM; ++r) acc[s][r] = 0.0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        double a[MM];
+#pragma unroll
+        for (int r = 0; r < MM; ++r) a[r] = gshfl<G>(mask, A0[i / G][r], i % G);
+#pragma unroll
+        for (int s = 0; s < NR; ++s) {
+          const double xv = XB[s][M::bkwrd_in_dyn(i)];
+#pragma unroll
+          for (int r = 0; r < MM; ++r) acc[s][r] = fma(a[r], xv, acc[s][r]);
+        }
+      }
+      // A0 <- -W00 (own columns) ; A1[:, fw(j)] -= W01[:, j]
+      double m0 = 0.0;
+#pragma unroll
+      for (int s = 0; s < SL0; ++s) {
+        double cs = 0.0;
+#pragma unroll
+        for (int r = 0; r < MM; ++r) { A0[s][r] = -acc[s][r]; cs += fabs(acc[s][r]); }
+        m0 = fmax(m0, cs);
+      }
+#pragma unroll
+      for (int s = 0; s < SL2; ++s) {
+        const int col = s * G + lg;
+        if (col < NF) {
+          const int tc = M::fwrd_in_dyn(col);
+#pragma unroll
+          for (int r = 0; r < MM; ++r) A1s[r + MM * tc] -= acc[SL0 + s][r];
+        }
+      }
+      __syncwarp(mask);
+      // pass 2: columns of A2 broadcast; own columns j of [W10 | W11] = A2 * X[fw, j]
+#pragma unroll
+      for (int s = 0; s < NR; ++s)
+#pragma unroll
+        for (int r = 0; r < MM; ++r) acc[s][r] = 0.0;
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        double a[MM];
+#pragma unroll
+        for (int r = 0; r < MM; ++r) a[r] = gshfl<G>(mask, A2[i / G][r], i % G);
+#pragma unroll
+        for (int s = 0; s < NR; ++s) {
+          const double xv = XB[s][M::fwrd_in_dyn(i)];
+#pragma unroll
+          for (int r = 0; r < MM; ++r) acc[s][r] = fma(a[r], xv, acc[s][r]);
+        }
+      }
+      double m2 = 0.0;
+#pragma unroll
+      for (int s = 0; s < SL2; ++s) {
+        double cs = 0.0;
+#pragma unroll
+        for (int r = 0; r < MM; ++r) { A2[s][r] = -acc[SL0 + s][r]; cs += fabs(acc[SL0 + s][r]); }
+        m2 = fmax(m2, cs);
+      }
+#pragma unroll
+      for (int s = 0; s < SL0; ++s) {
+        const int col = s * G + lg;
+        if (col < K) {
+          const int tc = M::bkwrd_in_dyn(col);
+#pragma unroll
+          for (int r = 0; r < MM; ++r) { A1s[r + MM * tc] -= acc[s][r]; accs[r + MM * col] += acc[s][r]; }
+        }
+      }
+      __syncwarp(mask);
+      // next A1 into registers
+#pragma unroll
+      for (int s = 0; s < SL1; ++s) {
+        const int col = s * G + lg;
+#pragma unroll
+        for (int r = 0; r < MM; ++r) A1w[s][r] = (col < MM) ? A1s[r + MM * col] : 0.0;
+      }
+      m0 = gmax<G>(mask, m0);
+      m2 = gmax<G>(mask, m2);
+      if (!(m0 <= 1e150) || !(m2 <= 1e150)) { if (it == 1) result = ST_SOLVER; else stalled = true; break; }
+      n0 = m0; n2 = m2;
+      if (n0 < opt.cr_tol && n2 < opt.cr_tol) { conv = true; break; }
+    }
+    if (result == ST_OK && !conv) {
+      // Blanchard-Kahn reading of a reduction that does not converge (see solve_kernel.cuh)
+      if (stalled) result = (n0 < n2) ? ST_INDETERMINATE : ST_UNSTABLE;
+      else result = (n0 >= opt.cr_tol) ? ST_UNSTABLE : ST_INDETERMINATE;
+    }
+  }
+  __syncwarp(mask);
+
+  if (result == ST_OK) {
+    // ---- G (dynamic rows, backward columns) = -(A1(0) - acc_hat)^-1 A0(0) -----------------------------
+#pragma unroll
+    for (int s = 0; s < SL1; ++s)
+#pragma unroll
+      for (int r = 0; r < MM; ++r) A1w[s][r] = 0.0;
+#pragma unroll
+    for (int s = 0; s < SL0; ++s)
+#pragma unroll
+      for (int r = 0; r < MM; ++r) A0[s][r] = 0.0;
+#pragma unroll
+    for (int s = 0; s < SL2; ++s)
+#pragma unroll
+      for (int r = 0; r < MM; ++r) A2[s][r] = 0.0;
+    load_blocks(true);                               // A0 <- -A0(0), A1w <- A1(0), A2 <- A2(0)
+    store_a1();                                      // A1s <- A1(0)
+    __syncwarp(mask);
+#pragma unroll
+    for (int s = 0; s < SL0; ++s) {
+      const int col = s * G + lg;
+      if (col < K) {
+        const int tc = M::bkwrd_in_dyn(col);
+#pragma unroll
+        for (int r = 0; r < MM; ++r) A1s[r + MM * tc] -= accs[r + MM * col];
+      }
+    }
+    __syncwarp(mask);
+    double A1h[SL1][MM];
+#pragma unroll
+    for (int s = 0; s < SL1; ++s) {
+      const int col = s * G + lg;
+#pragma unroll
+      for (int r = 0; r < MM; ++r) A1h[s][r] = (col < MM) ? A1s[r + MM * col] : 0.0;
+    }
+    bool okq = qr_solve<MM, G, SL0>(A1h, A0, lg, mask);       // A0 now holds G's own columns
+    // ---- g_u = -(A1(0) + A2(0) G[fw, :])^-1 F_u ---------------------------------------------------------
+    double w[SL0][MM];
+#pragma unroll
+    for (int s = 0; s < SL0; ++s)
+#pragma unroll
+      for (int r = 0; r < MM; ++r) w[s][r] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      double a[MM];
+#pragma unroll
+      for (int r = 0; r < MM; ++r) a[r] = gshfl<G>(mask, A2[i / G][r], i % G);
+#pragma unroll
+      for (int s = 0; s < SL0; ++s) {
+        const double xv = A0[s][M::fwrd_in_dyn(i)];
+#pragma unroll
+        for (int r = 0; r < MM; ++r) w[s][r] = fma(a[r], xv, w[s][r]);
+      }
+    }
+    __syncwarp(mask);
+    // A1w still holds A1(0) (qr_solve above worked on A1h)
+    store_a1();
+    __syncwarp(mask);
+#pragma unroll
+    for (int s = 0; s < SL0; ++s) {
+      const int col = s * G + lg;
+      if (col < K) {
+        const int tc = M::bkwrd_in_dyn(col);
+#pragma unroll
+        for (int r = 0; r < MM; ++r) A1s[r + MM * tc] += w[s][r];
+      }
+    }
+    __syncwarp(mask);
+#pragma unroll
+    for (int s = 0; s < SL1; ++s) {
+      const int col = s * G + lg;
+#pragma unroll
+      for (int r = 0; r < MM; ++r) A1h[s][r] = (col < MM) ? A1s[r + MM * col] : 0.0;
+    }
+    double U[SLU][MM];
+#pragma unroll
+    for (int s = 0; s < SLU; ++s)
+#pragma unroll
+      for (int r = 0; r < MM; ++r) U[s][r] = 0.0;
+#pragma unroll
+    for (int e = 0; e < M::RED_NNZ; ++e) {
+      const int rr = M::red_row(e), c = M::red_col(e);
+      if (c >= K + MM + NF) {
+        const int cu = c - K - MM - NF;
+        if (lg == cu % G) U[cu / G][rr] = -md[(L::OFF_RED + e) * st];
+      }
+    }
+    okq = qr_solve<MM, G, SLU>(A1h, U, lg, mask) && okq;
+    if (!okq) result = ST_SOLVER;
+    if (real && okq) {
+#pragma unroll
+      for (int s = 0; s < SL0; ++s) {
+        const int col = s * G + lg;
+        if (col < K) {
+#pragma unroll
+          for (int r = 0; r < MM; ++r) mid[(L::OFF_G + r + MM * col) * st + d] = A0[s][r];
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < SLU; ++s) {
+        const int col = s * G + lg;
+        if (col < NX) {
+#pragma unroll
+          for (int r = 0; r < MM; ++r) mid[(L::OFF_GU + r + MM * col) * st + d] = U[s][r];
+        }
+      }
+    }
+  }
+  if (real && lg == 0) {
+    status[d] = result;
+    if (cr_iters) cr_iters[d] = it;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void __launch_bounds__(128)
+assemble_kernel(const double* __restrict__ mid, long long n_draws, double lyap_tol, int lyap_maxit,
+                double* __restrict__ ss, int* __restrict__ status, double* __restrict__ g1_out,
+                int* __restrict__ lyap_iters) {
+  constexpr int N = M::N, NX = M::NX, K = M::K, NF = M::NF, S = M::S, MM = M::M;
+  constexpr int NS = M::NS, NY = M::NY;
+  constexpr int cC = S, cB = S + K, cA = S + K + MM, cU = S + K + MM + NF;
+  using L = SSLayout<M>;
+  using ML = MidLayout<M>;
+  const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_draws) return;
+  if (status[d] != ST_OK) return;
+  const double* md = mid + d;
+  const long long st = n_draws;
+
+  double Gd[MM * K], gud[MM * NX], Se[NX * NX];
+#pragma unroll
+  for (int i = 0; i < MM * K; ++i) Gd[i] = md[(ML::OFF_G + i) * st];
+#pragma unroll
+  for (int i = 0; i < MM * NX; ++i) gud[i] = md[(ML::OFF_GU + i) * st];
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) Se[i] = md[(ML::OFF_SE + i) * st];
+
+  // ---- static rows: R_s y_s = -(C_top + B_top G + A_top G[fw,:] G[bk,:]) etc., sparse pivot rows -------
+  double gst[(S > 0 ? S : 1) * (K + NX)];
+  bool ok = true;
+  if (S > 0) {
+    double GG[NF * (K + NX)];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < K; ++q) s = fma(Gd[M::fwrd_in_dyn(i) + MM * q], Gd[M::bkwrd_in_dyn(q) + MM * j], s);
+        GG[i + NF * j] = s;
+      }
+#pragma unroll
+      for (int e = 0; e < NX; ++e) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < K; ++q) s = fma(Gd[M::fwrd_in_dyn(i) + MM * q], gud[M::bkwrd_in_dyn(q) + MM * e], s);
+        GG[i + NF * (K + e)] = s;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < S * (K + NX); ++i) gst[i] = 0.0;
+    double rdiag[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) rdiag[q] = 0.0;
+    // accumulate the right-hand sides from the non-static entries of the pivot rows
+#pragma unroll
+    for (int e = 0; e < M::TOP_NNZ; ++e) {
+      const int q = M::top_row(e), c = M::top_col(e);
+      const double v = md[(ML::OFF_TOP + e) * st];
+      if (c < S) {
+        if (c == q) rdiag[q] = v;
+      } else if (c < cB) {
+        gst[q + S * (c - cC)] -= v;
+      } else if (c < cA) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) gst[q + S * j] = fma(-v, Gd[(c - cB) + MM * j], gst[q + S * j]);
+#pragma unroll
+        for (int x = 0; x < NX; ++x) gst[q + S * (K + x)] = fma(-v, gud[(c - cB) + MM * x], gst[q + S * (K + x)]);
+      } else if (c < cU) {
+#pragma unroll
+        for (int j = 0; j < K + NX; ++j) gst[q + S * j] = fma(-v, GG[(c - cA) + NF * j], gst[q + S * j]);
+      } else {
+        gst[q + S * (K + (c - cU))] -= v;
+      }
+    }
+    // back-substitution with the upper-triangular R_s (entries c > q of the pivot rows), last row first
+#pragma unroll
+    for (int q = S - 1; q >= 0; --q) {
+#pragma unroll
+      for (int e = 0; e < M::TOP_NNZ; ++e) {
+        if (M::top_row(e) == q && M::top_col(e) > q && M::top_col(e) < S) {
+          const double v = md[(ML::OFF_TOP + e) * st];
+#pragma unroll
+          for (int j = 0; j < K + NX; ++j) gst[q + S * j] = fma(-v, gst[M::top_col(e) + S * j], gst[q + S * j]);
+        }
+      }
+      ok = ok && (rdiag[q] != 0.0);
+      const double inv = 1.0 / rdiag[q];
+#pragma unroll
+      for (int j = 0; j < K + NX; ++j) gst[q + S * j] *= inv;
+    }
+  }
+  if (!ok) { status[d] = ST_SOLVER; return; }
+  if (g1_out) {
+    double* g1 = g1_out + d * (long long)(N * (K + NX));
+#pragma unroll
+    for (int c = 0; c < K + NX; ++c)
+#pragma unroll
+      for (int v = 0; v < N; ++v) {
+        const int pos = M::var_pos(v);
+        double val;
+        if (M::var_static(v)) val = gst[pos + S * c];
+        else val = (c < K) ? Gd[pos + MM * c] : gud[pos + MM * (c - K)];
+        g1[v + N * c] = val;
+      }
+  }
+
+  // ---- Lyapunov doubling on the K x K predetermined block ---------------------------------------------
+  double Ak[K * K], Sg[K * K], Tm[K * K];
+  {
+    double Bs[K * NX], BQ[K * NX];
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int i = 0; i < K; ++i) Ak[i + K * j] = Gd[M::bkwrd_in_dyn(i) + MM * j];
+#pragma unroll
+    for (int e = 0; e < NX; ++e)
+#pragma unroll
+      for (int i = 0; i < K; ++i) Bs[i + K * e] = gud[M::bkwrd_in_dyn(i) + MM * e];
+#pragma unroll
+    for (int e = 0; e < NX; ++e)
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int f = 0; f < NX; ++f) s = fma(Bs[i + K * f], Se[f + NX * e], s);
+        BQ[i + K * e] = s;
+      }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int e = 0; e < NX; ++e) s = fma(BQ[i + K * e], Bs[j + K * e], s);
+        Sg[i + K * j] = s;
+      }
+  }
+  bool lconv = false;
+  int li_done = 0;
+  for (int li = 0; li < lyap_maxit; ++li) {
+    li_done = li + 1;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < K; ++q) s = fma(Ak[i + K * q], Sg[q + K * j], s);
+        Tm[i + K * j] = s;
+      }
+    double dmax = 0.0, smax = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < K; ++q) s = fma(Tm[i + K * q], Ak[j + K * q], s);
+        dmax = fmax(dmax, fabs(s));
+        const double v = Sg[i + K * j] + s;
+        Sg[i + K * j] = v;
+        smax = fmax(smax, fabs(v));
+      }
+    if (!isfinite(smax)) break;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < K; ++q) s = fma(Ak[i + K * q], Ak[q + K * j], s);
+        Tm[i + K * j] = s;
+      }
+    double amax = 0.0;
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) { Ak[i] = Tm[i]; amax = fmax(amax, fabs(Tm[i])); }
+    if (dmax <= lyap_tol * smax && amax < 1.0) { lconv = true; break; }
+    if (!isfinite(amax)) break;
+  }
+  if (lyap_iters) lyap_iters[d] = li_done;
+  if (!lconv) { status[d] = ST_NONSTATIONARY; return; }
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+#pragma unroll
+    for (int i = j + 1; i < K; ++i) {
+      const double v = 0.5 * (Sg[i + K * j] + Sg[j + K * i]);
+      Sg[i + K * j] = v; Sg[j + K * i] = v;
+    }
+
+  // ---- state-space assembly (estimation.jl:640-658) ---------------------------------------------------
+  double* so = ss + d;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int v = M::state_ids(s);
+    const int pos = M::var_pos(v);
+    double g1r[K], g2r[NX];
+#pragma unroll
+    for (int j = 0; j < K; ++j) g1r[j] = M::var_static(v) ? gst[pos + S * j] : Gd[pos + MM * j];
+#pragma unroll
+    for (int e = 0; e < NX; ++e) g2r[e] = M::var_static(v) ? gst[pos + S * (K + e)] : gud[pos + MM * e];
+    double rq[NX], gs[K];
+#pragma unroll
+    for (int e = 0; e < NX; ++e) {
+      double a = 0.0;
+#pragma unroll
+      for (int f = 0; f < NX; ++f) a = fma(g2r[f], Se[f + NX * e], a);
+      rq[e] = a;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      double a = 0.0;
+#pragma unroll
+      for (int q = 0; q < K; ++q) a = fma(g1r[q], Sg[q + K * j], a);
+      gs[j] = a;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) so[(L::OFF_T + s * K + j) * st] = g1r[j];
+#pragma unroll
+    for (int t = 0; t <= s; ++t) {
+      const int v2 = M::state_ids(t);
+      const int pos2 = M::var_pos(v2);
+      double qq = 0.0;
+#pragma unroll
+      for (int e = 0; e < NX; ++e) qq = fma(rq[e], M::var_static(v2) ? gst[pos2 + S * (K + e)] : gud[pos2 + MM * e], qq);
+      double pp = qq;
+#pragma unroll
+      for (int j = 0; j < K; ++j) pp = fma(gs[j], M::var_static(v2) ? gst[pos2 + S * j] : Gd[pos2 + MM * j], pp);
+      so[(L::OFF_QQ + tri(s, t)) * st] = qq;
+      so[(L::OFF_P0 + tri(s, t)) * st] = pp;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NY; ++i) so[(L::OFF_YB + i) * st] = md[(ML::OFF_YB + i) * st];
+#pragma unroll
+  for (int i = 0; i < NY * (NY + 1) / 2; ++i) so[(L::OFF_H + i) * st] = md[(ML::OFF_H + i) * st];
+}
+
+}  // namespace dyb

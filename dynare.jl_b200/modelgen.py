@@ -457,6 +457,115 @@ def _dbl_list(v) -> str:
     return "{" + ", ".join(repr(x) if np.isfinite(x) else "0.0" for x in v) + "}" if v else "{0.0}"
 
 
+
+def plan_static_elim(S: ModelSpec, jperm):
+    """Symbolic phase of the static elimination (reference: LRE ``remove_static!``, QR on the static
+    columns): Householder reflectors restricted to the structurally non-zero rows, pivot rows chosen
+    for least fill.  Zero entries contribute nothing to a reflector, so this is numerically the dense
+    Householder QR of a row-permuted Jacobian; only the operation list is specialised to the model.
+    Returns (initial pattern dict (r,c)->jac position, steps, pivot rows, remaining rows, final pattern)."""
+    n, ncol, s = S.n, S.ncol, S.s
+    keys = sorted(S.jac.keys(), key=lambda rc: (rc[1], rc[0]))
+    pat = np.zeros((n, ncol), dtype=bool)
+    init = {}
+    for pos, (r, c) in enumerate(keys):
+        pat[r, jperm[c]] = True
+        init[(r, jperm[c])] = pos
+    used, steps = [], []
+    for j in range(s):
+        cand = [r for r in range(n) if r not in used and pat[r, j]]
+        if not cand:
+            raise ValueError(f"{S.name}: static block structurally singular at column {j}")
+        piv = min(cand, key=lambda r: (int(pat[r].sum()), r))
+        rows = [piv] + [r for r in cand if r != piv]
+        used.append(piv)
+        cols = []
+        if len(rows) > 1:
+            for c in range(j + 1, ncol):
+                nzr = [r for r in rows if pat[r, c]]
+                if nzr:
+                    cols.append((c, nzr))
+                    pat[rows, c] = True
+            pat[rows[1:], j] = False
+        steps.append((j, rows, cols))
+    rest = [r for r in range(n) if r not in used]
+    return init, steps, used, rest, pat
+
+
+def _emit_static_elim(S: ModelSpec, jperm, jac_lines, jac_out, A, arr):
+    n, ncol, s = S.n, S.ncol, S.s
+    init, steps, used, rest, pat = plan_static_elim(S, jperm)
+    red = [(rr, c - s) for rr, r in enumerate(rest) for c in range(s, ncol) if pat[r, c]]
+    top = [(q, c) for q, r in enumerate(used) for c in range(ncol) if pat[r, c]]
+    A("")
+    A("  // ---- structure-aware static elimination (symbolic phase done at model set-up) ----------------")
+    A("  // Householder QR on the static columns restricted to structurally non-zero rows; outputs the")
+    A("  // non-zeros of the reduced (dynamic) system, rows = remaining equations, columns [lags | dyn | leads | shocks],")
+    A("  // then of the S pivot rows [R_s | lags | dyn | leads | shocks] used to recover the static variables.")
+    A(f"  static constexpr int RED_NNZ = {len(red)};")
+    A(f"  static constexpr int TOP_NNZ = {len(top)};")
+    arr("red_row", [r for r, _ in red])
+    arr("red_col", [c for _, c in red])
+    arr("top_row", [r for r, _ in top])
+    arr("top_col", [c for _, c in top])
+    A("  template <class OT>")
+    A("  DYB_HD static bool static_elim(const double* __restrict__ p, const double* __restrict__ y, OT& out) {")
+    for nm, ex, _ in jac_lines:
+        A(f"    const double {nm} = {ex};")
+    keys = sorted(S.jac.keys(), key=lambda rc: (rc[1], rc[0]))
+    expr_of = {(r, jperm[c]): ex for (r, c), (_, _, ex) in zip(keys, jac_out)}
+    live = set()
+    for (r, c), ex in sorted(expr_of.items(), key=lambda kv: (kv[0][1], kv[0][0])):
+        A(f"    double w_{r}_{c} = {ex};")
+        live.add((r, c))
+    fill = set()
+    for j, rows, cols in steps:
+        for c, nzr in cols:
+            for r in rows:
+                if (r, c) not in live:
+                    fill.add((r, c))
+        if len(rows) > 1 and (rows[0], j) not in live:
+            fill.add((rows[0], j))
+    for (r, c) in sorted(fill, key=lambda rc: (rc[1], rc[0])):
+        A(f"    double w_{r}_{c} = 0.0;   // fill-in")
+    live |= fill
+    A("    bool ok = true;")
+    nfma = 0
+    for j, rows, cols in steps:
+        if len(rows) == 1:
+            continue
+        piv, oth = rows[0], rows[1:]
+        A(f"    {{  // static column {j}: reflector over equations {rows}")
+        A("      const double s2 = " + " + ".join(f"w_{r}_{j}*w_{r}_{j}" for r in oth) + ";")
+        A(f"      const double xp = w_{piv}_{j};")
+        A("      const double sn = fma(xp, xp, s2);")
+        A("      ok = ok && (sn > 0.0);")
+        A("      const double nrm = sqrt(sn);")
+        A("      const double alpha = xp >= 0.0 ? -nrm : nrm;")
+        A("      const double vp = xp - alpha;")
+        A("      const double beta = 1.0 / (-alpha * vp);")
+        for c, nzr in cols:
+            terms = []
+            for r in nzr:
+                terms.append(f"vp*w_{r}_{c}" if r == piv else f"w_{r}_{j}*w_{r}_{c}")
+            A(f"      {{ const double dt = beta*({' + '.join(terms)});")
+            for r in rows:
+                coef = "vp" if r == piv else f"w_{r}_{j}"
+                A(f"        w_{r}_{c} = fma(-dt, {coef}, w_{r}_{c});")
+                nfma += 2
+            A("      }")
+            # declare fill-in variables before the block that assigns them
+        A(f"      w_{piv}_{j} = alpha;")
+        A("    }")
+    for e, (rr, c) in enumerate(red):
+        A(f"    out[{e}] = w_{rest[rr]}_{c + s};")
+    for e, (q, c) in enumerate(top):
+        A(f"    out[{len(red) + e}] = w_{used[q]}_{c};")
+    A("    return ok;")
+    A("  }")
+    A(f"  static constexpr int STATIC_ELIM_FMA = {nfma};")
+
+
 def emit_cuda(spec: ModelSpec) -> str:
     """CUDA header: a traits struct with compile-time sizes/index sets and the device model function."""
     ss_lines, res_lines, res_out, jac_lines, jac_out = _lower(spec)
@@ -539,6 +648,7 @@ def emit_cuda(spec: ModelSpec) -> str:
         A(f"    J[{r + S.n * c}] = {ex};")
     A("  }")
     A(f"  static constexpr int JAC_NNZ = {len(jac_out)};")
+    _emit_static_elim(S, jperm, jac_lines, jac_out, A, arr)
     A("};")
     A("}  // namespace dyb")
     return "\n".join(L) + "\n"

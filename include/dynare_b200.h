@@ -77,6 +77,7 @@ typedef struct dyb_options {
   double lyap_tol;          /* relative increment at which doubling stops (default 1e-16) */
   int32_t lyap_maxit;       /* (default 60) */
   int32_t presample;        /* periods excluded from the likelihood sum (default 0) */
+  int32_t solver;           /* 0 auto; 1 one thread per draw (any size); 2 cooperative register-resident (m <= 12) */
 } dyb_options;
 
 /* ---- library / registry ------------------------------------------------------------------- */

@@ -202,3 +202,24 @@ def test_pinned_host_buffers(golden, ws_factory):
     ll, st = ws.loglikelihood(pth.array, out=pll.array, status=pst.array)
     assert np.allclose(pll.array, g["loglik"], rtol=RTOL_LOGLIK, atol=0) and np.all(pst.array == 0)
     pth.free(); pll.free(); pst.free()
+
+
+@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+def test_solver_variants_agree(name, golden, ws_factory):
+    """solver = 1 (one thread per draw, pivoted LU) and solver = 2 (cooperative, Householder QR in registers)
+    are two implementations of the same stages; both must meet the oracle tolerances."""
+    g = golden(name)
+    ws = ws_factory(name, g["Y"])
+    res = {}
+    for variant in (1, 2):
+        ws.set_options(solver=variant)
+        ll, st = ws.loglikelihood(g["theta"])
+        fo = ws.first_order(g["theta"])
+        assert np.array_equal(st, g["status"])
+        assert np.max(np.abs(ll - g["loglik"]) / np.abs(g["loglik"])) <= RTOL_LOGLIK
+        g1 = np.concatenate([fo["g1_1"], fo["g1_2"]], axis=2)
+        assert np.abs(g1 - g["g1"]).max() <= ATOL_POLICY
+        res[variant] = (ll, fo["cr_iters"])
+    ws.set_options(solver=0)
+    assert np.array_equal(res[1][1], res[2][1])          # same number of cyclic-reduction iterations
+    assert np.max(np.abs(res[1][0] - res[2][0]) / np.abs(res[1][0])) <= 1e-9

@@ -221,5 +221,7 @@ def test_solver_variants_agree(name, golden, ws_factory):
         assert np.abs(g1 - g["g1"]).max() <= ATOL_POLICY
         res[variant] = (ll, fo["cr_iters"])
     ws.set_options(solver=0)
-    assert np.array_equal(res[1][1], res[2][1])          # same number of cyclic-reduction iterations
+    # same number of cyclic-reduction iterations up to rounding at the stopping threshold
+    assert np.max(np.abs(res[1][1].astype(int) - res[2][1].astype(int))) <= 1
+    assert np.mean(res[1][1] != res[2][1]) < 0.05
     assert np.max(np.abs(res[1][0] - res[2][0]) / np.abs(res[1][0])) <= 1e-9

@@ -20,8 +20,29 @@
 
 namespace dyb {
 
+// fast fp64 reciprocal square root: hardware seed (MUFU.RSQ64H, ~20 bits) + two Newton steps (<= 1 ulp for
+// normal inputs); callers guard non-positive / non-finite arguments separately
+DYB_D double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+
 template <class M>
-__global__ void __launch_bounds__(128)
+struct KalmanCfg {
+  static constexpr int BLOCK = 64;
+  // packed R Q R' goes to shared memory ([element][thread], conflict-free) to keep the register count low
+  // enough for 7 CTAs per SM (one wave for 65 536 draws on 148 SMs)
+  static constexpr int QQ_N = M::NS * (M::NS + 1) / 2;
+  static constexpr bool QQ_SMEM = (QQ_N * BLOCK * 8 <= 16 * 1024);
+  static constexpr int MIN_CTAS = QQ_SMEM ? 7 : 4;
+};
+
+template <class M>
+__global__ void __launch_bounds__(KalmanCfg<M>::BLOCK, KalmanCfg<M>::MIN_CTAS)
 kalman_kernel(const double* __restrict__ ss, long long n_draws,
               const double* __restrict__ Y,            // NY x nobs, column-major, NaN = missing
               int nobs, int presample,
@@ -29,8 +50,10 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
               double* __restrict__ loglik, int* __restrict__ status_out) {
   constexpr int NS = M::NS, K = M::K, NY = M::NY;
   using L = SSLayout<M>;
-  extern __shared__ double ysh[];                      // NY * nobs
+  using Cfg = KalmanCfg<M>;
+  extern __shared__ double ysh[];                      // NY * nobs, then (optionally) QQ_N * BLOCK
   for (int i = threadIdx.x; i < NY * nobs; i += blockDim.x) ysh[i] = Y[i];
+  double* qsh = ysh + NY * nobs + threadIdx.x;          // this thread's column of the R Q R' tile
   __syncthreads();
 
   const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -44,7 +67,7 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
   const long long st = n_draws;
 
   double Tl[NS * K];                      // row-major
-  double QQ[NS * (NS + 1) / 2];
+  double QQ[Cfg::QQ_SMEM ? 1 : NS * (NS + 1) / 2];
   double P[NS * (NS + 1) / 2];
   double a[NS];
   double yb[NY];
@@ -52,7 +75,11 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
 #pragma unroll
   for (int i = 0; i < NS * K; ++i) Tl[i] = s_[(L::OFF_T + i) * st];
 #pragma unroll
-  for (int i = 0; i < NS * (NS + 1) / 2; ++i) { QQ[i] = s_[(L::OFF_QQ + i) * st]; P[i] = s_[(L::OFF_P0 + i) * st]; }
+  for (int i = 0; i < NS * (NS + 1) / 2; ++i) {
+    const double q = s_[(L::OFF_QQ + i) * st];
+    if (Cfg::QQ_SMEM) qsh[i * Cfg::BLOCK] = q; else QQ[i] = q;
+    P[i] = s_[(L::OFF_P0 + i) * st];
+  }
 #pragma unroll
   for (int i = 0; i < NY; ++i) yb[i] = s_[(L::OFF_YB + i) * st];
 #pragma unroll
@@ -60,7 +87,7 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
 #pragma unroll
   for (int i = 0; i < NS; ++i) a[i] = 0.0;
 
-  double acc = 0.0;
+  double acc = 0.0, detp = 1.0;
   int nseen = 0;
   bool bad = false;
 
@@ -92,12 +119,11 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
       double djj = F[tri(j, j)];
 #pragma unroll
       for (int q = 0; q < j; ++q) djj = fma(-F[tri(j, q)], F[tri(j, q)], djj);
-      if (!(djj > 0.0)) bad = true;
+      if (!(djj > 0.0) || !(djj < 1e300)) bad = true;
       det *= djj;
-      const double ljj = sqrt(djj);
-      const double r = 1.0 / ljj;
+      const double r = fast_rsqrt(djj);
       rdiag[j] = r;
-      F[tri(j, j)] = ljj;
+      F[tri(j, j)] = djj * r;
 #pragma unroll
       for (int i = j + 1; i < NY; ++i) {
         double x = F[tri(i, j)];
@@ -117,7 +143,13 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
       w[i] = x * rdiag[i];
       quad = fma(w[i], w[i], quad);
     }
-    if (t >= presample) { acc += log(det) + quad; nseen += nobs_t; }
+    if (t >= presample) {
+      // sum_t log det F_t is accumulated as a running product, folded into the sum whenever it leaves a safe range
+      detp *= det;
+      if (!(detp > 1e-200 && detp < 1e200)) { acc += log(detp); detp = 1.0; }
+      acc += quad;
+      nseen += nobs_t;
+    }
     if (t == nobs - 1) break;
 
     // U = L^-1 (Z P)[:, lagged]   (NY x K)
@@ -165,13 +197,14 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
       }
 #pragma unroll
       for (int t2 = 0; t2 <= s; ++t2) {
-        double x2 = QQ[tri(s, t2)];
+        double x2 = Cfg::QQ_SMEM ? qsh[tri(s, t2) * Cfg::BLOCK] : QQ[tri(s, t2)];
 #pragma unroll
         for (int j = 0; j < K; ++j) x2 = fma(mrow[j], Tl[t2 * K + j], x2);
         P[tri(s, t2)] = x2;
       }
     }
   }
+  acc += log(detp);
   const double ll = -0.5 * (nseen * 1.8378770664093453 + acc);     // log(2 pi)
   if (bad || !isfinite(ll)) {
     loglik[d] = -INFINITY;

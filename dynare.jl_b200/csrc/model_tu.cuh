@@ -60,9 +60,10 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
 cudaError_t mt_kalman(const double* d_ss, long long n, const double* d_Y, int nobs, int presample,
                       const int* d_status_in, double* d_loglik, int* d_status_out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  const int block = 128;
+  using Cfg = KalmanCfg<MT>;
+  const int block = Cfg::BLOCK;
   const long long grid = (n + block - 1) / block;
-  const size_t smem = sizeof(double) * (size_t)MT::NY * (size_t)nobs;
+  const size_t smem = sizeof(double) * ((size_t)MT::NY * (size_t)nobs + (Cfg::QQ_SMEM ? (size_t)Cfg::QQ_N * block : 0));
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kalman_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -35,6 +35,14 @@ class Options(C.Structure):
                 ("solver", C.c_int32)]
 
 
+class SmcOptions(C.Structure):
+    _fields_ = [("npart", C.c_int64), ("nphi", C.c_int32), ("lam", C.c_double), ("c0", C.c_double),
+                ("acpt0", C.c_double), ("trgt", C.c_double), ("alp", C.c_double), ("resampling", C.c_int32),
+                ("seed", C.c_uint64)]
+
+
+COMM_ID_BYTES = 128
+
 _P = C.c_void_p
 _D = C.c_void_p      # double* (host or device address)
 _I32 = C.c_void_p
@@ -74,6 +82,28 @@ SIGNATURES = {
     "dyb_smc_resample_multinomial": (C.c_int, [C.c_int, _D, _D, C.c_int64, _I64, C.POINTER(C.c_int64)]),
     "dyb_smc_resample_systematic": (C.c_int, [C.c_int, _D, C.c_double, C.c_int64, _I64, C.POINTER(C.c_int64)]),
     "dyb_smc_moments": (C.c_int, [C.c_int, _D, _D, C.c_int64, C.c_int32, _D, _D]),
+    "dyb_set_priors": (C.c_int, [_P, C.c_int32, _I32, _D, _D]),
+    "dyb_logprior_batch": (C.c_int, [_P, _D, C.c_int64, _D]),
+    "dyb_logposterior_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D, _I32]),
+    "dyb_transform_batch": (C.c_int, [_P, _D, C.c_int64, C.c_int32, _D, _D]),
+    "dyb_rng_fill": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int32,
+                               C.c_int32, _D]),
+    "dyb_smc_default_options": (C.c_int, [C.POINTER(SmcOptions)]),
+    "dyb_smc_create": (C.c_int, [_P, C.POINTER(SmcOptions), _D, C.POINTER(_P)]),
+    "dyb_smc_destroy": (C.c_int, [_P]),
+    "dyb_smc_local_range": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dyb_smc_init": (C.c_int, [_P, _D, _I32]),
+    "dyb_smc_run": (C.c_int, [_P, C.c_int32]),
+    "dyb_smc_stages_done": (C.c_int, [_P]),
+    "dyb_smc_get_particles": (C.c_int, [_P, _D, _D, _D, _D]),
+    "dyb_smc_get_stats": (C.c_int, [_P, _D, _D, _D, C.POINTER(C.c_double)]),
+    "dyb_rwmh_run": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_uint32, C.c_int32, _D, C.c_uint64,
+                               _D, _D, _I64, _D, _D]),
+    "dyb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "dyb_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_void_p]),
+    "dyb_comm_destroy": (C.c_int, [_P]),
+    "dyb_comm_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "dyb_comm_allreduce_sum": (C.c_int, [_P, C.c_void_p, C.c_int64, C.c_int32]),
     "dyb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_int64]),
     "dyb_host_free": (C.c_int, [_P]),
 }

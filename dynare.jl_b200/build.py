@@ -16,7 +16,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 
 def sources():
-    return [os.path.join(CSRC, "api.cu")] + sorted(glob.glob(os.path.join(CSRC, "generated", "*.cu")))
+    return [os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "sampler.cu")] + sorted(glob.glob(os.path.join(CSRC, "generated", "*.cu")))
 
 
 def _deps():
@@ -47,7 +47,7 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

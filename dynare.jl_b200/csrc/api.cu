@@ -7,9 +7,8 @@
 #include <string>
 #include <vector>
 
-#include "registry.h"
+#include "internal.h"
 #include "kalman_generic.cuh"
-#include "smc_kernels.cuh"
 
 namespace dyb {
 
@@ -21,114 +20,9 @@ const std::vector<const ModelOps*>& registry() { return reg_mut(); }
 void register_model(const ModelOps* m) { reg_mut().push_back(m); }
 
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+std::string& last_error_ref() { return g_err; }
 
-#define DYB_CUDA(expr)                                                                      \
-  do {                                                                                      \
-    cudaError_t e_ = (expr);                                                                \
-    if (e_ != cudaSuccess)                                                                  \
-      return fail(DYB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
-  } while (0)
-
-static const ModelOps* find_model(const char* name) {
-  if (!name) return nullptr;
-  for (auto* m : registry()) if (std::strcmp(m->name, name) == 0) return m;
-  return nullptr;
-}
-
-static bool is_device_ptr(const void* p) {
-  if (!p) return false;
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
-static bool is_pinned_ptr(const void* p) {
-  if (!p) return false;
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeHost;
-}
-
-// growable device / pinned buffers
-struct DevBuf {
-  void* p = nullptr; size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    size_t want = bytes + bytes / 4;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-  template <class T> T* as() const { return static_cast<T*>(p); }
-};
-struct PinBuf {
-  void* p = nullptr; size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
-    size_t want = bytes + bytes / 4;
-    cudaError_t e = cudaMallocHost(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-  template <class T> T* as() const { return static_cast<T*>(p); }
-};
-
-// Per-call staging of arguments that may live on the host or on the device.
-struct Stager {
-  cudaStream_t st;
-  struct Back { void* host; void* dev; size_t bytes; };
-  std::vector<void*> temps;
-  std::vector<Back> backs;
-  cudaError_t err = cudaSuccess;
-  explicit Stager(cudaStream_t s) : st(s) {}
-  template <class T> const T* in(const T* p, size_t count) {
-    if (!p || is_device_ptr(p)) return p;
-    void* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, count * sizeof(T) + 8);
-    if (e != cudaSuccess) { err = e; return nullptr; }
-    temps.push_back(d);
-    e = cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) err = e;
-    return static_cast<const T*>(d);
-  }
-  template <class T> T* out(T* p, size_t count) {
-    if (!p || is_device_ptr(p)) return p;
-    void* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, count * sizeof(T) + 8);
-    if (e != cudaSuccess) { err = e; return nullptr; }
-    temps.push_back(d);
-    backs.push_back({p, d, count * sizeof(T)});
-    return static_cast<T*>(d);
-  }
-  template <class T> T* temp(size_t count) {
-    void* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, count * sizeof(T) + 8);
-    if (e != cudaSuccess) { err = e; return nullptr; }
-    temps.push_back(d);
-    return static_cast<T*>(d);
-  }
-  cudaError_t finish() {
-    cudaError_t e = err;
-    for (auto& b : backs) {
-      cudaError_t e2 = cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = e2;
-    }
-    cudaError_t e3 = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = e3;
-    for (void* t : temps) cudaFree(t);
-    temps.clear(); backs.clear();
-    return e;
-  }
-  ~Stager() { for (void* t : temps) cudaFree(t); }
-};
-
-static cudaStream_t device_stream(int device) {
+cudaStream_t device_stream(int device) {
   static std::mutex mu;
   static std::vector<cudaStream_t> streams;
   std::lock_guard<std::mutex> lk(mu);
@@ -140,23 +34,6 @@ static cudaStream_t device_stream(int device) {
 }  // namespace dyb
 
 using namespace dyb;
-
-struct dyb_handle {
-  const ModelOps* ops = nullptr;
-  int device = 0;
-  cudaStream_t stream = nullptr;        // stream in use
-  cudaStream_t own_stream = nullptr;    // the handle's private stream
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  bool ev_valid = false;
-  std::vector<cudaEvent_t> timer_ev;    // triples (start, after solve, after filter)
-  int timer_n = 0;
-  bool timers_armed = false;
-  HostState hs;
-  DevBuf d_theta, d_ss, d_st1, d_ll, d_st2, d_Y, d_mid;
-  PinBuf h_in, h_out;
-  int ny_obs = 0, nobs = 0;
-  int64_t launches = 0;
-};
 
 static void default_options(dyb_options* o) {
   o->cr_tol = 1e-8;
@@ -220,6 +97,7 @@ int dyb_destroy(dyb_handle* h) {
   if (!h) return DYB_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  comm_release(h);
   h->d_theta.release(); h->d_ss.release(); h->d_st1.release(); h->d_ll.release(); h->d_st2.release(); h->d_Y.release(); h->d_mid.release();
   h->h_in.release(); h->h_out.release();
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -562,97 +440,6 @@ int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t p
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   if (smem > 48 * 1024) DYB_CUDA(cudaFuncSetAttribute(kalman_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kalman_generic_kernel<<<(unsigned)grid, 256, smem, st>>>(g);
-  DYB_CUDA(cudaGetLastError());
-  DYB_CUDA(sg.finish());
-  return DYB_OK;
-}
-
-// ---- SMC -------------------------------------------------------------------------------------
-static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
-
-int dyb_smc_reweight(int device, const double* w, const double* loglh, double dphi, int64_t n,
-                     double* w_out, double* zhat, double* ess) {
-  if (n <= 0 || !w || !loglh || !w_out) return fail(DYB_ERR_ARG, "bad argument");
-  DYB_CUDA(cudaSetDevice(device));
-  cudaStream_t st = device_stream(device);
-  Stager sg(st);
-  const size_t N = (size_t)n;
-  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
-  const double* dw = sg.in(w, N);
-  const double* dl = sg.in(loglh, N);
-  double* dwo = sg.out(w_out, N);
-  double* wt = sg.temp<double>(N);
-  double* bt = sg.temp<double>((size_t)nb);
-  double* scal = sg.temp<double>(2);
-  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
-  smc_incweight_kernel<<<nblk(n, 256), 256, 0, st>>>(dw, dl, dphi, n, wt);
-  smc_block_sum_kernel<<<nblk(nb, 64), 64, 0, st>>>(wt, n, 0, bt);
-  smc_total_kernel<<<1, 32, 0, st>>>(bt, nb, scal);
-  smc_normalise_kernel<<<nblk(n, 256), 256, 0, st>>>(wt, scal, n, dwo);
-  smc_block_sum_kernel<<<nblk(nb, 64), 64, 0, st>>>(dwo, n, 1, bt);
-  smc_total_kernel<<<1, 32, 0, st>>>(bt, nb, scal + 1);
-  DYB_CUDA(cudaGetLastError());
-  double hs[2];
-  DYB_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
-  DYB_CUDA(sg.finish());
-  if (zhat) *zhat = hs[0];
-  if (ess) *ess = 1.0 / hs[1];
-  return DYB_OK;
-}
-
-static int resample_impl(int device, const double* w, const double* u, double u0, int systematic, int64_t n,
-                         int64_t* idx, int64_t* n_clamped) {
-  if (n <= 0 || !w || !idx || (!systematic && !u)) return fail(DYB_ERR_ARG, "bad argument");
-  DYB_CUDA(cudaSetDevice(device));
-  cudaStream_t st = device_stream(device);
-  Stager sg(st);
-  const size_t N = (size_t)n;
-  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
-  const double* dw = sg.in(w, N);
-  const double* du = systematic ? nullptr : sg.in(u, N);
-  long long* didx = reinterpret_cast<long long*>(sg.out(idx, N));
-  double* cw = sg.temp<double>(N);
-  double* bt = sg.temp<double>((size_t)nb);
-  double* offs = sg.temp<double>((size_t)nb);
-  unsigned long long* dcl = sg.temp<unsigned long long>(1);
-  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
-  DYB_CUDA(cudaMemsetAsync(dcl, 0, sizeof(unsigned long long), st));
-  smc_block_scan_kernel<<<nblk(nb, 64), 64, 0, st>>>(dw, n, cw, bt);
-  smc_offsets_kernel<<<1, 32, 0, st>>>(bt, nb, offs);
-  smc_add_offsets_kernel<<<nblk(n, 256), 256, 0, st>>>(cw, offs, n);
-  smc_search_kernel<<<nblk(n, 256), 256, 0, st>>>(cw, n, du, u0, systematic, 0, n, didx, dcl);
-  DYB_CUDA(cudaGetLastError());
-  unsigned long long hcl = 0;
-  DYB_CUDA(cudaMemcpyAsync(&hcl, dcl, sizeof(hcl), cudaMemcpyDeviceToHost, st));
-  DYB_CUDA(sg.finish());
-  if (n_clamped) *n_clamped = (int64_t)hcl;
-  return DYB_OK;
-}
-
-int dyb_smc_resample_multinomial(int device, const double* w, const double* u, int64_t n, int64_t* idx, int64_t* n_clamped) {
-  return resample_impl(device, w, u, 0.0, 0, n, idx, n_clamped);
-}
-int dyb_smc_resample_systematic(int device, const double* w, double u0, int64_t n, int64_t* idx, int64_t* n_clamped) {
-  return resample_impl(device, w, nullptr, u0, 1, n, idx, n_clamped);
-}
-
-int dyb_smc_moments(int device, const double* para, const double* w, int64_t n, int32_t np, double* mu, double* R) {
-  if (n <= 0 || np <= 0 || np > MAX_EST || !para || !w || !mu || !R) return fail(DYB_ERR_ARG, "bad argument");
-  DYB_CUDA(cudaSetDevice(device));
-  cudaStream_t st = device_stream(device);
-  Stager sg(st);
-  const size_t N = (size_t)n;
-  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
-  const double* dp = sg.in(para, N * np);
-  const double* dw = sg.in(w, N);
-  double* dmu = sg.out(mu, (size_t)np);
-  double* dR = sg.out(R, (size_t)np * np);
-  double* part = sg.temp<double>((size_t)nb * np * np);
-  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
-  smc_moment1_kernel<<<nblk(nb * np, 64), 64, 0, st>>>(dp, dw, n, np, part);
-  smc_reduce_partials_kernel<<<nblk(np, 64), 64, 0, st>>>(part, nb, np, dmu);
-  smc_moment2_kernel<<<nblk(nb * np * np, 64), 64, 0, st>>>(dp, dw, dmu, n, np, part);
-  smc_reduce_partials_kernel<<<nblk(np * np, 64), 64, 0, st>>>(part, nb, np * np, dR);
   DYB_CUDA(cudaGetLastError());
   DYB_CUDA(sg.finish());
   return DYB_OK;

@@ -176,6 +176,37 @@ class BatchSSWs:
         L.check(self.lib.dyb_last_kernel_ms(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    # -- priors / posterior (device) ------------------------------------------------------------------
+    def set_priors(self, priors: PriorSet):
+        """Upload the prior of every estimated parameter (hyper-parameters as the distributions take them)."""
+        if len(priors) != self.np:
+            raise ValueError("one prior per estimated parameter is required")
+        code, a, b = priors.abi_arrays()
+        L.check(self.lib.dyb_set_priors(self._h, self.np, L.ptr(code), L.ptr(a), L.ptr(b)))
+        self.priors = priors
+
+    def logprior(self, Theta):
+        Theta = self._theta(Theta)
+        out = np.empty(Theta.shape[0])
+        L.check(self.lib.dyb_logprior_batch(self._h, L.ptr(Theta), Theta.shape[0], L.ptr(out)))
+        return out
+
+    def logposterior(self, Theta):
+        """(logpost, loglik, status): logprior + loglik, -inf for failed draws (estimation.jl:503-515)."""
+        Theta = self._theta(Theta)
+        n = Theta.shape[0]
+        lp = np.empty(n); ll = np.empty(n); st = np.empty(n, dtype=np.int32)
+        L.check(self.lib.dyb_logposterior_batch(self._h, L.ptr(Theta), n, L.ptr(lp), L.ptr(ll), L.ptr(st)))
+        return lp, ll, st
+
+    def transform(self, X, inverse=False):
+        """inverse=False: R^np -> parameters, returns (theta, logjac); inverse=True: parameters -> R^np."""
+        X = self._theta(X)
+        n = X.shape[0]
+        out = np.empty_like(X); lj = np.empty(n)
+        L.check(self.lib.dyb_transform_batch(self._h, L.ptr(X), n, 1 if inverse else 0, L.ptr(out), L.ptr(lj)))
+        return out if inverse else (out, lj)
+
     # -- stage-level ----------------------------------------------------------------------------------
     def first_order(self, Theta):
         """Returns dict(g1_1 (N,n,k), g1_2 (N,n,nx), ybar (N,n), cr_iters (N,), status (N,))."""
@@ -220,8 +251,7 @@ class DSGELogPosteriorDensity:
     ``logprior(theta) + loglikelihood(theta)``, ``-inf`` for any failed draw."""
 
     def __init__(self, ssws: BatchSSWs, priors: PriorSet):
-        if len(priors) != ssws.np:
-            raise ValueError("one prior per estimated parameter is required")
+        ssws.set_priors(priors)
         self.ssws = ssws
         self.priors = priors
 
@@ -229,12 +259,7 @@ class DSGELogPosteriorDensity:
         return self.ssws.np
 
     def __call__(self, Theta):
-        Theta = self.ssws._theta(Theta)
-        ll, st = self.ssws.loglikelihood(Theta)
-        lp = self.priors.logpriordensity(Theta)
-        out = lp + ll
-        out[(st != 0) | ~np.isfinite(out)] = -np.inf
-        return out
+        return self.ssws.logposterior(Theta)[0]
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -265,6 +290,13 @@ def kalman_batch(Y, z_idx, T, RQR, P0, a0=None, H=None, presample=0, device=0):
     L.check(lib.dyb_kalman_batch(device, ns, ny, nobs, presample, L.ptr(z), L.ptr(Yf), L.ptr(Tc), L.ptr(Qc),
                                  L.ptr(Pc), L.ptr(a0c), L.ptr(Hc), n, L.ptr(ll), L.ptr(st)))
     return ll, st
+
+
+def rng_fill(seed, first, n, step, stream=0, kind=0, count=1, device=0):
+    """The samplers' Philox stream: kind 0 -> (n, count) uniforms of `stream`, kind 1 -> (n, count) normals."""
+    out = np.empty((n, count))
+    L.check(L.load().dyb_rng_fill(device, seed, first, n, step, stream, kind, count, L.ptr(out)))
+    return out
 
 
 def smc_reweight(w, loglh, dphi, device=0):

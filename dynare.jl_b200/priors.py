@@ -59,11 +59,19 @@ def weibull_specification(mu, var):
     return a, mu / special.gamma(1 + 1 / a)
 
 
+# mod-file shape codes of the reference (src/estimation/priors.jl:482-529), used by the C ABI
+SHAPE_CODES = {"beta": 1, "gamma": 2, "normal": 3, "inv_gamma": 4, "uniform": 5, "inv_gamma2": 6, "weibull": 8}
+
+
 @dataclass
 class Prior:
     shape: str
     a: float
     b: float
+
+    @property
+    def code(self) -> int:
+        return SHAPE_CODES[self.shape]
 
     def logpdf(self, x):
         x = np.asarray(x, dtype=np.float64)
@@ -151,6 +159,12 @@ class PriorSet:
 
     def __len__(self):
         return len(self.priors)
+
+    def abi_arrays(self):
+        """(shape codes int32, a, b) as dyb_set_priors takes them."""
+        return (np.array([p.code for p in self.priors], dtype=np.int32),
+                np.array([p.a for p in self.priors], dtype=np.float64),
+                np.array([p.b for p in self.priors], dtype=np.float64))
 
     def logpriordensity(self, theta) -> np.ndarray:
         """theta: (N, np) -> (N,)  sum_k logpdf(prior_k, theta_k)  (estimation.jl:455-462)."""

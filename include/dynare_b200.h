@@ -172,6 +172,80 @@ int dyb_smc_resample_systematic(int device, const double* w, double u0, int64_t 
 int dyb_smc_moments(int device, const double* para, const double* w, int64_t n, int32_t np,
                     double* mu, double* R);
 
+/* ---- samplers around the batched likelihood ---------------------------------------------------------------
+ * Priors: the `prior` vector of EstimatedParameters (src/dynare_containers.jl:800-841).  shape[k] uses the
+ * reference's mod-file codes (src/estimation/priors.jl:482-529): 1 Beta(a,b), 2 Gamma(shape a, scale b),
+ * 3 Normal(mean a, std b), 4 InverseGamma1(alpha a, theta b) (src/distributions/inversegamma1.jl:134-141),
+ * 5 Uniform(a,b), 6 InverseGamma(alpha a, theta b), 8 Weibull(shape a, scale b); (a, b) are the distribution's
+ * own hyper-parameters, i.e. what src/distributions/distribution_parameters.jl:4-76 returns. */
+int dyb_set_priors(dyb_handle* h, int32_t np, const int32_t* shape, const double* a, const double* b);
+/* logpriordensity (src/estimation/estimation.jl:455-462) for N draws; host or device pointers */
+int dyb_logprior_batch(dyb_handle* h, const double* theta, int64_t n_draws, double* logprior);
+/* DSGELogPosteriorDensity callable (src/estimation/estimation.jl:503-515): logprior + loglik, -Inf for a
+ * failed draw; loglik / status may be NULL */
+int dyb_logposterior_batch(dyb_handle* h, const double* theta, int64_t n_draws, double* logpost,
+                           double* loglik, int32_t* status);
+/* DSGETransformation (src/estimation/estimation.jl:465-487): inverse = 0 maps R^np -> parameters and returns the
+ * log-Jacobian (TransformedLogDensity); inverse = 1 maps parameters -> R^np (logjac unused) */
+int dyb_transform_batch(dyb_handle* h, const double* in, int64_t n_draws, int32_t inverse, double* out,
+                        double* logjac);
+/* the samplers' counter-based generator (Philox4x32-10; counter = (index, step, stream, block), key = seed):
+ * kind 0: out[count x n] uniforms on [0,1) of `stream` (1 mixture component, 2 accept, 0 resampling);
+ * kind 1: the first `count` standard normals of (index, step).  For tests and for reproducing a run. */
+int dyb_rng_fill(int device, uint64_t seed, int64_t first_index, int64_t n, uint32_t step, uint32_t stream,
+                 int32_t kind, int32_t count, double* out);
+
+/* SMC with the particles resident on the device(s): `smc(pdraw!, logprior, loglikelihood, names, np)`
+ * (src/estimation/smc.jl:64-313).  Fields default to `Tune` (smc.jl:13-62). */
+typedef struct dyb_smc dyb_smc;
+typedef struct dyb_smc_options {
+  int64_t npart;      /* particles in total, over all ranks (Tune.npart = 1000) */
+  int32_t nphi;       /* tempering stages (400) */
+  double lam;         /* bending coefficient of the schedule phi_i = ((i-1)/(nphi-1))^lam (2) */
+  double c0;          /* initial scale of the proposal covariance (0.5) */
+  double acpt0;       /* initial acceptance rate (0.25) */
+  double trgt;        /* target acceptance rate (0.25) */
+  double alp;         /* mixture weight of the random-walk proposal (0.9) */
+  int32_t resampling; /* 0 multinomial (smc.jl:135), 1 systematic (the commented call smc.jl:133) */
+  uint64_t seed;
+} dyb_smc_options;
+int dyb_smc_default_options(dyb_smc_options* opt);
+/* phi: nphi user-supplied tempering values or NULL for the schedule above.  With a communicator attached
+ * (dyb_comm_init) rank r owns particles [r*npart/nranks, (r+1)*npart/nranks). */
+int dyb_smc_create(dyb_handle* h, const dyb_smc_options* opt, const double* phi, dyb_smc** out);
+int dyb_smc_destroy(dyb_smc* s);
+int dyb_smc_local_range(const dyb_smc* s, int64_t* first, int64_t* n_local);
+/* initial particles (smc.jl:84-101): para_local np x n_local drawn from the prior by the caller; evaluates the
+ * likelihood and the prior; status[i] != 0 marks draws the reference rejects (replace them and call again) */
+int dyb_smc_init(dyb_smc* s, const double* para_local, int32_t* status);
+/* the next n_stages tempering stages: correction, selection, mutation (smc.jl:110-243); asynchronous */
+int dyb_smc_run(dyb_smc* s, int32_t n_stages);
+int dyb_smc_stages_done(const dyb_smc* s);
+/* local slices of the particle system (host or device destinations, any may be NULL); synchronises */
+int dyb_smc_get_particles(dyb_smc* s, double* para, double* w, double* loglh, double* logpost);
+/* stats nphi x 6 row-major (zhat, ESS, resampled, c, acpt, clamped indices so far); mu np, R np x np of the last
+ * mutation step; logmdd = sum_i log zhat_i (smc.jl:301).  Any output may be NULL; synchronises. */
+int dyb_smc_get_stats(dyb_smc* s, double* stats, double* mu, double* R, double* logmdd);
+
+/* random-walk Metropolis on n_chains chains at once (run_mcmc, src/estimation/estimation.jl:964-989): proposal
+ * y' = y + chol_cov z; transformed != 0: y lives in R^np and the target is the TransformedLogDensity
+ * (estimation.jl:926-929).  y np x n_chains in/out, logp / accepted n_chains out, history np x n_chains x n_iter and
+ * history_logp n_chains x n_iter optional.  first_chain offsets the chain index used by the generator (sharding
+ * over ranks); first_step lets a run be continued with fresh random numbers. */
+int dyb_rwmh_run(dyb_handle* h, int64_t n_chains, int64_t first_chain, int32_t n_iter, uint32_t first_step,
+                 int32_t transformed, const double* chol_cov, uint64_t seed, double* y, double* logp,
+                 int64_t* accepted, double* history, double* history_logp);
+
+/* ---- several GPUs: one process per GPU, NCCL only for the SMC stage coupling (weights, block partials, resampled
+ * particles).  Rank 0 calls dyb_comm_unique_id and ships the 128 bytes to the other ranks by any host channel. */
+#define DYB_COMM_ID_BYTES 128
+int dyb_comm_unique_id(void* id /* DYB_COMM_ID_BYTES out */);
+int dyb_comm_init(dyb_handle* h, int32_t rank, int32_t nranks, const void* id);
+int dyb_comm_destroy(dyb_handle* h);
+int dyb_comm_info(const dyb_handle* h, int32_t* rank, int32_t* nranks);
+/* in-place sum over ranks of a device buffer of doubles (is_int64 = 0) or int64 (1) on the handle's stream */
+int dyb_comm_allreduce_sum(dyb_handle* h, void* d_buf, int64_t count, int32_t is_int64);
+
 /* ---- pinned host memory ---------------------------------------------------------------------------- */
 int dyb_host_alloc(void** ptr, int64_t bytes);
 int dyb_host_free(void* ptr);

@@ -95,6 +95,8 @@ SIGNATURES = {
     "dyb_smc_init": (C.c_int, [_P, _D, _I32]),
     "dyb_smc_run": (C.c_int, [_P, C.c_int32]),
     "dyb_smc_stages_done": (C.c_int, [_P]),
+    "dyb_smc_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "dyb_smc_get_timing": (C.c_int, [_P, C.POINTER(C.c_int32), _D]),
     "dyb_smc_get_particles": (C.c_int, [_P, _D, _D, _D, _D]),
     "dyb_smc_get_stats": (C.c_int, [_P, _D, _D, _D, C.POINTER(C.c_double)]),
     "dyb_rwmh_run": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_uint32, C.c_int32, _D, C.c_uint64,

@@ -105,6 +105,8 @@ struct dyb_smc {
   int systematic = 0;
   unsigned long long seed = 0;
   int stage = 0;                 // stages completed (0 = not initialised, 1 = particles initialised, ...)
+  bool profiling = false;
+  std::vector<cudaEvent_t> tev;  // SMC_TSEG + 1 events per profiled stage
   DevBuf para, loglh, logpost, w_g, wt_g, cw_g, bt, offs, scal, flag, tune, idx, para_g, loglh_g, logpost_g,
       part_g, mu, R, L, rdiag, aux, err, prop, qx, q0, lx, st, priorx, acc_g, nclamp, stats;
   void release() {
@@ -112,8 +114,12 @@ struct dyb_smc {
                      &loglh_g, &logpost_g, &part_g, &mu, &R, &L, &rdiag, &aux, &err, &prop, &qx, &q0, &lx, &st,
                      &priorx, &acc_g, &nclamp, &stats};
     for (DevBuf* b : all) b->release();
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    tev.clear();
   }
 };
+// segments of a stage timed by dyb_smc_get_timing: correction, selection, moments + Cholesky, proposal, likelihood, accept
+constexpr int SMC_TSEG = 6;
 
 extern "C" {
 
@@ -135,10 +141,10 @@ int dyb_smc_reweight(int device, const double* w, const double* loglh, double dp
   double* scal = sg.temp<double>(2);
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   smc_incweight_kernel<<<nblk(n, 256), 256, 0, st>>>(dw, dl, dphi, n, wt);
-  smc_block_sum_kernel<<<nblk(nb, 64), 64, 0, st>>>(wt, n, 0, bt);
+  smc_block_sum_kernel<<<(unsigned)nb, 32, 0, st>>>(wt, n, 0, bt);
   smc_total_kernel<<<1, 32, 0, st>>>(bt, nb, scal);
   smc_normalise_kernel<<<nblk(n, 256), 256, 0, st>>>(wt, scal, n, dwo);
-  smc_block_sum_kernel<<<nblk(nb, 64), 64, 0, st>>>(dwo, n, 1, bt);
+  smc_block_sum_kernel<<<(unsigned)nb, 32, 0, st>>>(dwo, n, 1, bt);
   smc_total_kernel<<<1, 32, 0, st>>>(bt, nb, scal + 1);
   DYB_CUDA(cudaGetLastError());
   double hs[2];
@@ -198,9 +204,9 @@ int dyb_smc_moments(int device, const double* para, const double* w, int64_t n, 
   double* dR = sg.out(R, (size_t)np * np);
   double* part = sg.temp<double>((size_t)nb * np * np);
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
-  smc_moment1_kernel<<<nblk(nb * np, 64), 64, 0, st>>>(dp, dw, n, np, part);
+  smc_moment_kernel<<<dim3((unsigned)nb, nblk(np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(dp, dw, nullptr, n, np, part);
   smc_reduce_partials_kernel<<<nblk(np, 64), 64, 0, st>>>(part, nb, np, dmu);
-  smc_moment2_kernel<<<nblk(nb * np * np, 64), 64, 0, st>>>(dp, dw, dmu, n, np, part);
+  smc_moment_kernel<<<dim3((unsigned)nb, nblk(np * np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(dp, dw, dmu, n, np, part);
   smc_reduce_partials_kernel<<<nblk(np * np, 64), 64, 0, st>>>(part, nb, np * np, dR);
   DYB_CUDA(cudaGetLastError());
   DYB_CUDA(sg.finish());
@@ -232,6 +238,14 @@ int dyb_comm_init(dyb_handle* h, int32_t rank, int32_t nranks, const void* id) {
   ncclResult_t r = api->CommInitRank(&c->comm, nranks, u, rank);
   if (r != ncclSuccess) { delete c; return fail(DYB_ERR_NCCL, std::string("ncclCommInitRank: ") + api->GetErrorString(r)); }
   h->comm = c;
+  // first collective: NCCL builds its channels and registers buffers lazily, keep that out of the samplers' timings
+  double* warm = nullptr;
+  DYB_CUDA(cudaMalloc(&warm, 8 * (size_t)nranks));
+  DYB_CUDA(cudaMemsetAsync(warm, 0, 8 * (size_t)nranks, h->stream));
+  DYB_NCCL(api->AllGather(warm + rank, warm, 1, ncclDouble, c->comm, h->stream));
+  DYB_NCCL(api->AllReduce(warm, warm, 1, ncclDouble, ncclSum, c->comm, h->stream));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  DYB_CUDA(cudaFree(warm));
   return DYB_OK;
 }
 
@@ -472,17 +486,26 @@ static int smc_stage(dyb_smc* s, int i) {
   int rc = prior_set(h, &ps);
   if (rc) return rc;
 
+  cudaEvent_t* tev = nullptr;
+  if (s->profiling) {
+    const size_t base = s->tev.size();
+    for (int k = 0; k <= SMC_TSEG; ++k) { cudaEvent_t e; DYB_CUDA(cudaEventCreate(&e)); s->tev.push_back(e); }
+    tev = &s->tev[base];
+  }
+#define DYB_MARK(k) do { if (tev) DYB_CUDA(cudaEventRecord(tev[k], st)); } while (0)
+  DYB_MARK(0);
   // 1. correction (smc.jl:118-123) and ESS (:129); the weights of ALL particles are replicated on every rank
   smc_incweight_kernel<<<nblk(n, 256), 256, 0, st>>>(w_g + first, s->loglh.as<double>(), dphi, n, wt_g + first);
   rc = all_gather(h, wt_g + first, wt_g, (size_t)n, ncclDouble, 8);
   if (rc) return rc;
-  smc_block_sum_kernel<<<nblk(nb, 64), 64, 0, st>>>(wt_g, N, 0, s->bt.as<double>());
+  smc_block_sum_kernel<<<(unsigned)nb, 32, 0, st>>>(wt_g, N, 0, s->bt.as<double>());
   smc_total_kernel<<<1, 32, 0, st>>>(s->bt.as<double>(), nb, s->scal.as<double>());
   smc_normalise_kernel<<<nblk(N, 256), 256, 0, st>>>(wt_g, s->scal.as<double>(), N, w_g);
-  smc_block_sum_kernel<<<nblk(nb, 64), 64, 0, st>>>(w_g, N, 1, s->bt.as<double>());
+  smc_block_sum_kernel<<<(unsigned)nb, 32, 0, st>>>(w_g, N, 1, s->bt.as<double>());
   smc_total_kernel<<<1, 32, 0, st>>>(s->bt.as<double>(), nb, s->scal.as<double>() + 1);
   smc_stage_scalars_kernel<<<1, 32, 0, st>>>(s->scal.as<double>(), N, s->trgt, tune, flag, stats);
 
+  DYB_MARK(1);
   // 2. selection (smc.jl:130-145): every kernel is predicated on the device flag, the collectives are unconditional
   smc_block_scan_kernel<<<nblk(nb, 64), 64, 0, st>>>(w_g, N, s->cw_g.as<double>(), s->bt.as<double>());
   smc_offsets_kernel<<<1, 32, 0, st>>>(s->bt.as<double>(), nb, s->offs.as<double>());
@@ -500,19 +523,22 @@ static int smc_stage(dyb_smc* s, int i) {
                                                            s->loglh.as<double>(), s->logpost.as<double>());
   smc_equal_weights_kernel<<<nblk(N, 256), 256, 0, st>>>(w_g, N, flag);
 
+  DYB_MARK(2);
   // 3. mutation: particle mean and covariance (smc.jl:154-165) in the canonical blocked order
   double* part_g = s->part_g.as<double>();
-  smc_moment1_kernel<<<nblk(nb_l * np, 64), 64, 0, st>>>(s->para.as<double>(), w_g + first, n, np, part_g + (size_t)s->rank * nb_l * np);
+  smc_moment_kernel<<<dim3((unsigned)nb_l, nblk(np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(
+      s->para.as<double>(), w_g + first, nullptr, n, np, part_g + (size_t)s->rank * nb_l * np);
   rc = all_gather(h, part_g + (size_t)s->rank * nb_l * np, part_g, (size_t)nb_l * np, ncclDouble, 8);
   if (rc) return rc;
   smc_reduce_partials_kernel<<<nblk(np, 64), 64, 0, st>>>(part_g, nb, np, s->mu.as<double>());
-  smc_moment2_kernel<<<nblk(nb_l * np * np, 64), 64, 0, st>>>(s->para.as<double>(), w_g + first, s->mu.as<double>(), n, np,
-                                                               part_g + (size_t)s->rank * nb_l * np * np);
+  smc_moment_kernel<<<dim3((unsigned)nb_l, nblk(np * np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(
+      s->para.as<double>(), w_g + first, s->mu.as<double>(), n, np, part_g + (size_t)s->rank * nb_l * np * np);
   rc = all_gather(h, part_g + (size_t)s->rank * nb_l * np * np, part_g, (size_t)nb_l * np * np, ncclDouble, 8);
   if (rc) return rc;
   smc_reduce_partials_kernel<<<nblk(np * np, 64), 64, 0, st>>>(part_g, nb, np * np, s->R.as<double>());
   smc_chol_kernel<<<1, 32, 0, st>>>(s->R.as<double>(), np, s->L.as<double>(), s->rdiag.as<double>(), s->aux.as<double>(), s->err.as<int>());
 
+  DYB_MARK(3);
   SmcProposeArgs pa;
   pa.para = s->para.as<double>(); pa.loglh = s->loglh.as<double>(); pa.logpost = s->logpost.as<double>();
   pa.mu = s->mu.as<double>(); pa.L = s->L.as<double>(); pa.rdiag = s->rdiag.as<double>(); pa.aux = s->aux.as<double>();
@@ -520,8 +546,10 @@ static int smc_stage(dyb_smc* s, int i) {
   pa.prop = s->prop.as<double>(); pa.qx = s->qx.as<double>(); pa.q0 = s->q0.as<double>();
   smc_propose_kernel<<<nblk(n, 128), 128, sizeof(double) * (np * np + 2 * np), st>>>(pa);
   DYB_CUDA(cudaGetLastError());
+  DYB_MARK(4);
   rc = dyb_loglik_batch_device(h, s->prop.as<double>(), n, s->lx.as<double>(), s->st.as<int>());
   if (rc) return rc;
+  DYB_MARK(5);
   logprior_kernel<<<nblk(n, 128), 128, 0, st>>>(ps, s->prop.as<double>(), n, s->priorx.as<double>());
   unsigned long long* acc = s->acc_g.as<unsigned long long>();
   DYB_CUDA(cudaMemsetAsync(acc + s->rank, 0, 8, st));
@@ -536,6 +564,8 @@ static int smc_stage(dyb_smc* s, int i) {
   smc_acpt_kernel<<<1, 32, 0, st>>>(acc, s->nranks, N, tune, stats);
   smc_store_clamped_kernel<<<1, 32, 0, st>>>(s->nclamp.as<unsigned long long>(), stats);
   DYB_CUDA(cudaGetLastError());
+  DYB_MARK(6);
+#undef DYB_MARK
   h->launches += 23;
   return DYB_OK;
 }
@@ -553,6 +583,28 @@ int dyb_smc_run(dyb_smc* s, int32_t n_stages) {
 }
 
 int dyb_smc_stages_done(const dyb_smc* s) { return s ? s->stage : 0; }
+
+int dyb_smc_set_profiling(dyb_smc* s, int32_t on) {
+  if (!s) return fail(DYB_ERR_ARG, "null argument");
+  s->profiling = on != 0;
+  return DYB_OK;
+}
+
+int dyb_smc_get_timing(dyb_smc* s, int32_t* n_stages, double* ms) {
+  if (!s || !ms) return fail(DYB_ERR_ARG, "null argument");
+  DYB_CUDA(cudaSetDevice(s->h->device));
+  DYB_CUDA(cudaStreamSynchronize(s->h->stream));
+  for (int k = 0; k < SMC_TSEG; ++k) ms[k] = 0.0;
+  const size_t ns = s->tev.size() / (SMC_TSEG + 1);
+  for (size_t i = 0; i < ns; ++i)
+    for (int k = 0; k < SMC_TSEG; ++k) {
+      float x = 0;
+      DYB_CUDA(cudaEventElapsedTime(&x, s->tev[i * (SMC_TSEG + 1) + k], s->tev[i * (SMC_TSEG + 1) + k + 1]));
+      ms[k] += x;
+    }
+  if (n_stages) *n_stages = (int32_t)ns;
+  return DYB_OK;
+}
 
 int dyb_smc_get_particles(dyb_smc* s, double* para, double* w, double* loglh, double* logpost) {
   if (!s) return fail(DYB_ERR_ARG, "null argument");

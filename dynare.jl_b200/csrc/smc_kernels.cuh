@@ -1,11 +1,12 @@
 // SMC particle-weight primitives on device (reference src/estimation/smc.jl:118-167, 340-361).
 //
 // Every sum over particles uses ONE canonical association order, independent of launch geometry and
-// of how particles are sharded over GPUs:  sequential fp64 sum inside each block of SMC_BLOCK = 1024
-// consecutive particles, then a sequential sum over block totals.  The cumulative weight used for
-// resampling is  cw[b*1024 + i] = offset_b + local_b[i]  with local_b the sequential inclusive scan
-// of block b and offset_b the sequential sum of the previous block totals.  The CPU oracle
-// (oracle/smc.py) uses the same order, which is what makes resampling indices bit-exact.
+// of how particles are sharded over GPUs (three levels):
+//   sequential fp64 sum of each run of 32 consecutive particles; sequential sum of the 32 run totals of each
+//   block of SMC_BLOCK = 1024 consecutive particles; sequential sum over block totals.
+// The cumulative weight used for resampling is  cw[b*1024 + i] = offset_b + local_b[i]  with local_b the
+// sequential inclusive scan of block b and offset_b the sequential sum of the previous blocks' scan totals.
+// The CPU oracle (oracle/smc.py) uses the same orders, which is what makes resampling indices bit-exact.
 #pragma once
 #include "model_traits.cuh"
 
@@ -20,18 +21,31 @@ __global__ void smc_incweight_kernel(const double* __restrict__ w, const double*
   if (i < n) wt[i] = w[i] * exp(dphi * loglh[i]);
 }
 
-// sequential sum of f(x) inside each 1024-block: one thread per block. mode 0: x ; 1: x*x
+constexpr int SMC_RUN = 32;     // SMC_BLOCK = SMC_RUN * 32
+
+// sequential combination of the 32 lane values of a warp, lane 0 first (every lane gets the result)
+DYB_D double warp_sum_in_order(double s) {
+  double t = 0.0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) t = __dadd_rn(t, __shfl_sync(0xffffffffu, s, j));
+  return t;
+}
+
+// canonical total of f(x) over each 1024-block: one warp per block, lane j owns run j. mode 0: x ; 1: x*x
+// launch <<<number of blocks, 32>>>
 __global__ void smc_block_sum_kernel(const double* __restrict__ x, long long n, int mode,
                                      double* __restrict__ block_tot) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
-  if (b >= nb) return;
-  const long long lo = b * SMC_BLOCK;
-  const long long hi = (lo + SMC_BLOCK < n) ? lo + SMC_BLOCK : n;
+  const long long lo = (long long)blockIdx.x * SMC_BLOCK + (long long)threadIdx.x * SMC_RUN;
   double s = 0.0;
-  if (mode == 0) for (long long i = lo; i < hi; ++i) s += x[i];
-  else for (long long i = lo; i < hi; ++i) s = __dadd_rn(s, __dmul_rn(x[i], x[i]));   // no FMA contraction: same bits as the CPU order
-  block_tot[b] = s;
+  for (int i = 0; i < SMC_RUN; ++i) {
+    const long long e = lo + i;
+    if (e < n) {
+      const double v = x[e];
+      s = mode == 0 ? __dadd_rn(s, v) : __dadd_rn(s, __dmul_rn(v, v));   // no FMA contraction: same bits as the CPU order
+    }
+  }
+  const double t = warp_sum_in_order(s);
+  if (threadIdx.x == 0) block_tot[blockIdx.x] = t;
 }
 
 // sequential sum over block totals (single thread); out[0] = total
@@ -94,41 +108,32 @@ __global__ void smc_search_kernel(const double* __restrict__ cw, long long n,
   idx[i - lo] = a;
 }
 
-// weighted first moment: partial[b*np + p] = sum_{i in block b} w[i] * para[p + np*i]  (sequential)
-__global__ void smc_moment1_kernel(const double* __restrict__ para, const double* __restrict__ w,
-                                   long long n, int np, double* __restrict__ partial) {
-  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nb * np) return;
-  const long long b = e / np;
-  const int p = (int)(e % np);
-  const long long lo = b * SMC_BLOCK;
-  const long long hi = (lo + SMC_BLOCK < n) ? lo + SMC_BLOCK : n;
+// weighted moments of the particles in the canonical order.  mu == nullptr: first moment,
+//   partial[b*np + p] = sum_{i in block b} w[i] * para[p + np*i];
+// else second central moment, partial[b*np*np + p + np*q] = sum_i (w_i (x_ip - mu_p)) (x_iq - mu_q).
+// launch <<<dim3(blocks, ceil(ncomp / SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE)>>>: one warp per (block, component),
+// lane j sums run j sequentially, then the 32 run totals are combined in order.
+constexpr int SMC_MOM_TILE = 8;
+__global__ void smc_moment_kernel(const double* __restrict__ para, const double* __restrict__ w,
+                                  const double* __restrict__ mu, long long n, int np,
+                                  double* __restrict__ partial) {
+  const int ncomp = mu ? np * np : np;
+  const int c = blockIdx.y * SMC_MOM_TILE + threadIdx.y;
+  if (c >= ncomp) return;                                  // whole warp leaves together
+  const int p = c % np, q = c / np;
+  const double mp = mu ? mu[p] : 0.0, mq = mu ? mu[q] : 0.0;
+  const long long lo = (long long)blockIdx.x * SMC_BLOCK + (long long)threadIdx.x * SMC_RUN;
   double s = 0.0;
-  for (long long i = lo; i < hi; ++i) s = __dadd_rn(s, __dmul_rn(w[i], para[p + (long long)np * i]));
-  partial[e] = s;
-}
-
-// weighted second central moment: partial[b*np*np + p + np*q] = sum_i w_i (x_ip - mu_p)(x_iq - mu_q)
-__global__ void smc_moment2_kernel(const double* __restrict__ para, const double* __restrict__ w,
-                                   const double* __restrict__ mu, long long n, int np,
-                                   double* __restrict__ partial) {
-  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int np2 = np * np;
-  if (e >= nb * np2) return;
-  const long long b = e / np2;
-  const int pq = (int)(e % np2);
-  const int p = pq % np, q = pq / np;
-  const long long lo = b * SMC_BLOCK;
-  const long long hi = (lo + SMC_BLOCK < n) ? lo + SMC_BLOCK : n;
-  const double mp = mu[p], mq = mu[q];
-  double s = 0.0;
-  for (long long i = lo; i < hi; ++i) {
-    const double* x = para + (long long)np * i;
-    s = __dadd_rn(s, __dmul_rn(__dmul_rn(w[i], x[p] - mp), x[q] - mq));
+  for (int i = 0; i < SMC_RUN; ++i) {
+    const long long e = lo + i;
+    if (e < n) {
+      const double* x = para + (long long)np * e;
+      if (mu) s = __dadd_rn(s, __dmul_rn(__dmul_rn(w[e], x[p] - mp), x[q] - mq));
+      else s = __dadd_rn(s, __dmul_rn(w[e], x[p]));
+    }
   }
-  partial[e] = s;
+  const double t = warp_sum_in_order(s);
+  if (threadIdx.x == 0) partial[(long long)blockIdx.x * ncomp + c] = t;
 }
 
 // out[c] = sequential sum over blocks of partial[b*ncomp + c]

@@ -113,6 +113,16 @@ class SMC:
         """Enqueue the next ``n_stages`` tempering stages (all remaining ones by default); asynchronous."""
         L.check(self.ssws.lib.dyb_smc_run(self._s, self.nphi if n_stages is None else n_stages))
 
+    def set_profiling(self, on=True):
+        L.check(self.ssws.lib.dyb_smc_set_profiling(self._s, 1 if on else 0))
+
+    def timing(self):
+        """Per-segment device time (ms, totals over the profiled stages) from CUDA events."""
+        ms = np.zeros(6); n = C.c_int32()
+        L.check(self.ssws.lib.dyb_smc_get_timing(self._s, C.byref(n), L.ptr(ms)))
+        names = ("correction", "selection", "moments", "proposal", "likelihood", "accept")
+        return dict(stages=n.value, **dict(zip(names, ms.tolist())))
+
     def stages_done(self) -> int:
         return self.ssws.lib.dyb_smc_stages_done(self._s)
 

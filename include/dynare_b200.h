@@ -221,6 +221,11 @@ int dyb_smc_init(dyb_smc* s, const double* para_local, int32_t* status);
 /* the next n_stages tempering stages: correction, selection, mutation (smc.jl:110-243); asynchronous */
 int dyb_smc_run(dyb_smc* s, int32_t n_stages);
 int dyb_smc_stages_done(const dyb_smc* s);
+/* per-stage time split from CUDA events on the handle's stream: when profiling is on, every stage records 7 events;
+ * ms[6] = totals of (correction + weight all-gather, selection + particle all-gather, moments + Cholesky, proposal,
+ * likelihood of the proposals, prior + accept + acceptance all-gather) over the profiled stages.  Synchronises. */
+int dyb_smc_set_profiling(dyb_smc* s, int32_t on);
+int dyb_smc_get_timing(dyb_smc* s, int32_t* n_stages, double* ms);
 /* local slices of the particle system (host or device destinations, any may be NULL); synchronises */
 int dyb_smc_get_particles(dyb_smc* s, double* para, double* w, double* loglh, double* logpost);
 /* stats nphi x 6 row-major (zhat, ESS, resampled, c, acpt, clamped indices so far); mu np, R np x np of the last

@@ -5,14 +5,17 @@ correction (``:118-123``), ESS (``:129``), ``multinomial_resampling`` (``:340-36
 moments (``:154-161``).  The reference leaves the floating-point association order of its sums to
 Julia's ``sum``/``cumsum``; the engine's contract ("indices bit-exact given identical weights and
 uniforms") is stated against ONE specified order, restated here in plain sequential loops:
-    sum inside each block of 1024 consecutive particles, left to right; then block totals, left to right;
-    cw[b*1024 + i] = offset_b + local_b[i].
+    sums: each run of 32 consecutive particles left to right; the 32 run totals of each block of 1024 consecutive
+    particles left to right; the block totals left to right;
+    cumulative weights: cw[b*1024 + i] = offset_b + local_b[i] with local_b the left-to-right inclusive scan of
+    block b and offset_b the left-to-right sum of the previous blocks' scan totals.
 """
 from __future__ import annotations
 
 import numpy as np
 
 BLOCK = 1024
+RUN = 32
 
 
 def _block_totals(x):
@@ -20,10 +23,13 @@ def _block_totals(x):
     nb = (n + BLOCK - 1) // BLOCK
     tot = np.zeros(nb)
     for b in range(nb):
-        s = 0.0
-        for v in x[b * BLOCK:(b + 1) * BLOCK]:
-            s += float(v)
-        tot[b] = s
+        t = 0.0
+        for r in range(BLOCK // RUN):
+            s = 0.0
+            for v in x[b * BLOCK + r * RUN:b * BLOCK + (r + 1) * RUN]:
+                s += float(v)
+            t += s
+        tot[b] = t
     return tot
 
 

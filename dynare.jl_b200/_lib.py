@@ -41,6 +41,12 @@ class SmcOptions(C.Structure):
                 ("seed", C.c_uint64)]
 
 
+class ModelDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("n_static", C.c_int32),
+                ("n_bkwrd_b", C.c_int32), ("n_fwrd_b", C.c_int32), ("i_static", C.c_void_p),
+                ("i_bkwrd_b", C.c_void_p), ("i_fwrd_b", C.c_void_p), ("obs_idx", C.c_void_p)]
+
+
 COMM_ID_BYTES = 128
 
 _P = C.c_void_p
@@ -82,6 +88,10 @@ SIGNATURES = {
     "dyb_smc_resample_multinomial": (C.c_int, [C.c_int, _D, _D, C.c_int64, _I64, C.POINTER(C.c_int64)]),
     "dyb_smc_resample_systematic": (C.c_int, [C.c_int, _D, C.c_double, C.c_int64, _I64, C.POINTER(C.c_int64)]),
     "dyb_smc_moments": (C.c_int, [C.c_int, _D, _D, C.c_int64, C.c_int32, _D, _D]),
+    "dyb_create_generic": (C.c_int, [C.POINTER(ModelDesc), C.c_int, C.POINTER(_P)]),
+    "dyb_first_order_from_jacobian_batch": (C.c_int, [_P, _D, _D, C.c_int32, C.c_int64, _D, _D, _D, _D, _I32, _I32, _I32]),
+    "dyb_loglik_from_jacobian_batch": (C.c_int, [_P, _D, _D, _D, C.c_int32, _D, C.c_int32, _I32, C.c_int64, _D, _I32]),
+    "dyb_lyapunov_batch": (C.c_int, [C.c_int, C.c_int32, _D, _D, C.c_int64, C.c_double, C.c_int32, _D, _I32, _I32]),
     "dyb_set_priors": (C.c_int, [_P, C.c_int32, _I32, _D, _D]),
     "dyb_logprior_batch": (C.c_int, [_P, _D, C.c_int64, _D]),
     "dyb_logposterior_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D, _I32]),

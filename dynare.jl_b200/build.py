@@ -16,7 +16,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 
 def sources():
-    return [os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "sampler.cu")] + sorted(glob.glob(os.path.join(CSRC, "generated", "*.cu")))
+    return [os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "sampler.cu"), os.path.join(CSRC, "generic.cu")] + sorted(glob.glob(os.path.join(CSRC, "generated", "*.cu")))
 
 
 def _deps():

@@ -8,7 +8,6 @@
 #include <vector>
 
 #include "internal.h"
-#include "kalman_generic.cuh"
 
 namespace dyb {
 
@@ -82,6 +81,7 @@ int dyb_create(const char* model, int device, dyb_handle** out) {
   DYB_CUDA(cudaSetDevice(device));
   dyb_handle* h = new dyb_handle();
   h->ops = m;
+  h->dims = m->dims;
   h->device = device;
   m->defaults(h->hs);
   default_options(&h->hs.opt);
@@ -98,6 +98,7 @@ int dyb_destroy(dyb_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   comm_release(h);
+  generic_release(h);
   h->d_theta.release(); h->d_ss.release(); h->d_st1.release(); h->d_ll.release(); h->d_st2.release(); h->d_Y.release(); h->d_mid.release();
   h->h_in.release(); h->h_out.release();
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -109,7 +110,7 @@ int dyb_destroy(dyb_handle* h) {
 
 int dyb_get_dims(const dyb_handle* h, dyb_model_dims* dims) {
   if (!h || !dims) return fail(DYB_ERR_ARG, "null argument");
-  *dims = h->ops->dims;
+  *dims = h->dims;
   return DYB_OK;
 }
 int dyb_get_options(const dyb_handle* h, dyb_options* opt) {
@@ -127,8 +128,9 @@ int dyb_set_options(dyb_handle* h, const dyb_options* opt) {
 }
 
 int dyb_set_calibration(dyb_handle* h, const double* params, const double* sigma_e, const double* sigma_m) {
+  if (h && !h->ops) return fail(DYB_ERR_UNSUPPORTED, "this handle has no device model function (dyb_create_generic): use the *_from_jacobian entry points");
   if (!h) return fail(DYB_ERR_ARG, "null handle");
-  const dyb_model_dims& d = h->ops->dims;
+  const dyb_model_dims& d = h->dims;
   if (params) h->hs.params.assign(params, params + d.npar);
   if (sigma_e) h->hs.sigma_e.assign(sigma_e, sigma_e + d.nx * d.nx);
   if (sigma_m) h->hs.sigma_m.assign(sigma_m, sigma_m + d.ny * d.ny);
@@ -136,8 +138,9 @@ int dyb_set_calibration(dyb_handle* h, const double* params, const double* sigma
 }
 
 int dyb_set_estimated_params(dyb_handle* h, int32_t np, const int32_t* kind, const int32_t* i1, const int32_t* i2) {
+  if (h && !h->ops) return fail(DYB_ERR_UNSUPPORTED, "this handle has no device model function (dyb_create_generic): use the *_from_jacobian entry points");
   if (!h || np < 0 || np > MAX_EST || (np > 0 && (!kind || !i1 || !i2))) return fail(DYB_ERR_ARG, "bad estimated-parameter map");
-  const dyb_model_dims& d = h->ops->dims;
+  const dyb_model_dims& d = h->dims;
   for (int q = 0; q < np; ++q) {
     int lim1, lim2;
     switch (kind[q]) {
@@ -155,7 +158,7 @@ int dyb_set_estimated_params(dyb_handle* h, int32_t np, const int32_t* kind, con
 
 int dyb_set_observations(dyb_handle* h, const double* Y, int32_t ny, int32_t nobs) {
   if (!h || !Y) return fail(DYB_ERR_ARG, "null argument");
-  if (ny != h->ops->dims.ny) return fail(DYB_ERR_ARG, "observations must have ny rows");
+  if (ny != h->dims.ny) return fail(DYB_ERR_ARG, "observations must have ny rows");
   if (nobs < 0) return fail(DYB_ERR_ARG, "nobs < 0");
   if ((size_t)ny * nobs * sizeof(double) > 200 * 1024) return fail(DYB_ERR_UNSUPPORTED, "observation matrix larger than 200 KB");
   DYB_CUDA(cudaSetDevice(h->device));
@@ -169,7 +172,7 @@ int dyb_set_observations(dyb_handle* h, const double* Y, int32_t ny, int32_t nob
 
 static cudaEvent_t* timer_slot(dyb_handle* h);
 static int reserve_batch(dyb_handle* h, int64_t n) {
-  const dyb_model_dims& d = h->ops->dims;
+  const dyb_model_dims& d = h->dims;
   const size_t N = (size_t)(n > 0 ? n : 1);
   DYB_CUDA(h->d_ss.reserve(sizeof(double) * d.ss_doubles * N));
   DYB_CUDA(h->d_st1.reserve(sizeof(int) * N));
@@ -178,6 +181,7 @@ static int reserve_batch(dyb_handle* h, int64_t n) {
 }
 
 int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, double* d_loglik, int32_t* d_status) {
+  if (h && !h->ops) return fail(DYB_ERR_UNSUPPORTED, "this handle has no device model function (dyb_create_generic): use the *_from_jacobian entry points");
   if (!h || n < 0 || (n > 0 && (!d_theta || !d_loglik || !d_status))) return fail(DYB_ERR_ARG, "null argument");
   if (h->nobs <= 0 && h->d_Y.p == nullptr) return fail(DYB_ERR_STATE, "dyb_set_observations has not been called");
   if (n == 0) return DYB_OK;
@@ -210,6 +214,7 @@ static cudaEvent_t* timer_slot(dyb_handle* h) {
 }
 
 int dyb_loglik_batch(dyb_handle* h, const double* theta, int64_t n, double* loglik, int32_t* status) {
+  if (h && !h->ops) return fail(DYB_ERR_UNSUPPORTED, "this handle has no device model function (dyb_create_generic): use the *_from_jacobian entry points");
   if (!h || n < 0 || (n > 0 && (!theta || !loglik || !status))) return fail(DYB_ERR_ARG, "null argument");
   if (n == 0) return DYB_OK;
   DYB_CUDA(cudaSetDevice(h->device));
@@ -343,10 +348,11 @@ int dyb_fp64_peak(int device, double* tflops) {
 
 int dyb_first_order_batch(dyb_handle* h, const double* theta, int64_t n, double* g1, double* ybar,
                           int32_t* cr_iters, int32_t* lyap_iters, int32_t* status) {
+  if (h && !h->ops) return fail(DYB_ERR_UNSUPPORTED, "this handle has no device model function (dyb_create_generic): use the *_from_jacobian entry points");
   if (!h || n < 0 || (n > 0 && (!theta || !status))) return fail(DYB_ERR_ARG, "null argument");
   if (n == 0) return DYB_OK;
   DYB_CUDA(cudaSetDevice(h->device));
-  const dyb_model_dims& d = h->ops->dims;
+  const dyb_model_dims& d = h->dims;
   int rc = reserve_batch(h, n);
   if (rc) return rc;
   Stager sg(h->stream);
@@ -372,10 +378,11 @@ int dyb_first_order_batch(dyb_handle* h, const double* theta, int64_t n, double*
 
 int dyb_state_space_batch(dyb_handle* h, const double* theta, int64_t n, double* T, double* RQR, double* P0,
                           double* ybar_obs, double* H, int32_t* status) {
+  if (h && !h->ops) return fail(DYB_ERR_UNSUPPORTED, "this handle has no device model function (dyb_create_generic): use the *_from_jacobian entry points");
   if (!h || n < 0 || (n > 0 && (!theta || !status))) return fail(DYB_ERR_ARG, "null argument");
   if (n == 0) return DYB_OK;
   DYB_CUDA(cudaSetDevice(h->device));
-  const dyb_model_dims& d = h->ops->dims;
+  const dyb_model_dims& d = h->dims;
   int rc = reserve_batch(h, n);
   if (rc) return rc;
   Stager sg(h->stream);
@@ -392,55 +399,6 @@ int dyb_state_space_batch(dyb_handle* h, const double* theta, int64_t n, double*
   DYB_CUDA(h->ops->solve(h->hs, dth, n, so, h->stream));
   DYB_CUDA(h->ops->unpack(h->d_ss.as<double>(), n, dT, dQ, dP, dy, dH, h->stream));
   h->launches += 1 + h->ops->solve_launches(h->hs);
-  DYB_CUDA(sg.finish());
-  return DYB_OK;
-}
-
-int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t presample,
-                     const int32_t* z_idx, const double* Y, const double* T, const double* RQR,
-                     const double* P0, const double* a0, const double* H, int64_t n,
-                     double* loglik, int32_t* status) {
-  if (ns <= 0 || ny <= 0 || ny > 64 || ny > ns || nobs < 0 || presample < 0 || n < 0)
-    return fail(DYB_ERR_ARG, "bad sizes (need 0 < ny <= min(ns, 64))");
-  if (n == 0) return DYB_OK;
-  if (!z_idx || !Y || !T || !RQR || !P0 || !loglik || !status) return fail(DYB_ERR_ARG, "null argument");
-  DYB_CUDA(cudaSetDevice(device));
-  cudaStream_t st = device_stream(device);
-  Stager sg(st);
-  const size_t N = (size_t)n, ns2 = (size_t)ns * ns;
-  KalmanGenericArgs g;
-  g.ns = ns; g.ny = ny; g.nobs = nobs; g.presample = presample;
-  g.z_idx = sg.in(z_idx, (size_t)ny);
-  g.Y = sg.in(Y, (size_t)ny * (nobs > 0 ? nobs : 1));
-  g.T = sg.in(T, ns2 * N);
-  g.RQR = sg.in(RQR, ns2 * N);
-  g.P0 = sg.in(P0, ns2 * N);
-  g.a0 = sg.in(a0, (size_t)ns * N);
-  g.H = sg.in(H, (size_t)ny * ny * N);
-  g.n_draws = n;
-  g.loglik = sg.out(loglik, N);
-  g.status = sg.out(status, N);
-  if (!is_device_ptr(z_idx)) for (int i = 0; i < ny; ++i) if (z_idx[i] < 0 || z_idx[i] >= ns) return fail(DYB_ERR_ARG, "z_idx out of range");
-  int dev_sms = 148, max_smem = 0;
-  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
-  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const size_t small = sizeof(double) * ((size_t)ny * ns + (size_t)ny * ny + 2 * (size_t)ns + 2 * (size_t)ny + 32);
-  const size_t full = small + sizeof(double) * 2 * ns2;
-  size_t smem;
-  long long grid;
-  if (full + 1024 <= (size_t)max_smem) {
-    smem = full; g.scratch = nullptr;
-    grid = n;
-    if (grid > 65535LL * 16) grid = 65535LL * 16;
-  } else {
-    smem = small;
-    grid = (long long)dev_sms * 2 < n ? (long long)dev_sms * 2 : n;
-    g.scratch = sg.temp<double>(2 * ns2 * (size_t)grid);
-  }
-  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
-  if (smem > 48 * 1024) DYB_CUDA(cudaFuncSetAttribute(kalman_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kalman_generic_kernel<<<(unsigned)grid, 256, smem, st>>>(g);
-  DYB_CUDA(cudaGetLastError());
   DYB_CUDA(sg.finish());
   return DYB_OK;
 }

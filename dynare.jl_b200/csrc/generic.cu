@@ -1,0 +1,294 @@
+// Run-time-size entry points (include/dynare_b200.h, "models without a generated device function"): a handle built
+// from index sets alone, the solve / likelihood from host-evaluated Jacobians, the batched doubling Lyapunov
+// solver and the generic dense Kalman filter.
+#include <algorithm>
+
+#include "internal.h"
+#include "kalman_generic.cuh"
+#include "solve_generic.cuh"
+
+namespace dyb {
+
+struct GenericHost {
+  GenericModel gm{};           // sizes + device pointers into d_idx
+  DevBuf d_idx;
+  std::vector<int> obs_state;  // ny: Kalman state observed by each row of Y
+  size_t smem = 0;
+};
+
+void generic_release(dyb_handle* h) {
+  if (h && h->generic) {
+    h->generic->d_idx.release();
+    delete h->generic;
+    h->generic = nullptr;
+  }
+}
+
+// launch the dense Kalman filter on device-resident state spaces (shared by dyb_kalman_batch and the
+// from-Jacobian likelihood); scratch (2 ns^2 doubles per CTA) only when P and T P do not fit in shared memory
+static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaStream_t st, Stager& sg) {
+  int dev_sms = 148, max_smem = 0;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const size_t ns2 = (size_t)g.ns * g.ns;
+  const size_t small = sizeof(double) * ((size_t)g.ny * g.ns + (size_t)g.ny * g.ny + 2 * (size_t)g.ns + 2 * (size_t)g.ny + 32);
+  const size_t full = small + sizeof(double) * 2 * ns2;
+  size_t smem;
+  long long grid;
+  if (full + 1024 <= (size_t)max_smem) {
+    smem = full; g.scratch = nullptr;
+    grid = g.n_draws;
+    if (grid > 65535LL * 16) grid = 65535LL * 16;
+  } else {
+    smem = small;
+    grid = (long long)dev_sms * 2 < g.n_draws ? (long long)dev_sms * 2 : g.n_draws;
+    g.scratch = sg.temp<double>(2 * ns2 * (size_t)grid);
+    if (sg.err != cudaSuccess) return sg.err;
+  }
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kalman_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kalman_generic_kernel<<<(unsigned)grid, 256, smem, st>>>(g);
+  return cudaGetLastError();
+}
+
+}  // namespace dyb
+
+using namespace dyb;
+
+extern "C" {
+
+int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t presample,
+                     const int32_t* z_idx, const double* Y, const double* T, const double* RQR,
+                     const double* P0, const double* a0, const double* H, int64_t n,
+                     double* loglik, int32_t* status) {
+  if (ns <= 0 || ny <= 0 || ny > 64 || ny > ns || nobs < 0 || presample < 0 || n < 0)
+    return fail(DYB_ERR_ARG, "bad sizes (need 0 < ny <= min(ns, 64))");
+  if (n == 0) return DYB_OK;
+  if (!z_idx || !Y || !T || !RQR || !P0 || !loglik || !status) return fail(DYB_ERR_ARG, "null argument");
+  DYB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = device_stream(device);
+  Stager sg(st);
+  const size_t N = (size_t)n, ns2 = (size_t)ns * ns;
+  KalmanGenericArgs g{};
+  g.ns = ns; g.ny = ny; g.nobs = nobs; g.presample = presample;
+  g.z_idx = sg.in(z_idx, (size_t)ny);
+  g.Y = sg.in(Y, (size_t)ny * (nobs > 0 ? nobs : 1));
+  g.T = sg.in(T, ns2 * N);
+  g.RQR = sg.in(RQR, ns2 * N);
+  g.P0 = sg.in(P0, ns2 * N);
+  g.a0 = sg.in(a0, (size_t)ns * N);
+  g.H = sg.in(H, (size_t)ny * ny * N);
+  g.n_draws = n;
+  g.loglik = sg.out(loglik, N);
+  g.status = sg.out(status, N);
+  if (!is_device_ptr(z_idx)) for (int i = 0; i < ny; ++i) if (z_idx[i] < 0 || z_idx[i] >= ns) return fail(DYB_ERR_ARG, "z_idx out of range");
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  g.scratch = nullptr;
+  DYB_CUDA(launch_kalman_generic(g, device, st, sg));
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+
+// ---- handle from index sets alone --------------------------------------------------------------------------------
+int dyb_create_generic(const dyb_model_desc* md, int device, dyb_handle** out) {
+  if (!out) return fail(DYB_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!md || md->n < 1 || md->nx < 1 || md->ny < 1 || md->n_static < 0 || md->n_bkwrd_b < 0 || md->n_fwrd_b < 0 ||
+      md->n_static >= md->n || md->ny > 64 || (md->n_static > 0 && !md->i_static) || (md->n_bkwrd_b > 0 && !md->i_bkwrd_b) ||
+      (md->n_fwrd_b > 0 && !md->i_fwrd_b) || !md->obs_idx)
+    return fail(DYB_ERR_ARG, "bad model description");
+  const int n = md->n, nx = md->nx, ny = md->ny, s = md->n_static, k = md->n_bkwrd_b, nf = md->n_fwrd_b, m = n - s;
+  auto in_range_sorted = [&](const int32_t* v, int cnt) {
+    for (int i = 0; i < cnt; ++i) if (v[i] < 0 || v[i] >= n || (i > 0 && v[i] <= v[i - 1])) return false;
+    return true;
+  };
+  if (!in_range_sorted(md->i_static, s) || !in_range_sorted(md->i_bkwrd_b, k) || !in_range_sorted(md->i_fwrd_b, nf))
+    return fail(DYB_ERR_ARG, "index sets must be strictly increasing 0-based variable indices");
+  std::vector<int> var_static(n, 0), var_pos(n, 0);
+  for (int i = 0; i < s; ++i) var_static[md->i_static[i]] = 1;
+  for (int i = 0; i < k; ++i) if (var_static[md->i_bkwrd_b[i]]) return fail(DYB_ERR_ARG, "a static variable cannot have a lag");
+  for (int i = 0; i < nf; ++i) if (var_static[md->i_fwrd_b[i]]) return fail(DYB_ERR_ARG, "a static variable cannot have a lead");
+  { int ps = 0, pd = 0; for (int v = 0; v < n; ++v) var_pos[v] = var_static[v] ? ps++ : pd++; }
+  std::vector<int> bk(k), fw(nf);
+  for (int i = 0; i < k; ++i) bk[i] = var_pos[md->i_bkwrd_b[i]];
+  for (int i = 0; i < nf; ++i) fw[i] = var_pos[md->i_fwrd_b[i]];
+  // compressed Jacobian columns [lags | current | leads | shocks] (src/perturbations.jl:616-635) -> working columns
+  const int ncol = k + n + nf + nx;
+  std::vector<int> jperm(ncol);
+  for (int j = 0; j < k; ++j) jperm[j] = s + j;
+  for (int v = 0; v < n; ++v) jperm[k + v] = var_static[v] ? var_pos[v] : s + k + var_pos[v];
+  for (int j = 0; j < nf; ++j) jperm[k + n + j] = s + k + m + j;
+  for (int e = 0; e < nx; ++e) jperm[k + n + nf + e] = s + k + m + nf + e;
+  // Kalman states: sort(union(obs_idx, i_bkwrd_b)) (src/estimation/estimation.jl:384-390)
+  std::vector<int> state_ids(md->i_bkwrd_b, md->i_bkwrd_b + k);
+  for (int i = 0; i < ny; ++i) {
+    if (md->obs_idx[i] < 0 || md->obs_idx[i] >= n) return fail(DYB_ERR_ARG, "obs_idx out of range");
+    state_ids.push_back(md->obs_idx[i]);
+  }
+  std::sort(state_ids.begin(), state_ids.end());
+  state_ids.erase(std::unique(state_ids.begin(), state_ids.end()), state_ids.end());
+  const int ns = (int)state_ids.size();
+  auto pos_in_states = [&](int v) { return (int)(std::lower_bound(state_ids.begin(), state_ids.end(), v) - state_ids.begin()); };
+  std::vector<int> obs_state(ny), lagged(k), obs_var(md->obs_idx, md->obs_idx + ny);
+  for (int i = 0; i < ny; ++i) obs_state[i] = pos_in_states(md->obs_idx[i]);
+  for (int j = 0; j < k; ++j) lagged[j] = pos_in_states(md->i_bkwrd_b[j]);
+
+  int ndev = 0;
+  DYB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(DYB_ERR_ARG, "no such CUDA device");
+  DYB_CUDA(cudaSetDevice(device));
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const size_t smem = sizeof(double) * generic_solve_smem_doubles(n, nx, ny, s, k, nf, ns);
+  if (smem + 1024 > (size_t)max_smem)
+    return fail(DYB_ERR_UNSUPPORTED, "model too large for the shared-memory generic solver (" + std::to_string(smem / 1024) + " KB per draw)");
+
+  dyb_handle* h = new dyb_handle();
+  h->device = device;
+  h->dims = dyb_model_dims{n, nx, 0, k, nf, s, ncol, ns, ny, 0, 0};
+  h->hs.np = 0;
+  h->hs.opt.cr_tol = 1e-8; h->hs.opt.cr_maxit = 100; h->hs.opt.steady_tol = std::cbrt(2.220446049250313e-16);
+  h->hs.opt.lyap_tol = 1e-16; h->hs.opt.lyap_maxit = 60; h->hs.opt.presample = 0; h->hs.opt.solver = 0;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  h->stream = h->own_stream;
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  GenericHost* gh = new GenericHost();
+  h->generic = gh;
+  // pack the index arrays into one device buffer
+  std::vector<int> pack;
+  auto push = [&](const std::vector<int>& v) { const size_t off = pack.size(); pack.insert(pack.end(), v.begin(), v.end()); return off; };
+  const size_t o_jperm = push(jperm), o_bk = push(bk), o_fw = push(fw), o_vs = push(var_static), o_vp = push(var_pos),
+               o_sid = push(state_ids), o_ov = push(obs_var), o_lag = push(lagged);
+  if (e == cudaSuccess) e = gh->d_idx.reserve(sizeof(int) * pack.size());
+  if (e == cudaSuccess) e = cudaMemcpy(gh->d_idx.p, pack.data(), sizeof(int) * pack.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { dyb_destroy(h); return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
+  const int* base = gh->d_idx.as<int>();
+  gh->gm = GenericModel{n, nx, ny, s, k, nf, m, ncol, ns, base + o_jperm, base + o_bk, base + o_fw, base + o_vs, base + o_vp,
+                        base + o_sid, base + o_ov, base + o_lag};
+  gh->obs_state = obs_state;
+  gh->smem = smem;
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(solve_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { dyb_destroy(h); return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
+  }
+  *out = h;
+  return DYB_OK;
+}
+
+static int generic_solve(dyb_handle* h, GenericSolveArgs a) {
+  GenericHost* gh = h->generic;
+  a.cr_tol = h->hs.opt.cr_tol; a.cr_maxit = h->hs.opt.cr_maxit; a.lyap_tol = h->hs.opt.lyap_tol; a.lyap_maxit = h->hs.opt.lyap_maxit;
+  long long grid = a.n_draws;
+  if (grid > 148LL * 64) grid = 148LL * 64;
+  solve_generic_kernel<<<(unsigned)grid, 128, gh->smem, h->stream>>>(gh->gm, a);
+  DYB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return DYB_OK;
+}
+
+int dyb_first_order_from_jacobian_batch(dyb_handle* h, const double* jac, const double* sigma_e, int32_t sigma_e_per_draw,
+                                        int64_t n, double* g1, double* T, double* RQR, double* P0,
+                                        int32_t* cr_iters, int32_t* lyap_iters, int32_t* status) {
+  if (!h || !h->generic) return fail(DYB_ERR_ARG, "needs a handle made by dyb_create_generic");
+  if (n < 0 || (n > 0 && (!jac || !sigma_e || !status))) return fail(DYB_ERR_ARG, "null argument");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  const dyb_model_dims& d = h->dims;
+  Stager sg(h->stream);
+  const size_t N = (size_t)n, ns2 = (size_t)d.ns * d.ns;
+  GenericSolveArgs a{};
+  a.jac = sg.in(jac, (size_t)d.n * d.ncol * N);
+  a.sigma_e = sg.in(sigma_e, (size_t)d.nx * d.nx * (sigma_e_per_draw ? N : 1));
+  a.stride_se = sigma_e_per_draw ? (long long)d.nx * d.nx : 0;
+  a.n_draws = n;
+  a.g1 = sg.out(g1, (size_t)d.n * (d.k + d.nx) * N);
+  a.T = sg.out(T, ns2 * N); a.RQR = sg.out(RQR, ns2 * N); a.P0 = sg.out(P0, ns2 * N);
+  a.status = sg.out(status, N); a.cr_iters = sg.out(cr_iters, N); a.lyap_iters = sg.out(lyap_iters, N);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  if (a.g1) DYB_CUDA(cudaMemsetAsync(a.g1, 0, sizeof(double) * (size_t)d.n * (d.k + d.nx) * N, h->stream));
+  int rc = generic_solve(h, a);
+  if (rc) return rc;
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int dyb_loglik_from_jacobian_batch(dyb_handle* h, const double* jac, const double* ybar, const double* sigma_e,
+                                   int32_t sigma_e_per_draw, const double* sigma_m, int32_t sigma_m_per_draw,
+                                   const int32_t* status_in, int64_t n, double* loglik, int32_t* status) {
+  if (!h || !h->generic) return fail(DYB_ERR_ARG, "needs a handle made by dyb_create_generic");
+  if (n < 0 || (n > 0 && (!jac || !sigma_e || !loglik || !status))) return fail(DYB_ERR_ARG, "null argument");
+  if (h->d_Y.p == nullptr) return fail(DYB_ERR_STATE, "dyb_set_observations has not been called");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  const dyb_model_dims& d = h->dims;
+  GenericHost* gh = h->generic;
+  const size_t ns2 = (size_t)d.ns * d.ns;
+  // bounded working set: the dense state spaces of one chunk of draws
+  const long long chunk = std::max<long long>(1, std::min<long long>(n, (long long)((1ULL << 30) / (sizeof(double) * (3 * ns2 + d.ny * (d.ny + 1))))));
+  Stager sg(h->stream);
+  const size_t N = (size_t)n;
+  const double* djac = sg.in(jac, (size_t)d.n * d.ncol * N);
+  const double* dyb_ = sg.in(ybar, (size_t)d.n * N);
+  const double* dse = sg.in(sigma_e, (size_t)d.nx * d.nx * (sigma_e_per_draw ? N : 1));
+  const double* dsm = sg.in(sigma_m, (size_t)d.ny * d.ny * (sigma_m_per_draw ? N : 1));
+  const int* dsi = sg.in(status_in, N);
+  double* dll = sg.out(loglik, N);
+  int* dst = sg.out(status, N);
+  double* dT = sg.temp<double>(ns2 * chunk); double* dQ = sg.temp<double>(ns2 * chunk); double* dP = sg.temp<double>(ns2 * chunk);
+  double* dyo = sg.temp<double>((size_t)d.ny * chunk); double* dH = sg.temp<double>((size_t)d.ny * d.ny * chunk);
+  int* dst1 = sg.temp<int>((size_t)chunk);
+  int* dz = sg.temp<int>((size_t)d.ny);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  DYB_CUDA(cudaMemcpyAsync(dz, gh->obs_state.data(), sizeof(int) * d.ny, cudaMemcpyHostToDevice, h->stream));
+  for (long long lo = 0; lo < n; lo += chunk) {
+    const long long c = std::min<long long>(chunk, n - lo);
+    GenericSolveArgs a{};
+    a.jac = djac + (size_t)lo * d.n * d.ncol;
+    a.ybar = dyb_ ? dyb_ + (size_t)lo * d.n : nullptr;
+    a.sigma_e = dse + (sigma_e_per_draw ? (size_t)lo * d.nx * d.nx : 0);
+    a.stride_se = sigma_e_per_draw ? (long long)d.nx * d.nx : 0;
+    a.sigma_m = dsm ? dsm + (sigma_m_per_draw ? (size_t)lo * d.ny * d.ny : 0) : nullptr;
+    a.stride_sm = sigma_m_per_draw ? (long long)d.ny * d.ny : 0;
+    a.status_in = dsi ? dsi + lo : nullptr;
+    a.n_draws = c;
+    a.T = dT; a.RQR = dQ; a.P0 = dP; a.ybar_obs = dyo; a.H = dH; a.status = dst1;
+    int rc = generic_solve(h, a);
+    if (rc) return rc;
+    KalmanGenericArgs g{};
+    g.ns = d.ns; g.ny = d.ny; g.nobs = h->nobs; g.presample = h->hs.opt.presample;
+    g.z_idx = dz; g.Y = h->d_Y.as<double>(); g.T = dT; g.RQR = dQ; g.P0 = dP; g.a0 = nullptr; g.H = dH;
+    g.ybar_obs = dyo; g.status_in = dst1;
+    g.n_draws = c; g.loglik = dll + lo; g.status = dst + lo; g.scratch = nullptr;
+    DYB_CUDA(launch_kalman_generic(g, h->device, h->stream, sg));
+    h->launches += 1;
+  }
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int dyb_lyapunov_batch(int device, int32_t k, const double* A, const double* B, int64_t n, double tol, int32_t maxit,
+                       double* X, int32_t* iters, int32_t* status) {
+  if (k < 1 || n < 0 || maxit < 1 || !(tol >= 0) || (n > 0 && (!A || !B || !X || !status))) return fail(DYB_ERR_ARG, "bad argument");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(device));
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const size_t smem = sizeof(double) * (3 * (size_t)k * k + 8);
+  if (smem + 1024 > (size_t)max_smem) return fail(DYB_ERR_UNSUPPORTED, "k too large for the shared-memory Lyapunov solver");
+  cudaStream_t st = device_stream(device);
+  Stager sg(st);
+  const size_t N = (size_t)n, k2 = (size_t)k * k;
+  LyapunovArgs a{k, sg.in(A, k2 * N), sg.in(B, k2 * N), sg.out(X, k2 * N), sg.out(iters, N), sg.out(status, N), n, tol, maxit};
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  if (smem > 48 * 1024) DYB_CUDA(cudaFuncSetAttribute(lyapunov_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long grid = n < 148LL * 64 ? n : 148LL * 64;
+  lyapunov_generic_kernel<<<(unsigned)grid, 128, smem, st>>>(a);
+  DYB_CUDA(cudaGetLastError());
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+}  // extern "C"

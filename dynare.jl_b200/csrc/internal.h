@@ -136,10 +136,14 @@ struct PriorDev {
   double cst;       // normalising constant of the log-density
 };
 struct Comm;        // NCCL communicator wrapper (sampler.cu)
+struct GenericHost; // run-time model description (generic.cu)
+void generic_release(dyb_handle* h);
 }  // namespace dyb
 
 struct dyb_handle {
-  const dyb::ModelOps* ops = nullptr;
+  const dyb::ModelOps* ops = nullptr;     // null for handles made by dyb_create_generic
+  dyb_model_dims dims{};
+  dyb::GenericHost* generic = nullptr;    // generic.cu
   int device = 0;
   cudaStream_t stream = nullptr;        // stream in use
   cudaStream_t own_stream = nullptr;    // the handle's private stream

@@ -20,6 +20,8 @@ struct KalmanGenericArgs {
   const double* P0;        // ns x ns per draw
   const double* a0;        // ns per draw or null
   const double* H;         // ny x ny per draw or null
+  const double* ybar_obs;  // ny per draw or null: steady state of the observables, removed from Y (data.jl:355-363)
+  const int* status_in;    // per draw or null: draws that already failed upstream are passed through
   long long n_draws;
   double* loglik;
   int* status;
@@ -57,6 +59,11 @@ kalman_generic_kernel(KalmanGenericArgs g) {
     const double* QQ = g.RQR + (size_t)d * ns * ns;
     const double* P0 = g.P0 + (size_t)d * ns * ns;
     const double* Hm = g.H ? g.H + (size_t)d * ny * ny : nullptr;
+    const double* yb = g.ybar_obs ? g.ybar_obs + (size_t)d * ny : nullptr;
+    if (g.status_in && g.status_in[d] != ST_OK) {
+      if (tid == 0) { g.loglik[d] = -INFINITY; g.status[d] = g.status_in[d]; }
+      continue;
+    }
     if (tid == 0) bad = 0;
     for (int i = tid; i < ny; i += nt) zi[i] = g.z_idx[i];
     for (int i = tid; i < ns * ns; i += nt) P[i] = P0[i];
@@ -70,7 +77,7 @@ kalman_generic_kernel(KalmanGenericArgs g) {
       // v, F
       for (int i = tid; i < ny; i += nt) {
         const double yi = yt[i];
-        v[i] = isnan(yi) ? 0.0 : yi - a[zi[i]];
+        v[i] = isnan(yi) ? 0.0 : (yi - (yb ? yb[i] : 0.0)) - a[zi[i]];
       }
       for (int e = tid; e < ny * ny; e += nt) {
         const int i = e % ny, j = e / ny;

@@ -246,6 +246,88 @@ class BatchSSWs:
             pass
 
 
+class GenericSSWs:
+    """State-space workspace of a model WITHOUT a generated device function: the host evaluates steady state and
+    Jacobian per draw (as the reference does, src/perturbations.jl:533-561) and this class runs everything after
+    that on the GPU.  Index sets are 0-based, as ``Model`` holds them (src/dynare_containers.jl:110-131)."""
+
+    def __init__(self, n, nx, i_static, i_bkwrd_b, i_fwrd_b, obs_idx, observations=None, device=0):
+        self.lib = L.load()
+        self._idx = [np.ascontiguousarray(a, dtype=np.int32) for a in (i_static, i_bkwrd_b, i_fwrd_b, obs_idx)]
+        d = L.ModelDesc(n, nx, len(self._idx[3]), len(self._idx[0]), len(self._idx[1]), len(self._idx[2]),
+                        *[a.ctypes.data if a.size else None for a in self._idx])
+        h = C.c_void_p()
+        L.check(self.lib.dyb_create_generic(C.byref(d), device, C.byref(h)))
+        self._h = h
+        dm = L.ModelDims()
+        L.check(self.lib.dyb_get_dims(self._h, C.byref(dm)))
+        self.dims = dm.asdict()
+        if observations is not None:
+            self.set_observations(observations)
+
+    set_observations = BatchSSWs.set_observations
+    options = BatchSSWs.options
+    set_options = BatchSSWs.set_options
+    close = BatchSSWs.close
+    __del__ = BatchSSWs.__del__
+
+    def _jac(self, jac):
+        """(N, n, ncol) numpy -> per-draw column-major."""
+        jac = np.asarray(jac, dtype=np.float64)
+        if jac.ndim != 3 or jac.shape[1:] != (self.dims["n"], self.dims["ncol"]):
+            raise ValueError(f"jac must be (N, {self.dims['n']}, {self.dims['ncol']})")
+        return np.ascontiguousarray(jac.transpose(0, 2, 1))
+
+    def _cov(self, S, k):
+        if S is None:
+            return None, 0
+        S = np.asarray(S, dtype=np.float64)
+        if S.shape == (k, k):
+            return np.ascontiguousarray(S.T), 0
+        return np.ascontiguousarray(S.transpose(0, 2, 1)), 1
+
+    def first_order(self, jac, sigma_e):
+        """dict(g1_1, g1_2, T, RQR, P0, cr_iters, lyap_iters, status) from compressed Jacobians (N, n, ncol)."""
+        J = self._jac(jac)
+        n = J.shape[0]
+        d = self.dims
+        Se, per = self._cov(sigma_e, d["nx"])
+        g1 = np.zeros((n, d["k"] + d["nx"], d["n"])); ns = d["ns"]
+        T = np.zeros((n, ns, ns)); Q = np.zeros((n, ns, ns)); P = np.zeros((n, ns, ns))
+        it = np.zeros(n, dtype=np.int32); li = np.zeros(n, dtype=np.int32); st = np.zeros(n, dtype=np.int32)
+        L.check(self.lib.dyb_first_order_from_jacobian_batch(self._h, L.ptr(J), L.ptr(Se), per, n, L.ptr(g1), L.ptr(T),
+                                                             L.ptr(Q), L.ptr(P), L.ptr(it), L.ptr(li), L.ptr(st)))
+        g1 = g1.transpose(0, 2, 1)
+        tr = lambda a: a.transpose(0, 2, 1)
+        return dict(g1_1=g1[:, :, :d["k"]], g1_2=g1[:, :, d["k"]:], T=tr(T), RQR=tr(Q), P0=tr(P), cr_iters=it,
+                    lyap_iters=li, status=st)
+
+    def loglikelihood(self, jac, ybar, sigma_e, sigma_m=None, status_in=None):
+        """(loglik[N], status[N]) from host-evaluated Jacobians and steady states (N, n)."""
+        J = self._jac(jac)
+        n = J.shape[0]
+        d = self.dims
+        yb = None if ybar is None else _f64(ybar, (n, d["n"]))
+        Se, pe = self._cov(sigma_e, d["nx"])
+        Sm, pm = self._cov(sigma_m, d["ny"])
+        si = None if status_in is None else np.ascontiguousarray(status_in, dtype=np.int32)
+        ll = np.empty(n); st = np.empty(n, dtype=np.int32)
+        L.check(self.lib.dyb_loglik_from_jacobian_batch(self._h, L.ptr(J), L.ptr(yb), L.ptr(Se), pe, L.ptr(Sm), pm,
+                                                        L.ptr(si), n, L.ptr(ll), L.ptr(st)))
+        return ll, st
+
+
+def lyapunov_batch(A, B, tol=1e-16, maxit=60, device=0):
+    """Batched doubling solve of X = A X A' + B: A, B (N, k, k).  Returns (X, iters, status)."""
+    A = np.asarray(A, dtype=np.float64); B = np.asarray(B, dtype=np.float64)
+    n, k, _ = A.shape
+    cm = lambda a: np.ascontiguousarray(a.transpose(0, 2, 1))
+    Ac, Bc = cm(A), cm(B)                    # keep the column-major copies alive across the call
+    X = np.empty((n, k, k)); it = np.empty(n, dtype=np.int32); st = np.empty(n, dtype=np.int32)
+    L.check(L.load().dyb_lyapunov_batch(device, k, L.ptr(Ac), L.ptr(Bc), n, tol, maxit, L.ptr(X), L.ptr(it), L.ptr(st)))
+    return X.transpose(0, 2, 1), it, st
+
+
 class DSGELogPosteriorDensity:
     """Batched analogue of the reference callable (estimation.jl:439-453, 503-515):
     ``logprior(theta) + loglikelihood(theta)``, ``-inf`` for any failed draw."""

@@ -155,6 +155,42 @@ int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t p
                      const double* T, const double* RQR, const double* P0, const double* a0,
                      const double* H, int64_t n_draws, double* loglik, int32_t* status);
 
+/* ---- models without a generated device function -----------------------------------------------------------
+ * The host evaluates steady state and Jacobian per draw (compute_steady_state!, get_dynamic_jacobian!,
+ * set_compressed_jacobian!: src/steady_state/SteadyState.jl:183-252, src/model.jl:120-139,
+ * src/perturbations.jl:616-635) -- e.g. on Julia threads -- and uploads them; everything after that runs here.
+ * dyb_model_desc carries what `Model` / `LRE.Indices` / `SSWs` carry (src/dynare_containers.jl:110-131, 602;
+ * src/estimation/estimation.jl:384-390): strictly increasing 0-based variable indices. */
+typedef struct dyb_model_desc {
+  int32_t n, nx, ny;
+  int32_t n_static, n_bkwrd_b, n_fwrd_b;
+  const int32_t* i_static;    /* variables appearing only at the current period */
+  const int32_t* i_bkwrd_b;   /* variables with a lag (backward and both) = the solution's state columns */
+  const int32_t* i_fwrd_b;    /* variables with a lead (forward and both) */
+  const int32_t* obs_idx;     /* ny: observed variable of each row of Y, in varobs order */
+} dyb_model_desc;
+/* a handle with run-time sizes; dyb_set_observations / dyb_set_options / dyb_get_dims / dyb_destroy apply, the
+ * theta-based entry points return DYB_ERR_UNSUPPORTED */
+int dyb_create_generic(const dyb_model_desc* desc, int device, dyb_handle** out);
+/* LRE.first_order_solver! + compute_variance! + state-space assembly from compressed Jacobians
+ * (n x ncol per draw, column-major, columns [lags of i_bkwrd_b | all n current | leads of i_fwrd_b | nx shocks]).
+ * sigma_e: nx x nx, one per draw (sigma_e_per_draw != 0) or shared.  Outputs per draw (any may be NULL):
+ * g1 n x (k+nx), T / RQR / P0 ns x ns, iterations taken. */
+int dyb_first_order_from_jacobian_batch(dyb_handle* h, const double* jac, const double* sigma_e,
+                                        int32_t sigma_e_per_draw, int64_t n_draws, double* g1, double* T,
+                                        double* RQR, double* P0, int32_t* cr_iters, int32_t* lyap_iters,
+                                        int32_t* status);
+/* loglikelihood (src/estimation/estimation.jl:603-702) from host-evaluated Jacobians: ybar n per draw (NULL = 0)
+ * for the detrending of the observables, sigma_m ny x ny per draw / shared / NULL (= 0), status_in (NULL = all ok)
+ * marks draws whose steady state already failed on the host (passed through with loglik = -Inf) */
+int dyb_loglik_from_jacobian_batch(dyb_handle* h, const double* jac, const double* ybar, const double* sigma_e,
+                                   int32_t sigma_e_per_draw, const double* sigma_m, int32_t sigma_m_per_draw,
+                                   const int32_t* status_in, int64_t n_draws, double* loglik, int32_t* status);
+/* batched doubling solve of X = A X A' + B (k x k per draw): the solver behind compute_variance!
+ * (src/estimation/estimation.jl:630); tol = relative increment at which doubling stops, status 5 when it diverges */
+int dyb_lyapunov_batch(int device, int32_t k, const double* A, const double* B, int64_t n_draws, double tol,
+                       int32_t maxit, double* X, int32_t* iters, int32_t* status);
+
 /* ---- SMC primitives on device (src/estimation/smc.jl) -------------------------------------------- */
 /* correction step (smc.jl:118-123) + ESS (smc.jl:129): w_out = w * exp(dphi * loglh) / zhat */
 int dyb_smc_reweight(int device, const double* w, const double* loglh, double dphi, int64_t n,

@@ -41,7 +41,8 @@ def kalman_flops_per_eval(ns, ny, nx, nobs):
     return w_kf * nobs + w_qq
 
 
-def solve_flops_per_eval(d, cr_it, lyap_it):
+def solve_flops_split(d, cr_it, lyap_it):
+    """(static elimination, cyclic reduction + g_u, Lyapunov + assembly): the three kernels of the solve stage."""
     n, k, s, nx, nf, ns = d["n"], d["k"], d["s"], d["nx"], d["nf"], d["ns"]
     m = n - s
     ncol = d["ncol"]
@@ -49,7 +50,26 @@ def solve_flops_per_eval(d, cr_it, lyap_it):
     w_static = 2 * n * s ** 2 - (2.0 / 3.0) * s ** 3 + 4 * n * s * (ncol - s)
     w_gu = 2 * n ** 2 * nf + (2.0 / 3.0) * n ** 3 + 2 * n ** 2 * nx
     w_lyap = 6 * k ** 3 * lyap_it + 2 * ns * k * (k + ns) + 2 * ns * nx * (nx + ns)
-    return w_cr + w_static + w_gu + w_lyap
+    return w_static, w_cr + w_gu, w_lyap
+
+
+def solve_flops_per_eval(d, cr_it, lyap_it):
+    return sum(solve_flops_split(d, cr_it, lyap_it))
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/*_ncu_summary.json)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            for name, v in d.get("kernels", {}).items():
+                if name.startswith(kernel.split("<")[0]):
+                    return {"bytes": v["dram_bytes"], "source": os.path.relpath(path, ROOT)}
+        except Exception:
+            continue
+    return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -241,6 +261,7 @@ def run_ours(args):
         barrier()
         t1 = time.time()
         dev_ms = e0.elapsed_time(e1)
+        model_ms, cr_ms, asm_ms = ws.timers_read_solve_split()
         nb, solve_ms, filter_ms = ws.timers_read()
         launches = ws.kernel_launches() - launches0
         clocks = sampler.stop(t0, t1) if rank == 0 else None
@@ -286,25 +307,34 @@ def run_ours(args):
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         fp64 = fp64_peak(local)
         k_solve = solve_ms / max(nb, 1); k_filt = filter_ms / max(nb, 1)
+        fl_static, fl_cr, fl_asm = solve_flops_split(d, cr_it, ly_it)
+        mid = d["mid_doubles"]                     # doubles per draw between the solve kernels
+
+        def kern(name, ms_total, flop, bytes_):
+            ms = ms_total / max(nb, 1)
+            return {"name": name, "ms_per_launch": ms, "flop_per_launch": flop * n,
+                    "tflops": flop * n / (ms * 1e-3) / 1e12 if ms > 0 else None, "hbm_bytes_per_launch": n * bytes_}
         kernels = [
-            {"name": "solve_kernel<fs2000>", "ms_per_launch": k_solve, "flop_per_launch": fl_sol * n,
-             "tflops": fl_sol * n / (k_solve * 1e-3) / 1e12 if k_solve > 0 else None,
-             "hbm_bytes_per_launch": n * (npar * 8 + d["ss_doubles"] * 8 + 4)},
-            {"name": "kalman_kernel<fs2000>", "ms_per_launch": k_filt, "flop_per_launch": fl_kal * n,
-             "tflops": fl_kal * n / (k_filt * 1e-3) / 1e12 if k_filt > 0 else None,
-             "hbm_bytes_per_launch": n * (d["ss_doubles"] * 8 + 4 + 12)},
+            kern(f"model_kernel<{MODEL}>", model_ms, fl_static, npar * 8 + mid * 8 + 4),
+            kern(f"cr_kernel<{MODEL},4>", cr_ms, fl_cr, mid * 8 + 4),
+            kern(f"assemble_kernel<{MODEL}>", asm_ms, fl_asm, mid * 8 + d["ss_doubles"] * 8 + 4),
+            kern(f"kalman_kernel<{MODEL}>", filter_ms, fl_kal, d["ss_doubles"] * 8 + 4 + 12),
         ]
+        if cr_ms == 0.0:      # one-kernel solver path
+            kernels = [kern(f"solve_kernel<{MODEL}>", solve_ms, fl_sol, npar * 8 + d["ss_doubles"] * 8 + 4), kernels[3]]
         dom = max(kernels, key=lambda kx: kx["ms_per_launch"])
+        traffic = ncu_traffic(dom["name"])
         roofline = {
             "kernel": dom["name"], "bound": "fp64", "achieved": dom["tflops"], "peak": fp64, "unit": "TFLOP/s",
-            "frac": dom["tflops"] / fp64 if fp64 > 0 else None, "traffic": None,
+            "frac": dom["tflops"] / fp64 if fp64 > 0 else None,
+            "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
             "peak_source": "measured live: dyb_fp64_peak DFMA microbenchmark (MEASURED_PEAKS.json has no fp64 figure)",
             "algorithmic_flop_per_eval": {"kalman": fl_kal, "solve": fl_sol, "cr_iters_mean": cr_it, "lyap_iters_mean": ly_it},
             "hbm": {"achieved": dom["hbm_bytes_per_launch"] / (dom["ms_per_launch"] * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
                     "frac": dom["hbm_bytes_per_launch"] / (dom["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak},
             "kernels": kernels,
-            "kernel_share_of_step": {"solve": k_solve / step_ms, "filter": k_filt / step_ms},
+            "kernel_share_of_step": {kx["name"]: kx["ms_per_launch"] / step_ms for kx in kernels},
         }
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,

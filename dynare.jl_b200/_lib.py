@@ -23,7 +23,7 @@ class DybError(RuntimeError):
 
 class ModelDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("n", "nx", "npar", "k", "nf", "s", "ncol", "ns", "ny", "np_default", "ss_doubles")]
+                ("n", "nx", "npar", "k", "nf", "s", "ncol", "ns", "ny", "np_default", "ss_doubles", "mid_doubles")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -79,6 +79,7 @@ SIGNATURES = {
     "dyb_set_stream": (C.c_int, [_P, C.c_void_p]),
     "dyb_kernel_timers_reset": (C.c_int, [_P]),
     "dyb_kernel_timers_read": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "dyb_kernel_timers_read_solve_split": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "dyb_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "dyb_state_space_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D, _D, _D, _D, _I32]),
     "dyb_kalman_batch": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _D,

@@ -190,7 +190,7 @@ int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, dou
   if (rc) return rc;
   SolveOut so{h->d_ss.as<double>(), h->d_st1.as<int>(), nullptr, nullptr, nullptr, nullptr, h->d_mid.as<double>()};
   cudaEvent_t* ev = h->timers_armed ? timer_slot(h) : nullptr;
-  if (ev) h->timer_n += 1; else ev = h->ev;
+  if (ev) { h->timer_n += 1; so.ev_after_model = ev[3]; so.ev_after_cr = ev[4]; } else ev = h->ev;
   DYB_CUDA(cudaEventRecord(ev[0], h->stream));
   DYB_CUDA(h->ops->solve(h->hs, d_theta, n, so, h->stream));
   DYB_CUDA(cudaEventRecord(ev[1], h->stream));
@@ -205,12 +205,12 @@ int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, dou
 // timed variant used when the accumulating timers are armed: records into the timer ring instead
 static cudaEvent_t* timer_slot(dyb_handle* h) {
   if (h->timer_n >= 4096) return nullptr;
-  while ((int)h->timer_ev.size() < 3 * (h->timer_n + 1)) {
+  while ((int)h->timer_ev.size() < 5 * (h->timer_n + 1)) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
     h->timer_ev.push_back(e);
   }
-  return &h->timer_ev[3 * h->timer_n];
+  return &h->timer_ev[5 * h->timer_n];
 }
 
 int dyb_loglik_batch(dyb_handle* h, const double* theta, int64_t n, double* loglik, int32_t* status) {
@@ -293,14 +293,36 @@ int dyb_kernel_timers_read(dyb_handle* h, int32_t* n_batches, float* solve_ms_to
   float a = 0, b = 0;
   for (int i = 0; i < h->timer_n; ++i) {
     float x = 0, y = 0;
-    DYB_CUDA(cudaEventElapsedTime(&x, h->timer_ev[3 * i], h->timer_ev[3 * i + 1]));
-    DYB_CUDA(cudaEventElapsedTime(&y, h->timer_ev[3 * i + 1], h->timer_ev[3 * i + 2]));
+    DYB_CUDA(cudaEventElapsedTime(&x, h->timer_ev[5 * i], h->timer_ev[5 * i + 1]));
+    DYB_CUDA(cudaEventElapsedTime(&y, h->timer_ev[5 * i + 1], h->timer_ev[5 * i + 2]));
     a += x; b += y;
   }
   if (n_batches) *n_batches = h->timer_n;
   if (solve_ms_total) *solve_ms_total = a;
   if (filter_ms_total) *filter_ms_total = b;
   h->timers_armed = false;
+  return DYB_OK;
+}
+
+// split of the solve stage of the armed batches: model set-up (steady state, Jacobian, static elimination), cyclic
+// reduction (+ g_u), assembly (static rows, Lyapunov, state space); all zero on the one-kernel solver path
+int dyb_kernel_timers_read_solve_split(dyb_handle* h, float* model_ms_total, float* cr_ms_total, float* assemble_ms_total) {
+  if (!h) return fail(DYB_ERR_ARG, "null handle");
+  DYB_CUDA(cudaSetDevice(h->device));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  float m = 0, c = 0, s = 0;
+  if (h->ops && h->ops->solve_launches(h->hs) == 3) {
+    for (int i = 0; i < h->timer_n; ++i) {
+      float x = 0, y = 0, z = 0;
+      DYB_CUDA(cudaEventElapsedTime(&x, h->timer_ev[5 * i], h->timer_ev[5 * i + 3]));
+      DYB_CUDA(cudaEventElapsedTime(&y, h->timer_ev[5 * i + 3], h->timer_ev[5 * i + 4]));
+      DYB_CUDA(cudaEventElapsedTime(&z, h->timer_ev[5 * i + 4], h->timer_ev[5 * i + 1]));
+      m += x; c += y; s += z;
+    }
+  }
+  if (model_ms_total) *model_ms_total = m;
+  if (cr_ms_total) *cr_ms_total = c;
+  if (assemble_ms_total) *assemble_ms_total = s;
   return DYB_OK;
 }
 

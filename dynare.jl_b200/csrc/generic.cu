@@ -148,7 +148,7 @@ int dyb_create_generic(const dyb_model_desc* md, int device, dyb_handle** out) {
 
   dyb_handle* h = new dyb_handle();
   h->device = device;
-  h->dims = dyb_model_dims{n, nx, 0, k, nf, s, ncol, ns, ny, 0, 0};
+  h->dims = dyb_model_dims{n, nx, 0, k, nf, s, ncol, ns, ny, 0, 0, 0};
   h->hs.np = 0;
   h->hs.opt.cr_tol = 1e-8; h->hs.opt.cr_maxit = 100; h->hs.opt.steady_tol = std::cbrt(2.220446049250313e-16);
   h->hs.opt.lyap_tol = 1e-16; h->hs.opt.lyap_maxit = 60; h->hs.opt.presample = 0; h->hs.opt.solver = 0;

@@ -45,9 +45,11 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
   const bool coop = mt_coop_fits && hs.opt.solver != 1;
   if (coop) {
     model_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.mid, out.status, out.ybar);
+    if (out.ev_after_model) cudaEventRecord(out.ev_after_model, st);
     const long long gridc = (n * G + block - 1) / block;
     CrOptions co{hs.opt.cr_tol, hs.opt.cr_maxit};
     cr_kernel<MT, G><<<(unsigned)gridc, block, 0, st>>>(out.mid, n, co, out.status, out.cr_iters);
+    if (out.ev_after_cr) cudaEventRecord(out.ev_after_cr, st);
     assemble_kernel<MT><<<(unsigned)grid, block, 0, st>>>(out.mid, n, hs.opt.lyap_tol, hs.opt.lyap_maxit, out.ss,
                                                           out.status, out.g1, out.lyap_iters);
   } else {
@@ -99,7 +101,7 @@ cudaError_t mt_unpack(const double* d_ss, long long n, double* T, double* RQR, d
 
 const ModelOps mt_ops = {
   MT::name,
-  {MT::N, MT::NX, MT::NPAR, MT::K, MT::NF, MT::S, MT::NCOL, MT::NS, MT::NY, MT::NP_DEFAULT, SSLayout<MT>::SIZE},
+  {MT::N, MT::NX, MT::NPAR, MT::K, MT::NF, MT::S, MT::NCOL, MT::NS, MT::NY, MT::NP_DEFAULT, SSLayout<MT>::SIZE, MidLayout<MT>::SIZE},
   MidLayout<MT>::SIZE,
   mt_defaults, mt_solve_launches, mt_solve, mt_kalman, mt_unpack
 };

@@ -24,6 +24,7 @@ struct SolveOut {
   int* cr_iters;
   int* lyap_iters;
   double* mid;       // scratch for the cooperative solver, mid_doubles x N (device)
+  cudaEvent_t ev_after_model = nullptr, ev_after_cr = nullptr;   // optional timing marks between the solver's kernels
 };
 
 struct ModelOps {

@@ -168,6 +168,12 @@ class BatchSSWs:
         L.check(self.lib.dyb_kernel_timers_read(self._h, C.byref(n), C.byref(a), C.byref(b)))
         return n.value, a.value, b.value
 
+    def timers_read_solve_split(self):
+        """(model set-up ms, cyclic-reduction ms, assembly ms) totals of the armed batches; call before timers_read."""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        L.check(self.lib.dyb_kernel_timers_read_solve_split(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def kernel_launches(self) -> int:
         return int(self.lib.dyb_kernel_launches(self._h))
 

@@ -66,6 +66,7 @@ typedef struct dyb_model_dims {
   int32_t ny;       /* observables */
   int32_t np_default; /* estimated parameters declared in the model file */
   int32_t ss_doubles; /* doubles per draw handed from the solve stage to the filter stage */
+  int32_t mid_doubles; /* doubles per draw exchanged between the kernels of the solve stage */
 } dyb_model_dims;
 
 /* Numerical options (reference: StochSimulOptions src/perturbations.jl:1-45, SteadyOptions tolf
@@ -129,6 +130,10 @@ int dyb_last_kernel_ms(dyb_handle* h, float* solve_ms, float* filter_ms);
  * reset (up to 4096 batches); read synchronises the stream */
 int dyb_kernel_timers_reset(dyb_handle* h);
 int dyb_kernel_timers_read(dyb_handle* h, int32_t* n_batches, float* solve_ms_total, float* filter_ms_total);
+/* split of the armed batches' solve stage into its three kernels (model set-up, cyclic reduction, assembly);
+ * call before dyb_kernel_timers_read; zeros on the one-kernel solver path */
+int dyb_kernel_timers_read_solve_split(dyb_handle* h, float* model_ms_total, float* cr_ms_total,
+                                       float* assemble_ms_total);
 /* measured fp64 FMA throughput of the device (TFLOP/s) from a register-resident DFMA loop on all SMs:
  * the roofline denominator for this path, which MEASURED_PEAKS.json does not carry */
 int dyb_fp64_peak(int device, double* tflops);

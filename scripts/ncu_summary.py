@@ -50,6 +50,39 @@ def full(path):
                 print(f"   {w:85s} {r[i]:>16s} {units[i]}")
 
 
+def summary_json(rep, out_path):
+    """profiles/*_ncu_summary.json: the per-kernel figures bench.py reads for `roofline.traffic`."""
+    import json
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, u = rows[0], rows[1]
+    want = {"gpu__time_duration.sum": "duration_us", "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
+            "launch__registers_per_thread": "registers", "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_active_pct",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct", "smsp__inst_executed.sum": "warp_instructions",
+            "lts__t_sector_hit_rate.pct": "l2_hit_pct"}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = {"capture": f"ncu --set full --clock-control none --import-source on ({rep})", "kernels": {}}
+    for r in rows[2:]:
+        name = r[h.index("Kernel Name")].split("(")[0].replace("void ", "").replace("dyb::", "").replace("Model_", "")
+        d = {}
+        for k, v in want.items():
+            if k in h:
+                i = h.index(k)
+                x = float(r[i].replace(",", ""))
+                if v.startswith("dram"):
+                    d[v + "_bytes"] = x * scale[u[i]]
+                else:
+                    d[v] = x
+        d["dram_bytes"] = d.get("dram_read_bytes", 0) + d.get("dram_write_bytes", 0)
+        out["kernels"][name] = d
+    with open(out_path, "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
-    for a in sys.argv[1:]:
-        (launches if a.endswith(".csv") else full)(a)
+    if len(sys.argv) == 4 and sys.argv[1] == "--json":
+        summary_json(sys.argv[2], sys.argv[3])
+    else:
+        for a in sys.argv[1:]:
+            (launches if a.endswith(".csv") else full)(a)

@@ -81,6 +81,7 @@ SIGNATURES = {
     "dyb_kernel_timers_read": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "dyb_kernel_timers_read_solve_split": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "dyb_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "dyb_fp64_peak_dmma": (C.c_int, [C.c_int, C.c_int32, C.POINTER(C.c_double)]),
     "dyb_state_space_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D, _D, _D, _D, _I32]),
     "dyb_kalman_batch": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _D,
                                    _D, _D, _D, _D, _D, C.c_int64, _D, _I32]),
@@ -89,6 +90,7 @@ SIGNATURES = {
     "dyb_smc_resample_multinomial": (C.c_int, [C.c_int, _D, _D, C.c_int64, _I64, C.POINTER(C.c_int64)]),
     "dyb_smc_resample_systematic": (C.c_int, [C.c_int, _D, C.c_double, C.c_int64, _I64, C.POINTER(C.c_int64)]),
     "dyb_smc_moments": (C.c_int, [C.c_int, _D, _D, C.c_int64, C.c_int32, _D, _D]),
+    "dyb_set_kalman_variant": (C.c_int, [C.c_int32]),
     "dyb_create_generic": (C.c_int, [C.POINTER(ModelDesc), C.c_int, C.POINTER(_P)]),
     "dyb_first_order_from_jacobian_batch": (C.c_int, [_P, _D, _D, C.c_int32, C.c_int64, _D, _D, _D, _D, _I32, _I32, _I32]),
     "dyb_loglik_from_jacobian_batch": (C.c_int, [_P, _D, _D, _D, C.c_int32, _D, C.c_int32, _I32, C.c_int64, _D, _I32]),

@@ -44,6 +44,50 @@ static void default_options(dyb_options* o) {
   o->solver = 0;
 }
 
+namespace dyb {
+// fp64 tensor-core microbenchmark: SHAPE 0 = mma.m8n8k4 (256 FMA / warp instruction), 1 = mma.m16n8k16 (2048 FMA);
+// 4 independent accumulator tiles per warp, operands constant in registers
+template <int SHAPE>
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double seed) {
+  const double a0 = seed + 1e-3 * threadIdx.x, b0 = 1.0 - 1e-3 * threadIdx.x;
+  if (SHAPE == 0) {
+    double c[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { c[t][0] = t; c[t][1] = -t; }
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a0), "d"(b0));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) s += c[t][0] + c[t][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+  } else {
+    double c[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { c[t][0] = t; c[t][1] = -t; c[t][2] = 2 * t; c[t][3] = 1; }
+    const double a[8] = {a0, a0 + 1, a0 + 2, a0 + 3, a0 + 4, a0 + 5, a0 + 6, a0 + 7};
+    const double b[4] = {b0, b0 + 1, b0 + 2, b0 + 3};
+#pragma unroll 2
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                     : "+d"(c[t][0]), "+d"(c[t][1]), "+d"(c[t][2]), "+d"(c[t][3])
+                     : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+                       "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) s += c[t][0] + c[t][1] + c[t][2] + c[t][3];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+  }
+}
+}  // namespace dyb
+
 extern "C" {
 
 int dyb_version(void) { return DYB_VERSION; }
@@ -339,6 +383,37 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 }  // namespace dyb
+
+// measured fp64 TENSOR-core throughput (TFLOP/s): shape 0 = m8n8k4, 1 = m16n8k16
+int dyb_fp64_peak_dmma(int device, int32_t shape, double* tflops) {
+  if (!tflops || shape < 0 || shape > 1) return fail(DYB_ERR_ARG, "bad argument");
+  DYB_CUDA(cudaSetDevice(device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  double* out = nullptr;
+  DYB_CUDA(cudaMalloc(&out, sizeof(double) * blocks * threads));
+  cudaStream_t st = device_stream(device);
+  cudaEvent_t e0, e1;
+  DYB_CUDA(cudaEventCreate(&e0)); DYB_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    DYB_CUDA(cudaEventRecord(e0, st));
+    if (shape == 0) dmma_peak_kernel<0><<<blocks, threads, 0, st>>>(out, iters, 1.0 + rep);
+    else dmma_peak_kernel<1><<<blocks, threads, 0, st>>>(out, iters, 1.0 + rep);
+    DYB_CUDA(cudaEventRecord(e1, st));
+    DYB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    DYB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double fma_per_instr = shape == 0 ? 256.0 : 2048.0;
+    const double fl = 2.0 * fma_per_instr * 4.0 * iters * (double)blocks * (threads / 32);
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops = best;
+  return DYB_OK;
+}
 
 int dyb_fp64_peak(int device, double* tflops) {
   if (!tflops) return fail(DYB_ERR_ARG, "null argument");

@@ -5,6 +5,7 @@
 
 #include "internal.h"
 #include "kalman_generic.cuh"
+#include "kalman_dmma.cuh"
 #include "solve_generic.cuh"
 
 namespace dyb {
@@ -26,10 +27,34 @@ void generic_release(dyb_handle* h) {
 
 // launch the dense Kalman filter on device-resident state spaces (shared by dyb_kalman_batch and the
 // from-Jacobian likelihood); scratch (2 ns^2 doubles per CTA) only when P and T P do not fit in shared memory
+static int g_kalman_variant = 0;      // 0 auto, 1 scalar (kalman_generic.cuh), 2 tensor-core (kalman_dmma.cuh)
+
 static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaStream_t st, Stager& sg) {
   int dev_sms = 148, max_smem = 0;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  {
+    const KalmanDmmaGeom q = kalman_dmma_geom(g.ns, g.ny);
+    const size_t smem = sizeof(double) * kalman_dmma_smem_doubles(g.ns, g.ny);
+    const bool fits = q.nsp / 8 <= DMMA_MAX_TILES && smem + 1024 <= (size_t)max_smem;
+    if (fits && (g_kalman_variant == 2 || (g_kalman_variant == 0 && g.ns > 8))) {
+      long long grid = g.n_draws < (long long)dev_sms * 32 ? g.n_draws : (long long)dev_sms * 32;
+      g.scratch = nullptr;
+      const int ntile = q.nsp / 8;
+      auto launch = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return e;
+        }
+        kern<<<(unsigned)grid, 32 * ntile, smem, st>>>(g, q);
+        return cudaGetLastError();
+      };
+      if (ntile <= 3) return launch(kalman_dmma_kernel<3>);
+      if (ntile <= 5) return launch(kalman_dmma_kernel<5>);
+      if (ntile <= 8) return launch(kalman_dmma_kernel<8>);
+      return launch(kalman_dmma_kernel<DMMA_MAX_TILES>);
+    }
+  }
   const size_t ns2 = (size_t)g.ns * g.ns;
   const size_t small = sizeof(double) * ((size_t)g.ny * g.ns + (size_t)g.ny * g.ny + 2 * (size_t)g.ns + 2 * (size_t)g.ny + 32);
   const size_t full = small + sizeof(double) * 2 * ns2;
@@ -91,6 +116,12 @@ int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t p
   return DYB_OK;
 }
 
+
+int dyb_set_kalman_variant(int32_t variant) {
+  if (variant < 0 || variant > 2) return fail(DYB_ERR_ARG, "variant must be 0 (auto), 1 (scalar) or 2 (tensor-core)");
+  g_kalman_variant = variant;
+  return DYB_OK;
+}
 
 // ---- handle from index sets alone --------------------------------------------------------------------------------
 int dyb_create_generic(const dyb_model_desc* md, int device, dyb_handle** out) {

@@ -360,6 +360,18 @@ def fp64_peak(device=0) -> float:
     return t.value
 
 
+def fp64_peak_dmma(shape=0, device=0) -> float:
+    """Measured fp64 tensor-core peak (TFLOP/s): shape 0 = mma.m8n8k4, 1 = mma.m16n8k16."""
+    t = C.c_double()
+    L.check(L.load().dyb_fp64_peak_dmma(device, shape, C.byref(t)))
+    return t.value
+
+
+def set_kalman_variant(variant: int):
+    """0 auto, 1 scalar dense filter kernel, 2 tensor-core (DMMA) kernel."""
+    L.check(L.load().dyb_set_kalman_variant(variant))
+
+
 def kalman_batch(Y, z_idx, T, RQR, P0, a0=None, H=None, presample=0, device=0):
     """Generic batched Kalman log-likelihood.  T, RQR, P0: (N, ns, ns) numpy (row-major per draw);
     Y: ny x nobs; z_idx: state observed by each row.  Returns (loglik[N], status[N])."""

@@ -137,6 +137,8 @@ int dyb_kernel_timers_read_solve_split(dyb_handle* h, float* model_ms_total, flo
 /* measured fp64 FMA throughput of the device (TFLOP/s) from a register-resident DFMA loop on all SMs:
  * the roofline denominator for this path, which MEASURED_PEAKS.json does not carry */
 int dyb_fp64_peak(int device, double* tflops);
+/* same for the fp64 tensor-core path (mma.sync ... f64): shape 0 = m8n8k4, 1 = m16n8k16 */
+int dyb_fp64_peak_dmma(int device, int32_t shape, double* tflops);
 
 /* ---- stage-level entry points (host pointers) ---------------------------------------------------- */
 /* LRE.first_order_solver! (src/perturbations.jl:663-664): g1 = [g1_1 | g1_2], n x (k+nx) per draw,
@@ -159,6 +161,10 @@ int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t p
                      const int32_t* z_idx, const double* Y,
                      const double* T, const double* RQR, const double* P0, const double* a0,
                      const double* H, int64_t n_draws, double* loglik, int32_t* status);
+
+/* which dense filter kernel dyb_kalman_batch / dyb_loglik_from_jacobian_batch use: 0 auto (tensor-core kernel for
+ * 8 < ns <= 88, scalar kernel otherwise), 1 scalar, 2 tensor-core (fp64 mma.sync); process-wide, for A/B tests */
+int dyb_set_kalman_variant(int32_t variant);
 
 /* ---- models without a generated device function -----------------------------------------------------------
  * The host evaluates steady state and Jacobian per draw (compute_steady_state!, get_dynamic_jacobian!,

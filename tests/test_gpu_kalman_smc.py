@@ -22,15 +22,23 @@ def _random_state_space(rng, n, ns, ny, nx):
     return T, RQR, P0, H
 
 
-@pytest.mark.parametrize("ns,ny,nobs,n", [(6, 2, 50, 40), (40, 7, 60, 12), (110, 20, 12, 3)])
-def test_generic_kalman_matches_oracle(ns, ny, nobs, n):
-    from dynare_jl_b200.engine import kalman_batch
+@pytest.mark.parametrize("ns,ny,nobs,n,variant", [
+    (6, 2, 50, 40, 0), (6, 2, 50, 40, 2), (40, 7, 60, 12, 1), (40, 7, 60, 12, 2), (24, 5, 30, 9, 2), (37, 9, 25, 7, 2),
+    (64, 12, 20, 5, 2), (88, 20, 10, 3, 2), (110, 20, 12, 3, 0), (200, 20, 6, 2, 0)])
+def test_generic_kalman_matches_oracle(ns, ny, nobs, n, variant):
+    """variant 1 = scalar kernel, 2 = tensor-core (DMMA) kernel, 0 = automatic choice; sizes of BASELINE configs 4
+    (ns 40, ny 7) and 5 (ns 200, ny 20) included."""
+    from dynare_jl_b200.engine import kalman_batch, set_kalman_variant
+    set_kalman_variant(variant)
     rng = np.random.default_rng(ns)
     T, RQR, P0, H = _random_state_space(rng, n, ns, ny, ny)
     z = np.arange(ny)[::-1].copy() if ns < 20 else np.arange(ny)
     Y = rng.standard_normal((ny, nobs))
     Y[0, 3] = np.nan
+    if nobs > 8:
+        Y[:, 5] = np.nan                       # a period without any observation
     ll, st = kalman_batch(Y, z, T, RQR, P0, H=H)
+    set_kalman_variant(0)
     Z = np.zeros((ny, ns)); Z[np.arange(ny), z] = 1
     for i in range(n):
         ref = pl.kalman_likelihood(Y, Z, H[i], T[i], np.eye(ns), RQR[i], np.zeros(ns), P0[i])

@@ -154,15 +154,16 @@ def cpu_port_rate(Y, budget_s, seed=1):
     """evals/s of the C restatement on all host threads over a bounded sample of the same workload."""
     from oracle import cbuild
     theta = prior_draws(DRAWS_PER_GPU, seed)
-    cbuild.loglik_batch(MODEL, theta[:2048], Y)                  # warm-up + calibration
-    t = time.perf_counter(); _, _, used = cbuild.loglik_batch(MODEL, theta[:8192], Y); dt = time.perf_counter() - t
+    nth = host_cores()                                           # explicit: torchrun exports OMP_NUM_THREADS=1
+    cbuild.loglik_batch(MODEL, theta[:2048], Y, nthreads=nth)    # warm-up + calibration
+    t = time.perf_counter(); _, _, used = cbuild.loglik_batch(MODEL, theta[:8192], Y, nthreads=nth); dt = time.perf_counter() - t
     rate = 8192 / dt
     n = int(min(max(rate * budget_s, 8192), 64 * DRAWS_PER_GPU))
     reps = max(1, int(np.ceil(n / DRAWS_PER_GPU)))
     done, t = 0, time.perf_counter()
     for r in range(reps):
         m = min(DRAWS_PER_GPU, n - done)
-        cbuild.loglik_batch(MODEL, theta[:m], Y)
+        cbuild.loglik_batch(MODEL, theta[:m], Y, nthreads=nth)
         done += m
     dt = time.perf_counter() - t
     return done / dt, used, done
@@ -179,12 +180,13 @@ def run_reference(args):
     Y = load_problem()
     sample = 32768
     theta = prior_draws(sample, 1)
+    nth = host_cores()                                           # explicit: torchrun exports OMP_NUM_THREADS=1
     for _ in range(max(args.warmup, 1)):
-        cbuild.loglik_batch(MODEL, theta[:4096], Y)
+        cbuild.loglik_batch(MODEL, theta[:4096], Y, nthreads=nth)
     t = time.perf_counter()
     used = 1
     for _ in range(args.steps):
-        _, _, used = cbuild.loglik_batch(MODEL, theta, Y)
+        _, _, used = cbuild.loglik_batch(MODEL, theta, Y, nthreads=nth)
     dt = time.perf_counter() - t
     val = args.steps * sample / dt
     line = {

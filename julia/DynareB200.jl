@@ -89,4 +89,75 @@ function multinomial_resampling(w::Vector{Float64}, u::Vector{Float64}; device =
     return idx .+ 1
 end
 
+
+# ---- priors, log-posterior (src/estimation/estimation.jl:455-462, 503-515) ---------------------------------------
+# shape codes are the reference's own (src/estimation/priors.jl:482-529); (a, b) = params(prior) of the Distribution
+const SHAPE = Dict(:Beta => 1, :Gamma => 2, :Normal => 3, :InverseGamma1 => 4, :Uniform => 5, :InverseGamma => 6, :Weibull => 8)
+function set_priors!(ws::BatchSSWs, priors::Vector)
+    shape = Int32[SHAPE[nameof(typeof(p))] for p in priors]
+    ab = [Float64.(params(p)) for p in priors]           # Distributions.params: (a, b) / (μ, σ) / (α, θ)
+    a = Float64[x[1] for x in ab]; b = Float64[x[2] for x in ab]
+    check(ccall((:dyb_set_priors, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+                ws.handle, length(shape), shape, a, b))
+end
+"Batched `(problem::DSGELogPosteriorDensity)(θ)`: one column of Θ per draw, `-Inf` for failed draws."
+function logposterior!(out::Vector{Float64}, Θ::Matrix{Float64}, ws::BatchSSWs)
+    GC.@preserve out Θ check(ccall((:dyb_logposterior_batch, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}), ws.handle, Θ, size(Θ, 2), out, C_NULL, C_NULL))
+    return out
+end
+
+# ---- SMC with device-resident particles: replaces `smc(pdraw!, logprior, loglikelihood, names, np)` (smc.jl:64-313) ----
+struct SmcOptions          # mirrors dyb_smc_options; defaults = Tune (smc.jl:13-62)
+    npart::Int64; nphi::Int32; lam::Float64; c0::Float64; acpt0::Float64; trgt::Float64; alp::Float64
+    resampling::Int32; seed::UInt64
+end
+function smc(ws::BatchSSWs, pdraw!::Function; npart = 1000, nphi = 400, lam = 2.0, seed = 0)
+    opt = Ref(SmcOptions(npart, nphi, lam, 0.5, 0.25, 0.25, 0.9, 0, seed))
+    s = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dyb_smc_create, LIB), Cint, (Ptr{Cvoid}, Ref{SmcOptions}, Ptr{Float64}, Ref{Ptr{Cvoid}}), ws.handle, opt, C_NULL, s))
+    first = Ref{Int64}(0); nloc = Ref{Int64}(0)
+    check(ccall((:dyb_smc_local_range, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), s[], first, nloc))
+    para = Matrix{Float64}(undef, ws.np, nloc[]); st = ones(Int32, nloc[]); θ = Vector{Float64}(undef, ws.np)
+    while any(!=(0), st)                                   # smc.jl:84-101: redraw until the likelihood is finite
+        for j in findall(!=(0), st); pdraw!(θ); para[:, j] .= θ; end
+        check(ccall((:dyb_smc_init, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}), s[], para, st))
+    end
+    check(ccall((:dyb_smc_run, LIB), Cint, (Ptr{Cvoid}, Int32), s[], nphi))      # all stages, asynchronous
+    stats = Matrix{Float64}(undef, 6, nphi); mu = Vector{Float64}(undef, ws.np); R = Matrix{Float64}(undef, ws.np, ws.np)
+    logmdd = Ref(0.0)
+    check(ccall((:dyb_smc_get_stats, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}), s[], stats, mu, R, logmdd))
+    w = Vector{Float64}(undef, nloc[]); loglh = similar(w); logpost = similar(w)
+    check(ccall((:dyb_smc_get_particles, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), s[], para, w, loglh, logpost))
+    ccall((:dyb_smc_destroy, LIB), Cint, (Ptr{Cvoid},), s[])
+    return (para = para, w = w, loglh = loglh, logpost = logpost, stats = stats, mu = mu, R = R, logmdd = logmdd[])
+end
+
+# ---- RWMH on many chains: replaces run_mcmc (estimation.jl:964-989); y np × nchains in the transformed space ----------
+function rwmh!(y::Matrix{Float64}, ws::BatchSSWs, cholcov::Matrix{Float64}, niter::Integer; seed = 0, transformed = true)
+    n = size(y, 2); logp = Vector{Float64}(undef, n); acc = zeros(Int64, n)
+    GC.@preserve y check(ccall((:dyb_rwmh_run, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Int32, UInt32, Int32, Ptr{Float64}, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+        ws.handle, n, 0, niter, 0, transformed ? 1 : 0, cholcov, seed, y, logp, acc, C_NULL, C_NULL))
+    return logp, acc
+end
+
+# ---- several GPUs: one Julia process per GPU (Distributed / MPI); rank 0 creates the id, everyone attaches --------------
+unique_id() = (id = Vector{UInt8}(undef, 128); check(ccall((:dyb_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)); id)
+comm_init!(ws::BatchSSWs, rank, nranks, id::Vector{UInt8}) =
+    check(ccall((:dyb_comm_init, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), ws.handle, rank, nranks, id))
+
+# ---- any model, host-evaluated Jacobians (no generated device function) ---------------------------------------------------
+struct ModelDesc
+    n::Int32; nx::Int32; ny::Int32; n_static::Int32; n_bkwrd_b::Int32; n_fwrd_b::Int32
+    i_static::Ptr{Int32}; i_bkwrd_b::Ptr{Int32}; i_fwrd_b::Ptr{Int32}; obs_idx::Ptr{Int32}
+end
+"jac: n × ncol × N from `set_compressed_jacobian!` per draw (threaded on the host), ybar: n × N."
+function loglik_from_jacobian!(out, status, h::Ptr{Cvoid}, jac::Array{Float64,3}, ybar::Matrix{Float64}, Σe::Matrix{Float64})
+    GC.@preserve out status jac ybar Σe check(ccall((:dyb_loglik_from_jacobian_batch, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Ptr{Int32}, Int64, Ptr{Float64}, Ptr{Int32}),
+        h, jac, ybar, Σe, 0, C_NULL, 0, C_NULL, size(jac, 3), out, status))
+    return out
+end
+
 end # module

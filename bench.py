@@ -274,24 +274,51 @@ def run_ours(args):
     step_ms = tmax.item() / args.steps
     value = world * n * args.steps / (tmax.item() * 1e-3)
 
-    # ---- end to end through the public API with (pinned) host buffers --------------------------------
+    # ---- end to end through the public API with pinned host buffers ---------------------------------------------
+    # (a) one synchronous call per step: H2D + kernels + D2H, host wall clock around the call
     pth = PinnedArray((n, npar)); pll = PinnedArray((n,)); pst = PinnedArray((n,), np.int32)
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(4, min(args.steps, 20))
     for i in range(2):
         pth.array[:] = host_pool[i % pool]
         ws.loglikelihood(pth.array, out=pll.array, status=pst.array)
     barrier()
-    e2e_t = 0.0
+    sync_t = 0.0
     for i in range(e2e_steps):
         pth.array[:] = host_pool[(i + 2) % pool]          # a fresh batch lands in pinned memory (not timed)
         barrier()
         t = time.perf_counter()
         ws.loglikelihood(pth.array, out=pll.array, status=pst.array)   # H2D + kernels + D2H, synchronous
-        e2e_t += time.perf_counter() - t
-    te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+        sync_t += time.perf_counter() - t
+    # (b) the same steps double-buffered: two handles / streams used alternately through dyb_loglik_batch_async, so the
+    # PCIe copies of one step overlap the kernels of the other; every step's H2D and D2H is inside the timed region
+    ws2 = BatchSSWs(MODEL, Y, device=local)
+    W = (ws, ws2)
+    ring = 4
+    pin_in = [PinnedArray((n, npar)) for _ in range(ring)]
+    pin_ll = [PinnedArray((n,)) for _ in range(2)]; pin_st = [PinnedArray((n,), np.int32) for _ in range(2)]
+    for r in range(ring):
+        pin_in[r].array[:] = host_pool[(r + 5) % pool]
+    for k in range(2):                                   # warm-up of both handles
+        W[k].loglikelihood_async(pin_in[k].array, pin_ll[k].array, pin_st[k].array); W[k].sync()
+    barrier()
+    ok_seen = 0
+    t = time.perf_counter()
+    for i in range(e2e_steps):
+        k = i % 2
+        W[k].sync()                                      # step i-2 of this handle is complete: its result is on the host
+        if i >= 2:
+            ok_seen += int(pin_st[k].array[0] == 0)      # touch the host copy of the result
+        W[k].loglikelihood_async(pin_in[i % ring].array, pin_ll[k].array, pin_st[k].array)
+    W[0].sync(); W[1].sync()
+    pipe_t = time.perf_counter() - t
+    te = torch.tensor([sync_t, pipe_t], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / te.item()
+    e2e_sync_value = world * n * e2e_steps / te[0].item()
+    e2e_value = world * n * e2e_steps / te[1].item()
+    for b in pin_in + pin_ll + pin_st:
+        b.free()
+    ws2.close()
 
     if rank == 0:
         d = ws.dims
@@ -350,8 +377,12 @@ def run_ours(args):
                        "ok_draws_last_step": n_ok},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": n * npar * 8,
                     "d2h_bytes_per_step": n * 12, "steps": e2e_steps,
-                    "how": "BatchSSWs.loglikelihood (dyb_loglik_batch) with pinned host buffers; host wall clock "
-                           "around the synchronous call, max over ranks"},
+                    "how": "BatchSSWs.loglikelihood_async (dyb_loglik_batch_async) with pinned host buffers, two handles "
+                           "used alternately so one step's PCIe copies overlap the other's kernels; host wall clock over "
+                           "all steps incl. every H2D and D2H, max over ranks",
+                    "sync_call_value": e2e_sync_value,
+                    "sync_call_how": "one synchronous BatchSSWs.loglikelihood (dyb_loglik_batch) per step, host wall "
+                                     "clock around each call"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "clocks": clocks,

@@ -71,6 +71,7 @@ SIGNATURES = {
     "dyb_set_estimated_params": (C.c_int, [_P, C.c_int32, _I32, _I32, _I32]),
     "dyb_set_observations": (C.c_int, [_P, _D, C.c_int32, C.c_int32]),
     "dyb_loglik_batch": (C.c_int, [_P, _D, C.c_int64, _D, _I32]),
+    "dyb_loglik_batch_async": (C.c_int, [_P, _D, C.c_int64, _D, _I32]),
     "dyb_loglik_batch_device": (C.c_int, [_P, _D, C.c_int64, _D, _I32]),
     "dyb_sync": (C.c_int, [_P]),
     "dyb_kernel_launches": (C.c_int64, [_P]),

@@ -257,19 +257,24 @@ static cudaEvent_t* timer_slot(dyb_handle* h) {
   return &h->timer_ev[5 * h->timer_n];
 }
 
-int dyb_loglik_batch(dyb_handle* h, const double* theta, int64_t n, double* loglik, int32_t* status) {
+static int loglik_batch_impl(dyb_handle* h, const double* theta, int64_t n, double* loglik, int32_t* status, bool async) {
   if (h && !h->ops) return fail(DYB_ERR_UNSUPPORTED, "this handle has no device model function (dyb_create_generic): use the *_from_jacobian entry points");
   if (!h || n < 0 || (n > 0 && (!theta || !loglik || !status))) return fail(DYB_ERR_ARG, "null argument");
   if (n == 0) return DYB_OK;
   DYB_CUDA(cudaSetDevice(h->device));
   const int np = h->hs.np;
   const size_t N = (size_t)n;
+  const bool dev_in = is_device_ptr(theta);
+  const bool pin_in = dev_in || is_pinned_ptr(theta);
+  const bool pin_ll = is_pinned_ptr(loglik) || is_device_ptr(loglik);
+  const bool pin_st = is_pinned_ptr(status) || is_device_ptr(status);
+  if (async && !(pin_in && pin_ll && pin_st))
+    return fail(DYB_ERR_ARG, "the asynchronous call needs pinned (dyb_host_alloc) or device buffers");
   DYB_CUDA(h->d_theta.reserve(sizeof(double) * np * N + 8));
   DYB_CUDA(h->d_ll.reserve(sizeof(double) * N));
   DYB_CUDA(h->d_st2.reserve(sizeof(int) * N));
-  const bool dev_in = is_device_ptr(theta);
   const void* src = theta;
-  if (!dev_in && !is_pinned_ptr(theta)) {
+  if (!pin_in) {
     DYB_CUDA(h->h_in.reserve(sizeof(double) * np * N + 8));
     std::memcpy(h->h_in.p, theta, sizeof(double) * np * N);
     src = h->h_in.p;
@@ -278,17 +283,27 @@ int dyb_loglik_batch(dyb_handle* h, const double* theta, int64_t n, double* logl
                            dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
   int rc = dyb_loglik_batch_device(h, h->d_theta.as<double>(), n, h->d_ll.as<double>(), h->d_st2.as<int>());
   if (rc) return rc;
-  const bool pin_ll = is_pinned_ptr(loglik) || is_device_ptr(loglik);
-  const bool pin_st = is_pinned_ptr(status) || is_device_ptr(status);
   DYB_CUDA(h->h_out.reserve((sizeof(double) + sizeof(int)) * N + 16));
   double* ll_stage = h->h_out.as<double>();
   int* st_stage = reinterpret_cast<int*>(ll_stage + N);
   DYB_CUDA(cudaMemcpyAsync(pin_ll ? (void*)loglik : (void*)ll_stage, h->d_ll.p, sizeof(double) * N, cudaMemcpyDefault, h->stream));
   DYB_CUDA(cudaMemcpyAsync(pin_st ? (void*)status : (void*)st_stage, h->d_st2.p, sizeof(int) * N, cudaMemcpyDefault, h->stream));
+  if (async) return DYB_OK;
   DYB_CUDA(cudaStreamSynchronize(h->stream));
   if (!pin_ll) std::memcpy(loglik, ll_stage, sizeof(double) * N);
   if (!pin_st) std::memcpy(status, st_stage, sizeof(int) * N);
   return DYB_OK;
+}
+
+int dyb_loglik_batch(dyb_handle* h, const double* theta, int64_t n, double* loglik, int32_t* status) {
+  return loglik_batch_impl(h, theta, n, loglik, status, false);
+}
+
+// same call without the final synchronisation: H2D, kernels and D2H are enqueued on the handle's stream and the call
+// returns; results are valid after dyb_sync.  Buffers must be pinned (dyb_host_alloc) or device memory and stay
+// untouched until then.  Two handles used alternately overlap one batch's copies with the other's kernels.
+int dyb_loglik_batch_async(dyb_handle* h, const double* theta, int64_t n, double* loglik, int32_t* status) {
+  return loglik_batch_impl(h, theta, n, loglik, status, true);
 }
 
 int dyb_sync(dyb_handle* h) {

@@ -46,9 +46,9 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
   if (coop) {
     model_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.mid, out.status, out.ybar);
     if (out.ev_after_model) cudaEventRecord(out.ev_after_model, st);
-    const long long gridc = (n * G + block - 1) / block;
+    const long long gridc = (n * G + CrCfg<MT>::BLOCK - 1) / CrCfg<MT>::BLOCK;
     CrOptions co{hs.opt.cr_tol, hs.opt.cr_maxit};
-    cr_kernel<MT, G><<<(unsigned)gridc, block, 0, st>>>(out.mid, n, co, out.status, out.cr_iters);
+    cr_kernel<MT, G><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters);
     if (out.ev_after_cr) cudaEventRecord(out.ev_after_cr, st);
     assemble_kernel<MT><<<(unsigned)grid, block, 0, st>>>(out.mid, n, hs.opt.lyap_tol, hs.opt.lyap_maxit, out.ss,
                                                           out.status, out.g1, out.lyap_iters);

@@ -202,126 +202,134 @@ DYB_D bool qr_solve(double (&A)[(MM + G - 1) / G][MM], double (&B)[NR][MM], int 
 
 struct CrOptions { double cr_tol; int cr_maxit; };
 
+// Geometry of cr_kernel: G lanes per draw, CTAs of BLOCK threads, one shared-memory tile per draw holding
+// A1 (MM x MM) | acc_hat (MM x K) | A0 (MM x K) | A2 (MM x NF), column-major.  The tile stride is padded to
+// 4 (mod 16) doubles so that the "own column" accesses of a half-warp (4 draws x 4 lanes, column stride MM)
+// fall into 16 distinct 8-byte banks when MM is odd.
+template <class M>
+struct CrCfg {
+  static constexpr int G = 4, BLOCK = 64, GROUPS = BLOCK / G;
+  static constexpr int MM = M::M, K = M::K, NF = M::NF;
+  static constexpr int OFF_A1 = 0, OFF_ACC = MM * MM, OFF_A0 = OFF_ACC + MM * K, OFF_A2 = OFF_A0 + MM * K;
+  static constexpr int TILE_RAW = OFF_A2 + MM * NF;
+  static constexpr int TILE = TILE_RAW + ((4 - TILE_RAW % 16) + 16) % 16;
+  static constexpr int MIN_CTAS = 6;
+};
+
+// All 32 lanes of a warp (8 draws) run the SAME instruction stream: shuffles use the full mask (a partial mask costs
+// a WARPSYNC / BSSY / BSYNC sequence per shuffle), the iteration runs until every draw of the warp has stopped, and a
+// draw that has stopped is frozen by predicating its commits (short divergent sections without shuffles), so its
+// result does not depend on its neighbours.  Between iterations the whole state of a draw lives in its shared tile;
+// registers only hold the transient copies of one iteration (A1 and [X0 | X2] by column, then the GEMM accumulators).
 template <class M, int G>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(CrCfg<M>::BLOCK, CrCfg<M>::MIN_CTAS)
 cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
           int* __restrict__ status, int* __restrict__ cr_iters) {
+  using C = CrCfg<M>;
+  static_assert(G == C::G, "lane count");
   constexpr int MM = M::M, K = M::K, NF = M::NF, NX = M::NX;
   constexpr int SL1 = (MM + G - 1) / G, SL0 = (K + G - 1) / G, SL2 = (NF + G - 1) / G, SLU = (NX + G - 1) / G;
   constexpr int NR = SL0 + SL2;
-  constexpr int GROUPS = 128 / G;
-  constexpr int TILE = MM * MM + MM * K;          // per group: A1 (current) | acc_hat
+  constexpr unsigned FULL = 0xffffffffu;
   using L = MidLayout<M>;
-  __shared__ double tile[GROUPS * TILE];
+  __shared__ double tile[C::GROUPS * C::TILE];
 
-  const int lane = threadIdx.x & 31;
   const int lg = threadIdx.x % G;
-  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
   long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const bool real = d < n_draws;
   if (!real) d = n_draws - 1;                       // tail groups recompute the last draw and store nothing
-  double* A1s = tile + (threadIdx.x / G) * TILE;
-  double* accs = A1s + MM * MM;
+  double* A1s = tile + (threadIdx.x / G) * C::TILE + C::OFF_A1;
+  double* accs = A1s + (C::OFF_ACC - C::OFF_A1);
+  double* A0s = A1s + (C::OFF_A0 - C::OFF_A1);
+  double* A2s = A1s + (C::OFF_A2 - C::OFF_A1);
   const double* md = mid + d;
   const long long st = n_draws;
   const int st_in = status[d];
 
-  // distributed registers
-  double A1w[SL1][MM], A0[SL0][MM], A2[SL2][MM], XB[NR][MM];
-#pragma unroll
-  for (int s = 0; s < SL1; ++s)
-#pragma unroll
-    for (int r = 0; r < MM; ++r) A1w[s][r] = 0.0;
-#pragma unroll
-  for (int s = 0; s < SL0; ++s)
-#pragma unroll
-    for (int r = 0; r < MM; ++r) A0[s][r] = 0.0;
-#pragma unroll
-  for (int s = 0; s < SL2; ++s)
-#pragma unroll
-    for (int r = 0; r < MM; ++r) A2[s][r] = 0.0;
-
-  auto load_blocks = [&](bool neg_a0) {
+  // (re)load A1(0), A0(0), A2(0) of the draw into the tile; acc_hat is left alone unless zero_acc
+  auto load_tile = [&](bool zero_acc) {
+    for (int e = lg; e < C::OFF_ACC; e += G) A1s[e] = 0.0;
+    for (int e = lg; e < MM * K + MM * NF; e += G) A0s[e] = 0.0;
+    if (zero_acc) for (int e = lg; e < MM * K; e += G) accs[e] = 0.0;
+    __syncwarp(FULL);
 #pragma unroll
     for (int e = 0; e < M::RED_NNZ; ++e) {
+      if (e % G != lg) continue;
       const int rr = M::red_row(e), c = M::red_col(e);
-      if (c < K) {
-        if (lg == c % G) A0[c / G][rr] = neg_a0 ? -md[(L::OFF_RED + e) * st] : md[(L::OFF_RED + e) * st];
-      } else if (c < K + MM) {
-        if (lg == (c - K) % G) A1w[(c - K) / G][rr] = md[(L::OFF_RED + e) * st];
-      } else if (c < K + MM + NF) {
-        if (lg == (c - K - MM) % G) A2[(c - K - MM) / G][rr] = md[(L::OFF_RED + e) * st];
-      }
+      if (c < K) A0s[rr + MM * c] = md[(L::OFF_RED + e) * st];
+      else if (c < K + MM) A1s[rr + MM * (c - K)] = md[(L::OFF_RED + e) * st];
+      else if (c < K + MM + NF) A2s[rr + MM * (c - K - MM)] = md[(L::OFF_RED + e) * st];
     }
+    __syncwarp(FULL);
   };
-  load_blocks(false);
+  load_tile(true);
 
-  // own columns of A1 into the shared tile; acc_hat = 0
-  auto store_a1 = [&]() {
+  int it = 0;
+  int result = st_in;                 // draws that already failed are frozen from the start
+  bool active = (st_in == ST_OK), conv = false, stalled = false;
+  double n0 = 0.0, n2 = 0.0;
+  for (int iter = 1; iter <= opt.cr_maxit; ++iter) {
+    if (!__any_sync(FULL, active)) break;
+    // own columns of A1 and of [A0 | A2]
+    double A1w[SL1][MM], XB[NR][MM];
 #pragma unroll
     for (int s = 0; s < SL1; ++s) {
       const int col = s * G + lg;
-      if (col < MM) {
 #pragma unroll
-        for (int r = 0; r < MM; ++r) A1s[r + MM * col] = A1w[s][r];
+      for (int r = 0; r < MM; ++r) A1w[s][r] = (col < MM) ? A1s[r + MM * col] : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < SL0; ++s) {
+      const int col = s * G + lg;
+#pragma unroll
+      for (int r = 0; r < MM; ++r) XB[s][r] = (col < K) ? A0s[r + MM * col] : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < SL2; ++s) {
+      const int col = s * G + lg;
+#pragma unroll
+      for (int r = 0; r < MM; ++r) XB[SL0 + s][r] = (col < NF) ? A2s[r + MM * col] : 0.0;
+    }
+    // [X0 | X2] = A1^-1 [A0 | A2]
+    const bool okq = qr_solve<MM, G, NR>(A1w, XB, lg, FULL);
+    const bool commit = active && okq;
+
+    // pass 1: own columns j of [W00 | W01] = A0 * X[bk, j], columns of A0 broadcast from the tile
+    double acc[NR][MM];
+#pragma unroll
+    for (int s = 0; s < NR; ++s)
+#pragma unroll
+      for (int r = 0; r < MM; ++r) acc[s][r] = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      double a[MM];
+#pragma unroll
+      for (int r = 0; r < MM; ++r) a[r] = A0s[r + MM * i];
+#pragma unroll
+      for (int s = 0; s < NR; ++s) {
+        const double xv = XB[s][M::bkwrd_in_dyn(i)];
+#pragma unroll
+        for (int r = 0; r < MM; ++r) acc[s][r] = fma(a[r], xv, acc[s][r]);
       }
     }
-  };
-  store_a1();
+    double m0 = 0.0;
 #pragma unroll
-  for (int s = 0; s < SL0; ++s) {
-    const int col = s * G + lg;
-    if (col < K) {
+    for (int s = 0; s < SL0; ++s) {
+      double cs = 0.0;
 #pragma unroll
-      for (int r = 0; r < MM; ++r) accs[r + MM * col] = 0.0;
+      for (int r = 0; r < MM; ++r) cs += fabs(acc[s][r]);
+      m0 = fmax(m0, cs);
     }
-  }
-  __syncwarp(mask);
-
-  int it = 0;
-  int result = st_in;                 // draws that already failed skip the iteration
-  bool conv = false, stalled = false;
-  double n0 = 0.0, n2 = 0.0;
-  if (st_in == ST_OK) {
-    for (it = 1; it <= opt.cr_maxit; ++it) {
-      // [X0 | X2] = A1^-1 [A0 | A2]
-#pragma unroll
-      for (int s = 0; s < SL0; ++s)
-#pragma unroll
-        for (int r = 0; r < MM; ++r) XB[s][r] = A0[s][r];
-#pragma unroll
-      for (int s = 0; s < SL2; ++s)
-#pragma unroll
-        for (int r = 0; r < MM; ++r) XB[SL0 + s][r] = A2[s][r];
-      const bool okq = qr_solve<MM, G, NR>(A1w, XB, lg, mask);
-      if (!okq) { if (it == 1) result = ST_SOLVER; else stalled = true; break; }
-
-      // pass 1: columns of A0 broadcast; own columns j of [W00 | W01] = A0 * X[bk, j]
-      double acc[NR][MM];
-#pragma unroll
-      for (int s = 0; s < NR; ++s)
-#pragma unroll
-        for (int r = 0; r < MM; ++r) acc[s][r] = 0.0;
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-        double a[MM];
-#pragma unroll
-        for (int r = 0; r < MM; ++r) a[r] = gshfl<G>(mask, A0[i / G][r], i % G);
-#pragma unroll
-        for (int s = 0; s < NR; ++s) {
-          const double xv = XB[s][M::bkwrd_in_dyn(i)];
-#pragma unroll
-          for (int r = 0; r < MM; ++r) acc[s][r] = fma(a[r], xv, acc[s][r]);
-        }
-      }
+    __syncwarp(FULL);                               // every lane has read A0 before anybody overwrites it
+    if (commit) {
       // A0 <- -W00 (own columns) ; A1[:, fw(j)] -= W01[:, j]
-      double m0 = 0.0;
 #pragma unroll
       for (int s = 0; s < SL0; ++s) {
-        double cs = 0.0;
+        const int col = s * G + lg;
+        if (col < K) {
 #pragma unroll
-        for (int r = 0; r < MM; ++r) { A0[s][r] = -acc[s][r]; cs += fabs(acc[s][r]); }
-        m0 = fmax(m0, cs);
+          for (int r = 0; r < MM; ++r) A0s[r + MM * col] = -acc[s][r];
+        }
       }
 #pragma unroll
       for (int s = 0; s < SL2; ++s) {
@@ -332,31 +340,42 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
           for (int r = 0; r < MM; ++r) A1s[r + MM * tc] -= acc[SL0 + s][r];
         }
       }
-      __syncwarp(mask);
-      // pass 2: columns of A2 broadcast; own columns j of [W10 | W11] = A2 * X[fw, j]
+    }
+    __syncwarp(FULL);
+    // pass 2: own columns j of [W10 | W11] = A2 * X[fw, j]
 #pragma unroll
-      for (int s = 0; s < NR; ++s)
+    for (int s = 0; s < NR; ++s)
 #pragma unroll
-        for (int r = 0; r < MM; ++r) acc[s][r] = 0.0;
+      for (int r = 0; r < MM; ++r) acc[s][r] = 0.0;
 #pragma unroll
-      for (int i = 0; i < NF; ++i) {
-        double a[MM];
+    for (int i = 0; i < NF; ++i) {
+      double a[MM];
 #pragma unroll
-        for (int r = 0; r < MM; ++r) a[r] = gshfl<G>(mask, A2[i / G][r], i % G);
+      for (int r = 0; r < MM; ++r) a[r] = A2s[r + MM * i];
 #pragma unroll
-        for (int s = 0; s < NR; ++s) {
-          const double xv = XB[s][M::fwrd_in_dyn(i)];
+      for (int s = 0; s < NR; ++s) {
+        const double xv = XB[s][M::fwrd_in_dyn(i)];
 #pragma unroll
-          for (int r = 0; r < MM; ++r) acc[s][r] = fma(a[r], xv, acc[s][r]);
-        }
+        for (int r = 0; r < MM; ++r) acc[s][r] = fma(a[r], xv, acc[s][r]);
       }
-      double m2 = 0.0;
+    }
+    double m2 = 0.0;
+#pragma unroll
+    for (int s = 0; s < SL2; ++s) {
+      double cs = 0.0;
+#pragma unroll
+      for (int r = 0; r < MM; ++r) cs += fabs(acc[SL0 + s][r]);
+      m2 = fmax(m2, cs);
+    }
+    __syncwarp(FULL);
+    if (commit) {
 #pragma unroll
       for (int s = 0; s < SL2; ++s) {
-        double cs = 0.0;
+        const int col = s * G + lg;
+        if (col < NF) {
 #pragma unroll
-        for (int r = 0; r < MM; ++r) { A2[s][r] = -acc[SL0 + s][r]; cs += fabs(acc[SL0 + s][r]); }
-        m2 = fmax(m2, cs);
+          for (int r = 0; r < MM; ++r) A2s[r + MM * col] = -acc[SL0 + s][r];
+        }
       }
 #pragma unroll
       for (int s = 0; s < SL0; ++s) {
@@ -367,132 +386,120 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
           for (int r = 0; r < MM; ++r) { A1s[r + MM * tc] -= acc[s][r]; accs[r + MM * col] += acc[s][r]; }
         }
       }
-      __syncwarp(mask);
-      // next A1 into registers
-#pragma unroll
-      for (int s = 0; s < SL1; ++s) {
-        const int col = s * G + lg;
-#pragma unroll
-        for (int r = 0; r < MM; ++r) A1w[s][r] = (col < MM) ? A1s[r + MM * col] : 0.0;
-      }
-      m0 = gmax<G>(mask, m0);
-      m2 = gmax<G>(mask, m2);
-      if (!(m0 <= 1e150) || !(m2 <= 1e150)) { if (it == 1) result = ST_SOLVER; else stalled = true; break; }
-      n0 = m0; n2 = m2;
-      if (n0 < opt.cr_tol && n2 < opt.cr_tol) { conv = true; break; }
     }
-    if (result == ST_OK && !conv) {
-      // Blanchard-Kahn reading of a reduction that does not converge (see solve_kernel.cuh)
-      if (stalled) result = (n0 < n2) ? ST_INDETERMINATE : ST_UNSTABLE;
-      else result = (n0 >= opt.cr_tol) ? ST_UNSTABLE : ST_INDETERMINATE;
+    __syncwarp(FULL);
+    m0 = gmax<G>(FULL, m0);
+    m2 = gmax<G>(FULL, m2);
+    if (active) {
+      it = iter;
+      if (!okq || !(m0 <= 1e150) || !(m2 <= 1e150)) {
+        if (iter == 1) result = ST_SOLVER; else stalled = true;
+        active = false;
+      } else {
+        n0 = m0; n2 = m2;
+        if (n0 < opt.cr_tol && n2 < opt.cr_tol) { conv = true; active = false; }
+      }
     }
   }
-  __syncwarp(mask);
+  if (active) it = opt.cr_maxit + 1;               // ran out of iterations
+  if (result == ST_OK && !conv) {
+    // Blanchard-Kahn reading of a reduction that does not converge (see solve_kernel.cuh)
+    if (stalled) result = (n0 < n2) ? ST_INDETERMINATE : ST_UNSTABLE;
+    else result = (n0 >= opt.cr_tol) ? ST_UNSTABLE : ST_INDETERMINATE;
+  }
 
-  if (result == ST_OK) {
-    // ---- G (dynamic rows, backward columns) = -(A1(0) - acc_hat)^-1 A0(0) -----------------------------
+  // ---- G (dynamic rows, backward columns) = -(A1(0) - acc_hat)^-1 A0(0); executed by every lane, stored if ok --------
+  load_tile(false);
 #pragma unroll
-    for (int s = 0; s < SL1; ++s)
+  for (int s = 0; s < SL0; ++s) {
+    const int col = s * G + lg;
+    if (col < K) {
+      const int tc = M::bkwrd_in_dyn(col);
 #pragma unroll
-      for (int r = 0; r < MM; ++r) A1w[s][r] = 0.0;
+      for (int r = 0; r < MM; ++r) A1s[r + MM * tc] -= accs[r + MM * col];
+    }
+  }
+  __syncwarp(FULL);
+  double A1h[SL1][MM], Gc[SL0][MM];
 #pragma unroll
-    for (int s = 0; s < SL0; ++s)
+  for (int s = 0; s < SL1; ++s) {
+    const int col = s * G + lg;
 #pragma unroll
-      for (int r = 0; r < MM; ++r) A0[s][r] = 0.0;
+    for (int r = 0; r < MM; ++r) A1h[s][r] = (col < MM) ? A1s[r + MM * col] : 0.0;
+  }
 #pragma unroll
-    for (int s = 0; s < SL2; ++s)
+  for (int s = 0; s < SL0; ++s) {
+    const int col = s * G + lg;
 #pragma unroll
-      for (int r = 0; r < MM; ++r) A2[s][r] = 0.0;
-    load_blocks(true);                               // A0 <- -A0(0), A1w <- A1(0), A2 <- A2(0)
-    store_a1();                                      // A1s <- A1(0)
-    __syncwarp(mask);
+    for (int r = 0; r < MM; ++r) Gc[s][r] = (col < K) ? -A0s[r + MM * col] : 0.0;
+  }
+  bool okq = qr_solve<MM, G, SL0>(A1h, Gc, lg, FULL);         // Gc now holds G's own columns
+  // ---- g_u = -(A1(0) + A2(0) G[fw, :])^-1 F_u ---------------------------------------------------------------------------
+  double w[SL0][MM];
+#pragma unroll
+  for (int s = 0; s < SL0; ++s)
+#pragma unroll
+    for (int r = 0; r < MM; ++r) w[s][r] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NF; ++i) {
+    double a[MM];
+#pragma unroll
+    for (int r = 0; r < MM; ++r) a[r] = A2s[r + MM * i];
+#pragma unroll
+    for (int s = 0; s < SL0; ++s) {
+      const double xv = Gc[s][M::fwrd_in_dyn(i)];
+#pragma unroll
+      for (int r = 0; r < MM; ++r) w[s][r] = fma(a[r], xv, w[s][r]);
+    }
+  }
+  __syncwarp(FULL);
+  // A1 tile <- A1(0) + acc_hat on the backward columns (undo the subtraction above), then + w
+#pragma unroll
+  for (int s = 0; s < SL0; ++s) {
+    const int col = s * G + lg;
+    if (col < K) {
+      const int tc = M::bkwrd_in_dyn(col);
+#pragma unroll
+      for (int r = 0; r < MM; ++r) A1s[r + MM * tc] = (A1s[r + MM * tc] + accs[r + MM * col]) + w[s][r];
+    }
+  }
+  __syncwarp(FULL);
+#pragma unroll
+  for (int s = 0; s < SL1; ++s) {
+    const int col = s * G + lg;
+#pragma unroll
+    for (int r = 0; r < MM; ++r) A1h[s][r] = (col < MM) ? A1s[r + MM * col] : 0.0;
+  }
+  double U[SLU][MM];
+#pragma unroll
+  for (int s = 0; s < SLU; ++s)
+#pragma unroll
+    for (int r = 0; r < MM; ++r) U[s][r] = 0.0;
+#pragma unroll
+  for (int e = 0; e < M::RED_NNZ; ++e) {
+    const int rr = M::red_row(e), c = M::red_col(e);
+    if (c >= K + MM + NF) {
+      const int cu = c - K - MM - NF;
+      if (lg == cu % G) U[cu / G][rr] = -md[(L::OFF_RED + e) * st];
+    }
+  }
+  okq = qr_solve<MM, G, SLU>(A1h, U, lg, FULL) && okq;
+  if (result == ST_OK && !okq) result = ST_SOLVER;
+  if (real && result == ST_OK) {
 #pragma unroll
     for (int s = 0; s < SL0; ++s) {
       const int col = s * G + lg;
       if (col < K) {
-        const int tc = M::bkwrd_in_dyn(col);
 #pragma unroll
-        for (int r = 0; r < MM; ++r) A1s[r + MM * tc] -= accs[r + MM * col];
+        for (int r = 0; r < MM; ++r) mid[(L::OFF_G + r + MM * col) * st + d] = Gc[s][r];
       }
     }
-    __syncwarp(mask);
-    double A1h[SL1][MM];
 #pragma unroll
-    for (int s = 0; s < SL1; ++s) {
+    for (int s = 0; s < SLU; ++s) {
       const int col = s * G + lg;
+      if (col < NX) {
 #pragma unroll
-      for (int r = 0; r < MM; ++r) A1h[s][r] = (col < MM) ? A1s[r + MM * col] : 0.0;
-    }
-    bool okq = qr_solve<MM, G, SL0>(A1h, A0, lg, mask);       // A0 now holds G's own columns
-    // ---- g_u = -(A1(0) + A2(0) G[fw, :])^-1 F_u ---------------------------------------------------------
-    double w[SL0][MM];
-#pragma unroll
-    for (int s = 0; s < SL0; ++s)
-#pragma unroll
-      for (int r = 0; r < MM; ++r) w[s][r] = 0.0;
-#pragma unroll
-    for (int i = 0; i < NF; ++i) {
-      double a[MM];
-#pragma unroll
-      for (int r = 0; r < MM; ++r) a[r] = gshfl<G>(mask, A2[i / G][r], i % G);
-#pragma unroll
-      for (int s = 0; s < SL0; ++s) {
-        const double xv = A0[s][M::fwrd_in_dyn(i)];
-#pragma unroll
-        for (int r = 0; r < MM; ++r) w[s][r] = fma(a[r], xv, w[s][r]);
-      }
-    }
-    __syncwarp(mask);
-    // A1w still holds A1(0) (qr_solve above worked on A1h)
-    store_a1();
-    __syncwarp(mask);
-#pragma unroll
-    for (int s = 0; s < SL0; ++s) {
-      const int col = s * G + lg;
-      if (col < K) {
-        const int tc = M::bkwrd_in_dyn(col);
-#pragma unroll
-        for (int r = 0; r < MM; ++r) A1s[r + MM * tc] += w[s][r];
-      }
-    }
-    __syncwarp(mask);
-#pragma unroll
-    for (int s = 0; s < SL1; ++s) {
-      const int col = s * G + lg;
-#pragma unroll
-      for (int r = 0; r < MM; ++r) A1h[s][r] = (col < MM) ? A1s[r + MM * col] : 0.0;
-    }
-    double U[SLU][MM];
-#pragma unroll
-    for (int s = 0; s < SLU; ++s)
-#pragma unroll
-      for (int r = 0; r < MM; ++r) U[s][r] = 0.0;
-#pragma unroll
-    for (int e = 0; e < M::RED_NNZ; ++e) {
-      const int rr = M::red_row(e), c = M::red_col(e);
-      if (c >= K + MM + NF) {
-        const int cu = c - K - MM - NF;
-        if (lg == cu % G) U[cu / G][rr] = -md[(L::OFF_RED + e) * st];
-      }
-    }
-    okq = qr_solve<MM, G, SLU>(A1h, U, lg, mask) && okq;
-    if (!okq) result = ST_SOLVER;
-    if (real && okq) {
-#pragma unroll
-      for (int s = 0; s < SL0; ++s) {
-        const int col = s * G + lg;
-        if (col < K) {
-#pragma unroll
-          for (int r = 0; r < MM; ++r) mid[(L::OFF_G + r + MM * col) * st + d] = A0[s][r];
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < SLU; ++s) {
-        const int col = s * G + lg;
-        if (col < NX) {
-#pragma unroll
-          for (int r = 0; r < MM; ++r) mid[(L::OFF_GU + r + MM * col) * st + d] = U[s][r];
-        }
+        for (int r = 0; r < MM; ++r) mid[(L::OFF_GU + r + MM * col) * st + d] = U[s][r];
       }
     }
   }

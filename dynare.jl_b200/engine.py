@@ -148,6 +148,12 @@ class BatchSSWs:
         L.check(self.lib.dyb_loglik_batch(self._h, L.ptr(Theta), n, L.ptr(ll), L.ptr(st)))
         return ll, st
 
+    def loglikelihood_async(self, Theta, out, status):
+        """Enqueue H2D + kernels + D2H and return; ``Theta`` / ``out`` / ``status`` must be pinned (``PinnedArray``)
+        or device memory and stay untouched until ``sync()``."""
+        n = Theta.shape[0]
+        L.check(self.lib.dyb_loglik_batch_async(self._h, L.ptr(Theta), n, L.ptr(out), L.ptr(status)))
+
     def loglikelihood_device(self, d_theta: int, n: int, d_loglik: int, d_status: int):
         """Device-pointer variant (addresses as ints); asynchronous, call ``sync()``."""
         L.check(self.lib.dyb_loglik_batch_device(self._h, L.ptr(d_theta), n, L.ptr(d_loglik), L.ptr(d_status)))

@@ -114,6 +114,10 @@ int dyb_set_observations(dyb_handle* h, const double* Y, int32_t ny, int32_t nob
  * memory (dyb_host_alloc) is copied asynchronously without staging. */
 int dyb_loglik_batch(dyb_handle* h, const double* theta, int64_t n_draws,
                      double* loglik /* N */, int32_t* status /* N */);
+/* same without the final synchronisation (results valid after dyb_sync); buffers must be pinned or device memory.
+ * Two handles used alternately overlap one batch's PCIe copies with the other's kernels. */
+int dyb_loglik_batch_async(dyb_handle* h, const double* theta, int64_t n_draws,
+                           double* loglik /* N */, int32_t* status /* N */);
 /* same, all pointers are device pointers on the handle's device; asynchronous on the handle's stream */
 int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n_draws,
                             double* d_loglik, int32_t* d_status);

@@ -6,6 +6,7 @@
 #include "internal.h"
 #include "kalman_generic.cuh"
 #include "kalman_dmma.cuh"
+#include "kalman_dmma_large.cuh"
 #include "solve_generic.cuh"
 
 namespace dyb {
@@ -53,6 +54,25 @@ static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaSt
       if (ntile <= 5) return launch(kalman_dmma_kernel<5>);
       if (ntile <= 8) return launch(kalman_dmma_kernel<8>);
       return launch(kalman_dmma_kernel<DMMA_MAX_TILES>);
+    }
+  }
+  {
+    // large state spaces: persistent CTAs, P and T P in an L2-resident scratch, blocked tensor-core GEMMs
+    const KalmanLargeGeom q = kalman_large_geom(g.ns, g.ny);
+    const size_t smem = sizeof(double) * kalman_large_smem_doubles(g.ns, g.ny);
+    const int threads = 32 * q.nwarps;
+    const bool fits = q.nwarps <= 16 && smem + 1024 <= (size_t)max_smem &&
+                      (size_t)8 * threads >= (size_t)q.nsp * DL_BK + (size_t)DL_BK * 8 * DL_NTP;
+    if (fits && g_kalman_variant != 1 && g.ns > 8 * DMMA_MAX_TILES) {
+      long long grid = g.n_draws < dev_sms ? g.n_draws : dev_sms;
+      g.scratch = sg.temp<double>(kalman_large_scratch_doubles(g.ns) * (size_t)grid);
+      if (sg.err != cudaSuccess) return sg.err;
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kalman_dmma_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+      }
+      kalman_dmma_large_kernel<<<(unsigned)grid, threads, smem, st>>>(g, q);
+      return cudaGetLastError();
     }
   }
   const size_t ns2 = (size_t)g.ns * g.ns;

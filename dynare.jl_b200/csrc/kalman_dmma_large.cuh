@@ -1,0 +1,291 @@
+// Dense batched Kalman log-likelihood for LARGE state spaces (88 < ns <= 256: BASELINE config 5, ns = 200, ny = 20)
+// on the fp64 tensor cores.  P and T P of a draw do not fit in shared memory (2 x 320 KB at ns = 200), so they live
+// in a per-CTA global scratch that stays L2-resident; one persistent CTA per SM walks over the draws.  The two big
+// products of a period,  M = T P  and  P = M T' + R Q R'  (lower block triangle, mirrored), are blocked GEMMs:
+// k-panels of 8 columns of A (all rows) and 8 rows of B (a pass of up to NTP tile columns) are staged through shared
+// memory with register prefetch (global loads of panel p+1 are in flight while panel p is multiplied), every warp owns
+// up to two 8-row strips of the result and keeps their accumulators in registers, fragments are read conflict-free
+// (leading dimensions = 4 or 12 mod 16) and multiplied with mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).
+// The rank-ny downdate P -= U'U uses the same instruction with U in shared memory.
+//
+// Replaces `kalman_likelihood(Y,Z,H,T,R,Q,a0,P,start,last,presample,ws)` (reference call site
+// src/estimation/estimation.jl:687-700) for a selection matrix Z; arguments shared with kalman_generic.cuh.
+#pragma once
+#include "kalman_dmma.cuh"
+
+namespace dyb {
+
+constexpr int DL_BK = 8;          // k-panel depth
+constexpr int DL_NTP = 9;         // tile columns per pass (accumulators: 2 strips x 9 tiles x 2 doubles per lane)
+constexpr int DL_LDB = 12;        // leading dimension of the staged B panel (8 rows, = 12 mod 16)
+
+struct KalmanLargeGeom { int nsp, lda, nyp, ldu, nwarps; };
+
+inline KalmanLargeGeom kalman_large_geom(int ns, int ny) {
+  KalmanLargeGeom q;
+  q.nsp = (ns + 7) / 8 * 8; q.lda = dmma_pad_ld(q.nsp);
+  q.nyp = (ny + 3) / 4 * 4; q.ldu = dmma_pad_ld(q.nyp);
+  q.nwarps = (q.nsp / 8 + 1) / 2;
+  return q;
+}
+inline size_t kalman_large_smem_doubles(int ns, int ny) {
+  const KalmanLargeGeom q = kalman_large_geom(ns, ny);
+  return 2 * ((size_t)q.lda * DL_BK + (size_t)DL_LDB * 8 * DL_NTP) + (size_t)q.ldu * q.nsp + (size_t)ny * ny +
+         2 * (size_t)q.nsp + 2 * (size_t)ny + 8;
+}
+inline size_t kalman_large_scratch_doubles(int ns) {
+  const size_t nsp = (size_t)((ns + 7) / 8 * 8);
+  return 2 * nsp * nsp;
+}
+
+// C = A B (+ Cinit) on the nsp x nsp tile grid, block-cooperative.
+//   A(i,k) = Ag[i + lda_g k]                         (valid for i, k < nv; zero beyond)
+//   B(k,j) = BT ? Bg[j + ldb_g k] : Bg[k + ldb_g j]  (same validity)
+//   SYMM: only tiles on or below the block diagonal are computed, the result is mirrored (C symmetric)
+//   Cinit (may be null): nv x nv column-major with leading dimension nv, added to the valid part
+// (no __restrict__ on purpose: A / B may have been written earlier in the same kernel, the read-only data path must not
+// be used for them)
+template <bool BT, bool SYMM>
+DYB_D void block_gemm_dmma(const double* Ag, int lda_g, const double* Bg, int ldb_g, int nv,
+                           int nsp, int lda, const double* Cinit, double* Cg, int ldc,
+                           double* As0, double* Bs0, int panel_doubles) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int nw = nt >> 5, ntile = nsp / 8, npanel = nsp / DL_BK;
+  constexpr int MAXR = 8;                 // staged doubles per thread and panel (>= (nsp*8 + 8*72) / threads)
+  for (int jt0 = 0; jt0 < ntile; jt0 += DL_NTP) {
+    const int ntw = (ntile - jt0 < DL_NTP) ? ntile - jt0 : DL_NTP;
+    const int ncolw = 8 * ntw, jbase = 8 * jt0;
+    const int nA = nsp * DL_BK, nB = DL_BK * ncolw;
+    double c[2][DL_NTP][2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int si = warp + s * nw;
+#pragma unroll
+      for (int jt = 0; jt < DL_NTP; ++jt) {
+        c[s][jt][0] = 0.0; c[s][jt][1] = 0.0;
+        if (Cinit && si < ntile && jt < ntw && (!SYMM || jt0 + jt <= si)) {
+          const int i = 8 * si + gq, j = jbase + 8 * jt + 2 * tq;
+          if (i < nv && j < nv) c[s][jt][0] = Cinit[i + (size_t)nv * j];
+          if (i < nv && j + 1 < nv) c[s][jt][1] = Cinit[i + (size_t)nv * (j + 1)];
+        }
+      }
+    }
+    double stage[MAXR];
+    auto fetch = [&](int p) {
+      const int k0 = p * DL_BK;
+#pragma unroll
+      for (int r = 0; r < MAXR; ++r) {
+        const int e = tid + r * nt;
+        double v = 0.0;
+        if (e < nA) {
+          const int i = e % nsp, kk = e / nsp;
+          if (i < nv && k0 + kk < nv) v = Ag[i + (size_t)lda_g * (k0 + kk)];
+        } else if (e < nA + nB) {
+          const int f = e - nA;
+          if (BT) {
+            const int n = f % ncolw, kk = f / ncolw;
+            if (jbase + n < nv && k0 + kk < nv) v = Bg[(jbase + n) + (size_t)ldb_g * (k0 + kk)];
+          } else {
+            const int kk = f % DL_BK, n = f / DL_BK;
+            if (jbase + n < nv && k0 + kk < nv) v = Bg[(k0 + kk) + (size_t)ldb_g * (jbase + n)];
+          }
+        }
+        stage[r] = v;
+      }
+    };
+    auto commit = [&](int buf) {
+      double* As = As0 + buf * panel_doubles;
+      double* Bs = Bs0 + buf * panel_doubles;
+#pragma unroll
+      for (int r = 0; r < MAXR; ++r) {
+        const int e = tid + r * nt;
+        if (e < nA) {
+          const int i = e % nsp, kk = e / nsp;
+          As[i + lda * kk] = stage[r];
+        } else if (e < nA + nB) {
+          const int f = e - nA;
+          int kk, n;
+          if (BT) { n = f % ncolw; kk = f / ncolw; } else { kk = f % DL_BK; n = f / DL_BK; }
+          Bs[kk + DL_LDB * n] = stage[r];
+        }
+      }
+    };
+    fetch(0);
+    commit(0);
+    __syncthreads();
+    for (int p = 0; p < npanel; ++p) {
+      if (p + 1 < npanel) fetch(p + 1);
+      const double* As = As0 + (p & 1) * panel_doubles;
+      const double* Bs = Bs0 + (p & 1) * panel_doubles;
+#pragma unroll
+      for (int ks = 0; ks < DL_BK / 4; ++ks) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int si = warp + s * nw;
+          if (si < ntile) {
+            const double av = As[(8 * si + gq) + lda * (4 * ks + tq)];
+#pragma unroll
+            for (int jt = 0; jt < DL_NTP; ++jt)
+              if (jt < ntw && (!SYMM || jt0 + jt <= si))
+                dmma884(c[s][jt][0], c[s][jt][1], av, Bs[(4 * ks + tq) + DL_LDB * (8 * jt + gq)]);
+          }
+        }
+      }
+      if (p + 1 < npanel) commit((p + 1) & 1);
+      __syncthreads();
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int si = warp + s * nw;
+      if (si >= ntile) continue;
+#pragma unroll
+      for (int jt = 0; jt < DL_NTP; ++jt) {
+        if (jt >= ntw) continue;
+        const int i = 8 * si + gq, j = jbase + 8 * jt + 2 * tq;
+        if (!SYMM) {
+          Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1];
+        } else if (jt0 + jt < si) {
+          Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1];
+          Cg[j + (size_t)ldc * i] = c[s][jt][0]; Cg[(j + 1) + (size_t)ldc * i] = c[s][jt][1];
+        } else if (jt0 + jt == si) {
+          if (i >= j) { Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[j + (size_t)ldc * i] = c[s][jt][0]; }
+          if (i >= j + 1) { Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1]; Cg[(j + 1) + (size_t)ldc * i] = c[s][jt][1]; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// blockDim.x = 32 * nwarps (nwarps = ceil(ntile / 2) <= 16); g.scratch: 2 nsp^2 doubles per CTA
+__global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGenericArgs g, KalmanLargeGeom q) {
+  extern __shared__ double sm[];
+  const int ns = g.ns, ny = g.ny, nsp = q.nsp, lda = q.lda, nyp = q.nyp, ldu = q.ldu;
+  const int ntile = nsp / 8;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3, nw = nt >> 5;
+  const int panel_doubles = lda * DL_BK + DL_LDB * 8 * DL_NTP;
+  double* As0 = sm;                                  // two panels: [As | Bs] [As | Bs]
+  double* Bs0 = sm + lda * DL_BK;
+  double* U = sm + 2 * panel_doubles;                // U[q + ldu * s], q < nyp
+  double* F = U + (size_t)ldu * nsp;
+  double* a = F + (size_t)ny * ny;
+  double* au = a + nsp;
+  double* v = au + nsp;
+  double* w = v + ny;
+  __shared__ int bad;
+  __shared__ int zi[64];
+  double* P = g.scratch + (size_t)blockIdx.x * 2 * nsp * nsp;      // P[i + nsp * j]
+  double* Mx = P + (size_t)nsp * nsp;
+
+  for (long long d = blockIdx.x; d < g.n_draws; d += gridDim.x) {
+    __syncthreads();
+    if (g.status_in && g.status_in[d] != ST_OK) {
+      if (tid == 0) { g.loglik[d] = -INFINITY; g.status[d] = g.status_in[d]; }
+      continue;
+    }
+    const double* Tm = g.T + (size_t)d * ns * ns;
+    const double* QQ = g.RQR + (size_t)d * ns * ns;
+    const double* P0 = g.P0 + (size_t)d * ns * ns;
+    const double* Hm = g.H ? g.H + (size_t)d * ny * ny : nullptr;
+    const double* yb = g.ybar_obs ? g.ybar_obs + (size_t)d * ny : nullptr;
+    if (tid == 0) bad = 0;
+    for (int i = tid; i < ny; i += nt) zi[i] = g.z_idx[i];
+    for (int e = tid; e < nsp * nsp; e += nt) {
+      const int i = e % nsp, j = e / nsp;
+      P[e] = (i < ns && j < ns) ? P0[i + (size_t)ns * j] : 0.0;
+    }
+    for (int e = tid; e < ldu * nsp; e += nt) U[e] = 0.0;
+    for (int i = tid; i < nsp; i += nt) { a[i] = (g.a0 && i < ns) ? g.a0[(size_t)d * ns + i] : 0.0; au[i] = 0.0; }
+    __syncthreads();
+    double acc = 0.0;          // only thread 0's copy is used
+    int nseen = 0;
+
+    for (int t = 0; t < g.nobs; ++t) {
+      const double* yt = g.Y + (size_t)t * ny;
+      for (int i = tid; i < ny; i += nt) {
+        const double yi = yt[i];
+        v[i] = isnan(yi) ? 0.0 : (yi - (yb ? yb[i] : 0.0)) - a[zi[i]];
+      }
+      for (int e = tid; e < ny * ny; e += nt) {
+        const int i = e % ny, j = e / ny;
+        const bool mi = isnan(yt[i]), mj = isnan(yt[j]);
+        double f = P[zi[i] + (size_t)nsp * zi[j]] + (Hm ? Hm[e] : 0.0);
+        if (mi || mj) f = (i == j) ? 1.0 : 0.0;
+        F[e] = f;
+      }
+      __syncthreads();
+      if (tid < 32) {                         // Cholesky of F by warp 0 (right-looking), then w = L^-1 v
+        for (int j = 0; j < ny; ++j) {
+          const double djj = F[j + ny * j];
+          __syncwarp();
+          if (tid == 0) { if (!(djj > 0.0)) bad = 1; F[j + ny * j] = sqrt(djj); }
+          __syncwarp();
+          const double ljj = F[j + ny * j];
+          for (int i = j + 1 + tid; i < ny; i += 32) F[i + ny * j] /= ljj;
+          __syncwarp();
+          for (int c = j + 1; c < ny; ++c) {
+            const double lcj = F[c + ny * j];
+            for (int i = c + tid; i < ny; i += 32) F[i + ny * c] -= F[i + ny * j] * lcj;
+          }
+          __syncwarp();
+        }
+        if (tid == 0) {
+          double quad = 0.0, ldet = 0.0;
+          int cnt = 0;
+          for (int i = 0; i < ny; ++i) {
+            double x = v[i];
+            for (int p = 0; p < i; ++p) x -= F[i + ny * p] * w[p];
+            x /= F[i + ny * i];
+            w[i] = x;
+            quad += x * x;
+            ldet += log(F[i + ny * i]);
+            cnt += isnan(yt[i]) ? 0 : 1;
+          }
+          if (t >= g.presample) { acc += 2.0 * ldet + quad; nseen += cnt; }
+        }
+      }
+      __syncthreads();
+      if (t == g.nobs - 1) break;
+      // U[:, s] = L^-1 (Z P)[:, s] ; au = a + U'w
+      for (int s = tid; s < ns; s += nt) {
+        double x = a[s];
+        for (int i = 0; i < ny; ++i) {
+          double u = isnan(yt[i]) ? 0.0 : P[zi[i] + (size_t)nsp * s];
+          for (int p = 0; p < i; ++p) u -= F[i + ny * p] * U[p + ldu * s];
+          u /= F[i + ny * i];
+          U[i + ldu * s] = u;
+          x += u * w[i];
+        }
+        au[s] = x;
+      }
+      __syncthreads();
+      // a <- T au
+      for (int i = tid; i < ns; i += nt) {
+        double x = 0.0;
+        for (int p = 0; p < ns; ++p) x = fma(Tm[i + (size_t)ns * p], au[p], x);
+        a[i] = x;
+      }
+      // P <- P - U'U, tile by tile (full matrix; both triangles get identical sums)
+      for (int tl = warp; tl < ntile * ntile; tl += nw) {
+        const int i0 = 8 * (tl % ntile), j0 = 8 * (tl / ntile);
+        double c0 = P[(i0 + gq) + (size_t)nsp * (j0 + 2 * tq)], c1 = P[(i0 + gq) + (size_t)nsp * (j0 + 2 * tq + 1)];
+        for (int k0 = 0; k0 < nyp; k0 += 4)
+          dmma884(c0, c1, -U[(k0 + tq) + ldu * (i0 + gq)], U[(k0 + tq) + ldu * (j0 + gq)]);
+        P[(i0 + gq) + (size_t)nsp * (j0 + 2 * tq)] = c0; P[(i0 + gq) + (size_t)nsp * (j0 + 2 * tq + 1)] = c1;
+      }
+      __syncthreads();
+      // M = T P ; P = M T' + R Q R'
+      block_gemm_dmma<false, false>(Tm, ns, P, nsp, ns, nsp, lda, nullptr, Mx, nsp, As0, Bs0, panel_doubles);
+      block_gemm_dmma<true, true>(Mx, nsp, Tm, ns, ns, nsp, lda, QQ, P, nsp, As0, Bs0, panel_doubles);
+    }
+    if (tid == 0) {
+      const double ll = -0.5 * (nseen * 1.8378770664093453 + acc);
+      if (bad || !isfinite(ll)) { g.loglik[d] = -INFINITY; g.status[d] = ST_F_NOT_PD; }
+      else { g.loglik[d] = ll; g.status[d] = ST_OK; }
+    }
+  }
+}
+
+}  // namespace dyb

@@ -24,10 +24,12 @@ def _random_state_space(rng, n, ns, ny, nx):
 
 @pytest.mark.parametrize("ns,ny,nobs,n,variant", [
     (6, 2, 50, 40, 0), (6, 2, 50, 40, 2), (40, 7, 60, 12, 1), (40, 7, 60, 12, 2), (24, 5, 30, 9, 2), (37, 9, 25, 7, 2),
-    (64, 12, 20, 5, 2), (88, 20, 10, 3, 2), (110, 20, 12, 3, 0), (200, 20, 6, 2, 0)])
+    (64, 12, 20, 5, 2), (88, 20, 10, 3, 2), (110, 20, 12, 3, 0), (110, 20, 12, 3, 1), (97, 3, 9, 4, 0),
+    (200, 20, 6, 2, 0), (200, 20, 6, 2, 1), (256, 7, 4, 2, 0)])
 def test_generic_kalman_matches_oracle(ns, ny, nobs, n, variant):
-    """variant 1 = scalar kernel, 2 = tensor-core (DMMA) kernel, 0 = automatic choice; sizes of BASELINE configs 4
-    (ns 40, ny 7) and 5 (ns 200, ny 20) included."""
+    """variant 1 = scalar kernel, 2 = tensor-core (DMMA) kernel, 0 = automatic choice (shared-memory DMMA kernel for
+    8 < ns <= 88, L2-scratch DMMA kernel for 88 < ns <= 256); sizes of BASELINE configs 4 (ns 40, ny 7) and 5 (ns 200,
+    ny 20) included."""
     from dynare_jl_b200.engine import kalman_batch, set_kalman_variant
     set_kalman_variant(variant)
     rng = np.random.default_rng(ns)

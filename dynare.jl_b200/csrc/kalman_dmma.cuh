@@ -31,6 +31,57 @@ DYB_HD int dmma_pad_ld(int n) {        // smallest ld >= n with ld mod 16 in {4,
   return ld;
 }
 
+// Cholesky of the ny x ny innovation covariance (ny <= 8) and w = L^-1 v by ONE warp with the matrix in registers:
+// lane i owns row i, pivots and multipliers travel by shuffles (no shared-memory round trips on the critical path).
+// In: F (column-major, lower part used), v.  Out: F <- L (lower incl. diagonal), w, and on every lane the sums
+// quad = w'w and ldet = sum_i log L_ii; returns false if a pivot is not positive.
+DYB_D bool chol8_warp(double* F, int ny, const double* v, double* w, double& quad, double& ldet) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = (lane < ny && j <= lane) ? F[lane + ny * j] : 0.0;
+  double rd = 1.0, ldiag = 1.0;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < ny) {
+      const double d = __shfl_sync(FULL, f[j], j);
+      ok = ok && (d > 0.0);
+      const double r = rsqrt(d);
+      const double lij = (lane == j) ? d * r : f[j] * r;
+      f[j] = lij;
+      if (lane == j) { rd = r; ldiag = lij; }
+#pragma unroll
+      for (int c = j + 1; c < 8; ++c) {
+        if (c < ny) {
+          const double lcj = __shfl_sync(FULL, lij, c);
+          f[c] = fma(-lij, lcj, f[c]);
+        }
+      }
+    }
+  }
+  double x = lane < ny ? v[lane] : 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < ny) {
+      const double wj = __shfl_sync(FULL, x * rd, j);
+      if (lane > j) x = fma(-f[j], wj, x);
+    }
+  }
+  const double wi = x * rd;
+  double q2 = lane < ny ? wi * wi : 0.0, lg = lane < ny ? log(ldiag) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { q2 += __shfl_xor_sync(FULL, q2, o); lg += __shfl_xor_sync(FULL, lg, o); }
+  if (lane < ny) {
+    w[lane] = wi;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j <= lane) F[lane + ny * j] = f[j];
+  }
+  quad = q2; ldet = lg;
+  return ok;
+}
+
 struct KalmanDmmaGeom { int nsp, ld, nyp, ldu; };
 
 inline KalmanDmmaGeom kalman_dmma_geom(int ns, int ny) {
@@ -106,7 +157,15 @@ kalman_dmma_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
         F[e] = f;
       }
       __syncthreads();
-      if (tid < 32) {                         // Cholesky of F by warp 0 (right-looking), then w = L^-1 v
+      if (tid < 32 && ny <= 8) {              // small ny: register / shuffle Cholesky
+        double quad, ldet;
+        const bool okc = chol8_warp(F, ny, v, w, quad, ldet);
+        const int cnt = __popc(__ballot_sync(0xffffffffu, tid < ny && !isnan(yt[tid < ny ? tid : 0])));
+        if (tid == 0) {
+          if (!okc) bad = 1;
+          if (t >= g.presample) { acc += 2.0 * ldet + quad; nseen += cnt; }
+        }
+      } else if (tid < 32) {                  // Cholesky of F by warp 0 (right-looking), then w = L^-1 v
         for (int j = 0; j < ny; ++j) {
           const double djj = F[j + ny * j];
           __syncwarp();
@@ -152,10 +211,13 @@ kalman_dmma_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
       }
       __syncthreads();
       // ---- P <- P - U'U  (strip of warp `warp`) ; a <- T au -------------------------------------------------------
-      for (int i = tid; i < ns; i += nt) {
+      for (int base = 0; base < 4 * ns; base += nt) {       // 4 lanes per row, combined by shuffles (uniform loop)
+        const int idx = base + tid, i = idx >> 2, part = idx & 3;
         double x = 0.0;
-        for (int p = 0; p < ns; ++p) x = fma(Ts[i + ld * p], au[p], x);
-        a[i] = x;                              // nobody reads a[] before the next barrier
+        if (idx < 4 * ns) for (int p = part; p < ns; p += 4) x = fma(Ts[i + ld * p], au[p], x);
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        if (idx < 4 * ns && part == 0) a[i] = x;            // nobody reads a[] before the next barrier
       }
       {
         double c[MAXT][2];

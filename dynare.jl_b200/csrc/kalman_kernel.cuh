@@ -33,12 +33,16 @@ DYB_D double fast_rsqrt(double x) {
 
 template <class M>
 struct KalmanCfg {
-  static constexpr int BLOCK = 64;
   // packed R Q R' goes to shared memory ([element][thread], conflict-free) to keep the register count low
-  // enough for 7 CTAs per SM (one wave for 65 536 draws on 148 SMs)
+  // enough for 7 CTAs per SM (one wave for 65 536 draws on 148 SMs).  Models whose packed covariance would not
+  // fit the register file beside T_l (ls2003: 55 + 55 + 60 doubles) keep P in shared memory as well and use
+  // one-warp CTAs so that 7 of them still fit an SM.
   static constexpr int QQ_N = M::NS * (M::NS + 1) / 2;
-  static constexpr bool QQ_SMEM = (QQ_N * BLOCK * 8 <= 16 * 1024);
-  static constexpr int MIN_CTAS = QQ_SMEM ? 7 : 4;
+  static constexpr bool P_SMEM = (QQ_N + M::NS * M::K > 96);
+  static constexpr int BLOCK = P_SMEM ? 32 : 64;
+  static constexpr bool QQ_SMEM = P_SMEM || (QQ_N * BLOCK * 8 <= 16 * 1024);
+  static constexpr int SMEM_DOUBLES_PER_THREAD = (QQ_SMEM ? QQ_N : 0) + (P_SMEM ? QQ_N : 0);
+  static constexpr int MIN_CTAS = 7;
 };
 
 template <class M>
@@ -54,6 +58,7 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
   extern __shared__ double ysh[];                      // NY * nobs, then (optionally) QQ_N * BLOCK
   for (int i = threadIdx.x; i < NY * nobs; i += blockDim.x) ysh[i] = Y[i];
   double* qsh = ysh + NY * nobs + threadIdx.x;          // this thread's column of the R Q R' tile
+  double* psh = qsh + Cfg::QQ_N * Cfg::BLOCK;           // ... and of the P tile (P_SMEM only)
   __syncthreads();
 
   const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,7 +73,9 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
 
   double Tl[NS * K];                      // row-major
   double QQ[Cfg::QQ_SMEM ? 1 : NS * (NS + 1) / 2];
-  double P[NS * (NS + 1) / 2];
+  double Preg[Cfg::P_SMEM ? 1 : NS * (NS + 1) / 2];
+  auto Pget = [&](int e) -> double { return Cfg::P_SMEM ? psh[e * Cfg::BLOCK] : Preg[Cfg::P_SMEM ? 0 : e]; };
+  auto Pset = [&](int e, double v) { if (Cfg::P_SMEM) psh[e * Cfg::BLOCK] = v; else Preg[Cfg::P_SMEM ? 0 : e] = v; };
   double a[NS];
   double yb[NY];
   double H[NY * (NY + 1) / 2];
@@ -78,7 +85,7 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
   for (int i = 0; i < NS * (NS + 1) / 2; ++i) {
     const double q = s_[(L::OFF_QQ + i) * st];
     if (Cfg::QQ_SMEM) qsh[i * Cfg::BLOCK] = q; else QQ[i] = q;
-    P[i] = s_[(L::OFF_P0 + i) * st];
+    Pset(i, s_[(L::OFF_P0 + i) * st]);
   }
 #pragma unroll
   for (int i = 0; i < NY; ++i) yb[i] = s_[(L::OFF_YB + i) * st];
@@ -107,7 +114,7 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
     for (int i = 0; i < NY; ++i)
 #pragma unroll
       for (int j = 0; j <= i; ++j) {
-        double f = P[sym(M::obs_idx_state(i), M::obs_idx_state(j))] + H[tri(i, j)];
+        double f = Pget(sym(M::obs_idx_state(i), M::obs_idx_state(j))) + H[tri(i, j)];
         if (miss[i] || miss[j]) f = (i == j) ? 1.0 : 0.0;
         F[tri(i, j)] = f;
       }
@@ -158,7 +165,7 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
     for (int j = 0; j < K; ++j) {
 #pragma unroll
       for (int i = 0; i < NY; ++i) {
-        double x = miss[i] ? 0.0 : P[sym(M::obs_idx_state(i), M::lagged_state_ids(j))];
+        double x = miss[i] ? 0.0 : Pget(sym(M::obs_idx_state(i), M::lagged_state_ids(j)));
 #pragma unroll
         for (int q = 0; q < i; ++q) x = fma(-F[tri(i, q)], U[q + NY * j], x);
         U[i + NY * j] = x * rdiag[i];
@@ -174,12 +181,13 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
       al[j] = x;
 #pragma unroll
       for (int q = 0; q <= j; ++q) {
-        double pjq = P[sym(M::lagged_state_ids(j), M::lagged_state_ids(q))];
+        double pjq = Pget(sym(M::lagged_state_ids(j), M::lagged_state_ids(q)));
 #pragma unroll
         for (int i = 0; i < NY; ++i) pjq = fma(-U[i + NY * j], U[i + NY * q], pjq);
         Pll[tri(j, q)] = pjq;
       }
     }
+    if (Cfg::P_SMEM) asm volatile("" ::: "memory");
     // ---- time update ---------------------------------------------------------------------------
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -200,8 +208,9 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
         double x2 = Cfg::QQ_SMEM ? qsh[tri(s, t2) * Cfg::BLOCK] : QQ[tri(s, t2)];
 #pragma unroll
         for (int j = 0; j < K; ++j) x2 = fma(mrow[j], Tl[t2 * K + j], x2);
-        P[tri(s, t2)] = x2;
+        Pset(tri(s, t2), x2);
       }
+      if (Cfg::P_SMEM) asm volatile("" ::: "memory");   // keep the shared-memory loads of row s inside its iteration
     }
   }
   acc += log(detp);

@@ -65,7 +65,7 @@ cudaError_t mt_kalman(const double* d_ss, long long n, const double* d_Y, int no
   using Cfg = KalmanCfg<MT>;
   const int block = Cfg::BLOCK;
   const long long grid = (n + block - 1) / block;
-  const size_t smem = sizeof(double) * ((size_t)MT::NY * (size_t)nobs + (Cfg::QQ_SMEM ? (size_t)Cfg::QQ_N * block : 0));
+  const size_t smem = sizeof(double) * ((size_t)MT::NY * (size_t)nobs + (size_t)Cfg::SMEM_DOUBLES_PER_THREAD * block);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kalman_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -98,6 +98,115 @@ static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaSt
   return cudaGetLastError();
 }
 
+
+// ---- prior-predictive quantities per draw (src/estimation/priorprediction.jl:64-98): stdev of every endogenous
+// variable from the unconditional variance (compute_variance!, robustsqrt: src/perturbations.jl:195, 205) and impulse
+// responses to a one-standard-deviation shock (irfs!, src/perturbations.jl:670-694).  One CTA per draw. ------------
+struct PriorPredArgs {
+  int n, k, nx, periods;
+  int bk[64];
+  const double* g1;          // n x (k+nx) per draw
+  const double* sigma_e;     // nx x nx per draw
+  const int* status_in;
+  long long n_draws;
+  double lyap_tol; int lyap_maxit;
+  double* stdev;             // n per draw (may be null)
+  double* irfs;              // n x periods x nx per draw (may be null)
+  int* status;
+};
+
+// Sigma_e of every draw: the shock part of set_estimated_parameters! (src/estimation/estimation.jl:517-601)
+struct SigmaEArgs { int np, nx; int est_type[MAX_EST], est_i[MAX_EST], est_j[MAX_EST]; };
+__global__ void sigma_e_kernel(SigmaEArgs a, const double* __restrict__ sigma_e0, const double* __restrict__ theta,
+                               long long n_draws, double* __restrict__ out) {
+  const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_draws) return;
+  double* S = out + d * a.nx * a.nx;
+  for (int e = 0; e < a.nx * a.nx; ++e) S[e] = sigma_e0[e];
+  for (int q = 0; q < a.np; ++q) {
+    const double v = theta[d * a.np + q];
+    const int i = a.est_i[q], j = a.est_j[q];
+    if (a.est_type[q] == EST_SD_SHOCK) S[i + a.nx * j] = v * v;
+    else if (a.est_type[q] == EST_VAR_SHOCK) S[i + a.nx * j] = v;
+    else if (a.est_type[q] == EST_CORR_SHOCK) { const double c = v * sqrt(S[i + a.nx * i] * S[j + a.nx * j]); S[i + a.nx * j] = c; S[j + a.nx * i] = c; }
+  }
+}
+
+__global__ void __launch_bounds__(128) prior_predictive_kernel(PriorPredArgs a) {
+  extern __shared__ double sm[];
+  const int n = a.n, k = a.k, nx = a.nx, tid = threadIdx.x, nt = blockDim.x;
+  double* Ak = sm; double* Sg = Ak + k * k; double* Tm = Sg + k * k; double* BQ = Tm + k * k;   // BQ: k x nx
+  double* red = BQ + k * nx; double* ycur = red + 8; double* ynext = ycur + n;
+  for (long long d = blockIdx.x; d < a.n_draws; d += gridDim.x) {
+    __syncthreads();
+    int status = a.status_in[d];
+    const double* g1 = a.g1 + (size_t)d * n * (k + nx);
+    const double* g2 = g1 + (size_t)n * k;
+    const double* Se = a.sigma_e + (size_t)d * nx * nx;
+    if (status == ST_OK && a.stdev) {
+      for (int e = tid; e < k * k; e += nt) Ak[e] = g1[a.bk[e % k] + n * (e / k)];
+      for (int e = tid; e < k * nx; e += nt) {
+        const int i = e % k, q = e / k;
+        double s = 0.0;
+        for (int f = 0; f < nx; ++f) s = fma(g2[a.bk[i] + n * f], Se[f + nx * q], s);
+        BQ[e] = s;
+      }
+      __syncthreads();
+      for (int e = tid; e < k * k; e += nt) {
+        const int i = e % k, j = e / k;
+        double s = 0.0;
+        for (int q = 0; q < nx; ++q) s = fma(BQ[i + k * q], g2[a.bk[j] + n * q], s);
+        Sg[e] = s;
+      }
+      __syncthreads();
+      int it = 0;
+      if (!blk_lyapunov(Ak, Sg, Tm, k, a.lyap_tol, a.lyap_maxit, red, &it)) status = ST_NONSTATIONARY;
+      __syncthreads();
+      // diag of Sigma_y = g1_1 Sigma_s g1_1' + g1_2 Sigma_e g1_2'
+      for (int v = tid; v < n; v += nt) {
+        double s = 0.0;
+        for (int i = 0; i < k; ++i) {
+          double r = 0.0;
+          for (int j = 0; j < k; ++j) r = fma(Sg[i + k * j], g1[v + n * j], r);
+          s = fma(g1[v + n * i], r, s);
+        }
+        for (int q = 0; q < nx; ++q) {
+          double r = 0.0;
+          for (int f = 0; f < nx; ++f) r = fma(Se[q + nx * f], g2[v + n * f], r);
+          s = fma(g2[v + n * q], r, s);
+        }
+        a.stdev[(size_t)d * n + v] = status == ST_OK ? sqrt(s + 2.220446049250313e-16) : NAN;
+      }
+    } else if (a.stdev) {
+      for (int v = tid; v < n; v += nt) a.stdev[(size_t)d * n + v] = NAN;
+    }
+    if (a.irfs) {
+      double* out = a.irfs + (size_t)d * n * a.periods * nx;
+      for (int q = 0; q < nx; ++q) {
+        __syncthreads();
+        const double x = sqrt(Se[q + nx * q] + 2.220446049250313e-16);
+        for (int v = tid; v < n; v += nt) {
+          const double y = status == ST_OK || status == ST_NONSTATIONARY ? g2[v + n * q] * x : NAN;
+          ycur[v] = y;
+          out[v + (size_t)n * (0 + (size_t)a.periods * q)] = y;
+        }
+        for (int p = 1; p < a.periods; ++p) {
+          __syncthreads();
+          for (int v = tid; v < n; v += nt) {
+            double s = 0.0;
+            for (int j = 0; j < k; ++j) s = fma(g1[v + n * j], ycur[a.bk[j]], s);
+            ynext[v] = s;
+            out[v + (size_t)n * (p + (size_t)a.periods * q)] = s;
+          }
+          __syncthreads();
+          double* t_ = ycur; ycur = ynext; ynext = t_;
+        }
+      }
+    }
+    if (tid == 0) a.status[d] = status;
+  }
+}
+
 }  // namespace dyb
 
 using namespace dyb;
@@ -316,6 +425,48 @@ int dyb_loglik_from_jacobian_batch(dyb_handle* h, const double* jac, const doubl
     DYB_CUDA(launch_kalman_generic(g, h->device, h->stream, sg));
     h->launches += 1;
   }
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int dyb_prior_predictive_batch(dyb_handle* h, const double* theta, int64_t n, int32_t periods, double* ybar, double* stdev,
+                                double* irfs, int32_t* status) {
+  if (h && !h->ops) return fail(DYB_ERR_UNSUPPORTED, "needs a handle with a device model function");
+  if (!h || n < 0 || periods < 0 || (n > 0 && (!theta || !status))) return fail(DYB_ERR_ARG, "bad argument");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  const dyb_model_dims& d = h->dims;
+  if (d.k > 64) return fail(DYB_ERR_UNSUPPORTED, "more than 64 state variables");
+  const size_t N = (size_t)n;
+  Stager sg(h->stream);
+  double* dg1 = sg.temp<double>((size_t)d.n * (d.k + d.nx) * N);
+  double* dse = sg.temp<double>((size_t)d.nx * d.nx * N);
+  int* dst1 = sg.temp<int>(N);
+  double* dse0 = sg.temp<double>((size_t)d.nx * d.nx);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  DYB_CUDA(cudaMemcpyAsync(dse0, h->hs.sigma_e.data(), sizeof(double) * d.nx * d.nx, cudaMemcpyHostToDevice, h->stream));
+  int rc = dyb_first_order_batch(h, theta, n, dg1, ybar, nullptr, nullptr, reinterpret_cast<int32_t*>(dst1));
+  if (rc) return rc;
+  const double* dth = sg.in(theta, (size_t)h->hs.np * N);
+  int* dst = sg.out(status, N);
+  double* dsd = sg.out(stdev, (size_t)d.n * N);
+  double* dirf = (irfs && periods > 0) ? sg.out(irfs, (size_t)d.n * periods * d.nx * N) : nullptr;
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  SigmaEArgs sa{};
+  sa.np = h->hs.np; sa.nx = d.nx;
+  for (int q = 0; q < h->hs.np; ++q) { sa.est_type[q] = h->hs.est_type[q]; sa.est_i[q] = h->hs.est_i[q]; sa.est_j[q] = h->hs.est_j[q]; }
+  sigma_e_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(sa, dse0, dth, n, dse);
+  PriorPredArgs pa{};
+  pa.n = d.n; pa.k = d.k; pa.nx = d.nx; pa.periods = periods;
+  h->ops->bkwrd_indices(pa.bk);
+  pa.g1 = dg1; pa.sigma_e = dse; pa.status_in = dst1; pa.n_draws = n;
+  pa.lyap_tol = h->hs.opt.lyap_tol; pa.lyap_maxit = h->hs.opt.lyap_maxit;
+  pa.stdev = dsd; pa.irfs = dirf; pa.status = dst;
+  const size_t smem = sizeof(double) * (3 * (size_t)d.k * d.k + (size_t)d.k * d.nx + 8 + 2 * (size_t)d.n);
+  long long grid = n < 148LL * 16 ? n : 148LL * 16;
+  prior_predictive_kernel<<<(unsigned)grid, 128, smem, h->stream>>>(pa);
+  DYB_CUDA(cudaGetLastError());
+  h->launches += 2;
   DYB_CUDA(sg.finish());
   return DYB_OK;
 }

@@ -39,6 +39,7 @@ struct ModelOps {
   // expand the SoA hand-off buffer into dense per-draw matrices (any output may be null)
   cudaError_t (*unpack)(const double* d_ss, long long n, double* T, double* RQR, double* P0,
                         double* ybar_obs, double* H, cudaStream_t);
+  void (*bkwrd_indices)(int* i_bkwrd_b /* dims.k */);   // variables with a lag, 0-based (Model.i_bkwrd_b)
 };
 
 const std::vector<const ModelOps*>& registry();

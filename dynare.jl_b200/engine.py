@@ -234,6 +234,17 @@ class BatchSSWs:
         g1 = g1.transpose(0, 2, 1)
         return dict(g1_1=g1[:, :, :d["k"]], g1_2=g1[:, :, d["k"]:], ybar=yb, cr_iters=it, lyap_iters=li, status=st)
 
+    def prior_predictive(self, Theta, periods=40):
+        """run_simulations (priorprediction.jl:64-98) for N draws at once: dict(steady_state (N, n), stdev (N, n),
+        irfs (N, nx, periods, n), status); failed draws carry NaN."""
+        Theta = self._theta(Theta)
+        n = Theta.shape[0]
+        d = self.dims
+        yb = np.full((n, d["n"]), np.nan); sd = np.empty((n, d["n"])); irf = np.empty((n, d["nx"], periods, d["n"]))
+        st = np.empty(n, dtype=np.int32)
+        L.check(self.lib.dyb_prior_predictive_batch(self._h, L.ptr(Theta), n, periods, L.ptr(yb), L.ptr(sd), L.ptr(irf), L.ptr(st)))
+        return dict(steady_state=yb, stdev=sd, irfs=irf, status=st)
+
     def state_space(self, Theta):
         """Returns dict(T, RQR, P0 (N,ns,ns), ybar_obs (N,ny), H (N,ny,ny), status)."""
         Theta = self._theta(Theta)

@@ -157,6 +157,13 @@ int dyb_state_space_batch(dyb_handle* h, const double* theta, int64_t n_draws,
                           double* T, double* RQR, double* P0, double* ybar_obs, double* H,
                           int32_t* status);
 
+/* prior-predictive quantities for N draws (run_simulations, src/estimation/priorprediction.jl:64-98): steady state,
+ * stdev = robustsqrt(diag(endogenous_variance)) of every endogenous variable (src/perturbations.jl:195-205) and the
+ * impulse responses of irfs! (src/perturbations.jl:670-694) to a one-standard-deviation shock.  Per draw: ybar n,
+ * stdev n, irfs n x periods x nx (column-major); status as in dyb_first_order_batch; any output but status may be NULL */
+int dyb_prior_predictive_batch(dyb_handle* h, const double* theta, int64_t n_draws, int32_t periods,
+                               double* ybar, double* stdev, double* irfs, int32_t* status);
+
 /* generic batched Kalman log-likelihood for arbitrary (dense) state spaces -- the
  * kalman_likelihood(Y,Z,H,T,R,Q,a0,P,start,last,presample,ws) call (src/estimation/estimation.jl:687-700)
  * without a model: per draw T ns x ns, RQR ns x ns, P0 ns x ns, a0 ns (NULL = 0), H ny x ny (NULL = 0);

@@ -225,3 +225,34 @@ def test_solver_variants_agree(name, golden, ws_factory):
     assert np.max(np.abs(res[1][1].astype(int) - res[2][1].astype(int))) <= 1
     assert np.mean(res[1][1] != res[2][1]) < 0.05
     assert np.max(np.abs(res[1][0] - res[2][0]) / np.abs(res[1][0])) <= 1e-9
+
+
+@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+def test_prior_predictive_moments_and_irfs(name, golden, ws_factory):
+    """run_simulations (priorprediction.jl:64-98): steady state, robustsqrt(diag(variance)) and the 40-period responses of
+    irfs! (perturbations.jl:670-694) for a batch of draws against the oracle's per-draw computation."""
+    g = golden(name)
+    m = models.get_model(name)
+    ws = ws_factory(name, g["Y"])
+    theta = g["theta"][:64]
+    out = ws.prior_predictive(theta, periods=40)
+    gs = g["status"][:64]
+    assert np.array_equal(out["status"] != 0, (gs != 0) & (gs != pl.ST_F_NOT_PD))      # filter failures do not exist here
+    eps = np.finfo(float).eps
+    checked = 0
+    for i in range(theta.shape[0]):
+        if out["status"][i] != 0:
+            assert np.all(np.isnan(out["stdev"][i]))
+            continue
+        d = pl.solve_draw(m, theta[i])
+        g11, g12 = d["sol"]["g1_1"], d["sol"]["g1_2"]
+        assert np.allclose(out["steady_state"][i], d["ybar"], rtol=1e-12, atol=1e-14)
+        sd = np.sqrt(np.diag(d["Sigma_y"]) + eps)
+        assert np.allclose(out["stdev"][i], sd, rtol=1e-8, atol=1e-12)
+        for q in range(m.nx):
+            y = g12[:, q] * np.sqrt(d["sigma_e"][q, q] + eps)
+            for p in range(40):
+                assert np.allclose(out["irfs"][i, q, p], y, rtol=1e-8, atol=1e-12), (i, q, p)
+                y = g11 @ y[m.i_bkwrd_b]
+        checked += 1
+    assert checked > 30

@@ -218,6 +218,9 @@ def build_spec(name: str, mf: ModFile) -> ModelSpec:
             txt = kw_pat.sub(lambda m: m.group(1) + "__kw", txt)
         return sp.sympify(txt.replace("^", "**"), locals=d)
 
+    # model-local variables (`# name = expr;`): substituted into the equations, in file order
+    for lname, lexpr in mf.model_locals:
+        local[lname] = parse(_time_subst(lexpr, names))
     resid = [parse(e) for e in eq_txt]
     for r in resid:
         bad = [s_ for s_ in r.free_symbols if s_.name not in local]
@@ -294,12 +297,26 @@ def build_spec(name: str, mf: ModFile) -> ModelSpec:
     for u, expr in mf.shock_var.items():
         if u in exo:
             sigma_e0[exo.index(u), exo.index(u)] = float(parse(expr).subs(pval))
+    for (a, b), expr in mf.shock_cov.items():
+        if a in exo and b in exo:
+            sigma_e0[exo.index(a), exo.index(b)] = sigma_e0[exo.index(b), exo.index(a)] = float(parse(expr).subs(pval))
     for (a, b), expr in mf.shock_corr.items():
         ia, ib = exo.index(a), exo.index(b)
         c = float(parse(expr).subs(pval)) * np.sqrt(sigma_e0[ia, ia] * sigma_e0[ib, ib])
         sigma_e0[ia, ib] = sigma_e0[ib, ia] = c
     ny = len(mf.varobs)
     sigma_m0 = np.zeros((ny, ny))
+    # calibrated measurement errors: `var <observed variable>; stderr s;` etc. in the shocks block
+    for u, expr in mf.shock_stderr.items():
+        if u in mf.varobs:
+            sigma_m0[mf.varobs.index(u), mf.varobs.index(u)] = float(parse(expr).subs(pval)) ** 2
+    for u, expr in mf.shock_var.items():
+        if u in mf.varobs:
+            sigma_m0[mf.varobs.index(u), mf.varobs.index(u)] = float(parse(expr).subs(pval))
+    for (a, b), expr in mf.shock_cov.items():
+        if a in mf.varobs and b in mf.varobs:
+            sigma_m0[mf.varobs.index(a), mf.varobs.index(b)] = sigma_m0[mf.varobs.index(b), mf.varobs.index(a)] = \
+                float(parse(expr).subs(pval))
 
     # --- observation / state bookkeeping (estimation.jl:384-390) ---------------------------
     obs_idx = [endo.index(v) for v in mf.varobs]
@@ -318,6 +335,12 @@ def build_spec(name: str, mf: ModFile) -> ModelSpec:
             else:
                 o = mf.varobs.index(e.name1)
                 est_type.append(EST_SD_MEAS); est_i.append(o); est_j.append(o)
+        elif e.kind == "var":
+            if e.name1 in exo:
+                est_type.append(EST_VAR_SHOCK); est_i.append(exo.index(e.name1)); est_j.append(exo.index(e.name1))
+            else:
+                o = mf.varobs.index(e.name1)
+                est_type.append(EST_VAR_MEAS); est_i.append(o); est_j.append(o)
         elif e.kind == "corr":
             if e.name1 in exo:
                 est_type.append(EST_CORR_SHOCK); est_i.append(exo.index(e.name1)); est_j.append(exo.index(e.name2))

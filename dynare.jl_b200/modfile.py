@@ -7,9 +7,12 @@ the reference tree and is not available here, so this module reads the declarati
 blocks directly.  It is a host-side set-up tool (runs once per model, never per draw).
 
 Supported: ``var``, ``varexo``, ``parameters``, parameter calibration statements,
-``model;`` / ``model(linear);``, ``steady_state_model;``, ``shocks;`` (``var x; stderr s;``,
-``var x = v;``, ``corr a, b = r;``), ``varobs``, ``estimated_params;``,
-``estimated_params_init;``, ``x.prior(shape=..., mean=..., stdev=...)`` statements and the
+``model;`` / ``model(linear);`` with model-local variables (``# name = expr;``), ``steady_state_model;``,
+``shocks;`` (``var x; stderr s;``, ``var x = v;``, ``var x, y = c;``, ``corr a, b = r;``, on shocks and on observed
+variables = calibrated measurement errors), ``varobs``, ``estimated_params;``, ``estimated_params_init;``,
+``x.prior(shape=..., mean=..., stdev=...)`` statements, the reference's Julia-syntax
+``prior!(:x | stdev(:x) | variance(:x) | corr(:a, :b), shape=..., mean=..., stdev=... | variance=..., domain=[a, b])``
+(``src/estimation/priors.jl:64-178``; e.g. ``test/models/estimation/nk1.mod:52-75``), ``verbatim`` blocks (skipped) and the
 ``nobs`` / ``first_obs`` / ``datafile`` options of ``estimation(...)`` (also when the
 statement is commented out with ``//``, which is how the reference's fixtures carry it:
 ``test/models/ls2003/ls2003.mod:85``).
@@ -41,11 +44,13 @@ class ModFile:
     params: List[str] = field(default_factory=list)
     calibration: List[Tuple[str, str]] = field(default_factory=list)   # (name, expr) in file order
     equations: List[Tuple[str, str]] = field(default_factory=list)     # (lhs, rhs); rhs '0' if none
+    model_locals: List[Tuple[str, str]] = field(default_factory=list)  # `# name = expr;` inside the model block
     linear: bool = False
     steady_state_model: List[Tuple[str, str]] = field(default_factory=list)
     shock_stderr: Dict[str, str] = field(default_factory=dict)
     shock_var: Dict[str, str] = field(default_factory=dict)
     shock_corr: Dict[Tuple[str, str], str] = field(default_factory=dict)
+    shock_cov: Dict[Tuple[str, str], str] = field(default_factory=dict)
     varobs: List[str] = field(default_factory=list)
     estimated_params: List[EstimatedParam] = field(default_factory=list)
     estimation_options: Dict[str, str] = field(default_factory=dict)
@@ -60,7 +65,59 @@ _SHAPES = {
     "uniform_pdf": "uniform", "uniform": "uniform",
     "inv_gamma2_pdf": "inv_gamma2", "inv_gamma2": "inv_gamma2",
     "weibull_pdf": "weibull", "weibull": "weibull",
+    # Julia-syntax names of prior!(..., shape=...) (src/estimation/priors.jl:147-178)
+    "inversegamma1": "inv_gamma", "inversegamma2": "inv_gamma2", "inversegamma": "inv_gamma2",
 }
+
+
+def _split_top(s: str) -> List[str]:
+    """Split on commas that are not inside (), [] or {}."""
+    out, depth, cur = [], 0, []
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append("".join(cur)); cur = []
+        else:
+            cur.append(ch)
+    out.append("".join(cur))
+    return [x.strip() for x in out if x.strip()]
+
+
+def _parse_prior_bang(stmt: str) -> Optional[EstimatedParam]:
+    """``prior!(:x, shape=Gamma, mean=0.5, stdev=0.5)`` and its stdev(:x) / variance(:x) / corr(:a, :b) forms."""
+    m = re.match(r"prior!\s*\((.*)\)\s*$", stmt, flags=re.S)
+    if not m:
+        return None
+    args = _split_top(m.group(1))
+    head = args[0].replace(" ", "")
+    mm = re.match(r"^:(\w+)$", head)
+    if mm:
+        kind, n1, n2 = "param", mm.group(1), None
+    else:
+        mm = re.match(r"^(stdev|variance)\(:(\w+)\)$", head)
+        if mm:
+            kind, n1, n2 = ("stderr" if mm.group(1) == "stdev" else "var"), mm.group(2), None
+        else:
+            mm = re.match(r"^corr\(:(\w+),:(\w+)\)$", head)
+            if not mm:
+                raise ValueError(f"unsupported prior! target: {args[0]!r}")
+            kind, n1, n2 = "corr", mm.group(1), mm.group(2)
+    kw = {}
+    for item in args[1:]:
+        k, v = item.split("=", 1)
+        kw[k.strip()] = v.strip()
+    shape = _SHAPES[kw["shape"].lower()]
+    mean = _num(kw["mean"])
+    stdev = _num(kw["stdev"]) if "stdev" in kw else _num(kw["variance"]) ** 0.5
+    init = _num(kw["initialvalue"]) if "initialvalue" in kw else None
+    dom = None
+    if "domain" in kw:
+        lo, hi = _split_top(kw["domain"].strip()[1:-1])
+        dom = (_num(lo), _num(hi))
+    return EstimatedParam(kind, n1, n2, shape, mean, stdev, init, dom)
 
 
 def _num(s: str) -> float:
@@ -69,7 +126,9 @@ def _num(s: str) -> float:
         return float("inf")
     if s == "-inf":
         return float("-inf")
-    return float(eval(s.replace("^", "**"), {"__builtins__": {}}, {}))
+    import math
+    env = {k: getattr(math, k) for k in ("sqrt", "exp", "log", "pi")}
+    return float(eval(s.replace("^", "**"), {"__builtins__": {}}, env))
 
 
 def _strip_comments(text: str) -> Tuple[str, List[str]]:
@@ -104,9 +163,42 @@ def _parse_estimation_options(stmt: str, opts: Dict[str, str]) -> None:
             opts[item.strip()] = "true"
 
 
+def _extract_bang_calls(text: str) -> Tuple[str, List[str]]:
+    """Pull the reference's Julia-syntax statements ``name!( ... )`` (balanced parentheses, no terminating ``;``
+    required) out of the text; returns (remaining text, calls)."""
+    calls, out, pos = [], [], 0
+    for m in re.finditer(r"\b\w+!\s*\(", text):
+        if m.start() < pos:
+            continue
+        depth, i = 0, m.end() - 1
+        while i < len(text):
+            if text[i] == "(":
+                depth += 1
+            elif text[i] == ")":
+                depth -= 1
+                if depth == 0:
+                    break
+            i += 1
+        calls.append(" ".join(text[m.start():i + 1].split()))
+        out.append(text[pos:m.start()])
+        pos = i + 1
+        while pos < len(text) and text[pos] in " \t":
+            pos += 1
+        if pos < len(text) and text[pos] == ";":
+            pos += 1
+    out.append(text[pos:])
+    return "".join(out), calls
+
+
 def parse_mod(text: str) -> ModFile:
     mf = ModFile()
     clean, comments = _strip_comments(text)
+    clean, bang_calls = _extract_bang_calls(clean)
+    for c in bang_calls:
+        if c.startswith("prior!"):
+            ep = _parse_prior_bang(c)
+            if ep is not None:
+                mf.estimated_params.append(ep)
     # an estimation statement that only exists as a comment still defines the sample
     for c in comments:
         if re.match(r"\s*estimation\s*\(", c):
@@ -123,7 +215,13 @@ def parse_mod(text: str) -> ModFile:
                 block = None
                 pending_shock = None
                 continue
+            if block == "verbatim":
+                continue
             if block == "model":
+                if flat.startswith("#"):
+                    lhs, rhs = flat[1:].split("=", 1)
+                    mf.model_locals.append((lhs.strip(), rhs.strip()))
+                    continue
                 if "=" in flat:
                     lhs, rhs = flat.split("=", 1)
                 else:
@@ -135,6 +233,10 @@ def parse_mod(text: str) -> ModFile:
                 lhs, rhs = flat.split("=", 1)
                 mf.steady_state_model.append((lhs.strip(), rhs.strip()))
             elif block == "shocks":
+                m = re.match(r"var\s+(\w+)\s*,\s*(\w+)\s*=\s*(.+)$", flat)
+                if m:
+                    mf.shock_cov[(m.group(1), m.group(2))] = m.group(3)
+                    continue
                 m = re.match(r"var\s+(\w+)\s*=\s*(.+)$", flat)
                 if m:
                     mf.shock_var[m.group(1)] = m.group(2)
@@ -143,7 +245,7 @@ def parse_mod(text: str) -> ModFile:
                 if m:
                     pending_shock = m.group(1)
                     continue
-                m = re.match(r"stderr\s+(.+)$", flat)
+                m = re.match(r"stderr\b\s*(.+)$", flat)
                 if m and pending_shock:
                     mf.shock_stderr[pending_shock] = m.group(1)
                     pending_shock = None
@@ -189,7 +291,7 @@ def parse_mod(text: str) -> ModFile:
             continue
 
         m = re.match(r"(model|steady_state_model|shocks|estimated_params|estimated_params_init|"
-                     r"initval|endval|histval|observation_trends|estimated_params_bounds)"
+                     r"initval|endval|histval|observation_trends|estimated_params_bounds|verbatim)"
                      r"\s*(\(([^)]*)\))?$", flat)
         if m:
             block = m.group(1)
@@ -217,6 +319,11 @@ def parse_mod(text: str) -> ModFile:
             stdev = _num(kw["stdev"]) if "stdev" in kw else _num(kw["variance"]) ** 0.5
             mf.estimated_params.append(
                 EstimatedParam(kind, n1, n2, _SHAPES[kw["shape"].lower()], _num(kw["mean"]), stdev))
+            continue
+        if flat.startswith("prior!"):
+            ep = _parse_prior_bang(flat)
+            if ep is not None:
+                mf.estimated_params.append(ep)
             continue
         m = re.match(r"(\w+)\s*=\s*(.+)$", flat)
         if m and m.group(1) in mf.params:

@@ -23,12 +23,14 @@
 
 extern const oracle_model oracle_model_fs2000;
 extern const oracle_model oracle_model_ls2003;
+extern const oracle_model oracle_model_hs_nk;
 
 enum { ST_OK = 0, ST_STEADY, ST_INDETERMINATE, ST_UNSTABLE, ST_SOLVER, ST_NONSTATIONARY, ST_F_NOT_PD };
 
 static const oracle_model* find_model(const char* name) {
   if (!strcmp(name, "fs2000")) return &oracle_model_fs2000;
   if (!strcmp(name, "ls2003")) return &oracle_model_ls2003;
+  if (!strcmp(name, "hs_nk")) return &oracle_model_hs_nk;
   return 0;
 }
 

@@ -11,6 +11,8 @@ SURVEY.md section 8c).  The known answers pinned here are mathematical identitie
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 
@@ -222,5 +224,59 @@ class LS2003(HandModel):
         return np.array(r)
 
 
+class HSNK(HandModel):
+    """Herbst-Schorfheide small New Keynesian model as the reference carries it in
+    ``test/models/estimation/test1.mod`` (model :26-36, steady state :38-47, calibrated measurement errors :55-58,
+    priors :60-77: parameters, one shock stderr, one measurement stderr, one shock and one measurement correlation)."""
+    name = "hs_nk"
+    linear = False
+    endo = ["y", "R", "pi", "z", "g", "YGR", "INFL", "INT"]
+    exo = ["eg", "ep", "ez"]
+    params = ["tau", "rho_R", "psi1", "psi2", "rho_g", "rho_z", "kappa", "piA", "gammaQ", "rA", "s_ep", "s_eg", "s_ez"]
+    params0 = np.array([2.83, 0.77, 1.8, 0.63, 0.98, 0.88, 0.78, 3.3, 0.52, 0.42, 0.22, 0.72, 0.31])
+    sigma_e0 = np.eye(3)
+    sigma_m0 = np.diag([(0.20 * 0.579923) ** 2, (0.20 * 1.470832) ** 2, (0.20 * 2.237937) ** 2])
+    varobs = ["YGR", "INFL", "INT"]
+    lagged = ["y", "R", "z", "g"]
+    led = ["y", "pi", "z", "g"]
+    est = [("param", "rA"), ("param", "piA"), ("param", "gammaQ"), ("param", "tau"), ("param", "kappa"),
+           ("param", "psi1"), ("param", "psi2"), ("param", "rho_R"), ("param", "rho_g"), ("param", "rho_z"),
+           ("param", "s_eg"), ("param", "s_ez"), ("stderr", "ep"), ("stderr", "INFL"),
+           ("corr", "eg", "ez"), ("corr", "YGR", "INT")]
+    priors = [("gamma", 0.5, 0.2), ("gamma", 7.0, 2.0), ("normal", 0.4, 0.2), ("gamma", 2.0, 0.5), ("beta", 0.5, 0.2),
+              ("gamma", 1.5, 0.25), ("gamma", 0.5, 0.25), ("beta", 0.5, 0.2), ("beta", 0.5, 0.2), ("beta", 0.5, 0.2),
+              ("inv_gamma", 1.2533141373155003, math.sqrt(0.4292036732051032)),
+              ("inv_gamma", 0.6266570686577502, math.sqrt(0.1073009183012758)),
+              ("inv_gamma", 1.0, 0.1), ("inv_gamma", 0.4, 0.1), ("normal", 0.0, 0.01), ("normal", 0.0, 0.01)]
+
+    @property
+    def theta_mode(self):                      # estimated_params_init (:80-93), calibration / prior mean elsewhere
+        return np.array([0.333453026636814, 3.427852381637088, 0.624767199308368, 2.263895645223946, 0.9,
+                         1.932357745633903, 0.465714640873466, 0.764476492352786, 0.990359718181570,
+                         0.917302546854851, 0.632177304244290, 0.192160214260411, 1.0, 0.4, 0.0, 0.0])
+
+    def steady_state(self, p):
+        tau, rho_R, psi1, psi2, rho_g, rho_z, kappa, piA, gammaQ, rA, s_ep, s_eg, s_ez = p
+        return np.array([0.0, 0.0, 0.0, 0.0, 0.0, gammaQ, piA, piA + rA + 4 * gammaQ])
+
+    def dynamic_resid(self, ym, y_, yp, u, p):
+        tau, rho_R, psi1, psi2, rho_g, rho_z, kappa, piA, gammaQ, rA, s_ep, s_eg, s_ez = p
+        y, R, pi, z, g, YGR, INFL, INT = y_
+        y_1, R_1, z_1, g_1 = ym[0], ym[1], ym[3], ym[4]
+        y1, pi1, z1, g1 = yp[0], yp[2], yp[3], yp[4]
+        eg, ep, ez = u
+        beta = 1 / (1 + rA / 400)
+        return np.array([
+            y - (y1 - (1 / tau) * (R - pi1 - z1) + g - g1),
+            pi - (beta * pi1 + kappa * (y - g)),
+            R - (rho_R * R_1 + (1 - rho_R) * (psi1 * pi + psi2 * (y - g)) + s_ep * ep / 100),
+            g - (rho_g * g_1 + s_eg * eg / 100),
+            z - (rho_z * z_1 + s_ez * ez / 100),
+            YGR - (gammaQ + 100 * (y - y_1 + z)),
+            INFL - (piA + 400 * pi),
+            INT - (piA + rA + 4 * gammaQ + 400 * R),
+        ])
+
+
 def get_model(name: str) -> HandModel:
-    return {"fs2000": FS2000, "ls2003": LS2003}[name]()
+    return {"fs2000": FS2000, "ls2003": LS2003, "hs_nk": HSNK}[name]()

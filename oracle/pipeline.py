@@ -39,7 +39,8 @@ class DrawFailure(Exception):
 def set_estimated_parameters(model, theta):
     params = np.array(model.params0, dtype=float)
     sigma_e = np.array(model.sigma_e0, dtype=float)
-    sigma_m = np.zeros((model.ny, model.ny))
+    sm0 = getattr(model, "sigma_m0", None)                  # calibrated measurement errors (shocks block)
+    sigma_m = np.zeros((model.ny, model.ny)) if sm0 is None else np.array(sm0, dtype=float)
     for spec, v in zip(model.est, theta):
         kind = spec[0]
         if kind == "param":
@@ -308,7 +309,11 @@ def simulate_observations(model, theta, nobs, seed):
     a = V @ (np.sqrt(np.clip(w, 0, None)) * rng.standard_normal(ns))
     cQ = np.linalg.cholesky(ss["Q"])
     Y = np.zeros((model.ny, nobs))
+    H = ss["H"]
+    cH = np.linalg.cholesky(H + 1e-300 * np.eye(model.ny)) if np.any(H) else None
     for t in range(nobs):
         Y[:, t] = ss["Z"] @ a + d["ybar"][model.obs_idx]
+        if cH is not None:                                   # measurement errors (models that declare them)
+            Y[:, t] += cH @ rng.standard_normal(model.ny)
         a = ss["T"] @ a + ss["R"] @ (cQ @ rng.standard_normal(model.nx))
     return Y

@@ -23,6 +23,8 @@ REF = os.environ.get("DYNARE_REFERENCE", "/root/reference")
 MODELS = {
     "fs2000": "test/models/fs2000/fs2000.mod",
     "ls2003": "test/models/ls2003/ls2003.mod",
+    # Herbst-Schorfheide NK model with prior!() syntax, calibrated and estimated measurement errors, correlations
+    "hs_nk": "test/models/estimation/test1.mod",
 }
 
 

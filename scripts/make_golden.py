@@ -40,11 +40,20 @@ def make(name, Y, n_draws, seed):
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    fs = models.get_model("fs2000")
-    Yfs = pl.simulate_observations(fs, fs.theta_mode, 192, 20260101)
-    make("fs2000", Yfs, 256, 1)
-    Yls = np.load(os.path.join(GOLD, "ls2003_data.npy"))
-    make("ls2003", Yls, 256, 1)
+    only = sys.argv[1:]
+    if not only or "fs2000" in only:
+        fs = models.get_model("fs2000")
+        Yfs = pl.simulate_observations(fs, fs.theta_mode, 192, 20260101)
+        make("fs2000", Yfs, 256, 1)
+    if not only or "ls2003" in only:
+        Yls = np.load(os.path.join(GOLD, "ls2003_data.npy"))
+        make("ls2003", Yls, 256, 1)
+    if only and "hs_nk" not in only:
+        return
+    # hs_nk: the reference's data file (dsge1_data.csv) is not in the tree; 80 synthetic quarters at the
+    # estimated_params_init point, measurement errors included
+    nk = models.get_model("hs_nk")
+    make("hs_nk", pl.simulate_observations(nk, nk.theta_mode, 80, 20260102), 256, 1)
 
 
 if __name__ == "__main__":

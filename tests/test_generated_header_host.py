@@ -23,7 +23,7 @@ int jperm(int c) { return M::jperm(c); }
 """
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_generated_model_function_on_host(name, tmp_path):
     src = tmp_path / "shim.cpp"
     src.write_text(SHIM % dict(name=name))

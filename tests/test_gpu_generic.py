@@ -27,7 +27,7 @@ def _host_side(m, theta):
     return J, yb, Se, Sm, st
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_generic_path_matches_oracle(name, golden):
     from dynare_jl_b200.engine import GenericSSWs
     g = golden(name)

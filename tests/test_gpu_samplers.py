@@ -62,7 +62,7 @@ def test_logprior_and_transform_all_shapes(golden):
     ws.close()
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_logposterior_matches_oracle(name, golden):
     from dynare_jl_b200.engine import BatchSSWs, DSGELogPosteriorDensity
     g = golden(name)
@@ -86,7 +86,8 @@ def _oracle_loglik(name, Y):
     return f
 
 
-@pytest.mark.parametrize("name,npart,resampling", [("ls2003", 2048, "multinomial"), ("fs2000", 1500, "systematic")])
+@pytest.mark.parametrize("name,npart,resampling", [("ls2003", 2048, "multinomial"), ("fs2000", 1500, "systematic"),
+                                                   ("hs_nk", 1024, "multinomial")])
 def test_smc_stages_match_oracle(name, npart, resampling, golden):
     """Every tempering stage, replayed by the CPU oracle from the device state of the previous stage with the
     same random numbers: weights, ESS, resampling decision, moments, proposals, accept decisions, particles."""

@@ -8,7 +8,8 @@ import pytest
 from conftest import REFERENCE, ROOT
 from oracle import models
 
-MODS = {"fs2000": "test/models/fs2000/fs2000.mod", "ls2003": "test/models/ls2003/ls2003.mod"}
+MODS = {"fs2000": "test/models/fs2000/fs2000.mod", "ls2003": "test/models/ls2003/ls2003.mod",
+        "hs_nk": "test/models/estimation/test1.mod"}
 
 
 def _spec(name):
@@ -16,7 +17,7 @@ def _spec(name):
     return modelgen.spec_from_file(name, os.path.join(REFERENCE, MODS[name]))
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_committed_description_matches_oracle_bookkeeping(name):
     with open(os.path.join(ROOT, "dynare.jl_b200", "models", f"{name}.json")) as f:
         d = json.load(f)
@@ -39,7 +40,7 @@ def test_fs2000_structure():
     assert d["endo"][14:] == ["AUX_ENDO_LEAD_c_1", "AUX_ENDO_LEAD_P_1"]
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_symbolic_jacobian_matches_complex_step(name, have_reference):
     if not have_reference:
         pytest.skip("reference model files not available on this box")
@@ -58,7 +59,7 @@ def test_symbolic_jacobian_matches_complex_step(name, have_reference):
         assert np.abs(Jo - Jg).max() <= 1e-12 * max(1.0, np.abs(Jo).max())
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_generated_sources_are_current(name, have_reference):
     if not have_reference:
         pytest.skip("reference model files not available on this box")

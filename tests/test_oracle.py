@@ -6,7 +6,7 @@ import scipy.linalg as sla
 from oracle import models, pipeline as pl
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_quadratic_residual_and_stability(name):
     m = models.get_model(name)
     d = pl.solve_draw(m, m.theta_mode)
@@ -21,7 +21,7 @@ def test_quadratic_residual_and_stability(name):
     assert np.abs((A @ G + B) @ d["sol"]["g1_2"] + Fu).max() < 1e-12
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_qz_and_cyclic_reduction_agree(name):
     m = models.get_model(name)
     a = pl.solve_draw(m, m.theta_mode, "GS")["sol"]
@@ -43,7 +43,7 @@ def test_fs2000_eigenvalues_at_calibration():
     assert int(np.sum((eig >= pl.QZ_CRITERIUM))) - (m.n - m.nf) == m.nf
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_lyapunov_identity(name):
     """P0 = T P0 T' + R Q R'  (pattern of reference test/test_smc.jl:29-42)."""
     m = models.get_model(name)
@@ -127,7 +127,7 @@ def test_status_classification():
     assert st == pl.ST_UNSTABLE and ll == -np.inf
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_golden_matches_live_oracle(name, golden):
     g = golden(name)
     m = models.get_model(name)

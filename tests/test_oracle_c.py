@@ -5,15 +5,17 @@ import pytest
 from oracle import cbuild, models, pipeline as pl
 
 
-@pytest.mark.parametrize("name", ["fs2000", "ls2003"])
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_c_port_matches_golden(name, golden):
     g = golden(name)
     n, kk = g["g1"].shape[1], g["g1"].shape[2]
     ll, st, used, g1 = cbuild.loglik_batch(name, g["theta"], g["Y"], want_g1=True, dims=(n, kk))
     assert used >= 1
     assert np.array_equal(st, g["status"])
-    assert np.max(np.abs(ll - g["loglik"]) / np.abs(g["loglik"])) < 1e-8
-    assert np.abs(g1 - g["g1"]).max() < 1e-10          # CR (C port) vs QZ (numpy oracle)
+    ok = g["status"] == 0
+    assert np.all(np.isneginf(ll[~ok]))
+    assert np.max(np.abs(ll[ok] - g["loglik"][ok]) / np.abs(g["loglik"][ok])) < 1e-8
+    assert np.abs(g1[ok] - g["g1"][ok]).max() < 1e-10          # CR (C port) vs QZ (numpy oracle)
 
 
 def test_c_port_status_and_missing_data(golden):

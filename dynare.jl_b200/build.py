@@ -54,5 +54,31 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
     return LIB
 
 
+def build_model_library(name: str, mod_path: str, out_dir: str) -> str:
+    """Compile ONE user model into its own shared object (the run-time analogue of Dynare's `use_dll`):
+    .mod text -> device model function (modelgen) -> nvcc -> <out_dir>/libdynare_b200_model_<name>.so.
+    Loading it (engine.load_model_library) registers the model with libdynare_b200.so, after which
+    dyb_create("<name>", ...) works like for the shipped models.  Writes <out_dir>/<name>.json beside it."""
+    from . import modelgen
+    build_library()
+    os.makedirs(out_dir, exist_ok=True)
+    spec = modelgen.spec_from_file(name, mod_path)
+    cuh = os.path.join(out_dir, f"model_{name}.cuh")
+    cu = os.path.join(out_dir, f"model_{name}.cu")
+    with open(cuh, "w") as f:
+        f.write(modelgen.emit_cuda(spec).replace('#include "../model_traits.cuh"', '#include "model_traits.cuh"'))
+    with open(cu, "w") as f:
+        f.write(f"// GENERATED -- instantiates the solve and filter kernels for model '{name}'.\n"
+                f"#include \"model_{name}.cuh\"\n#define DYB_MODEL dyb::Model_{name}\n#include \"model_tu.cuh\"\n")
+    modelgen.write_json(spec, os.path.join(out_dir, f"{name}.json"))
+    lib = os.path.join(out_dir, f"libdynare_b200_model_{name}.so")
+    cmd = [NVCC, *FLAGS, "-I", CSRC, "-I", out_dir, "-shared", "-o", lib, cu, "-L", PKG, "-l:libdynare_b200.so",
+           "-Xlinker", f"-rpath={PKG}", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {cu}:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -558,7 +558,7 @@ assemble_kernel(const double* __restrict__ mid, long long n_draws, double lyap_t
     }
 #pragma unroll
     for (int i = 0; i < S * (K + NX); ++i) gst[i] = 0.0;
-    double rdiag[S];
+    double rdiag[S > 0 ? S : 1];
 #pragma unroll
     for (int q = 0; q < S; ++q) rdiag[q] = 0.0;
     // accumulate the right-hand sides from the non-static entries of the pivot rows

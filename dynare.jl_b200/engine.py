@@ -35,10 +35,29 @@ def available_models():
     return [lib.dyb_model_name(i).decode() for i in range(lib.dyb_model_count())]
 
 
+_MODEL_DIRS = [os.path.join(PACKAGE_DIR, "models")]
+_MODEL_LIBS = []
+
+
 def model_description(name: str) -> dict:
     """Plain-data description written by the model set-up (names, index sets, priors, defaults)."""
-    with open(os.path.join(PACKAGE_DIR, "models", f"{name}.json")) as f:
-        return json.load(f)
+    for d in _MODEL_DIRS:
+        p = os.path.join(d, f"{name}.json")
+        if os.path.exists(p):
+            with open(p) as f:
+                return json.load(f)
+    raise FileNotFoundError(f"no description for model {name!r}")
+
+
+def load_model_library(path: str):
+    """Load a model compiled by ``build.build_model_library``: its static initialiser registers the model with
+    libdynare_b200.so (which must be loaded first, with global symbols); the .json beside it becomes visible to
+    ``model_description``."""
+    L.load()
+    _MODEL_LIBS.append(C.CDLL(os.path.abspath(path), mode=C.RTLD_GLOBAL))
+    d = os.path.dirname(os.path.abspath(path))
+    if d not in _MODEL_DIRS:
+        _MODEL_DIRS.append(d)
 
 
 def _f64(a, shape=None):

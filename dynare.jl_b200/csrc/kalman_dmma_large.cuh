@@ -53,10 +53,20 @@ DYB_D void block_gemm_dmma(const double* Ag, int lda_g, const double* Bg, int ld
   const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   const int nw = nt >> 5, ntile = nsp / 8, npanel = nsp / DL_BK;
   constexpr int MAXR = 8;                 // staged doubles per thread and panel (>= (nsp*8 + 8*72) / threads)
+  const int bs_off = (int)(Bs0 - As0);    // the B panel follows the A panel inside a stage buffer
   for (int jt0 = 0; jt0 < ntile; jt0 += DL_NTP) {
     const int ntw = (ntile - jt0 < DL_NTP) ? ntile - jt0 : DL_NTP;
     const int ncolw = 8 * ntw, jbase = 8 * jt0;
     const int nA = nsp * DL_BK, nB = DL_BK * ncolw;
+    // tiles of strip s that this pass computes form a prefix 0 .. nact[s]-1 (SYMM: up to the block diagonal)
+    int nact[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int si = warp + s * nw;
+      int na = si < ntile ? ntw : 0;
+      if (SYMM && si < ntile) { const int lim = si - jt0 + 1; na = lim < na ? (lim > 0 ? lim : 0) : na; }
+      nact[s] = na;
+    }
     double c[2][DL_NTP][2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -64,53 +74,55 @@ DYB_D void block_gemm_dmma(const double* Ag, int lda_g, const double* Bg, int ld
 #pragma unroll
       for (int jt = 0; jt < DL_NTP; ++jt) {
         c[s][jt][0] = 0.0; c[s][jt][1] = 0.0;
-        if (Cinit && si < ntile && jt < ntw && (!SYMM || jt0 + jt <= si)) {
+        if (Cinit && jt < nact[s]) {
           const int i = 8 * si + gq, j = jbase + 8 * jt + 2 * tq;
           if (i < nv && j < nv) c[s][jt][0] = Cinit[i + (size_t)nv * j];
           if (i < nv && j + 1 < nv) c[s][jt][1] = Cinit[i + (size_t)nv * (j + 1)];
         }
       }
     }
+    // staging descriptors of this thread, fixed for the pass: global offset at panel 0 (-1: always zero), k index inside
+    // the panel, shared-memory offset, A or B
+    int gofs[MAXR], sofs[MAXR];
+    unsigned kks = 0, isb = 0;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+      const int e = tid + r * nt;
+      int go = -1, so = -1, kk = 0;
+      if (e < nA) {
+        const int i = e % nsp; kk = e / nsp;
+        so = i + lda * kk;
+        if (i < nv) go = i + lda_g * kk;
+      } else if (e < nA + nB) {
+        const int f = e - nA;
+        int n;
+        if (BT) { n = f % ncolw; kk = f / ncolw; } else { kk = f % DL_BK; n = f / DL_BK; }
+        so = bs_off + kk + DL_LDB * n;
+        isb |= 1u << r;
+        if (jbase + n < nv) go = BT ? (jbase + n) + ldb_g * kk : kk + ldb_g * (jbase + n);
+      }
+      gofs[r] = go; sofs[r] = so; kks |= (unsigned)kk << (4 * r);
+    }
+    const int stepA = lda_g * DL_BK, stepB = BT ? ldb_g * DL_BK : DL_BK;
     double stage[MAXR];
     auto fetch = [&](int p) {
       const int k0 = p * DL_BK;
 #pragma unroll
       for (int r = 0; r < MAXR; ++r) {
-        const int e = tid + r * nt;
         double v = 0.0;
-        if (e < nA) {
-          const int i = e % nsp, kk = e / nsp;
-          if (i < nv && k0 + kk < nv) v = Ag[i + (size_t)lda_g * (k0 + kk)];
-        } else if (e < nA + nB) {
-          const int f = e - nA;
-          if (BT) {
-            const int n = f % ncolw, kk = f / ncolw;
-            if (jbase + n < nv && k0 + kk < nv) v = Bg[(jbase + n) + (size_t)ldb_g * (k0 + kk)];
-          } else {
-            const int kk = f % DL_BK, n = f / DL_BK;
-            if (jbase + n < nv && k0 + kk < nv) v = Bg[(k0 + kk) + (size_t)ldb_g * (jbase + n)];
-          }
-        }
+        const int kk = (kks >> (4 * r)) & 15;
+        if (gofs[r] >= 0 && k0 + kk < nv)
+          v = ((isb >> r) & 1) ? Bg[(size_t)gofs[r] + (size_t)p * stepB] : Ag[(size_t)gofs[r] + (size_t)p * stepA];
         stage[r] = v;
       }
     };
     auto commit = [&](int buf) {
-      double* As = As0 + buf * panel_doubles;
-      double* Bs = Bs0 + buf * panel_doubles;
+      double* dst = As0 + buf * panel_doubles;
 #pragma unroll
-      for (int r = 0; r < MAXR; ++r) {
-        const int e = tid + r * nt;
-        if (e < nA) {
-          const int i = e % nsp, kk = e / nsp;
-          As[i + lda * kk] = stage[r];
-        } else if (e < nA + nB) {
-          const int f = e - nA;
-          int kk, n;
-          if (BT) { n = f % ncolw; kk = f / ncolw; } else { kk = f % DL_BK; n = f / DL_BK; }
-          Bs[kk + DL_LDB * n] = stage[r];
-        }
-      }
+      for (int r = 0; r < MAXR; ++r) if (sofs[r] >= 0) dst[sofs[r]] = stage[r];
     };
+    const bool full = (nact[0] == DL_NTP) && (nact[1] == DL_NTP || nact[1] == 0);
+    const bool two = nact[1] > 0;
     fetch(0);
     commit(0);
     __syncthreads();
@@ -118,17 +130,32 @@ DYB_D void block_gemm_dmma(const double* Ag, int lda_g, const double* Bg, int ld
       if (p + 1 < npanel) fetch(p + 1);
       const double* As = As0 + (p & 1) * panel_doubles;
       const double* Bs = Bs0 + (p & 1) * panel_doubles;
+      const double* Ap0 = As + (8 * warp + gq) + lda * tq;
+      const double* Ap1 = Ap0 + 8 * nw;
+      const double* Bp = Bs + tq + DL_LDB * gq;
+      if (full) {                                   // warp-uniform: no per-tile predicates in the common case
 #pragma unroll
-      for (int ks = 0; ks < DL_BK / 4; ++ks) {
+        for (int ks = 0; ks < DL_BK / 4; ++ks) {
+          const double a0 = Ap0[lda * 4 * ks];
+          const double a1 = two ? Ap1[lda * 4 * ks] : 0.0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int si = warp + s * nw;
-          if (si < ntile) {
-            const double av = As[(8 * si + gq) + lda * (4 * ks + tq)];
+          for (int jt = 0; jt < DL_NTP; ++jt) {
+            const double b = Bp[4 * ks + DL_LDB * 8 * jt];
+            dmma884(c[0][jt][0], c[0][jt][1], a0, b);
+            if (two) dmma884(c[1][jt][0], c[1][jt][1], a1, b);
+          }
+        }
+      } else {
 #pragma unroll
-            for (int jt = 0; jt < DL_NTP; ++jt)
-              if (jt < ntw && (!SYMM || jt0 + jt <= si))
-                dmma884(c[s][jt][0], c[s][jt][1], av, Bs[(4 * ks + tq) + DL_LDB * (8 * jt + gq)]);
+        for (int ks = 0; ks < DL_BK / 4; ++ks) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (nact[s] > 0) {
+              const double av = (s == 0 ? Ap0 : Ap1)[lda * 4 * ks];
+#pragma unroll
+              for (int jt = 0; jt < DL_NTP; ++jt)
+                if (jt < nact[s]) dmma884(c[s][jt][0], c[s][jt][1], av, Bp[4 * ks + DL_LDB * 8 * jt]);
+            }
           }
         }
       }
@@ -138,17 +165,16 @@ DYB_D void block_gemm_dmma(const double* Ag, int lda_g, const double* Bg, int ld
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const int si = warp + s * nw;
-      if (si >= ntile) continue;
 #pragma unroll
       for (int jt = 0; jt < DL_NTP; ++jt) {
-        if (jt >= ntw) continue;
+        if (jt >= nact[s]) continue;
         const int i = 8 * si + gq, j = jbase + 8 * jt + 2 * tq;
         if (!SYMM) {
           Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1];
         } else if (jt0 + jt < si) {
           Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1];
           Cg[j + (size_t)ldc * i] = c[s][jt][0]; Cg[(j + 1) + (size_t)ldc * i] = c[s][jt][1];
-        } else if (jt0 + jt == si) {
+        } else {
           if (i >= j) { Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[j + (size_t)ldc * i] = c[s][jt][0]; }
           if (i >= j + 1) { Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1]; Cg[(j + 1) + (size_t)ldc * i] = c[s][jt][1]; }
         }

@@ -8,6 +8,7 @@
 #include "kalman_dmma.cuh"
 #include "kalman_dmma_large.cuh"
 #include "solve_generic.cuh"
+#include "kalman_smoother.cuh"
 
 namespace dyb {
 
@@ -116,19 +117,95 @@ struct PriorPredArgs {
 };
 
 // Sigma_e of every draw: the shock part of set_estimated_parameters! (src/estimation/estimation.jl:517-601)
-struct SigmaEArgs { int np, nx; int est_type[MAX_EST], est_i[MAX_EST], est_j[MAX_EST]; };
-__global__ void sigma_e_kernel(SigmaEArgs a, const double* __restrict__ sigma_e0, const double* __restrict__ theta,
-                               long long n_draws, double* __restrict__ out) {
+struct SigmaEArgs { int np, nx, ny; int est_type[MAX_EST], est_i[MAX_EST], est_j[MAX_EST]; };
+// sigma_m0 / out_m may be null (only Sigma_e wanted)
+__global__ void sigma_e_kernel(SigmaEArgs a, const double* __restrict__ sigma_e0, const double* __restrict__ sigma_m0,
+                               const double* __restrict__ theta, long long n_draws, double* __restrict__ out,
+                               double* __restrict__ out_m) {
   const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n_draws) return;
   double* S = out + d * a.nx * a.nx;
+  double* Sm = out_m ? out_m + d * a.ny * a.ny : nullptr;
   for (int e = 0; e < a.nx * a.nx; ++e) S[e] = sigma_e0[e];
+  if (Sm) for (int e = 0; e < a.ny * a.ny; ++e) Sm[e] = sigma_m0[e];
   for (int q = 0; q < a.np; ++q) {
     const double v = theta[d * a.np + q];
-    const int i = a.est_i[q], j = a.est_j[q];
-    if (a.est_type[q] == EST_SD_SHOCK) S[i + a.nx * j] = v * v;
-    else if (a.est_type[q] == EST_VAR_SHOCK) S[i + a.nx * j] = v;
-    else if (a.est_type[q] == EST_CORR_SHOCK) { const double c = v * sqrt(S[i + a.nx * i] * S[j + a.nx * j]); S[i + a.nx * j] = c; S[j + a.nx * i] = c; }
+    const int i = a.est_i[q], j = a.est_j[q], ty = a.est_type[q];
+    if (ty == EST_SD_SHOCK) S[i + a.nx * j] = v * v;
+    else if (ty == EST_VAR_SHOCK) S[i + a.nx * j] = v;
+    else if (ty == EST_CORR_SHOCK) { const double c = v * sqrt(S[i + a.nx * i] * S[j + a.nx * j]); S[i + a.nx * j] = c; S[j + a.nx * i] = c; }
+    else if (Sm && ty == EST_SD_MEAS) Sm[i + a.ny * j] = v * v;
+    else if (Sm && ty == EST_VAR_MEAS) Sm[i + a.ny * j] = v;
+    else if (Sm && ty == EST_CORR_MEAS) { const double c = v * sqrt(Sm[i + a.ny * i] * Sm[j + a.ny * j]); Sm[i + a.ny * j] = c; Sm[j + a.ny * i] = c; }
+  }
+}
+
+// state space with EVERY endogenous variable as a state, as calibsmoother! builds it (src/filters/kalman/kalman.jl:78-125):
+// T[:, i_bkwrd_b] = g1_1, R = g1_2, P0 = endogenous_variance.  One CTA per draw.
+struct FullStateArgs {
+  int n, k, nx, ny;
+  int bk[64], obs[64];
+  const double* g1; const double* sigma_e; const double* ybar; const int* status_in; long long n_draws;
+  double lyap_tol; int lyap_maxit;
+  double* T; double* R; double* P0; double* ybar_obs; int* status;
+};
+__global__ void __launch_bounds__(128) full_state_space_kernel(FullStateArgs a) {
+  extern __shared__ double sm[];
+  const int n = a.n, k = a.k, nx = a.nx, tid = threadIdx.x, nt = blockDim.x;
+  double* Ak = sm; double* Sg = Ak + k * k; double* Tm = Sg + k * k; double* BQ = Tm + k * k; double* red = BQ + k * nx;
+  for (long long d = blockIdx.x; d < a.n_draws; d += gridDim.x) {
+    __syncthreads();
+    int status = a.status_in[d];
+    const double* g1 = a.g1 + (size_t)d * n * (k + nx);
+    const double* g2 = g1 + (size_t)n * k;
+    const double* Se = a.sigma_e + (size_t)d * nx * nx;
+    if (status == ST_OK) {
+      for (int e = tid; e < k * k; e += nt) Ak[e] = g1[a.bk[e % k] + n * (e / k)];
+      for (int e = tid; e < k * nx; e += nt) {
+        const int i = e % k, q = e / k;
+        double s = 0.0;
+        for (int f = 0; f < nx; ++f) s = fma(g2[a.bk[i] + n * f], Se[f + nx * q], s);
+        BQ[e] = s;
+      }
+      __syncthreads();
+      for (int e = tid; e < k * k; e += nt) {
+        const int i = e % k, j = e / k;
+        double s = 0.0;
+        for (int q = 0; q < nx; ++q) s = fma(BQ[i + k * q], g2[a.bk[j] + n * q], s);
+        Sg[e] = s;
+      }
+      __syncthreads();
+      int it = 0;
+      if (!blk_lyapunov(Ak, Sg, Tm, k, a.lyap_tol, a.lyap_maxit, red, &it)) status = ST_NONSTATIONARY;
+      __syncthreads();
+    }
+    if (status == ST_OK) {
+      double* To = a.T + (size_t)d * n * n;
+      double* Ro = a.R + (size_t)d * n * nx;
+      double* Po = a.P0 + (size_t)d * n * n;
+      for (int e = tid; e < n * n; e += nt) To[e] = 0.0;
+      __syncthreads();
+      for (int e = tid; e < n * k; e += nt) To[(e % n) + (size_t)n * a.bk[e / n]] = g1[e];
+      for (int e = tid; e < n * nx; e += nt) Ro[e] = g2[e];
+      for (int e = tid; e < n * n; e += nt) {
+        const int v = e % n, w = e / n;
+        if (v < w) continue;
+        double s = 0.0;
+        for (int i = 0; i < k; ++i) {
+          double rr = 0.0;
+          for (int j = 0; j < k; ++j) rr = fma(Sg[i + k * j], g1[w + n * j], rr);
+          s = fma(g1[v + n * i], rr, s);
+        }
+        for (int q = 0; q < nx; ++q) {
+          double rr = 0.0;
+          for (int f = 0; f < nx; ++f) rr = fma(Se[q + nx * f], g2[w + n * f], rr);
+          s = fma(g2[v + n * q], rr, s);
+        }
+        Po[v + (size_t)n * w] = s; Po[w + (size_t)n * v] = s;
+      }
+      for (int i = tid; i < a.ny; i += nt) a.ybar_obs[(size_t)d * a.ny + i] = a.ybar[(size_t)d * n + a.obs[i]];
+    }
+    if (tid == 0) a.status[d] = status;
   }
 }
 
@@ -453,9 +530,9 @@ int dyb_prior_predictive_batch(dyb_handle* h, const double* theta, int64_t n, in
   double* dirf = (irfs && periods > 0) ? sg.out(irfs, (size_t)d.n * periods * d.nx * N) : nullptr;
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   SigmaEArgs sa{};
-  sa.np = h->hs.np; sa.nx = d.nx;
+  sa.np = h->hs.np; sa.nx = d.nx; sa.ny = d.ny;
   for (int q = 0; q < h->hs.np; ++q) { sa.est_type[q] = h->hs.est_type[q]; sa.est_i[q] = h->hs.est_i[q]; sa.est_j[q] = h->hs.est_j[q]; }
-  sigma_e_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(sa, dse0, dth, n, dse);
+  sigma_e_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(sa, dse0, nullptr, dth, n, dse, nullptr);
   PriorPredArgs pa{};
   pa.n = d.n; pa.k = d.k; pa.nx = d.nx; pa.periods = periods;
   h->ops->bkwrd_indices(pa.bk);
@@ -467,6 +544,112 @@ int dyb_prior_predictive_batch(dyb_handle* h, const double* theta, int64_t n, in
   prior_predictive_kernel<<<(unsigned)grid, 128, smem, h->stream>>>(pa);
   DYB_CUDA(cudaGetLastError());
   h->launches += 2;
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+static int launch_smoother(KalmanSmootherArgs g, int device, cudaStream_t st, Stager& sg) {
+  int dev_sms = 148, max_smem = 0;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const size_t smem = sizeof(double) * smoother_smem_doubles(g.ns, g.ny, g.nx);
+  if (smem + 1024 > (size_t)max_smem) return fail(DYB_ERR_UNSUPPORTED, "state space too large for the shared-memory smoother");
+  long long grid = g.n_draws < (long long)dev_sms * 4 ? g.n_draws : (long long)dev_sms * 4;
+  g.work = sg.temp<double>(smoother_work_doubles(g.ns, g.ny, g.nobs) * (size_t)grid);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  if (smem > 48 * 1024) DYB_CUDA(cudaFuncSetAttribute(kalman_smoother_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kalman_smoother_kernel<<<(unsigned)grid, 256, smem, st>>>(g);
+  DYB_CUDA(cudaGetLastError());
+  return DYB_OK;
+}
+
+int dyb_kalman_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, int32_t nobs, const int32_t* z_idx,
+                              const double* Y, const double* T, const double* R, const double* Q, const double* P0,
+                              const double* a0, const double* H, int64_t n, double* alphah, double* etah, double* epsilonh,
+                              double* att, double* a_pred, double* loglik, int32_t* status) {
+  if (ns <= 0 || ny <= 0 || ny > 64 || ny > ns || nx <= 0 || nobs <= 0 || n < 0) return fail(DYB_ERR_ARG, "bad sizes");
+  if (n == 0) return DYB_OK;
+  if (!z_idx || !Y || !T || !R || !Q || !P0 || !status) return fail(DYB_ERR_ARG, "null argument");
+  DYB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = device_stream(device);
+  Stager sg(st);
+  const size_t N = (size_t)n, ns2 = (size_t)ns * ns;
+  KalmanSmootherArgs g{};
+  g.ns = ns; g.ny = ny; g.nx = nx; g.nobs = nobs;
+  g.z_idx = sg.in(z_idx, (size_t)ny);
+  g.Y = sg.in(Y, (size_t)ny * nobs);
+  g.T = sg.in(T, ns2 * N); g.R = sg.in(R, (size_t)ns * nx * N); g.Q = sg.in(Q, (size_t)nx * nx * N); g.P0 = sg.in(P0, ns2 * N);
+  g.a0 = sg.in(a0, (size_t)ns * N); g.H = sg.in(H, (size_t)ny * ny * N);
+  g.n_draws = n;
+  g.alphah = sg.out(alphah, (size_t)ns * nobs * N); g.etah = sg.out(etah, (size_t)nx * nobs * N);
+  g.epsilonh = sg.out(epsilonh, (size_t)ny * nobs * N); g.att = sg.out(att, (size_t)ns * nobs * N);
+  g.a_pred = sg.out(a_pred, (size_t)ns * (nobs + 1) * N);
+  g.loglik = sg.out(loglik, N); g.status = sg.out(status, N);
+  if (!is_device_ptr(z_idx)) for (int i = 0; i < ny; ++i) if (z_idx[i] < 0 || z_idx[i] >= ns) return fail(DYB_ERR_ARG, "z_idx out of range");
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  int rc = launch_smoother(g, device, st, sg);
+  if (rc) return rc;
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int dyb_smoother_batch(dyb_handle* h, const double* theta, int64_t n, double* alphah, double* etah, double* epsilonh,
+                       double* loglik, int32_t* status) {
+  if (h && !h->ops) return fail(DYB_ERR_UNSUPPORTED, "needs a handle with a device model function");
+  if (!h || n < 0 || (n > 0 && (!theta || !status))) return fail(DYB_ERR_ARG, "bad argument");
+  if (h->d_Y.p == nullptr) return fail(DYB_ERR_STATE, "dyb_set_observations has not been called");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  const dyb_model_dims& d = h->dims;
+  if (d.k > 64) return fail(DYB_ERR_UNSUPPORTED, "more than 64 state variables");
+  const size_t N = (size_t)n, n2 = (size_t)d.n * d.n;
+  Stager sg(h->stream);
+  double* dg1 = sg.temp<double>((size_t)d.n * (d.k + d.nx) * N);
+  double* dyb_ = sg.temp<double>((size_t)d.n * N);
+  double* dse = sg.temp<double>((size_t)d.nx * d.nx * N);
+  double* dsm = sg.temp<double>((size_t)d.ny * d.ny * N);
+  double* dse0 = sg.temp<double>((size_t)d.nx * d.nx);
+  double* dsm0 = sg.temp<double>((size_t)d.ny * d.ny);
+  int* dst1 = sg.temp<int>(N);
+  int* dst2 = sg.temp<int>(N);
+  double* dT = sg.temp<double>(n2 * N); double* dR = sg.temp<double>((size_t)d.n * d.nx * N); double* dP = sg.temp<double>(n2 * N);
+  double* dyo = sg.temp<double>((size_t)d.ny * N);
+  int* dz = sg.temp<int>((size_t)d.ny);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  DYB_CUDA(cudaMemcpyAsync(dse0, h->hs.sigma_e.data(), sizeof(double) * d.nx * d.nx, cudaMemcpyHostToDevice, h->stream));
+  DYB_CUDA(cudaMemcpyAsync(dsm0, h->hs.sigma_m.data(), sizeof(double) * d.ny * d.ny, cudaMemcpyHostToDevice, h->stream));
+  int rc = dyb_first_order_batch(h, theta, n, dg1, dyb_, nullptr, nullptr, reinterpret_cast<int32_t*>(dst1));
+  if (rc) return rc;
+  const double* dth = sg.in(theta, (size_t)h->hs.np * N);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  SigmaEArgs sa{};
+  sa.np = h->hs.np; sa.nx = d.nx; sa.ny = d.ny;
+  for (int q = 0; q < h->hs.np; ++q) { sa.est_type[q] = h->hs.est_type[q]; sa.est_i[q] = h->hs.est_i[q]; sa.est_j[q] = h->hs.est_j[q]; }
+  sigma_e_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(sa, dse0, dsm0, dth, n, dse, dsm);
+  FullStateArgs fa{};
+  fa.n = d.n; fa.k = d.k; fa.nx = d.nx; fa.ny = d.ny;
+  h->ops->bkwrd_indices(fa.bk);
+  h->ops->obs_indices(fa.obs);
+  fa.g1 = dg1; fa.sigma_e = dse; fa.ybar = dyb_; fa.status_in = dst1; fa.n_draws = n;
+  fa.lyap_tol = h->hs.opt.lyap_tol; fa.lyap_maxit = h->hs.opt.lyap_maxit;
+  fa.T = dT; fa.R = dR; fa.P0 = dP; fa.ybar_obs = dyo; fa.status = dst2;
+  const size_t smem_fs = sizeof(double) * (3 * (size_t)d.k * d.k + (size_t)d.k * d.nx + 8);
+  long long grid = n < 148LL * 16 ? n : 148LL * 16;
+  full_state_space_kernel<<<(unsigned)grid, 128, smem_fs, h->stream>>>(fa);
+  DYB_CUDA(cudaGetLastError());
+  DYB_CUDA(cudaMemcpyAsync(dz, fa.obs, sizeof(int) * d.ny, cudaMemcpyHostToDevice, h->stream));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));                 // fa.obs lives on this stack frame
+  KalmanSmootherArgs g{};
+  g.ns = d.n; g.ny = d.ny; g.nx = d.nx; g.nobs = h->nobs;
+  g.z_idx = dz; g.Y = h->d_Y.as<double>(); g.T = dT; g.R = dR; g.Q = dse; g.P0 = dP; g.a0 = nullptr; g.H = dsm;
+  g.ybar_obs = dyo; g.level = dyb_; g.status_in = dst2; g.n_draws = n;
+  g.alphah = sg.out(alphah, (size_t)d.n * h->nobs * N); g.etah = sg.out(etah, (size_t)d.nx * h->nobs * N);
+  g.epsilonh = sg.out(epsilonh, (size_t)d.ny * h->nobs * N);
+  g.loglik = sg.out(loglik, N); g.status = sg.out(status, N);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  rc = launch_smoother(g, h->device, h->stream, sg);
+  if (rc) return rc;
+  h->launches += 3;
   DYB_CUDA(sg.finish());
   return DYB_OK;
 }

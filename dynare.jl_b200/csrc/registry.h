@@ -40,6 +40,7 @@ struct ModelOps {
   cudaError_t (*unpack)(const double* d_ss, long long n, double* T, double* RQR, double* P0,
                         double* ybar_obs, double* H, cudaStream_t);
   void (*bkwrd_indices)(int* i_bkwrd_b /* dims.k */);   // variables with a lag, 0-based (Model.i_bkwrd_b)
+  void (*obs_indices)(int* obs_idx /* dims.ny */);      // observed variable of each row of Y, 0-based
 };
 
 const std::vector<const ModelOps*>& registry();

@@ -264,6 +264,17 @@ class BatchSSWs:
         L.check(self.lib.dyb_prior_predictive_batch(self._h, L.ptr(Theta), n, periods, L.ptr(yb), L.ptr(sd), L.ptr(irf), L.ptr(st)))
         return dict(steady_state=yb, stdev=sd, irfs=irf, status=st)
 
+    def smoother(self, Theta):
+        """calibsmoother! for N draws: dict(alphah (N, nobs, n) smoothed variables in levels, etah (N, nobs, nx),
+        epsilonh (N, nobs, ny), loglik, status)."""
+        Theta = self._theta(Theta)
+        n = Theta.shape[0]
+        d = self.dims
+        al = np.full((n, self.nobs, d["n"]), np.nan); et = np.full((n, self.nobs, d["nx"]), np.nan)
+        ep = np.full((n, self.nobs, d["ny"]), np.nan); ll = np.empty(n); st = np.empty(n, dtype=np.int32)
+        L.check(self.lib.dyb_smoother_batch(self._h, L.ptr(Theta), n, L.ptr(al), L.ptr(et), L.ptr(ep), L.ptr(ll), L.ptr(st)))
+        return dict(alphah=al, etah=et, epsilonh=ep, loglik=ll, status=st)
+
     def state_space(self, Theta):
         """Returns dict(T, RQR, P0 (N,ns,ns), ybar_obs (N,ny), H (N,ny,ny), status)."""
         Theta = self._theta(Theta)
@@ -433,6 +444,29 @@ def rng_fill(seed, first, n, step, stream=0, kind=0, count=1, device=0):
     out = np.empty((n, count))
     L.check(L.load().dyb_rng_fill(device, seed, first, n, step, stream, kind, count, L.ptr(out)))
     return out
+
+
+def kalman_smoother_batch(Y, z_idx, T, R, Q, P0, a0=None, H=None, device=0):
+    """Dense batched smoother: T, P0 (N, ns, ns), R (N, ns, nx), Q (N, nx, nx) numpy row-major per draw.
+    Returns dict(alphah (N, nobs, ns), etah (N, nobs, nx), epsilonh (N, nobs, ny), att, a_pred, loglik, status)."""
+    lib = L.load()
+    T = np.asarray(T, dtype=np.float64)
+    n, ns, _ = T.shape
+    Y = np.asarray(Y, dtype=np.float64)
+    ny, nobs = Y.shape
+    nx = np.asarray(R).shape[2]
+    cm = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).transpose(0, 2, 1))
+    Tc, Rc, Qc, Pc = cm(T), cm(R), cm(Q), cm(P0)
+    Hc = None if H is None else cm(H)
+    a0c = None if a0 is None else _f64(a0, (n, ns))
+    z = np.ascontiguousarray(z_idx, dtype=np.int32)
+    Yf = np.asfortranarray(Y)
+    al = np.empty((n, nobs, ns)); et = np.empty((n, nobs, nx)); ep = np.empty((n, nobs, ny)); at = np.empty((n, nobs, ns))
+    ap = np.empty((n, nobs + 1, ns)); ll = np.empty(n); st = np.empty(n, dtype=np.int32)
+    L.check(lib.dyb_kalman_smoother_batch(device, ns, ny, nx, nobs, L.ptr(z), L.ptr(Yf), L.ptr(Tc), L.ptr(Rc), L.ptr(Qc),
+                                          L.ptr(Pc), L.ptr(a0c), L.ptr(Hc), n, L.ptr(al), L.ptr(et), L.ptr(ep), L.ptr(at),
+                                          L.ptr(ap), L.ptr(ll), L.ptr(st)))
+    return dict(alphah=al, etah=et, epsilonh=ep, att=at, a_pred=ap, loglik=ll, status=st)
 
 
 def smc_reweight(w, loglh, dphi, device=0):

@@ -164,6 +164,23 @@ int dyb_state_space_batch(dyb_handle* h, const double* theta, int64_t n_draws,
 int dyb_prior_predictive_batch(dyb_handle* h, const double* theta, int64_t n_draws, int32_t periods,
                                double* ybar, double* stdev, double* irfs, int32_t* status);
 
+/* fixed-interval Kalman smoother for N dense state spaces at once (the `kalman_smoother!` call of calibsmoother!,
+ * src/filters/kalman/kalman.jl:126-150): smoothed states alphah ns x nobs, smoothed shocks etah nx x nobs, smoothed
+ * measurement errors epsilonh ny x nobs, updated states att ns x nobs, predicted states a_pred ns x (nobs+1) per draw
+ * (any may be NULL), log-likelihood and status.  R ns x nx and Q nx x nx per draw; z_idx / Y / H / a0 as in
+ * dyb_kalman_batch. */
+int dyb_kalman_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, int32_t nobs, const int32_t* z_idx,
+                              const double* Y, const double* T, const double* R, const double* Q, const double* P0,
+                              const double* a0, const double* H, int64_t n_draws, double* alphah, double* etah,
+                              double* epsilonh, double* att, double* a_pred, double* loglik, int32_t* status);
+/* calibsmoother! (src/filters/kalman/kalman.jl:52-264) for N parameter draws: every endogenous variable is a state
+ * (T[:, i_bkwrd_b] = g1_1, R = g1_2, P0 = endogenous_variance), observations detrended by the steady state; outputs in
+ * LEVELS (steady state added back, kalman.jl:240-243): alphah n x nobs, etah nx x nobs, epsilonh ny x nobs per draw.
+ * H is the measurement-error covariance of the draw (the reference's calibsmoother! uses H = 0, which is the same thing
+ * for models without measurement errors).  Stationary models only (status 5 otherwise). */
+int dyb_smoother_batch(dyb_handle* h, const double* theta, int64_t n_draws, double* alphah, double* etah,
+                       double* epsilonh, double* loglik, int32_t* status);
+
 /* generic batched Kalman log-likelihood for arbitrary (dense) state spaces -- the
  * kalman_likelihood(Y,Z,H,T,R,Q,a0,P,start,last,presample,ws) call (src/estimation/estimation.jl:687-700)
  * without a model: per draw T ns x ns, RQR ns x ns, P0 ns x ns, a0 ns (NULL = 0), H ny x ny (NULL = 0);

@@ -317,3 +317,79 @@ def simulate_observations(model, theta, nobs, seed):
             Y[:, t] += cH @ rng.standard_normal(model.ny)
         a = ss["T"] @ a + ss["R"] @ (cQ @ rng.standard_normal(model.nx))
     return Y
+
+
+# -----------------------------------------------------------------------------------------
+# Kalman smoother (reference `kalman_smoother!` call, src/filters/kalman/kalman.jl:52-160; KalmanFilterTools)
+# -----------------------------------------------------------------------------------------
+def kalman_smoother(Y, Z, H, T, R, Q, a0, P0):
+    """Fixed-interval state / disturbance smoother (Durbin & Koopman 2012, sections 4.3-4.5) with rows of missing
+    observations (NaN) dropped period by period.  Returns dict(a_pred (ns, nobs+1), att (ns, nobs), alphah (ns, nobs),
+    etah (nx, nobs), epsilonh (ny, nobs), loglik)."""
+    ny, nobs = Y.shape
+    ns = T.shape[0]
+    nx = R.shape[1]
+    a = np.array(a0, dtype=float); P = np.array(P0, dtype=float)
+    QQ = R @ Q @ R.T
+    A = np.zeros((ns, nobs + 1)); att = np.zeros((ns, nobs))
+    store = []
+    ll = 0.0
+    for t in range(nobs):
+        A[:, t] = a
+        obs = ~np.isnan(Y[:, t])
+        Zt = Z[obs]
+        if obs.any():
+            v = Y[obs, t] - Zt @ a
+            F = Zt @ P @ Zt.T + H[np.ix_(obs, obs)]
+            Fi = np.linalg.inv(F)
+            G = P @ Zt.T @ Fi
+            K = T @ G
+            ll += -0.5 * (obs.sum() * np.log(2 * np.pi) + np.linalg.slogdet(F)[1] + v @ Fi @ v)
+            att[:, t] = a + G @ v
+            L = T - K @ Zt
+            store.append((obs, Zt, Fi @ v, K, L, P.copy()))
+            a = T @ a + K @ v
+            P = T @ P @ L.T + QQ
+        else:
+            att[:, t] = a
+            store.append((obs, Zt, np.zeros(0), np.zeros((ns, 0)), T.copy(), P.copy()))
+            a = T @ a
+            P = T @ P @ T.T + QQ
+        P = 0.5 * (P + P.T)
+    A[:, nobs] = a
+    r = np.zeros(ns)
+    alphah = np.zeros((ns, nobs)); etah = np.zeros((nx, nobs)); eps = np.zeros((ny, nobs))
+    for t in range(nobs - 1, -1, -1):
+        obs, Zt, u, K, L, Pt = store[t]
+        etah[:, t] = Q @ R.T @ r
+        e = u - K.T @ r
+        full = np.zeros(ny); full[obs] = e
+        eps[:, t] = H @ full
+        r = Zt.T @ u + L.T @ r
+        alphah[:, t] = A[:, t] + Pt @ r
+    return dict(a_pred=A, att=att, alphah=alphah, etah=etah, epsilonh=eps, loglik=ll)
+
+
+def gaussian_smoother_bruteforce(Y, Z, H, T, R, Q, a0, P0):
+    """Independent second opinion for the smoothed states: E[alpha_t | all observations] from the explicit joint
+    Gaussian law of (alpha_0..alpha_{n-1}, y_0..y_{n-1}) (no missing observations)."""
+    ny, nobs = Y.shape
+    ns = T.shape[0]
+    QQ = R @ Q @ R.T
+    V = [np.array(P0, dtype=float)]
+    for t in range(1, nobs):
+        V.append(T @ V[-1] @ T.T + QQ)
+    Saa = np.zeros((nobs * ns, nobs * ns))
+    for s in range(nobs):
+        C = V[s].copy()
+        for t in range(s, nobs):
+            if t > s:
+                C = T @ C
+            Saa[t * ns:(t + 1) * ns, s * ns:(s + 1) * ns] = C
+            Saa[s * ns:(s + 1) * ns, t * ns:(t + 1) * ns] = C.T
+    Zb = np.kron(np.eye(nobs), Z)
+    Syy = Zb @ Saa @ Zb.T + np.kron(np.eye(nobs), H)
+    mean_a = np.concatenate([np.linalg.matrix_power(T, t) @ a0 for t in range(nobs)])
+    y = Y.T.reshape(-1) - Zb @ mean_a
+    ah = mean_a + Saa @ Zb.T @ np.linalg.solve(Syy, y)
+    return ah.reshape(nobs, ns).T

@@ -135,3 +135,31 @@ def test_golden_matches_live_oracle(name, golden):
         ll, st = pl.loglikelihood(m, g["theta"][i], g["Y"])
         assert st == g["status"][i]
         assert abs(ll - g["loglik"][i]) <= 1e-12 * abs(ll)
+
+
+def test_smoother_oracle_matches_bruteforce_conditional_expectation():
+    """The recursive smoother against E[alpha | Y] from the stacked joint Gaussian law; and structural identities
+    with missing observations (states consistent with smoothed shocks)."""
+    rng = np.random.default_rng(4)
+    ns, ny, nx, nobs = 5, 2, 3, 12
+    Qo, _ = np.linalg.qr(rng.standard_normal((ns, ns)))
+    T = Qo @ np.diag(rng.uniform(0.2, 0.9, ns)) @ Qo.T
+    R = rng.standard_normal((ns, nx)) * 0.3
+    Q = np.diag(rng.uniform(0.5, 1.5, nx))
+    H = 0.05 * np.eye(ny)
+    Z = np.zeros((ny, ns)); Z[0, 3] = 1; Z[1, 1] = 1
+    import scipy.linalg as sla
+    P0 = sla.solve_discrete_lyapunov(T, R @ Q @ R.T)
+    Y = rng.standard_normal((ny, nobs))
+    sm = pl.kalman_smoother(Y, Z, H, T, R, Q, np.zeros(ns), P0)
+    ref = pl.gaussian_smoother_bruteforce(Y, Z, H, T, R, Q, np.zeros(ns), P0)
+    assert np.abs(sm["alphah"] - ref).max() < 1e-10
+    assert abs(sm["loglik"] - pl.kalman_likelihood(Y, Z, H, T, R, Q, np.zeros(ns), P0)) < 1e-10
+    # smoothed states obey the transition equation with the smoothed shocks, also with missing data
+    Y[0, 4] = np.nan; Y[:, 7] = np.nan
+    sm = pl.kalman_smoother(Y, Z, H, T, R, Q, np.zeros(ns), P0)
+    for t in range(nobs - 1):
+        assert np.abs(sm["alphah"][:, t + 1] - (T @ sm["alphah"][:, t] + R @ sm["etah"][:, t])).max() < 1e-10
+    obs = ~np.isnan(Y)
+    fit = Z @ sm["alphah"] + sm["epsilonh"]
+    assert np.abs((fit - Y)[obs]).max() < 1e-10                  # y = Z alpha_hat + eps_hat where observed

@@ -41,7 +41,7 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
   prm.lyap_tol = hs.opt.lyap_tol; prm.lyap_maxit = hs.opt.lyap_maxit;
   const int block = 128;
   const long long grid = (n + block - 1) / block;
-  constexpr int G = 4;
+  constexpr int G = CrCfg<MT>::G;
   const bool coop = mt_coop_fits && hs.opt.solver != 1;
   if (coop) {
     model_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.mid, out.status, out.ybar);

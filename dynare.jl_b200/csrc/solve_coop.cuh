@@ -202,18 +202,26 @@ DYB_D bool qr_solve(double (&A)[(MM + G - 1) / G][MM], double (&B)[NR][MM], int 
 
 struct CrOptions { double cr_tol; int cr_maxit; };
 
+#ifndef DYB_CR_LANES
+#define DYB_CR_LANES 4
+#endif
+#ifndef DYB_CR_MIN_CTAS
+#define DYB_CR_MIN_CTAS 6
+#endif
+
 // Geometry of cr_kernel: G lanes per draw, CTAs of BLOCK threads, one shared-memory tile per draw holding
 // A1 (MM x MM) | acc_hat (MM x K) | A0 (MM x K) | A2 (MM x NF), column-major.  The tile stride is padded to
 // 4 (mod 16) doubles so that the "own column" accesses of a half-warp (4 draws x 4 lanes, column stride MM)
 // fall into 16 distinct 8-byte banks when MM is odd.
 template <class M>
 struct CrCfg {
-  static constexpr int G = 4, BLOCK = 64, GROUPS = BLOCK / G;
+  static constexpr int G = DYB_CR_LANES, BLOCK = 64, GROUPS = BLOCK / G;
   static constexpr int MM = M::M, K = M::K, NF = M::NF;
   static constexpr int OFF_A1 = 0, OFF_ACC = MM * MM, OFF_A0 = OFF_ACC + MM * K, OFF_A2 = OFF_A0 + MM * K;
   static constexpr int TILE_RAW = OFF_A2 + MM * NF;
-  static constexpr int TILE = TILE_RAW + ((4 - TILE_RAW % 16) + 16) % 16;
-  static constexpr int MIN_CTAS = 6;
+  static constexpr int PAD_TO = (G == 4) ? 4 : 8;       // tile stride mod 16 that spreads a half-warp over 16 banks
+  static constexpr int TILE = TILE_RAW + ((PAD_TO - TILE_RAW % 16) + 16) % 16;
+  static constexpr int MIN_CTAS = DYB_CR_MIN_CTAS;
 };
 
 // All 32 lanes of a warp (8 draws) run the SAME instruction stream: shuffles use the full mask (a partial mask costs

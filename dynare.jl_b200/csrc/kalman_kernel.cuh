@@ -31,6 +31,10 @@ DYB_D double fast_rsqrt(double x) {
   return y;
 }
 
+#ifndef DYB_KF_MIN_CTAS
+#define DYB_KF_MIN_CTAS 7
+#endif
+
 template <class M>
 struct KalmanCfg {
   // packed R Q R' goes to shared memory ([element][thread], conflict-free) to keep the register count low
@@ -42,7 +46,7 @@ struct KalmanCfg {
   static constexpr int BLOCK = P_SMEM ? 32 : 64;
   static constexpr bool QQ_SMEM = P_SMEM || (QQ_N * BLOCK * 8 <= 16 * 1024);
   static constexpr int SMEM_DOUBLES_PER_THREAD = (QQ_SMEM ? QQ_N : 0) + (P_SMEM ? QQ_N : 0);
-  static constexpr int MIN_CTAS = 7;
+  static constexpr int MIN_CTAS = DYB_KF_MIN_CTAS;
 };
 
 template <class M>

@@ -16,12 +16,18 @@ struct GenericHost {
   GenericModel gm{};           // sizes + device pointers into d_idx
   DevBuf d_idx;
   std::vector<int> obs_state;  // ny: Kalman state observed by each row of Y
-  size_t smem = 0;
+  size_t smem = 0;             // bytes of shared memory per draw
+  bool warp_groups = false;    // one warp per draw (small models) instead of one CTA per draw
+  DevBuf bT, bQ, bP, byo, bH, bst, bz;   // persistent work buffers of dyb_loglik_from_jacobian_batch
+  DevBuf bJ, byb, bse, bsm, bsi;         // persistent staging of its host inputs
 };
 
 void generic_release(dyb_handle* h) {
   if (h && h->generic) {
     h->generic->d_idx.release();
+    DevBuf* all[] = {&h->generic->bT, &h->generic->bQ, &h->generic->bP, &h->generic->byo, &h->generic->bH, &h->generic->bst,
+                     &h->generic->bz, &h->generic->bJ, &h->generic->byb, &h->generic->bse, &h->generic->bsm, &h->generic->bsi};
+    for (DevBuf* b : all) b->release();
     delete h->generic;
     h->generic = nullptr;
   }
@@ -39,7 +45,7 @@ static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaSt
     const KalmanDmmaGeom q = kalman_dmma_geom(g.ns, g.ny);
     const size_t smem = sizeof(double) * kalman_dmma_smem_doubles(g.ns, g.ny);
     const bool fits = q.nsp / 8 <= DMMA_MAX_TILES && smem + 1024 <= (size_t)max_smem;
-    if (fits && (g_kalman_variant == 2 || (g_kalman_variant == 0 && g.ns > 8))) {
+    if (fits && g_kalman_variant != 1) {
       long long grid = g.n_draws < (long long)dev_sms * 32 ? g.n_draws : (long long)dev_sms * 32;
       g.scratch = nullptr;
       const int ntile = q.nsp / 8;
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(128) full_state_space_kernel(FullStateArgs a) 
       }
       __syncthreads();
       int it = 0;
-      if (!blk_lyapunov(Ak, Sg, Tm, k, a.lyap_tol, a.lyap_maxit, red, &it)) status = ST_NONSTATIONARY;
+      if (!blk_lyapunov<128>(Ak, Sg, Tm, k, a.lyap_tol, a.lyap_maxit, red, &it)) status = ST_NONSTATIONARY;
       __syncthreads();
     }
     if (status == ST_OK) {
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(128) prior_predictive_kernel(PriorPredArgs a) 
       }
       __syncthreads();
       int it = 0;
-      if (!blk_lyapunov(Ak, Sg, Tm, k, a.lyap_tol, a.lyap_maxit, red, &it)) status = ST_NONSTATIONARY;
+      if (!blk_lyapunov<128>(Ak, Sg, Tm, k, a.lyap_tol, a.lyap_maxit, red, &it)) status = ST_NONSTATIONARY;
       __syncthreads();
       // diag of Sigma_y = g1_1 Sigma_s g1_1' + g1_2 Sigma_e g1_2'
       for (int v = tid; v < n; v += nt) {
@@ -407,10 +413,13 @@ int dyb_create_generic(const dyb_model_desc* md, int device, dyb_handle** out) {
                         base + o_sid, base + o_ov, base + o_lag};
   gh->obs_state = obs_state;
   gh->smem = smem;
-  if (smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(solve_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { dyb_destroy(h); return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
+  gh->warp_groups = smem <= 24 * 1024;
+  if (gh->warp_groups) {
+    if (4 * smem > 48 * 1024) e = cudaFuncSetAttribute(solve_generic_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * smem));
+  } else if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(solve_generic_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
+  if (e != cudaSuccess) { dyb_destroy(h); return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
   *out = h;
   return DYB_OK;
 }
@@ -418,9 +427,16 @@ int dyb_create_generic(const dyb_model_desc* md, int device, dyb_handle** out) {
 static int generic_solve(dyb_handle* h, GenericSolveArgs a) {
   GenericHost* gh = h->generic;
   a.cr_tol = h->hs.opt.cr_tol; a.cr_maxit = h->hs.opt.cr_maxit; a.lyap_tol = h->hs.opt.lyap_tol; a.lyap_maxit = h->hs.opt.lyap_maxit;
-  long long grid = a.n_draws;
-  if (grid > 148LL * 64) grid = 148LL * 64;
-  solve_generic_kernel<<<(unsigned)grid, 128, gh->smem, h->stream>>>(gh->gm, a);
+  const int per_draw = (int)(gh->smem / sizeof(double));
+  if (gh->warp_groups) {                 // small model: one warp per draw, four draws per CTA
+    long long grid = (a.n_draws + 3) / 4;
+    if (grid > 148LL * 64) grid = 148LL * 64;
+    solve_generic_kernel<32><<<(unsigned)grid, 128, 4 * gh->smem, h->stream>>>(gh->gm, a, per_draw);
+  } else {
+    long long grid = a.n_draws;
+    if (grid > 148LL * 64) grid = 148LL * 64;
+    solve_generic_kernel<128><<<(unsigned)grid, 128, gh->smem, h->stream>>>(gh->gm, a, per_draw);
+  }
   DYB_CUDA(cudaGetLastError());
   h->launches += 1;
   return DYB_OK;
@@ -467,17 +483,31 @@ int dyb_loglik_from_jacobian_batch(dyb_handle* h, const double* jac, const doubl
   const long long chunk = std::max<long long>(1, std::min<long long>(n, (long long)((1ULL << 30) / (sizeof(double) * (3 * ns2 + d.ny * (d.ny + 1))))));
   Stager sg(h->stream);
   const size_t N = (size_t)n;
-  const double* djac = sg.in(jac, (size_t)d.n * d.ncol * N);
-  const double* dyb_ = sg.in(ybar, (size_t)d.n * N);
-  const double* dse = sg.in(sigma_e, (size_t)d.nx * d.nx * (sigma_e_per_draw ? N : 1));
-  const double* dsm = sg.in(sigma_m, (size_t)d.ny * d.ny * (sigma_m_per_draw ? N : 1));
-  const int* dsi = sg.in(status_in, N);
+  // inputs: device pointers are used in place, host arrays go through persistent device buffers (pinned host memory from
+  // dyb_host_alloc is copied at full PCIe speed)
+  cudaError_t se_ = cudaSuccess;
+  auto stage = [&](DevBuf& b, const void* p, size_t bytes) -> const void* {
+    if (!p || is_device_ptr(p)) return p;
+    if (se_ == cudaSuccess) se_ = b.reserve(bytes);
+    if (se_ == cudaSuccess) se_ = cudaMemcpyAsync(b.p, p, bytes, cudaMemcpyHostToDevice, h->stream);
+    return b.p;
+  };
+  const double* djac = static_cast<const double*>(stage(gh->bJ, jac, sizeof(double) * d.n * d.ncol * N));
+  const double* dyb_ = static_cast<const double*>(stage(gh->byb, ybar, sizeof(double) * d.n * N));
+  const double* dse = static_cast<const double*>(stage(gh->bse, sigma_e, sizeof(double) * d.nx * d.nx * (sigma_e_per_draw ? N : 1)));
+  const double* dsm = static_cast<const double*>(stage(gh->bsm, sigma_m, sizeof(double) * d.ny * d.ny * (sigma_m_per_draw ? N : 1)));
+  const int* dsi = static_cast<const int*>(stage(gh->bsi, status_in, sizeof(int) * N));
+  if (se_ != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(se_));
   double* dll = sg.out(loglik, N);
   int* dst = sg.out(status, N);
-  double* dT = sg.temp<double>(ns2 * chunk); double* dQ = sg.temp<double>(ns2 * chunk); double* dP = sg.temp<double>(ns2 * chunk);
-  double* dyo = sg.temp<double>((size_t)d.ny * chunk); double* dH = sg.temp<double>((size_t)d.ny * d.ny * chunk);
-  int* dst1 = sg.temp<int>((size_t)chunk);
-  int* dz = sg.temp<int>((size_t)d.ny);
+  DYB_CUDA(gh->bT.reserve(sizeof(double) * ns2 * chunk)); DYB_CUDA(gh->bQ.reserve(sizeof(double) * ns2 * chunk));
+  DYB_CUDA(gh->bP.reserve(sizeof(double) * ns2 * chunk)); DYB_CUDA(gh->byo.reserve(sizeof(double) * d.ny * chunk));
+  DYB_CUDA(gh->bH.reserve(sizeof(double) * d.ny * d.ny * chunk)); DYB_CUDA(gh->bst.reserve(sizeof(int) * chunk));
+  DYB_CUDA(gh->bz.reserve(sizeof(int) * d.ny));
+  double* dT = gh->bT.as<double>(); double* dQ = gh->bQ.as<double>(); double* dP = gh->bP.as<double>();
+  double* dyo = gh->byo.as<double>(); double* dH = gh->bH.as<double>();
+  int* dst1 = gh->bst.as<int>();
+  int* dz = gh->bz.as<int>();
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   DYB_CUDA(cudaMemcpyAsync(dz, gh->obs_state.data(), sizeof(int) * d.ny, cudaMemcpyHostToDevice, h->stream));
   for (long long lo = 0; lo < n; lo += chunk) {

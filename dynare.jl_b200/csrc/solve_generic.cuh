@@ -40,9 +40,20 @@ struct GenericSolveArgs {
   int* status; int* cr_iters; int* lyap_iters;
 };
 
-// ---- CTA-cooperative dense helpers (column-major, all threads of the block must call) ---------------------
+// A draw is worked on by a GROUP of GSZ threads: one warp (GSZ = 32, several draws per CTA, __syncwarp between phases)
+// for small models, the whole CTA (GSZ = blockDim, __syncthreads) for large ones.
+template <int GSZ>
+struct Grp {
+  int tid, nt;
+  DYB_D Grp() : tid(GSZ == 32 ? (threadIdx.x & 31) : threadIdx.x), nt(GSZ == 32 ? 32 : blockDim.x) {}
+  DYB_D void sync() const { if (GSZ == 32) __syncwarp(); else __syncthreads(); }
+};
+
+// ---- group-cooperative dense helpers (column-major, all threads of the group must call) ---------------------
+template <int GSZ>
 DYB_D void blk_lu_factor(double* a, int n, int* piv, int* okflag) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const Grp<GSZ> gp;
+  const int tid = gp.tid, nt = gp.nt;
   for (int p = 0; p < n; ++p) {
     if (tid == 0) {
       int r = p;
@@ -51,26 +62,28 @@ DYB_D void blk_lu_factor(double* a, int n, int* piv, int* okflag) {
       piv[p] = r;
       if (!(best > 0.0) || !isfinite(best)) *okflag = 0;
     }
-    __syncthreads();
+    gp.sync();
     if (!*okflag) return;
     const int r = piv[p];
     if (r != p) for (int c = tid; c < n; c += nt) { const double t = a[p + n * c]; a[p + n * c] = a[r + n * c]; a[r + n * c] = t; }
-    __syncthreads();
+    gp.sync();
     const double inv = 1.0 / a[p + n * p];
     for (int i = p + 1 + tid; i < n; i += nt) a[i + n * p] *= inv;
-    __syncthreads();
+    gp.sync();
     const int w = n - p - 1;
     for (int e = tid; e < w * w; e += nt) {
       const int i = p + 1 + e % w, c = p + 1 + e / w;
       a[i + n * c] = fma(-a[i + n * p], a[p + n * c], a[i + n * c]);
     }
-    __syncthreads();
+    gp.sync();
   }
 }
 
 // solve L U x = P b for nrhs column-major right-hand sides in place: one thread per column
+template <int GSZ>
 DYB_D void blk_lu_solve(const double* lu, const int* piv, double* b, int n, int nrhs) {
-  for (int c = threadIdx.x; c < nrhs; c += blockDim.x) {
+  const Grp<GSZ> gp;
+  for (int c = gp.tid; c < nrhs; c += gp.nt) {
     double* x = b + n * c;
     for (int p = 0; p < n; ++p) { const int r = piv[p]; if (r != p) { const double t = x[p]; x[p] = x[r]; x[r] = t; } }
     for (int p = 0; p < n; ++p) { const double xp = x[p]; for (int i = p + 1; i < n; ++i) x[i] = fma(-lu[i + n * p], xp, x[i]); }
@@ -80,13 +93,15 @@ DYB_D void blk_lu_solve(const double* lu, const int* piv, double* b, int n, int 
       for (int i = 0; i < p; ++i) x[i] = fma(-lu[i + n * p], xp, x[i]);
     }
   }
-  __syncthreads();
+  gp.sync();
 }
 
 // doubling solve of X = A X A' + B (k x k): on entry Ak = A, Sg = B; on exit Sg = X (symmetrised).
 // red: >= 4 doubles of shared scratch.  Returns 1 on convergence (same stopping rule as solve_kernel.cuh).
+template <int GSZ>
 DYB_D int blk_lyapunov(double* Ak, double* Sg, double* Tm, int k, double tol, int maxit, double* red, int* iters) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const Grp<GSZ> gp;
+  const int tid = gp.tid, nt = gp.nt;
   int conv = 0, done = 0;
   for (int li = 0; li < maxit; ++li) {
     done = li + 1;
@@ -97,7 +112,7 @@ DYB_D int blk_lyapunov(double* Ak, double* Sg, double* Tm, int k, double tol, in
       Tm[e] = s;
     }
     if (tid == 0) { red[0] = 0.0; red[1] = 0.0; red[2] = 0.0; }
-    __syncthreads();
+    gp.sync();
     double dmax = 0.0, smax = 0.0;
     bool nan_seen = false;
     for (int e = tid; e < k * k; e += nt) {
@@ -112,20 +127,20 @@ DYB_D int blk_lyapunov(double* Ak, double* Sg, double* Tm, int k, double tol, in
     // non-negative doubles order like their bit patterns: atomicMax on the integer view
     atomicMax(reinterpret_cast<unsigned long long*>(&red[0]), (unsigned long long)__double_as_longlong(dmax));
     atomicMax(reinterpret_cast<unsigned long long*>(&red[1]), (unsigned long long)__double_as_longlong(nan_seen ? INFINITY : smax));
-    __syncthreads();
+    gp.sync();
     for (int e = tid; e < k * k; e += nt) {
       const int i = e % k, j = e / k;
       double s = 0.0;
       for (int q = 0; q < k; ++q) s = fma(Ak[i + k * q], Ak[q + k * j], s);
       Tm[e] = s;
     }
-    __syncthreads();
+    gp.sync();
     double amax = 0.0;
     for (int e = tid; e < k * k; e += nt) { const double v = Tm[e]; Ak[e] = v; amax = fmax(amax, isfinite(v) ? fabs(v) : INFINITY); }
     atomicMax(reinterpret_cast<unsigned long long*>(&red[2]), (unsigned long long)__double_as_longlong(amax));
-    __syncthreads();
+    gp.sync();
     const double D = red[0], S = red[1], A = red[2];
-    __syncthreads();
+    gp.sync();
     if (!isfinite(S)) break;
     if (D <= tol * S && A < 1.0) { conv = 1; break; }
     if (!isfinite(A)) break;
@@ -136,12 +151,12 @@ DYB_D int blk_lyapunov(double* Ak, double* Sg, double* Tm, int k, double tol, in
       const int i = e % k, j = e / k;
       if (i > j) Tm[e] = 0.5 * (Sg[i + k * j] + Sg[j + k * i]);
     }
-    __syncthreads();
+    gp.sync();
     for (int e = tid; e < k * k; e += nt) {
       const int i = e % k, j = e / k;
       if (i > j) { Sg[i + k * j] = Tm[e]; Sg[j + k * i] = Tm[e]; }
     }
-    __syncthreads();
+    gp.sync();
   }
   return conv;
 }
@@ -159,15 +174,20 @@ inline size_t generic_solve_smem_doubles(int n, int nx, int ny, int s, int k, in
   d += 2 * (size_t)ns * k + 2 * (size_t)ns * nx;                     // g1s, GS, g2s, RQ
   d += (size_t)nx * nx + (size_t)(ncol > 8 ? ncol : 8);              // Se, red
   d += (m + 1) / 2 + 1;                                              // piv (ints)
+  d += 8;                                                            // per-group scalars (flags, norms)
   return d;
 }
 
+template <int GSZ>
 __global__ void __launch_bounds__(128)
-solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
-  extern __shared__ double sm[];
+solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) {
+  extern __shared__ double sm_all[];
+  const Grp<GSZ> gp;
+  const int ngroups = GSZ == 32 ? (int)(blockDim.x >> 5) : 1, grp = GSZ == 32 ? (int)(threadIdx.x >> 5) : 0;
+  double* sm = sm_all + (size_t)grp * per_draw_doubles;
   const int n = gm.n, nx = gm.nx, ny = gm.ny, S = gm.s, K = gm.k, NF = gm.nf, MM = gm.m, NCOL = gm.ncol, NS = gm.ns;
   const int cC = S, cB = S + K, cA = S + K + MM, cU = S + K + MM + NF;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = gp.tid, nt = gp.nt;
   double* W = sm;
   double* A0 = W + (size_t)n * NCOL;
   double* A2 = A0 + MM * K;
@@ -191,11 +211,13 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
   double* Se = RQ + NS * nx;
   double* red = Se + nx * nx;
   int* piv = reinterpret_cast<int*>(red + (NCOL > 8 ? NCOL : 8));
-  __shared__ int okflag, st_sh, it_sh;
-  __shared__ double n0_sh, n2_sh;
+  double* scal = reinterpret_cast<double*>(piv) + (MM + 1) / 2 + 1;       // per-group scalars
+  int& okflag = *reinterpret_cast<int*>(scal);
+  double& n0_sh = scal[1];
+  double& n2_sh = scal[2];
 
-  for (long long d = blockIdx.x; d < a.n_draws; d += gridDim.x) {
-    __syncthreads();
+  for (long long d = (long long)blockIdx.x * ngroups + grp; d < a.n_draws; d += (long long)gridDim.x * ngroups) {
+    gp.sync();
     if (a.status_in && a.status_in[d] != ST_OK) {
       if (tid == 0) { a.status[d] = a.status_in[d]; if (a.cr_iters) a.cr_iters[d] = 0; if (a.lyap_iters) a.lyap_iters[d] = 0; }
       continue;
@@ -204,7 +226,7 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
     const double* J = a.jac + (size_t)d * n * NCOL;
     // ---- Jacobian into the working column order; NaN / Inf anywhere -> steady-state class failure -------------
     if (tid == 0) { okflag = 1; red[0] = 0.0; }
-    __syncthreads();
+    gp.sync();
     double chk = 0.0;
     for (int e = tid; e < n * NCOL; e += nt) {
       const double v = J[e];
@@ -213,7 +235,7 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
     }
     for (int e = tid; e < nx * nx; e += nt) { const double v = a.sigma_e[(size_t)d * a.stride_se + e]; Se[e] = v; chk = fma(v, 0.0, chk); }
     if (!(chk == 0.0)) okflag = 0;
-    __syncthreads();
+    gp.sync();
     if (!okflag) status = ST_STEADY;
 
     // ---- Householder QR on the static columns, applied to every other column ------------------------------
@@ -224,7 +246,7 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
         for (int i = j; i < n; ++i) nrm2 = fma(col[i], col[i], nrm2);
         red[0] = nrm2;
       }
-      __syncthreads();
+      gp.sync();
       const double nrm2 = red[0];
       const double nrm = sqrt(nrm2);
       if (!(nrm > 0.0) || !isfinite(nrm)) { status = ST_SOLVER; break; }      // uniform: every thread reads red[0]
@@ -239,9 +261,9 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
         x[j] = fma(-dot, vj, x[j]);
         for (int i = j + 1; i < n; ++i) x[i] = fma(-dot, col[i], x[i]);
       }
-      __syncthreads();
+      gp.sync();
       if (tid == 0) { col[j] = alpha; for (int i = j + 1; i < n; ++i) col[i] = 0.0; }
-      __syncthreads();
+      gp.sync();
     }
 
     // ---- cyclic reduction on the MM x MM dynamic block --------------------------------------------------------
@@ -251,7 +273,7 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
       for (int e = tid; e < MM * NF; e += nt) { const int r = e % MM, j = e / MM; A2[e] = W[S + r + n * (cA + j)]; }
       for (int e = tid; e < MM * MM; e += nt) { const int r = e % MM, c = e / MM; A1[e] = W[S + r + n * (cB + c)]; }
       if (tid == 0) { n0_sh = 0.0; n2_sh = 0.0; }
-      __syncthreads();
+      gp.sync();
       bool conv = false, stalled = false;
       double n0 = 0.0, n2 = 0.0;
       for (it = 1; it <= a.cr_maxit; ++it) {
@@ -259,11 +281,11 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
         for (int e = tid; e < MM * K; e += nt) X[e] = A0[e];
         for (int e = tid; e < MM * NF; e += nt) X[MM * K + e] = A2[e];
         if (tid == 0) okflag = 1;
-        __syncthreads();
-        blk_lu_factor(LU, MM, piv, &okflag);
-        __syncthreads();
+        gp.sync();
+        blk_lu_factor<GSZ>(LU, MM, piv, &okflag);
+        gp.sync();
         if (!okflag) { if (it == 1) status = ST_SOLVER; else stalled = true; break; }
-        blk_lu_solve(LU, piv, X, MM, K + NF);
+        blk_lu_solve<GSZ>(LU, piv, X, MM, K + NF);
         const double* X0 = X;
         const double* X2 = X + MM * K;
         // A1 forward columns -= A0 X2[bk,:] ; A1 backward columns -= A2 X0[fw,:] (also accumulated in acc_hat)
@@ -273,18 +295,18 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
           for (int i = 0; i < K; ++i) s = fma(A0[r + MM * i], X2[gm.bkwrd_in_dyn[i] + MM * j], s);
           LU[e] = s;                                     // LU is free after the solve: staging
         }
-        __syncthreads();
+        gp.sync();
         for (int e = tid; e < MM * NF; e += nt) { const int r = e % MM, j = e / MM; A1[r + MM * gm.fwrd_in_dyn[j]] -= LU[e]; }
-        __syncthreads();
+        gp.sync();
         for (int e = tid; e < MM * K; e += nt) {
           const int r = e % MM, j = e / MM;
           double s = 0.0;
           for (int i = 0; i < NF; ++i) s = fma(A2[r + MM * i], X0[gm.fwrd_in_dyn[i] + MM * j], s);
           LU[e] = s;
         }
-        __syncthreads();
+        gp.sync();
         for (int e = tid; e < MM * K; e += nt) { const int r = e % MM, j = e / MM; A1[r + MM * gm.bkwrd_in_dyn[j]] -= LU[e]; acc_hat[e] += LU[e]; }
-        __syncthreads();
+        gp.sync();
         // A0 <- -A0 X0[bk,:] ; A2 <- -A2 X2[fw,:]
         for (int e = tid; e < MM * K; e += nt) {
           const int r = e % MM, j = e / MM;
@@ -292,18 +314,18 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
           for (int i = 0; i < K; ++i) s = fma(A0[r + MM * i], X0[gm.bkwrd_in_dyn[i] + MM * j], s);
           LU[e] = -s;
         }
-        __syncthreads();
+        gp.sync();
         for (int e = tid; e < MM * K; e += nt) A0[e] = LU[e];
-        __syncthreads();
+        gp.sync();
         for (int e = tid; e < MM * NF; e += nt) {
           const int r = e % MM, j = e / MM;
           double s = 0.0;
           for (int i = 0; i < NF; ++i) s = fma(A2[r + MM * i], X2[gm.fwrd_in_dyn[i] + MM * j], s);
           LU[e] = -s;
         }
-        __syncthreads();
+        gp.sync();
         for (int e = tid; e < MM * NF; e += nt) A2[e] = LU[e];
-        __syncthreads();
+        gp.sync();
         // 1-norms (largest column sum), sequential per column so the value does not depend on the launch geometry
         for (int j = tid; j < K + NF; j += nt) {
           const double* c = j < K ? A0 + MM * j : A2 + MM * (j - K);
@@ -311,7 +333,7 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
           for (int r = 0; r < MM; ++r) cs += fabs(c[r]);
           red[j] = cs;
         }
-        __syncthreads();
+        gp.sync();
         if (tid == 0) {
           double m0 = 0.0, m2 = 0.0;
           for (int j = 0; j < K; ++j) m0 = fmax(m0, red[j]);
@@ -320,9 +342,9 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
           for (int j = 0; j < K + NF; ++j) bad = bad || !(red[j] <= 1e150);
           n0_sh = bad ? NAN : m0; n2_sh = m2;
         }
-        __syncthreads();
+        gp.sync();
         const double m0 = n0_sh, m2 = n2_sh;
-        __syncthreads();
+        gp.sync();
         if (!(m0 <= 1e150) || !(m2 <= 1e150)) { if (it == 1) status = ST_SOLVER; else stalled = true; break; }
         n0 = m0; n2 = m2;
         if (n0 < a.cr_tol && n2 < a.cr_tol) { conv = true; break; }
@@ -332,25 +354,25 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
         else status = (n0 >= a.cr_tol) ? ST_UNSTABLE : ST_INDETERMINATE;
       }
     }
-    __syncthreads();
+    gp.sync();
 
     if (status == ST_OK) {
       // ---- G (dynamic rows, backward columns) = -A1hat^-1 A0(0) ------------------------------------------------
       for (int e = tid; e < MM * MM; e += nt) { const int r = e % MM, c = e / MM; LU[e] = W[S + r + n * (cB + c)]; }
-      __syncthreads();
+      gp.sync();
       for (int e = tid; e < MM * K; e += nt) { const int r = e % MM, j = e / MM; LU[r + MM * gm.bkwrd_in_dyn[j]] -= acc_hat[e]; Gd[e] = -W[S + r + n * (cC + j)]; }
       if (tid == 0) okflag = 1;
-      __syncthreads();
-      blk_lu_factor(LU, MM, piv, &okflag);
-      __syncthreads();
+      gp.sync();
+      blk_lu_factor<GSZ>(LU, MM, piv, &okflag);
+      gp.sync();
       if (!okflag) status = ST_SOLVER;
-      else blk_lu_solve(LU, piv, Gd, MM, K);
+      else blk_lu_solve<GSZ>(LU, piv, Gd, MM, K);
     }
-    __syncthreads();
+    gp.sync();
     if (status == ST_OK) {
       // ---- g_u = -(A G + B)^-1 F_u on the dynamic block ---------------------------------------------------------
       for (int e = tid; e < MM * MM; e += nt) { const int r = e % MM, c = e / MM; LU[e] = W[S + r + n * (cB + c)]; }
-      __syncthreads();
+      gp.sync();
       for (int e = tid; e < MM * K; e += nt) {
         const int r = e % MM, j = e / MM;
         double s = 0.0;
@@ -359,13 +381,13 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
       }
       for (int e = tid; e < MM * nx; e += nt) { const int r = e % MM, q = e / MM; gud[e] = -W[S + r + n * (cU + q)]; }
       if (tid == 0) okflag = 1;
-      __syncthreads();
-      blk_lu_factor(LU, MM, piv, &okflag);
-      __syncthreads();
+      gp.sync();
+      blk_lu_factor<GSZ>(LU, MM, piv, &okflag);
+      gp.sync();
       if (!okflag) status = ST_SOLVER;
-      else blk_lu_solve(LU, piv, gud, MM, nx);
+      else blk_lu_solve<GSZ>(LU, piv, gud, MM, nx);
     }
-    __syncthreads();
+    gp.sync();
     if (status == ST_OK && S > 0) {
       // ---- static rows by back-substitution: R_s y_s + B_top y_d + A_top y_f(+1) + C_top y_b(-1) + Fu_top u = 0 ---
       for (int e = tid; e < NF * (K + nx); e += nt) {
@@ -378,7 +400,7 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
         GG[e] = s;
       }
       if (tid == 0) okflag = 1;
-      __syncthreads();
+      gp.sync();
       for (int c = tid; c < K + nx; c += nt) {
         const double* gcol = (c < K) ? (Gd + MM * c) : (gud + MM * (c - K));
         for (int q = 0; q < S; ++q) {
@@ -395,10 +417,10 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
           gst[q + S * c] = s / dg;
         }
       }
-      __syncthreads();
+      gp.sync();
       if (!okflag) status = ST_SOLVER;
     }
-    __syncthreads();
+    gp.sync();
     if (status == ST_OK && a.g1) {
       double* g1 = a.g1 + (size_t)d * n * (K + nx);
       for (int e = tid; e < n * (K + nx); e += nt) {
@@ -413,24 +435,24 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
     if (status == ST_OK) {
       for (int e = tid; e < K * K; e += nt) { const int i = e % K, j = e / K; Ak[e] = Gd[gm.bkwrd_in_dyn[i] + MM * j]; }
       for (int e = tid; e < K * nx; e += nt) { const int i = e % K, q = e / K; Bs[e] = gud[gm.bkwrd_in_dyn[i] + MM * q]; }
-      __syncthreads();
+      gp.sync();
       for (int e = tid; e < K * nx; e += nt) {
         const int i = e % K, q = e / K;
         double s = 0.0;
         for (int f = 0; f < nx; ++f) s = fma(Bs[i + K * f], Se[f + nx * q], s);
         BQ[e] = s;
       }
-      __syncthreads();
+      gp.sync();
       for (int e = tid; e < K * K; e += nt) {
         const int i = e % K, j = e / K;
         double s = 0.0;
         for (int q = 0; q < nx; ++q) s = fma(BQ[i + K * q], Bs[j + K * q], s);
         Sg[e] = s;
       }
-      __syncthreads();
-      if (!blk_lyapunov(Ak, Sg, Tm, K, a.lyap_tol, a.lyap_maxit, red, &lyap_it)) status = ST_NONSTATIONARY;
+      gp.sync();
+      if (!blk_lyapunov<GSZ>(Ak, Sg, Tm, K, a.lyap_tol, a.lyap_maxit, red, &lyap_it)) status = ST_NONSTATIONARY;
     }
-    __syncthreads();
+    gp.sync();
 
     // ---- dense state space (estimation.jl:640-658) -----------------------------------------------------------------
     if (status == ST_OK) {
@@ -441,7 +463,7 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
         const double val = gm.var_static[v] ? gst[pos + S * c] : ((c < K) ? Gd[pos + MM * c] : gud[pos + MM * (c - K)]);
         if (c < K) g1s[sI + NS * c] = val; else g2s[sI + NS * (c - K)] = val;
       }
-      __syncthreads();
+      gp.sync();
       for (int e = tid; e < NS * nx; e += nt) {
         const int sI = e % NS, q = e / NS;
         double s = 0.0;
@@ -454,12 +476,12 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
         for (int q = 0; q < K; ++q) s = fma(g1s[sI + NS * q], Sg[q + K * j], s);
         GS[e] = s;
       }
-      __syncthreads();
+      gp.sync();
       double* To = a.T ? a.T + (size_t)d * NS * NS : nullptr;
       double* Qo = a.RQR ? a.RQR + (size_t)d * NS * NS : nullptr;
       double* Po = a.P0 ? a.P0 + (size_t)d * NS * NS : nullptr;
       if (To) for (int e = tid; e < NS * NS; e += nt) To[e] = 0.0;
-      __syncthreads();
+      gp.sync();
       if (To) for (int e = tid; e < NS * K; e += nt) { const int sI = e % NS, j = e / NS; To[sI + NS * gm.lagged_state[j]] = g1s[e]; }
       for (int e = tid; e < NS * NS; e += nt) {
         const int sI = e % NS, t = e / NS;
@@ -480,7 +502,6 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a) {
       if (a.lyap_iters) a.lyap_iters[d] = lyap_it;
     }
   }
-  (void)st_sh; (void)it_sh;
 }
 
 // ---- stand-alone batched doubling Lyapunov: X = A X A' + B, one CTA per draw (compute_variance!'s solver) ---------
@@ -496,7 +517,7 @@ __global__ void __launch_bounds__(128) lyapunov_generic_kernel(LyapunovArgs a) {
     for (int e = tid; e < k * k; e += nt) { Ak[e] = a.A[(size_t)d * k * k + e]; Sg[e] = a.B[(size_t)d * k * k + e]; }
     __syncthreads();
     int it = 0;
-    const int conv = blk_lyapunov(Ak, Sg, Tm, k, a.tol, a.maxit, red, &it);
+    const int conv = blk_lyapunov<128>(Ak, Sg, Tm, k, a.tol, a.maxit, red, &it);
     for (int e = tid; e < k * k; e += nt) a.X[(size_t)d * k * k + e] = conv ? Sg[e] : NAN;
     if (tid == 0) { a.status[d] = conv ? ST_OK : ST_NONSTATIONARY; if (a.iters) a.iters[d] = it; }
   }

@@ -23,7 +23,7 @@ def _random_state_space(rng, n, ns, ny, nx):
 
 
 @pytest.mark.parametrize("ns,ny,nobs,n,variant", [
-    (6, 2, 50, 40, 0), (6, 2, 50, 40, 2), (40, 7, 60, 12, 1), (40, 7, 60, 12, 2), (24, 5, 30, 9, 2), (37, 9, 25, 7, 2),
+    (6, 2, 50, 40, 0), (6, 2, 50, 40, 1), (3, 1, 20, 11, 0), (40, 7, 60, 12, 1), (40, 7, 60, 12, 2), (24, 5, 30, 9, 2), (37, 9, 25, 7, 2),
     (64, 12, 20, 5, 2), (88, 20, 10, 3, 2), (110, 20, 12, 3, 0), (110, 20, 12, 3, 1), (97, 3, 9, 4, 0),
     (200, 20, 6, 2, 0), (200, 20, 6, 2, 1), (256, 7, 4, 2, 0)])
 def test_generic_kalman_matches_oracle(ns, ny, nobs, n, variant):

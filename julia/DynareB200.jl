@@ -160,4 +160,53 @@ function loglik_from_jacobian!(out, status, h::Ptr{Cvoid}, jac::Array{Float64,3}
     return out
 end
 
+"Handle for a model without a generated device function (index sets as `Model` holds them, 1-based here)."
+function create_generic(n, nx, i_static, i_bkwrd_b, i_fwrd_b, obs_idx; device = 0)
+    a = Int32.(i_static .- 1); b = Int32.(i_bkwrd_b .- 1); c = Int32.(i_fwrd_b .- 1); o = Int32.(obs_idx .- 1)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve a b c o begin
+        desc = Ref(ModelDesc(n, nx, length(o), length(a), length(b), length(c), pointer(a), pointer(b), pointer(c), pointer(o)))
+        check(ccall((:dyb_create_generic, LIB), Cint, (Ref{ModelDesc}, Cint, Ref{Ptr{Cvoid}}), desc, device, h))
+    end
+    return h[]
+end
+
+# ---- prior-predictive quantities and the smoother for a batch of draws ---------------------------------------------
+"run_simulations (priorprediction.jl:64-98) for all columns of Θ: steady state, stdev, IRFs (n × periods × nx × N)."
+function prior_predictive(ws::BatchSSWs, Θ::Matrix{Float64}, n, nx; periods = 40)
+    N = size(Θ, 2)
+    ybar = Matrix{Float64}(undef, n, N); sd = similar(ybar); irfs = Array{Float64,4}(undef, n, periods, nx, N)
+    st = Vector{Int32}(undef, N)
+    GC.@preserve Θ check(ccall((:dyb_prior_predictive_batch, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+        ws.handle, Θ, N, periods, ybar, sd, irfs, st))
+    return ybar, sd, irfs, st
+end
+"calibsmoother! (kalman.jl:52-264) for all columns of Θ: smoothed variables in levels (n × nobs × N), smoothed shocks."
+function smoother(ws::BatchSSWs, Θ::Matrix{Float64}, n, nx, ny, nobs)
+    N = size(Θ, 2)
+    alphah = Array{Float64,3}(undef, n, nobs, N); etah = Array{Float64,3}(undef, nx, nobs, N)
+    epsh = Array{Float64,3}(undef, ny, nobs, N); ll = Vector{Float64}(undef, N); st = Vector{Int32}(undef, N)
+    GC.@preserve Θ check(ccall((:dyb_smoother_batch, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+        ws.handle, Θ, N, alphah, etah, epsh, ll, st))
+    return alphah, etah, epsh, ll, st
+end
+"FiniteDiff.finite_difference_hessian(objective, x) (estimation.jl:873, 882) as ONE batched posterior evaluation."
+function finite_difference_hessian(ws::BatchSSWs, x::Vector{Float64})
+    n = length(x); h = max.(eps()^(1/4) .* abs.(x), eps()^(1/4))
+    pts = [copy(x)]
+    for i in 1:n, m in (2.0, 1.0, -1.0, -2.0); p = copy(x); p[i] += m * h[i]; push!(pts, p); end
+    for i in 1:n, j in i+1:n, (si, sj) in ((1, 1), (1, -1), (-1, 1), (-1, -1)); p = copy(x); p[i] += si * h[i]; p[j] += sj * h[j]; push!(pts, p); end
+    f = -logposterior!(Vector{Float64}(undef, length(pts)), reduce(hcat, pts), ws)
+    H = Matrix{Float64}(undef, n, n); k = 2
+    for i in 1:n
+        H[i, i] = (-f[k] + 16f[k+1] - 30f[1] + 16f[k+2] - f[k+3]) / (12h[i]^2); k += 4
+    end
+    for i in 1:n, j in i+1:n
+        H[i, j] = H[j, i] = (f[k] - f[k+1] - f[k+2] + f[k+3]) / (4h[i] * h[j]); k += 4
+    end
+    return H
+end
+
 end # module

@@ -35,7 +35,7 @@ DYB_HD int dmma_pad_ld(int n) {        // smallest ld >= n with ld mod 16 in {4,
 // lane i owns row i, pivots and multipliers travel by shuffles (no shared-memory round trips on the critical path).
 // In: F (column-major, lower part used), v.  Out: F <- L (lower incl. diagonal), w, and on every lane the sums
 // quad = w'w and ldet = sum_i log L_ii; returns false if a pivot is not positive.
-DYB_D bool chol8_warp(double* F, int ny, const double* v, double* w, double& quad, double& ldet) {
+DYB_D bool chol8_warp(double* F, int ny, const double* v, double* w, double* rdv, double& quad, double& ldet) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   double f[8];
@@ -75,6 +75,7 @@ DYB_D bool chol8_warp(double* F, int ny, const double* v, double* w, double& qua
   for (int o = 16; o > 0; o >>= 1) { q2 += __shfl_xor_sync(FULL, q2, o); lg += __shfl_xor_sync(FULL, lg, o); }
   if (lane < ny) {
     w[lane] = wi;
+    rdv[lane] = rd;
 #pragma unroll
     for (int j = 0; j < 8; ++j) if (j <= lane) F[lane + ny * j] = f[j];
   }
@@ -92,7 +93,7 @@ inline KalmanDmmaGeom kalman_dmma_geom(int ns, int ny) {
 }
 inline size_t kalman_dmma_smem_doubles(int ns, int ny) {
   const KalmanDmmaGeom q = kalman_dmma_geom(ns, ny);
-  return 3 * (size_t)q.ld * q.nsp + (size_t)q.ldu * q.nsp + (size_t)ny * ny + 2 * (size_t)q.nsp + 2 * (size_t)ny + 8;
+  return 3 * (size_t)q.ld * q.nsp + (size_t)q.ldu * q.nsp + (size_t)ny * ny + 2 * (size_t)q.nsp + 3 * (size_t)ny + 8;
 }
 
 // blockDim.x = 32 * nsp / 8 <= 32 * MAXT; MAXT bounds the accumulator tiles a warp holds (register budget)
@@ -113,6 +114,7 @@ kalman_dmma_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
   double* au = a + nsp;
   double* v = au + nsp;
   double* w = v + ny;
+  double* rdv = w + ny;                         // 1 / L_ii of the current period
   __shared__ int bad;
   __shared__ int zi[64];
   const int i0 = 8 * warp;
@@ -159,7 +161,7 @@ kalman_dmma_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
       __syncthreads();
       if (tid < 32 && ny <= 8) {              // small ny: register / shuffle Cholesky
         double quad, ldet;
-        const bool okc = chol8_warp(F, ny, v, w, quad, ldet);
+        const bool okc = chol8_warp(F, ny, v, w, rdv, quad, ldet);
         const int cnt = __popc(__ballot_sync(0xffffffffu, tid < ny && !isnan(yt[tid < ny ? tid : 0])));
         if (tid == 0) {
           if (!okc) bad = 1;
@@ -186,7 +188,9 @@ kalman_dmma_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
           for (int i = 0; i < ny; ++i) {
             double x = v[i];
             for (int p = 0; p < i; ++p) x -= F[i + ny * p] * w[p];
-            x /= F[i + ny * i];
+            const double ri = 1.0 / F[i + ny * i];
+            rdv[i] = ri;
+            x *= ri;
             w[i] = x;
             quad += x * x;
             ldet += log(F[i + ny * i]);
@@ -203,7 +207,7 @@ kalman_dmma_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
         for (int i = 0; i < ny; ++i) {
           double u = isnan(yt[i]) ? 0.0 : Ps[zi[i] + ld * s];
           for (int p = 0; p < i; ++p) u -= F[i + ny * p] * U[p + ldu * s];
-          u /= F[i + ny * i];
+          u *= rdv[i];
           U[i + ldu * s] = u;
           x += u * w[i];
         }

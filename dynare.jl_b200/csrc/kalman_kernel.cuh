@@ -20,17 +20,6 @@
 
 namespace dyb {
 
-// fast fp64 reciprocal square root: hardware seed (MUFU.RSQ64H, ~20 bits) + two Newton steps (<= 1 ulp for
-// normal inputs); callers guard non-positive / non-finite arguments separately
-DYB_D double fast_rsqrt(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double hx = 0.5 * x;
-  y = y * fma(-hx * y, y, 1.5);
-  y = y * fma(-hx * y, y, 1.5);
-  return y;
-}
-
 #ifndef DYB_KF_MIN_CTAS
 #define DYB_KF_MIN_CTAS 7
 #endif

@@ -33,4 +33,26 @@ DYB_HD constexpr int tri(int i, int j) {            // packed lower-triangular i
 }
 DYB_HD constexpr int sym(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
 
+#if defined(__CUDACC__)
+// fast fp64 reciprocal square root: hardware seed (MUFU.RSQ64H, ~20 bits) + two Newton steps (<= 1 ulp for
+// normal inputs); callers guard non-positive / non-finite arguments separately
+DYB_D double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+
+// fast fp64 reciprocal: hardware seed (MUFU.RCP64H) + two Newton steps; callers guard zero / non-finite arguments
+DYB_D double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = fma(y, fma(-x, y, 1.0), y);
+  y = fma(y, fma(-x, y, 1.0), y);
+  return y;
+}
+#endif
+
 }  // namespace dyb

@@ -154,11 +154,11 @@ DYB_D bool qr_solve(double (&A)[(MM + G - 1) / G][MM], double (&B)[NR][MM], int 
     for (int r = p + 1; r < MM; ++r) sg = fma(x[r], x[r], sg);
     const double s = fma(x[p], x[p], sg);
     ok = ok && (s > 0.0) && (s < 1e300);
-    const double rn = rsqrt(s);
+    const double rn = fast_rsqrt(s);
     const double nrm = s * rn;
     const double alpha = x[p] >= 0.0 ? -nrm : nrm;
     const double vp = x[p] - alpha;
-    const double beta = 1.0 / (-alpha * vp);
+    const double beta = fast_rcp(-alpha * vp);
     rinv[p] = x[p] >= 0.0 ? -rn : rn;
 #pragma unroll
     for (int sl = p / G; sl < SL; ++sl) {

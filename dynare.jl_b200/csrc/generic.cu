@@ -290,6 +290,37 @@ __global__ void __launch_bounds__(128) prior_predictive_kernel(PriorPredArgs a) 
   }
 }
 
+
+// unconditional forecast from a given initial point (forecast_!, src/forecast.jl:154-159 -> simul_first_order! with zero
+// shocks): Y[:, 0] = y0, Y[:, h] = ybar + g1_1 (Y[:, h-1] - ybar)[i_bkwrd_b].  One warp per draw.
+struct ForecastArgs {
+  int n, k, periods;
+  int bk[64];
+  const double* g1; long long g1_stride; const double* ybar; const double* y0; const int* status_in; long long n_draws;
+  double* Y;
+};
+__global__ void __launch_bounds__(128) forecast_kernel(ForecastArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (d >= a.n_draws) return;
+  const int n = a.n, k = a.k;
+  double* Y = a.Y + (size_t)d * n * (a.periods + 1);
+  const double* g1 = a.g1 + (size_t)d * a.g1_stride;
+  const double* yb = a.ybar + (size_t)d * n;
+  const bool ok = a.status_in[d] == ST_OK;
+  for (int v = lane; v < n; v += 32) Y[v] = ok ? a.y0[(size_t)d * n + v] : NAN;
+  __syncwarp();
+  for (int h = 1; h <= a.periods; ++h) {
+    const double* prev = Y + (size_t)n * (h - 1);
+    for (int v = lane; v < n; v += 32) {
+      double s = yb[v];
+      for (int j = 0; j < k; ++j) s = fma(g1[v + n * j], prev[a.bk[j]] - yb[a.bk[j]], s);
+      Y[v + (size_t)n * h] = ok ? s : NAN;
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace dyb
 
 using namespace dyb;
@@ -680,6 +711,34 @@ int dyb_smoother_batch(dyb_handle* h, const double* theta, int64_t n, double* al
   rc = launch_smoother(g, h->device, h->stream, sg);
   if (rc) return rc;
   h->launches += 3;
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int dyb_forecast_batch(dyb_handle* h, const double* theta, int64_t n, int32_t periods, const double* y0, double* Y, int32_t* status) {
+  if (h && !h->ops) return fail(DYB_ERR_UNSUPPORTED, "needs a handle with a device model function");
+  if (!h || n < 0 || periods < 0 || (n > 0 && (!theta || !y0 || !Y || !status))) return fail(DYB_ERR_ARG, "bad argument");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  const dyb_model_dims& d = h->dims;
+  if (d.k > 64) return fail(DYB_ERR_UNSUPPORTED, "more than 64 state variables");
+  const size_t N = (size_t)n;
+  Stager sg(h->stream);
+  double* dg1 = sg.temp<double>((size_t)d.n * (d.k + d.nx) * N);
+  double* dyb_ = sg.temp<double>((size_t)d.n * N);
+  int* dst = sg.out(status, N);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  int rc = dyb_first_order_batch(h, theta, n, dg1, dyb_, nullptr, nullptr, reinterpret_cast<int32_t*>(dst));
+  if (rc) return rc;
+  ForecastArgs fa{};
+  fa.n = d.n; fa.k = d.k; fa.periods = periods;
+  h->ops->bkwrd_indices(fa.bk);
+  fa.g1 = dg1; fa.g1_stride = (long long)d.n * (d.k + d.nx); fa.ybar = dyb_; fa.y0 = sg.in(y0, (size_t)d.n * N); fa.status_in = dst; fa.n_draws = n;
+  fa.Y = sg.out(Y, (size_t)d.n * (periods + 1) * N);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  forecast_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, h->stream>>>(fa);
+  DYB_CUDA(cudaGetLastError());
+  h->launches += 1;
   DYB_CUDA(sg.finish());
   return DYB_OK;
 }

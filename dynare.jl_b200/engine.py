@@ -275,6 +275,15 @@ class BatchSSWs:
         L.check(self.lib.dyb_smoother_batch(self._h, L.ptr(Theta), n, L.ptr(al), L.ptr(et), L.ptr(ep), L.ptr(ll), L.ptr(st)))
         return dict(alphah=al, etah=et, epsilonh=ep, loglik=ll, status=st)
 
+    def forecast(self, Theta, y0, periods):
+        """Unconditional forecast (forecast.jl:54-159) for N draws from the levels y0 (N, n): (N, periods+1, n), status."""
+        Theta = self._theta(Theta)
+        n = Theta.shape[0]
+        y0 = _f64(y0, (n, self.dims["n"]))
+        Y = np.empty((n, periods + 1, self.dims["n"])); st = np.empty(n, dtype=np.int32)
+        L.check(self.lib.dyb_forecast_batch(self._h, L.ptr(Theta), n, periods, L.ptr(y0), L.ptr(Y), L.ptr(st)))
+        return Y, st
+
     def state_space(self, Theta):
         """Returns dict(T, RQR, P0 (N,ns,ns), ybar_obs (N,ny), H (N,ny,ny), status)."""
         Theta = self._theta(Theta)

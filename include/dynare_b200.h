@@ -181,6 +181,11 @@ int dyb_kalman_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, in
 int dyb_smoother_batch(dyb_handle* h, const double* theta, int64_t n_draws, double* alphah, double* etah,
                        double* epsilonh, double* loglik, int32_t* status);
 
+/* unconditional forecast for N draws (forecasting_ -> forecast_!, src/forecast.jl:54-159): y0 n per draw in levels
+ * (last smoothed state in calibsmoother mode, histval otherwise), Y n x (periods+1) per draw, Y[:,0] = y0 */
+int dyb_forecast_batch(dyb_handle* h, const double* theta, int64_t n_draws, int32_t periods, const double* y0,
+                       double* Y, int32_t* status);
+
 /* generic batched Kalman log-likelihood for arbitrary (dense) state spaces -- the
  * kalman_likelihood(Y,Z,H,T,R,Q,a0,P,start,last,presample,ws) call (src/estimation/estimation.jl:687-700)
  * without a model: per draw T ns x ns, RQR ns x ns, P0 ns x ns, a0 ns (NULL = 0), H ny x ny (NULL = 0);

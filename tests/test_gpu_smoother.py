@@ -71,3 +71,30 @@ def test_model_smoother_matches_oracle(name, golden):
         checked += 1
     assert checked >= 5
     ws.close()
+
+
+@pytest.mark.parametrize("name", ["fs2000", "hs_nk"])
+def test_forecast_from_last_smoothed_state(name, golden):
+    """forecasting_ in calibsmoother mode (forecast.jl:54-115): y0 = last smoothed state, zero future shocks."""
+    from dynare_jl_b200.engine import BatchSSWs
+    g = golden(name)
+    m = models.get_model(name)
+    ws = BatchSSWs(name, g["Y"])
+    theta = g["theta"][:16]
+    sm = ws.smoother(theta)
+    y0 = np.where(np.isfinite(sm["alphah"][:, -1, :]), sm["alphah"][:, -1, :], 0.0)
+    Y, st = ws.forecast(theta, y0, 12)
+    assert np.array_equal(st != 0, sm["status"] != 0) or np.all((st != 0) <= (sm["status"] != 0))
+    checked = 0
+    for i in range(16):
+        if st[i] != 0:
+            assert np.all(np.isnan(Y[i]))
+            continue
+        d = pl.solve_draw(m, theta[i])
+        y = y0[i].copy()
+        for h in range(13):
+            assert np.allclose(Y[i, h], y, rtol=1e-10, atol=1e-12)
+            y = d["ybar"] + d["sol"]["g1_1"] @ (y - d["ybar"])[m.i_bkwrd_b]
+        checked += 1
+    assert checked >= 8
+    ws.close()

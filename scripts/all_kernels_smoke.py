@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small invocations of every kernel family in one process (a quick all-kernels check; also usable under
-compute-sanitizer where that tool is available: compute-sanitizer --tool memcheck python scripts/sanitize_smoke.py)."""
+compute-sanitizer where that tool is available: compute-sanitizer --tool memcheck python scripts/all_kernels_smoke.py)."""
 import os
 import sys
 

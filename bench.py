@@ -286,6 +286,7 @@ def run_ours(args):
     nb, solve_ms, filter_ms = ws.timers_read()
     serial_ms = (solve_ms + filter_ms) / max(nb, 1)
     n_ok = int((d_st == 0).sum().item())
+    status_hist = torch.bincount(d_st.to(torch.int64), minlength=7).tolist()     # failure classes of the last batch
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -393,7 +394,9 @@ def run_ours(args):
                              f"hand-off buffer > 126 MB L2)",
                        "parallelism": f"draws sharded over {world} GPU(s), no data-path collective",
                        "streams": "successive steps alternate between two handles / CUDA streams (two batches in flight)",
-                       "ok_draws_last_step": n_ok},
+                       "ok_draws_last_step": n_ok,
+                       "status_histogram_last_step": dict(zip(["ok", "steady_state", "indeterminate", "unstable", "solver",
+                                                               "nonstationary", "F_not_pd"], status_hist))},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": n * npar * 8,
                     "d2h_bytes_per_step": n * 12, "steps": e2e_steps,
                     "how": "BatchSSWs.loglikelihood_async (dyb_loglik_batch_async) with pinned host buffers, two handles "

@@ -1,8 +1,9 @@
-// Generic batched Kalman log-likelihood for dense state spaces of run-time size: one CTA per
-// draw, the covariance recursion in shared memory when it fits (ns <= ~96), otherwise in a
-// per-CTA global scratch that stays L2-resident.  Same recursion as kalman_kernel.cuh but with a
-// dense transition matrix (no lagged-column structure assumed), used by dyb_kalman_batch for the
-// model-free configurations.
+// Generic batched Kalman log-likelihood for dense state spaces of run-time size, SCALAR fp64 variant: one CTA per
+// draw, the covariance recursion in shared memory when it fits (ns <= ~96), otherwise in a per-CTA global scratch
+// that stays L2-resident.  Same recursion as kalman_kernel.cuh but with a dense transition matrix (no lagged-column
+// structure assumed).  The tensor-core kernels (kalman_dmma.cuh, kalman_dmma_large.cuh) are the production path up
+// to ns = 256; this one serves larger state spaces and is the A/B reference (dyb_set_kalman_variant(1)).  It also
+// defines KalmanGenericArgs, shared by the three dense filter kernels.
 //
 // Replaces `kalman_likelihood(Y,Z,H,T,R,Q,a0,P,start,last,presample,ws)` (reference call site
 // src/estimation/estimation.jl:687-700) for a selection matrix Z given by z_idx.

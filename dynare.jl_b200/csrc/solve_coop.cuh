@@ -4,12 +4,14 @@
 //   model_kernel<M>      one thread per draw: parameter scatter, steady state + residual check, Jacobian
 //                        and the structure-aware static elimination generated at model set-up
 //                        (M::static_elim).  Writes the non-zeros of the reduced system and of the pivot rows.
-//   cr_kernel<M,G>       G lanes per draw, matrices distributed by COLUMN over the lanes and held in
-//                        registers with compile-time indices only: cyclic reduction where the m x m solve
-//                        is a Householder QR (no pivoting => no dynamic register indexing) followed by a
-//                        backward elimination; columns are exchanged with warp shuffles.  A1 and the
-//                        accumulated correction live in a small per-group shared-memory tile.  Then
-//                        G = -A1hat^-1 A0 and g_u = -(A2 G + A1)^-1 F_u with the same solver.
+//   cr_kernel<M,G>       G lanes per draw, all draws of a warp in ONE instruction stream (full-mask shuffles, finished
+//                        draws frozen by predicated commits).  Between iterations the state of a draw (A1, A0, A2,
+//                        accumulated correction) lives in a shared tile; inside an iteration A1 and [X0 | X2] are
+//                        distributed by COLUMN over the lanes in registers with compile-time indices only: the
+//                        m x m solve is a Householder QR (no pivoting => no dynamic register indexing) followed by
+//                        a backward elimination, pivot columns travel by warp shuffles, A0 / A2 columns are
+//                        broadcast from the tile.  Then G = -A1hat^-1 A0 and g_u = -(A2 G + A1)^-1 F_u with the
+//                        same solver.
 //   assemble_kernel<M>   one thread per draw: static rows by sparse back-substitution, Lyapunov doubling,
 //                        state-space assembly into the hand-off buffer of the filter kernel.
 //

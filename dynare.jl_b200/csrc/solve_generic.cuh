@@ -1,11 +1,11 @@
 // Run-time-size first-order solve for models WITHOUT a generated device function: the host (Julia) evaluates
 // steady state and Jacobian per draw (src/steady_state/SteadyState.jl:183-252, src/model.jl:120-139,
 // src/perturbations.jl:616-635) and uploads the compressed Jacobians; this kernel does everything after that
-// for one draw per CTA with every matrix of the draw in shared memory:
+// with every matrix of the draw in shared memory, one warp per draw (small models) or one CTA per draw:
 //   static elimination (Householder) -> cyclic reduction + Blanchard-Kahn status -> g_u -> static rows
-//   -> doubling Lyapunov -> dense state space (T, R Q R', P0, ybar[varobs], H) for kalman_generic_kernel.
+//   -> doubling Lyapunov -> dense state space (T, R Q R', P0, ybar[varobs], H) for the dense filter kernels.
 // Same algorithm and failure semantics as solve_kernel.cuh (one thread per draw, compile-time sizes); the loops
-// are distributed over the threads of the CTA.  Reference stages replaced: LRE.first_order_solver!
+// are distributed over the threads of the group.  Reference stages replaced: LRE.first_order_solver!
 // (src/perturbations.jl:663-664), compute_variance! (src/estimation/estimation.jl:630), state-space assembly
 // (estimation.jl:640-658).  Also hosts the stand-alone batched doubling Lyapunov solver (dyb_lyapunov_batch).
 #pragma once

@@ -199,3 +199,27 @@ def test_rwmh_matches_oracle(golden):
         total_acc += acc
     assert 0 < total_acc < nchain * niter
     ws.close()
+
+
+def test_rwmh_chains_can_be_sharded(golden):
+    """Chains are independent and their random numbers are keyed by the global chain index: running them in two
+    shards (two GPUs / two calls) reproduces the single-call result bit for bit."""
+    from dynare_jl_b200.engine import BatchSSWs
+    from dynare_jl_b200.samplers import rwmh
+    g = golden("ls2003")
+    ps = _model_priors("ls2003")
+    ws = BatchSSWs("ls2003", g["Y"])
+    ws.set_priors(ps)
+    ok = np.flatnonzero(g["status"] == 0)[:64]
+    y0 = ws.transform(g["theta"][ok], inverse=True)
+    cov = np.diag(np.full(ws.np, 0.03 ** 2))
+    full = rwmh(ws, ps, y0, cov, mcmc_replic=15, mcmc_chains=64, seed=5, keep_history=True)
+    a = rwmh(ws, ps, y0[:32], cov, mcmc_replic=15, mcmc_chains=32, seed=5, first_chain=0, keep_history=True)
+    b = rwmh(ws, ps, y0[32:], cov, mcmc_replic=15, mcmc_chains=32, seed=5, first_chain=32, keep_history=True)
+    assert np.array_equal(full["history"], np.concatenate([a["history"], b["history"]], axis=1))
+    assert np.array_equal(full["accepted"], np.concatenate([a["accepted"], b["accepted"]]))
+    # a run can be continued: 15 sweeps == 10 sweeps + 5 sweeps started at step 10
+    c1 = rwmh(ws, ps, y0, cov, mcmc_replic=10, mcmc_chains=64, seed=5)
+    c2 = rwmh(ws, ps, c1["y"], cov, mcmc_replic=5, mcmc_chains=64, seed=5, first_step=10)
+    assert np.array_equal(c2["y"], full["y"]) and 0 < full["accepted"].sum() < 64 * 15
+    ws.close()

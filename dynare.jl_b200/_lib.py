@@ -74,6 +74,7 @@ SIGNATURES = {
     "dyb_loglik_batch_async": (C.c_int, [_P, _D, C.c_int64, _D, _I32]),
     "dyb_loglik_batch_device": (C.c_int, [_P, _D, C.c_int64, _D, _I32]),
     "dyb_sync": (C.c_int, [_P]),
+    "dyb_query": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "dyb_kernel_launches": (C.c_int64, [_P]),
     "dyb_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "dyb_first_order_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D, _I32, _I32, _I32]),

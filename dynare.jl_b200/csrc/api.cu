@@ -313,6 +313,16 @@ int dyb_sync(dyb_handle* h) {
   return DYB_OK;
 }
 
+// non-blocking completion query for the asynchronous entry points: *done = 1 when the handle's stream is idle
+int dyb_query(dyb_handle* h, int32_t* done) {
+  if (!h || !done) return fail(DYB_ERR_ARG, "null argument");
+  DYB_CUDA(cudaSetDevice(h->device));
+  const cudaError_t e = cudaStreamQuery(h->stream);
+  if (e == cudaSuccess) { *done = 1; return DYB_OK; }
+  if (e == cudaErrorNotReady) { cudaGetLastError(); *done = 0; return DYB_OK; }
+  return fail(DYB_ERR_CUDA, cudaGetErrorString(e));
+}
+
 int64_t dyb_kernel_launches(const dyb_handle* h) { return h ? h->launches : 0; }
 
 int dyb_last_kernel_ms(dyb_handle* h, float* solve_ms, float* filter_ms) {

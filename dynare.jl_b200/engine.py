@@ -180,6 +180,12 @@ class BatchSSWs:
     def sync(self):
         L.check(self.lib.dyb_sync(self._h))
 
+    def done(self) -> bool:
+        """Non-blocking: has everything enqueued on this handle finished?"""
+        d = C.c_int32()
+        L.check(self.lib.dyb_query(self._h, C.byref(d)))
+        return bool(d.value)
+
     def set_stream(self, cuda_stream: Optional[int]):
         """Run on a caller-owned CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
         L.check(self.lib.dyb_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))

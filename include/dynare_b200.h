@@ -122,6 +122,8 @@ int dyb_loglik_batch_async(dyb_handle* h, const double* theta, int64_t n_draws,
 int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n_draws,
                             double* d_loglik, int32_t* d_status);
 int dyb_sync(dyb_handle* h);
+/* non-blocking completion query for the asynchronous calls: *done = 1 once everything enqueued on the handle finished */
+int dyb_query(dyb_handle* h, int32_t* done);
 /* run the handle's work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores the
  * handle's private stream) -- lets a host framework order and time the engine with its own events */
 int dyb_set_stream(dyb_handle* h, void* cuda_stream);

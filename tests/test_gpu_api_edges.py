@@ -66,6 +66,9 @@ def test_async_call_matches_sync_call(ws, golden):
     pth.array[:] = g["theta"]
     pll.array[:] = 0.0
     ws.loglikelihood_async(pth.array, pll.array, pst.array)
+    while not ws.done():                       # completion query of the asynchronous call
+        pass
+    assert ws.done()
     ws.sync()
     ll, st = ws.loglikelihood(g["theta"])
     assert np.array_equal(pll.array, ll) and np.array_equal(pst.array, st)             # same kernels: bit-identical

@@ -36,6 +36,7 @@ void generic_release(dyb_handle* h) {
 // launch the dense Kalman filter on device-resident state spaces (shared by dyb_kalman_batch and the
 // from-Jacobian likelihood); scratch (2 ns^2 doubles per CTA) only when P and T P do not fit in shared memory
 static int g_kalman_variant = 0;      // 0 auto, 1 scalar (kalman_generic.cuh), 2 tensor-core (kalman_dmma.cuh)
+static int g_kalman_bulk = 1;         // large-ns kernel: stage the GEMM panels with cp.async.bulk when alignment allows
 
 static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaStream_t st, Stager& sg) {
   int dev_sms = 148, max_smem = 0;
@@ -66,7 +67,10 @@ static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaSt
   {
     // large state spaces: persistent CTAs, P and T P in an L2-resident scratch, blocked tensor-core GEMMs
     const KalmanLargeGeom q = kalman_large_geom(g.ns, g.ny);
-    const size_t smem = sizeof(double) * kalman_large_smem_doubles(g.ns, g.ny);
+    // bulk-copy staging needs every operand column to be a 16-byte aligned run: ns a multiple of 8, aligned bases
+    const bool bulk = g_kalman_bulk && g.ns % 8 == 0 && ((uintptr_t)g.T % 16 == 0) && ((uintptr_t)g.RQR % 16 == 0) &&
+                      sizeof(double) * kalman_large_smem_doubles(g.ns, g.ny, true) + 1024 <= (size_t)max_smem;
+    const size_t smem = sizeof(double) * kalman_large_smem_doubles(g.ns, g.ny, bulk);
     const int threads = 32 * q.nwarps;
     const bool fits = q.nwarps <= 16 && smem + 1024 <= (size_t)max_smem &&
                       (size_t)8 * threads >= (size_t)q.nsp * DL_BK + (size_t)DL_BK * 8 * DL_NTP;
@@ -74,12 +78,15 @@ static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaSt
       long long grid = g.n_draws < dev_sms ? g.n_draws : dev_sms;
       g.scratch = sg.temp<double>(kalman_large_scratch_doubles(g.ns) * (size_t)grid);
       if (sg.err != cudaSuccess) return sg.err;
-      if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kalman_dmma_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-      }
-      kalman_dmma_large_kernel<<<(unsigned)grid, threads, smem, st>>>(g, q);
-      return cudaGetLastError();
+      auto launch = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return e;
+        }
+        kern<<<(unsigned)grid, threads, smem, st>>>(g, q);
+        return cudaGetLastError();
+      };
+      return bulk ? launch(kalman_dmma_large_kernel<true>) : launch(kalman_dmma_large_kernel<false>);
     }
   }
   const size_t ns2 = (size_t)g.ns * g.ns;
@@ -361,8 +368,9 @@ int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t p
 
 
 int dyb_set_kalman_variant(int32_t variant) {
-  if (variant < 0 || variant > 2) return fail(DYB_ERR_ARG, "variant must be 0 (auto), 1 (scalar) or 2 (tensor-core)");
-  g_kalman_variant = variant;
+  if (variant < 0 || variant > 3) return fail(DYB_ERR_ARG, "variant must be 0 (auto), 1 (scalar), 2 (tensor-core) or 3 (tensor-core, no bulk copies)");
+  g_kalman_bulk = variant != 3;
+  g_kalman_variant = variant == 3 ? 2 : variant;
   return DYB_OK;
 }
 

@@ -28,11 +28,7 @@ inline KalmanLargeGeom kalman_large_geom(int ns, int ny) {
   q.nwarps = (q.nsp / 8 + 1) / 2;
   return q;
 }
-inline size_t kalman_large_smem_doubles(int ns, int ny) {
-  const KalmanLargeGeom q = kalman_large_geom(ns, ny);
-  return 2 * ((size_t)q.lda * DL_BK + (size_t)DL_LDB * 8 * DL_NTP) + (size_t)q.ldu * q.nsp + (size_t)ny * ny +
-         2 * (size_t)q.nsp + 2 * (size_t)ny + 8;
-}
+inline size_t kalman_large_smem_doubles(int ns, int ny, bool bulk = false);
 inline size_t kalman_large_scratch_doubles(int ns) {
   const size_t nsp = (size_t)((ns + 7) / 8 * 8);
   return 2 * nsp * nsp;
@@ -184,17 +180,186 @@ DYB_D void block_gemm_dmma(const double* Ag, int lda_g, const double* Bg, int ld
   }
 }
 
+// ---- the same blocked GEMM with the panels moved by the bulk-copy engine (cp.async.bulk = SASS UBLKCP, completion on an
+// mbarrier): no thread spends instructions on staging.  Needs ns = nsp (a multiple of 8, so that every column of an
+// operand is a 16-byte aligned contiguous run); k-panels of 16.  Layout of a stage: A panel As[i + lda kk] (16 columns
+// of nsp rows), B panel either Bs[kk + 20 n] (B read by columns: runs of 16 k-values) or BsT[n + ldn kk] (B = T': runs
+// of the pass's n values), both conflict-free for the fragment loads.
+constexpr int DB_BK = 16;
+constexpr int DB_LDB = 20;                 // >= 16, = 4 mod 16
+DYB_HD int bulk_stage_doubles(int lda) {
+  const int ldn = dmma_pad_ld(8 * DL_NTP);
+  const int b = DB_LDB * 8 * DL_NTP > ldn * DB_BK ? DB_LDB * 8 * DL_NTP : ldn * DB_BK;
+  return lda * DB_BK + b;
+}
+
+DYB_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+DYB_D void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+DYB_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DYB_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+DYB_D void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool BT, bool SYMM>
+DYB_D void block_gemm_dmma_bulk(const double* Ag, int lda_g, const double* Bg, int ldb_g, int nsp, int lda,
+                                const double* Cinit, double* Cg, int ldc, double* stage0, int stage_doubles,
+                                unsigned long long* bars, unsigned& phases) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int nw = nt >> 5, ntile = nsp / 8, npanel = (nsp + DB_BK - 1) / DB_BK;
+  const int ldn = dmma_pad_ld(8 * DL_NTP);
+  // operands may have been written with ordinary stores by this CTA: make them visible to the bulk-copy (async) proxy
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncthreads();
+  for (int jt0 = 0; jt0 < ntile; jt0 += DL_NTP) {
+    const int ntw = (ntile - jt0 < DL_NTP) ? ntile - jt0 : DL_NTP;
+    const int ncolw = 8 * ntw, jbase = 8 * jt0;
+    int nact[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int si = warp + s * nw;
+      int na = si < ntile ? ntw : 0;
+      if (SYMM && si < ntile) { const int lim = si - jt0 + 1; na = lim < na ? (lim > 0 ? lim : 0) : na; }
+      nact[s] = na;
+    }
+    double c[2][DL_NTP][2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int si = warp + s * nw;
+#pragma unroll
+      for (int jt = 0; jt < DL_NTP; ++jt) {
+        c[s][jt][0] = 0.0; c[s][jt][1] = 0.0;
+        if (Cinit && jt < nact[s]) {
+          const int i = 8 * si + gq, j = jbase + 8 * jt + 2 * tq;
+          c[s][jt][0] = Cinit[i + (size_t)nsp * j];
+          c[s][jt][1] = Cinit[i + (size_t)nsp * (j + 1)];
+        }
+      }
+    }
+    // producer: warp 0 issues the copies of panel p into stage (p & 1)
+    auto issue = [&](int p) {
+      if (warp != 0) return;
+      const int k0 = p * DB_BK, kc = (nsp - k0 < DB_BK) ? nsp - k0 : DB_BK;
+      double* As = stage0 + (size_t)(p & 1) * stage_doubles;
+      double* Bs = As + lda * DB_BK;
+      unsigned long long* bar = bars + (p & 1);
+      if (lane == 0) mbar_expect_tx(bar, (unsigned)(8 * (kc * nsp + kc * ncolw)));
+      __syncwarp();
+      for (int kk = lane; kk < kc; kk += 32) bulk_g2s(As + lda * kk, Ag + (size_t)lda_g * (k0 + kk), 8u * nsp, bar);
+      if (BT) {
+        for (int kk = lane; kk < kc; kk += 32) bulk_g2s(Bs + ldn * kk, Bg + jbase + (size_t)ldb_g * (k0 + kk), 8u * ncolw, bar);
+      } else {
+        for (int n = lane; n < ncolw; n += 32) bulk_g2s(Bs + DB_LDB * n, Bg + k0 + (size_t)ldb_g * (jbase + n), 8u * kc, bar);
+      }
+    };
+    const bool full = (nact[0] == DL_NTP) && (nact[1] == DL_NTP || nact[1] == 0);
+    const bool two = nact[1] > 0;
+    issue(0);
+    for (int p = 0; p < npanel; ++p) {
+      const int st = p & 1;
+      if (p + 1 < npanel) issue(p + 1);           // its stage was released by the barrier that ended iteration p - 1
+      mbar_wait(bars + st, (phases >> st) & 1u);
+      phases ^= 1u << st;
+      const int k0 = p * DB_BK, kc = (nsp - k0 < DB_BK) ? nsp - k0 : DB_BK;
+      const double* As = stage0 + (size_t)st * stage_doubles;
+      const double* Bs = As + lda * DB_BK;
+      const double* Ap0 = As + (8 * warp + gq) + lda * tq;
+      const double* Ap1 = Ap0 + 8 * nw;
+      const double* Bp = BT ? Bs + gq + ldn * tq : Bs + tq + DB_LDB * gq;
+      const int bstep_k = BT ? 4 * ldn : 4, bstep_n = BT ? 8 : 8 * DB_LDB;
+      if (full) {
+#pragma unroll
+        for (int ks = 0; ks < DB_BK / 4; ++ks) {
+          if (4 * ks < kc) {
+            const double a0 = Ap0[lda * 4 * ks];
+            const double a1 = two ? Ap1[lda * 4 * ks] : 0.0;
+#pragma unroll
+            for (int jt = 0; jt < DL_NTP; ++jt) {
+              const double b = Bp[bstep_k * ks + bstep_n * jt];
+              dmma884(c[0][jt][0], c[0][jt][1], a0, b);
+              if (two) dmma884(c[1][jt][0], c[1][jt][1], a1, b);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < DB_BK / 4; ++ks) {
+          if (4 * ks < kc) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              if (nact[s] > 0) {
+                const double av = (s == 0 ? Ap0 : Ap1)[lda * 4 * ks];
+#pragma unroll
+                for (int jt = 0; jt < DL_NTP; ++jt)
+                  if (jt < nact[s]) dmma884(c[s][jt][0], c[s][jt][1], av, Bp[bstep_k * ks + bstep_n * jt]);
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();                              // every warp is done with stage st
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int si = warp + s * nw;
+#pragma unroll
+      for (int jt = 0; jt < DL_NTP; ++jt) {
+        if (jt >= nact[s]) continue;
+        const int i = 8 * si + gq, j = jbase + 8 * jt + 2 * tq;
+        if (!SYMM) {
+          Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1];
+        } else if (jt0 + jt < si) {
+          Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1];
+          Cg[j + (size_t)ldc * i] = c[s][jt][0]; Cg[(j + 1) + (size_t)ldc * i] = c[s][jt][1];
+        } else {
+          if (i >= j) { Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[j + (size_t)ldc * i] = c[s][jt][0]; }
+          if (i >= j + 1) { Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1]; Cg[(j + 1) + (size_t)ldc * i] = c[s][jt][1]; }
+        }
+      }
+    }
+  }
+}
+
+inline size_t kalman_large_smem_doubles(int ns, int ny, bool bulk) {
+  const KalmanLargeGeom q = kalman_large_geom(ns, ny);
+  const size_t stage = bulk ? (size_t)bulk_stage_doubles(q.lda) : (size_t)q.lda * DL_BK + (size_t)DL_LDB * 8 * DL_NTP;
+  return 2 * stage + (size_t)q.ldu * q.nsp + (size_t)ny * ny + 2 * (size_t)q.nsp + 2 * (size_t)ny + 8;
+}
+
 // blockDim.x = 32 * nwarps (nwarps = ceil(ntile / 2) <= 16); g.scratch: 2 nsp^2 doubles per CTA
+template <bool BULK>
 __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGenericArgs g, KalmanLargeGeom q) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int ns = g.ns, ny = g.ny, nsp = q.nsp, lda = q.lda, nyp = q.nyp, ldu = q.ldu;
   const int ntile = nsp / 8;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3, nw = nt >> 5;
-  const int panel_doubles = lda * DL_BK + DL_LDB * 8 * DL_NTP;
-  double* As0 = sm;                                  // two panels: [As | Bs] [As | Bs]
+  const int panel_doubles = BULK ? bulk_stage_doubles(lda) : lda * DL_BK + DL_LDB * 8 * DL_NTP;
+  double* As0 = sm;                                  // two stages: [As | Bs] [As | Bs]
   double* Bs0 = sm + lda * DL_BK;
   double* U = sm + 2 * panel_doubles;                // U[q + ldu * s], q < nyp
+  __shared__ __align__(8) unsigned long long bars[2];
+  unsigned phases = 0;                               // parity of the next completion of each stage barrier
+  if (BULK) {
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+  }
   double* F = U + (size_t)ldu * nsp;
   double* a = F + (size_t)ny * ny;
   double* au = a + nsp;
@@ -303,8 +468,14 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
       }
       __syncthreads();
       // M = T P ; P = M T' + R Q R'
-      block_gemm_dmma<false, false>(Tm, ns, P, nsp, ns, nsp, lda, nullptr, Mx, nsp, As0, Bs0, panel_doubles);
-      block_gemm_dmma<true, true>(Mx, nsp, Tm, ns, ns, nsp, lda, QQ, P, nsp, As0, Bs0, panel_doubles);
+      if (BULK) {
+        block_gemm_dmma_bulk<false, false>(Tm, ns, P, nsp, nsp, lda, nullptr, Mx, nsp, As0, panel_doubles, bars, phases);
+        block_gemm_dmma_bulk<true, true>(Mx, nsp, Tm, ns, nsp, lda, QQ, P, nsp, As0, panel_doubles, bars, phases);
+        __syncthreads();
+      } else {
+        block_gemm_dmma<false, false>(Tm, ns, P, nsp, ns, nsp, lda, nullptr, Mx, nsp, As0, Bs0, panel_doubles);
+        block_gemm_dmma<true, true>(Mx, nsp, Tm, ns, ns, nsp, lda, QQ, P, nsp, As0, Bs0, panel_doubles);
+      }
     }
     if (tid == 0) {
       const double ll = -0.5 * (nseen * 1.8378770664093453 + acc);

@@ -185,8 +185,8 @@ DYB_D void block_gemm_dmma(const double* Ag, int lda_g, const double* Bg, int ld
 // operand is a 16-byte aligned contiguous run); k-panels of 16.  Layout of a stage: A panel As[i + lda kk] (16 columns
 // of nsp rows), B panel either Bs[kk + 20 n] (B read by columns: runs of 16 k-values) or BsT[n + ldn kk] (B = T': runs
 // of the pass's n values), both conflict-free for the fragment loads.
-constexpr int DB_BK = 16;
-constexpr int DB_LDB = 20;                 // >= 16, = 4 mod 16
+constexpr int DB_BK = 32;
+constexpr int DB_LDB = 36;                 // >= DB_BK, = 4 mod 16
 DYB_HD int bulk_stage_doubles(int lda) {
   const int ldn = dmma_pad_ld(8 * DL_NTP);
   const int b = DB_LDB * 8 * DL_NTP > ldn * DB_BK ? DB_LDB * 8 * DL_NTP : ldn * DB_BK;

@@ -9,6 +9,7 @@
 #include "kalman_dmma_large.cuh"
 #include "solve_generic.cuh"
 #include "kalman_smoother.cuh"
+#include "kalman_diffuse.cuh"
 
 namespace dyb {
 
@@ -658,6 +659,47 @@ int dyb_kalman_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, in
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   int rc = launch_smoother(g, device, st, sg);
   if (rc) return rc;
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int dyb_kalman_diffuse_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, int32_t nobs, const int32_t* z_idx,
+                                      const double* Y, const double* T, const double* R, const double* Q,
+                                      const double* Pinf0, const double* Pstar0, const double* a0, const double* Hdiag,
+                                      double tol, int64_t n, double* alphah, double* etah, double* epsilonh, double* att,
+                                      double* a_pred, double* loglik, int32_t* n_diffuse, int32_t* status) {
+  if (ns <= 0 || ny <= 0 || ny > 64 || ny > ns || nx <= 0 || nobs <= 0 || n < 0 || !(tol > 0.0)) return fail(DYB_ERR_ARG, "bad sizes");
+  if (n == 0) return DYB_OK;
+  if (!z_idx || !Y || !T || !R || !Q || !Pinf0 || !Pstar0 || !status) return fail(DYB_ERR_ARG, "null argument");
+  DYB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = device_stream(device);
+  Stager sg(st);
+  const size_t N = (size_t)n, ns2 = (size_t)ns * ns;
+  KalmanDiffuseArgs g{};
+  g.ns = ns; g.ny = ny; g.nx = nx; g.nobs = nobs; g.tol = tol;
+  g.z_idx = sg.in(z_idx, (size_t)ny);
+  g.Y = sg.in(Y, (size_t)ny * nobs);
+  g.T = sg.in(T, ns2 * N); g.R = sg.in(R, (size_t)ns * nx * N); g.Q = sg.in(Q, (size_t)nx * nx * N);
+  g.Pinf0 = sg.in(Pinf0, ns2 * N); g.Pstar0 = sg.in(Pstar0, ns2 * N);
+  g.a0 = sg.in(a0, (size_t)ns * N); g.Hdiag = sg.in(Hdiag, (size_t)ny * N);
+  g.n_draws = n;
+  g.alphah = sg.out(alphah, (size_t)ns * nobs * N); g.etah = sg.out(etah, (size_t)nx * nobs * N);
+  g.epsilonh = sg.out(epsilonh, (size_t)ny * nobs * N); g.att = sg.out(att, (size_t)ns * nobs * N);
+  g.a_pred = sg.out(a_pred, (size_t)ns * (nobs + 1) * N);
+  g.loglik = sg.out(loglik, N); g.n_diffuse = sg.out(n_diffuse, N); g.status = sg.out(status, N);
+  if (!is_device_ptr(z_idx)) for (int i = 0; i < ny; ++i) if (z_idx[i] < 0 || z_idx[i] >= ns) return fail(DYB_ERR_ARG, "z_idx out of range");
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  int dev_sms = 148, max_smem = 0;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const size_t smem = sizeof(double) * diffuse_smem_doubles(ns, nx);
+  if (smem + 1024 > (size_t)max_smem) return fail(DYB_ERR_UNSUPPORTED, "state space too large for the shared-memory diffuse smoother");
+  long long grid = n < (long long)dev_sms * 2 ? n : (long long)dev_sms * 2;
+  g.work = sg.temp<double>(diffuse_work_doubles(ns, ny, nobs) * (size_t)grid);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  if (smem > 48 * 1024) DYB_CUDA(cudaFuncSetAttribute(kalman_diffuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kalman_diffuse_kernel<<<(unsigned)grid, 256, smem, st>>>(g);
+  DYB_CUDA(cudaGetLastError());
   DYB_CUDA(sg.finish());
   return DYB_OK;
 }

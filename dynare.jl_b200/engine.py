@@ -484,6 +484,56 @@ def kalman_smoother_batch(Y, z_idx, T, R, Q, P0, a0=None, H=None, device=0):
     return dict(alphah=al, etah=et, epsilonh=ep, att=at, a_pred=ap, loglik=ll, status=st)
 
 
+def diffuse_initial_covariances(T, R, Q, criterium=1 - 1e-6, device=0):
+    """Host-side preparation of the diffuse smoother, mirroring src/filters/kalman/kalman.jl:163-195 for each draw:
+    ordered real Schur form of T (LAPACK gees, moduli > criterium first -- host LAPACK in the reference too), Lyapunov
+    solve on the stable block (on the device), results rotated back to the original basis.
+    T (N, ns, ns), R (N, ns, nx), Q (N, nx, nx).  Returns (Pinf0, Pstar0 (N, ns, ns), k (N,) unit-root counts)."""
+    import scipy.linalg as sla
+    T = np.asarray(T, dtype=np.float64); R = np.asarray(R, dtype=np.float64); Q = np.asarray(Q, dtype=np.float64)
+    n, ns, _ = T.shape
+    Pinf = np.zeros((n, ns, ns)); Pstar = np.zeros((n, ns, ns)); ks = np.zeros(n, dtype=np.int32)
+    groups = {}
+    for d in range(n):
+        S, Zs, k = sla.schur(T[d], output="real", sort=lambda re, im: np.hypot(re, im) > criterium)
+        ks[d] = k
+        Pinf[d] = Zs[:, :k] @ Zs[:, :k].T
+        if ns > k:
+            tR = Zs[:, k:].T @ R[d]
+            groups.setdefault(int(k), []).append((d, S[k:, k:], tR @ Q[d] @ tR.T, Zs[:, k:]))
+    for k, items in groups.items():
+        X, _, st = lyapunov_batch(np.stack([it[1] for it in items]), np.stack([it[2] for it in items]), device=device)
+        for (d, _, _, Z2), x, s in zip(items, X, st):
+            if s != 0:
+                raise L.DybError(5, f"Lyapunov solve on the stable block failed for draw {d} (status {int(s)})")
+            Pstar[d] = Z2 @ (0.5 * (x + x.T)) @ Z2.T
+    return Pinf, Pstar, ks
+
+
+def kalman_diffuse_smoother_batch(Y, z_idx, T, R, Q, Pinf0, Pstar0, a0=None, Hdiag=None, tol=1e-8, device=0):
+    """Exact-diffuse batched filter + smoother (dyb_kalman_diffuse_smoother_batch): per-draw arrays as in
+    kalman_smoother_batch, Hdiag (N, ny) or None.  Returns the same dict plus n_diffuse (N,)."""
+    lib = L.load()
+    T = np.asarray(T, dtype=np.float64)
+    n, ns, _ = T.shape
+    Y = np.asarray(Y, dtype=np.float64)
+    ny, nobs = Y.shape
+    nx = np.asarray(R).shape[2]
+    cm = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).transpose(0, 2, 1))
+    Tc, Rc, Qc, Pic, Psc = cm(T), cm(R), cm(Q), cm(Pinf0), cm(Pstar0)
+    Hc = None if Hdiag is None else _f64(Hdiag, (n, ny))
+    a0c = None if a0 is None else _f64(a0, (n, ns))
+    z = np.ascontiguousarray(z_idx, dtype=np.int32)
+    Yf = np.asfortranarray(Y)
+    al = np.empty((n, nobs, ns)); et = np.empty((n, nobs, nx)); ep = np.empty((n, nobs, ny)); at = np.empty((n, nobs, ns))
+    ap = np.empty((n, nobs + 1, ns)); ll = np.empty(n); st = np.empty(n, dtype=np.int32); nd = np.empty(n, dtype=np.int32)
+    L.check(lib.dyb_kalman_diffuse_smoother_batch(device, ns, ny, nx, nobs, L.ptr(z), L.ptr(Yf), L.ptr(Tc), L.ptr(Rc),
+                                                  L.ptr(Qc), L.ptr(Pic), L.ptr(Psc), L.ptr(a0c), L.ptr(Hc), float(tol), n,
+                                                  L.ptr(al), L.ptr(et), L.ptr(ep), L.ptr(at), L.ptr(ap), L.ptr(ll),
+                                                  L.ptr(nd), L.ptr(st)))
+    return dict(alphah=al, etah=et, epsilonh=ep, att=at, a_pred=ap, loglik=ll, n_diffuse=nd, status=st)
+
+
 def smc_reweight(w, loglh, dphi, device=0):
     lib = L.load()
     w = _f64(w); loglh = _f64(loglh)

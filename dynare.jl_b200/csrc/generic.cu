@@ -77,7 +77,7 @@ static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaSt
                       (size_t)8 * threads >= (size_t)q.nsp * DL_BK + (size_t)DL_BK * 8 * DL_NTP;
     if (fits && g_kalman_variant != 1 && g.ns > 8 * DMMA_MAX_TILES) {
       long long grid = g.n_draws < dev_sms ? g.n_draws : dev_sms;
-      g.scratch = sg.temp<double>(kalman_large_scratch_doubles(g.ns) * (size_t)grid);
+      g.scratch = sg.temp<double>(kalman_large_scratch_doubles(g.ns, g.ny) * (size_t)grid);
       if (sg.err != cudaSuccess) return sg.err;
       auto launch = [&](auto kern) -> cudaError_t {
         if (smem > 48 * 1024) {

@@ -32,19 +32,20 @@ DYB_HD int dmma_pad_ld(int n) {        // smallest ld >= n with ld mod 16 in {4,
 }
 
 // Cholesky of the ny x ny innovation covariance (ny <= 8) and w = L^-1 v by ONE warp with the matrix in registers:
-// lane i owns row i, pivots and multipliers travel by shuffles (no shared-memory round trips on the critical path).
+// lane i owns row i (ny <= NY <= 32), pivots and multipliers travel by shuffles (no shared-memory round trips on the critical path).
 // In: F (column-major, lower part used), v.  Out: F <- L (lower incl. diagonal), w, and on every lane the sums
 // quad = w'w and ldet = sum_i log L_ii; returns false if a pivot is not positive.
-DYB_D bool chol8_warp(double* F, int ny, const double* v, double* w, double* rdv, double& quad, double& ldet) {
+template <int NY>
+DYB_D bool chol_warp(double* F, int ny, const double* v, double* w, double* rdv, double& quad, double& ldet) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  double f[8];
+  double f[NY];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) f[j] = (lane < ny && j <= lane) ? F[lane + ny * j] : 0.0;
+  for (int j = 0; j < NY; ++j) f[j] = (lane < ny && j <= lane) ? F[lane + ny * j] : 0.0;
   double rd = 1.0, ldiag = 1.0;
   bool ok = true;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NY; ++j) {
     if (j < ny) {
       const double d = __shfl_sync(FULL, f[j], j);
       ok = ok && (d > 0.0);
@@ -53,7 +54,7 @@ DYB_D bool chol8_warp(double* F, int ny, const double* v, double* w, double* rdv
       f[j] = lij;
       if (lane == j) { rd = r; ldiag = lij; }
 #pragma unroll
-      for (int c = j + 1; c < 8; ++c) {
+      for (int c = j + 1; c < NY; ++c) {
         if (c < ny) {
           const double lcj = __shfl_sync(FULL, lij, c);
           f[c] = fma(-lij, lcj, f[c]);
@@ -63,7 +64,7 @@ DYB_D bool chol8_warp(double* F, int ny, const double* v, double* w, double* rdv
   }
   double x = lane < ny ? v[lane] : 0.0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NY; ++j) {
     if (j < ny) {
       const double wj = __shfl_sync(FULL, x * rd, j);
       if (lane > j) x = fma(-f[j], wj, x);
@@ -77,9 +78,59 @@ DYB_D bool chol8_warp(double* F, int ny, const double* v, double* w, double* rdv
     w[lane] = wi;
     rdv[lane] = rd;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (j <= lane) F[lane + ny * j] = f[j];
+    for (int j = 0; j < NY; ++j) if (j <= lane) F[lane + ny * j] = f[j];
   }
   quad = q2; ldet = lg;
+  return ok;
+}
+
+DYB_D bool chol8_warp(double* F, int ny, const double* v, double* w, double* rdv, double& quad, double& ldet) {
+  return chol_warp<8>(F, ny, v, w, rdv, quad, ldet);
+}
+// The same factorisation for ny <= NY <= 32 as a LOOP over the pivot columns whose body has static register indices:
+// after column j is eliminated every lane shifts its row one place to the left, so the pivot column is always f[0].
+// (A fully unrolled version is ~100 KB of straight-line code that is executed once per period and misses the
+// instruction cache every time: measured 47k cycles at ny = 20 against ~4k for this loop.)
+template <int NY>
+DYB_D bool chol_warp_rot(double* F, int ny, const double* v, double* w, double* rdv, double& quad, double& ldet) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double f[NY];
+#pragma unroll
+  for (int c = 0; c < NY; ++c) f[c] = (lane < ny && c <= lane) ? F[lane + ny * c] : 0.0;
+  double x = lane < ny ? v[lane] : 0.0;
+  double rd = 1.0, ldiag = 1.0, wi = 0.0;
+  bool ok = true;
+#pragma unroll 1
+  for (int j = 0; j < ny; ++j) {
+    const double d = __shfl_sync(FULL, f[0], j);
+    ok = ok && (d > 0.0);
+    const double r = rsqrt(d);
+    const double lij = (lane == j) ? d * r : f[0] * r;
+    if (lane >= j && lane < ny) F[lane + ny * j] = lij;
+    const double wj = __shfl_sync(FULL, x * r, j);
+    if (lane == j) { rd = r; ldiag = lij; wi = wj; }
+    if (lane > j) x = fma(-lij, wj, x);
+#pragma unroll
+    for (int c = 1; c < NY; ++c) {
+      const double lcj = __shfl_sync(FULL, lij, j + c);       // lanes >= ny hold zeros; upper-part entries are never used
+      f[c - 1] = fma(-lij, lcj, f[c]);
+    }
+    f[NY - 1] = 0.0;
+  }
+  double q2 = lane < ny ? wi * wi : 0.0, lg = lane < ny ? log(ldiag) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { q2 += __shfl_xor_sync(FULL, q2, o); lg += __shfl_xor_sync(FULL, lg, o); }
+  if (lane < ny) { w[lane] = wi; rdv[lane] = rd; }
+  quad = q2; ldet = lg;
+  return ok;
+}
+// out of line, so that the NY doubles of a matrix row do not compete with the caller's accumulators for registers
+template <int NY>
+__noinline__ DYB_D bool chol_warp_call(double* F, int ny, const double* v, double* w, double* rdv, double* quad_ldet) {
+  double quad, ldet;
+  const bool ok = chol_warp_rot<NY>(F, ny, v, w, rdv, quad, ldet);
+  quad_ldet[0] = quad; quad_ldet[1] = ldet;
   return ok;
 }
 

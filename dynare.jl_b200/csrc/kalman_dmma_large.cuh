@@ -19,19 +19,20 @@ constexpr int DL_BK = 8;          // k-panel depth
 constexpr int DL_NTP = 9;         // tile columns per pass (accumulators: 2 strips x 9 tiles x 2 doubles per lane)
 constexpr int DL_LDB = 12;        // leading dimension of the staged B panel (8 rows, = 12 mod 16)
 
-struct KalmanLargeGeom { int nsp, lda, nyp, ldu, nwarps; };
+struct KalmanLargeGeom { int nsp, lda, nyp, ldu, nwarps, nxp; };
 
 inline KalmanLargeGeom kalman_large_geom(int ns, int ny) {
   KalmanLargeGeom q;
   q.nsp = (ns + 7) / 8 * 8; q.lda = dmma_pad_ld(q.nsp);
   q.nyp = (ny + 3) / 4 * 4; q.ldu = dmma_pad_ld(q.nyp);
   q.nwarps = (q.nsp / 8 + 1) / 2;
+  q.nxp = (ny + 1 + 7) / 8 * 8;          // extension columns of the bulk path: U' (ny), a + U'w (1), zero padding
   return q;
 }
 inline size_t kalman_large_smem_doubles(int ns, int ny, bool bulk = false);
-inline size_t kalman_large_scratch_doubles(int ns) {
-  const size_t nsp = (size_t)((ns + 7) / 8 * 8);
-  return 2 * nsp * nsp;
+inline size_t kalman_large_scratch_doubles(int ns, int ny) {
+  const KalmanLargeGeom q = kalman_large_geom(ns, ny);
+  return 2 * (size_t)q.nsp * (q.nsp + q.nxp) + (size_t)q.nsp * q.nxp;      // [P | U' au] , [T P | K a'] , -K
 }
 
 // C = A B (+ Cinit) on the nsp x nsp tile grid, block-cooperative.
@@ -187,10 +188,8 @@ DYB_D void block_gemm_dmma(const double* Ag, int lda_g, const double* Bg, int ld
 // of the pass's n values), both conflict-free for the fragment loads.
 constexpr int DB_BK = 32;
 constexpr int DB_LDB = 36;                 // >= DB_BK, = 4 mod 16
-DYB_HD int bulk_stage_doubles(int lda) {
-  const int ldn = dmma_pad_ld(8 * DL_NTP);
-  const int b = DB_LDB * 8 * DL_NTP > ldn * DB_BK ? DB_LDB * 8 * DL_NTP : ldn * DB_BK;
-  return lda * DB_BK + b;
+DYB_HD int bulk_stage_doubles(int nsp) {
+  return nsp * DB_BK + dmma_pad_ld(8 * DL_NTP) * DB_BK;        // A panel (leading dimension nsp) + B panel by rows
 }
 
 DYB_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -216,13 +215,53 @@ DYB_D void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long lo
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <bool BT, bool SYMM>
-DYB_D void block_gemm_dmma_bulk(const double* Ag, int lda_g, const double* Bg, int ldb_g, int nsp, int lda,
-                                const double* Cinit, double* Cg, int ldc, double* stage0, int stage_doubles,
-                                unsigned long long* bars, unsigned& phases) {
+// k-steps of one staged panel for a warp whose strips own N (<= NTP) tiles of the pass: strip 1 (if TWO) all N tiles,
+// strip 0 its first n0 <= N tiles (n0 warp-uniform).  N is a template parameter so that the B fragments of a k-step are
+// loaded together ahead of an unpredicated DMMA sequence.
+template <int N, bool TWO>
+DYB_D void dmma_panel_steps(double (&c)[2][DL_NTP][2], int n0, const double* Ap0, const double* Ap1, const double* Bp,
+                            int nsp, int ldn, int kc) {
+#pragma unroll 2
+  for (int ks = 0; ks < kc / 4; ++ks) {
+    double b[N];
+#pragma unroll
+    for (int jt = 0; jt < N; ++jt) b[jt] = Bp[4 * ldn * ks + 8 * jt];
+    if (TWO) {
+      const double a1 = Ap1[nsp * 4 * ks];
+#pragma unroll
+      for (int jt = 0; jt < N; ++jt) dmma884(c[1][jt][0], c[1][jt][1], a1, b[jt]);
+    }
+    if (n0 == N) {
+      const double a0 = Ap0[nsp * 4 * ks];
+#pragma unroll
+      for (int jt = 0; jt < N; ++jt) dmma884(c[0][jt][0], c[0][jt][1], a0, b[jt]);
+    } else if (n0 > 0) {
+      const double a0 = Ap0[nsp * 4 * ks];
+#pragma unroll
+      for (int jt = 0; jt < N; ++jt)
+        if (jt < n0) dmma884(c[0][jt][0], c[0][jt][1], a0, b[jt]);
+    }
+  }
+}
+
+// C = A B (+ Cinit) with C nsp x ncols and inner dimension kdim (all multiples of 8):
+//   A(i,k) = Ag[i + nsp k]  -- the leading dimension IS nsp, so a k-panel is ONE contiguous run and ONE bulk copy
+//            (the copy engine's cost is per copy, not per byte: 104 copies per panel cost ~7.5k cycles);
+//            the staged panel keeps leading dimension nsp, which costs a 2- or 4-way bank conflict on the two A
+//            fragment loads of a k-step (the nine B loads stay conflict-free)
+//   B(k,j) = k < ksplit ? Bg[j + ldb_g k] : Bg2[j + ldb_g2 (k - ksplit)]   (B given by rows: one copy per k)
+//   SYMM: only tiles on or below the block diagonal are computed, the result is mirrored
+//   Cneg (may be null): -C is also written there (leading dimension nsp), its column zero_col as zero
+// The filter's rank-ny correction rides inside the products:  K = T U' and a' = T (a + U'w) are one thin product
+// T [U' | a + U'w], and  P' = [T P | K] [T | -K]' + R Q R'  is one product with inner dimension nsp + nxp.
+template <bool SYMM>
+DYB_D void block_gemm_dmma_bulk(const double* Ag, const double* Bg, int ldb_g, const double* Bg2, int ldb_g2,
+                                int ksplit, int nsp, int ncols, int kdim,
+                                const double* Cinit, double* Cg, int ldc, double* Cneg, int zero_col,
+                                double* stage0, int stage_doubles, unsigned long long* bars, unsigned& phases) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-  const int nw = nt >> 5, ntile = nsp / 8, npanel = (nsp + DB_BK - 1) / DB_BK;
+  const int nw = nt >> 5, ntm = nsp / 8, ntile = ncols / 8, npanel = (kdim + DB_BK - 1) / DB_BK;
   const int ldn = dmma_pad_ld(8 * DL_NTP);
   // operands may have been written with ordinary stores by this CTA: make them visible to the bulk-copy (async) proxy
   asm volatile("fence.proxy.async;" ::: "memory");
@@ -234,8 +273,8 @@ DYB_D void block_gemm_dmma_bulk(const double* Ag, int lda_g, const double* Bg, i
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const int si = warp + s * nw;
-      int na = si < ntile ? ntw : 0;
-      if (SYMM && si < ntile) { const int lim = si - jt0 + 1; na = lim < na ? (lim > 0 ? lim : 0) : na; }
+      int na = si < ntm ? ntw : 0;
+      if (SYMM && si < ntm) { const int lim = si - jt0 + 1; na = lim < na ? (lim > 0 ? lim : 0) : na; }
       nact[s] = na;
     }
     double c[2][DL_NTP][2];
@@ -254,64 +293,112 @@ DYB_D void block_gemm_dmma_bulk(const double* Ag, int lda_g, const double* Bg, i
     }
     // producer: warp 0 issues the copies of panel p into stage (p & 1)
     auto issue = [&](int p) {
+#ifdef DYB_KL_NOCOPY
+      return;
+#endif
       if (warp != 0) return;
-      const int k0 = p * DB_BK, kc = (nsp - k0 < DB_BK) ? nsp - k0 : DB_BK;
+      const int k0 = p * DB_BK, kc = (kdim - k0 < DB_BK) ? kdim - k0 : DB_BK;
       double* As = stage0 + (size_t)(p & 1) * stage_doubles;
-      double* Bs = As + lda * DB_BK;
+      double* Bs = As + nsp * DB_BK;
       unsigned long long* bar = bars + (p & 1);
-      if (lane == 0) mbar_expect_tx(bar, (unsigned)(8 * (kc * nsp + kc * ncolw)));
+      if (lane == 0) {
+        mbar_expect_tx(bar, (unsigned)(8 * (kc * nsp + kc * ncolw)));
+        bulk_g2s(As, Ag + (size_t)nsp * k0, 8u * nsp * kc, bar);
+      }
       __syncwarp();
-      for (int kk = lane; kk < kc; kk += 32) bulk_g2s(As + lda * kk, Ag + (size_t)lda_g * (k0 + kk), 8u * nsp, bar);
-      if (BT) {
-        for (int kk = lane; kk < kc; kk += 32) bulk_g2s(Bs + ldn * kk, Bg + jbase + (size_t)ldb_g * (k0 + kk), 8u * ncolw, bar);
-      } else {
-        for (int n = lane; n < ncolw; n += 32) bulk_g2s(Bs + DB_LDB * n, Bg + k0 + (size_t)ldb_g * (jbase + n), 8u * kc, bar);
+      for (int kk = lane; kk < kc; kk += 32) {
+        const int k = k0 + kk;
+        const double* src = k < ksplit ? Bg + jbase + (size_t)ldb_g * k : Bg2 + jbase + (size_t)ldb_g2 * (k - ksplit);
+        bulk_g2s(Bs + ldn * kk, src, 8u * ncolw, bar);
       }
     };
-    const bool full = (nact[0] == DL_NTP) && (nact[1] == DL_NTP || nact[1] == 0);
-    const bool two = nact[1] > 0;
+    // warp-uniform by construction; taken from a vote so that ptxas knows it too and the mma.sync sequences below are
+    // not interleaved with WARPSYNC / NOP pairs
+    const bool full = __all_sync(0xffffffffu, (nact[0] == DL_NTP) && (nact[1] == DL_NTP || nact[1] == 0));
+    const bool two = __all_sync(0xffffffffu, nact[1] > 0);
+    const int n0u = __reduce_max_sync(0xffffffffu, nact[0]), n1u = __reduce_max_sync(0xffffffffu, nact[1]);
     issue(0);
     for (int p = 0; p < npanel; ++p) {
       const int st = p & 1;
       if (p + 1 < npanel) issue(p + 1);           // its stage was released by the barrier that ended iteration p - 1
+#ifndef DYB_KL_NOCOPY
       mbar_wait(bars + st, (phases >> st) & 1u);
       phases ^= 1u << st;
-      const int k0 = p * DB_BK, kc = (nsp - k0 < DB_BK) ? nsp - k0 : DB_BK;
+#endif
+      const int k0 = p * DB_BK, kc = (kdim - k0 < DB_BK) ? kdim - k0 : DB_BK;
       const double* As = stage0 + (size_t)st * stage_doubles;
-      const double* Bs = As + lda * DB_BK;
-      const double* Ap0 = As + (8 * warp + gq) + lda * tq;
+      const double* Bs = As + nsp * DB_BK;
+#ifdef DYB_KL_NOMMA
+      if (kc < 0) {
+#else
+      {
+#endif
+      const double* Ap0 = As + (8 * warp + gq) + nsp * tq;
       const double* Ap1 = Ap0 + 8 * nw;
-      const double* Bp = BT ? Bs + gq + ldn * tq : Bs + tq + DB_LDB * gq;
-      const int bstep_k = BT ? 4 * ldn : 4, bstep_n = BT ? 8 : 8 * DB_LDB;
-      if (full) {
+      const double* Bp = Bs + gq + ldn * tq;
+      if (full && two) {
 #pragma unroll
         for (int ks = 0; ks < DB_BK / 4; ++ks) {
           if (4 * ks < kc) {
-            const double a0 = Ap0[lda * 4 * ks];
-            const double a1 = two ? Ap1[lda * 4 * ks] : 0.0;
+            const double a0 = Ap0[nsp * 4 * ks];
+            const double a1 = Ap1[nsp * 4 * ks];
 #pragma unroll
             for (int jt = 0; jt < DL_NTP; ++jt) {
-              const double b = Bp[bstep_k * ks + bstep_n * jt];
+              const double b = Bp[4 * ldn * ks + 8 * jt];
               dmma884(c[0][jt][0], c[0][jt][1], a0, b);
-              if (two) dmma884(c[1][jt][0], c[1][jt][1], a1, b);
+              dmma884(c[1][jt][0], c[1][jt][1], a1, b);
             }
           }
         }
-      } else {
+      } else if (full) {
+#pragma unroll
+        for (int ks = 0; ks < DB_BK / 4; ++ks) {
+          if (4 * ks < kc) {
+            const double a0 = Ap0[nsp * 4 * ks];
+#pragma unroll
+            for (int jt = 0; jt < DL_NTP; ++jt) dmma884(c[0][jt][0], c[0][jt][1], a0, Bp[4 * ldn * ks + 8 * jt]);
+          }
+        }
+      } else if (n1u >= n0u && n1u > 0) {           // two strips, strip 1 owns at least as many tiles (always so here)
+        switch (n1u) {
+          case 1: dmma_panel_steps<1, true>(c, n0u, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 2: dmma_panel_steps<2, true>(c, n0u, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 3: dmma_panel_steps<3, true>(c, n0u, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 4: dmma_panel_steps<4, true>(c, n0u, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 5: dmma_panel_steps<5, true>(c, n0u, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 6: dmma_panel_steps<6, true>(c, n0u, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 7: dmma_panel_steps<7, true>(c, n0u, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 8: dmma_panel_steps<8, true>(c, n0u, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          default: dmma_panel_steps<9, true>(c, n0u, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+        }
+      } else if (n1u == 0 && n0u > 0) {             // one strip
+        switch (n0u) {
+          case 1: dmma_panel_steps<1, false>(c, 1, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 2: dmma_panel_steps<2, false>(c, 2, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 3: dmma_panel_steps<3, false>(c, 3, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 4: dmma_panel_steps<4, false>(c, 4, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 5: dmma_panel_steps<5, false>(c, 5, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 6: dmma_panel_steps<6, false>(c, 6, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 7: dmma_panel_steps<7, false>(c, 7, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          case 8: dmma_panel_steps<8, false>(c, 8, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+          default: dmma_panel_steps<9, false>(c, 9, Ap0, Ap1, Bp, nsp, ldn, kc); break;
+        }
+      } else if (n0u > 0) {                         // strip 0 owns more tiles than strip 1: predicated fallback
 #pragma unroll
         for (int ks = 0; ks < DB_BK / 4; ++ks) {
           if (4 * ks < kc) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
               if (nact[s] > 0) {
-                const double av = (s == 0 ? Ap0 : Ap1)[lda * 4 * ks];
+                const double av = (s == 0 ? Ap0 : Ap1)[nsp * 4 * ks];
 #pragma unroll
                 for (int jt = 0; jt < DL_NTP; ++jt)
-                  if (jt < nact[s]) dmma884(c[s][jt][0], c[s][jt][1], av, Bp[bstep_k * ks + bstep_n * jt]);
+                  if (jt < nact[s]) dmma884(c[s][jt][0], c[s][jt][1], av, Bp[4 * ldn * ks + 8 * jt]);
               }
             }
           }
         }
+      }
       }
       __syncthreads();                              // every warp is done with stage st
     }
@@ -324,6 +411,10 @@ DYB_D void block_gemm_dmma_bulk(const double* Ag, int lda_g, const double* Bg, i
         const int i = 8 * si + gq, j = jbase + 8 * jt + 2 * tq;
         if (!SYMM) {
           Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1];
+          if (Cneg) {
+            Cneg[i + (size_t)nsp * j] = j == zero_col ? 0.0 : -c[s][jt][0];
+            Cneg[i + (size_t)nsp * (j + 1)] = j + 1 == zero_col ? 0.0 : -c[s][jt][1];
+          }
         } else if (jt0 + jt < si) {
           Cg[i + (size_t)ldc * j] = c[s][jt][0]; Cg[i + (size_t)ldc * (j + 1)] = c[s][jt][1];
           Cg[j + (size_t)ldc * i] = c[s][jt][0]; Cg[(j + 1) + (size_t)ldc * i] = c[s][jt][1];
@@ -338,11 +429,11 @@ DYB_D void block_gemm_dmma_bulk(const double* Ag, int lda_g, const double* Bg, i
 
 inline size_t kalman_large_smem_doubles(int ns, int ny, bool bulk) {
   const KalmanLargeGeom q = kalman_large_geom(ns, ny);
-  const size_t stage = bulk ? (size_t)bulk_stage_doubles(q.lda) : (size_t)q.lda * DL_BK + (size_t)DL_LDB * 8 * DL_NTP;
-  return 2 * stage + (size_t)q.ldu * q.nsp + (size_t)ny * ny + 2 * (size_t)q.nsp + 2 * (size_t)ny + 8;
+  const size_t stage = bulk ? (size_t)bulk_stage_doubles(q.nsp) : (size_t)q.lda * DL_BK + (size_t)DL_LDB * 8 * DL_NTP;
+  return 2 * stage + (size_t)q.ldu * q.nsp + (size_t)ny * ny + 2 * (size_t)q.nsp + 3 * (size_t)ny + 8;
 }
 
-// blockDim.x = 32 * nwarps (nwarps = ceil(ntile / 2) <= 16); g.scratch: 2 nsp^2 doubles per CTA
+// blockDim.x = 32 * nwarps (nwarps = ceil(ntile / 2) <= 16); g.scratch: kalman_large_scratch_doubles per CTA
 template <bool BULK>
 __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGenericArgs g, KalmanLargeGeom q) {
   extern __shared__ __align__(16) double sm[];
@@ -350,7 +441,7 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
   const int ntile = nsp / 8;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3, nw = nt >> 5;
-  const int panel_doubles = BULK ? bulk_stage_doubles(lda) : lda * DL_BK + DL_LDB * 8 * DL_NTP;
+  const int panel_doubles = BULK ? bulk_stage_doubles(nsp) : lda * DL_BK + DL_LDB * 8 * DL_NTP;
   double* As0 = sm;                                  // two stages: [As | Bs] [As | Bs]
   double* Bs0 = sm + lda * DL_BK;
   double* U = sm + 2 * panel_doubles;                // U[q + ldu * s], q < nyp
@@ -365,10 +456,14 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
   double* au = a + nsp;
   double* v = au + nsp;
   double* w = v + ny;
+  double* rdv = w + ny;
   __shared__ int bad;
   __shared__ int zi[64];
-  double* P = g.scratch + (size_t)blockIdx.x * 2 * nsp * nsp;      // P[i + nsp * j]
-  double* Mx = P + (size_t)nsp * nsp;
+  const int nxp = q.nxp;
+  double* P = g.scratch + (size_t)blockIdx.x * (2 * (size_t)nsp * (nsp + nxp) + (size_t)nsp * nxp);   // P[i + nsp * j]
+  double* Mx = P + (size_t)nsp * (nsp + nxp);        // T P, then (bulk path) K = T U' and a' in the extension columns
+  double* Kneg = Mx + (size_t)nsp * (nsp + nxp);     // -K, the extra rows of the second product's B operand
+  double* PxT = P + (size_t)nsp * nsp;               // [U' | a + U'w | 0] by rows: PxT[q + nxp s]
 
   for (long long d = blockIdx.x; d < g.n_draws; d += gridDim.x) {
     __syncthreads();
@@ -385,15 +480,26 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
     for (int i = tid; i < ny; i += nt) zi[i] = g.z_idx[i];
     for (int e = tid; e < nsp * nsp; e += nt) {
       const int i = e % nsp, j = e / nsp;
-      P[e] = (i < ns && j < ns) ? P0[i + (size_t)ns * j] : 0.0;
+      // lower triangle mirrored: the bulk path reads P by rows (P = P')
+      P[e] = (i < ns && j < ns) ? (i >= j ? P0[i + (size_t)ns * j] : P0[j + (size_t)ns * i]) : 0.0;
     }
     for (int e = tid; e < ldu * nsp; e += nt) U[e] = 0.0;
+    if (BULK) for (int e = tid; e < nsp * nxp; e += nt) PxT[e] = 0.0;
     for (int i = tid; i < nsp; i += nt) { a[i] = (g.a0 && i < ns) ? g.a0[(size_t)d * ns + i] : 0.0; au[i] = 0.0; }
     __syncthreads();
     double acc = 0.0;          // only thread 0's copy is used
     int nseen = 0;
 
+#ifdef DYB_KL_PROFILE
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, c0 = 0;
+#define KL_MARK(k) { __syncthreads(); const long long c1 = clock64(); pc[k] += c1 - c0; c0 = c1; }
+#else
+#define KL_MARK(k)
+#endif
     for (int t = 0; t < g.nobs; ++t) {
+#ifdef DYB_KL_PROFILE
+      __syncthreads(); c0 = clock64();
+#endif
       const double* yt = g.Y + (size_t)t * ny;
       for (int i = tid; i < ny; i += nt) {
         const double yi = yt[i];
@@ -407,7 +513,27 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
         F[e] = f;
       }
       __syncthreads();
-      if (tid < 32) {                         // Cholesky of F by warp 0 (right-looking), then w = L^-1 v
+      KL_MARK(4)
+      if (tid < 32 && ny <= 32) {             // Cholesky of F and w = L^-1 v by warp 0, F in registers (one row per lane)
+        double ql[2];
+        bool okc;
+#ifdef DYB_KL_PROFILE
+        const long long cc0 = clock64();
+#endif
+        if (ny <= 8) okc = chol_warp_call<8>(F, ny, v, w, rdv, ql);
+        else if (ny <= 16) okc = chol_warp_call<16>(F, ny, v, w, rdv, ql);
+        else if (ny <= 24) okc = chol_warp_call<24>(F, ny, v, w, rdv, ql);
+        else okc = chol_warp_call<32>(F, ny, v, w, rdv, ql);
+        const double quad = ql[0], ldet = ql[1];
+#ifdef DYB_KL_PROFILE
+        pc[5] += clock64() - cc0;
+#endif
+        const int cnt = __popc(__ballot_sync(0xffffffffu, tid < ny && !isnan(yt[tid < ny ? tid : 0])));
+        if (tid == 0) {
+          if (!okc) bad = 1;
+          if (t >= g.presample) { acc += 2.0 * ldet + quad; nseen += cnt; }
+        }
+      } else if (tid < 32) {                  // ny > 32: right-looking Cholesky in shared memory
         for (int j = 0; j < ny; ++j) {
           const double djj = F[j + ny * j];
           __syncwarp();
@@ -428,7 +554,9 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
           for (int i = 0; i < ny; ++i) {
             double x = v[i];
             for (int p = 0; p < i; ++p) x -= F[i + ny * p] * w[p];
-            x /= F[i + ny * i];
+            const double ri = 1.0 / F[i + ny * i];
+            rdv[i] = ri;
+            x *= ri;
             w[i] = x;
             quad += x * x;
             ldet += log(F[i + ny * i]);
@@ -438,6 +566,7 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
         }
       }
       __syncthreads();
+      KL_MARK(0)
       if (t == g.nobs - 1) break;
       // U[:, s] = L^-1 (Z P)[:, s] ; au = a + U'w
       for (int s = tid; s < ns; s += nt) {
@@ -445,13 +574,31 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
         for (int i = 0; i < ny; ++i) {
           double u = isnan(yt[i]) ? 0.0 : P[zi[i] + (size_t)nsp * s];
           for (int p = 0; p < i; ++p) u -= F[i + ny * p] * U[p + ldu * s];
-          u /= F[i + ny * i];
+          u *= rdv[i];
           U[i + ldu * s] = u;
+          if (BULK) PxT[i + (size_t)nxp * s] = u;
           x += u * w[i];
         }
         au[s] = x;
+        if (BULK) PxT[ny + (size_t)nxp * s] = x;
       }
       __syncthreads();
+      KL_MARK(1)
+      if (BULK) {
+        // M = T P (P symmetric: B by rows = P itself) ; [K | a'] = T [U' | a + U'w] ; P' = [M | K] [T | -K]' + R Q R'
+        block_gemm_dmma_bulk<false>(Tm, P, nsp, nullptr, 0, nsp, nsp, nsp, nsp, nullptr, Mx, nsp, nullptr, -1,
+                                    As0, panel_doubles, bars, phases);
+        block_gemm_dmma_bulk<false>(Tm, PxT, nxp, nullptr, 0, nsp, nsp, nxp, nsp, nullptr, Mx + (size_t)nsp * nsp, nsp,
+                                    Kneg, ny, As0, panel_doubles, bars, phases);
+        __syncthreads();
+        KL_MARK(2)
+        for (int i = tid; i < ns; i += nt) a[i] = Mx[i + (size_t)nsp * (nsp + ny)];
+        block_gemm_dmma_bulk<true>(Mx, Tm, ns, Kneg, nsp, nsp, nsp, nsp, nsp + nxp, QQ, P, nsp, nullptr, -1,
+                                   As0, panel_doubles, bars, phases);
+        __syncthreads();
+        KL_MARK(3)
+        continue;
+      }
       // a <- T au
       for (int i = tid; i < ns; i += nt) {
         double x = 0.0;
@@ -468,15 +615,13 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
       }
       __syncthreads();
       // M = T P ; P = M T' + R Q R'
-      if (BULK) {
-        block_gemm_dmma_bulk<false, false>(Tm, ns, P, nsp, nsp, lda, nullptr, Mx, nsp, As0, panel_doubles, bars, phases);
-        block_gemm_dmma_bulk<true, true>(Mx, nsp, Tm, ns, nsp, lda, QQ, P, nsp, As0, panel_doubles, bars, phases);
-        __syncthreads();
-      } else {
-        block_gemm_dmma<false, false>(Tm, ns, P, nsp, ns, nsp, lda, nullptr, Mx, nsp, As0, Bs0, panel_doubles);
-        block_gemm_dmma<true, true>(Mx, nsp, Tm, ns, ns, nsp, lda, QQ, P, nsp, As0, Bs0, panel_doubles);
-      }
+      block_gemm_dmma<false, false>(Tm, ns, P, nsp, ns, nsp, lda, nullptr, Mx, nsp, As0, Bs0, panel_doubles);
+      block_gemm_dmma<true, true>(Mx, nsp, Tm, ns, ns, nsp, lda, QQ, P, nsp, As0, Bs0, panel_doubles);
     }
+#ifdef DYB_KL_PROFILE
+    if (tid == 0 && d == 0) printf("cycles per period: (chol call %lld) F build %lld  chol %lld  U-solve %lld  product1 %lld  product2 %lld\n",
+                                   pc[5] / g.nobs, pc[4] / g.nobs, pc[0] / g.nobs, pc[1] / g.nobs, pc[2] / g.nobs, pc[3] / g.nobs);
+#endif
     if (tid == 0) {
       const double ll = -0.5 * (nseen * 1.8378770664093453 + acc);
       if (bad || !isfinite(ll)) { g.loglik[d] = -INFINITY; g.status[d] = ST_F_NOT_PD; }

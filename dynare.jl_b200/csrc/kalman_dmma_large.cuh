@@ -293,9 +293,6 @@ DYB_D void block_gemm_dmma_bulk(const double* Ag, const double* Bg, int ldb_g, c
     }
     // producer: warp 0 issues the copies of panel p into stage (p & 1)
     auto issue = [&](int p) {
-#ifdef DYB_KL_NOCOPY
-      return;
-#endif
       if (warp != 0) return;
       const int k0 = p * DB_BK, kc = (kdim - k0 < DB_BK) ? kdim - k0 : DB_BK;
       double* As = stage0 + (size_t)(p & 1) * stage_doubles;
@@ -321,18 +318,12 @@ DYB_D void block_gemm_dmma_bulk(const double* Ag, const double* Bg, int ldb_g, c
     for (int p = 0; p < npanel; ++p) {
       const int st = p & 1;
       if (p + 1 < npanel) issue(p + 1);           // its stage was released by the barrier that ended iteration p - 1
-#ifndef DYB_KL_NOCOPY
       mbar_wait(bars + st, (phases >> st) & 1u);
       phases ^= 1u << st;
-#endif
       const int k0 = p * DB_BK, kc = (kdim - k0 < DB_BK) ? kdim - k0 : DB_BK;
       const double* As = stage0 + (size_t)st * stage_doubles;
       const double* Bs = As + nsp * DB_BK;
-#ifdef DYB_KL_NOMMA
-      if (kc < 0) {
-#else
       {
-#endif
       const double* Ap0 = As + (8 * warp + gq) + nsp * tq;
       const double* Ap1 = Ap0 + 8 * nw;
       const double* Bp = Bs + gq + ldn * tq;
@@ -431,6 +422,34 @@ inline size_t kalman_large_smem_doubles(int ns, int ny, bool bulk) {
   const KalmanLargeGeom q = kalman_large_geom(ns, ny);
   const size_t stage = bulk ? (size_t)bulk_stage_doubles(q.nsp) : (size_t)q.lda * DL_BK + (size_t)DL_LDB * 8 * DL_NTP;
   return 2 * stage + (size_t)q.ldu * q.nsp + (size_t)ny * ny + 2 * (size_t)q.nsp + 3 * (size_t)ny + 8;
+}
+
+// U[:, s] = L^-1 (Z P)[:, s] and au = a + U'w, one state s per thread, with the column in registers: right-looking
+// substitution whose body has static register indices (the pending right-hand sides shift one place per step, as in
+// chol_warp_rot).  Writes U' and a + U'w by rows into PxT for the thin product.
+template <int NY>
+DYB_D void usolve_regs(int tid, int nt, int ns, int ny, const double* yt, const int* zi, const double* P, int ldP,
+                       const double* F, const double* rdv, const double* w, const double* a, double* au,
+                       double* PxT, int ldx) {
+  for (int s = tid; s < ns; s += nt) {
+    double x[NY];
+#pragma unroll
+    for (int i = 0; i < NY; ++i) x[i] = (i < ny && !isnan(yt[i])) ? P[zi[i] + (size_t)ldP * s] : 0.0;
+    double acc = a[s];
+    double* row = PxT + (size_t)ldx * s;
+#pragma unroll 1
+    for (int i = 0; i < ny; ++i) {
+      const double u = x[0] * rdv[i];
+      row[i] = u;
+      acc = fma(u, w[i], acc);
+      const double* Fi = F + i + (size_t)ny * i;                 // F[i + c, i] = Fi[c]
+#pragma unroll
+      for (int c = 1; c < NY; ++c) x[c - 1] = (i + c < ny) ? fma(-Fi[c], u, x[c]) : 0.0;
+      x[NY - 1] = 0.0;
+    }
+    au[s] = acc;
+    row[ny] = acc;
+  }
 }
 
 // blockDim.x = 32 * nwarps (nwarps = ceil(ntile / 2) <= 16); g.scratch: kalman_large_scratch_doubles per CTA
@@ -569,18 +588,25 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
       KL_MARK(0)
       if (t == g.nobs - 1) break;
       // U[:, s] = L^-1 (Z P)[:, s] ; au = a + U'w
-      for (int s = tid; s < ns; s += nt) {
-        double x = a[s];
-        for (int i = 0; i < ny; ++i) {
-          double u = isnan(yt[i]) ? 0.0 : P[zi[i] + (size_t)nsp * s];
-          for (int p = 0; p < i; ++p) u -= F[i + ny * p] * U[p + ldu * s];
-          u *= rdv[i];
-          U[i + ldu * s] = u;
-          if (BULK) PxT[i + (size_t)nxp * s] = u;
-          x += u * w[i];
+      if (BULK && ny <= 32) {
+        if (ny <= 8) usolve_regs<8>(tid, nt, ns, ny, yt, zi, P, nsp, F, rdv, w, a, au, PxT, nxp);
+        else if (ny <= 16) usolve_regs<16>(tid, nt, ns, ny, yt, zi, P, nsp, F, rdv, w, a, au, PxT, nxp);
+        else if (ny <= 24) usolve_regs<24>(tid, nt, ns, ny, yt, zi, P, nsp, F, rdv, w, a, au, PxT, nxp);
+        else usolve_regs<32>(tid, nt, ns, ny, yt, zi, P, nsp, F, rdv, w, a, au, PxT, nxp);
+      } else {
+        for (int s = tid; s < ns; s += nt) {
+          double x = a[s];
+          for (int i = 0; i < ny; ++i) {
+            double u = isnan(yt[i]) ? 0.0 : P[zi[i] + (size_t)nsp * s];
+            for (int p = 0; p < i; ++p) u -= F[i + ny * p] * U[p + ldu * s];
+            u *= rdv[i];
+            U[i + ldu * s] = u;
+            if (BULK) PxT[i + (size_t)nxp * s] = u;
+            x += u * w[i];
+          }
+          au[s] = x;
+          if (BULK) PxT[ny + (size_t)nxp * s] = x;
         }
-        au[s] = x;
-        if (BULK) PxT[ny + (size_t)nxp * s] = x;
       }
       __syncthreads();
       KL_MARK(1)

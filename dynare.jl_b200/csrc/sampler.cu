@@ -172,7 +172,7 @@ static int resample_impl(int device, const double* w, const double* u, double u0
   unsigned long long* dcl = sg.temp<unsigned long long>(1);
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   DYB_CUDA(cudaMemsetAsync(dcl, 0, sizeof(unsigned long long), st));
-  smc_block_scan_kernel<<<nblk(nb, 64), 64, 0, st>>>(dw, n, cw, bt);
+  smc_block_scan_kernel<<<(unsigned)nb, 32, 0, st>>>(dw, n, cw, bt);
   smc_offsets_kernel<<<1, 32, 0, st>>>(bt, nb, offs);
   smc_add_offsets_kernel<<<nblk(n, 256), 256, 0, st>>>(cw, offs, n);
   smc_search_kernel<<<nblk(n, 256), 256, 0, st>>>(cw, n, du, u0, systematic, 0, n, didx, dcl);
@@ -191,6 +191,30 @@ int dyb_smc_resample_systematic(int device, const double* w, double u0, int64_t 
   return resample_impl(device, w, nullptr, u0, 1, n, idx, n_clamped);
 }
 
+// second central moment partials in the canonical order: staged through shared memory when a block of particles fits
+static cudaError_t launch_moment2(const double* para, const double* w, const double* mu, long long n, int np, long long nb,
+                                  double* part, int device, cudaStream_t st) {
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const size_t smem = smc_moment2_smem_bytes(np);
+  if (nb > 0 && smem + 1024 <= (size_t)max_smem) {
+    static int configured_for = -1;
+    if (configured_for < (int)smem) {
+      cudaError_t e = cudaFuncSetAttribute(smc_moment2_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
+      if (e != cudaSuccess) return e;
+      configured_for = max_smem;
+    }
+    unsigned groups = (unsigned)((296 + nb - 1) / nb);                       // about two CTAs per SM in total
+    const unsigned maxg = (unsigned)((np * np + SMC_MOM_TILE - 1) / SMC_MOM_TILE);
+    if (groups > maxg) groups = maxg;
+    if (groups < 1) groups = 1;
+    smc_moment2_staged_kernel<<<dim3((unsigned)nb, groups), dim3(32, SMC_MOM_TILE), smem, st>>>(para, w, mu, n, np, part);
+  } else if (nb > 0) {
+    smc_moment_kernel<<<dim3((unsigned)nb, nblk(np * np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(para, w, mu, n, np, part);
+  }
+  return cudaGetLastError();
+}
+
 int dyb_smc_moments(int device, const double* para, const double* w, int64_t n, int32_t np, double* mu, double* R) {
   if (n <= 0 || np <= 0 || np > MAX_EST || !para || !w || !mu || !R) return fail(DYB_ERR_ARG, "bad argument");
   DYB_CUDA(cudaSetDevice(device));
@@ -206,7 +230,7 @@ int dyb_smc_moments(int device, const double* para, const double* w, int64_t n, 
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   smc_moment_kernel<<<dim3((unsigned)nb, nblk(np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(dp, dw, nullptr, n, np, part);
   smc_reduce_partials_kernel<<<nblk(np, 64), 64, 0, st>>>(part, nb, np, dmu);
-  smc_moment_kernel<<<dim3((unsigned)nb, nblk(np * np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(dp, dw, dmu, n, np, part);
+  DYB_CUDA(launch_moment2(dp, dw, dmu, n, np, nb, part, device, st));
   smc_reduce_partials_kernel<<<nblk(np * np, 64), 64, 0, st>>>(part, nb, np * np, dR);
   DYB_CUDA(cudaGetLastError());
   DYB_CUDA(sg.finish());
@@ -507,7 +531,7 @@ static int smc_stage(dyb_smc* s, int i) {
 
   DYB_MARK(1);
   // 2. selection (smc.jl:130-145): every kernel is predicated on the device flag, the collectives are unconditional
-  smc_block_scan_kernel<<<nblk(nb, 64), 64, 0, st>>>(w_g, N, s->cw_g.as<double>(), s->bt.as<double>());
+  smc_block_scan_kernel<<<(unsigned)nb, 32, 0, st>>>(w_g, N, s->cw_g.as<double>(), s->bt.as<double>());
   smc_offsets_kernel<<<1, 32, 0, st>>>(s->bt.as<double>(), nb, s->offs.as<double>());
   smc_add_offsets_kernel<<<nblk(N, 256), 256, 0, st>>>(s->cw_g.as<double>(), s->offs.as<double>(), N);
   smc_select_kernel<<<nblk(n, 256), 256, 0, st>>>(s->cw_g.as<double>(), N, s->seed, (unsigned)i, s->systematic, first, n, flag,
@@ -531,8 +555,8 @@ static int smc_stage(dyb_smc* s, int i) {
   rc = all_gather(h, part_g + (size_t)s->rank * nb_l * np, part_g, (size_t)nb_l * np, ncclDouble, 8);
   if (rc) return rc;
   smc_reduce_partials_kernel<<<nblk(np, 64), 64, 0, st>>>(part_g, nb, np, s->mu.as<double>());
-  smc_moment_kernel<<<dim3((unsigned)nb_l, nblk(np * np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(
-      s->para.as<double>(), w_g + first, s->mu.as<double>(), n, np, part_g + (size_t)s->rank * nb_l * np * np);
+  DYB_CUDA(launch_moment2(s->para.as<double>(), w_g + first, s->mu.as<double>(), n, np, nb_l,
+                          part_g + (size_t)s->rank * nb_l * np * np, h->device, st));
   rc = all_gather(h, part_g + (size_t)s->rank * nb_l * np * np, part_g, (size_t)nb_l * np * np, ncclDouble, 8);
   if (rc) return rc;
   smc_reduce_partials_kernel<<<nblk(np * np, 64), 64, 0, st>>>(part_g, nb, np * np, s->R.as<double>());

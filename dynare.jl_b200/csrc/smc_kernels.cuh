@@ -64,17 +64,26 @@ __global__ void smc_normalise_kernel(const double* __restrict__ wt, const double
   if (i < n) w_out[i] = wt[i] / zhat[0];
 }
 
-// local inclusive scan inside each 1024-block (one thread per block) + block totals
+// local inclusive scan inside each 1024-block + block totals.  The scan is sequential by definition (canonical order);
+// one warp per block stages the weights through shared memory with coalesced loads and stores, so that the 1024
+// dependent additions of lane 0 wait on shared memory instead of on one global load each (70 us -> 8 us at 16 blocks).
+// launch <<<number of blocks, 32>>>
 __global__ void smc_block_scan_kernel(const double* __restrict__ w, long long n,
                                       double* __restrict__ local, double* __restrict__ block_tot) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nb = (n + SMC_BLOCK - 1) / SMC_BLOCK;
-  if (b >= nb) return;
-  const long long lo = b * SMC_BLOCK;
-  const long long hi = (lo + SMC_BLOCK < n) ? lo + SMC_BLOCK : n;
-  double s = 0.0;
-  for (long long i = lo; i < hi; ++i) { s += w[i]; local[i] = s; }
-  block_tot[b] = s;
+  __shared__ double ws[SMC_BLOCK];
+  const long long lo = (long long)blockIdx.x * SMC_BLOCK;
+  const int cnt = (int)((lo + SMC_BLOCK < n) ? SMC_BLOCK : n - lo);
+  const int lane = threadIdx.x;
+  for (int k = lane; k < cnt; k += 32) ws[k] = w[lo + k];
+  __syncwarp();
+  if (lane == 0) {
+    double s = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < cnt; ++i) { s += ws[i]; ws[i] = s; }
+    block_tot[blockIdx.x] = s;
+  }
+  __syncwarp();
+  for (int k = lane; k < cnt; k += 32) local[lo + k] = ws[k];
 }
 
 // exclusive sequential scan of block totals (single thread): offs[b] = sum_{b' < b} tot[b']
@@ -134,6 +143,44 @@ __global__ void smc_moment_kernel(const double* __restrict__ para, const double*
   }
   const double t = warp_sum_in_order(s);
   if (threadIdx.x == 0) partial[(long long)blockIdx.x * ncomp + c] = t;
+}
+
+// The second moment again, same arithmetic in the same order, for np small enough that a 1024-particle block fits in
+// shared memory ((np + 1) * 1056 doubles): the block is read ONCE per CTA with coalesced loads instead of once per
+// component from 32 scattered rows per warp-load (the scattered version moves ~0.5 GB through L2 at 16 384 x 17).
+// Particle e of the block sits at column e + e / 32, so that the 32 lanes of a warp (runs 32 apart) hit distinct banks.
+// launch <<<dim3(blocks, groups), dim3(32, SMC_MOM_TILE), smc_moment2_smem_bytes(np)>>>; group g owns components
+// c = g, g + groups, ... spread over the CTA's warps.
+constexpr int SMC_MOM_LD = SMC_BLOCK + SMC_BLOCK / 32;
+inline size_t smc_moment2_smem_bytes(int np) { return sizeof(double) * (size_t)(np + 1) * SMC_MOM_LD; }
+__global__ void smc_moment2_staged_kernel(const double* __restrict__ para, const double* __restrict__ w,
+                                          const double* __restrict__ mu, long long n, int np,
+                                          double* __restrict__ partial) {
+  extern __shared__ double sm_mom[];
+  double* xs = sm_mom;                         // xs[p * LD + col]
+  double* wsm = sm_mom + (size_t)np * SMC_MOM_LD;
+  const int tid = threadIdx.y * 32 + threadIdx.x, nt = 32 * SMC_MOM_TILE;
+  const long long lo = (long long)blockIdx.x * SMC_BLOCK;
+  const int cnt = (int)((lo + SMC_BLOCK < n) ? SMC_BLOCK : n - lo);
+  for (int k = tid; k < cnt * np; k += nt) {
+    const int e = k / np, p = k - e * np;
+    xs[(size_t)p * SMC_MOM_LD + e + e / 32] = para[(long long)np * lo + k];
+  }
+  for (int e = tid; e < cnt; e += nt) wsm[e + e / 32] = w[lo + e];
+  __syncthreads();
+  const int ncomp = np * np, lane = threadIdx.x;
+  for (int c = blockIdx.y + gridDim.y * threadIdx.y; c < ncomp; c += gridDim.y * SMC_MOM_TILE) {
+    const int p = c % np, q = c / np;
+    const double mp = mu[p], mq = mu[q];
+    const double* xp = xs + (size_t)p * SMC_MOM_LD + 33 * lane;
+    const double* xq = xs + (size_t)q * SMC_MOM_LD + 33 * lane;
+    const double* wl = wsm + 33 * lane;
+    double s = 0.0;
+    for (int i = 0; i < SMC_RUN; ++i)
+      if (lane * SMC_RUN + i < cnt) s = __dadd_rn(s, __dmul_rn(__dmul_rn(wl[i], xp[i] - mp), xq[i] - mq));
+    const double t = warp_sum_in_order(s);
+    if (lane == 0) partial[(long long)blockIdx.x * ncomp + c] = t;
+  }
 }
 
 // out[c] = sequential sum over blocks of partial[b*ncomp + c]

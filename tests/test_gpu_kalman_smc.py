@@ -25,7 +25,10 @@ def _random_state_space(rng, n, ns, ny, nx):
 @pytest.mark.parametrize("ns,ny,nobs,n,variant", [
     (6, 2, 50, 40, 0), (6, 2, 50, 40, 1), (3, 1, 20, 11, 0), (40, 7, 60, 12, 1), (40, 7, 60, 12, 2), (24, 5, 30, 9, 2), (37, 9, 25, 7, 2),
     (64, 12, 20, 5, 2), (88, 20, 10, 3, 2), (110, 20, 12, 3, 0), (110, 20, 12, 3, 1), (97, 3, 9, 4, 0),
-    (200, 20, 6, 2, 0), (200, 20, 6, 2, 1), (256, 7, 4, 2, 0)])
+    (200, 20, 6, 2, 0), (200, 20, 6, 2, 1), (256, 7, 4, 2, 0),
+    # large kernel, bulk-staged path: ny a multiple of 8 (no spare column in the last tile), ny > 32 (shared-memory
+    # Cholesky and substitution), ny = 1, 13 warps with an odd strip count; variant 3 = register-staged panels
+    (104, 24, 8, 3, 0), (104, 36, 6, 2, 0), (96, 1, 12, 3, 0), (136, 16, 7, 2, 0), (200, 20, 6, 2, 3), (104, 36, 6, 2, 3)])
 def test_generic_kalman_matches_oracle(ns, ny, nobs, n, variant):
     """variant 1 = scalar kernel, 2 = tensor-core (DMMA) kernel, 0 = automatic choice (shared-memory DMMA kernel for
     8 < ns <= 88, L2-scratch DMMA kernel for 88 < ns <= 256); sizes of BASELINE configs 4 (ns 40, ny 7) and 5 (ns 200,
@@ -46,6 +49,21 @@ def test_generic_kalman_matches_oracle(ns, ny, nobs, n, variant):
         ref = pl.kalman_likelihood(Y, Z, H[i], T[i], np.eye(ns), RQR[i], np.zeros(ns), P0[i])
         assert st[i] == 0
         assert abs(ll[i] - ref) <= 1e-8 * abs(ref), (i, ll[i], ref)
+
+
+def test_large_kalman_flags_non_pd_draw_and_keeps_the_others():
+    from dynare_jl_b200.engine import kalman_batch
+    rng = np.random.default_rng(5)
+    ns, ny, n = 96, 4, 3
+    T, RQR, P0, H = _random_state_space(rng, n, ns, ny, ny)
+    P0[1] = -P0[1]
+    Y = rng.standard_normal((ny, 6))
+    ll, st = kalman_batch(Y, np.arange(ny), T, RQR, P0, H=H)
+    assert st[1] == pl.ST_F_NOT_PD and ll[1] == -np.inf
+    Z = np.zeros((ny, ns)); Z[np.arange(ny), np.arange(ny)] = 1
+    for i in (0, 2):
+        ref = pl.kalman_likelihood(Y, Z, H[i], T[i], np.eye(ns), RQR[i], np.zeros(ns), P0[i])
+        assert st[i] == 0 and abs(ll[i] - ref) <= 1e-8 * abs(ref)
 
 
 def test_generic_kalman_flags_non_pd():

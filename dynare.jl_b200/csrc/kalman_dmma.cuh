@@ -169,6 +169,7 @@ kalman_dmma_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
   __shared__ int bad;
   __shared__ int zi[64];
   const int i0 = 8 * warp;
+  const int wu = __reduce_max_sync(0xffffffffu, warp);   // = warp, as a value that ptxas knows to be warp-uniform
 
   for (long long d = blockIdx.x; d < g.n_draws; d += gridDim.x) {
     __syncthreads();
@@ -218,7 +219,18 @@ kalman_dmma_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
           if (!okc) bad = 1;
           if (t >= g.presample) { acc += 2.0 * ldet + quad; nseen += cnt; }
         }
-      } else if (tid < 32) {                  // Cholesky of F by warp 0 (right-looking), then w = L^-1 v
+      } else if (tid < 32 && ny <= 32) {      // loop-form register Cholesky (chol_warp_rot)
+        double ql[2];
+        bool okc;
+        if (ny <= 16) okc = chol_warp_call<16>(F, ny, v, w, rdv, ql);
+        else if (ny <= 24) okc = chol_warp_call<24>(F, ny, v, w, rdv, ql);
+        else okc = chol_warp_call<32>(F, ny, v, w, rdv, ql);
+        const int cnt = __popc(__ballot_sync(0xffffffffu, tid < ny && !isnan(yt[tid < ny ? tid : 0])));
+        if (tid == 0) {
+          if (!okc) bad = 1;
+          if (t >= g.presample) { acc += 2.0 * ql[1] + ql[0]; nseen += cnt; }
+        }
+      } else if (tid < 32) {                  // ny > 32: Cholesky of F by warp 0 in shared memory, then w = L^-1 v
         for (int j = 0; j < ny; ++j) {
           const double djj = F[j + ny * j];
           __syncwarp();
@@ -312,7 +324,7 @@ kalman_dmma_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
 #pragma unroll
         for (int jt = 0; jt < MAXT; ++jt) {
           c[jt][0] = 0.0; c[jt][1] = 0.0;
-          if (jt <= warp) {
+          if (jt <= wu) {
             const int i = i0 + gq, j = 8 * jt + 2 * tq;
             if (i < ns && j < ns) c[jt][0] = QQ[i + (size_t)ns * j];
             if (i < ns && j + 1 < ns) c[jt][1] = QQ[i + (size_t)ns * (j + 1)];
@@ -322,13 +334,13 @@ kalman_dmma_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
           const double av = Ms[(i0 + gq) + ld * (k0 + tq)];
 #pragma unroll
           for (int jt = 0; jt < MAXT; ++jt)
-            if (jt <= warp) dmma884(c[jt][0], c[jt][1], av, Ts[(8 * jt + gq) + ld * (k0 + tq)]);
+            if (jt <= wu) dmma884(c[jt][0], c[jt][1], av, Ts[(8 * jt + gq) + ld * (k0 + tq)]);
         }
 #pragma unroll
         for (int jt = 0; jt < MAXT; ++jt)
-          if (jt <= warp) {
+          if (jt <= wu) {
             const int i = i0 + gq, j = 8 * jt + 2 * tq;
-            if (jt < warp) {
+            if (jt < wu) {
               Ps[i + ld * j] = c[jt][0]; Ps[i + ld * (j + 1)] = c[jt][1];
               Ps[j + ld * i] = c[jt][0]; Ps[(j + 1) + ld * i] = c[jt][1];
             } else {                            // diagonal tile: keep the lower triangle, mirror it

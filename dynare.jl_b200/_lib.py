@@ -89,8 +89,9 @@ SIGNATURES = {
     "dyb_kalman_smoother_batch": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _D, _D, _D, _D, _D,
                                             _D, _D, C.c_int64, _D, _D, _D, _D, _D, _D, _I32]),
     "dyb_kalman_diffuse_smoother_batch": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _D, _D, _D,
-                                                    _D, _D, _D, _D, _D, C.c_double, C.c_int64, _D, _D, _D, _D, _D, _D,
-                                                    _I32, _I32]),
+                                                    _D, _D, _D, _D, _D, _D, C.c_double, C.c_int64, _D, _D, _D, _D, _D,
+                                                    _D, _I32, _I32]),
+    "dyb_shock_covariances_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D]),
     "dyb_smoother_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D, _D, _D, _I32]),
     "dyb_forecast_batch": (C.c_int, [_P, _D, C.c_int64, C.c_int32, _D, _D, _I32]),
     "dyb_kalman_batch": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _D,

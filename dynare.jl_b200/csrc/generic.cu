@@ -666,7 +666,7 @@ int dyb_kalman_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, in
 int dyb_kalman_diffuse_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, int32_t nobs, const int32_t* z_idx,
                                       const double* Y, const double* T, const double* R, const double* Q,
                                       const double* Pinf0, const double* Pstar0, const double* a0, const double* Hdiag,
-                                      double tol, int64_t n, double* alphah, double* etah, double* epsilonh, double* att,
+                                      const double* ybar_obs, double tol, int64_t n, double* alphah, double* etah, double* epsilonh, double* att,
                                       double* a_pred, double* loglik, int32_t* n_diffuse, int32_t* status) {
   if (ns <= 0 || ny <= 0 || ny > 64 || ny > ns || nx <= 0 || nobs <= 0 || n < 0 || !(tol > 0.0)) return fail(DYB_ERR_ARG, "bad sizes");
   if (n == 0) return DYB_OK;
@@ -681,7 +681,7 @@ int dyb_kalman_diffuse_smoother_batch(int device, int32_t ns, int32_t ny, int32_
   g.Y = sg.in(Y, (size_t)ny * nobs);
   g.T = sg.in(T, ns2 * N); g.R = sg.in(R, (size_t)ns * nx * N); g.Q = sg.in(Q, (size_t)nx * nx * N);
   g.Pinf0 = sg.in(Pinf0, ns2 * N); g.Pstar0 = sg.in(Pstar0, ns2 * N);
-  g.a0 = sg.in(a0, (size_t)ns * N); g.Hdiag = sg.in(Hdiag, (size_t)ny * N);
+  g.a0 = sg.in(a0, (size_t)ns * N); g.Hdiag = sg.in(Hdiag, (size_t)ny * N); g.ybar_obs = sg.in(ybar_obs, (size_t)ny * N);
   g.n_draws = n;
   g.alphah = sg.out(alphah, (size_t)ns * nobs * N); g.etah = sg.out(etah, (size_t)nx * nobs * N);
   g.epsilonh = sg.out(epsilonh, (size_t)ny * nobs * N); g.att = sg.out(att, (size_t)ns * nobs * N);
@@ -699,6 +699,31 @@ int dyb_kalman_diffuse_smoother_batch(int device, int32_t ns, int32_t ny, int32_
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   if (smem > 48 * 1024) DYB_CUDA(cudaFuncSetAttribute(kalman_diffuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kalman_diffuse_kernel<<<(unsigned)grid, 256, smem, st>>>(g);
+  DYB_CUDA(cudaGetLastError());
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int dyb_shock_covariances_batch(dyb_handle* h, const double* theta, int64_t n, double* sigma_e, double* sigma_m) {
+  if (!h || n < 0 || (n > 0 && (!theta || (!sigma_e && !sigma_m)))) return fail(DYB_ERR_ARG, "bad argument");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  const dyb_model_dims& d = h->dims;
+  const size_t N = (size_t)n;
+  Stager sg(h->stream);
+  const double* dth = sg.in(theta, (size_t)h->hs.np * N);
+  double* dse = sg.out(sigma_e, (size_t)d.nx * d.nx * N);
+  double* dsm = sg.out(sigma_m, (size_t)d.ny * d.ny * N);
+  if (!dse) dse = sg.temp<double>((size_t)d.nx * d.nx * N);
+  double* dse0 = sg.temp<double>((size_t)d.nx * d.nx);
+  double* dsm0 = sg.temp<double>((size_t)d.ny * d.ny);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  DYB_CUDA(cudaMemcpyAsync(dse0, h->hs.sigma_e.data(), sizeof(double) * d.nx * d.nx, cudaMemcpyHostToDevice, h->stream));
+  DYB_CUDA(cudaMemcpyAsync(dsm0, h->hs.sigma_m.data(), sizeof(double) * d.ny * d.ny, cudaMemcpyHostToDevice, h->stream));
+  SigmaEArgs sa{};
+  sa.np = h->hs.np; sa.nx = d.nx; sa.ny = d.ny;
+  for (int q = 0; q < h->hs.np; ++q) { sa.est_type[q] = h->hs.est_type[q]; sa.est_i[q] = h->hs.est_i[q]; sa.est_j[q] = h->hs.est_j[q]; }
+  sigma_e_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(sa, dse0, dsm0, dth, n, dse, dsm);
   DYB_CUDA(cudaGetLastError());
   DYB_CUDA(sg.finish());
   return DYB_OK;

@@ -27,6 +27,7 @@ struct KalmanDiffuseArgs {
   const double* Pstar0;    // ns x ns per draw
   const double* a0;        // ns per draw or null
   const double* Hdiag;     // ny per draw or null
+  const double* ybar_obs;  // ny per draw or null: subtracted from the observations (steady state of the observables)
   long long n_draws;
   double* work;            // per CTA: diffuse_work_doubles
   double* alphah;          // ns x nobs
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) kalman_diffuse_kernel(KalmanDiffuseArgs g
     const double* Rm = g.R + (size_t)d * ns * nx;
     const double* Qm = g.Q + (size_t)d * nx * nx;
     const double* Hd = g.Hdiag ? g.Hdiag + (size_t)d * ny : nullptr;
+    const double* yb = g.ybar_obs ? g.ybar_obs + (size_t)d * ny : nullptr;
     for (int i = tid; i < ny; i += nt) zi[i] = g.z_idx[i];
     for (int i = tid; i < ns * ns; i += nt) {
       Ps[i] = g.Pstar0[(size_t)d * ns * ns + i];
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256) kalman_diffuse_kernel(KalmanDiffuseArgs g
         const double yi = yt[i];
         if (isnan(yi)) { if (tid == 0) st[0] = -1.0; continue; }
         const int z = zi[i];
-        const double v = yi - a[z];
+        const double v = (yi - (yb ? yb[i] : 0.0)) - a[z];
         const double Fs = Ps[z + (size_t)ns * z] + (Hd ? Hd[i] : 0.0);
         const double Fi = diffuse ? Pi[z + (size_t)ns * z] : 0.0;
         double* Kst = Kstore + 2 * (size_t)ns * ((size_t)ny * t + i);
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(256) kalman_diffuse_kernel(KalmanDiffuseArgs g
       if (g.epsilonh) for (int i = tid; i < ny; i += nt) {   // eps_hat = y - Z alpha_hat where H_ii > 0
         const double yi = yt[i];
         const bool has = !isnan(yi) && Hd && Hd[i] > 0.0;
-        g.epsilonh[(size_t)d * ny * nobs + i + (size_t)ny * t] = has ? yi - Ks[zi[i]] : 0.0;
+        g.epsilonh[(size_t)d * ny * nobs + i + (size_t)ny * t] = has ? (yi - (yb ? yb[i] : 0.0)) - Ks[zi[i]] : 0.0;
       }
       __syncthreads();
     }

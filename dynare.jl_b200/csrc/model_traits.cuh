@@ -34,6 +34,15 @@ DYB_HD constexpr int tri(int i, int j) {            // packed lower-triangular i
 DYB_HD constexpr int sym(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
 
 #if defined(__CUDACC__)
+// cyclic reduction: relative change of ||A0(j)|| below which a non-vanishing A0 sequence is read as a unit root
+constexpr double CR_UNIT_ROOT_EPS = 1e-6;
+
+// doubling Lyapunov solve: the model counts as non-stationary when a root lies within 1e-6 of the unit circle (the
+// reference splits at 1 - 1e-6, src/filters/kalman/kalman.jl:172-180): after LYAP_UNIT_ROOT_IT + 1 doublings the
+// iterate is A^(2^20), whose norm is (1 - 1e-6)^(2^20) = 0.35 at that boundary
+constexpr int LYAP_UNIT_ROOT_IT = 19;
+constexpr double LYAP_UNIT_ROOT_NORM = 0.35;
+
 // fast fp64 reciprocal square root: hardware seed (MUFU.RSQ64H, ~20 bits) + two Newton steps (<= 1 ulp for
 // normal inputs); callers guard non-positive / non-finite arguments separately
 DYB_D double fast_rsqrt(double x) {

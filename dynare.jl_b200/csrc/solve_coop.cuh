@@ -406,8 +406,12 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
         if (iter == 1) result = ST_SOLVER; else stalled = true;
         active = false;
       } else {
+        const double n0_prev = n0;
         n0 = m0; n2 = m2;
-        if (n0 < opt.cr_tol && n2 < opt.cr_tol) { conv = true; active = false; }
+        // converged: both sequences vanished, or A2(j) vanished while A0(j) has settled on a non-zero limit -- a unit
+        // root among the stable roots (the reference's generalised Schur solver counts |lambda| < 1 + 1e-6 as stable);
+        // the correction of A1hat, and with it the error of G, is then O(n2): hence the squared tolerance on n2
+        if ((n0 < opt.cr_tol && n2 < opt.cr_tol) || (n2 < opt.cr_tol * opt.cr_tol && fabs(n0 - n0_prev) <= CR_UNIT_ROOT_EPS * n0)) { conv = true; active = false; }
       }
     }
   }
@@ -695,6 +699,7 @@ assemble_kernel(const double* __restrict__ mid, long long n_draws, double lyap_t
 #pragma unroll
     for (int i = 0; i < K * K; ++i) { Ak[i] = Tm[i]; amax = fmax(amax, fabs(Tm[i])); }
     if (dmax <= lyap_tol * smax && amax < 1.0) { lconv = true; break; }
+    if (li == LYAP_UNIT_ROOT_IT && amax >= LYAP_UNIT_ROOT_NORM) break;      // a root within 1e-6 of the unit circle
     if (!isfinite(amax)) break;
   }
   if (lyap_iters) lyap_iters[d] = li_done;

@@ -143,6 +143,7 @@ DYB_D int blk_lyapunov(double* Ak, double* Sg, double* Tm, int k, double tol, in
     gp.sync();
     if (!isfinite(S)) break;
     if (D <= tol * S && A < 1.0) { conv = 1; break; }
+    if (li == LYAP_UNIT_ROOT_IT && A >= LYAP_UNIT_ROOT_NORM) break;         // a root within 1e-6 of the unit circle
     if (!isfinite(A)) break;
   }
   if (iters) *iters = done;
@@ -346,8 +347,9 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
         const double m0 = n0_sh, m2 = n2_sh;
         gp.sync();
         if (!(m0 <= 1e150) || !(m2 <= 1e150)) { if (it == 1) status = ST_SOLVER; else stalled = true; break; }
+        const double n0_prev = n0;
         n0 = m0; n2 = m2;
-        if (n0 < a.cr_tol && n2 < a.cr_tol) { conv = true; break; }
+        if ((n0 < a.cr_tol && n2 < a.cr_tol) || (n2 < a.cr_tol * a.cr_tol && fabs(n0 - n0_prev) <= CR_UNIT_ROOT_EPS * n0)) { conv = true; break; }
       }
       if (status == ST_OK && !conv) {
         if (stalled) status = (n0 < n2) ? ST_INDETERMINATE : ST_UNSTABLE;

@@ -256,8 +256,10 @@ __device__ int solve_draw(const SolveParams<M>& prm, const double* __restrict__ 
       if (it == 1) status = ST_SOLVER; else stalled = true;
       break;
     }
+    const double n0_prev = n0;
     n0 = m0; n2 = m2;
-    if (n0 < prm.cr_tol && n2 < prm.cr_tol) { conv = true; break; }
+    // unit roots among the stable roots: A0(j) settles on a non-zero limit while A2(j) vanishes (see solve_coop.cuh)
+    if ((n0 < prm.cr_tol && n2 < prm.cr_tol) || (n2 < prm.cr_tol * prm.cr_tol && fabs(n0 - n0_prev) <= CR_UNIT_ROOT_EPS * n0)) { conv = true; break; }
   }
   if (cr_it_out) *cr_it_out = it;
   if (status == ST_OK && !conv) {
@@ -382,6 +384,7 @@ __device__ int solve_draw(const SolveParams<M>& prm, const double* __restrict__ 
     double amax = 0.0;
     for (int i = 0; i < K * K; ++i) { Ak[i] = Tm[i]; amax = fmax(amax, fabs(Tm[i])); }
     if (dmax <= prm.lyap_tol * smax && amax < 1.0) { lconv = true; break; }
+    if (li == LYAP_UNIT_ROOT_IT && amax >= LYAP_UNIT_ROOT_NORM) break;      // a root within 1e-6 of the unit circle
     if (!isfinite(amax)) break;
   }
   if (lyap_it_out) *lyap_it_out = li_done;

@@ -281,6 +281,52 @@ class BatchSSWs:
         L.check(self.lib.dyb_smoother_batch(self._h, L.ptr(Theta), n, L.ptr(al), L.ptr(et), L.ptr(ep), L.ptr(ll), L.ptr(st)))
         return dict(alphah=al, etah=et, epsilonh=ep, loglik=ll, status=st)
 
+    def shock_covariances(self, Theta):
+        """Sigma_e (N, nx, nx) and Sigma_m (N, ny, ny) of every draw (set_estimated_parameters!, estimation.jl:517-601)."""
+        Theta = self._theta(Theta)
+        n = Theta.shape[0]
+        d = self.dims
+        se = np.empty((n, d["nx"], d["nx"])); sm = np.empty((n, d["ny"], d["ny"]))
+        L.check(self.lib.dyb_shock_covariances_batch(self._h, L.ptr(Theta), n, L.ptr(se), L.ptr(sm)))
+        return se.transpose(0, 2, 1), sm.transpose(0, 2, 1)
+
+    def smoother_nonstationary(self, Theta, Y, tol=1e-8):
+        """The non-stationary branch of calibsmoother! (src/filters/kalman/kalman.jl:163-223) for N draws of a model with
+        unit roots: first-order solution on the device (unit roots are accepted among the stable roots), every
+        endogenous variable a state (T[:, i_bkwrd_b] = g1_1, R = g1_2; kalman.jl:78-108), ordered Schur split and
+        Lyapunov equation on the stable block (host LAPACK as in the reference + device doubling), exact-diffuse filter
+        and smoother on the device.  Y (ny, nobs) in levels.  Returns dict(alphah (N, nobs, n) in levels, etah, epsilonh,
+        loglik (diffuse), n_diffuse, n_unit_roots, status); H must be diagonal (measurement-error variances)."""
+        Theta = self._theta(Theta)
+        N = Theta.shape[0]
+        d = self.dims
+        desc = model_description(self.model)
+        fo = self.first_order(Theta)
+        ok = (fo["status"] == 0) | (fo["status"] == 5)          # 5: Lyapunov doubling did not converge = unit roots
+        n, nx, ny = d["n"], d["nx"], d["ny"]
+        Y = np.asarray(Y, dtype=np.float64)
+        nobs = Y.shape[1]
+        out = dict(alphah=np.full((N, nobs, n), np.nan), etah=np.full((N, nobs, nx), np.nan),
+                   epsilonh=np.full((N, nobs, ny), np.nan), loglik=np.full(N, -np.inf),
+                   n_diffuse=np.zeros(N, dtype=np.int32), n_unit_roots=np.zeros(N, dtype=np.int32), status=fo["status"].copy())
+        idx = np.flatnonzero(ok)
+        if idx.size == 0:
+            return out
+        se, sm = self.shock_covariances(Theta[idx])
+        T = np.zeros((idx.size, n, n))
+        T[:, :, desc["i_bkwrd_b"]] = fo["g1_1"][idx]
+        R = np.ascontiguousarray(fo["g1_2"][idx])
+        Pinf, Pstar, ku = diffuse_initial_covariances(T, R, se, device=self.device)
+        ybo = fo["ybar"][idx][:, desc["obs_idx"]]
+        Hd = np.ascontiguousarray(np.diagonal(sm, axis1=1, axis2=2))
+        r = kalman_diffuse_smoother_batch(Y, desc["obs_idx"], T, R, se, Pinf, Pstar, Hdiag=Hd, ybar_obs=ybo, tol=tol,
+                                          device=self.device)
+        out["alphah"][idx] = r["alphah"] + fo["ybar"][idx][:, None, :]
+        out["etah"][idx] = r["etah"]; out["epsilonh"][idx] = r["epsilonh"]
+        out["loglik"][idx] = r["loglik"]; out["n_diffuse"][idx] = r["n_diffuse"]; out["n_unit_roots"][idx] = ku
+        out["status"][idx] = r["status"]
+        return out
+
     def forecast(self, Theta, y0, periods):
         """Unconditional forecast (forecast.jl:54-159) for N draws from the levels y0 (N, n): (N, periods+1, n), status."""
         Theta = self._theta(Theta)
@@ -510,7 +556,8 @@ def diffuse_initial_covariances(T, R, Q, criterium=1 - 1e-6, device=0):
     return Pinf, Pstar, ks
 
 
-def kalman_diffuse_smoother_batch(Y, z_idx, T, R, Q, Pinf0, Pstar0, a0=None, Hdiag=None, tol=1e-8, device=0):
+def kalman_diffuse_smoother_batch(Y, z_idx, T, R, Q, Pinf0, Pstar0, a0=None, Hdiag=None, ybar_obs=None, tol=1e-8,
+                                  device=0):
     """Exact-diffuse batched filter + smoother (dyb_kalman_diffuse_smoother_batch): per-draw arrays as in
     kalman_smoother_batch, Hdiag (N, ny) or None.  Returns the same dict plus n_diffuse (N,)."""
     lib = L.load()
@@ -522,13 +569,14 @@ def kalman_diffuse_smoother_batch(Y, z_idx, T, R, Q, Pinf0, Pstar0, a0=None, Hdi
     cm = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).transpose(0, 2, 1))
     Tc, Rc, Qc, Pic, Psc = cm(T), cm(R), cm(Q), cm(Pinf0), cm(Pstar0)
     Hc = None if Hdiag is None else _f64(Hdiag, (n, ny))
+    ybc = None if ybar_obs is None else _f64(ybar_obs, (n, ny))
     a0c = None if a0 is None else _f64(a0, (n, ns))
     z = np.ascontiguousarray(z_idx, dtype=np.int32)
     Yf = np.asfortranarray(Y)
     al = np.empty((n, nobs, ns)); et = np.empty((n, nobs, nx)); ep = np.empty((n, nobs, ny)); at = np.empty((n, nobs, ns))
     ap = np.empty((n, nobs + 1, ns)); ll = np.empty(n); st = np.empty(n, dtype=np.int32); nd = np.empty(n, dtype=np.int32)
     L.check(lib.dyb_kalman_diffuse_smoother_batch(device, ns, ny, nx, nobs, L.ptr(z), L.ptr(Yf), L.ptr(Tc), L.ptr(Rc),
-                                                  L.ptr(Qc), L.ptr(Pic), L.ptr(Psc), L.ptr(a0c), L.ptr(Hc), float(tol), n,
+                                                  L.ptr(Qc), L.ptr(Pic), L.ptr(Psc), L.ptr(a0c), L.ptr(Hc), L.ptr(ybc), float(tol), n,
                                                   L.ptr(al), L.ptr(et), L.ptr(ep), L.ptr(at), L.ptr(ap), L.ptr(ll),
                                                   L.ptr(nd), L.ptr(st)))
     return dict(alphah=al, etah=et, epsilonh=ep, att=at, a_pred=ap, loglik=ll, n_diffuse=nd, status=st)

@@ -183,12 +183,16 @@ int dyb_kalman_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, in
  * so Finf may be rank deficient; Hdiag ny per draw (NULL = 0) is the diagonal of H.  A period is diffuse while
  * max diag(Pinf) > tol (the reference passes 1e-8, kalman.jl:211).  loglik is the diffuse log-likelihood
  * (Durbin & Koopman 2012, eq. 7.3), n_diffuse the number of diffuse periods; other arguments and outputs as in
- * dyb_kalman_smoother_batch; with Pinf0 = 0 the results are those of dyb_kalman_smoother_batch. */
+ * dyb_kalman_smoother_batch; ybar_obs ny per draw (NULL = 0) is subtracted from the observations; with Pinf0 = 0 the
+ * results are those of dyb_kalman_smoother_batch. */
 int dyb_kalman_diffuse_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, int32_t nobs, const int32_t* z_idx,
                                       const double* Y, const double* T, const double* R, const double* Q,
                                       const double* Pinf0, const double* Pstar0, const double* a0, const double* Hdiag,
-                                      double tol, int64_t n_draws, double* alphah, double* etah, double* epsilonh,
+                                      const double* ybar_obs, double tol, int64_t n_draws, double* alphah, double* etah, double* epsilonh,
                                       double* att, double* a_pred, double* loglik, int32_t* n_diffuse, int32_t* status);
+/* Sigma_e (nx x nx) and Sigma_m (ny x ny) of every draw as set_estimated_parameters! builds them
+ * (src/estimation/estimation.jl:517-601: stderr -> variance, corr -> covariance); either output may be NULL */
+int dyb_shock_covariances_batch(dyb_handle* h, const double* theta, int64_t n_draws, double* sigma_e, double* sigma_m);
 /* calibsmoother! (src/filters/kalman/kalman.jl:52-264) for N parameter draws: every endogenous variable is a state
  * (T[:, i_bkwrd_b] = g1_1, R = g1_2, P0 = endogenous_variance), observations detrended by the steady state; outputs in
  * LEVELS (steady state added back, kalman.jl:240-243): alphah n x nobs, etah nx x nobs, epsilonh ny x nobs per draw.

@@ -192,6 +192,14 @@ function smoother(ws::BatchSSWs, Θ::Matrix{Float64}, n, nx, ny, nobs)
         ws.handle, Θ, N, alphah, etah, epsh, ll, st))
     return alphah, etah, epsh, ll, st
 end
+"Σ_e (nx × nx × N) and Σ_m (ny × ny × N) of every column of Θ, as set_estimated_parameters! builds them (estimation.jl:517-601)."
+function shock_covariances(ws::BatchSSWs, Θ::Matrix{Float64}, nx, ny)
+    N = size(Θ, 2)
+    se = Array{Float64,3}(undef, nx, nx, N); sm = Array{Float64,3}(undef, ny, ny, N)
+    GC.@preserve Θ check(ccall((:dyb_shock_covariances_batch, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}), ws.handle, Θ, N, se, sm))
+    return se, sm
+end
 """
 The non-stationary branch of calibsmoother! (kalman.jl:163-223) for N state spaces sharing one data set.  `T` ns×ns×N,
 `R` ns×nx×N, `Q` nx×nx×N; `Pinf0`, `Pstar0` ns×ns×N in the ORIGINAL basis: with `F = Schur(gees!(...))` as at
@@ -200,18 +208,19 @@ kalman.jl:166-174 and `k` unit roots, `Pinf0 = F.Z[:, 1:k] * F.Z[:, 1:k]'`, `Pst
 """
 function diffuse_smoother(Y::Matrix{Float64}, z_idx::Vector{Int}, T::Array{Float64,3}, R::Array{Float64,3},
                           Q::Array{Float64,3}, Pinf0::Array{Float64,3}, Pstar0::Array{Float64,3};
-                          Hdiag = nothing, tol = 1e-8, device = 0)
+                          Hdiag = nothing, ybar_obs = nothing, tol = 1e-8, device = 0)
     ns, _, N = size(T); nx = size(R, 2); ny, nobs = size(Y)
     z0 = Int32.(z_idx .- 1)
     alphah = Array{Float64,3}(undef, ns, nobs, N); etah = Array{Float64,3}(undef, nx, nobs, N)
     epsh = Array{Float64,3}(undef, ny, nobs, N); att = similar(alphah); apred = Array{Float64,3}(undef, ns, nobs + 1, N)
     ll = Vector{Float64}(undef, N); nd = Vector{Int32}(undef, N); st = Vector{Int32}(undef, N)
     hd = Hdiag === nothing ? Ptr{Float64}(C_NULL) : pointer(Hdiag)
-    GC.@preserve Y z0 T R Q Pinf0 Pstar0 Hdiag check(ccall((:dyb_kalman_diffuse_smoother_batch, LIB), Cint,
+    yb = ybar_obs === nothing ? Ptr{Float64}(C_NULL) : pointer(ybar_obs)      # ny × N, subtracted from Y
+    GC.@preserve Y z0 T R Q Pinf0 Pstar0 Hdiag ybar_obs check(ccall((:dyb_kalman_diffuse_smoother_batch, LIB), Cint,
         (Cint, Int32, Int32, Int32, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-         Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
-        device, ns, ny, nx, nobs, z0, Y, T, R, Q, Pinf0, Pstar0, C_NULL, hd, tol, N, alphah, etah, epsh, att, apred, ll, nd, st))
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+        device, ns, ny, nx, nobs, z0, Y, T, R, Q, Pinf0, Pstar0, C_NULL, hd, yb, tol, N, alphah, etah, epsh, att, apred, ll, nd, st))
     return (; alphah, etah, epsilonh = epsh, att, a_pred = apred, loglik = ll, n_diffuse = nd, status = st)
 end
 "FiniteDiff.finite_difference_hessian(objective, x) (estimation.jl:873, 882) as ONE batched posterior evaluation."

@@ -103,6 +103,7 @@ static void ws_free(ws_t* w) {
   free(w->piv);
 }
 
+#define CR_UNIT_ROOT_EPS 1e-6
 typedef struct { double cr_tol; int cr_maxit; double steady_tol; double lyap_tol; int lyap_maxit; } opts_t;
 
 /* theta -> g1 (n x (k+nx)), ybar, Se, Sm; returns status */
@@ -197,8 +198,12 @@ static int solve_draw(const oracle_model* M, const opts_t* o, int np, const int*
       if (!(c2 <= m2)) m2 = c2;
     }
     if (!(m0 <= 1e150) || !(m2 <= 1e150)) { if (it == 1) status = ST_SOLVER; else stalled = 1; break; }
-    n0 = m0; n2 = m2;
-    if (n0 < o->cr_tol && n2 < o->cr_tol) { conv = 1; break; }
+    {
+      const double n0_prev = n0;
+      n0 = m0; n2 = m2;
+      /* unit roots among the stable roots: A0(j) settles on a non-zero limit while A2(j) vanishes */
+      if ((n0 < o->cr_tol && n2 < o->cr_tol) || (n2 < o->cr_tol * o->cr_tol && fabs(n0 - n0_prev) <= CR_UNIT_ROOT_EPS * n0)) { conv = 1; break; }
+    }
   }
   /* Blanchard-Kahn reading of a non-converging reduction: A0(j) not vanishing = too few stable roots
    * (UnstableSystemException); A2(j) not vanishing = too many (UndeterminateSystemException) */
@@ -272,6 +277,7 @@ static int variance(const oracle_model* M, const opts_t* o, ws_t* w) {
     double amax = 0;
     for (int i = 0; i < k * k; ++i) { Ak[i] = Tm[i]; if (fabs(Tm[i]) > amax) amax = fabs(Tm[i]); }
     if (dmax <= o->lyap_tol * smax && amax < 1.0) { conv = 1; break; }
+    if (it == 19 && amax >= 0.35) break;   /* a root within 1e-6 of the unit circle: (1 - 1e-6)^(2^20) = 0.35 */
     if (!isfinite(amax)) break;
   }
   if (!conv) return ST_NONSTATIONARY;

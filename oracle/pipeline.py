@@ -97,6 +97,9 @@ def solve_qz(A, B, C, criterium=QZ_CRITERIUM):
     return G, np.sort(mod)
 
 
+CR_UNIT_ROOT_EPS = 1e-6
+
+
 def solve_cr(A0, A1, A2, tol=1e-13, maxit=100):
     """Cyclic reduction for A0 + A1 X + A2 X^2 = 0 (Bini-Latouche-Meini; the algorithm of
     Dynare's ``cycle_reduction`` which PolynomialMatrixEquations mirrors).
@@ -130,8 +133,10 @@ def solve_cr(A0, A1, A2, tol=1e-13, maxit=100):
         A1chk = A1chk - W[:m, m:]
         A0 = -W[:m, :m]
         A2 = -W[m:, m:]
+        n0_prev = n0
         n0, n2 = m0, m2
-        if n0 < tol and n2 < tol:
+        # unit roots among the stable roots: A0(j) settles on a non-zero limit while A2(j) vanishes
+        if (n0 < tol and n2 < tol) or (n2 < tol * tol and abs(n0 - n0_prev) <= CR_UNIT_ROOT_EPS * n0):
             break
     else:
         # A0(j) ~ lambda_m^(2^j) not vanishing: too few stable roots; A2(j) not vanishing: too many
@@ -171,7 +176,7 @@ def compute_variance(model, sol, sigma_e):
     ib = model.i_bkwrd_b
     Gs = sol["g1_1"][ib, :]
     Bs = sol["g1_2"][ib, :]
-    if np.max(np.abs(np.linalg.eigvals(Gs))) >= 1.0:
+    if np.max(np.abs(np.linalg.eigvals(Gs))) > 1.0 - 1e-6:      # the reference's split (kalman.jl:172-180)
         raise DrawFailure(ST_NONSTATIONARY)
     Sig_s = sla.solve_discrete_lyapunov(Gs, Bs @ sigma_e @ Bs.T)
     Sig_s = 0.5 * (Sig_s + Sig_s.T)

@@ -58,4 +58,10 @@ for ns, ny, variant in ((12, 3, 1), (24, 5, 2), (40, 7, 2), (97, 6, 0)):
         kalman_smoother_batch(Y, np.arange(ny), T, np.tile(np.eye(ns)[:, :ny] * 0.1, (n, 1, 1)), np.tile(np.eye(ny), (n, 1, 1)), P)
     print("dense", ns, "ok")
 A = 0.5 * np.tile(np.eye(6), (4, 1, 1)); lyapunov_batch(A, np.tile(np.eye(6), (4, 1, 1)))
+# exact-diffuse filter / smoother: a random walk plus noise observed through a second state
+from dynare_jl_b200.engine import diffuse_initial_covariances, kalman_diffuse_smoother_batch   # noqa: E402
+Td = np.tile(np.array([[1.0, 0.0], [1.0, 0.0]]), (2, 1, 1)); Rd = np.tile(np.array([[1.0, 0.0], [1.0, 0.3]]), (2, 1, 1))
+Qd = np.tile(np.eye(2), (2, 1, 1))
+Pinf, Pstar, _ = diffuse_initial_covariances(Td, Rd, Qd)
+kalman_diffuse_smoother_batch(rng.standard_normal((1, 9)), [1], Td, Rd, Qd, Pinf, Pstar)
 print("all ok")

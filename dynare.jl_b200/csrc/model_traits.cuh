@@ -43,6 +43,79 @@ constexpr double CR_UNIT_ROOT_EPS = 1e-6;
 constexpr int LYAP_UNIT_ROOT_IT = 19;
 constexpr double LYAP_UNIT_ROOT_NORM = 0.35;
 
+// Newton's method on the static model of M (generated static_fj / static_resid_ss), for models without a closed-form
+// steady state: full steps, halved while they do not reduce the sum of squared residuals; y holds the starting point
+// on entry and the steady state on exit, NaN when the iteration fails (the caller's residual check then gives status 1).
+// The reference solves the same system with a trust-region solver from the same point
+// (src/steady_state/SteadyState.jl:183-252); both stop far below its acceptance threshold cbrt(eps).
+constexpr int NEWTON_MAXIT = 50;
+constexpr double NEWTON_TOL = 1e-13;
+constexpr int NEWTON_HALVINGS = 30;
+constexpr double NEWTON_STEP_TOL = 1e-6;
+constexpr double NEWTON_ESCAPE = 1e8;       // iterates larger than this multiple of the starting point: a root at infinity
+template <class M>
+DYB_HD void newton_steady_state(const double* __restrict__ p, double* __restrict__ y) {
+  constexpr int N = M::N;
+  double f[N], J[N * N], yt[N];
+  bool done = false;
+  double y0max = 1.0, last_step = 0.0;
+  for (int i = 0; i < N; ++i) y0max = y0max > fabs(y[i]) ? y0max : fabs(y[i]);
+  for (int it = 0; it < NEWTON_MAXIT && !done; ++it) {
+    for (int e = 0; e < N * N; ++e) J[e] = 0.0;
+    M::static_fj(p, y, f, J);
+    double fmax = 0.0, ymax = 0.0, g0 = 0.0;
+    bool finite = true;
+    for (int i = 0; i < N; ++i) {
+      finite = finite && (f[i] - f[i] == 0.0);
+      fmax = fmax > fabs(f[i]) ? fmax : fabs(f[i]);
+      ymax = ymax > fabs(y[i]) ? ymax : fabs(y[i]);
+      g0 += f[i] * f[i];
+    }
+    if (!finite || ymax > NEWTON_ESCAPE * y0max) break;
+    // small residuals AND a small last step: along a root at infinity (e.g. 1/c -> 0) the residuals shrink while the
+    // iterates keep doubling
+    if (fmax <= NEWTON_TOL * (1.0 + ymax) && last_step <= NEWTON_STEP_TOL * (1.0 + ymax)) { done = true; break; }
+    // solve J dy = -f by LU with partial pivoting (in place; f becomes dy)
+    bool singular = false;
+    for (int c = 0; c < N; ++c) {
+      int piv = c;
+      double best = fabs(J[c + N * c]);
+      for (int r = c + 1; r < N; ++r) if (fabs(J[r + N * c]) > best) { best = fabs(J[r + N * c]); piv = r; }
+      if (!(best > 0.0)) { singular = true; break; }
+      if (piv != c) {
+        for (int q = 0; q < N; ++q) { const double t = J[c + N * q]; J[c + N * q] = J[piv + N * q]; J[piv + N * q] = t; }
+        const double t = f[c]; f[c] = f[piv]; f[piv] = t;
+      }
+      const double inv = 1.0 / J[c + N * c];
+      for (int r = c + 1; r < N; ++r) {
+        const double l = J[r + N * c] * inv;
+        if (l != 0.0) {
+          for (int q = c + 1; q < N; ++q) J[r + N * q] -= l * J[c + N * q];
+          f[r] -= l * f[c];
+        }
+      }
+    }
+    if (singular) break;
+    for (int r = N - 1; r >= 0; --r) {
+      double x = -f[r];
+      for (int q = r + 1; q < N; ++q) x -= J[r + N * q] * f[q];
+      f[r] = x / J[r + N * r];
+    }
+    double t = 1.0;
+    bool accepted = false;
+    for (int h = 0; h < NEWTON_HALVINGS; ++h) {
+      for (int i = 0; i < N; ++i) yt[i] = y[i] + t * f[i];
+      const double g = M::static_resid_ss(p, yt);
+      if (g - g == 0.0 && g < g0) { accepted = true; break; }
+      t *= 0.5;
+    }
+    if (!accepted) break;
+    last_step = 0.0;
+    for (int i = 0; i < N; ++i) { last_step = last_step > fabs(yt[i] - y[i]) ? last_step : fabs(yt[i] - y[i]); y[i] = yt[i]; }
+  }
+  if (!done) for (int i = 0; i < N; ++i) y[i] = NAN;
+}
+
 // fast fp64 reciprocal square root: hardware seed (MUFU.RSQ64H, ~20 bits) + two Newton steps (<= 1 ulp for
 // normal inputs); callers guard non-positive / non-finite arguments separately
 DYB_D double fast_rsqrt(double x) {

@@ -84,6 +84,9 @@ class ModelSpec:
     ss_assign: List[Tuple[sp.Symbol, sp.Expr]] = field(default_factory=list)
     static_resid: List[sp.Expr] = field(default_factory=list)
     jac: Dict[Tuple[int, int], sp.Expr] = field(default_factory=dict)   # (row, compressed col) -> expr
+    # numerical steady state (no steady_state_model block): Newton from `initval` on the static model
+    ss_numeric: bool = False
+    static_jac: Dict[Tuple[int, int], sp.Expr] = field(default_factory=dict)   # (row, variable) -> d static_resid / d y
 
     # sizes ------------------------------------------------------------------------------
     @property
@@ -131,6 +134,7 @@ class ModelSpec:
             name=self.name, n=self.n, n_orig=self.n_orig, nx=self.nx, npar=len(self.params),
             k=self.k, nf=self.nf, s=self.s, m=self.m, ncol=self.ncol, ns=self.ns, ny=self.ny,
             nl=self.nl, np_est=self.np_est, linear=self.linear,
+            steady_state="numeric" if self.ss_numeric else "closed_form",
             endo=self.endo, exo=self.exo, params=self.params,
             param_values=[float(v) for v in self.param_values],
             lead_lag_incidence=self.lli.astype(int).tolist(),
@@ -260,6 +264,15 @@ def build_spec(name: str, mf: ModFile) -> ModelSpec:
             target = temps.setdefault(lhs, sp.Symbol(f"ss_{lhs}", real=True))
         ss_assign.append((target, parse(rhs, temps)))
         assigned.add(lhs)
+    # without a steady_state_model block a non-linear model gets its steady state from Newton's method on the static
+    # model, started at the `initval` block (the reference: `steady` -> solve_steady_state!,
+    # src/steady_state/SteadyState.jl:183-252); ss_assign then holds that starting point
+    ss_numeric = not mf.linear and not mf.steady_state_model
+    if ss_numeric:
+        for lhs, rhs in mf.initval:
+            if lhs in endo:
+                ss_assign.append((local[lhs], parse(rhs)))
+                assigned.add(lhs)
     for v in endo[:n_orig]:
         if v not in assigned:
             if mf.linear or not mf.steady_state_model:
@@ -277,6 +290,15 @@ def build_spec(name: str, mf: ModFile) -> ModelSpec:
     for u in usym:
         to_ss[u] = sp.Integer(0)
     static_resid = [r.subs(to_ss) for r in resid]
+    static_jac: Dict[Tuple[int, int], sp.Expr] = {}
+    if ss_numeric:
+        for i, r in enumerate(static_resid):
+            fs = r.free_symbols
+            for j, sym in enumerate(ysym):
+                if sym in fs:
+                    dd = sp.diff(r, sym)
+                    if dd != 0:
+                        static_jac[(i, j)] = dd
 
     k, nf = len(i_bkwrd_b), len(i_fwrd_b)
     cols: List[sp.Symbol] = [ym[j] for j in i_bkwrd_b] + list(ysym) + [yp[j] for j in i_fwrd_b] + usym
@@ -356,6 +378,7 @@ def build_spec(name: str, mf: ModFile) -> ModelSpec:
         est=list(mf.estimated_params), est_type=est_type, est_i=est_i, est_j=est_j,
         estimation_options=dict(mf.estimation_options),
         psym=psym, ysym=ysym, ss_assign=ss_assign, static_resid=static_resid, jac=jac,
+        ss_numeric=ss_numeric, static_jac=static_jac,
     )
 
 
@@ -367,6 +390,9 @@ def spec_from_file(name: str, path: str) -> ModelSpec:
 # =========================================================================================
 # numeric evaluation on the host (used by tests and by the host-evaluated-Jacobian entry point)
 # =========================================================================================
+NEWTON_MAXIT, NEWTON_TOL, NEWTON_HALVINGS, NEWTON_ESCAPE, NEWTON_STEP_TOL = 50, 1e-13, 30, 1e8, 1e-6   # as in csrc/model_traits.cuh
+
+
 class HostModel:
     """Lambdified steady state / static residuals / compressed Jacobian of a ``ModelSpec``."""
 
@@ -385,7 +411,47 @@ class HostModel:
 
     def steady_state(self, params) -> np.ndarray:
         with np.errstate(all="ignore"):
-            return np.array(self._ss(list(params)), dtype=np.float64)
+            y = np.array(self._ss(list(params)), dtype=np.float64)
+            if not self.spec.ss_numeric:
+                return y
+            return self._newton(list(params), y)
+
+    def _newton(self, p, y):
+        """The same iteration as newton_steady_state (csrc/model_traits.cuh): full Newton steps on the static model,
+        halved while they do not reduce the sum of squared residuals; stops on max|f| <= 1e-13 (1 + max|y|)."""
+        sp_ = self.spec
+        n = sp_.n
+        if not hasattr(self, "_sj"):
+            self._sjkeys = sorted(sp_.static_jac.keys())
+            self._sj = sp.lambdify([sp_.psym, sp_.ysym], [sp_.static_jac[kx] for kx in self._sjkeys], modules="numpy")
+        y0max = max(1.0, np.abs(y).max())
+        last_step = 0.0
+        for _ in range(NEWTON_MAXIT):
+            f = np.array(self._res(p, list(y)), dtype=np.float64)
+            if not np.all(np.isfinite(f)) or np.abs(y).max() > NEWTON_ESCAPE * y0max:      # NaN, or a root at infinity
+                return np.full(n, np.nan)
+            if np.abs(f).max() <= NEWTON_TOL * (1.0 + np.abs(y).max()) and last_step <= NEWTON_STEP_TOL * (1.0 + np.abs(y).max()):
+                return y
+            J = np.zeros((n, n))
+            for (r, c), v in zip(self._sjkeys, self._sj(p, list(y))):
+                J[r, c] = v
+            try:
+                dy = np.linalg.solve(J, -f)
+            except np.linalg.LinAlgError:
+                return np.full(n, np.nan)
+            g0 = f @ f
+            t = 1.0
+            for _h in range(NEWTON_HALVINGS):
+                yt = y + t * dy
+                ft = np.array(self._res(p, list(yt)), dtype=np.float64)
+                if np.all(np.isfinite(ft)) and ft @ ft < g0:
+                    break
+                t *= 0.5
+            else:
+                return np.full(n, np.nan)
+            last_step = np.abs(yt - y).max()
+            y = yt
+        return np.full(n, np.nan)
 
     def static_residuals(self, params, ybar) -> np.ndarray:
         with np.errstate(all="ignore"):
@@ -468,6 +534,21 @@ def _lower(spec: ModelSpec):
     jac_lines = [(str(a), pr(b), True) for a, b in jrep]
     jac_out = [(r, c, pr(e)) for (r, c), e in zip(keys, jred)]
     return ss_lines, res_lines, res_out, jac_lines, jac_out
+
+
+def _lower_static_fj(spec: ModelSpec):
+    """Static residuals and their Jacobian (n x n, column-major) as one straight-line block sharing subexpressions."""
+    pr = _Printer()
+    sub = {**{s_: sp.Symbol(f"p[{i}]") for i, s_ in enumerate(spec.psym)},
+           **{s_: sp.Symbol(f"y[{i}]") for i, s_ in enumerate(spec.ysym)}}
+    keys = sorted(spec.static_jac.keys(), key=lambda rc: (rc[1], rc[0]))
+    exprs = [r.subs(sub) for r in spec.static_resid] + [spec.static_jac[kx].subs(sub) for kx in keys]
+    rep, red = sp.cse(exprs, symbols=sp.numbered_symbols("s_"), optimizations="basic")
+    lines = [(str(a), pr(b)) for a, b in rep]
+    n = spec.n
+    f_out = [pr(e) for e in red[:n]]
+    j_out = [(r, c, pr(e)) for (r, c), e in zip(keys, red[n:])]
+    return lines, f_out, j_out
 
 
 def _int_list(v) -> str:
@@ -646,11 +727,32 @@ def emit_cuda(spec: ModelSpec) -> str:
     darr("sigma_e0", S.sigma_e0.T)
     darr("sigma_m0", S.sigma_m0.T)
     A("")
-    A("  // closed-form steady state (reference: generated steady_state!, src/dynare_functions.jl:39-41)")
-    A("  DYB_HD static void steady_state(const double* __restrict__ p, double* __restrict__ y) {")
-    for nm, ex, is_local in ss_lines:
-        A(f"    {'const double ' if is_local else ''}{nm} = {ex};")
-    A("  }")
+    if S.ss_numeric:
+        lines, f_out, j_out = _lower_static_fj(S)
+        A("  // numerical steady state: Newton's method on the static model from the initval point")
+        A("  // (reference: `steady` -> solve_steady_state!, src/steady_state/SteadyState.jl:183-252)")
+        A("  static constexpr bool NUMERIC_SS = true;")
+        A("  DYB_HD static void initval(const double* __restrict__ p, double* __restrict__ y) {")
+        for nm, ex, is_local in ss_lines:
+            A(f"    {'const double ' if is_local else ''}{nm} = {ex};")
+        A("  }")
+        A("  // f = static residuals, J = their Jacobian (N x N column-major, zero-initialised by the caller)")
+        A("  DYB_HD static void static_fj(const double* __restrict__ p, const double* __restrict__ y,")
+        A("                               double* __restrict__ f, double* __restrict__ J) {")
+        for nm, ex in lines:
+            A(f"    const double {nm} = {ex};")
+        for i, ex in enumerate(f_out):
+            A(f"    f[{i}] = {ex};")
+        for r, c, ex in j_out:
+            A(f"    J[{r + S.n * c}] = {ex};")
+        A("  }")
+        A("  DYB_HD static void steady_state(const double* __restrict__ p, double* __restrict__ y);")
+    else:
+        A("  // closed-form steady state (reference: generated steady_state!, src/dynare_functions.jl:39-41)")
+        A("  DYB_HD static void steady_state(const double* __restrict__ p, double* __restrict__ y) {")
+        for nm, ex, is_local in ss_lines:
+            A(f"    {'const double ' if is_local else ''}{nm} = {ex};")
+        A("  }")
     A("  // sum of squared static residuals at y (reference: check_steady_state, src/steady_state/SteadyState.jl:476-482)")
     A("  DYB_HD static double static_resid_ss(const double* __restrict__ p, const double* __restrict__ y) {")
     for nm, ex, _ in res_lines:
@@ -673,11 +775,18 @@ def emit_cuda(spec: ModelSpec) -> str:
     A(f"  static constexpr int JAC_NNZ = {len(jac_out)};")
     _emit_static_elim(S, jperm, jac_lines, jac_out, A, arr)
     A("};")
+    if S.ss_numeric:
+        A(f"DYB_HD void Model_{S.name}::steady_state(const double* __restrict__ p, double* __restrict__ y) {{")
+        A("  initval(p, y);")
+        A(f"  newton_steady_state<Model_{S.name}>(p, y);")
+        A("}")
     A("}  // namespace dyb")
     return "\n".join(L) + "\n"
 
 
 def emit_c(spec: ModelSpec) -> str:
+    if spec.ss_numeric:
+        raise NotImplementedError("the C restatement covers models with a closed-form steady state only")
     """Plain-C model functions + descriptor for the CPU oracle port (oracle/c)."""
     ss_lines, res_lines, res_out, jac_lines, jac_out = _lower(spec)
     S = spec

@@ -47,6 +47,7 @@ class ModFile:
     model_locals: List[Tuple[str, str]] = field(default_factory=list)  # `# name = expr;` inside the model block
     linear: bool = False
     steady_state_model: List[Tuple[str, str]] = field(default_factory=list)
+    initval: List[Tuple[str, str]] = field(default_factory=list)        # (name, expr): starting point of `steady`
     shock_stderr: Dict[str, str] = field(default_factory=dict)
     shock_var: Dict[str, str] = field(default_factory=dict)
     shock_corr: Dict[Tuple[str, str], str] = field(default_factory=dict)
@@ -287,7 +288,11 @@ def parse_mod(text: str) -> ModFile:
                 for ep in mf.estimated_params:
                     if (ep.kind, ep.name1, ep.name2) == key:
                         ep.init = _num(parts[1])
-            # other blocks (initval, histval, ...) are ignored
+            elif block == "initval":
+                if "=" in flat:
+                    lhs, rhs = flat.split("=", 1)
+                    mf.initval.append((lhs.strip(), rhs.strip()))
+            # other blocks (histval, endval, ...) are ignored
             continue
 
         m = re.match(r"(model|steady_state_model|shocks|estimated_params|estimated_params_init|"

@@ -158,3 +158,117 @@ def test_unit_root_model_smoother_matches_diffuse_oracle(built_ur):
         assert np.abs(out["alphah"][i].T - ref["alphah"]).max() <= 1e-9 * max(1.0, np.abs(ref["alphah"]).max())
         assert np.abs(out["etah"][i].T - ref["etah"]).max() <= 1e-9 * max(1.0, np.abs(ref["etah"]).max())
     ws.close()
+
+
+# ---- a model WITHOUT a steady_state_model block: Newton's method on the static model, on the device ------------------
+MOD_NUM = """
+var c k a y_obs;
+varexo e;
+parameters alpha beta delta rho sig;
+alpha = 0.33; beta = 0.99; delta = 0.025; rho = 0.9; sig = 0.01;
+model;
+  1/c = beta*(1/c(+1))*(alpha*exp(a(+1))*k^(alpha-1) + 1 - delta);
+  c + k = exp(a)*k(-1)^alpha + (1-delta)*k(-1);
+  a = rho*a(-1) + sig*e;
+  y_obs = exp(a)*k(-1)^alpha;
+end;
+initval;
+  k = 10; c = 1; a = 0; y_obs = 2;
+end;
+shocks;
+  var e; stderr 1;
+end;
+varobs y_obs;
+estimated_params;
+  alpha, beta_pdf, 0.33, 0.05;
+  rho, beta_pdf, 0.8, 0.1;
+  stderr e, inv_gamma_pdf, 1.0, inf;
+end;
+"""
+
+
+def _rbc_oracle():
+    """The same model written by hand for the oracle, with its closed-form steady state."""
+    from oracle.models import HandModel
+
+    class RBC(HandModel):
+        name = "rbcnum"
+        endo = ["c", "k", "a", "y_obs"]
+        exo = ["e"]
+        params = ["alpha", "beta", "delta", "rho", "sig"]
+        params0 = np.array([0.33, 0.99, 0.025, 0.9, 0.01])
+        sigma_e0 = np.array([[1.0]])
+        varobs = ["y_obs"]
+        lagged = ["k", "a"]
+        led = ["c", "a"]
+        est = [("param", "alpha"), ("param", "rho"), ("stderr", "e")]
+
+        def steady_state(self, p):
+            alpha, beta, delta = p[0], p[1], p[2]
+            k = ((1 / beta - 1 + delta) / alpha) ** (1 / (alpha - 1))
+            return np.array([k ** alpha - delta * k, k, 0.0, k ** alpha])
+
+        def dynamic_resid(self, ym, y, yp, u, p):
+            alpha, beta, delta, rho, sig = p
+            c, k, a, yo = y
+            return np.array([
+                1 / c - beta * (1 / yp[0]) * (alpha * np.exp(yp[2]) * k ** (alpha - 1) + 1 - delta),
+                c + k - np.exp(a) * ym[1] ** alpha - (1 - delta) * ym[1],
+                a - rho * ym[2] - sig * u[0],
+                yo - np.exp(a) * ym[1] ** alpha])
+    return RBC()
+
+
+@pytest.fixture(scope="module")
+def built_num(tmp_path_factory):
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("no nvcc")
+    from dynare_jl_b200 import build
+    d = tmp_path_factory.mktemp("nummodel")
+    mod = d / "rbcnum.mod"
+    mod.write_text(MOD_NUM)
+    return build.build_model_library("rbcnum", str(mod), str(d))
+
+
+def test_numeric_steady_state_host_mirror_finds_the_closed_form():
+    from dynare_jl_b200 import modelgen
+    from dynare_jl_b200.modfile import parse_mod
+    spec = modelgen.build_spec("rbcnum", parse_mod(MOD_NUM))
+    assert spec.ss_numeric and spec.describe()["steady_state"] == "numeric"
+    hm = modelgen.HostModel(spec)
+    m = _rbc_oracle()
+    for alpha in (0.33, 0.2, 0.45):
+        p = spec.param_values.copy(); p[0] = alpha
+        assert np.abs(hm.steady_state(p) - m.steady_state(p)).max() <= 1e-11 * np.abs(m.steady_state(p)).max()
+    p = spec.param_values.copy(); p[0] = 0.0                    # 1 = beta (1 - delta): no steady state, reported as NaN
+    assert not np.all(np.isfinite(hm.steady_state(p)))
+
+
+@pytest.mark.gpu
+def test_numeric_steady_state_model_matches_oracle(built_num):
+    """Steady state by Newton's method on the device (no steady_state_model block), then the usual path: policy
+    matrices and likelihood against the oracle run on the hand-written model with its closed-form steady state."""
+    from dynare_jl_b200.engine import BatchSSWs, load_model_library, model_description
+    from oracle import pipeline as pl
+    load_model_library(built_num)
+    assert model_description("rbcnum")["steady_state"] == "numeric"
+    m = _rbc_oracle()
+    rng = np.random.default_rng(4)
+    theta = np.column_stack([rng.uniform(0.2, 0.45, 40), rng.uniform(0.3, 0.97, 40), rng.uniform(0.5, 2.0, 40)])
+    Y = m.steady_state(m.params0)[3] + 0.05 * rng.standard_normal((1, 50))
+    ws = BatchSSWs("rbcnum", Y)
+    fo = ws.first_order(theta)
+    ll, st = ws.loglikelihood(theta)
+    assert np.all(st == 0) and np.all(fo["status"] == 0)
+    for i, th in enumerate(theta):
+        d = pl.solve_draw(m, th)
+        assert np.abs(fo["ybar"][i] - d["ybar"]).max() <= 1e-10 * np.abs(d["ybar"]).max()
+        assert np.abs(fo["g1_1"][i] - d["sol"]["g1_1"]).max() <= 1e-10 * max(1.0, np.abs(d["sol"]["g1_1"]).max())
+        assert np.abs(fo["g1_2"][i] - d["sol"]["g1_2"]).max() <= 1e-10 * max(1.0, np.abs(d["sol"]["g1_2"]).max())
+        ref, rst = pl.loglikelihood(m, th, Y)
+        assert rst == 0 and abs(ll[i] - ref) <= 1e-8 * abs(ref)
+    # a draw without a steady state is flagged, the others are unaffected
+    bad = theta.copy(); bad[3, 0] = 0.0
+    ll2, st2 = ws.loglikelihood(bad)
+    assert st2[3] == 1 and ll2[3] == -np.inf and np.all(st2[np.arange(40) != 3] == 0)
+    ws.close()

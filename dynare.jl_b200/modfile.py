@@ -204,6 +204,7 @@ def parse_mod(text: str) -> ModFile:
     for c in comments:
         if re.match(r"\s*estimation\s*\(", c):
             _parse_estimation_options(c.strip().rstrip(";"), mf.estimation_options)
+    clean = re.sub(r"(?m)^\s*using\s+[\w., ]+$", "", clean)          # Julia statements of the reference front end
     stmts = [s.strip() for s in clean.split(";")]
     block = None
     pending_shock: Optional[str] = None
@@ -254,6 +255,9 @@ def parse_mod(text: str) -> ModFile:
                 m = re.match(r"corr\s+(\w+)\s*,\s*(\w+)\s*=\s*(.+)$", flat)
                 if m:
                     mf.shock_corr[(m.group(1), m.group(2))] = m.group(3)
+                    continue
+                if re.match(r"(periods|values)\b", flat):
+                    pending_shock = None
                     continue
                 raise ValueError(f"unsupported shocks statement: {flat!r}")
             elif block == "estimated_params":
@@ -312,9 +316,10 @@ def parse_mod(text: str) -> ModFile:
         m = re.match(r"(std\s*\(\s*(\w+)\s*\)|corr\s*\(\s*(\w+)\s*,\s*(\w+)\s*\)|(\w+))\.prior\s*\((.*)\)$", flat)
         if m:
             kw = {}
-            for item in m.group(6).split(","):
-                k, v = item.split("=", 1)
-                kw[k.strip()] = v.strip()
+            for item in _split_top(m.group(6)):
+                if "=" in item:
+                    k, v = item.split("=", 1)
+                    kw[k.strip()] = v.strip()
             if m.group(2):
                 kind, n1, n2 = "stderr", m.group(2), None
             elif m.group(3):

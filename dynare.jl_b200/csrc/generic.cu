@@ -618,6 +618,15 @@ int dyb_prior_predictive_batch(dyb_handle* h, const double* theta, int64_t n, in
   return DYB_OK;
 }
 
+// persistent CTAs of the smoothers keep one period-by-period workspace each: fewer CTAs rather than more than
+// SMOOTHER_WORKSPACE_BYTES of scratch (ns = 96, T = 500 is 37 MB per CTA)
+constexpr size_t SMOOTHER_WORKSPACE_BYTES = (size_t)4 << 30;
+static long long cap_grid_by_workspace(long long grid, size_t bytes_per_cta) {
+  const long long fit = (long long)(SMOOTHER_WORKSPACE_BYTES / (bytes_per_cta ? bytes_per_cta : 1));
+  if (fit < 1) return 1;
+  return grid < fit ? grid : fit;
+}
+
 static int launch_smoother(KalmanSmootherArgs g, int device, cudaStream_t st, Stager& sg) {
   int dev_sms = 148, max_smem = 0;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
@@ -625,6 +634,7 @@ static int launch_smoother(KalmanSmootherArgs g, int device, cudaStream_t st, St
   const size_t smem = sizeof(double) * smoother_smem_doubles(g.ns, g.ny, g.nx);
   if (smem + 1024 > (size_t)max_smem) return fail(DYB_ERR_UNSUPPORTED, "state space too large for the shared-memory smoother");
   long long grid = g.n_draws < (long long)dev_sms * 4 ? g.n_draws : (long long)dev_sms * 4;
+  grid = cap_grid_by_workspace(grid, sizeof(double) * smoother_work_doubles(g.ns, g.ny, g.nobs));
   g.work = sg.temp<double>(smoother_work_doubles(g.ns, g.ny, g.nobs) * (size_t)grid);
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   if (smem > 48 * 1024) DYB_CUDA(cudaFuncSetAttribute(kalman_smoother_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -695,6 +705,7 @@ int dyb_kalman_diffuse_smoother_batch(int device, int32_t ns, int32_t ny, int32_
   const size_t smem = sizeof(double) * diffuse_smem_doubles(ns, nx);
   if (smem + 1024 > (size_t)max_smem) return fail(DYB_ERR_UNSUPPORTED, "state space too large for the shared-memory diffuse smoother");
   long long grid = n < (long long)dev_sms * 2 ? n : (long long)dev_sms * 2;
+  grid = cap_grid_by_workspace(grid, sizeof(double) * diffuse_work_doubles(ns, ny, nobs));
   g.work = sg.temp<double>(diffuse_work_doubles(ns, ny, nobs) * (size_t)grid);
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   if (smem > 48 * 1024) DYB_CUDA(cudaFuncSetAttribute(kalman_diffuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -198,12 +198,8 @@ static cudaError_t launch_moment2(const double* para, const double* w, const dou
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   const size_t smem = smc_moment2_smem_bytes(np);
   if (nb > 0 && smem + 1024 <= (size_t)max_smem) {
-    static int configured_for = -1;
-    if (configured_for < (int)smem) {
-      cudaError_t e = cudaFuncSetAttribute(smc_moment2_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
-      if (e != cudaSuccess) return e;
-      configured_for = max_smem;
-    }
+    cudaError_t e = cudaFuncSetAttribute(smc_moment2_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;                   // per device: set on every call (host-side, microseconds)
     unsigned groups = (unsigned)((296 + nb - 1) / nb);                       // about two CTAs per SM in total
     const unsigned maxg = (unsigned)((np * np + SMC_MOM_TILE - 1) / SMC_MOM_TILE);
     if (groups > maxg) groups = maxg;

@@ -7,6 +7,7 @@
 #include "kalman_generic.cuh"
 #include "kalman_dmma.cuh"
 #include "kalman_dmma_large.cuh"
+#include "kalman_lanes.cuh"
 #include "solve_generic.cuh"
 #include "kalman_smoother.cuh"
 #include "kalman_diffuse.cuh"
@@ -37,12 +38,31 @@ void generic_release(dyb_handle* h) {
 // launch the dense Kalman filter on device-resident state spaces (shared by dyb_kalman_batch and the
 // from-Jacobian likelihood); scratch (2 ns^2 doubles per CTA) only when P and T P do not fit in shared memory
 static int g_kalman_variant = 0;      // 0 auto, 1 scalar (kalman_generic.cuh), 2 tensor-core (kalman_dmma.cuh)
+static int g_kalman_lanes_max = 12;   // auto choice: sub-warp kernel up to this many states (13-16: spills, DMMA kernel wins)
 static int g_kalman_bulk = 1;         // large-ns kernel: stage the GEMM panels with cp.async.bulk when alignment allows
 
 static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaStream_t st, Stager& sg) {
   int dev_sms = 148, max_smem = 0;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  // small state spaces: four lanes per draw (kalman_lanes.cuh); variant 4 forces it, variants 1-3 bypass it
+  if (g.ns <= 16 && g.ny <= KLN_NY && (g_kalman_variant == 4 || (g_kalman_variant == 0 && g.ns <= g_kalman_lanes_max))) {
+    g.scratch = nullptr;
+    auto launch = [&](auto kern, size_t smem) -> cudaError_t {
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+      }
+      long long blocks = (g.n_draws + KLN_DRAWS - 1) / KLN_DRAWS;
+      const long long cap = (long long)dev_sms * 64;
+      if (blocks > cap) blocks = cap;
+      kern<<<(unsigned)blocks, KLN_G * KLN_DRAWS, smem, st>>>(g);
+      return cudaGetLastError();
+    };
+    if (g.ns <= 8) return launch(kalman_lanes_kernel<8>, KalmanLanesCfg<8>::SMEM_BYTES);
+    if (g.ns <= 12) return launch(kalman_lanes_kernel<12>, KalmanLanesCfg<12>::SMEM_BYTES);
+    return launch(kalman_lanes_kernel<16>, KalmanLanesCfg<16>::SMEM_BYTES);
+  }
   {
     const KalmanDmmaGeom q = kalman_dmma_geom(g.ns, g.ny);
     const size_t smem = sizeof(double) * kalman_dmma_smem_doubles(g.ns, g.ny);
@@ -369,7 +389,8 @@ int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t p
 
 
 int dyb_set_kalman_variant(int32_t variant) {
-  if (variant < 0 || variant > 3) return fail(DYB_ERR_ARG, "variant must be 0 (auto), 1 (scalar), 2 (tensor-core) or 3 (tensor-core, no bulk copies)");
+  if (variant < 0 || variant > 4)
+    return fail(DYB_ERR_ARG, "variant must be 0 (auto), 1 (scalar), 2 (tensor-core), 3 (tensor-core, no bulk copies) or 4 (sub-warp, ns <= 16)");
   g_kalman_bulk = variant != 3;
   g_kalman_variant = variant == 3 ? 2 : variant;
   return DYB_OK;

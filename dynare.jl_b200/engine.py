@@ -476,7 +476,8 @@ def fp64_peak_dmma(shape=0, device=0) -> float:
 
 
 def set_kalman_variant(variant: int):
-    """0 auto, 1 scalar dense filter kernel, 2 tensor-core (DMMA) kernel."""
+    """0 auto, 1 scalar dense filter kernel, 2 tensor-core (DMMA) kernel, 3 DMMA without bulk copies, 4 four lanes per draw
+    (ns <= 16, ny <= 8)."""
     L.check(L.load().dyb_set_kalman_variant(variant))
 
 

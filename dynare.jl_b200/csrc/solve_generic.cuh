@@ -51,13 +51,15 @@ struct Grp {
 
 // ---- group-cooperative dense helpers (column-major, all threads of the group must call) ---------------------
 template <int GSZ>
-DYB_D void blk_lu_factor(double* a, int n, int* piv, int* okflag) {
+__device__ __noinline__ void blk_lu_factor(double* a, int n, int* piv, int* okflag) {
   const Grp<GSZ> gp;
   const int tid = gp.tid, nt = gp.nt;
+  #pragma unroll 1
   for (int p = 0; p < n; ++p) {
     if (tid == 0) {
       int r = p;
       double best = fabs(a[p + n * p]);
+      #pragma unroll 1
       for (int i = p + 1; i < n; ++i) { const double v = fabs(a[i + n * p]); if (v > best) { best = v; r = i; } }
       piv[p] = r;
       if (!(best > 0.0) || !isfinite(best)) *okflag = 0;
@@ -68,9 +70,11 @@ DYB_D void blk_lu_factor(double* a, int n, int* piv, int* okflag) {
     if (r != p) for (int c = tid; c < n; c += nt) { const double t = a[p + n * c]; a[p + n * c] = a[r + n * c]; a[r + n * c] = t; }
     gp.sync();
     const double inv = 1.0 / a[p + n * p];
+    #pragma unroll 1
     for (int i = p + 1 + tid; i < n; i += nt) a[i + n * p] *= inv;
     gp.sync();
     const int w = n - p - 1;
+    #pragma unroll 1
     for (int e = tid; e < w * w; e += nt) {
       const int i = p + 1 + e % w, c = p + 1 + e / w;
       a[i + n * c] = fma(-a[i + n * p], a[p + n * c], a[i + n * c]);
@@ -81,15 +85,20 @@ DYB_D void blk_lu_factor(double* a, int n, int* piv, int* okflag) {
 
 // solve L U x = P b for nrhs column-major right-hand sides in place: one thread per column
 template <int GSZ>
-DYB_D void blk_lu_solve(const double* lu, const int* piv, double* b, int n, int nrhs) {
+__device__ __noinline__ void blk_lu_solve(const double* lu, const int* piv, double* b, int n, int nrhs) {
   const Grp<GSZ> gp;
+  #pragma unroll 1
   for (int c = gp.tid; c < nrhs; c += gp.nt) {
     double* x = b + n * c;
+    #pragma unroll 1
     for (int p = 0; p < n; ++p) { const int r = piv[p]; if (r != p) { const double t = x[p]; x[p] = x[r]; x[r] = t; } }
+    #pragma unroll 1
     for (int p = 0; p < n; ++p) { const double xp = x[p]; for (int i = p + 1; i < n; ++i) x[i] = fma(-lu[i + n * p], xp, x[i]); }
+    #pragma unroll 1
     for (int p = n - 1; p >= 0; --p) {
       const double xp = x[p] / lu[p + n * p];
       x[p] = xp;
+      #pragma unroll 1
       for (int i = 0; i < p; ++i) x[i] = fma(-lu[i + n * p], xp, x[i]);
     }
   }
@@ -99,15 +108,18 @@ DYB_D void blk_lu_solve(const double* lu, const int* piv, double* b, int n, int 
 // doubling solve of X = A X A' + B (k x k): on entry Ak = A, Sg = B; on exit Sg = X (symmetrised).
 // red: >= 4 doubles of shared scratch.  Returns 1 on convergence (same stopping rule as solve_kernel.cuh).
 template <int GSZ>
-DYB_D int blk_lyapunov(double* Ak, double* Sg, double* Tm, int k, double tol, int maxit, double* red, int* iters) {
+__device__ __noinline__ int blk_lyapunov(double* Ak, double* Sg, double* Tm, int k, double tol, int maxit, double* red, int* iters) {
   const Grp<GSZ> gp;
   const int tid = gp.tid, nt = gp.nt;
   int conv = 0, done = 0;
+  #pragma unroll 1
   for (int li = 0; li < maxit; ++li) {
     done = li + 1;
+    #pragma unroll 1
     for (int e = tid; e < k * k; e += nt) {
       const int i = e % k, j = e / k;
       double s = 0.0;
+      #pragma unroll 1
       for (int q = 0; q < k; ++q) s = fma(Ak[i + k * q], Sg[q + k * j], s);
       Tm[e] = s;
     }
@@ -115,9 +127,11 @@ DYB_D int blk_lyapunov(double* Ak, double* Sg, double* Tm, int k, double tol, in
     gp.sync();
     double dmax = 0.0, smax = 0.0;
     bool nan_seen = false;
+    #pragma unroll 1
     for (int e = tid; e < k * k; e += nt) {
       const int i = e % k, j = e / k;
       double s = 0.0;
+      #pragma unroll 1
       for (int q = 0; q < k; ++q) s = fma(Tm[i + k * q], Ak[j + k * q], s);
       const double v = Sg[e] + s;
       Sg[e] = v;
@@ -128,14 +142,17 @@ DYB_D int blk_lyapunov(double* Ak, double* Sg, double* Tm, int k, double tol, in
     atomicMax(reinterpret_cast<unsigned long long*>(&red[0]), (unsigned long long)__double_as_longlong(dmax));
     atomicMax(reinterpret_cast<unsigned long long*>(&red[1]), (unsigned long long)__double_as_longlong(nan_seen ? INFINITY : smax));
     gp.sync();
+    #pragma unroll 1
     for (int e = tid; e < k * k; e += nt) {
       const int i = e % k, j = e / k;
       double s = 0.0;
+      #pragma unroll 1
       for (int q = 0; q < k; ++q) s = fma(Ak[i + k * q], Ak[q + k * j], s);
       Tm[e] = s;
     }
     gp.sync();
     double amax = 0.0;
+    #pragma unroll 1
     for (int e = tid; e < k * k; e += nt) { const double v = Tm[e]; Ak[e] = v; amax = fmax(amax, isfinite(v) ? fabs(v) : INFINITY); }
     atomicMax(reinterpret_cast<unsigned long long*>(&red[2]), (unsigned long long)__double_as_longlong(amax));
     gp.sync();
@@ -148,11 +165,13 @@ DYB_D int blk_lyapunov(double* Ak, double* Sg, double* Tm, int k, double tol, in
   }
   if (iters) *iters = done;
   if (conv) {
+    #pragma unroll 1
     for (int e = tid; e < k * k; e += nt) {
       const int i = e % k, j = e / k;
       if (i > j) Tm[e] = 0.5 * (Sg[i + k * j] + Sg[j + k * i]);
     }
     gp.sync();
+    #pragma unroll 1
     for (int e = tid; e < k * k; e += nt) {
       const int i = e % k, j = e / k;
       if (i > j) { Sg[i + k * j] = Tm[e]; Sg[j + k * i] = Tm[e]; }
@@ -217,6 +236,7 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
   double& n0_sh = scal[1];
   double& n2_sh = scal[2];
 
+  #pragma unroll 1
   for (long long d = (long long)blockIdx.x * ngroups + grp; d < a.n_draws; d += (long long)gridDim.x * ngroups) {
     gp.sync();
     if (a.status_in && a.status_in[d] != ST_OK) {
@@ -229,21 +249,25 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
     if (tid == 0) { okflag = 1; red[0] = 0.0; }
     gp.sync();
     double chk = 0.0;
+    #pragma unroll 1
     for (int e = tid; e < n * NCOL; e += nt) {
       const double v = J[e];
       chk = fma(v, 0.0, chk);
       W[(e % n) + n * gm.jperm[e / n]] = v;
     }
+    #pragma unroll 1
     for (int e = tid; e < nx * nx; e += nt) { const double v = a.sigma_e[(size_t)d * a.stride_se + e]; Se[e] = v; chk = fma(v, 0.0, chk); }
     if (!(chk == 0.0)) okflag = 0;
     gp.sync();
     if (!okflag) status = ST_STEADY;
 
     // ---- Householder QR on the static columns, applied to every other column ------------------------------
+    #pragma unroll 1
     for (int j = 0; j < S && status == ST_OK; ++j) {
       double* col = W + n * j;
       if (tid == 0) {
         double nrm2 = 0.0;
+        #pragma unroll 1
         for (int i = j; i < n; ++i) nrm2 = fma(col[i], col[i], nrm2);
         red[0] = nrm2;
       }
@@ -254,12 +278,15 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
       const double alpha = col[j] >= 0.0 ? -nrm : nrm;
       const double vj = col[j] - alpha;
       const double beta = 2.0 / (2.0 * (nrm2 - alpha * col[j]));
+      #pragma unroll 1
       for (int c = j + 1 + tid; c < NCOL; c += nt) {
         double* x = W + n * c;
         double dot = vj * x[j];
+        #pragma unroll 1
         for (int i = j + 1; i < n; ++i) dot = fma(col[i], x[i], dot);
         dot *= beta;
         x[j] = fma(-dot, vj, x[j]);
+        #pragma unroll 1
         for (int i = j + 1; i < n; ++i) x[i] = fma(-dot, col[i], x[i]);
       }
       gp.sync();
@@ -270,16 +297,23 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
     // ---- cyclic reduction on the MM x MM dynamic block --------------------------------------------------------
     int it = 0;
     if (status == ST_OK) {
+      #pragma unroll 1
       for (int e = tid; e < MM * K; e += nt) { const int r = e % MM, j = e / MM; A0[e] = W[S + r + n * (cC + j)]; acc_hat[e] = 0.0; }
+      #pragma unroll 1
       for (int e = tid; e < MM * NF; e += nt) { const int r = e % MM, j = e / MM; A2[e] = W[S + r + n * (cA + j)]; }
+      #pragma unroll 1
       for (int e = tid; e < MM * MM; e += nt) { const int r = e % MM, c = e / MM; A1[e] = W[S + r + n * (cB + c)]; }
       if (tid == 0) { n0_sh = 0.0; n2_sh = 0.0; }
       gp.sync();
       bool conv = false, stalled = false;
       double n0 = 0.0, n2 = 0.0;
+      #pragma unroll 1
       for (it = 1; it <= a.cr_maxit; ++it) {
+        #pragma unroll 1
         for (int e = tid; e < MM * MM; e += nt) LU[e] = A1[e];
+        #pragma unroll 1
         for (int e = tid; e < MM * K; e += nt) X[e] = A0[e];
+        #pragma unroll 1
         for (int e = tid; e < MM * NF; e += nt) X[MM * K + e] = A2[e];
         if (tid == 0) okflag = 1;
         gp.sync();
@@ -290,56 +324,73 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
         const double* X0 = X;
         const double* X2 = X + MM * K;
         // A1 forward columns -= A0 X2[bk,:] ; A1 backward columns -= A2 X0[fw,:] (also accumulated in acc_hat)
+        #pragma unroll 1
         for (int e = tid; e < MM * NF; e += nt) {
           const int r = e % MM, j = e / MM;
           double s = 0.0;
+          #pragma unroll 1
           for (int i = 0; i < K; ++i) s = fma(A0[r + MM * i], X2[gm.bkwrd_in_dyn[i] + MM * j], s);
           LU[e] = s;                                     // LU is free after the solve: staging
         }
         gp.sync();
+        #pragma unroll 1
         for (int e = tid; e < MM * NF; e += nt) { const int r = e % MM, j = e / MM; A1[r + MM * gm.fwrd_in_dyn[j]] -= LU[e]; }
         gp.sync();
+        #pragma unroll 1
         for (int e = tid; e < MM * K; e += nt) {
           const int r = e % MM, j = e / MM;
           double s = 0.0;
+          #pragma unroll 1
           for (int i = 0; i < NF; ++i) s = fma(A2[r + MM * i], X0[gm.fwrd_in_dyn[i] + MM * j], s);
           LU[e] = s;
         }
         gp.sync();
+        #pragma unroll 1
         for (int e = tid; e < MM * K; e += nt) { const int r = e % MM, j = e / MM; A1[r + MM * gm.bkwrd_in_dyn[j]] -= LU[e]; acc_hat[e] += LU[e]; }
         gp.sync();
         // A0 <- -A0 X0[bk,:] ; A2 <- -A2 X2[fw,:]
+        #pragma unroll 1
         for (int e = tid; e < MM * K; e += nt) {
           const int r = e % MM, j = e / MM;
           double s = 0.0;
+          #pragma unroll 1
           for (int i = 0; i < K; ++i) s = fma(A0[r + MM * i], X0[gm.bkwrd_in_dyn[i] + MM * j], s);
           LU[e] = -s;
         }
         gp.sync();
+        #pragma unroll 1
         for (int e = tid; e < MM * K; e += nt) A0[e] = LU[e];
         gp.sync();
+        #pragma unroll 1
         for (int e = tid; e < MM * NF; e += nt) {
           const int r = e % MM, j = e / MM;
           double s = 0.0;
+          #pragma unroll 1
           for (int i = 0; i < NF; ++i) s = fma(A2[r + MM * i], X2[gm.fwrd_in_dyn[i] + MM * j], s);
           LU[e] = -s;
         }
         gp.sync();
+        #pragma unroll 1
         for (int e = tid; e < MM * NF; e += nt) A2[e] = LU[e];
         gp.sync();
         // 1-norms (largest column sum), sequential per column so the value does not depend on the launch geometry
+        #pragma unroll 1
         for (int j = tid; j < K + NF; j += nt) {
           const double* c = j < K ? A0 + MM * j : A2 + MM * (j - K);
           double cs = 0.0;
+          #pragma unroll 1
           for (int r = 0; r < MM; ++r) cs += fabs(c[r]);
           red[j] = cs;
         }
         gp.sync();
         if (tid == 0) {
           double m0 = 0.0, m2 = 0.0;
+          #pragma unroll 1
           for (int j = 0; j < K; ++j) m0 = fmax(m0, red[j]);
+          #pragma unroll 1
           for (int j = 0; j < NF; ++j) m2 = fmax(m2, red[K + j]);
           bool bad = false;
+          #pragma unroll 1
           for (int j = 0; j < K + NF; ++j) bad = bad || !(red[j] <= 1e150);
           n0_sh = bad ? NAN : m0; n2_sh = m2;
         }
@@ -360,8 +411,10 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
 
     if (status == ST_OK) {
       // ---- G (dynamic rows, backward columns) = -A1hat^-1 A0(0) ------------------------------------------------
+      #pragma unroll 1
       for (int e = tid; e < MM * MM; e += nt) { const int r = e % MM, c = e / MM; LU[e] = W[S + r + n * (cB + c)]; }
       gp.sync();
+      #pragma unroll 1
       for (int e = tid; e < MM * K; e += nt) { const int r = e % MM, j = e / MM; LU[r + MM * gm.bkwrd_in_dyn[j]] -= acc_hat[e]; Gd[e] = -W[S + r + n * (cC + j)]; }
       if (tid == 0) okflag = 1;
       gp.sync();
@@ -373,14 +426,18 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
     gp.sync();
     if (status == ST_OK) {
       // ---- g_u = -(A G + B)^-1 F_u on the dynamic block ---------------------------------------------------------
+      #pragma unroll 1
       for (int e = tid; e < MM * MM; e += nt) { const int r = e % MM, c = e / MM; LU[e] = W[S + r + n * (cB + c)]; }
       gp.sync();
+      #pragma unroll 1
       for (int e = tid; e < MM * K; e += nt) {
         const int r = e % MM, j = e / MM;
         double s = 0.0;
+        #pragma unroll 1
         for (int i = 0; i < NF; ++i) s = fma(W[S + r + n * (cA + i)], Gd[gm.fwrd_in_dyn[i] + MM * j], s);
         LU[r + MM * gm.bkwrd_in_dyn[j]] += s;
       }
+      #pragma unroll 1
       for (int e = tid; e < MM * nx; e += nt) { const int r = e % MM, q = e / MM; gud[e] = -W[S + r + n * (cU + q)]; }
       if (tid == 0) okflag = 1;
       gp.sync();
@@ -392,9 +449,11 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
     gp.sync();
     if (status == ST_OK && S > 0) {
       // ---- static rows by back-substitution: R_s y_s + B_top y_d + A_top y_f(+1) + C_top y_b(-1) + Fu_top u = 0 ---
+      #pragma unroll 1
       for (int e = tid; e < NF * (K + nx); e += nt) {
         const int i = e % NF, c = e / NF;
         double s = 0.0;
+        #pragma unroll 1
         for (int q = 0; q < K; ++q) {
           const double g = (c < K) ? Gd[gm.bkwrd_in_dyn[q] + MM * c] : gud[gm.bkwrd_in_dyn[q] + MM * (c - K)];
           s = fma(Gd[gm.fwrd_in_dyn[i] + MM * q], g, s);
@@ -403,16 +462,22 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
       }
       if (tid == 0) okflag = 1;
       gp.sync();
+      #pragma unroll 1
       for (int c = tid; c < K + nx; c += nt) {
         const double* gcol = (c < K) ? (Gd + MM * c) : (gud + MM * (c - K));
+        #pragma unroll 1
         for (int q = 0; q < S; ++q) {
           double s = (c < K) ? W[q + n * (cC + c)] : W[q + n * (cU + (c - K))];
+          #pragma unroll 1
           for (int dd = 0; dd < MM; ++dd) s = fma(W[q + n * (cB + dd)], gcol[dd], s);
+          #pragma unroll 1
           for (int i = 0; i < NF; ++i) s = fma(W[q + n * (cA + i)], GG[i + NF * c], s);
           gst[q + S * c] = -s;
         }
+        #pragma unroll 1
         for (int q = S - 1; q >= 0; --q) {
           double s = gst[q + S * c];
+          #pragma unroll 1
           for (int r = q + 1; r < S; ++r) s = fma(-W[q + n * r], gst[r + S * c], s);
           const double dg = W[q + n * q];
           if (dg == 0.0) okflag = 0;
@@ -425,6 +490,7 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
     gp.sync();
     if (status == ST_OK && a.g1) {
       double* g1 = a.g1 + (size_t)d * n * (K + nx);
+      #pragma unroll 1
       for (int e = tid; e < n * (K + nx); e += nt) {
         const int v = e % n, c = e / n;
         const int pos = gm.var_pos[v];
@@ -435,19 +501,25 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
     // ---- Lyapunov doubling on the K x K predetermined block -----------------------------------------------------
     int lyap_it = 0;
     if (status == ST_OK) {
+      #pragma unroll 1
       for (int e = tid; e < K * K; e += nt) { const int i = e % K, j = e / K; Ak[e] = Gd[gm.bkwrd_in_dyn[i] + MM * j]; }
+      #pragma unroll 1
       for (int e = tid; e < K * nx; e += nt) { const int i = e % K, q = e / K; Bs[e] = gud[gm.bkwrd_in_dyn[i] + MM * q]; }
       gp.sync();
+      #pragma unroll 1
       for (int e = tid; e < K * nx; e += nt) {
         const int i = e % K, q = e / K;
         double s = 0.0;
+        #pragma unroll 1
         for (int f = 0; f < nx; ++f) s = fma(Bs[i + K * f], Se[f + nx * q], s);
         BQ[e] = s;
       }
       gp.sync();
+      #pragma unroll 1
       for (int e = tid; e < K * K; e += nt) {
         const int i = e % K, j = e / K;
         double s = 0.0;
+        #pragma unroll 1
         for (int q = 0; q < nx; ++q) s = fma(BQ[i + K * q], Bs[j + K * q], s);
         Sg[e] = s;
       }
@@ -458,6 +530,7 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
 
     // ---- dense state space (estimation.jl:640-658) -----------------------------------------------------------------
     if (status == ST_OK) {
+      #pragma unroll 1
       for (int e = tid; e < NS * (K + nx); e += nt) {
         const int sI = e % NS, c = e / NS;
         const int v = gm.state_ids[sI];
@@ -466,15 +539,19 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
         if (c < K) g1s[sI + NS * c] = val; else g2s[sI + NS * (c - K)] = val;
       }
       gp.sync();
+      #pragma unroll 1
       for (int e = tid; e < NS * nx; e += nt) {
         const int sI = e % NS, q = e / NS;
         double s = 0.0;
+        #pragma unroll 1
         for (int f = 0; f < nx; ++f) s = fma(g2s[sI + NS * f], Se[f + nx * q], s);
         RQ[e] = s;
       }
+      #pragma unroll 1
       for (int e = tid; e < NS * K; e += nt) {
         const int sI = e % NS, j = e / NS;
         double s = 0.0;
+        #pragma unroll 1
         for (int q = 0; q < K; ++q) s = fma(g1s[sI + NS * q], Sg[q + K * j], s);
         GS[e] = s;
       }
@@ -485,12 +562,15 @@ solve_generic_kernel(GenericModel gm, GenericSolveArgs a, int per_draw_doubles) 
       if (To) for (int e = tid; e < NS * NS; e += nt) To[e] = 0.0;
       gp.sync();
       if (To) for (int e = tid; e < NS * K; e += nt) { const int sI = e % NS, j = e / NS; To[sI + NS * gm.lagged_state[j]] = g1s[e]; }
+      #pragma unroll 1
       for (int e = tid; e < NS * NS; e += nt) {
         const int sI = e % NS, t = e / NS;
         if (sI < t) continue;
         double qq = 0.0;
+        #pragma unroll 1
         for (int q = 0; q < nx; ++q) qq = fma(RQ[sI + NS * q], g2s[t + NS * q], qq);
         double pp = qq;
+        #pragma unroll 1
         for (int j = 0; j < K; ++j) pp = fma(GS[sI + NS * j], g1s[t + NS * j], pp);
         if (Qo) { Qo[sI + NS * t] = qq; Qo[t + NS * sI] = qq; }
         if (Po) { Po[sI + NS * t] = pp; Po[t + NS * sI] = pp; }
@@ -514,12 +594,15 @@ __global__ void __launch_bounds__(128) lyapunov_generic_kernel(LyapunovArgs a) {
   extern __shared__ double sm[];
   const int k = a.k, tid = threadIdx.x, nt = blockDim.x;
   double* Ak = sm; double* Sg = Ak + k * k; double* Tm = Sg + k * k; double* red = Tm + k * k;
+  #pragma unroll 1
   for (long long d = blockIdx.x; d < a.n_draws; d += gridDim.x) {
     __syncthreads();
+    #pragma unroll 1
     for (int e = tid; e < k * k; e += nt) { Ak[e] = a.A[(size_t)d * k * k + e]; Sg[e] = a.B[(size_t)d * k * k + e]; }
     __syncthreads();
     int it = 0;
     const int conv = blk_lyapunov<128>(Ak, Sg, Tm, k, a.tol, a.maxit, red, &it);
+    #pragma unroll 1
     for (int e = tid; e < k * k; e += nt) a.X[(size_t)d * k * k + e] = conv ? Sg[e] : NAN;
     if (tid == 0) { a.status[d] = conv ? ST_OK : ST_NONSTATIONARY; if (a.iters) a.iters[d] = it; }
   }

@@ -254,8 +254,9 @@ DYB_D void dmma_panel_steps(double (&c)[2][DL_NTP][2], int n0, const double* Ap0
 //   Cneg (may be null): -C is also written there (leading dimension nsp), its column zero_col as zero
 // The filter's rank-ny correction rides inside the products:  K = T U' and a' = T (a + U'w) are one thin product
 // T [U' | a + U'w], and  P' = [T P | K] [T | -K]' + R Q R'  is one product with inner dimension nsp + nxp.
-template <bool SYMM>
-DYB_D void block_gemm_dmma_bulk(const double* Ag, const double* Bg, int ldb_g, const double* Bg2, int ldb_g2,
+// SYMM is a run-time flag and the kernel calls this function from ONE site inside a loop over its three products: three
+// inlined copies of the tile-path switch were ~400 KB of code and the kernel stalled on instruction fetch.
+DYB_D void block_gemm_dmma_bulk(const bool SYMM, const double* Ag, const double* Bg, int ldb_g, const double* Bg2, int ldb_g2,
                                 int ksplit, int nsp, int ncols, int kdim,
                                 const double* Cinit, double* Cg, int ldc, double* Cneg, int zero_col,
                                 double* stage0, int stage_doubles, unsigned long long* bars, unsigned& phases) {
@@ -496,14 +497,18 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
     const double* Hm = g.H ? g.H + (size_t)d * ny * ny : nullptr;
     const double* yb = g.ybar_obs ? g.ybar_obs + (size_t)d * ny : nullptr;
     if (tid == 0) bad = 0;
+    #pragma unroll 1
     for (int i = tid; i < ny; i += nt) zi[i] = g.z_idx[i];
+    #pragma unroll 1
     for (int e = tid; e < nsp * nsp; e += nt) {
       const int i = e % nsp, j = e / nsp;
       // lower triangle mirrored: the bulk path reads P by rows (P = P')
       P[e] = (i < ns && j < ns) ? (i >= j ? P0[i + (size_t)ns * j] : P0[j + (size_t)ns * i]) : 0.0;
     }
+    #pragma unroll 1
     for (int e = tid; e < ldu * nsp; e += nt) U[e] = 0.0;
     if (BULK) for (int e = tid; e < nsp * nxp; e += nt) PxT[e] = 0.0;
+    #pragma unroll 1
     for (int i = tid; i < nsp; i += nt) { a[i] = (g.a0 && i < ns) ? g.a0[(size_t)d * ns + i] : 0.0; au[i] = 0.0; }
     __syncthreads();
     double acc = 0.0;          // only thread 0's copy is used
@@ -520,10 +525,12 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
       __syncthreads(); c0 = clock64();
 #endif
       const double* yt = g.Y + (size_t)t * ny;
+      #pragma unroll 1
       for (int i = tid; i < ny; i += nt) {
         const double yi = yt[i];
         v[i] = isnan(yi) ? 0.0 : (yi - (yb ? yb[i] : 0.0)) - a[zi[i]];
       }
+      #pragma unroll 1
       for (int e = tid; e < ny * ny; e += nt) {
         const int i = e % ny, j = e / ny;
         const bool mi = isnan(yt[i]), mj = isnan(yt[j]);
@@ -559,10 +566,12 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
           if (tid == 0) { if (!(djj > 0.0)) bad = 1; F[j + ny * j] = sqrt(djj); }
           __syncwarp();
           const double ljj = F[j + ny * j];
+          #pragma unroll 1
           for (int i = j + 1 + tid; i < ny; i += 32) F[i + ny * j] /= ljj;
           __syncwarp();
           for (int c = j + 1; c < ny; ++c) {
             const double lcj = F[c + ny * j];
+            #pragma unroll 1
             for (int i = c + tid; i < ny; i += 32) F[i + ny * c] -= F[i + ny * j] * lcj;
           }
           __syncwarp();
@@ -594,6 +603,7 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
         else if (ny <= 24) usolve_regs<24>(tid, nt, ns, ny, yt, zi, P, nsp, F, rdv, w, a, au, PxT, nxp);
         else usolve_regs<32>(tid, nt, ns, ny, yt, zi, P, nsp, F, rdv, w, a, au, PxT, nxp);
       } else {
+        #pragma unroll 1
         for (int s = tid; s < ns; s += nt) {
           double x = a[s];
           for (int i = 0; i < ny; ++i) {
@@ -612,26 +622,37 @@ __global__ void __launch_bounds__(512, 1) kalman_dmma_large_kernel(KalmanGeneric
       KL_MARK(1)
       if (BULK) {
         // M = T P (P symmetric: B by rows = P itself) ; [K | a'] = T [U' | a + U'w] ; P' = [M | K] [T | -K]' + R Q R'
-        block_gemm_dmma_bulk<false>(Tm, P, nsp, nullptr, 0, nsp, nsp, nsp, nsp, nullptr, Mx, nsp, nullptr, -1,
-                                    As0, panel_doubles, bars, phases);
-        block_gemm_dmma_bulk<false>(Tm, PxT, nxp, nullptr, 0, nsp, nsp, nxp, nsp, nullptr, Mx + (size_t)nsp * nsp, nsp,
-                                    Kneg, ny, As0, panel_doubles, bars, phases);
-        __syncthreads();
-        KL_MARK(2)
-        for (int i = tid; i < ns; i += nt) a[i] = Mx[i + (size_t)nsp * (nsp + ny)];
-        block_gemm_dmma_bulk<true>(Mx, Tm, ns, Kneg, nsp, nsp, nsp, nsp, nsp + nxp, QQ, P, nsp, nullptr, -1,
-                                   As0, panel_doubles, bars, phases);
+#pragma unroll 1
+        for (int prod = 0; prod < 3; ++prod) {
+          const bool symm = prod == 2;
+          const double* Ag = prod == 2 ? Mx : Tm;
+          const double* Bg = prod == 0 ? P : (prod == 1 ? PxT : Tm);
+          const int ldb = prod == 0 ? nsp : (prod == 1 ? nxp : ns);
+          const int ncols = prod == 1 ? nxp : nsp;
+          const int kdim = prod == 2 ? nsp + nxp : nsp;
+          double* Cg = prod == 0 ? Mx : (prod == 1 ? Mx + (size_t)nsp * nsp : P);
+          block_gemm_dmma_bulk(symm, Ag, Bg, ldb, Kneg, nsp, nsp, nsp, ncols, kdim, prod == 2 ? QQ : nullptr, Cg, nsp,
+                               prod == 1 ? Kneg : nullptr, prod == 1 ? ny : -1, As0, panel_doubles, bars, phases);
+          if (prod == 1) {
+            __syncthreads();
+            KL_MARK(2)
+#pragma unroll 1
+            for (int i = tid; i < ns; i += nt) a[i] = Mx[i + (size_t)nsp * (nsp + ny)];
+          }
+        }
         __syncthreads();
         KL_MARK(3)
         continue;
       }
       // a <- T au
+      #pragma unroll 1
       for (int i = tid; i < ns; i += nt) {
         double x = 0.0;
         for (int p = 0; p < ns; ++p) x = fma(Tm[i + (size_t)ns * p], au[p], x);
         a[i] = x;
       }
       // P <- P - U'U, tile by tile (full matrix; both triangles get identical sums)
+      #pragma unroll 1
       for (int tl = warp; tl < ntile * ntile; tl += nw) {
         const int i0 = 8 * (tl % ntile), j0 = 8 * (tl / ntile);
         double c0 = P[(i0 + gq) + (size_t)nsp * (j0 + 2 * tq)], c1 = P[(i0 + gq) + (size_t)nsp * (j0 + 2 * tq + 1)];

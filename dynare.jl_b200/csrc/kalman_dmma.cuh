@@ -127,7 +127,7 @@ DYB_D bool chol_warp_rot(double* F, int ny, const double* v, double* w, double* 
 }
 // out of line, so that the NY doubles of a matrix row do not compete with the caller's accumulators for registers
 template <int NY>
-__noinline__ DYB_D bool chol_warp_call(double* F, int ny, const double* v, double* w, double* rdv, double* quad_ldet) {
+__device__ __noinline__ bool chol_warp_call(double* F, int ny, const double* v, double* w, double* rdv, double* quad_ldet) {
   double quad, ldet;
   const bool ok = chol_warp_rot<NY>(F, ny, v, w, rdv, quad, ldet);
   quad_ldet[0] = quad; quad_ldet[1] = ldet;

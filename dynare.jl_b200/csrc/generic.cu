@@ -38,30 +38,30 @@ void generic_release(dyb_handle* h) {
 // launch the dense Kalman filter on device-resident state spaces (shared by dyb_kalman_batch and the
 // from-Jacobian likelihood); scratch (2 ns^2 doubles per CTA) only when P and T P do not fit in shared memory
 static int g_kalman_variant = 0;      // 0 auto, 1 scalar (kalman_generic.cuh), 2 tensor-core (kalman_dmma.cuh)
-static int g_kalman_lanes_max = 12;   // auto choice: sub-warp kernel up to this many states (13-16: spills, DMMA kernel wins)
+static int g_kalman_lanes_max = 16;   // auto choice: sub-warp kernel up to this many states
 static int g_kalman_bulk = 1;         // large-ns kernel: stage the GEMM panels with cp.async.bulk when alignment allows
 
 static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaStream_t st, Stager& sg) {
   int dev_sms = 148, max_smem = 0;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  // small state spaces: four lanes per draw (kalman_lanes.cuh); variant 4 forces it, variants 1-3 bypass it
+  // small state spaces: four (ns <= 12) or eight lanes per draw (kalman_lanes.cuh); variant 4 forces it, variants 1-3 bypass it
   if (g.ns <= 16 && g.ny <= KLN_NY && (g_kalman_variant == 4 || (g_kalman_variant == 0 && g.ns <= g_kalman_lanes_max))) {
     g.scratch = nullptr;
-    auto launch = [&](auto kern, size_t smem) -> cudaError_t {
+    auto launch = [&](auto kern, size_t smem, int draws_per_cta) -> cudaError_t {
       if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
       }
-      long long blocks = (g.n_draws + KLN_DRAWS - 1) / KLN_DRAWS;
+      long long blocks = (g.n_draws + draws_per_cta - 1) / draws_per_cta;
       const long long cap = (long long)dev_sms * 64;
       if (blocks > cap) blocks = cap;
-      kern<<<(unsigned)blocks, KLN_G * KLN_DRAWS, smem, st>>>(g);
+      kern<<<(unsigned)blocks, KLN_THREADS, smem, st>>>(g);
       return cudaGetLastError();
     };
-    if (g.ns <= 8) return launch(kalman_lanes_kernel<8>, KalmanLanesCfg<8>::SMEM_BYTES);
-    if (g.ns <= 12) return launch(kalman_lanes_kernel<12>, KalmanLanesCfg<12>::SMEM_BYTES);
-    return launch(kalman_lanes_kernel<16>, KalmanLanesCfg<16>::SMEM_BYTES);
+    if (g.ns <= 8) return launch(kalman_lanes_kernel<8, 4>, KalmanLanesCfg<8, 4>::SMEM_BYTES, KalmanLanesCfg<8, 4>::DRAWS);
+    if (g.ns <= 12) return launch(kalman_lanes_kernel<12, 4>, KalmanLanesCfg<12, 4>::SMEM_BYTES, KalmanLanesCfg<12, 4>::DRAWS);
+    return launch(kalman_lanes_kernel<16, 8>, KalmanLanesCfg<16, 8>::SMEM_BYTES, KalmanLanesCfg<16, 8>::DRAWS);
   }
   {
     const KalmanDmmaGeom q = kalman_dmma_geom(g.ns, g.ny);

@@ -1,5 +1,6 @@
-// Dense batched Kalman log-likelihood for SMALL state spaces of run-time size (ns <= 16, ny <= 8): four lanes per
-// draw, eight draws per warp.  A CTA of two warps per draw with six block barriers per period (kalman_dmma.cuh) is the
+// Dense batched Kalman log-likelihood for SMALL state spaces of run-time size (ns <= 16, ny <= 8): G = four lanes per
+// draw, eight draws per warp (eight lanes and four draws for 12 < ns <= 16, whose rows of T would not fit the registers
+// of four lanes).  A CTA of two warps per draw with six block barriers per period (kalman_dmma.cuh) is the
 // wrong mapping below ~16 states: the tiles are mostly padding and the warps mostly wait.  Here lane g of a draw owns
 // the rows / columns i = g, g + 4, ... : it keeps those rows of T in registers, the covariance lives in a per-draw
 // shared-memory tile, and the time update is two register-blocked products
@@ -14,23 +15,24 @@
 
 namespace dyb {
 
-constexpr int KLN_G = 4;              // lanes per draw
 constexpr int KLN_NY = 8;             // largest ny
-constexpr int KLN_DRAWS = 16;         // draws per CTA (64 threads)
+constexpr int KLN_THREADS = 64;       // threads per CTA: 64 / G draws
 
-template <int NSMAX>
+template <int NSMAX, int G>
 struct KalmanLanesCfg {
-  static constexpr int R = NSMAX / KLN_G;                        // owned rows per lane
+  static constexpr int R = NSMAX / G;                            // owned rows per lane
+  static constexpr int DRAWS = KLN_THREADS / G;                  // draws per CTA
   // per-draw tile: P, W (NSMAX^2 each), U (KLN_NY x NSMAX), a, au; padded to an odd number of doubles so that the
   // eight draws of a warp sit in distinct banks
   static constexpr int RAW = 2 * NSMAX * NSMAX + KLN_NY * NSMAX + 2 * NSMAX;
   static constexpr int TILE = RAW | 1;
-  static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)TILE * KLN_DRAWS;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)TILE * DRAWS;
 };
 
-template <int NSMAX>
-__global__ void __launch_bounds__(KLN_G * KLN_DRAWS) kalman_lanes_kernel(KalmanGenericArgs g) {
-  using Cfg = KalmanLanesCfg<NSMAX>;
+template <int NSMAX, int G>
+__global__ void __launch_bounds__(KLN_THREADS) kalman_lanes_kernel(KalmanGenericArgs g) {
+  using Cfg = KalmanLanesCfg<NSMAX, G>;
+  constexpr int KLN_G = G, KLN_DRAWS = Cfg::DRAWS;
   constexpr int R = Cfg::R;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ double sm[];

@@ -215,9 +215,9 @@ int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t p
                      const double* T, const double* RQR, const double* P0, const double* a0,
                      const double* H, int64_t n_draws, double* loglik, int32_t* status);
 
-/* which dense filter kernel dyb_kalman_batch / dyb_loglik_from_jacobian_batch use: 0 auto (four lanes per draw up to
- * ns = 12 and ny = 8, tensor-core kernels up to ns = 256, scalar kernel beyond), 1 scalar, 2 tensor-core (fp64 mma.sync),
- * 3 tensor-core with the large-ns kernel's cp.async.bulk panel staging switched off, 4 four lanes per draw (ns <= 16,
+/* which dense filter kernel dyb_kalman_batch / dyb_loglik_from_jacobian_batch use: 0 auto (four / eight lanes per draw up to
+ * ns = 16 and ny = 8, tensor-core kernels up to ns = 256, scalar kernel beyond), 1 scalar, 2 tensor-core (fp64 mma.sync),
+ * 3 tensor-core with the large-ns kernel's cp.async.bulk panel staging switched off, 4 lanes-per-draw kernel (ns <= 16,
  * ny <= 8 only); process-wide, for A/B tests */
 int dyb_set_kalman_variant(int32_t variant);
 

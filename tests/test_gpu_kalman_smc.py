@@ -29,13 +29,13 @@ def _random_state_space(rng, n, ns, ny, nx):
     # large kernel, bulk-staged path: ny a multiple of 8 (no spare column in the last tile), ny > 32 (shared-memory
     # Cholesky and substitution), ny = 1, 13 warps with an odd strip count; variant 3 = register-staged panels
     (104, 24, 8, 3, 0), (104, 36, 6, 2, 0), (96, 1, 12, 3, 0), (136, 16, 7, 2, 0), (200, 20, 6, 2, 3), (104, 36, 6, 2, 3),
-    # four lanes per draw (variant 4; the automatic choice up to ns = 12): every register-array size, ny up to 8,
+    # four / eight lanes per draw (variant 4; the automatic choice up to ns = 16): every register-array size, ny up to 8,
     # batch sizes that leave idle draw slots in the last CTA
     (10, 5, 79, 37, 0), (10, 5, 79, 37, 2), (12, 8, 30, 16, 4), (9, 8, 25, 5, 4), (16, 8, 20, 33, 4), (13, 1, 15, 4, 4),
     (1, 1, 12, 3, 0), (8, 3, 40, 100, 4)])
 def test_generic_kalman_matches_oracle(ns, ny, nobs, n, variant):
     """variant 1 = scalar kernel, 2 = tensor-core (DMMA) kernel, 4 = four lanes per draw, 0 = automatic choice (four lanes
-    per draw for ns <= 12, shared-memory DMMA kernel up to ns = 88, L2-scratch DMMA kernel for 88 < ns <= 256); sizes of BASELINE configs 4 (ns 40, ny 7) and 5 (ns 200,
+    per draw for ns <= 12, eight for ns <= 16, shared-memory DMMA kernel up to ns = 88, L2-scratch DMMA kernel for 88 < ns <= 256); sizes of BASELINE configs 4 (ns 40, ny 7) and 5 (ns 200,
     ny 20) included."""
     from dynare_jl_b200.engine import kalman_batch, set_kalman_variant
     set_kalman_variant(variant)

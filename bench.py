@@ -109,7 +109,7 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons = [], None, set()
-        allsm = []
+        allsm, pw = [], []
         for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -121,11 +121,16 @@ class ClockSampler:
             allsm.append(clk)
             if t0 - 0.05 <= ts <= t1 + 0.15:
                 sm.append(clk)
+                try:
+                    pw.append(float(f[3]))
+                except ValueError:
+                    pass
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         use = sm if sm else allsm
         return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": mx,
+                "sm_min_mhz": float(np.min(use)) if use else None, "power_w": float(np.median(pw)) if pw else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -178,28 +183,31 @@ def run_reference(args):
         return
     from oracle import cbuild
     Y = load_problem()
-    sample = 32768
-    theta = prior_draws(sample, 1)
+    sample = DRAWS_PER_GPU                                       # the GPU arm's step: 65 536 draws
+    pool = 4                                                     # distinct batches, rotated as the GPU arm does
+    theta = prior_draws(sample * pool, 1).reshape(pool, sample, -1)
     nth = host_cores()                                           # explicit: torchrun exports OMP_NUM_THREADS=1
     for _ in range(max(args.warmup, 1)):
-        cbuild.loglik_batch(MODEL, theta[:4096], Y, nthreads=nth)
+        cbuild.loglik_batch(MODEL, theta[0][:4096], Y, nthreads=nth)
     t = time.perf_counter()
     used = 1
-    for _ in range(args.steps):
-        _, _, used = cbuild.loglik_batch(MODEL, theta, Y, nthreads=nth)
+    for i in range(args.steps):
+        _, _, used = cbuild.loglik_batch(MODEL, theta[i % pool], Y, nthreads=nth)
     dt = time.perf_counter() - t
     val = args.steps * sample / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "draws_per_step": sample},
+        "config": {"workload": WORKLOAD, "draws_per_gpu": sample, "global_draws": sample},
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": used, "kind": "port",
                          "sample": f"{sample} prior draws per step x {args.steps} steps, C restatement of the "
-                                   f"reference likelihood loop (oracle/c), OpenMP, {used} threads"},
+                                   f"reference likelihood loop (oracle/c: cyclic reduction instead of the reference's QZ, "
+                                   f"hand-rolled dense kernels, gcc -O3 -march=native -ffp-contract=off), OpenMP, {used} threads"},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference is Julia (not installable offline); timed: its CPU likelihood loop restated in C",
+        "note": "reference is Julia (not installable offline); timed: its CPU likelihood loop restated in C "
+                "(vs C port, not vs upstream Julia)",
     }
     print(json.dumps(line))
 
@@ -217,8 +225,10 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        gloo = dist.new_group(backend="gloo")                   # host-side object exchange (NCCL id, results)
 
     Y = load_problem()
     # two handles on two streams: successive steps alternate between them, so two batches are in flight and the
@@ -336,6 +346,28 @@ def run_ours(args):
     for b in pin_in + pin_ll + pin_st:
         b.free()
 
+    # ---- secondary legs: sustained clocks, configs 3 / 4 / 5 (bench_legs.py) ----------------------------------------
+    import bench_legs as BL
+    from dynare_jl_b200.engine import fp64_peak_dmma
+    extra = {}
+    if not args.no_legs:
+        sus = BL.sustained_leg(step, n, world, args.sustained_s, ClockSampler, local, rank, barrier)
+        tsus = torch.tensor([sus["seconds"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tsus, op=dist.ReduceOp.MAX)
+        sus["seconds"] = tsus.item(); sus["evals_per_s"] = world * n * sus["steps"] / tsus.item()
+        extra["sustained"] = sus
+        if rank == 0:                                             # per-GPU figures (no collective): rank 0 measures
+            dpk = fp64_peak_dmma(0, local)
+            extra["config4"] = BL.dense_filter_leg(local, 40, 7, 200, 32768, 64, 2, 2, dpk)
+            extra["config5"] = BL.dense_filter_leg(local, 200, 20, 500, args.config5_draws, 8, 3, 1, dpk)
+            extra["config5"]["projected_seconds_262144_draws_8gpu"] = 32768 / extra["config5"]["evals_per_s"]
+        barrier()
+        smc_a = BL.smc_leg(local, rank, world, gloo, 16384, 400)
+        smc_b = BL.smc_leg(local, rank, world, gloo, 131072, 100)
+        extra["smc"] = {"config3_16384x400": smc_a, "large_131072x100": smc_b}
+        barrier()
+
     if rank == 0:
         d = ws.dims
         # iterations actually taken (batch means) for the algorithmic flop count of the solve
@@ -408,6 +440,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "clocks": clocks,
+            **extra,
         }
         if world == 1 and not args.no_cpu:
             rate, used, done = cpu_port_rate(Y, args.cpu_budget)
@@ -429,6 +462,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the sustained / config 3 / 4 / 5 legs")
+    ap.add_argument("--sustained-s", type=float, default=3.0)
+    ap.add_argument("--config5-draws", type=int, default=4096)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -1,0 +1,189 @@
+"""Secondary legs of bench.py: BASELINE.json configs 3, 4, 5 and a sustained-clock leg, reported as extra keys of the
+ONE JSON line (the fs2000 headline stays the line's `value`).
+
+  smc        ls2003 SMC (config 3): 16 384 particles x 400 stages and 131 072 particles x 100 stages, particles sharded
+             over the GPUs the bench was launched on, NCCL / peer exchange per stage, bit-identity with the 1-GPU run
+  config4    dense filter ns = 40, ny = 7, T = 200, 32 768 chains per GPU
+  config5    dense filter ns = 200, ny = 20, T = 500, >= 4 096 draws per GPU, actually executed
+  sustained  >= 3 s of back-to-back fs2000 batches with the SM clock and the board power sampled
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def w_kf(ns, ny):
+    """dense-formula flop of one Kalman period."""
+    return 4 * ns ** 3 + 2 * ny * ns ** 2 + 3 * ns ** 2 + 2 * ny ** 2 * ns + 2 * ny * ns + ny ** 3 / 3 + 3 * ny ** 2 + 4 * ny
+
+
+# ------------------------------------------------------------------------------------------------------------
+def synthetic_state_spaces(ns, ny, pool, seed):
+    """SURVEY 8(d) generator: T = Qo diag(lambda) Qo', lambda ~ U(0.3, 0.97); R ns x ny ~ N(0, 0.1^2); P0 from the
+    Lyapunov equation.  Returns column-major-per-draw arrays (pool, ns, ns)."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(seed)
+    T = np.empty((pool, ns, ns)); Q = np.empty_like(T); P = np.empty_like(T)
+    for i in range(pool):
+        Qo, _ = np.linalg.qr(rng.standard_normal((ns, ns)))
+        T[i] = Qo @ np.diag(rng.uniform(0.3, 0.97, ns)) @ Qo.T
+        R = 0.1 * rng.standard_normal((ns, ny))
+        Q[i] = R @ R.T
+        P[i] = sla.solve_discrete_lyapunov(T[i], Q[i])
+    return T, Q, P, rng
+
+
+def dense_filter_leg(local, ns, ny, nobs, n, pool, seed, reps, dmma_peak):
+    import torch
+    from dynare_jl_b200 import _lib as L
+    lib = L.load()
+    dev = torch.device("cuda", local)
+    T, Q, P, rng = synthetic_state_spaces(ns, ny, pool, seed)
+    Y = rng.standard_normal((ny, nobs))
+    rep = (n + pool - 1) // pool
+    cm = lambda x: torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 1))).to(dev).repeat(rep, 1, 1)[:n].contiguous()
+    dT, dQ, dP = cm(T), cm(Q), cm(P)
+    dH = torch.from_numpy(np.tile(0.01 * np.eye(ny), (n, 1, 1))).to(dev)
+    dY = torch.from_numpy(np.asfortranarray(Y).T.copy()).to(dev)
+    dz = torch.arange(ny, dtype=torch.int32, device=dev)
+    dll = torch.empty(n, dtype=torch.float64, device=dev); dst = torch.empty(n, dtype=torch.int32, device=dev)
+
+    def run(m):
+        L.check(lib.dyb_kalman_batch(local, ns, ny, nobs, 0, L.ptr(dz), L.ptr(dY), L.ptr(dT), L.ptr(dQ), L.ptr(dP), None,
+                                     L.ptr(dH), m, L.ptr(dll), L.ptr(dst)))
+    run(min(n, 296))                                             # warm-up (module load, attribute set-up)
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        t = time.perf_counter()
+        run(n)                                                   # the call synchronises (default stream of the device)
+        dt = time.perf_counter() - t
+        best = min(best, dt)
+    flop = w_kf(ns, ny) * nobs * n
+    ok = int((dst == 0).sum().item())
+    return {"workload": f"dense Kalman filter ns={ns} ny={ny} T={nobs}, {n} draws per GPU (inputs resident in HBM, "
+                        f"{pool} distinct state spaces tiled)",
+            "seconds": best, "evals_per_s": n / best, "algorithmic_tflops": flop / best / 1e12,
+            "dmma_peak_tflops": dmma_peak, "frac_of_dmma_peak": flop / best / 1e12 / dmma_peak if dmma_peak else None,
+            "ok_draws": ok, "timing": "host clock around the synchronous dyb_kalman_batch call with device pointers, best of "
+                                      f"{reps}"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def smc_leg(local, rank, world, gloo, npart, nphi, seed=3, check=True, profile=True):
+    """One full SMC recursion on ls2003 with `npart` particles over `world` GPUs; rank 0 returns the record."""
+    import torch.distributed as dist
+    from dynare_jl_b200.engine import BatchSSWs, model_description
+    from dynare_jl_b200.priors import PriorSet
+    from dynare_jl_b200.samplers import SMC, Communicator
+
+    model = "ls2003"
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{model}_golden.npz")))
+    pri = PriorSet.from_description(model_description(model)["priors"])
+    ws = BatchSSWs(model, g["Y"], device=local)
+    comm = Communicator.from_torch_distributed(ws, group=gloo) if world > 1 else None
+
+    rng = np.random.default_rng(seed)                             # every rank draws the SAME initial set
+    para0 = pri.sample(rng, npart)
+    while True:
+        _, st = ws.loglikelihood(para0)
+        bad = np.flatnonzero(st != 0)
+        if bad.size == 0:
+            break
+        para0[bad] = pri.sample(rng, bad.size)
+
+    def one_run(w_, first, n_local, prof):
+        s = SMC(w_, pri, npart=npart, nphi=nphi, seed=seed)
+        s.initialise(np.random.default_rng(0), para=para0[s.first:s.first + s.n_local].copy())
+        s.set_profiling(prof)
+        return s
+
+    out = {}
+    # timed run (no per-segment events), then a profiled run for the split
+    times = []
+    for prof in ([False, True] if profile else [False]):
+        s = one_run(ws, 0, 0, prof)
+        if world > 1:
+            dist.barrier(group=gloo)
+        ws.sync()
+        t0 = time.perf_counter()
+        s.run()
+        st = s.stats()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            box = [None] * world
+            dist.all_gather_object(box, dt, group=gloo)
+            dt = max(box)
+        if not prof:
+            out["seconds"] = dt
+            out["ms_per_stage"] = 1e3 * dt / (nphi - 1)
+            out["logmdd"] = st["logmdd"]
+            out["resamples"] = int(st["resampled"].sum())
+            part = s.particles()
+            stats_main = st["stats"].copy()
+        else:
+            tm = s.timing()
+            n_st = max(tm.pop("stages"), 1)
+            out["stage_split_ms_rank0"] = {k: v / n_st for k, v in tm.items()}
+            out["seconds_profiled_run"] = dt
+        s.close()
+    if check:
+        if world > 1:
+            boxes = [None] * world
+            dist.all_gather_object(boxes, part, group=gloo)
+            full = {k: np.concatenate([b[k] for b in boxes]) for k in part}
+        else:
+            full = part
+        if rank == 0:
+            ws1 = BatchSSWs(model, g["Y"], device=local)
+            s1 = SMC(ws1, pri, npart=npart, nphi=nphi, seed=seed)
+            s1.initialise(np.random.default_rng(0), para=para0.copy())
+            t0 = time.perf_counter()
+            s1.run()
+            st1 = s1.stats()
+            out["seconds_single_gpu_same_box"] = time.perf_counter() - t0
+            p1 = s1.particles()
+            same = all(np.array_equal(full[k], p1[k]) for k in full) and np.array_equal(stats_main, st1["stats"])
+            out["identical_to_single_gpu"] = bool(same)
+            s1.close(); ws1.close()
+        if world > 1:
+            dist.barrier(group=gloo)
+    if comm:
+        comm.close()
+    ws.close()
+    out = {"workload": f"ls2003 SMC, {npart} particles x {nphi} stages, multinomial resampling, particles sharded over "
+                       f"{world} GPU(s)", "n_gpus": world, **out}
+    return out if rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------------------------
+def sustained_leg(step, n_per_step, world, seconds, sampler_cls, local, rank, barrier):
+    """Back-to-back batches for `seconds`: throughput, median SM clock and power under sustained load."""
+    import torch
+    dev = torch.device("cuda", local)
+    barrier()
+    smp = sampler_cls(local)
+    if rank == 0:
+        smp.start()
+        time.sleep(0.2)
+    t0 = time.time()
+    tp0 = time.perf_counter()
+    i = 0
+    while True:
+        for _ in range(256):
+            step(i); i += 1
+        if time.perf_counter() - tp0 >= seconds:
+            break
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - tp0
+    t1 = time.time()
+    clk = smp.stop(t0, t1) if rank == 0 else None
+    return {"seconds": dt, "steps": i, "evals_per_s": world * n_per_step * i / dt, "clocks": clk,
+            "how": "the headline step repeated back to back (two handles / streams), host clock over the whole run"}

@@ -43,12 +43,12 @@ class Communicator:
         return buf.raw
 
     @classmethod
-    def from_torch_distributed(cls, ssws: BatchSSWs):
+    def from_torch_distributed(cls, ssws: BatchSSWs, group=None):
         """Bootstrap over an initialised torch.distributed group (any backend): rank 0's id is broadcast."""
         import torch.distributed as dist
-        rank, nranks = dist.get_rank(), dist.get_world_size()
+        rank, nranks = dist.get_rank(group), dist.get_world_size(group)
         box = [cls.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
+        dist.broadcast_object_list(box, src=0, group=group)
         return cls(ssws, rank, nranks, box[0])
 
     def close(self):

@@ -116,6 +116,7 @@ SIGNATURES = {
     "dyb_smc_create": (C.c_int, [_P, C.POINTER(SmcOptions), _D, C.POINTER(_P)]),
     "dyb_smc_destroy": (C.c_int, [_P]),
     "dyb_smc_local_range": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dyb_smc_transport": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dyb_smc_init": (C.c_int, [_P, _D, _I32]),
     "dyb_smc_run": (C.c_int, [_P, C.c_int32]),
     "dyb_smc_stages_done": (C.c_int, [_P]),

@@ -139,6 +139,7 @@ int dyb_create(const char* model, int device, dyb_handle** out) {
 
 int dyb_destroy(dyb_handle* h) {
   if (!h) return DYB_OK;
+  if (h->n_smc > 0) return fail(DYB_ERR_STATE, "dyb_destroy: a dyb_smc object is still attached to this handle (dyb_smc_destroy first)");
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   comm_release(h);
@@ -168,6 +169,7 @@ int dyb_set_options(dyb_handle* h, const dyb_options* opt) {
       opt->lyap_maxit < 1 || opt->presample < 0 || opt->solver < 0 || opt->solver > 2)
     return fail(DYB_ERR_ARG, "invalid option value");
   h->hs.opt = *opt;
+  h->config_epoch += 1;
   return DYB_OK;
 }
 
@@ -178,6 +180,7 @@ int dyb_set_calibration(dyb_handle* h, const double* params, const double* sigma
   if (params) h->hs.params.assign(params, params + d.npar);
   if (sigma_e) h->hs.sigma_e.assign(sigma_e, sigma_e + d.nx * d.nx);
   if (sigma_m) h->hs.sigma_m.assign(sigma_m, sigma_m + d.ny * d.ny);
+  h->config_epoch += 1;
   return DYB_OK;
 }
 
@@ -197,6 +200,7 @@ int dyb_set_estimated_params(dyb_handle* h, int32_t np, const int32_t* kind, con
   }
   h->hs.np = np;
   for (int q = 0; q < np; ++q) { h->hs.est_type[q] = kind[q]; h->hs.est_i[q] = i1[q]; h->hs.est_j[q] = i2[q]; }
+  h->config_epoch += 1;
   return DYB_OK;
 }
 
@@ -211,6 +215,7 @@ int dyb_set_observations(dyb_handle* h, const double* Y, int32_t ny, int32_t nob
                                          is_device_ptr(Y) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
   DYB_CUDA(cudaStreamSynchronize(h->stream));
   h->ny_obs = ny; h->nobs = nobs;
+  h->config_epoch += 1;
   return DYB_OK;
 }
 
@@ -218,9 +223,11 @@ static cudaEvent_t* timer_slot(dyb_handle* h);
 static int reserve_batch(dyb_handle* h, int64_t n) {
   const dyb_model_dims& d = h->dims;
   const size_t N = (size_t)(n > 0 ? n : 1);
+  const void* before[3] = {h->d_ss.p, h->d_st1.p, h->d_mid.p};
   DYB_CUDA(h->d_ss.reserve(sizeof(double) * d.ss_doubles * N));
   DYB_CUDA(h->d_st1.reserve(sizeof(int) * N));
   DYB_CUDA(h->d_mid.reserve(sizeof(double) * (size_t)h->ops->mid_doubles * N));
+  if (before[0] != h->d_ss.p || before[1] != h->d_st1.p || before[2] != h->d_mid.p) h->config_epoch += 1;   // captured graphs hold the old addresses
   return DYB_OK;
 }
 
@@ -233,15 +240,19 @@ int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, dou
   int rc = reserve_batch(h, n);
   if (rc) return rc;
   SolveOut so{h->d_ss.as<double>(), h->d_st1.as<int>(), nullptr, nullptr, nullptr, nullptr, h->d_mid.as<double>()};
-  cudaEvent_t* ev = h->timers_armed ? timer_slot(h) : nullptr;
+  // inside a stream capture (the SMC stage graph) the timing events are left out: a captured record is no timestamp
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  DYB_CUDA(cudaStreamIsCapturing(h->stream, &cap));
+  const bool timed = cap == cudaStreamCaptureStatusNone;
+  cudaEvent_t* ev = (timed && h->timers_armed) ? timer_slot(h) : nullptr;
   if (ev) { h->timer_n += 1; so.ev_after_model = ev[3]; so.ev_after_cr = ev[4]; } else ev = h->ev;
-  DYB_CUDA(cudaEventRecord(ev[0], h->stream));
+  if (timed) DYB_CUDA(cudaEventRecord(ev[0], h->stream));
   DYB_CUDA(h->ops->solve(h->hs, d_theta, n, so, h->stream));
-  DYB_CUDA(cudaEventRecord(ev[1], h->stream));
+  if (timed) DYB_CUDA(cudaEventRecord(ev[1], h->stream));
   DYB_CUDA(h->ops->kalman(h->d_ss.as<double>(), n, h->d_Y.as<double>(), h->nobs, h->hs.opt.presample,
                           h->d_st1.as<int>(), d_loglik, d_status, h->stream));
-  DYB_CUDA(cudaEventRecord(ev[2], h->stream));
-  h->ev_valid = (ev == h->ev);
+  if (timed) DYB_CUDA(cudaEventRecord(ev[2], h->stream));
+  h->ev_valid = timed && (ev == h->ev);
   h->launches += 1 + h->ops->solve_launches(h->hs);
   return DYB_OK;
 }
@@ -343,6 +354,7 @@ int dyb_set_stream(dyb_handle* h, void* cuda_stream) {
   DYB_CUDA(cudaSetDevice(h->device));
   DYB_CUDA(cudaStreamSynchronize(h->stream));
   h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  h->config_epoch += 1;
   return DYB_OK;
 }
 

@@ -160,4 +160,6 @@ struct dyb_handle {
   // samplers (sampler.cu)
   std::vector<dyb::PriorDev> priors;    // one per estimated parameter once dyb_set_priors has been called
   dyb::Comm* comm = nullptr;
+  int n_smc = 0;                        // dyb_smc objects attached (dyb_destroy refuses while > 0)
+  long long config_epoch = 0;           // bumped by every setter: invalidates captured CUDA graphs
 };

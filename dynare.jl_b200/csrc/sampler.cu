@@ -2,10 +2,12 @@
 // the SMC tempering recursion with its particles resident on the device(s), random-walk Metropolis on many chains,
 // and the NCCL communicator that couples the particle shards of several GPUs.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <nccl.h>
 
 #include "internal.h"
 #include "sampler_kernels.cuh"
+#include "smc_stage.cuh"
 
 namespace dyb {
 
@@ -101,25 +103,55 @@ struct dyb_smc {
   long long npart = 0, first = 0, n_local = 0;
   int np = 0, nphi = 0, rank = 0, nranks = 1;
   std::vector<double> phi;
-  double trgt = 0.25, alp = 0.9;
+  double trgt = 0.25, alp = 0.9, c0 = 0.5, acpt0 = 0.25;
   int systematic = 0;
   unsigned long long seed = 0;
   int stage = 0;                 // stages completed (0 = not initialised, 1 = particles initialised, ...)
   bool profiling = false;
   std::vector<cudaEvent_t> tev;  // SMC_TSEG + 1 events per profiled stage
-  DevBuf para, loglh, logpost, w_g, wt_g, cw_g, bt, offs, scal, flag, tune, idx, para_g, loglh_g, logpost_g,
-      part_g, mu, R, L, rdiag, aux, err, prop, qx, q0, lx, st, priorx, acc_g, nclamp, stats;
+  // exchange of the mutated particles (smc_stage.cuh): peer stores into CUDA-IPC mapped slabs, or one ncclAllGather
+  bool p2p = false;              // peers' slabs are mapped into this process
+  bool published = false;        // the initial payload has reached every rank
+  unsigned long long epoch = 0;  // epoch base of the flags, advanced at every (re)start of the recursion
+  void* peer_slab[SMC_MAX_RANKS] = {};
+  size_t slab_bytes = 0, off_pay1 = 0, off_pub = 0, off_cnt = 0;
+  // one stage as a CUDA graph per payload parity (the launch sequence does not depend on the stage)
+  bool use_graph = true;
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  long long graph_cfg[2] = {-1, -1};
+  DevBuf slab, ctl, phi_d, w_g, wt_g, cwl, bt, bt2, btw, offs, idx, part1, part2, mu, R, L, rdiag, aux, prop, qx, q0,
+      lx, st, priorx, stats, tmp_para, tmp_ll, tmp_lp;
   void release() {
-    DevBuf* all[] = {&para, &loglh, &logpost, &w_g, &wt_g, &cw_g, &bt, &offs, &scal, &flag, &tune, &idx, &para_g,
-                     &loglh_g, &logpost_g, &part_g, &mu, &R, &L, &rdiag, &aux, &err, &prop, &qx, &q0, &lx, &st,
-                     &priorx, &acc_g, &nclamp, &stats};
+    DevBuf* all[] = {&slab, &ctl, &phi_d, &w_g, &wt_g, &cwl, &bt, &bt2, &btw, &offs, &idx, &part1, &part2, &mu, &R, &L,
+                     &rdiag, &aux, &prop, &qx, &q0, &lx, &st, &priorx, &stats, &tmp_para, &tmp_ll, &tmp_lp};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : tev) cudaEventDestroy(e);
     tev.clear();
+    for (int k = 0; k < 2; ++k) if (graph[k]) { cudaGraphExecDestroy(graph[k]); graph[k] = nullptr; }
   }
 };
 // segments of a stage timed by dyb_smc_get_timing: correction, selection, moments + Cholesky, proposal, likelihood, accept
 constexpr int SMC_TSEG = 6;
+
+static SmcStageArgs stage_args(const dyb_smc* s) {
+  SmcStageArgs a{};
+  a.ctl = s->ctl.as<SmcCtl>(); a.phi = s->phi_d.as<double>();
+  for (int r = 0; r < SMC_MAX_RANKS; ++r) a.slab[r] = nullptr;
+  if (s->p2p) for (int r = 0; r < s->nranks; ++r) a.slab[r] = static_cast<char*>(s->peer_slab[r]);
+  a.slab[s->rank] = s->slab.as<char>();
+  a.off_pay1 = s->off_pay1; a.off_pub = s->off_pub; a.off_cnt = s->off_cnt;
+  a.nranks = s->nranks; a.rank = s->rank;
+  a.npub = s->p2p ? s->nranks : 1; a.nwait = s->p2p ? s->nranks : 0;
+  a.N = s->npart; a.n = s->n_local; a.first = s->first; a.np = s->np;
+  a.w = s->w_g.as<double>(); a.wt = s->wt_g.as<double>(); a.cwl = s->cwl.as<double>(); a.bt = s->bt.as<double>();
+  a.bt2 = s->bt2.as<double>(); a.btw = s->btw.as<double>(); a.offs = s->offs.as<double>(); a.idx = s->idx.as<long long>();
+  a.part1 = s->part1.as<double>(); a.part2 = s->part2.as<double>(); a.mu = s->mu.as<double>(); a.R = s->R.as<double>();
+  a.L = s->L.as<double>(); a.rdiag = s->rdiag.as<double>(); a.aux = s->aux.as<double>(); a.stats = s->stats.as<double>();
+  a.prop = s->prop.as<double>(); a.qx = s->qx.as<double>(); a.q0 = s->q0.as<double>();
+  a.lx = s->lx.as<double>(); a.status = s->st.as<int>();
+  a.seed = s->seed; a.systematic = s->systematic; a.trgt = s->trgt; a.alp = s->alp;
+  return a;
+}
 
 extern "C" {
 
@@ -320,6 +352,7 @@ int dyb_set_priors(dyb_handle* h, int32_t np, const int32_t* shape, const double
     pr[k] = p;
   }
   h->priors = pr;
+  h->config_epoch += 1;
   return DYB_OK;
 }
 
@@ -407,6 +440,57 @@ int dyb_smc_default_options(dyb_smc_options* o) {
   return DYB_OK;
 }
 
+// peer mappings of the payload slabs: every rank all-gathers its cudaIpcMemHandle_t through NCCL and opens the others'
+static int smc_map_peers(dyb_smc* s) {
+  dyb_handle* h = s->h;
+  NcclApi* api = nccl_api();
+  const int G = s->nranks;
+  struct Rec { cudaIpcMemHandle_t hnd; int device; int ok; };
+  static_assert(sizeof(Rec) % 8 == 0, "record size");
+  Rec mine{};
+  mine.device = h->device;
+  mine.ok = cudaIpcGetMemHandle(&mine.hnd, s->slab.p) == cudaSuccess ? 1 : 0;
+  if (!mine.ok) cudaGetLastError();
+  Rec* d_all = nullptr;
+  DYB_CUDA(cudaMalloc(&d_all, sizeof(Rec) * G));
+  DYB_CUDA(cudaMemcpyAsync(d_all + s->rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice, h->stream));
+  DYB_NCCL(api->AllGather(d_all + s->rank, d_all, sizeof(Rec), ncclChar, h->comm->comm, h->stream));
+  std::vector<Rec> all((size_t)G);
+  DYB_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Rec) * G, cudaMemcpyDeviceToHost, h->stream));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  int ok = 1;
+  for (int r = 0; r < G; ++r) ok = ok && all[r].ok;
+  for (int r = 0; r < G && ok; ++r) {
+    if (r == s->rank) { s->peer_slab[r] = s->slab.p; continue; }
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, h->device, all[r].device) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+    if (cudaIpcOpenMemHandle(&s->peer_slab[r], all[r].hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError(); s->peer_slab[r] = nullptr; ok = 0;
+    }
+  }
+  // every rank must take the same decision
+  int* d_ok = reinterpret_cast<int*>(d_all);
+  DYB_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  DYB_NCCL(api->AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm->comm, h->stream));
+  DYB_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  DYB_CUDA(cudaFree(d_all));
+  if (!ok) {
+    for (int r = 0; r < G; ++r) if (r != s->rank && s->peer_slab[r]) { cudaIpcCloseMemHandle(s->peer_slab[r]); s->peer_slab[r] = nullptr; }
+    cudaGetLastError();
+  }
+  s->p2p = ok != 0;
+  return DYB_OK;
+}
+
+// all ranks have finished everything enqueued so far (used before slabs are rewritten from scratch or unmapped)
+static int smc_rank_barrier(dyb_smc* s) {
+  dyb_handle* h = s->h;
+  if (s->nranks == 1 || !h->comm) return DYB_OK;
+  DYB_NCCL(nccl_api()->AllReduce(s->aux.p, s->aux.p, 1, ncclDouble, ncclSum, h->comm->comm, h->stream));
+  return DYB_OK;
+}
+
 int dyb_smc_create(dyb_handle* h, const dyb_smc_options* o, const double* phi, dyb_smc** out) {
   if (!h || !o || !out) return fail(DYB_ERR_ARG, "null argument");
   *out = nullptr;
@@ -414,6 +498,7 @@ int dyb_smc_create(dyb_handle* h, const dyb_smc_options* o, const double* phi, d
     return fail(DYB_ERR_ARG, "invalid SMC option");
   if ((int)h->priors.size() != h->hs.np) return fail(DYB_ERR_STATE, "dyb_set_priors must be called before dyb_smc_create");
   const int nranks = h->comm ? h->comm->nranks : 1, rank = h->comm ? h->comm->rank : 0;
+  if (nranks > SMC_MAX_RANKS) return fail(DYB_ERR_ARG, "at most 16 ranks");
   if (nranks > 1 && o->npart % ((long long)SMC_BLOCK * nranks) != 0)
     return fail(DYB_ERR_ARG, "with several ranks the particle count must be a multiple of 1024 * nranks");
   DYB_CUDA(cudaSetDevice(h->device));
@@ -421,34 +506,62 @@ int dyb_smc_create(dyb_handle* h, const dyb_smc_options* o, const double* phi, d
   s->h = h; s->npart = o->npart; s->nranks = nranks; s->rank = rank;
   s->n_local = o->npart / nranks; s->first = s->n_local * rank;
   s->np = h->hs.np; s->nphi = o->nphi; s->trgt = o->trgt; s->alp = o->alp; s->systematic = o->resampling; s->seed = o->seed;
+  s->c0 = o->c0; s->acpt0 = o->acpt0;
   s->phi.resize((size_t)o->nphi);
   for (int i = 0; i < o->nphi; ++i) s->phi[i] = phi ? phi[i] : std::pow((double)i / (double)(o->nphi - 1), o->lam);   // smc.jl:48
+  const char* eg = std::getenv("DYB_SMC_GRAPH");
+  s->use_graph = !(eg && eg[0] == '0');
   const size_t N = (size_t)s->npart, n = (size_t)s->n_local, np = (size_t)s->np;
   const size_t nb = (N + SMC_BLOCK - 1) / SMC_BLOCK;
+  const size_t pay = 8 * N * (np + 2);
+  s->off_pay1 = (pay + 255) / 256 * 256;
+  s->off_pub = 2 * s->off_pay1;
+  s->off_cnt = s->off_pub + 8 * SMC_MAX_RANKS;
+  s->slab_bytes = s->off_cnt + 8 * 2 * SMC_MAX_RANKS;
   cudaError_t e = cudaSuccess;
   auto R = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.reserve(bytes + 16); };
-  R(s->para, 8 * np * n); R(s->loglh, 8 * n); R(s->logpost, 8 * n); R(s->w_g, 8 * N); R(s->wt_g, 8 * N); R(s->cw_g, 8 * N);
-  R(s->bt, 8 * nb); R(s->offs, 8 * nb); R(s->scal, 16); R(s->flag, 4); R(s->tune, sizeof(SmcTune)); R(s->idx, 8 * n);
-  R(s->para_g, 8 * np * N); R(s->loglh_g, 8 * N); R(s->logpost_g, 8 * N); R(s->part_g, 8 * nb * np * np);
-  R(s->mu, 8 * np); R(s->R, 8 * np * np); R(s->L, 8 * np * np); R(s->rdiag, 8 * np); R(s->aux, 16); R(s->err, 4);
+  // the slab is a cudaMalloc allocation of its own (cudaIpcGetMemHandle covers whole allocations)
+  if (cudaMalloc(&s->slab.p, s->slab_bytes) == cudaSuccess) s->slab.cap = s->slab_bytes; else e = cudaGetLastError();
+  R(s->ctl, sizeof(SmcCtl)); R(s->phi_d, 8 * (size_t)o->nphi);
+  R(s->w_g, 8 * N); R(s->wt_g, 8 * N); R(s->cwl, 8 * N); R(s->bt, 8 * nb); R(s->bt2, 8 * nb); R(s->btw, 8 * nb); R(s->offs, 8 * nb);
+  R(s->idx, 8 * N); R(s->part1, 8 * nb * np); R(s->part2, 8 * nb * np * np);
+  R(s->mu, 8 * np); R(s->R, 8 * np * np); R(s->L, 8 * np * np); R(s->rdiag, 8 * np); R(s->aux, 16);
   R(s->prop, 8 * np * n); R(s->qx, 8 * n); R(s->q0, 8 * n); R(s->lx, 8 * n); R(s->st, 4 * n); R(s->priorx, 8 * n);
-  R(s->acc_g, 8 * (size_t)nranks); R(s->nclamp, 8); R(s->stats, 8 * SMC_STATS * (size_t)o->nphi);
-  if (e != cudaSuccess) { s->release(); delete s; return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
-  const SmcTune t0{o->c0, o->acpt0};
-  DYB_CUDA(cudaMemcpyAsync(s->tune.p, &t0, sizeof(t0), cudaMemcpyHostToDevice, h->stream));
-  DYB_CUDA(cudaMemsetAsync(s->err.p, 0, 4, h->stream));
-  DYB_CUDA(cudaMemsetAsync(s->nclamp.p, 0, 8, h->stream));
-  DYB_CUDA(cudaMemsetAsync(s->stats.p, 0, 8 * SMC_STATS * (size_t)o->nphi, h->stream));
-  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  R(s->stats, 8 * SMC_STATS * (size_t)o->nphi);
+  R(s->tmp_para, 8 * np * n); R(s->tmp_ll, 8 * n); R(s->tmp_lp, 8 * n);
+  int rc = DYB_OK;
+  if (e != cudaSuccess) rc = fail(DYB_ERR_CUDA, cudaGetErrorString(e));
+  auto CK = [&](cudaError_t x) { if (rc == DYB_OK && x != cudaSuccess) rc = fail(DYB_ERR_CUDA, cudaGetErrorString(x)); };
+  if (rc == DYB_OK) {
+    CK(cudaMemsetAsync(s->slab.p, 0, s->slab_bytes, h->stream));
+    CK(cudaMemsetAsync(s->ctl.p, 0, sizeof(SmcCtl), h->stream));
+    CK(cudaMemsetAsync(s->stats.p, 0, 8 * SMC_STATS * (size_t)o->nphi, h->stream));
+    CK(cudaMemsetAsync(s->aux.p, 0, 16, h->stream));
+    CK(cudaMemcpyAsync(s->phi_d.p, s->phi.data(), 8 * (size_t)o->nphi, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  if (rc == DYB_OK && nranks > 1) {
+    const char* et = std::getenv("DYB_SMC_TRANSPORT");
+    if (!(et && std::strcmp(et, "nccl") == 0)) rc = smc_map_peers(s);
+  }
+  if (rc != DYB_OK) { s->release(); delete s; return rc; }
+  h->n_smc += 1;
   *out = s;
   return DYB_OK;
 }
 
 int dyb_smc_destroy(dyb_smc* s) {
   if (!s) return DYB_OK;
-  cudaSetDevice(s->h->device);
-  cudaStreamSynchronize(s->h->stream);
+  dyb_handle* h = s->h;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (s->p2p) {
+    // nobody may still be storing into a slab that is about to go away
+    if (smc_rank_barrier(s) == DYB_OK) cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < s->nranks; ++r) if (r != s->rank && s->peer_slab[r]) cudaIpcCloseMemHandle(s->peer_slab[r]);
+  }
   s->release();
+  h->n_smc -= 1;
   delete s;
   return DYB_OK;
 }
@@ -460,9 +573,17 @@ int dyb_smc_local_range(const dyb_smc* s, int64_t* first, int64_t* n_local) {
   return DYB_OK;
 }
 
+// 1 when the mutated particles travel by peer stores (CUDA IPC over NVLink), 0 for the NCCL all-gather / single GPU
+int dyb_smc_transport(const dyb_smc* s, int32_t* peer_stores, int32_t* cuda_graph) {
+  if (!s) return fail(DYB_ERR_ARG, "null argument");
+  if (peer_stores) *peer_stores = s->p2p ? 1 : 0;
+  if (cuda_graph) *cuda_graph = (s->use_graph && !s->profiling) ? 1 : 0;
+  return DYB_OK;
+}
+
 // initial particles (smc.jl:84-101): the caller draws them from the prior; the likelihood, the prior density and
 // logpost = phi[1] * loglh + logprior are evaluated here.  status[i] != 0 marks draws the reference would reject
-// (obj = -Inf): replace them and call again.
+// (obj = -Inf): replace them and call again.  Local to the rank (no collective).
 int dyb_smc_init(dyb_smc* s, const double* para_local, int32_t* status) {
   if (!s || !para_local) return fail(DYB_ERR_ARG, "null argument");
   dyb_handle* h = s->h;
@@ -471,133 +592,172 @@ int dyb_smc_init(dyb_smc* s, const double* para_local, int32_t* status) {
   int rc = prior_set(h, &ps);
   if (rc) return rc;
   const long long n = s->n_local;
-  DYB_CUDA(cudaMemcpyAsync(s->para.p, para_local, 8 * (size_t)s->np * n, cudaMemcpyDefault, h->stream));
-  rc = dyb_loglik_batch_device(h, s->para.as<double>(), n, s->loglh.as<double>(), s->st.as<int>());
+  cudaStream_t st = h->stream;
+  DYB_CUDA(cudaMemcpyAsync(s->prop.p, para_local, 8 * (size_t)s->np * n, cudaMemcpyDefault, st));
+  rc = dyb_loglik_batch_device(h, s->prop.as<double>(), n, s->lx.as<double>(), s->st.as<int>());
   if (rc) return rc;
-  logprior_kernel<<<nblk(n, 128), 128, 0, h->stream>>>(ps, s->para.as<double>(), n, s->priorx.as<double>());
-  // logpost = phi[0] * loglh + prior, written with the accept kernel's arithmetic: phi * l + prior
-  smc_init_logpost_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(s->loglh.as<double>(), s->priorx.as<double>(), s->phi[0], n,
-                                                              s->logpost.as<double>());
-  smc_fill_kernel<<<nblk(s->npart, 256), 256, 0, h->stream>>>(s->w_g.as<double>(), s->npart, 1.0 / (double)s->npart);
+  logprior_kernel<<<nblk(n, 128), 128, 0, st>>>(ps, s->prop.as<double>(), n, s->priorx.as<double>());
+  const SmcStageArgs a = stage_args(s);
+  smc_init_pack_kernel<<<nblk(n, 256), 256, 0, st>>>(a, s->prop.as<double>(), s->lx.as<double>(), s->priorx.as<double>(), s->phi[0]);
+  smc_fill_kernel<<<nblk(s->npart, 256), 256, 0, st>>>(s->w_g.as<double>(), s->npart, 1.0 / (double)s->npart);
+  SmcCtl c0{};
+  c0.stage = 1; c0.tune = SmcTune{s->c0, s->acpt0};
+  DYB_CUDA(cudaMemcpyAsync(s->ctl.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, st));
   const double st0[SMC_STATS] = {1.0, (double)s->npart, 0.0, 0.0, 0.0, 0.0};
-  DYB_CUDA(cudaMemcpyAsync(s->stats.p, st0, sizeof(st0), cudaMemcpyHostToDevice, h->stream));
+  DYB_CUDA(cudaMemcpyAsync(s->stats.p, st0, sizeof(st0), cudaMemcpyHostToDevice, st));
   DYB_CUDA(cudaGetLastError());
   h->launches += 3;
-  if (status) DYB_CUDA(cudaMemcpyAsync(status, s->st.p, 4 * (size_t)n, cudaMemcpyDefault, h->stream));
-  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  if (status) DYB_CUDA(cudaMemcpyAsync(status, s->st.p, 4 * (size_t)n, cudaMemcpyDefault, st));
+  DYB_CUDA(cudaStreamSynchronize(st));
   s->stage = 1;
+  s->published = false;
   return DYB_OK;
 }
 
-// one tempering stage i (0-based, i >= 1): correction, selection, mutation (smc.jl:110-243); asynchronous
-static int smc_stage(dyb_smc* s, int i) {
+// in-place all-gather of the rows each rank wrote into payload buffer `par` of its own slab, and of the acceptance counts
+static int smc_nccl_exchange(dyb_smc* s, int par, bool counts) {
+  dyb_handle* h = s->h;
+  NcclApi* api = nccl_api();
+  double* pay = reinterpret_cast<double*>(s->slab.as<char>() + (par ? s->off_pay1 : 0));
+  const size_t chunk = (size_t)s->n_local * (s->np + 2);
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(s->slab.as<char>() + s->off_cnt) + par * SMC_MAX_RANKS;
+  int rc = DYB_OK;
+  ncclResult_t r0 = api->GroupStart();
+  ncclResult_t r1 = api->AllGather(pay + chunk * s->rank, pay, chunk, ncclDouble, h->comm->comm, h->stream);
+  ncclResult_t r2 = counts ? api->AllGather(cnt + s->rank, cnt, 1, ncclUint64, h->comm->comm, h->stream) : ncclSuccess;
+  ncclResult_t r3 = api->GroupEnd();                   // always closed, whatever happened in between
+  for (ncclResult_t r : {r0, r1, r2, r3})
+    if (r != ncclSuccess && rc == DYB_OK) rc = fail(DYB_ERR_NCCL, std::string("SMC particle exchange: ") + api->GetErrorString(r));
+  return rc;
+}
+
+// the launch sequence of ONE tempering stage (smc.jl:110-243); every kernel reads the stage from the control block.
+// `par` = parity of the stage (only the NCCL exchange needs it on the host).  tev: 7 events or null.
+static int smc_stage_launch(dyb_smc* s, int par, cudaEvent_t* tev) {
   dyb_handle* h = s->h;
   cudaStream_t st = h->stream;
-  const long long N = s->npart, n = s->n_local, first = s->first;
+  const long long N = s->npart, n = s->n_local;
   const int np = s->np;
-  const long long nb = (N + SMC_BLOCK - 1) / SMC_BLOCK, nb_l = (n + SMC_BLOCK - 1) / SMC_BLOCK;
-  const double phi = s->phi[i], dphi = s->phi[i] - s->phi[i - 1];
-  double* stats = s->stats.as<double>() + (size_t)SMC_STATS * i;
-  double* w_g = s->w_g.as<double>();
-  double* wt_g = s->wt_g.as<double>();
-  int* flag = s->flag.as<int>();
-  SmcTune* tune = s->tune.as<SmcTune>();
+  const unsigned nb = (unsigned)((N + SMC_BLOCK - 1) / SMC_BLOCK);
   PriorSetDev ps;
   int rc = prior_set(h, &ps);
   if (rc) return rc;
-
-  cudaEvent_t* tev = nullptr;
-  if (s->profiling) {
-    const size_t base = s->tev.size();
-    for (int k = 0; k <= SMC_TSEG; ++k) { cudaEvent_t e; DYB_CUDA(cudaEventCreate(&e)); s->tev.push_back(e); }
-    tev = &s->tev[base];
-  }
+  const SmcStageArgs a = stage_args(s);
 #define DYB_MARK(k) do { if (tev) DYB_CUDA(cudaEventRecord(tev[k], st)); } while (0)
   DYB_MARK(0);
-  // 1. correction (smc.jl:118-123) and ESS (:129); the weights of ALL particles are replicated on every rank
-  smc_incweight_kernel<<<nblk(n, 256), 256, 0, st>>>(w_g + first, s->loglh.as<double>(), dphi, n, wt_g + first);
-  rc = all_gather(h, wt_g + first, wt_g, (size_t)n, ncclDouble, 8);
-  if (rc) return rc;
-  smc_block_sum_kernel<<<(unsigned)nb, 32, 0, st>>>(wt_g, N, 0, s->bt.as<double>());
-  smc_total_kernel<<<1, 32, 0, st>>>(s->bt.as<double>(), nb, s->scal.as<double>());
-  smc_normalise_kernel<<<nblk(N, 256), 256, 0, st>>>(wt_g, s->scal.as<double>(), N, w_g);
-  smc_block_sum_kernel<<<(unsigned)nb, 32, 0, st>>>(w_g, N, 1, s->bt.as<double>());
-  smc_total_kernel<<<1, 32, 0, st>>>(s->bt.as<double>(), nb, s->scal.as<double>() + 1);
-  smc_stage_scalars_kernel<<<1, 32, 0, st>>>(s->scal.as<double>(), N, s->trgt, tune, flag, stats);
-
+  smc_w1_kernel<<<nb, 256, 0, st>>>(a);
+  smc_w2_kernel<<<nb, 256, 0, st>>>(a);
   DYB_MARK(1);
-  // 2. selection (smc.jl:130-145): every kernel is predicated on the device flag, the collectives are unconditional
-  smc_block_scan_kernel<<<(unsigned)nb, 32, 0, st>>>(w_g, N, s->cw_g.as<double>(), s->bt.as<double>());
-  smc_offsets_kernel<<<1, 32, 0, st>>>(s->bt.as<double>(), nb, s->offs.as<double>());
-  smc_add_offsets_kernel<<<nblk(N, 256), 256, 0, st>>>(s->cw_g.as<double>(), s->offs.as<double>(), N);
-  smc_select_kernel<<<nblk(n, 256), 256, 0, st>>>(s->cw_g.as<double>(), N, s->seed, (unsigned)i, s->systematic, first, n, flag,
-                                                  s->idx.as<long long>(), s->nclamp.as<unsigned long long>());
-  if (s->nranks > 1) DYB_NCCL(nccl_api()->GroupStart());
-  rc = all_gather(h, s->para.p, s->para_g.p, (size_t)np * n, ncclDouble, 8);
-  if (!rc) rc = all_gather(h, s->loglh.p, s->loglh_g.p, (size_t)n, ncclDouble, 8);
-  if (!rc) rc = all_gather(h, s->logpost.p, s->logpost_g.p, (size_t)n, ncclDouble, 8);
-  if (s->nranks > 1) DYB_NCCL(nccl_api()->GroupEnd());
-  if (rc) return rc;
-  smc_take_kernel<<<nblk(n * (np + 2), 256), 256, 0, st>>>(s->para_g.as<double>(), s->loglh_g.as<double>(), s->logpost_g.as<double>(),
-                                                           s->idx.as<long long>(), n, np, flag, s->para.as<double>(),
-                                                           s->loglh.as<double>(), s->logpost.as<double>());
-  smc_equal_weights_kernel<<<nblk(N, 256), 256, 0, st>>>(w_g, N, flag);
-
+  smc_select_all_kernel<<<nblk(N, 256), 256, 0, st>>>(a);
   DYB_MARK(2);
-  // 3. mutation: particle mean and covariance (smc.jl:154-165) in the canonical blocked order
-  double* part_g = s->part_g.as<double>();
-  smc_moment_kernel<<<dim3((unsigned)nb_l, nblk(np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(
-      s->para.as<double>(), w_g + first, nullptr, n, np, part_g + (size_t)s->rank * nb_l * np);
-  rc = all_gather(h, part_g + (size_t)s->rank * nb_l * np, part_g, (size_t)nb_l * np, ncclDouble, 8);
-  if (rc) return rc;
-  smc_reduce_partials_kernel<<<nblk(np, 64), 64, 0, st>>>(part_g, nb, np, s->mu.as<double>());
-  DYB_CUDA(launch_moment2(s->para.as<double>(), w_g + first, s->mu.as<double>(), n, np, nb_l,
-                          part_g + (size_t)s->rank * nb_l * np * np, h->device, st));
-  rc = all_gather(h, part_g + (size_t)s->rank * nb_l * np * np, part_g, (size_t)nb_l * np * np, ncclDouble, 8);
-  if (rc) return rc;
-  smc_reduce_partials_kernel<<<nblk(np * np, 64), 64, 0, st>>>(part_g, nb, np * np, s->R.as<double>());
-  smc_chol_kernel<<<1, 32, 0, st>>>(s->R.as<double>(), np, s->L.as<double>(), s->rdiag.as<double>(), s->aux.as<double>(), s->err.as<int>());
-
+  smc_mom1_kernel<<<dim3(nb, nblk(np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(a);
+  {
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    const size_t staged = smc_moment2_smem_bytes(np);
+    unsigned groups = (296 + nb - 1) / nb;                                   // about two CTAs per SM in total
+    const unsigned maxg = (unsigned)((np * np + SMC_MOM_TILE - 1) / SMC_MOM_TILE);
+    if (groups > maxg) groups = maxg;
+    if (groups < 1) groups = 1;
+    if (staged + 1024 <= (size_t)max_smem) {
+      DYB_CUDA(cudaFuncSetAttribute(smc_mom2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
+      smc_mom2_kernel<true><<<dim3(nb, groups), dim3(32, SMC_MOM_TILE), staged, st>>>(a);
+    } else {
+      smc_mom2_kernel<false><<<dim3(nb, maxg), dim3(32, SMC_MOM_TILE), sizeof(double) * np * np, st>>>(a);
+    }
+  }
   DYB_MARK(3);
-  SmcProposeArgs pa;
-  pa.para = s->para.as<double>(); pa.loglh = s->loglh.as<double>(); pa.logpost = s->logpost.as<double>();
-  pa.mu = s->mu.as<double>(); pa.L = s->L.as<double>(); pa.rdiag = s->rdiag.as<double>(); pa.aux = s->aux.as<double>();
-  pa.tune = tune; pa.alp_mix = s->alp; pa.seed = s->seed; pa.stage = (unsigned)i; pa.first = first; pa.n_local = n; pa.np = np;
-  pa.prop = s->prop.as<double>(); pa.qx = s->qx.as<double>(); pa.q0 = s->q0.as<double>();
-  smc_propose_kernel<<<nblk(n, 128), 128, sizeof(double) * (np * np + 2 * np), st>>>(pa);
+  smc_propose2_kernel<<<nblk(n, 128), 128, sizeof(double) * (np * np + 2 * np), st>>>(a);
   DYB_CUDA(cudaGetLastError());
   DYB_MARK(4);
   rc = dyb_loglik_batch_device(h, s->prop.as<double>(), n, s->lx.as<double>(), s->st.as<int>());
   if (rc) return rc;
   DYB_MARK(5);
-  logprior_kernel<<<nblk(n, 128), 128, 0, st>>>(ps, s->prop.as<double>(), n, s->priorx.as<double>());
-  unsigned long long* acc = s->acc_g.as<unsigned long long>();
-  DYB_CUDA(cudaMemsetAsync(acc + s->rank, 0, 8, st));
-  SmcAcceptArgs aa;
-  aa.para = s->para.as<double>(); aa.loglh = s->loglh.as<double>(); aa.logpost = s->logpost.as<double>();
-  aa.prop = s->prop.as<double>(); aa.lx = s->lx.as<double>(); aa.status = s->st.as<int>(); aa.priorx = s->priorx.as<double>();
-  aa.qx = s->qx.as<double>(); aa.q0 = s->q0.as<double>(); aa.phi = phi; aa.dphi = dphi; aa.seed = s->seed; aa.stage = (unsigned)i;
-  aa.first = first; aa.n_local = n; aa.np = np; aa.accepted = acc + s->rank;
-  smc_accept_kernel<<<nblk(n, 256), 256, 0, st>>>(aa);
-  rc = all_gather(h, acc + s->rank, acc, 1, ncclUint64, 8);
-  if (rc) return rc;
-  smc_acpt_kernel<<<1, 32, 0, st>>>(acc, s->nranks, N, tune, stats);
-  smc_store_clamped_kernel<<<1, 32, 0, st>>>(s->nclamp.as<unsigned long long>(), stats);
+  smc_accept_publish_kernel<<<nblk(n, SMC_ACC_BLOCK), SMC_ACC_BLOCK, sizeof(double) * SMC_ACC_BLOCK * (np + 2), st>>>(a, ps);
   DYB_CUDA(cudaGetLastError());
+  if (s->nranks > 1 && !s->p2p) { rc = smc_nccl_exchange(s, par, true); if (rc) return rc; }
   DYB_MARK(6);
 #undef DYB_MARK
-  h->launches += 23;
+  h->launches += 7;
+  return DYB_OK;
+}
+
+// first run after dyb_smc_init: the initial payload reaches every rank
+static int smc_publish_initial(dyb_smc* s) {
+  dyb_handle* h = s->h;
+  s->epoch += (unsigned long long)s->nphi + 2ULL;
+  smc_set_epoch_kernel<<<1, 1, 0, h->stream>>>(s->ctl.as<SmcCtl>(), s->epoch);
+  if (s->nranks > 1) {
+    int rc = smc_rank_barrier(s);            // every rank is done with the previous contents of the slabs
+    if (rc) return rc;
+    if (s->p2p) {
+      const SmcStageArgs a = stage_args(s);
+      const long long nel = s->n_local * (s->np + 2);
+      unsigned g = nblk(nel, 256); if (g > 296) g = 296;
+      smc_publish_init_kernel<<<g, 256, 0, h->stream>>>(a);
+    } else {
+      rc = smc_nccl_exchange(s, 0, false);
+      if (rc) return rc;
+    }
+  }
+  DYB_CUDA(cudaGetLastError());
+  s->published = true;
   return DYB_OK;
 }
 
 int dyb_smc_run(dyb_smc* s, int32_t n_stages) {
   if (!s || n_stages < 0) return fail(DYB_ERR_ARG, "bad argument");
   if (s->stage < 1) return fail(DYB_ERR_STATE, "dyb_smc_init has not been called");
-  DYB_CUDA(cudaSetDevice(s->h->device));
+  dyb_handle* h = s->h;
+  DYB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc = DYB_OK;
+  if (!s->published) { rc = smc_publish_initial(s); if (rc) return rc; }
+  bool ran = false;
   for (int k = 0; k < n_stages && s->stage < s->nphi; ++k) {
-    int rc = smc_stage(s, s->stage);
-    if (rc) return rc;
+    const int par = s->stage & 1;
+    if (s->profiling) {
+      const size_t base = s->tev.size();
+      for (int q = 0; q <= SMC_TSEG; ++q) { cudaEvent_t e; DYB_CUDA(cudaEventCreate(&e)); s->tev.push_back(e); }
+      rc = smc_stage_launch(s, par, &s->tev[base]);
+      if (rc) return rc;
+    } else if (s->use_graph && k > 0) {
+      // stage 1 of a call runs as plain launches (it also sizes the likelihood buffers); later ones replay a graph
+      if (!s->graph[par] || s->graph_cfg[par] != h->config_epoch) {
+        if (s->graph[par]) { cudaGraphExecDestroy(s->graph[par]); s->graph[par] = nullptr; }
+        cudaGraph_t g = nullptr;
+        const int64_t launches0 = h->launches;
+        DYB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        rc = smc_stage_launch(s, par, nullptr);
+        const cudaError_t ce = cudaStreamEndCapture(st, &g);
+        h->launches = launches0;
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess || !g) { cudaGetLastError(); s->use_graph = false; }
+        else {
+          const cudaError_t ie = cudaGraphInstantiate(&s->graph[par], g, 0);
+          cudaGraphDestroy(g);
+          if (ie != cudaSuccess) { cudaGetLastError(); s->graph[par] = nullptr; s->use_graph = false; }
+          else s->graph_cfg[par] = h->config_epoch;
+        }
+      }
+      if (s->use_graph) {
+        DYB_CUDA(cudaGraphLaunch(s->graph[par], st));
+        h->launches += 7 + 1 + h->ops->solve_launches(h->hs);
+      } else {
+        rc = smc_stage_launch(s, par, nullptr);
+        if (rc) return rc;
+      }
+    } else {
+      rc = smc_stage_launch(s, par, nullptr);
+      if (rc) return rc;
+    }
     s->stage += 1;
+    ran = true;
+  }
+  if (ran) {
+    smc_finalize_kernel<<<1, 32, 0, st>>>(stage_args(s));
+    DYB_CUDA(cudaGetLastError());
+    h->launches += 1;
   }
   return DYB_OK;
 }
@@ -628,13 +788,18 @@ int dyb_smc_get_timing(dyb_smc* s, int32_t* n_stages, double* ms) {
 
 int dyb_smc_get_particles(dyb_smc* s, double* para, double* w, double* loglh, double* logpost) {
   if (!s) return fail(DYB_ERR_ARG, "null argument");
+  if (s->stage < 1) return fail(DYB_ERR_STATE, "dyb_smc_init has not been called");
   dyb_handle* h = s->h;
   DYB_CUDA(cudaSetDevice(h->device));
   const size_t n = (size_t)s->n_local;
-  if (para) DYB_CUDA(cudaMemcpyAsync(para, s->para.p, 8 * n * s->np, cudaMemcpyDefault, h->stream));
+  const double* pay = reinterpret_cast<const double*>(s->slab.as<char>() + (((s->stage - 1) & 1) ? s->off_pay1 : 0));
+  smc_unpack_rows_kernel<<<nblk(s->n_local, 256), 256, 0, h->stream>>>(pay, s->first, s->n_local, s->np, s->tmp_para.as<double>(),
+                                                                     s->tmp_ll.as<double>(), s->tmp_lp.as<double>());
+  DYB_CUDA(cudaGetLastError());
+  if (para) DYB_CUDA(cudaMemcpyAsync(para, s->tmp_para.p, 8 * n * s->np, cudaMemcpyDefault, h->stream));
   if (w) DYB_CUDA(cudaMemcpyAsync(w, s->w_g.as<double>() + s->first, 8 * n, cudaMemcpyDefault, h->stream));
-  if (loglh) DYB_CUDA(cudaMemcpyAsync(loglh, s->loglh.p, 8 * n, cudaMemcpyDefault, h->stream));
-  if (logpost) DYB_CUDA(cudaMemcpyAsync(logpost, s->logpost.p, 8 * n, cudaMemcpyDefault, h->stream));
+  if (loglh) DYB_CUDA(cudaMemcpyAsync(loglh, s->tmp_ll.p, 8 * n, cudaMemcpyDefault, h->stream));
+  if (logpost) DYB_CUDA(cudaMemcpyAsync(logpost, s->tmp_lp.p, 8 * n, cudaMemcpyDefault, h->stream));
   DYB_CUDA(cudaStreamSynchronize(h->stream));
   return DYB_OK;
 }
@@ -646,9 +811,9 @@ int dyb_smc_get_stats(dyb_smc* s, double* stats, double* mu, double* R, double* 
   dyb_handle* h = s->h;
   DYB_CUDA(cudaSetDevice(h->device));
   std::vector<double> hs((size_t)SMC_STATS * s->nphi);
-  int err = 0;
+  SmcCtl ctl{};
   DYB_CUDA(cudaMemcpyAsync(hs.data(), s->stats.p, 8 * hs.size(), cudaMemcpyDeviceToHost, h->stream));
-  DYB_CUDA(cudaMemcpyAsync(&err, s->err.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  DYB_CUDA(cudaMemcpyAsync(&ctl, s->ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
   if (mu) DYB_CUDA(cudaMemcpyAsync(mu, s->mu.p, 8 * (size_t)s->np, cudaMemcpyDefault, h->stream));
   if (R) DYB_CUDA(cudaMemcpyAsync(R, s->R.p, 8 * (size_t)s->np * s->np, cudaMemcpyDefault, h->stream));
   DYB_CUDA(cudaStreamSynchronize(h->stream));
@@ -658,7 +823,7 @@ int dyb_smc_get_stats(dyb_smc* s, double* stats, double* mu, double* R, double* 
     for (int i = 1; i < s->stage; ++i) a += std::log(hs[(size_t)SMC_STATS * i]);
     *logmdd = a;
   }
-  if (err) return fail(DYB_ERR_STATE, "the particle covariance was not positive definite at some stage (the reference's cholesky throws)");
+  if (ctl.err) return fail(DYB_ERR_STATE, "the particle covariance was not positive definite at some stage (the reference's cholesky throws)");
   return DYB_OK;
 }
 

@@ -196,219 +196,7 @@ __global__ void smc_fill_kernel(double* __restrict__ x, long long n, double v) {
   if (i < n) x[i] = v;
 }
 
-// logpost = phi[1] * loglh + logprior for the initial particles (smc.jl:96)
-__global__ void smc_init_logpost_kernel(const double* __restrict__ loglh, const double* __restrict__ prior, double phi0,
-                                        long long n, double* __restrict__ logpost) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) logpost[i] = phi0 * loglh[i] + prior[i];
-}
-
-// ESS (smc.jl:129), the selection flag (smc.jl:130) and the scale update (smc.jl:150-151) of one stage
-__global__ void smc_stage_scalars_kernel(const double* __restrict__ scal /* zhat, sum w^2 */, long long npart,
-                                         double trgt, SmcTune* __restrict__ tune, int* __restrict__ flag,
-                                         double* __restrict__ stats) {
-  if (blockIdx.x || threadIdx.x) return;
-  const double ess = 1.0 / scal[1];
-  const int f = ess < (double)npart / 2.0;
-  *flag = f;
-  const double e = exp(16.0 * (tune->acpt - trgt));
-  tune->c = tune->c * (0.95 + 0.10 * e / (1.0 + e));
-  stats[0] = scal[0]; stats[1] = ess; stats[2] = (double)f; stats[3] = tune->c;
-}
-
-// source index of each local output slot (global indices), only when *flag
-__global__ void smc_select_kernel(const double* __restrict__ cw, long long npart, unsigned long long seed, unsigned stage,
-                                  int systematic, long long first, long long n_local, const int* __restrict__ flag,
-                                  long long* __restrict__ idx, unsigned long long* __restrict__ n_clamped) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_local) return;
-  const long long g = first + i;
-  if (!*flag) { idx[i] = g; return; }
-  double ui;
-  if (systematic) ui = ((double)g + rng_uniform(seed, 0ULL, stage, RNG_RESAMPLE)) / (double)npart;
-  else ui = rng_uniform(seed, (unsigned long long)g, stage, RNG_RESAMPLE);
-  long long a = 0, b = npart;
-  while (a < b) {
-    const long long mid = (a + b) >> 1;
-    if (cw[mid] <= ui) a = mid + 1; else b = mid;
-  }
-  if (a >= npart) { a = npart - 1; atomicAdd(n_clamped, 1ULL); }
-  idx[i] = a;
-}
-
-// para/loglh/logpost <- gathered rows of the all-gathered copies (only when *flag)
-__global__ void smc_take_kernel(const double* __restrict__ para_g, const double* __restrict__ loglh_g,
-                                const double* __restrict__ logpost_g, const long long* __restrict__ idx,
-                                long long n_local, int np, const int* __restrict__ flag,
-                                double* __restrict__ para, double* __restrict__ loglh, double* __restrict__ logpost) {
-  if (!*flag) return;
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_local * (np + 2)) return;
-  const long long i = e / (np + 2);
-  const int c = (int)(e % (np + 2));
-  const long long s = idx[i];
-  if (c < np) para[i * np + c] = para_g[s * np + c];
-  else if (c == np) loglh[i] = loglh_g[s];
-  else logpost[i] = logpost_g[s];
-}
-
-__global__ void smc_equal_weights_kernel(double* __restrict__ w, long long npart, const int* __restrict__ flag) {
-  if (!*flag) return;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < npart) w[i] = 1.0 / (double)npart;
-}
-
-// Cholesky factor of the particle covariance (lower triangle of R is used), its diagonal, standard errors and
-// the log-determinants needed by the proposal densities (smc.jl:161-165, 326-338).  One warp.
-//   out: L np x np column-major (upper part zero), rdiag np (variances), aux[0] = sum_k log L_kk,
-//        aux[1] = sum_k log rdiag_k;  *err != 0 when R is not positive definite (the reference's cholesky throws)
-__global__ void smc_chol_kernel(const double* __restrict__ R, int np, double* __restrict__ L, double* __restrict__ rdiag,
-                                double* __restrict__ aux, int* __restrict__ err) {
-  __shared__ double A[MAX_EST * MAX_EST];
-  __shared__ double piv;
-  const int lane = threadIdx.x;
-  for (int e = lane; e < np * np; e += 32) {
-    const int i = e % np, j = e / np;
-    A[e] = (i >= j) ? R[i + np * j] : 0.0;
-  }
-  __syncwarp();
-  bool bad = false;
-  for (int j = 0; j < np; ++j) {
-    for (int i = j + lane; i < np; i += 32) {
-      double s = A[i + np * j];
-      for (int k = 0; k < j; ++k) s -= A[i + np * k] * A[j + np * k];
-      A[i + np * j] = s;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const double d = A[j + np * j];
-      if (!(d > 0.0) || !isfinite(d)) bad = true;
-      piv = sqrt(d);
-    }
-    __syncwarp();
-    const double ljj = piv;
-    for (int i = j + lane; i < np; i += 32) A[i + np * j] = (i == j) ? ljj : A[i + np * j] / ljj;
-    __syncwarp();
-  }
-  for (int e = lane; e < np * np; e += 32) L[e] = A[e];
-  for (int k = lane; k < np; k += 32) rdiag[k] = R[k + np * k];
-  if (lane == 0) {
-    double s0 = 0.0, s1 = 0.0;
-    for (int k = 0; k < np; ++k) { s0 += log(A[k + np * k]); s1 += log(R[k + np * k]); }
-    aux[0] = s0; aux[1] = s1;
-    if (bad) *err = 1;
-  }
-}
-
-struct SmcProposeArgs {
-  const double* para; const double* loglh; const double* logpost;     // current particles (local)
-  const double* mu; const double* L; const double* rdiag; const double* aux; const SmcTune* tune;
-  double alp_mix;                 // Tune.alp: mixture weight of the random-walk proposal
-  unsigned long long seed; unsigned stage; long long first, n_local; int np;
-  double* prop; double* qx; double* q0;
-};
-
-// one mutation proposal per particle (smc.jl:176-200) with the proposal log-densities (smc.jl:326-338).
-// `MvNormal(mu, c^2 * Rdiag)` with a VECTOR second argument is Distributions' (deprecated) standard-deviation
-// constructor, so the diagonal component's density uses sigma_k = c^2 Rdiag_k; reproduced as coded.
-__global__ void __launch_bounds__(128) smc_propose_kernel(SmcProposeArgs a) {
-  extern __shared__ double sh[];            // L (np*np), mu (np), rdiag (np)
-  const int np = a.np;
-  double* Ls = sh; double* mus = Ls + np * np; double* rds = mus + np;
-  for (int e = threadIdx.x; e < np * np; e += blockDim.x) Ls[e] = a.L[e];
-  for (int e = threadIdx.x; e < np; e += blockDim.x) { mus[e] = a.mu[e]; rds[e] = a.rdiag[e]; }
-  __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n_local) return;
-  const unsigned long long g = (unsigned long long)(a.first + i);
-  const double c = a.tune->c;
-  const double LOG2PI = 1.8378770664093453;
-  double z[MAX_EST], px[MAX_EST], dx[MAX_EST];
-  rng_normal_vector(a.seed, g, a.stage, np, z);
-  const double mix = rng_uniform(a.seed, g, a.stage, RNG_MIX);
-  const int mixsel = mix < a.alp_mix ? 1 : (mix < a.alp_mix + (1.0 - a.alp_mix) / 2.0 ? 2 : 3);
-  const double* p0 = a.para + i * np;
-  for (int k = 0; k < np; ++k) {
-    double s;
-    if (mixsel == 2) s = (c * sqrt(rds[k])) * z[k];
-    else { s = 0.0; for (int j = 0; j <= k; ++j) s += (c * Ls[k + np * j]) * z[j]; }
-    px[k] = (mixsel == 3 ? mus[k] : p0[k]) + s;
-    a.prop[i * np + k] = px[k];
-  }
-  double qx, q0;
-  if (mixsel == 2) {
-    double ld = 0.0, m1 = 0.0, m0 = 0.0;
-    for (int k = 0; k < np; ++k) {
-      const double sg = c * c * rds[k];
-      ld += log(sg);
-      const double e1 = (px[k] - p0[k]) / sg, e0 = (p0[k] - px[k]) / sg;
-      m1 += e1 * e1; m0 += e0 * e0;
-    }
-    const double c0 = -0.5 * (np * LOG2PI + 2.0 * ld);
-    qx = c0 - 0.5 * m1; q0 = c0 - 0.5 * m0;
-  } else {
-    const double c0 = -0.5 * (np * LOG2PI + 2.0 * np * log(c) + 2.0 * a.aux[0]);
-    // whitened residuals by forward substitution with c L
-    double m1 = 0.0, m0 = 0.0;
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int k = 0; k < np; ++k) {
-        const double ctr = (mixsel == 3) ? mus[k] : (pass == 0 ? p0[k] : px[k]);
-        double s = ((pass == 0 ? px[k] : p0[k]) - ctr);
-        for (int j = 0; j < k; ++j) s -= (c * Ls[k + np * j]) * dx[j];
-        dx[k] = s / (c * Ls[k + np * k]);
-        if (pass == 0) m1 += dx[k] * dx[k]; else m0 += dx[k] * dx[k];
-      }
-    }
-    qx = c0 - 0.5 * m1; q0 = c0 - 0.5 * m0;
-  }
-  a.qx[i] = qx; a.q0[i] = q0;
-}
-
-struct SmcAcceptArgs {
-  double* para; double* loglh; double* logpost;
-  const double* prop; const double* lx; const int* status; const double* priorx; const double* qx; const double* q0;
-  double phi, dphi; unsigned long long seed; unsigned stage; long long first, n_local; int np;
-  unsigned long long* accepted;
-};
-
-// accept / reject (smc.jl:202-232)
-__global__ void smc_accept_kernel(SmcAcceptArgs a) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool acc = false;
-  if (i < a.n_local) {
-    const double l0 = a.loglh[i];
-    const double post0 = a.logpost[i] + a.dphi * l0;
-    const double lx = a.status[i] != 0 ? -INFINITY : a.lx[i];
-    const double postx = a.phi * lx + a.priorx[i];
-    const double alp = exp((postx - a.qx[i]) - (post0 - a.q0[i]));
-    const double u = rng_uniform(a.seed, (unsigned long long)(a.first + i), a.stage, RNG_ACCEPT);
-    acc = u < alp;
-    if (acc) {
-      for (int k = 0; k < a.np; ++k) a.para[i * a.np + k] = a.prop[i * a.np + k];
-      a.loglh[i] = lx;
-      a.logpost[i] = postx;
-    } else {
-      a.logpost[i] = post0;
-    }
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, acc);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(a.accepted, (unsigned long long)__popc(m));
-}
-
-// acpt = mean(accepted) over ALL particles (smc.jl:236); counts: one entry per rank
-__global__ void smc_acpt_kernel(const unsigned long long* __restrict__ counts, int nranks, long long npart,
-                                SmcTune* __restrict__ tune, double* __restrict__ stats) {
-  if (blockIdx.x || threadIdx.x) return;
-  unsigned long long s = 0;
-  for (int r = 0; r < nranks; ++r) s += counts[r];
-  tune->acpt = (double)s / (double)npart;
-  stats[4] = tune->acpt;
-}
-
-__global__ void smc_store_clamped_kernel(const unsigned long long* __restrict__ n_clamped, double* __restrict__ stats) {
-  if (blockIdx.x || threadIdx.x) return;
-  stats[5] = (double)*n_clamped;
-}
+// The stage kernels themselves are in smc_stage.cuh.
 
 // ------------------------------------------------------------------------------------------------
 // random-walk Metropolis on many chains (estimation.jl:964-989)

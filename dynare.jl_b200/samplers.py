@@ -123,6 +123,12 @@ class SMC:
         names = ("correction", "selection", "moments", "proposal", "likelihood", "accept")
         return dict(stages=n.value, **dict(zip(names, ms.tolist())))
 
+    def transport(self):
+        """dict(peer_stores, cuda_graph): how the stages exchange particles and whether they replay a CUDA graph."""
+        a, b = C.c_int32(), C.c_int32()
+        L.check(self.ssws.lib.dyb_smc_transport(self._s, C.byref(a), C.byref(b)))
+        return dict(peer_stores=bool(a.value), cuda_graph=bool(b.value))
+
     def stages_done(self) -> int:
         return self.ssws.lib.dyb_smc_stages_done(self._s)
 

@@ -317,10 +317,19 @@ int dyb_smc_default_options(dyb_smc_options* opt);
 int dyb_smc_create(dyb_handle* h, const dyb_smc_options* opt, const double* phi, dyb_smc** out);
 int dyb_smc_destroy(dyb_smc* s);
 int dyb_smc_local_range(const dyb_smc* s, int64_t* first, int64_t* n_local);
+/* how the stages run: *peer_stores = 1 when the mutated particles travel by stores into the peers' CUDA-IPC mapped
+ * buffers over NVLink (the default with several ranks on one node), 0 for the in-place ncclAllGather (environment
+ * DYB_SMC_TRANSPORT=nccl, or no peer access) or a single GPU; *cuda_graph = 1 when stages replay a captured CUDA graph
+ * (DYB_SMC_GRAPH=0 and profiling switch it off).  Either output may be NULL. */
+int dyb_smc_transport(const dyb_smc* s, int32_t* peer_stores, int32_t* cuda_graph);
 /* initial particles (smc.jl:84-101): para_local np x n_local drawn from the prior by the caller; evaluates the
- * likelihood and the prior; status[i] != 0 marks draws the reference rejects (replace them and call again) */
+ * likelihood and the prior; status[i] != 0 marks draws the reference rejects (replace them and call again).  Local to
+ * the rank: ranks may call it a different number of times before the (collective) dyb_smc_run. */
 int dyb_smc_init(dyb_smc* s, const double* para_local, int32_t* status);
-/* the next n_stages tempering stages: correction, selection, mutation (smc.jl:110-243); asynchronous */
+/* the next n_stages tempering stages: correction, selection, mutation (smc.jl:110-243); asynchronous.  With several
+ * ranks this is a collective call: every rank runs the same number of stages.  A stage is seven fused kernels around the
+ * likelihood batch (csrc/smc_stage.cuh), replayed as a CUDA graph; its one exchange -- the mutated particles -- is
+ * written into every peer's memory by the accept kernel itself. */
 int dyb_smc_run(dyb_smc* s, int32_t n_stages);
 int dyb_smc_stages_done(const dyb_smc* s);
 /* per-stage time split from CUDA events on the handle's stream: when profiling is on, every stage records 7 events;
@@ -343,8 +352,9 @@ int dyb_rwmh_run(dyb_handle* h, int64_t n_chains, int64_t first_chain, int32_t n
                  int32_t transformed, const double* chol_cov, uint64_t seed, double* y, double* logp,
                  int64_t* accepted, double* history, double* history_logp);
 
-/* ---- several GPUs: one process per GPU, NCCL only for the SMC stage coupling (weights, block partials, resampled
- * particles).  Rank 0 calls dyb_comm_unique_id and ships the 128 bytes to the other ranks by any host channel. */
+/* ---- several GPUs: one process per GPU.  The NCCL communicator bootstraps the SMC stage coupling (exchange of CUDA-IPC
+ * handles, barriers) and carries the particle all-gather when peer stores are unavailable.
+ * Rank 0 calls dyb_comm_unique_id and ships the 128 bytes to the other ranks by any host channel. */
 #define DYB_COMM_ID_BYTES 128
 int dyb_comm_unique_id(void* id /* DYB_COMM_ID_BYTES out */);
 int dyb_comm_init(dyb_handle* h, int32_t rank, int32_t nranks, const void* id);

@@ -32,7 +32,7 @@ class ModelDims(C.Structure):
 class Options(C.Structure):
     _fields_ = [("cr_tol", C.c_double), ("cr_maxit", C.c_int32), ("steady_tol", C.c_double),
                 ("lyap_tol", C.c_double), ("lyap_maxit", C.c_int32), ("presample", C.c_int32),
-                ("solver", C.c_int32)]
+                ("solver", C.c_int32), ("filter_lanes", C.c_int32)]
 
 
 class SmcOptions(C.Structure):

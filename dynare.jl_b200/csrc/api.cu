@@ -42,6 +42,7 @@ static void default_options(dyb_options* o) {
   o->lyap_maxit = 60;
   o->presample = 0;
   o->solver = 0;
+  o->filter_lanes = 0;
 }
 
 namespace dyb {
@@ -166,7 +167,8 @@ int dyb_get_options(const dyb_handle* h, dyb_options* opt) {
 int dyb_set_options(dyb_handle* h, const dyb_options* opt) {
   if (!h || !opt) return fail(DYB_ERR_ARG, "null argument");
   if (!(opt->cr_tol > 0) || opt->cr_maxit < 1 || !(opt->steady_tol > 0) || !(opt->lyap_tol >= 0) ||
-      opt->lyap_maxit < 1 || opt->presample < 0 || opt->solver < 0 || opt->solver > 2)
+      opt->lyap_maxit < 1 || opt->presample < 0 || opt->solver < 0 || opt->solver > 2 ||
+      !(opt->filter_lanes == 0 || opt->filter_lanes == 1 || opt->filter_lanes == 4 || opt->filter_lanes == 8))
     return fail(DYB_ERR_ARG, "invalid option value");
   h->hs.opt = *opt;
   h->config_epoch += 1;
@@ -249,7 +251,7 @@ int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, dou
   if (timed) DYB_CUDA(cudaEventRecord(ev[0], h->stream));
   DYB_CUDA(h->ops->solve(h->hs, d_theta, n, so, h->stream));
   if (timed) DYB_CUDA(cudaEventRecord(ev[1], h->stream));
-  DYB_CUDA(h->ops->kalman(h->d_ss.as<double>(), n, h->d_Y.as<double>(), h->nobs, h->hs.opt.presample,
+  DYB_CUDA(h->ops->kalman(h->d_ss.as<double>(), n, h->d_Y.as<double>(), h->nobs, h->hs.opt.presample, h->hs.opt.filter_lanes,
                           h->d_st1.as<int>(), d_loglik, d_status, h->stream));
   if (timed) DYB_CUDA(cudaEventRecord(ev[2], h->stream));
   h->ev_valid = timed && (ev == h->ev);

@@ -455,7 +455,7 @@ int dyb_create_generic(const dyb_model_desc* md, int device, dyb_handle** out) {
   h->dims = dyb_model_dims{n, nx, 0, k, nf, s, ncol, ns, ny, 0, 0, 0};
   h->hs.np = 0;
   h->hs.opt.cr_tol = 1e-8; h->hs.opt.cr_maxit = 100; h->hs.opt.steady_tol = std::cbrt(2.220446049250313e-16);
-  h->hs.opt.lyap_tol = 1e-16; h->hs.opt.lyap_maxit = 60; h->hs.opt.presample = 0; h->hs.opt.solver = 0;
+  h->hs.opt.lyap_tol = 1e-16; h->hs.opt.lyap_maxit = 60; h->hs.opt.presample = 0; h->hs.opt.solver = 0; h->hs.opt.filter_lanes = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   h->stream = h->own_stream;
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);

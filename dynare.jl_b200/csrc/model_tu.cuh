@@ -7,6 +7,7 @@
 #include "solve_kernel.cuh"
 #include "solve_coop.cuh"
 #include "kalman_kernel.cuh"
+#include "kalman_sublanes.cuh"
 
 namespace dyb {
 namespace {
@@ -59,9 +60,38 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
   return cudaGetLastError();
 }
 
-cudaError_t mt_kalman(const double* d_ss, long long n, const double* d_Y, int nobs, int presample,
+// G lanes per draw for small batches (kalman_sublanes.cuh)
+template <int G>
+cudaError_t mt_kalman_sub(const double* d_ss, long long n, const double* d_Y, int nobs, int presample,
+                          const int* d_status_in, double* d_loglik, int* d_status_out, cudaStream_t st) {
+  using C = KalmanSubCfg<MT, G>;
+  const size_t smem = C::smem_bytes(nobs);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kalman_sublanes_kernel<MT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const long long grid = (n * G + C::BLOCK - 1) / C::BLOCK;
+  kalman_sublanes_kernel<MT, G><<<(unsigned)grid, C::BLOCK, smem, st>>>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out);
+  return cudaGetLastError();
+}
+
+// lanes per draw of the filter: 1 = one thread per draw (throughput kernel), 4 / 8 = shared-tile kernel for batches that
+// do not fill the GPU; `want` = dyb_options.filter_lanes (0 = choose by batch width)
+int mt_kalman_lanes(long long n, int nobs, int want) {
+  int g = want;
+  if (g != 1 && g != 4 && g != 8) g = (n <= 8192) ? 8 : (n <= 24576 ? 4 : 1);
+  if (g == 4 && KalmanSubCfg<MT, 4>::smem_bytes(nobs) > 200 * 1024) g = 8;
+  if (g == 8 && KalmanSubCfg<MT, 8>::smem_bytes(nobs) > 200 * 1024) g = 1;
+  if (MT::NS > 255) g = 1;
+  return g;
+}
+
+cudaError_t mt_kalman(const double* d_ss, long long n, const double* d_Y, int nobs, int presample, int want_lanes,
                       const int* d_status_in, double* d_loglik, int* d_status_out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
+  const int lanes = mt_kalman_lanes(n, nobs, want_lanes);
+  if (lanes == 8) return mt_kalman_sub<8>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out, st);
+  if (lanes == 4) return mt_kalman_sub<4>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out, st);
   using Cfg = KalmanCfg<MT>;
   const int block = Cfg::BLOCK;
   const long long grid = (n + block - 1) / block;

@@ -34,7 +34,8 @@ struct ModelOps {
   void (*defaults)(HostState&);
   int (*solve_launches)(const HostState&);   // kernels one solve() call launches
   cudaError_t (*solve)(const HostState&, const double* d_theta, long long n, SolveOut out, cudaStream_t);
-  cudaError_t (*kalman)(const double* d_ss, long long n, const double* d_Y, int nobs, int presample,
+  // lanes: dyb_options.filter_lanes (0 auto, 1, 4, 8)
+  cudaError_t (*kalman)(const double* d_ss, long long n, const double* d_Y, int nobs, int presample, int lanes,
                         const int* d_status_in, double* d_loglik, int* d_status_out, cudaStream_t);
   // expand the SoA hand-off buffer into dense per-draw matrices (any output may be null)
   cudaError_t (*unpack)(const double* d_ss, long long n, double* T, double* RQR, double* P0,

@@ -119,10 +119,10 @@ struct dyb_smc {
   bool use_graph = true;
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   long long graph_cfg[2] = {-1, -1};
-  DevBuf slab, ctl, phi_d, w_g, wt_g, cwl, bt, bt2, btw, offs, idx, part1, part2, mu, R, L, rdiag, aux, prop, qx, q0,
+  DevBuf slab, ctl, phi_d, w_g, wt_g, cwl, bt, bt2, btw, offs, idx, xsel, part1, part2, mu, R, L, rdiag, aux, prop, qx, q0,
       lx, st, priorx, stats, tmp_para, tmp_ll, tmp_lp;
   void release() {
-    DevBuf* all[] = {&slab, &ctl, &phi_d, &w_g, &wt_g, &cwl, &bt, &bt2, &btw, &offs, &idx, &part1, &part2, &mu, &R, &L,
+    DevBuf* all[] = {&slab, &ctl, &phi_d, &w_g, &wt_g, &cwl, &bt, &bt2, &btw, &offs, &idx, &xsel, &part1, &part2, &mu, &R, &L,
                      &rdiag, &aux, &prop, &qx, &q0, &lx, &st, &priorx, &stats, &tmp_para, &tmp_ll, &tmp_lp};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : tev) cudaEventDestroy(e);
@@ -144,7 +144,7 @@ static SmcStageArgs stage_args(const dyb_smc* s) {
   a.npub = s->p2p ? s->nranks : 1; a.nwait = s->p2p ? s->nranks : 0;
   a.N = s->npart; a.n = s->n_local; a.first = s->first; a.np = s->np;
   a.w = s->w_g.as<double>(); a.wt = s->wt_g.as<double>(); a.cwl = s->cwl.as<double>(); a.bt = s->bt.as<double>();
-  a.bt2 = s->bt2.as<double>(); a.btw = s->btw.as<double>(); a.offs = s->offs.as<double>(); a.idx = s->idx.as<long long>();
+  a.bt2 = s->bt2.as<double>(); a.btw = s->btw.as<double>(); a.offs = s->offs.as<double>(); a.idx = s->idx.as<long long>(); a.xsel = s->xsel.as<double>();
   a.part1 = s->part1.as<double>(); a.part2 = s->part2.as<double>(); a.mu = s->mu.as<double>(); a.R = s->R.as<double>();
   a.L = s->L.as<double>(); a.rdiag = s->rdiag.as<double>(); a.aux = s->aux.as<double>(); a.stats = s->stats.as<double>();
   a.prop = s->prop.as<double>(); a.qx = s->qx.as<double>(); a.q0 = s->q0.as<double>();
@@ -524,7 +524,7 @@ int dyb_smc_create(dyb_handle* h, const dyb_smc_options* o, const double* phi, d
   if (cudaMalloc(&s->slab.p, s->slab_bytes) == cudaSuccess) s->slab.cap = s->slab_bytes; else e = cudaGetLastError();
   R(s->ctl, sizeof(SmcCtl)); R(s->phi_d, 8 * (size_t)o->nphi);
   R(s->w_g, 8 * N); R(s->wt_g, 8 * N); R(s->cwl, 8 * N); R(s->bt, 8 * nb); R(s->bt2, 8 * nb); R(s->btw, 8 * nb); R(s->offs, 8 * nb);
-  R(s->idx, 8 * N); R(s->part1, 8 * nb * np); R(s->part2, 8 * nb * np * np);
+  R(s->idx, 8 * N); R(s->xsel, 8 * N * (np + 2)); R(s->part1, 8 * nb * np); R(s->part2, 8 * nb * np * np);
   R(s->mu, 8 * np); R(s->R, 8 * np * np); R(s->L, 8 * np * np); R(s->rdiag, 8 * np); R(s->aux, 16);
   R(s->prop, 8 * np * n); R(s->qx, 8 * n); R(s->q0, 8 * n); R(s->lx, 8 * n); R(s->st, 4 * n); R(s->priorx, 8 * n);
   R(s->stats, 8 * SMC_STATS * (size_t)o->nphi);
@@ -648,22 +648,30 @@ static int smc_stage_launch(dyb_smc* s, int par, cudaEvent_t* tev) {
   smc_w1_kernel<<<nb, 256, 0, st>>>(a);
   smc_w2_kernel<<<nb, 256, 0, st>>>(a);
   DYB_MARK(1);
-  smc_select_all_kernel<<<nblk(N, 256), 256, 0, st>>>(a);
+  smc_select_take_kernel<<<nblk(N, 256), 256, 0, st>>>(a);
   DYB_MARK(2);
-  smc_mom1_kernel<<<dim3(nb, nblk(np, SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE), 0, st>>>(a);
   {
+    // particle mean, then covariance + Cholesky: one wave of CTAs each, a block of 1024 rows staged through shared memory
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     const size_t staged = smc_moment2_smem_bytes(np);
-    unsigned groups = (296 + nb - 1) / nb;                                   // about two CTAs per SM in total
-    const unsigned maxg = (unsigned)((np * np + SMC_MOM_TILE - 1) / SMC_MOM_TILE);
-    if (groups > maxg) groups = maxg;
-    if (groups < 1) groups = 1;
-    if (staged + 1024 <= (size_t)max_smem) {
-      DYB_CUDA(cudaFuncSetAttribute(smc_mom2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
-      smc_mom2_kernel<true><<<dim3(nb, groups), dim3(32, SMC_MOM_TILE), staged, st>>>(a);
+    const bool fits = staged + 1024 <= (size_t)max_smem;
+    const size_t smem = fits ? staged : sizeof(double) * np * np;
+    const dim3 blk(32, SMC_MOM_WARPS);
+    auto groups_for = [&](int ncomp) {
+      unsigned g = 148 / nb, maxg = (unsigned)((ncomp + SMC_MOM_WARPS - 1) / SMC_MOM_WARPS);
+      if (!fits) g = maxg;
+      if (g > maxg) g = maxg;
+      return g < 1 ? 1u : g;
+    };
+    if (fits) {
+      DYB_CUDA(cudaFuncSetAttribute(smc_moments_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DYB_CUDA(cudaFuncSetAttribute(smc_moments_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smc_moments_kernel<false, true><<<dim3(nb, groups_for(np)), blk, smem, st>>>(a);
+      smc_moments_kernel<true, true><<<dim3(nb, groups_for(np * np)), blk, smem, st>>>(a);
     } else {
-      smc_mom2_kernel<false><<<dim3(nb, maxg), dim3(32, SMC_MOM_TILE), sizeof(double) * np * np, st>>>(a);
+      smc_moments_kernel<false, false><<<dim3(nb, groups_for(np)), blk, smem, st>>>(a);
+      smc_moments_kernel<true, false><<<dim3(nb, groups_for(np * np)), blk, smem, st>>>(a);
     }
   }
   DYB_MARK(3);

@@ -54,7 +54,8 @@ struct SmcStageArgs {
   long long N, n, first;             // particles in total, local count, first local particle
   int np;
   double *w, *wt, *cwl, *bt, *bt2, *btw, *offs;
-  long long* idx;                    // source particle of every slot (identity when the stage does not resample)
+  long long* idx;                    // source particle of every slot (only written when the stage resamples)
+  double* xsel;                      // the selected rows, contiguous (npart x (np + 2)), when the stage resamples
   double *part1, *part2, *mu, *R, *L, *rdiag, *aux;
   double* stats;                     // nphi x SMC_STATS
   double *prop, *qx, *q0;            // local proposals and their densities
@@ -78,6 +79,8 @@ DYB_D const double* smc_pay_in(const SmcStageArgs& a, int stage) {
 DYB_D double* smc_pay_out(const SmcStageArgs& a, int stage, int r) {
   return reinterpret_cast<double*>(a.slab[r] + ((stage & 1) ? a.off_pay1 : 0));
 }
+// rows the mutation step starts from: the gathered payload itself, or its resampled copy (smc.jl:130-145)
+DYB_D const double* smc_rows(const SmcStageArgs& a, int stage) { return a.ctl->flag ? a.xsel : smc_pay_in(a, stage); }
 DYB_D unsigned long long* smc_pub(const SmcStageArgs& a, int r) { return reinterpret_cast<unsigned long long*>(a.slab[r] + a.off_pub); }
 DYB_D unsigned long long* smc_cnt(const SmcStageArgs& a, int r, int stage) {
   return reinterpret_cast<unsigned long long*>(a.slab[r] + a.off_cnt) + (stage & 1) * SMC_MAX_RANKS;
@@ -201,48 +204,36 @@ __global__ void __launch_bounds__(256) smc_w2_kernel(SmcStageArgs a) {
   }
 }
 
-// ---- K3: source particle of EVERY slot (multinomial_resampling smc.jl:340-361 / systematic), equal weights (:143) ----
-__global__ void __launch_bounds__(256) smc_select_all_kernel(SmcStageArgs a) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.N) return;
-  if (!a.ctl->flag) { a.idx[j] = j; return; }
+// ---- K3: source particle of EVERY slot (multinomial_resampling smc.jl:340-361 / systematic), the selected rows copied
+// into a contiguous array (smc.jl:137-141) and equal weights (:143).  A stage that does not resample leaves at once: its
+// rows are the payload itself.  launch <<<ceil(npart / 256), 256>>>
+__global__ void __launch_bounds__(256) smc_select_take_kernel(SmcStageArgs a) {
+  __shared__ long long sidx[256];
+  if (!a.ctl->flag) return;
   const unsigned stage = (unsigned)a.ctl->stage;
-  double ui;
-  if (a.systematic) ui = ((double)j + rng_uniform(a.seed, 0ULL, stage, RNG_RESAMPLE)) / (double)a.N;
-  else ui = rng_uniform(a.seed, (unsigned long long)j, stage, RNG_RESAMPLE);
-  long long lo = 0, hi = a.N;               // first position with cw[pos] > ui, cw[pos] = offs[pos / 1024] + cwl[pos]
-  while (lo < hi) {
-    const long long mid = (lo + hi) >> 1;
-    if (a.offs[mid / SMC_BLOCK] + a.cwl[mid] <= ui) lo = mid + 1; else hi = mid;
-  }
-  if (lo >= a.N) { lo = a.N - 1; atomicAdd(&a.ctl->nclamp, 1ULL); }
-  a.idx[j] = lo;
-  a.w[j] = 1.0 / (double)a.N;
-}
-
-// ---- K4: first moment (smc.jl:154) of the selected particles; mu in the tail ---------------------------------------------
-// launch <<<dim3(blocks, ceil(np / SMC_MOM_TILE)), dim3(32, SMC_MOM_TILE)>>>
-__global__ void smc_mom1_kernel(SmcStageArgs a) {
-  const int np = a.np, PS = np + 2;
-  const double* pin = smc_pay_in(a, a.ctl->stage);
-  const int c = blockIdx.y * SMC_MOM_TILE + threadIdx.y;
-  if (c < np) {
-    const long long lo = (long long)blockIdx.x * SMC_BLOCK + (long long)threadIdx.x * SMC_RUN;
-    double s = 0.0;
-    for (int i = 0; i < SMC_RUN; ++i) {
-      const long long e = lo + i;
-      if (e < a.N) s = __dadd_rn(s, __dmul_rn(a.w[e], pin[a.idx[e] * PS + c]));
+  const long long j0 = (long long)blockIdx.x * 256, j = j0 + threadIdx.x;
+  if (j < a.N) {
+    double ui;
+    if (a.systematic) ui = ((double)j + rng_uniform(a.seed, 0ULL, stage, RNG_RESAMPLE)) / (double)a.N;
+    else ui = rng_uniform(a.seed, (unsigned long long)j, stage, RNG_RESAMPLE);
+    long long lo = 0, hi = a.N;             // first position with cw[pos] > ui, cw[pos] = offs[pos / 1024] + cwl[pos]
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (a.offs[mid / SMC_BLOCK] + a.cwl[mid] <= ui) lo = mid + 1; else hi = mid;
     }
-    const double t = warp_sum_in_order(s);
-    if (threadIdx.x == 0) a.part1[(long long)blockIdx.x * np + c] = t;
+    if (lo >= a.N) { lo = a.N - 1; atomicAdd(&a.ctl->nclamp, 1ULL); }
+    a.idx[j] = lo;
+    sidx[threadIdx.x] = lo;
+    a.w[j] = 1.0 / (double)a.N;
   }
-  if (smc_last_block(&a.ctl->ticket[2], gridDim.x * gridDim.y)) {
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int k = tid; k < np; k += 32 * SMC_MOM_TILE) {
-      double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(a.part1 + (size_t)b * np + k);
-      a.mu[k] = s;
-    }
+  __syncthreads();
+  const int PS = a.np + 2;
+  const int cnt = (int)((j0 + 256 <= a.N) ? 256 : a.N - j0);
+  const double* pin = smc_pay_in(a, (int)stage);
+  double* dst = a.xsel + j0 * PS;
+  for (int e = threadIdx.x; e < cnt * PS; e += 256) {
+    const int r = e / PS, c = e - r * PS;
+    dst[e] = pin[sidx[r] * PS + c];
   }
 }
 
@@ -279,89 +270,107 @@ DYB_D void smc_chol_warp(const double* __restrict__ R, int np, double* A, double
   }
 }
 
-// ---- K5: second central moment (smc.jl:155-160); R and its Cholesky factor in the tail ------------------------------------
-// STAGED: the 1024 selected rows of the block go through shared memory ((np + 1) * 1056 doubles, see smc_moment2_staged_kernel)
-// launch <<<dim3(blocks, groups), dim3(32, SMC_MOM_TILE), smem>>>; smem >= np * np doubles in either variant
-template <bool STAGED>
-__global__ void smc_mom2_kernel(SmcStageArgs a) {
+// ---- K4 / K5: particle mean (smc.jl:154) and covariance (:155-160) of the selected particles in the canonical order.
+// SECOND = false: partial[b*np + p] = sum_{i in block b} w_i x_ip, mu in the tail; SECOND = true: partial[b*np*np + p + np*q]
+// = sum_i (w_i (x_ip - mu_p)) (x_iq - mu_q), then R and its Cholesky factor in the tail.
+// STAGED: the 1024 rows of the block are read ONCE per CTA, coalesced, into shared memory ((np + 1) * 1056 doubles;
+// particle e at column e + e / 32 so that the 32 lanes of a warp, whose runs start 32 apart, hit distinct banks); one warp
+// per component, lane j sums run j sequentially, the 32 run totals are combined in order.  The grid is one wave:
+// <<<dim3(blocks, groups), dim3(32, SMC_MOM_WARPS), smem>>>, group g owns components g, g + groups, ...
+constexpr int SMC_MOM_WARPS = 16;
+template <bool SECOND, bool STAGED>
+__global__ void __launch_bounds__(32 * SMC_MOM_WARPS) smc_moments_kernel(SmcStageArgs a) {
   extern __shared__ double sm_mom[];
-  const int np = a.np, PS = np + 2, ncomp = np * np;
-  const double* pin = smc_pay_in(a, a.ctl->stage);
-  const int tid = threadIdx.y * 32 + threadIdx.x, nt = 32 * SMC_MOM_TILE, lane = threadIdx.x;
+  const int np = a.np, PS = np + 2, ncomp = SECOND ? np * np : np;
+  const double* x = smc_rows(a, a.ctl->stage);
+  const int tid = threadIdx.y * 32 + threadIdx.x, nt = 32 * SMC_MOM_WARPS, lane = threadIdx.x;
   const long long lo = (long long)blockIdx.x * SMC_BLOCK;
   const int cnt = (int)((lo + SMC_BLOCK < a.N) ? SMC_BLOCK : a.N - lo);
+  double* part = SECOND ? a.part2 : a.part1;
   if (STAGED) {
     double* xs = sm_mom;
     double* wsm = sm_mom + (size_t)np * SMC_MOM_LD;
-    for (int k = tid; k < cnt * np; k += nt) {
-      const int e = k / np, p = k - e * np;
-      xs[(size_t)p * SMC_MOM_LD + e + e / 32] = pin[a.idx[lo + e] * PS + p];
+    const double* src = x + lo * PS;
+    for (int k = tid; k < cnt * PS; k += nt) {
+      const int e = k / PS, p = k - e * PS;
+      if (p < np) xs[(size_t)p * SMC_MOM_LD + e + e / 32] = src[k];
     }
     for (int e = tid; e < cnt; e += nt) wsm[e + e / 32] = a.w[lo + e];
     __syncthreads();
-    for (int c = blockIdx.y + gridDim.y * threadIdx.y; c < ncomp; c += gridDim.y * SMC_MOM_TILE) {
+    for (int c = blockIdx.y + gridDim.y * threadIdx.y; c < ncomp; c += gridDim.y * SMC_MOM_WARPS) {
       const int p = c % np, q = c / np;
-      const double mp = a.mu[p], mq = a.mu[q];
       const double* xp = xs + (size_t)p * SMC_MOM_LD + 33 * lane;
-      const double* xq = xs + (size_t)q * SMC_MOM_LD + 33 * lane;
       const double* wl = wsm + 33 * lane;
       double s = 0.0;
-      for (int i = 0; i < SMC_RUN; ++i)
-        if (lane * SMC_RUN + i < cnt) s = __dadd_rn(s, __dmul_rn(__dmul_rn(wl[i], xp[i] - mp), xq[i] - mq));
+      if (SECOND) {
+        const double mp = a.mu[p], mq = a.mu[q];
+        const double* xq = xs + (size_t)q * SMC_MOM_LD + 33 * lane;
+        for (int i = 0; i < SMC_RUN; ++i)
+          if (lane * SMC_RUN + i < cnt) s = __dadd_rn(s, __dmul_rn(__dmul_rn(wl[i], xp[i] - mp), xq[i] - mq));
+      } else {
+        for (int i = 0; i < SMC_RUN; ++i)
+          if (lane * SMC_RUN + i < cnt) s = __dadd_rn(s, __dmul_rn(wl[i], xp[i]));
+      }
       const double t = warp_sum_in_order(s);
-      if (lane == 0) a.part2[(long long)blockIdx.x * ncomp + c] = t;
+      if (lane == 0) part[(long long)blockIdx.x * ncomp + c] = t;
     }
   } else {
-    for (int c = blockIdx.y + gridDim.y * threadIdx.y; c < ncomp; c += gridDim.y * SMC_MOM_TILE) {
+    for (int c = blockIdx.y + gridDim.y * threadIdx.y; c < ncomp; c += gridDim.y * SMC_MOM_WARPS) {
       const int p = c % np, q = c / np;
-      const double mp = a.mu[p], mq = a.mu[q];
+      const double mp = SECOND ? a.mu[p] : 0.0, mq = SECOND ? a.mu[q] : 0.0;
       double s = 0.0;
       for (int i = 0; i < SMC_RUN; ++i) {
         const int e = lane * SMC_RUN + i;
         if (e < cnt) {
-          const double* x = pin + a.idx[lo + e] * PS;
-          s = __dadd_rn(s, __dmul_rn(__dmul_rn(a.w[lo + e], x[p] - mp), x[q] - mq));
+          const double* xr = x + (lo + e) * PS;
+          if (SECOND) s = __dadd_rn(s, __dmul_rn(__dmul_rn(a.w[lo + e], xr[p] - mp), xr[q] - mq));
+          else s = __dadd_rn(s, __dmul_rn(a.w[lo + e], xr[p]));
         }
       }
       const double t = warp_sum_in_order(s);
-      if (lane == 0) a.part2[(long long)blockIdx.x * ncomp + c] = t;
+      if (lane == 0) part[(long long)blockIdx.x * ncomp + c] = t;
     }
   }
-  if (smc_last_block(&a.ctl->ticket[3], gridDim.x * gridDim.y)) {
+  if (smc_last_block(&a.ctl->ticket[SECOND ? 3 : 2], gridDim.x * gridDim.y)) {
+    double* out = SECOND ? a.R : a.mu;
     for (int k = tid; k < ncomp; k += nt) {
       double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(a.part2 + (size_t)b * ncomp + k);
-      a.R[k] = s;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(part + (size_t)b * ncomp + k);
+      out[k] = s;
     }
-    __syncthreads();
-    if (threadIdx.y == 0) smc_chol_warp(a.R, np, sm_mom, a.L, a.rdiag, a.aux, &a.ctl->err, lane);
+    if (SECOND) {
+      __syncthreads();
+      if (threadIdx.y == 0) smc_chol_warp(a.R, np, sm_mom, a.L, a.rdiag, a.aux, &a.ctl->err, lane);
+    }
   }
 }
 
 // ---- K6: one mutation proposal per local particle (smc.jl:176-200) with the proposal log-densities (:326-338) ----------
-// same arithmetic as smc_propose_kernel; the current particle is row idx[first + i] of the gathered payload
+// `MvNormal(mu, c^2 * Rdiag)` with a VECTOR second argument is Distributions' (deprecated) standard-deviation constructor,
+// so the diagonal component's density uses sigma_k = c^2 Rdiag_k; reproduced as coded.  c L is formed once per CTA; the two
+// whitening passes (density of the proposal seen from the particle and back) are independent and run in one loop.
 __global__ void __launch_bounds__(128) smc_propose2_kernel(SmcStageArgs a) {
-  extern __shared__ double sh[];            // L (np*np), mu (np), rdiag (np)
+  extern __shared__ double sh[];            // c L (np*np), mu (np), rdiag (np)
   const int np = a.np, PS = np + 2;
   double* Ls = sh; double* mus = Ls + np * np; double* rds = mus + np;
-  for (int e = threadIdx.x; e < np * np; e += blockDim.x) Ls[e] = a.L[e];
+  const double c = a.ctl->tune.c;
+  for (int e = threadIdx.x; e < np * np; e += blockDim.x) Ls[e] = c * a.L[e];
   for (int e = threadIdx.x; e < np; e += blockDim.x) { mus[e] = a.mu[e]; rds[e] = a.rdiag[e]; }
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   const unsigned stage = (unsigned)a.ctl->stage;
   const unsigned long long g = (unsigned long long)(a.first + i);
-  const double c = a.ctl->tune.c;
   const double LOG2PI = 1.8378770664093453;
-  double z[MAX_EST], px[MAX_EST], dx[MAX_EST];
+  double z[MAX_EST], px[MAX_EST], d1[MAX_EST], d0[MAX_EST];
   rng_normal_vector(a.seed, g, stage, np, z);
   const double mix = rng_uniform(a.seed, g, stage, RNG_MIX);
   const int mixsel = mix < a.alp ? 1 : (mix < a.alp + (1.0 - a.alp) / 2.0 ? 2 : 3);
-  const double* p0 = smc_pay_in(a, (int)stage) + a.idx[g] * PS;
+  const double* p0 = smc_rows(a, (int)stage) + g * PS;
   for (int k = 0; k < np; ++k) {
     double s;
     if (mixsel == 2) s = (c * sqrt(rds[k])) * z[k];
-    else { s = 0.0; for (int j = 0; j <= k; ++j) s += (c * Ls[k + np * j]) * z[j]; }
+    else { s = 0.0; for (int j = 0; j <= k; ++j) s += Ls[k + np * j] * z[j]; }
     px[k] = (mixsel == 3 ? mus[k] : p0[k]) + s;
     a.prop[i * np + k] = px[k];
   }
@@ -378,15 +387,16 @@ __global__ void __launch_bounds__(128) smc_propose2_kernel(SmcStageArgs a) {
     qx = c0 - 0.5 * m1; q0 = c0 - 0.5 * m0;
   } else {
     const double c0 = -0.5 * (np * LOG2PI + 2.0 * np * log(c) + 2.0 * a.aux[0]);
+    // whitened residuals by forward substitution with c L: pass "1" (proposal around the particle / the mean) and
+    // pass "0" (the particle around the proposal / the mean)
     double m1 = 0.0, m0 = 0.0;
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int k = 0; k < np; ++k) {
-        const double ctr = (mixsel == 3) ? mus[k] : (pass == 0 ? p0[k] : px[k]);
-        double s = ((pass == 0 ? px[k] : p0[k]) - ctr);
-        for (int j = 0; j < k; ++j) s -= (c * Ls[k + np * j]) * dx[j];
-        dx[k] = s / (c * Ls[k + np * k]);
-        if (pass == 0) m1 += dx[k] * dx[k]; else m0 += dx[k] * dx[k];
-      }
+    for (int k = 0; k < np; ++k) {
+      double s1 = px[k] - ((mixsel == 3) ? mus[k] : p0[k]);
+      double s0 = p0[k] - ((mixsel == 3) ? mus[k] : px[k]);
+      for (int j = 0; j < k; ++j) { const double l = Ls[k + np * j]; s1 -= l * d1[j]; s0 -= l * d0[j]; }
+      const double dg = Ls[k + np * k];
+      d1[k] = s1 / dg; d0[k] = s0 / dg;
+      m1 += d1[k] * d1[k]; m0 += d0[k] * d0[k];
     }
     qx = c0 - 0.5 * m1; q0 = c0 - 0.5 * m0;
   }
@@ -402,13 +412,13 @@ __global__ void __launch_bounds__(SMC_ACC_BLOCK) smc_accept_publish_kernel(SmcSt
   const int np = a.np, PS = np + 2;
   const int stage = a.ctl->stage;
   const double phi = a.phi[stage], dphi = a.phi[stage] - a.phi[stage - 1];
-  const double* pin = smc_pay_in(a, stage);
+  const double* pin = smc_rows(a, stage);
   const long long i0 = (long long)blockIdx.x * SMC_ACC_BLOCK;
   const long long i = i0 + threadIdx.x;
   bool acc = false;
   if (i < a.n) {
     const long long g = a.first + i;
-    const double* src = pin + a.idx[g] * PS;
+    const double* src = pin + g * PS;
     const double l0 = src[np];
     const double post0 = src[np + 1] + dphi * l0;
     const double lx = a.status[i] != 0 ? -INFINITY : a.lx[i];

@@ -1,19 +1,18 @@
 // Model-specialised Kalman-filter log-likelihood for SMALL batches: G lanes per draw.
 //
-// kalman_kernel<M> (one thread per draw, everything in registers) is the throughput kernel: it needs >= ~32 768 draws to
-// fill a B200.  An SMC stage on a shard of 2 048 - 16 384 particles runs it at one warp per scheduler, i.e. at the
-// latency of ONE thread walking the whole T-step recursion (ls2003: 0.23 ms whatever the batch).  This kernel computes
-// the same recursion (same structure exploited: Z a selection, T non-zero in the K lagged-state columns only, P
-// symmetric, missing rows neutralised -- see kalman_kernel.cuh; reference call src/estimation/estimation.jl:665-701)
-// with the draw's state in a shared-memory tile and the entries of every phase dealt round-robin to the G lanes of the
-// draw, so a period costs ~1/G of the dependent work plus four __syncwarp.  All draws of a warp run one instruction
-// stream (no data-dependent control flow), phases per period:
-//   1. v, F = (Z P Z' + H), Cholesky, w = L^-1 v, log det, v'F^-1 v            every lane, in registers (NY is small)
-//   2. U[:, j] = L^-1 (Z P)[:, lagged_j]                                      lane j mod G
-//   3. Pll = P_ll - U'U  (K(K+1)/2 entries),  al = a_l + U'w                  entries mod G
-//   4. Mrow = Tl Pll  (NS x K entries),  a <- Tl al                           entries mod G
-//   5. P <- R Q R' + Mrow Tl'  (NS(NS+1)/2 entries)                           entries mod G
-// Sums run in the same order as in kalman_kernel<M>, so both kernels agree to rounding of the Cholesky's rsqrt only.
+// kalman_kernel<M> (one thread per draw, everything in registers) is the throughput kernel: it needs >= ~16 384 draws to
+// occupy every scheduler of a B200.  An SMC stage on a shard of 2 048 - 8 192 particles runs it at less than one warp per
+// scheduler, i.e. at the latency of ONE thread walking the whole T-step recursion (ls2003: 0.23 ms whatever the batch).
+// This kernel computes the same recursion (same structure exploited: Z a selection, T non-zero in the K lagged-state
+// columns only, P symmetric, missing rows neutralised -- see kalman_kernel.cuh; reference call
+// src/estimation/estimation.jl:665-701) with the draw's P, a, Tl, R Q R' in a shared-memory tile:
+//   * the small dense algebra of a period -- v, F = Z P Z' + H, its Cholesky factor, w = L^-1 v, U = L^-1 (Z P)[:, lagged],
+//     the updated mean al and covariance Pll on the K lagged states -- is done by EVERY lane of the draw in registers
+//     (static indices, no exchange): it is O(NY^2 K + NY K^2) and its inputs are a few entries of the tile;
+//   * the time update, the O(NS^2 K) bulk, is dealt by ROW: lane g updates rows s = g, g + G, ... of
+//     a <- Tl al and P <- R Q R' + (Tl Pll) Tl' (lower triangle) and writes them back to the tile;
+//   * two __syncwarp per period (tile read -> tile written -> next period); all draws of a warp run one instruction stream.
+// Sums run in the same order as in kalman_kernel<M>: both kernels return the same bits.
 #pragma once
 #include "model_traits.cuh"
 #include "solve_kernel.cuh"
@@ -24,15 +23,13 @@ template <class M, int G>
 struct KalmanSubCfg {
   static constexpr int NS = M::NS, K = M::K, NY = M::NY;
   static constexpr int QQ_N = NS * (NS + 1) / 2, KK_N = K * (K + 1) / 2;
-  static constexpr int OFF_P = 0, OFF_QQ = OFF_P + QQ_N, OFF_TL = OFF_QQ + QQ_N, OFF_MR = OFF_TL + NS * K,
-                       OFF_U = OFF_MR + NS * K, OFF_PLL = OFF_U + NY * K, OFF_AL = OFF_PLL + KK_N, OFF_A = OFF_AL + K,
-                       TILE_RAW = OFF_A + NS;
+  static constexpr int OFF_P = 0, OFF_QQ = OFF_P + QQ_N, OFF_TL = OFF_QQ + QQ_N, OFF_A = OFF_TL + NS * K, TILE_RAW = OFF_A + NS;
   static constexpr int TILE = TILE_RAW | 1;                 // odd stride: the draws of a warp start in different banks
   static constexpr int BLOCK = 128, DRAWS = BLOCK / G;
-  static constexpr int NTAB = 2 * QQ_N + 2 * KK_N + K + NY; // decode tables (bytes, padded below)
-  static constexpr size_t smem_bytes(int nobs) {
-    return sizeof(double) * ((size_t)NY * nobs + (size_t)DRAWS * TILE) + ((NTAB + 15) / 16) * 16;
-  }
+  // doubles every lane keeps in registers: F, U, Pll, al, v, w, rdiag, one row of Tl and of Tl Pll
+  static constexpr int REG_DOUBLES = NY * (NY + 1) / 2 + NY * K + KK_N + K + 3 * NY + 2 * K;
+  static constexpr bool FITS = REG_DOUBLES <= 104 && NS <= 255;
+  static constexpr size_t smem_bytes(int nobs) { return sizeof(double) * ((size_t)NY * nobs + (size_t)DRAWS * TILE); }
 };
 
 template <class M, int G>
@@ -47,34 +44,14 @@ kalman_sublanes_kernel(const double* __restrict__ ss, long long n_draws, const d
   extern __shared__ double sm_ks[];
   double* ysh = sm_ks;                                        // NY x nobs
   double* tiles = ysh + (size_t)NY * nobs;
-  unsigned char* tab = reinterpret_cast<unsigned char*>(tiles + (size_t)C::DRAWS * C::TILE);
-  unsigned char* ps_ = tab;             // row of packed NS entry
-  unsigned char* pt_ = ps_ + QQ_N;      // column
-  unsigned char* kj_ = pt_ + QQ_N;      // row of packed K entry
-  unsigned char* kq_ = kj_ + KK_N;
-  unsigned char* lag_ = kq_ + KK_N;     // lagged_state_ids
-  unsigned char* obs_ = lag_ + K;       // obs_idx_state
   for (int i = threadIdx.x; i < NY * nobs; i += blockDim.x) ysh[i] = Y[i];
-  for (int e = threadIdx.x; e < QQ_N; e += blockDim.x) {
-    int r = 0, acc = 0;
-    while (e >= acc + r + 1) { acc += r + 1; ++r; }
-    ps_[e] = (unsigned char)r; pt_[e] = (unsigned char)(e - acc);
-  }
-  for (int e = threadIdx.x; e < KK_N; e += blockDim.x) {
-    int r = 0, acc = 0;
-    while (e >= acc + r + 1) { acc += r + 1; ++r; }
-    kj_[e] = (unsigned char)r; kq_[e] = (unsigned char)(e - acc);
-  }
-  for (int j = threadIdx.x; j < K; j += blockDim.x) lag_[j] = (unsigned char)M::lagged_state_ids(j);
-  for (int i = threadIdx.x; i < NY; i += blockDim.x) obs_[i] = (unsigned char)M::obs_idx_state(i);
 
   const int lg = threadIdx.x % G;
   long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const bool real = d < n_draws;
   if (!real) d = n_draws - 1;                                 // tail groups recompute the last draw and store nothing
   double* tl = tiles + (size_t)(threadIdx.x / G) * C::TILE;
-  double* Ps = tl + C::OFF_P; double* Qs = tl + C::OFF_QQ; double* Ts = tl + C::OFF_TL; double* Ms = tl + C::OFF_MR;
-  double* Us = tl + C::OFF_U; double* Pl = tl + C::OFF_PLL; double* als = tl + C::OFF_AL; double* as = tl + C::OFF_A;
+  double* Ps = tl + C::OFF_P; double* Qs = tl + C::OFF_QQ; double* Ts = tl + C::OFF_TL; double* as = tl + C::OFF_A;
   const double* s_ = ss + d;
   const long long st = n_draws;
   const int st_in = status_in[d];
@@ -96,7 +73,7 @@ kalman_sublanes_kernel(const double* __restrict__ ss, long long n_draws, const d
   int nseen = 0;
   bool bad = false;
   for (int t = 0; t < nobs; ++t) {
-    // ---- 1. innovation, its covariance and Cholesky factor: every lane ---------------------------------
+    // ---- measurement update, every lane in registers (as kalman_kernel<M>) ------------------------------------
     double v[NY], F[NY * (NY + 1) / 2], rdiag[NY], w[NY];
     bool miss[NY];
     int nobs_t = 0;
@@ -150,59 +127,63 @@ kalman_sublanes_kernel(const double* __restrict__ ss, long long n_draws, const d
       nseen += nobs_t;
     }
     if (t == nobs - 1) break;
-    // ---- 2. U = L^-1 (Z P)[:, lagged]: column j on lane j mod G -------------------------------------------
-    for (int j = lg; j < K; j += G) {
-      const int lj = lag_[j];
-      double u[NY];
+    double U[NY * K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
 #pragma unroll
       for (int i = 0; i < NY; ++i) {
-        const int oi = M::obs_idx_state(i);
-        double x = miss[i] ? 0.0 : Ps[oi >= lj ? tri(oi, lj) : tri(lj, oi)];
+        double x = miss[i] ? 0.0 : Ps[sym(M::obs_idx_state(i), M::lagged_state_ids(j))];
 #pragma unroll
-        for (int q = 0; q < i; ++q) x = fma(-F[tri(i, q)], u[q], x);
-        u[i] = x * rdiag[i];
-        Us[i + NY * j] = u[i];
+        for (int q = 0; q < i; ++q) x = fma(-F[tri(i, q)], U[q + NY * j], x);
+        U[i + NY * j] = x * rdiag[i];
       }
     }
-    __syncwarp(FULL);
-    // ---- 3. updated mean / covariance on the lagged states ------------------------------------------------------
-    for (int e = lg; e < KK_N; e += G) {
-      const int j = kj_[e], q = kq_[e];
-      const int lj = lag_[j], lq = lag_[q];
-      double pjq = Ps[lj >= lq ? tri(lj, lq) : tri(lq, lj)];
+    double al[K], Pll[KK_N];
 #pragma unroll
-      for (int i = 0; i < NY; ++i) pjq = fma(-Us[i + NY * j], Us[i + NY * q], pjq);
-      Pl[e] = pjq;
+    for (int j = 0; j < K; ++j) {
+      double x = as[M::lagged_state_ids(j)];
+#pragma unroll
+      for (int i = 0; i < NY; ++i) x = fma(U[i + NY * j], w[i], x);
+      al[j] = x;
+#pragma unroll
+      for (int q = 0; q <= j; ++q) {
+        double pjq = Ps[sym(M::lagged_state_ids(j), M::lagged_state_ids(q))];
+#pragma unroll
+        for (int i = 0; i < NY; ++i) pjq = fma(-U[i + NY * j], U[i + NY * q], pjq);
+        Pll[tri(j, q)] = pjq;
+      }
     }
-    for (int j = lg; j < K; j += G) {
-      double x = as[lag_[j]];
+    __syncwarp(FULL);                       // every lane has read a and P of this period
+    // ---- time update by rows: lane lg owns rows lg, lg + G, ... -------------------------------------------------
 #pragma unroll
-      for (int i = 0; i < NY; ++i) x = fma(Us[i + NY * j], w[i], x);
-      als[j] = x;
-    }
-    __syncwarp(FULL);
-    // ---- 4. Mrow = Tl Pll, a <- Tl al -----------------------------------------------------------------------------
-    for (int e = lg; e < NS * K; e += G) {
-      const int s = e / K, j = e - s * K;
-      double m = 0.0;
+    for (int r0 = 0; r0 < NS; r0 += G) {
+      const int s = r0 + lg;
+      if (s < NS) {
+        double trow[K], mrow[K];
 #pragma unroll
-      for (int q = 0; q < K; ++q) m = fma(Ts[s * K + q], Pl[q >= j ? tri(q, j) : tri(j, q)], m);
-      Ms[e] = m;
-    }
-    for (int s = lg; s < NS; s += G) {
-      double x = 0.0;
+        for (int j = 0; j < K; ++j) trow[j] = Ts[s * K + j];
+        double x = 0.0;
 #pragma unroll
-      for (int j = 0; j < K; ++j) x = fma(Ts[s * K + j], als[j], x);
-      as[s] = x;
-    }
-    __syncwarp(FULL);
-    // ---- 5. P <- R Q R' + Mrow Tl' -------------------------------------------------------------------------------
-    for (int e = lg; e < QQ_N; e += G) {
-      const int s = ps_[e], t2 = pt_[e];
-      double x2 = Qs[e];
+        for (int j = 0; j < K; ++j) x = fma(trow[j], al[j], x);
 #pragma unroll
-      for (int j = 0; j < K; ++j) x2 = fma(Ms[s * K + j], Ts[t2 * K + j], x2);
-      Ps[e] = x2;
+        for (int j = 0; j < K; ++j) {
+          double m = 0.0;
+#pragma unroll
+          for (int q = 0; q < K; ++q) m = fma(trow[q], Pll[sym(q, j)], m);
+          mrow[j] = m;
+        }
+        const int base = s * (s + 1) / 2;
+#pragma unroll
+        for (int t2 = 0; t2 < NS; ++t2) {
+          if (t2 <= s && t2 < r0 + G) {
+            double x2 = Qs[base + t2];
+#pragma unroll
+            for (int j = 0; j < K; ++j) x2 = fma(mrow[j], Ts[t2 * K + j], x2);
+            Ps[base + t2] = x2;
+          }
+        }
+        as[s] = x;
+      }
     }
     __syncwarp(FULL);
   }

@@ -3,6 +3,7 @@
 // solver and the generic dense Kalman filter.
 #include <algorithm>
 
+#include <atomic>
 #include "internal.h"
 #include "kalman_generic.cuh"
 #include "kalman_dmma.cuh"
@@ -37,9 +38,11 @@ void generic_release(dyb_handle* h) {
 
 // launch the dense Kalman filter on device-resident state spaces (shared by dyb_kalman_batch and the
 // from-Jacobian likelihood); scratch (2 ns^2 doubles per CTA) only when P and T P do not fit in shared memory
-static int g_kalman_variant = 0;      // 0 auto, 1 scalar (kalman_generic.cuh), 2 tensor-core (kalman_dmma.cuh)
-static int g_kalman_lanes_max = 16;   // auto choice: sub-warp kernel up to this many states
-static int g_kalman_bulk = 1;         // large-ns kernel: stage the GEMM panels with cp.async.bulk when alignment allows
+// PROCESS-WIDE A/B switches set by dyb_set_kalman_variant (every handle, device and thread reads them; atomics so that
+// a concurrent reader sees a consistent value -- a test that toggles them changes the kernel other handles use)
+static std::atomic<int> g_kalman_variant{0};      // 0 auto, 1 scalar (kalman_generic.cuh), 2 tensor-core (kalman_dmma.cuh)
+static std::atomic<int> g_kalman_lanes_max{16};   // auto choice: sub-warp kernel up to this many states
+static std::atomic<int> g_kalman_bulk{1};         // large-ns kernel: stage the GEMM panels with cp.async.bulk when alignment allows
 
 static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaStream_t st, Stager& sg) {
   int dev_sms = 148, max_smem = 0;

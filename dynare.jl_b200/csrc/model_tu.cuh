@@ -79,7 +79,7 @@ cudaError_t mt_kalman_sub(const double* d_ss, long long n, const double* d_Y, in
 // leave schedulers idle; `want` = dyb_options.filter_lanes (0 = choose by batch width)
 int mt_kalman_lanes(long long n, int nobs, int want) {
   int g = want;
-  if (g != 1 && g != 4 && g != 8) g = (n <= 8192) ? 8 : 1;
+  if (g != 1 && g != 4 && g != 8) g = (n <= 4096) ? 8 : 1;
   if (g == 4 && (!KalmanSubCfg<MT, 4>::FITS || KalmanSubCfg<MT, 4>::smem_bytes(nobs) > 200 * 1024)) g = 8;
   if (g == 8 && (!KalmanSubCfg<MT, 8>::FITS || KalmanSubCfg<MT, 8>::smem_bytes(nobs) > 200 * 1024)) g = 1;
   return g;

@@ -384,7 +384,7 @@ int dyb_transform_batch(dyb_handle* h, const double* in, int64_t n, int32_t inve
   Stager sg(h->stream);
   const double* din = sg.in(in, (size_t)ps.np * n);
   double* dout = sg.out(out, (size_t)ps.np * n);
-  double* dlj = sg.out(logjac, (size_t)n);
+  double* dlj = inverse ? nullptr : sg.out(logjac, (size_t)n);      // the inverse map writes no log-Jacobian
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
   transform_kernel<<<nblk(n, 128), 128, 0, h->stream>>>(ps, din, n, inverse, dout, dlj);
   DYB_CUDA(cudaGetLastError());

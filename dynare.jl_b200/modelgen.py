@@ -146,7 +146,8 @@ class ModelSpec:
             est_type=self.est_type, est_i=self.est_i, est_j=self.est_j,
             est_names=[(e.name1 if e.name2 is None else f"{e.name1}:{e.name2}") for e in self.est],
             priors=[dict(kind=e.kind, shape=e.shape, mean=e.mean,
-                         stdev=(e.stdev if np.isfinite(e.stdev) else "inf")) for e in self.est],
+                         stdev=(e.stdev if np.isfinite(e.stdev) else "inf"),
+                         **({"domain": list(e.domain)} if e.domain is not None else {})) for e in self.est],
             theta_init=[float(v) for v in self.theta_init()],
             estimation_options=self.estimation_options,
         )
@@ -171,10 +172,11 @@ def build_spec(name: str, mf: ModFile) -> ModelSpec:
             def repl(m):
                 nonlocal changed
                 v, d, h = m.group(1), m.group(2), int(m.group(3))
+                if v in exo and h >= 1:
+                    raise NotImplementedError(f"lead / lag on the exogenous variable {v!r} (needs an auxiliary endogenous "
+                                              "variable, which the reference's preprocessor creates)")
                 if h < 2 or v not in endo:
                     return m.group(0)
-                if v in exo:
-                    raise NotImplementedError("leads/lags on exogenous variables")
                 sgn = 1 if d == "p" else -1
                 kind = "LEAD" if sgn > 0 else "LAG"
                 cur = v

@@ -19,6 +19,8 @@ statement is commented out with ``//``, which is how the reference's fixtures ca
 """
 from __future__ import annotations
 
+import ast
+import math
 import re
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
@@ -111,13 +113,29 @@ def _parse_prior_bang(stmt: str) -> Optional[EstimatedParam]:
         k, v = item.split("=", 1)
         kw[k.strip()] = v.strip()
     shape = _SHAPES[kw["shape"].lower()]
-    mean = _num(kw["mean"])
-    stdev = _num(kw["stdev"]) if "stdev" in kw else _num(kw["variance"]) ** 0.5
     init = _num(kw["initialvalue"]) if "initialvalue" in kw else None
     dom = None
-    if "domain" in kw:
+    if "domain" in kw and kw["domain"].strip() not in ("[]", ""):
         lo, hi = _split_top(kw["domain"].strip()[1:-1])
         dom = (_num(lo), _num(hi))
+    # mean / stdev are optional (`missing` in the reference) when a Uniform prior is given by its domain
+    # (src/estimation/priors.jl:165-170): the moments of U(a, b) stand in for them
+    if "mean" in kw:
+        mean = _num(kw["mean"])
+    elif shape == "uniform" and dom is not None:
+        mean = 0.5 * (dom[0] + dom[1])
+    else:
+        raise ValueError(f"prior!({args[0]}): `mean` is required for shape {shape}")
+    if "stdev" in kw:
+        stdev = _num(kw["stdev"])
+    elif "variance" in kw:
+        stdev = _num(kw["variance"]) ** 0.5
+    elif shape == "uniform" and dom is not None:
+        stdev = (dom[1] - dom[0]) / 12 ** 0.5
+    else:
+        raise ValueError(f"prior!({args[0]}): `stdev` or `variance` is required for shape {shape}")
+    if dom is not None and shape != "uniform":
+        dom = None                                   # the reference reads `domain` for the Uniform shape only
     return EstimatedParam(kind, n1, n2, shape, mean, stdev, init, dom)
 
 
@@ -127,9 +145,30 @@ def _num(s: str) -> float:
         return float("inf")
     if s == "-inf":
         return float("-inf")
-    import math
-    env = {k: getattr(math, k) for k in ("sqrt", "exp", "log", "pi")}
-    return float(eval(s.replace("^", "**"), {"__builtins__": {}}, env))
+    return float(_eval_numeric(ast.parse(s.replace("^", "**"), mode="eval").body))
+
+
+_NUM_FUNCS = {"sqrt": math.sqrt, "exp": math.exp, "log": math.log}
+_NUM_BINOPS = {ast.Add: lambda a, b: a + b, ast.Sub: lambda a, b: a - b, ast.Mult: lambda a, b: a * b,
+               ast.Div: lambda a, b: a / b, ast.Pow: lambda a, b: a ** b}
+
+
+def _eval_numeric(node) -> float:
+    """Numeric literals of a mod file (e.g. ``(0.20*0.579923)``, ``1.25^2``, ``sqrt(2)``): a whitelist walk over the
+    syntax tree -- numbers, + - * / ^, unary sign, sqrt / exp / log, pi -- never ``eval``."""
+    if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
+        return float(node.value)
+    if isinstance(node, ast.BinOp) and type(node.op) in _NUM_BINOPS:
+        return _NUM_BINOPS[type(node.op)](_eval_numeric(node.left), _eval_numeric(node.right))
+    if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+        v = _eval_numeric(node.operand)
+        return -v if isinstance(node.op, ast.USub) else v
+    if isinstance(node, ast.Name) and node.id == "pi":
+        return math.pi
+    if (isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in _NUM_FUNCS
+            and len(node.args) == 1 and not node.keywords):
+        return _NUM_FUNCS[node.func.id](_eval_numeric(node.args[0]))
+    raise ValueError("unsupported numeric expression in the mod file")
 
 
 def _strip_comments(text: str) -> Tuple[str, List[str]]:
@@ -272,13 +311,22 @@ def parse_mod(text: str) -> ModFile:
                 else:
                     kind, n1, n2 = "param", head[0], None
                     rest = parts[1:]
-                # forms:  shape, mean, std   |   init, shape, mean, std  |  init, lb, ub, shape, mean, std
+                # forms:  shape, mean, std [, p3, p4 [, scale]]  |  init, shape, ...  |  init, lb, ub, shape, ...
+                # lb / ub are optimiser bounds the reference does not read (src/estimation/priors.jl:411-424); a uniform
+                # prior with empty mean and std is U(p3, p4) (parse_prior_distribution(::Val{5}), priors.jl:508-517)
                 si = next(i for i, p in enumerate(rest) if p.lower() in _SHAPES)
                 init = _num(rest[0]) if si >= 1 and rest[0] else None
                 shape = _SHAPES[rest[si].lower()]
-                mean = _num(rest[si + 1])
-                std = _num(rest[si + 2])
-                mf.estimated_params.append(EstimatedParam(kind, n1, n2, shape, mean, std, init))
+                tail = rest[si + 1:] + [""] * 4
+                dom = None
+                if shape == "uniform" and not tail[0] and not tail[1]:
+                    if not (tail[2] and tail[3]):
+                        raise ValueError(f"uniform prior of {n1}: give mean and std, or p3 and p4")
+                    dom = (_num(tail[2]), _num(tail[3]))
+                    mean, std = 0.5 * (dom[0] + dom[1]), (dom[1] - dom[0]) / 12 ** 0.5
+                else:
+                    mean, std = _num(tail[0]), _num(tail[1])
+                mf.estimated_params.append(EstimatedParam(kind, n1, n2, shape, mean, std, init, dom))
             elif block == "estimated_params_init":
                 parts = [p.strip() for p in flat.split(",")]
                 head = parts[0].split()

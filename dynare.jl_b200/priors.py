@@ -123,8 +123,11 @@ class Prior:
         raise ValueError(self.shape)
 
 
-def make_prior(shape: str, mean: float, stdev: float) -> Prior:
-    """``prior_`` (priors.jl:147-178)."""
+def make_prior(shape: str, mean: float, stdev: float, domain=None) -> Prior:
+    """``prior_`` (priors.jl:147-178).  ``domain`` = (a, b) gives the bounds of a Uniform prior directly
+    (priors.jl:165-170; ``p3, p4`` of an ``estimated_params`` row with empty mean and std, priors.jl:508-517)."""
+    if shape == "uniform" and domain is not None and len(domain) == 2:
+        return Prior(shape, float(domain[0]), float(domain[1]))
     var = stdev * stdev
     if shape == "beta":
         return Prior(shape, *beta_specification(mean, var))
@@ -154,7 +157,7 @@ class PriorSet:
         out = []
         for d in desc:
             sd = float("inf") if d["stdev"] == "inf" else float(d["stdev"])
-            out.append(make_prior(d["shape"], float(d["mean"]), sd))
+            out.append(make_prior(d["shape"], float(d["mean"]), sd, d.get("domain")))
         return cls(out)
 
     def __len__(self):

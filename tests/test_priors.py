@@ -53,3 +53,49 @@ def test_prior_set_sum_and_sampling_support():
     assert np.all(np.isfinite(lp))
     one = sum(p.logpdf(np.array([th[5, k]]))[0] for k, p in enumerate(ps.priors))
     assert math.isclose(lp[5], one, rel_tol=1e-13)
+
+
+def test_uniform_prior_from_domain():
+    """`prior!(:x, shape=Uniform, domain=[a, b])` takes (a, b) as the bounds and lets mean / stdev be missing
+    (src/estimation/priors.jl:165-170); an `estimated_params` row with empty mean and std takes p3, p4
+    (parse_prior_distribution(::Val{5}), priors.jl:508-517); the lb / ub columns are not read."""
+    from dynare_jl_b200.modfile import parse_mod
+    text = """
+    var y; varexo e; parameters rho sig tau;
+    rho = 0.5; sig = 1; tau = 0.2;
+    model; y = rho*y(-1) + sig*tau*e; end;
+    shocks; var e; stderr 1; end;
+    prior!(:rho, shape=Uniform, domain=[0, 1])
+    prior!(:sig, shape=Uniform, mean=1.0, stdev=0.5, domain=[0.2, 3.0])
+    prior!(:tau, shape=Uniform, mean=1.0, stdev=0.5)
+    varobs y;
+    """
+    mf = parse_mod(text)
+    eps = {e.name1: e for e in mf.estimated_params}
+    assert eps["rho"].domain == (0.0, 1.0) and eps["rho"].mean == 0.5 and abs(eps["rho"].stdev - 1 / 12 ** 0.5) < 1e-15
+    assert eps["sig"].domain == (0.2, 3.0) and eps["tau"].domain is None
+    pr = {k: make_prior(e.shape, e.mean, e.stdev, e.domain) for k, e in eps.items()}
+    assert (pr["rho"].a, pr["rho"].b) == (0.0, 1.0)
+    assert (pr["sig"].a, pr["sig"].b) == (0.2, 3.0)                     # the domain wins over the moments
+    assert abs(pr["tau"].a - (1.0 - 0.5 * 3 ** 0.5)) < 1e-15 and abs(pr["tau"].b - (1.0 + 0.5 * 3 ** 0.5)) < 1e-15
+    assert pr["rho"].logpdf(np.array([0.3]))[0] == 0.0 and pr["rho"].logpdf(np.array([1.2]))[0] == -np.inf
+    # the spec / JSON route keeps the domain
+    ps = PriorSet.from_description([dict(shape="uniform", mean=0.5, stdev=0.1, domain=[0.0, 1.0]),
+                                    dict(shape="uniform", mean=0.5, stdev=0.1)])
+    assert (ps.priors[0].a, ps.priors[0].b) == (0.0, 1.0) and ps.priors[1].a > 0.3
+    block = """
+    var y; varexo e; parameters rho sig;
+    rho = 0.5; sig = 1;
+    model; y = rho*y(-1) + sig*e; end;
+    shocks; var e; stderr 1; end;
+    estimated_params;
+    rho, 0.4, 0.01, 0.99, uniform_pdf, , , 0.1, 0.9;
+    sig, uniform_pdf, 1.0, 0.2;
+    end;
+    varobs y;
+    """
+    mf2 = parse_mod(block)
+    e0, e1 = mf2.estimated_params
+    assert e0.domain == (0.1, 0.9) and e0.init == 0.4 and e1.domain is None
+    p0 = make_prior(e0.shape, e0.mean, e0.stdev, e0.domain)
+    assert (p0.a, p0.b) == (0.1, 0.9)

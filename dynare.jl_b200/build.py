@@ -54,7 +54,7 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
     return LIB
 
 
-def build_model_library(name: str, mod_path: str, out_dir: str) -> str:
+def build_model_library(name: str, mod_path: str, out_dir: str, spec=None) -> str:
     """Compile ONE user model into its own shared object (the run-time analogue of Dynare's `use_dll`):
     .mod text -> device model function (modelgen) -> nvcc -> <out_dir>/libdynare_b200_model_<name>.so.
     Loading it (engine.load_model_library) registers the model with libdynare_b200.so, after which
@@ -62,7 +62,8 @@ def build_model_library(name: str, mod_path: str, out_dir: str) -> str:
     from . import modelgen
     build_library()
     os.makedirs(out_dir, exist_ok=True)
-    spec = modelgen.spec_from_file(name, mod_path)
+    if spec is None:                                  # else: a ModelSpec built elsewhere (preprocessor.spec_from_preprocessor)
+        spec = modelgen.spec_from_file(name, mod_path)
     cuh = os.path.join(out_dir, f"model_{name}.cuh")
     cu = os.path.join(out_dir, f"model_{name}.cu")
     with open(cuh, "w") as f:

@@ -87,6 +87,10 @@ class ModelSpec:
     # numerical steady state (no steady_state_model block): Newton from `initval` on the static model
     ss_numeric: bool = False
     static_jac: Dict[Tuple[int, int], sp.Expr] = field(default_factory=dict)   # (row, variable) -> d static_resid / d y
+    # the dynamic residuals before the steady state is substituted, with their lag / lead / shock symbols
+    # (kept for tooling that writes the model out again, e.g. scripts/write_preprocessor_sample.py)
+    dyn_resid: List[sp.Expr] = field(default_factory=list)
+    dyn_syms: Dict[str, List[sp.Symbol]] = field(default_factory=dict)
 
     # sizes ------------------------------------------------------------------------------
     @property
@@ -381,6 +385,7 @@ def build_spec(name: str, mf: ModFile) -> ModelSpec:
         estimation_options=dict(mf.estimation_options),
         psym=psym, ysym=ysym, ss_assign=ss_assign, static_resid=static_resid, jac=jac,
         ss_numeric=ss_numeric, static_jac=static_jac,
+        dyn_resid=list(resid), dyn_syms=dict(lag=ym, lead=yp, exo=usym),
     )
 
 

@@ -6,6 +6,8 @@
 # the closure `llikelihood` built for SMC (src/estimation/estimation.jl:316-326).
 module DynareB200
 
+using LinearAlgebra
+
 const LIB = get(ENV, "DYNARE_B200_LIB", "libdynare_b200.so")
 
 struct DybError <: Exception
@@ -238,6 +240,130 @@ function finite_difference_hessian(ws::BatchSSWs, x::Vector{Float64})
         H[i, j] = H[j, i] = (f[k] - f[k+1] - f[k+2] + f[k+3]) / (4h[i] * h[j]); k += 4
     end
     return H
+end
+
+
+# ---- the estimation ENTRY POINTS on `context` (mirrored 1:1 by dynare_jl_b200/estimation.py) ------------------------------
+# A Dynare.jl maintainer adds these as methods / replaces the bodies of the functions of the same names.
+#
+# device_model!(context): make the model of `context` known to the library.  The preprocessor has already written
+# <modfilepath>/model/json/modfile.json and <modfilepath>/model/julia/*.jl (that is what `context` was built from,
+# src/DynareParser.jl:10-15, 169-218; src/dynare_functions.jl:10-47); dynare_jl_b200.preprocessor translates exactly those
+# files into the CUDA model function, nvcc compiles it (~15 s, cached next to the model) and the shared object registers
+# the model under `name` when it is dlopen'ed.
+const MODEL_LIBS = Dict{String,Ptr{Cvoid}}()
+function device_model!(context; name = basename(context.modfileinfo.modfilepath),
+                       python = get(ENV, "DYNARE_B200_PYTHON", "python3"))
+    haskey(MODEL_LIBS, name) && return name
+    Libdl = Base.require(Base.PkgId(Base.UUID("8f399da3-3557-5675-b5ff-fb832c97cbdb"), "Libdl"))
+    Libdl.dlopen(LIB, Libdl.RTLD_GLOBAL | Libdl.RTLD_NOW)
+    outdir = joinpath(context.modfileinfo.modfilepath, "model", "b200")
+    lib = joinpath(outdir, "libdynare_b200_model_$(name).so")
+    if !isfile(lib) || mtime(lib) < mtime(joinpath(context.modfileinfo.modfilepath, "model", "json", "modfile.json"))
+        run(`$python -m dynare_jl_b200.preprocessor $name $(context.modfileinfo.modfilepath) $outdir`)
+    end
+    MODEL_LIBS[name] = Libdl.dlopen(lib, Libdl.RTLD_GLOBAL | Libdl.RTLD_NOW)
+    return name
+end
+
+"`SSWs(context, observations, varobs)` replacement: device model + calibration + estimated-parameter map + priors."
+function BatchSSWs(context, observations::AbstractMatrix; device::Integer = 0)
+    ws = BatchSSWs(context, observations, device_model!(context); device = device)
+    set_priors!(ws, context.work.estimated_parameters.prior)
+    return ws
+end
+
+"""
+    smc_compute!(; context, datafile = "", first_obs = 1, last_obs = 0, nobs = 0, npart = 1000, nphi = 400, lam = 2.0, seed = 0)
+
+Replaces the body of `smc_compute!` (src/estimation/estimation.jl:298-327): the three closures it builds for `smc`
+(`pdraw!`, `logprior`, `llikelihood`) disappear -- prior density, likelihood, reweighting, resampling and mutation all run
+on the device; only `prior_draw!(θ, ep)` (estimation.jl:329-333) stays on the host for the initial particles.
+"""
+function smc_compute!(; context, datafile = "", data = nothing, first_obs = 1, last_obs = 0, nobs = 0,
+                      npart = 1000, nphi = 400, lam = 2.0, seed = 0, device = 0)
+    ep = context.work.estimated_parameters
+    observations = Main.Dynare.get_observations(context, datafile, data, first_obs, last_obs, nobs)
+    ws = BatchSSWs(context, observations; device = device)
+    pdraw!(θ) = Main.Dynare.prior_draw!(θ, ep)
+    r = smc(ws, pdraw!; npart = npart, nphi = nphi, lam = lam, seed = seed)
+    μ = r.para * r.w                                        # posterior mean (smc.jl:283-290)
+    σ = sqrt.(max.(((r.para .- μ) .^ 2) * r.w, 0.0))
+    return (; r..., posterior_mean = μ, posterior_std = σ)
+end
+
+"""
+    rwmh_compute!(; context, datafile, data, initial_values, covariance, transformed_covariance, mcmc_chains, mcmc_jscale,
+                  mcmc_replic, transformed_parameters = true, seed = 0, ...)
+
+Replaces `rwmh_compute!` -> `mh_estimation` -> `run_mcmc` (estimation.jl:233-279, 912-989): all `mcmc_chains` chains advance
+together, one batched posterior evaluation per sweep (the reference runs them on `MCMCThreads()` over ONE shared mutable
+`context`).  Returns the chain histories in parameter space (np × mcmc_chains × mcmc_replic) and the acceptance rates.
+"""
+function rwmh_compute!(; context, datafile = "", data = nothing, first_obs = 1, last_obs = 0, nobs = 0,
+                       initial_values = Main.Dynare.prior_mean(context.work.estimated_parameters),
+                       covariance = Matrix(Main.Dynare.prior_variance(context.work.estimated_parameters)),
+                       transformed_covariance = Matrix{Float64}(undef, 0, 0), mcmc_chains = 1, mcmc_jscale = 0.0,
+                       mcmc_replic = 0, transformed_parameters = true, seed = 0, device = 0)
+    observations = Main.Dynare.get_transposed_data!(context, datafile, data, context.work.observed_variables, first_obs, last_obs, nobs)
+    ws = BatchSSWs(context, observations; device = device)
+    np = ws.np
+    y0 = reshape(collect(Float64, initial_values), np, 1)
+    if transformed_parameters
+        y0 = transform(ws, y0; inverse = true)
+        Σ = isempty(transformed_covariance) ? covariance : transformed_covariance
+    else
+        Σ = covariance
+    end
+    Σ = mcmc_jscale .* (Σ .+ Σ') ./ 2                       # run_mcmc symmetrises (estimation.jl:966)
+    L = Matrix(cholesky(Σ).L)
+    y = repeat(y0, 1, mcmc_chains)
+    hist = Array{Float64,3}(undef, np, mcmc_chains, mcmc_replic); hlp = Matrix{Float64}(undef, mcmc_chains, mcmc_replic)
+    logp = Vector{Float64}(undef, mcmc_chains); acc = zeros(Int64, mcmc_chains)
+    GC.@preserve y L hist hlp check(ccall((:dyb_rwmh_run, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Int32, UInt32, Int32, Ptr{Float64}, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+        ws.handle, mcmc_chains, 0, mcmc_replic, 0, transformed_parameters ? 1 : 0, L, seed, y, logp, acc, hist, hlp))
+    if transformed_parameters                              # transform_chains! (estimation.jl:957-959)
+        hist = reshape(transform(ws, reshape(hist, np, :)), np, mcmc_chains, mcmc_replic)
+    end
+    return (chains = hist, logp = hlp, acceptance_rate = acc ./ max(mcmc_replic, 1))
+end
+
+"DSGETransformation (estimation.jl:465-487) for all columns of X: ℝ^np -> parameters, or back with `inverse = true`."
+function transform(ws::BatchSSWs, X::Matrix{Float64}; inverse = false)
+    out = similar(X); lj = Vector{Float64}(undef, size(X, 2))
+    GC.@preserve X check(ccall((:dyb_transform_batch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Float64}, Ptr{Float64}),
+                                ws.handle, X, size(X, 2), inverse ? 1 : 0, out, lj))
+    return out
+end
+
+"""
+    posterior_mode_hessians!(context, ws, minimizer)
+
+The two `finite_difference_hessian` calls of `posterior_mode!` (estimation.jl:873-890) -- at the transformed minimiser and at
+the mode in parameter space -- each as ONE batch of 1 + 4 np + 2 np (np - 1) posterior evaluations; fills the same result
+fields.  The optimiser itself (`dynare_optimize`, estimation.jl:864-872) keeps calling the scalar `loglikelihood(θ, ws)`.
+"""
+function posterior_mode_hessians!(context, ws::BatchSSWs, mode_parameters::Vector{Float64})
+    results = context.results.model_results[1].estimation
+    hess = finite_difference_hessian(ws, mode_parameters)
+    hsd = sqrt.(diag(hess))
+    invhess = inv(hess ./ (hsd * hsd')) ./ (hsd * hsd')
+    d = diag(invhess); d[d .< 0] .= NaN
+    results.posterior_mode = copy(mode_parameters)
+    results.posterior_mode_std = sqrt.(d)
+    results.posterior_mode_covariance = invhess
+    return results
+end
+
+"`run_simulations(context, draws)` (priorprediction.jl:64-98) for all rows of `draws` in one call; failure classes from the statuses."
+function run_simulations(context, draws::Matrix{Float64}; device = 0)
+    m = context.models[1]
+    ws = BatchSSWs(context, Matrix{Float64}(undef, length(context.work.observed_variables), 0); device = device)
+    ybar, sd, irfs, st = prior_predictive(ws, Matrix(draws'), m.endogenous_nbr, m.exogenous_nbr)
+    failure = Float64.(st .!= 0)
+    return failure, (steady_state = ybar, stdev = sd, irfs = irfs, domain = count(==(1), st), undetermined = count(==(2), st),
+                     unstable = count(==(3), st), other = count(>(3), st))
 end
 
 end # module

@@ -32,7 +32,8 @@ class ModelDims(C.Structure):
 class Options(C.Structure):
     _fields_ = [("cr_tol", C.c_double), ("cr_maxit", C.c_int32), ("steady_tol", C.c_double),
                 ("lyap_tol", C.c_double), ("lyap_maxit", C.c_int32), ("presample", C.c_int32),
-                ("solver", C.c_int32), ("filter_lanes", C.c_int32)]
+                ("solver", C.c_int32), ("filter_lanes", C.c_int32),
+                ("univariate_fallback", C.c_int32)]
 
 
 class SmcOptions(C.Structure):
@@ -96,6 +97,8 @@ SIGNATURES = {
     "dyb_forecast_batch": (C.c_int, [_P, _D, C.c_int64, C.c_int32, _D, _D, _I32]),
     "dyb_kalman_batch": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _D,
                                    _D, _D, _D, _D, _D, C.c_int64, _D, _I32]),
+    "dyb_kalman_batch_fallback": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _D,
+                                            _D, _D, _D, _D, _D, C.c_int64, C.c_int32, _D, _I32]),
     "dyb_smc_reweight": (C.c_int, [C.c_int, _D, _D, C.c_double, C.c_int64, _D,
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dyb_smc_resample_multinomial": (C.c_int, [C.c_int, _D, _D, C.c_int64, _I64, C.POINTER(C.c_int64)]),

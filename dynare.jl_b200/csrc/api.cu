@@ -43,6 +43,7 @@ static void default_options(dyb_options* o) {
   o->presample = 0;
   o->solver = 0;
   o->filter_lanes = 0;
+  o->univariate_fallback = 0;
 }
 
 namespace dyb {
@@ -145,6 +146,7 @@ int dyb_destroy(dyb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   comm_release(h);
   generic_release(h);
+  h->d_uT.release(); h->d_uQ.release(); h->d_uP.release(); h->d_uyb.release(); h->d_uH.release(); h->d_uz.release(); h->d_uscr.release();
   h->d_theta.release(); h->d_ss.release(); h->d_st1.release(); h->d_ll.release(); h->d_st2.release(); h->d_Y.release(); h->d_mid.release();
   h->h_in.release(); h->h_out.release();
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -168,7 +170,8 @@ int dyb_set_options(dyb_handle* h, const dyb_options* opt) {
   if (!h || !opt) return fail(DYB_ERR_ARG, "null argument");
   if (!(opt->cr_tol > 0) || opt->cr_maxit < 1 || !(opt->steady_tol > 0) || !(opt->lyap_tol >= 0) ||
       opt->lyap_maxit < 1 || opt->presample < 0 || opt->solver < 0 || opt->solver > 2 ||
-      !(opt->filter_lanes == 0 || opt->filter_lanes == 1 || opt->filter_lanes == 4 || opt->filter_lanes == 8))
+      !(opt->filter_lanes == 0 || opt->filter_lanes == 1 || opt->filter_lanes == 4 || opt->filter_lanes == 8) ||
+      opt->univariate_fallback < 0 || opt->univariate_fallback > 2)
     return fail(DYB_ERR_ARG, "invalid option value");
   h->hs.opt = *opt;
   h->config_epoch += 1;
@@ -254,6 +257,10 @@ int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, dou
   DYB_CUDA(h->ops->kalman(h->d_ss.as<double>(), n, h->d_Y.as<double>(), h->nobs, h->hs.opt.presample, h->hs.opt.filter_lanes,
                           h->d_st1.as<int>(), d_loglik, d_status, h->stream));
   if (timed) DYB_CUDA(cudaEventRecord(ev[2], h->stream));
+  if (h->hs.opt.univariate_fallback) {
+    rc = univariate_fallback_from_handoff(h, n, h->d_st1.as<int>(), d_loglik, d_status);
+    if (rc) return rc;
+  }
   h->ev_valid = timed && (ev == h->ev);
   h->launches += 1 + h->ops->solve_launches(h->hs);
   return DYB_OK;

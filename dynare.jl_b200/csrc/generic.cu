@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include "internal.h"
+#include "kalman_univariate.cuh"
 #include "kalman_generic.cuh"
 #include "kalman_dmma.cuh"
 #include "kalman_dmma_large.cuh"
@@ -356,6 +357,48 @@ __global__ void __launch_bounds__(128) forecast_kernel(ForecastArgs a) {
 
 using namespace dyb;
 
+// the univariate fallback on the draws the production filter flagged (mode 1) / on every draw (mode 2)
+static cudaError_t launch_kalman_univariate(KalmanGenericArgs g, int mode, const int* status_in, int device, cudaStream_t st, DevBuf& scratch) {
+  int dev_sms = 148;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
+  long long blocks = g.n_draws < (long long)dev_sms * 8 ? g.n_draws : (long long)dev_sms * 8;
+  if (blocks < 1) return cudaSuccess;
+  cudaError_t e = scratch.reserve(sizeof(double) * 2 * (size_t)g.ns * g.ns * (size_t)blocks);
+  if (e != cudaSuccess) return e;
+  g.scratch = scratch.as<double>();
+  const size_t smem = kalman_univariate_smem_bytes(g.ns, g.ny);
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(kalman_univariate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kalman_univariate_kernel<<<(unsigned)blocks, 64, smem, st>>>(g, KalmanUnivariateSel{mode, status_in});
+  return cudaGetLastError();
+}
+
+namespace dyb {
+int univariate_fallback_from_handoff(dyb_handle* h, long long n, const int* d_status_solve, double* d_loglik, int* d_status) {
+  const dyb_model_dims& d = h->dims;
+  const size_t N = (size_t)n, ns2 = (size_t)d.ns * d.ns;
+  DYB_CUDA(h->d_uT.reserve(8 * ns2 * N)); DYB_CUDA(h->d_uQ.reserve(8 * ns2 * N)); DYB_CUDA(h->d_uP.reserve(8 * ns2 * N));
+  DYB_CUDA(h->d_uyb.reserve(8 * (size_t)d.ny * N)); DYB_CUDA(h->d_uH.reserve(8 * (size_t)d.ny * d.ny * N));
+  DYB_CUDA(h->d_uz.reserve(4 * (size_t)d.ny));
+  std::vector<int> z((size_t)d.ny);
+  h->ops->obs_state_positions(z.data());
+  DYB_CUDA(cudaMemcpyAsync(h->d_uz.p, z.data(), 4 * (size_t)d.ny, cudaMemcpyHostToDevice, h->stream));
+  DYB_CUDA(h->ops->unpack(h->d_ss.as<double>(), n, h->d_uT.as<double>(), h->d_uQ.as<double>(), h->d_uP.as<double>(),
+                          h->d_uyb.as<double>(), h->d_uH.as<double>(), h->stream));
+  KalmanGenericArgs g{};
+  g.ns = d.ns; g.ny = d.ny; g.nobs = h->nobs; g.presample = h->hs.opt.presample;
+  g.z_idx = h->d_uz.as<int>(); g.Y = h->d_Y.as<double>();
+  g.T = h->d_uT.as<double>(); g.RQR = h->d_uQ.as<double>(); g.P0 = h->d_uP.as<double>(); g.a0 = nullptr;
+  g.H = h->d_uH.as<double>(); g.ybar_obs = h->d_uyb.as<double>(); g.status_in = d_status_solve;
+  g.n_draws = n; g.loglik = d_loglik; g.status = d_status;
+  DYB_CUDA(launch_kalman_univariate(g, h->hs.opt.univariate_fallback, d_status_solve, h->device, h->stream, h->d_uscr));
+  h->launches += 2;
+  return DYB_OK;
+}
+}  // namespace dyb
+
 extern "C" {
 
 int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t presample,
@@ -390,6 +433,37 @@ int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t p
   return DYB_OK;
 }
 
+
+int dyb_kalman_batch_fallback(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t presample,
+                              const int32_t* z_idx, const double* Y, const double* T, const double* RQR,
+                              const double* P0, const double* a0, const double* H, int64_t n, int32_t mode,
+                              double* loglik, int32_t* status) {
+  if (ns <= 0 || ny <= 0 || ny > 64 || ny > ns || nobs < 0 || presample < 0 || n < 0 || mode < 1 || mode > 2)
+    return fail(DYB_ERR_ARG, "bad sizes (need 0 < ny <= min(ns, 64)) or mode (1, 2)");
+  if (n == 0) return DYB_OK;
+  if (!z_idx || !Y || !T || !RQR || !P0 || !loglik || !status) return fail(DYB_ERR_ARG, "null argument");
+  DYB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = device_stream(device);
+  Stager sg(st);
+  const size_t N = (size_t)n, ns2 = (size_t)ns * ns;
+  KalmanGenericArgs g{};
+  g.ns = ns; g.ny = ny; g.nobs = nobs; g.presample = presample;
+  g.z_idx = sg.in(z_idx, (size_t)ny);
+  g.Y = sg.in(Y, (size_t)ny * (nobs > 0 ? nobs : 1));
+  g.T = sg.in(T, ns2 * N); g.RQR = sg.in(RQR, ns2 * N); g.P0 = sg.in(P0, ns2 * N);
+  g.a0 = sg.in(a0, (size_t)ns * N); g.H = sg.in(H, (size_t)ny * ny * N);
+  g.n_draws = n; g.loglik = sg.out(loglik, N); g.status = sg.out(status, N);
+  if (!is_device_ptr(z_idx)) for (int i = 0; i < ny; ++i) if (z_idx[i] < 0 || z_idx[i] >= ns) return fail(DYB_ERR_ARG, "z_idx out of range");
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  g.scratch = nullptr;
+  DYB_CUDA(launch_kalman_generic(g, device, st, sg));
+  DevBuf scratch;
+  cudaError_t e = launch_kalman_univariate(g, mode, nullptr, device, st, scratch);
+  cudaError_t e2 = sg.finish();
+  scratch.release();
+  DYB_CUDA(e); DYB_CUDA(e2);
+  return DYB_OK;
+}
 
 int dyb_set_kalman_variant(int32_t variant) {
   if (variant < 0 || variant > 4)

@@ -138,6 +138,8 @@ struct PriorDev {
 struct Comm;        // NCCL communicator wrapper (sampler.cu)
 struct GenericHost; // run-time model description (generic.cu)
 void generic_release(dyb_handle* h);
+// dyb_options.univariate_fallback for the model-specific path: re-evaluates flagged draws from the hand-off buffer (generic.cu)
+int univariate_fallback_from_handoff(dyb_handle* h, long long n, const int* d_status_solve, double* d_loglik, int* d_status);
 }  // namespace dyb
 
 struct dyb_handle {
@@ -154,6 +156,7 @@ struct dyb_handle {
   bool timers_armed = false;
   dyb::HostState hs;
   dyb::DevBuf d_theta, d_ss, d_st1, d_ll, d_st2, d_Y, d_mid;
+  dyb::DevBuf d_uT, d_uQ, d_uP, d_uyb, d_uH, d_uz, d_uscr;     // dense state spaces of the univariate fallback (generic.cu)
   dyb::PinBuf h_in, h_out;
   int ny_obs = 0, nobs = 0;
   int64_t launches = 0;

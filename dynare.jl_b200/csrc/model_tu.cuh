@@ -132,11 +132,14 @@ void mt_bkwrd_indices(int* out) { for (int i = 0; i < MT::K; ++i) out[i] = MT::i
 
 void mt_obs_indices(int* out) { for (int i = 0; i < MT::NY; ++i) out[i] = MT::state_ids(MT::obs_idx_state(i)); }
 
+void mt_obs_state_positions(int* out) { for (int i = 0; i < MT::NY; ++i) out[i] = MT::obs_idx_state(i); }
+
 const ModelOps mt_ops = {
   MT::name,
   {MT::N, MT::NX, MT::NPAR, MT::K, MT::NF, MT::S, MT::NCOL, MT::NS, MT::NY, MT::NP_DEFAULT, SSLayout<MT>::SIZE, MidLayout<MT>::SIZE},
   MidLayout<MT>::SIZE,
-  mt_defaults, mt_solve_launches, mt_solve, mt_kalman, mt_unpack, mt_bkwrd_indices, mt_obs_indices
+  mt_defaults, mt_solve_launches, mt_solve, mt_kalman, mt_unpack, mt_bkwrd_indices, mt_obs_indices,
+  mt_obs_state_positions
 };
 
 struct Registrar { Registrar() { register_model(&mt_ops); } } mt_registrar;

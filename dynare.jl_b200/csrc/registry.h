@@ -42,6 +42,7 @@ struct ModelOps {
                         double* ybar_obs, double* H, cudaStream_t);
   void (*bkwrd_indices)(int* i_bkwrd_b /* dims.k */);   // variables with a lag, 0-based (Model.i_bkwrd_b)
   void (*obs_indices)(int* obs_idx /* dims.ny */);      // observed variable of each row of Y, 0-based
+  void (*obs_state_positions)(int* z_idx /* dims.ny */);   // position of each observable in the Kalman state (SSWs.obs_idx_state)
 };
 
 const std::vector<const ModelOps*>& registry();

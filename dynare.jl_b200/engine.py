@@ -481,9 +481,11 @@ def set_kalman_variant(variant: int):
     L.check(L.load().dyb_set_kalman_variant(variant))
 
 
-def kalman_batch(Y, z_idx, T, RQR, P0, a0=None, H=None, presample=0, device=0):
+def kalman_batch(Y, z_idx, T, RQR, P0, a0=None, H=None, presample=0, device=0, univariate_fallback=0):
     """Generic batched Kalman log-likelihood.  T, RQR, P0: (N, ns, ns) numpy (row-major per draw);
-    Y: ny x nobs; z_idx: state observed by each row.  Returns (loglik[N], status[N])."""
+    Y: ny x nobs; z_idx: state observed by each row.  Returns (loglik[N], status[N]).
+    ``univariate_fallback``: 1 = periods whose innovation covariance fails its Cholesky factorisation are processed one
+    observation at a time (KalmanFilterTools' behaviour), 2 = every period univariate (diagnostic)."""
     lib = L.load()
     T = np.asarray(T, dtype=np.float64)
     n, ns, _ = T.shape
@@ -496,8 +498,12 @@ def kalman_batch(Y, z_idx, T, RQR, P0, a0=None, H=None, presample=0, device=0):
     z = np.ascontiguousarray(z_idx, dtype=np.int32)
     Yf = np.asfortranarray(Y)
     ll = np.empty(n); st = np.empty(n, dtype=np.int32)
-    L.check(lib.dyb_kalman_batch(device, ns, ny, nobs, presample, L.ptr(z), L.ptr(Yf), L.ptr(Tc), L.ptr(Qc),
-                                 L.ptr(Pc), L.ptr(a0c), L.ptr(Hc), n, L.ptr(ll), L.ptr(st)))
+    if univariate_fallback:
+        L.check(lib.dyb_kalman_batch_fallback(device, ns, ny, nobs, presample, L.ptr(z), L.ptr(Yf), L.ptr(Tc), L.ptr(Qc),
+                                              L.ptr(Pc), L.ptr(a0c), L.ptr(Hc), n, int(univariate_fallback), L.ptr(ll), L.ptr(st)))
+    else:
+        L.check(lib.dyb_kalman_batch(device, ns, ny, nobs, presample, L.ptr(z), L.ptr(Yf), L.ptr(Tc), L.ptr(Qc),
+                                     L.ptr(Pc), L.ptr(a0c), L.ptr(Hc), n, L.ptr(ll), L.ptr(st)))
     return ll, st
 
 

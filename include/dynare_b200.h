@@ -82,6 +82,14 @@ typedef struct dyb_options {
   int32_t filter_lanes;     /* lanes per draw of the model-specific Kalman kernel: 0 auto (8 up to 4 096 draws per call, else
                              * 1), 1 = one thread per draw (throughput kernel), 4, 8 = shared-tile kernel for batches that
                              * leave schedulers idle (an SMC stage on a shard); same sums in the same order */
+  int32_t univariate_fallback; /* what a period whose innovation covariance F fails its Cholesky factorisation does:
+                             * 0 (default) the draw is rejected (status 6, loglik -Inf); 1 the period is processed one observation
+                             * at a time, observations with conditional variance <= 1e-10 skipped -- the behaviour of
+                             * KalmanFilterTools' kalman_likelihood, the package behind the reference call
+                             * src/estimation/estimation.jl:671-700 (restated from the published package: its source is not in
+                             * the reference tree); needs diagonal measurement-error covariances; 2 every period of every draw
+                             * univariate (diagnostic: must reproduce the multivariate likelihood).  Flagged draws are
+                             * re-evaluated by a slow dense kernel; the production kernels are untouched. */
 } dyb_options;
 
 /* ---- library / registry ------------------------------------------------------------------- */
@@ -217,6 +225,13 @@ int dyb_kalman_batch(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t p
                      const int32_t* z_idx, const double* Y,
                      const double* T, const double* RQR, const double* P0, const double* a0,
                      const double* H, int64_t n_draws, double* loglik, int32_t* status);
+
+/* dyb_kalman_batch followed by the univariate fallback (see dyb_options.univariate_fallback; mode 1 or 2) on the draws
+ * whose innovation covariance was not positive definite */
+int dyb_kalman_batch_fallback(int device, int32_t ns, int32_t ny, int32_t nobs, int32_t presample,
+                              const int32_t* z_idx, const double* Y,
+                              const double* T, const double* RQR, const double* P0, const double* a0,
+                              const double* H, int64_t n_draws, int32_t mode, double* loglik, int32_t* status);
 
 /* which dense filter kernel dyb_kalman_batch / dyb_loglik_from_jacobian_batch use: 0 auto (four / eight lanes per draw up to
  * ns = 16 and ny = 8, tensor-core kernels up to ns = 256, scalar kernel beyond), 1 scalar, 2 tensor-core (fp64 mma.sync),

@@ -203,10 +203,18 @@ def state_space(model, sol, sigma_e, sigma_m, Sigma_y):
 # -----------------------------------------------------------------------------------------
 # a-9  Kalman log-likelihood  (reference ``kalman_likelihood`` call, estimation.jl:671-700)
 # -----------------------------------------------------------------------------------------
-def kalman_likelihood(Y, Z, H, T, R, Q, a0, P0, start=0, last=None, presample=0):
+KALMAN_TOL = 1e-10          # KalmanFilterTools' `kalman_tol` [recalled from the package source, not vendored]
+
+
+def kalman_likelihood(Y, Z, H, T, R, Q, a0, P0, start=0, last=None, presample=0, univariate_fallback=0):
     """-1/2 [ nobs*ny*log(2 pi) + sum_t ( log det F_t + v_t' F_t^-1 v_t ) ].
     Missing observations are NaN in Y: rows are dropped for that period (the ``data_pattern``
-    variant, estimation.jl:665-685) and the constant counts only observed entries."""
+    variant, estimation.jl:665-685) and the constant counts only observed entries.
+
+    univariate_fallback (KalmanFilterTools' behaviour behind the call at estimation.jl:671-700, [recalled]: when the
+    Cholesky factorisation of F_t fails the period is processed one observation at a time, an observation whose
+    conditional variance is below ``kalman_tol`` being skipped): 0 = off (a failed factorisation rejects the draw),
+    1 = on, 2 = every period univariate (diagnostic).  The univariate step needs a diagonal H."""
     ny, nobs = Y.shape
     last = nobs if last is None else last
     a = a0.astype(float).copy()
@@ -221,10 +229,33 @@ def kalman_likelihood(Y, Z, H, T, R, Q, a0, P0, start=0, last=None, presample=0)
             v = Y[obs, t] - Zt @ a
             F = Zt @ P @ Zt.T + H[np.ix_(obs, obs)]
             F = 0.5 * (F + F.T)
-            try:
-                cF = np.linalg.cholesky(F)
-            except np.linalg.LinAlgError:
-                raise DrawFailure(ST_F_NOT_PD)
+            cF = None
+            if univariate_fallback != 2:
+                try:
+                    cF = np.linalg.cholesky(F)
+                except np.linalg.LinAlgError:
+                    if not univariate_fallback:
+                        raise DrawFailure(ST_F_NOT_PD)
+            if cF is None:
+                Hd = H[np.ix_(obs, obs)]
+                if np.any(Hd - np.diag(np.diag(Hd)) != 0):
+                    raise DrawFailure(ST_F_NOT_PD)
+                for q, i in enumerate(obs):
+                    z = Z[i, :]
+                    Fi = z @ P @ z + H[i, i]
+                    if Fi > KALMAN_TOL:
+                        vi = Y[i, t] - z @ a
+                        K = (P @ z) / Fi
+                        a = a + K * vi
+                        P = P - np.outer(K, K) * Fi
+                        if t >= start + presample:
+                            lik += np.log(Fi) + vi * vi / Fi
+                if t >= start + presample:
+                    ncount += obs.size
+                a = T @ a
+                P = T @ P @ T.T + QQ
+                P = 0.5 * (P + P.T)
+                continue
             w = sla.solve_triangular(cF, v, lower=True)
             PZt = P @ Zt.T
             U = sla.solve_triangular(cF, PZt.T, lower=True)          # L^-1 Z P

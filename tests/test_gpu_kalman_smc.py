@@ -139,3 +139,59 @@ def test_dense_filter_kernels_agree_with_initial_state_presample_and_correlated_
         for variant in (1, 2, 4):
             ll, st = res[variant]
             assert st[i] == 0 and abs(ll[i] - ref) <= 1e-8 * abs(ref), (variant, i, ll[i], ref)
+
+
+def test_univariate_fallback_dense():
+    """dyb_kalman_batch_fallback: mode 2 (every period one observation at a time) reproduces the multivariate filter for
+    diagonal H; an exactly singular innovation covariance is status 6 without the fallback and the oracle's value with it."""
+    import scipy.linalg as sla
+    from dynare_jl_b200.engine import kalman_batch
+    from oracle import pipeline as pl
+    rng = np.random.default_rng(21)
+    for ns, ny, nobs in ((3, 2, 40), (10, 5, 79), (40, 7, 30)):
+        n = 12
+        T = np.empty((n, ns, ns)); QQ = np.empty_like(T); P0 = np.empty_like(T)
+        for i in range(n):
+            Qo, _ = np.linalg.qr(rng.standard_normal((ns, ns)))
+            T[i] = Qo @ np.diag(rng.uniform(0.3, 0.95, ns)) @ Qo.T
+            R = 0.2 * rng.standard_normal((ns, ny)); QQ[i] = R @ R.T
+            P0[i] = sla.solve_discrete_lyapunov(T[i], QQ[i])
+        H = np.tile(np.diag(rng.uniform(0.0, 0.05, ny)), (n, 1, 1))
+        Y = rng.standard_normal((ny, nobs)); Y[0, 3] = np.nan
+        a, sa = kalman_batch(Y, np.arange(ny), T, QQ, P0, H=H)
+        b, sb = kalman_batch(Y, np.arange(ny), T, QQ, P0, H=H, univariate_fallback=2)
+        c, sc = kalman_batch(Y, np.arange(ny), T, QQ, P0, H=H, univariate_fallback=1)
+        assert np.all(sa == 0) and np.all(sb == 0) and np.all(sc == 0)
+        assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-10 and np.array_equal(a, c)
+        ref = pl.kalman_likelihood(Y, np.eye(ny, ns), H[0], T[0], np.eye(ns), QQ[0], np.zeros(ns), P0[0], univariate_fallback=2)
+        assert abs(b[0] - ref) <= 1e-10 * abs(ref)
+    T0 = np.zeros((2, 3, 3)); Q1 = np.array([[1.0, 1.0, 0.0], [1.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    QQ = np.stack([Q1, np.eye(3)])
+    Y2 = np.vstack([np.arange(1, 9) / 8.0] * 2)
+    ll0, st0 = kalman_batch(Y2, np.arange(2), T0, QQ, QQ)
+    assert st0[0] == 6 and st0[1] == 0 and ll0[0] == -np.inf
+    ll1, st1 = kalman_batch(Y2, np.arange(2), T0, QQ, QQ, univariate_fallback=1)
+    want = pl.kalman_likelihood(Y2, np.eye(2, 3), np.zeros((2, 2)), T0[0], np.eye(3), Q1, np.zeros(3), Q1, univariate_fallback=1)
+    assert np.all(st1 == 0) and abs(ll1[0] - want) <= 1e-13 * abs(want) and ll1[1] == ll0[1]
+
+
+@pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
+def test_univariate_fallback_model_path(name, golden):
+    """dyb_options.univariate_fallback on the model-specific path: 1 leaves every golden draw as it is (their F is positive
+    definite); 2 re-evaluates every draw one observation at a time and agrees wherever H is diagonal."""
+    from dynare_jl_b200.engine import BatchSSWs
+    g = golden(name)
+    ws = BatchSSWs(name, g["Y"])
+    base, sb = ws.loglikelihood(g["theta"])
+    ws.set_options(univariate_fallback=1)
+    one, s1 = ws.loglikelihood(g["theta"])
+    assert np.array_equal(base, one) and np.array_equal(sb, s1)
+    ws.set_options(univariate_fallback=2)
+    two, s2 = ws.loglikelihood(g["theta"])
+    _, sm = ws.shock_covariances(g["theta"])
+    diag_h = np.array([np.count_nonzero(m - np.diag(np.diag(m))) == 0 for m in sm])
+    ok = (sb == 0) & diag_h
+    assert ok.sum() >= 5 and np.all(s2[ok] == 0)
+    assert np.max(np.abs(two[ok] - base[ok]) / np.abs(base[ok])) <= 1e-9
+    assert np.all(s2[(sb == 0) & ~diag_h] == 6) and np.array_equal(s2[sb != 0], sb[sb != 0])
+    ws.close()

@@ -163,3 +163,32 @@ def test_smoother_oracle_matches_bruteforce_conditional_expectation():
     obs = ~np.isnan(Y)
     fit = Z @ sm["alphah"] + sm["epsilonh"]
     assert np.abs((fit - Y)[obs]).max() < 1e-10                  # y = Z alpha_hat + eps_hat where observed
+
+
+def test_univariate_fallback_of_the_oracle_filter():
+    """KalmanFilterTools' fallback as restated in oracle/pipeline.py: (i) all periods univariate == multivariate when H is
+    diagonal and F is positive definite; (ii) an exactly singular F rejects the draw with the fallback off and scores the
+    non-degenerate observation with it on (closed form)."""
+    rng = np.random.default_rng(11)
+    ns, ny, nobs = 5, 3, 30
+    Qo, _ = np.linalg.qr(rng.standard_normal((ns, ns)))
+    T = Qo @ np.diag(rng.uniform(0.2, 0.9, ns)) @ Qo.T
+    R = 0.3 * rng.standard_normal((ns, ny)); Q = np.eye(ny)
+    H = np.diag([0.01, 0.0, 0.02])
+    Z = np.eye(ny, ns)
+    import scipy.linalg as sla
+    P0 = sla.solve_discrete_lyapunov(T, R @ R.T)
+    Y = rng.standard_normal((ny, nobs)); Y[1, 4] = np.nan
+    a = pl.kalman_likelihood(Y, Z, H, T, R, Q, np.zeros(ns), P0)
+    b = pl.kalman_likelihood(Y, Z, H, T, R, Q, np.zeros(ns), P0, univariate_fallback=2)
+    c = pl.kalman_likelihood(Y, Z, H, T, R, Q, np.zeros(ns), P0, univariate_fallback=1)
+    assert abs(a - b) <= 1e-10 * abs(a) and a == c
+    # two observables that are the same state plus no measurement error: F = [[1, 1], [1, 1]] exactly
+    T0 = np.zeros((3, 3)); QQ = np.array([[1.0, 1.0, 0.0], [1.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    Y2 = np.vstack([np.arange(1, 9) / 8.0] * 2)
+    Z2 = np.eye(2, 3)
+    with pytest.raises(pl.DrawFailure):
+        pl.kalman_likelihood(Y2, Z2, np.zeros((2, 2)), T0, np.eye(3), QQ, np.zeros(3), QQ)
+    got = pl.kalman_likelihood(Y2, Z2, np.zeros((2, 2)), T0, np.eye(3), QQ, np.zeros(3), QQ, univariate_fallback=1)
+    want = -0.5 * (16 * np.log(2 * np.pi) + np.sum(Y2[0] ** 2))
+    assert abs(got - want) <= 1e-13 * abs(want)

@@ -242,6 +242,11 @@ int dyb_loglik_batch_device(dyb_handle* h, const double* d_theta, int64_t n, dou
   if (h->nobs <= 0 && h->d_Y.p == nullptr) return fail(DYB_ERR_STATE, "dyb_set_observations has not been called");
   if (n == 0) return DYB_OK;
   DYB_CUDA(cudaSetDevice(h->device));
+  if (!h->ops->register_solver) {
+    // a model beyond the register-resident kernels: generated model function -> run-time-size solver -> dense filter
+    h->ev_valid = false;
+    return hybrid_loglik(h, d_theta, n, d_loglik, d_status);
+  }
   int rc = reserve_batch(h, n);
   if (rc) return rc;
   SolveOut so{h->d_ss.as<double>(), h->d_st1.as<int>(), nullptr, nullptr, nullptr, nullptr, h->d_mid.as<double>()};
@@ -496,6 +501,19 @@ int dyb_first_order_batch(dyb_handle* h, const double* theta, int64_t n, double*
   if (n == 0) return DYB_OK;
   DYB_CUDA(cudaSetDevice(h->device));
   const dyb_model_dims& d = h->dims;
+  if (!h->ops->register_solver) {
+    Stager sgh(h->stream);
+    const size_t Nh = (size_t)n;
+    const double* dth = sgh.in(theta, (size_t)h->hs.np * Nh);
+    double* dg1 = sgh.out(g1, (size_t)d.n * (d.k + d.nx) * Nh);
+    double* dyb = sgh.out(ybar, (size_t)d.n * Nh);
+    int* dci = sgh.out(cr_iters, Nh); int* dli = sgh.out(lyap_iters, Nh); int* dst = sgh.out(status, Nh);
+    if (sgh.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sgh.err));
+    int rch = hybrid_first_order(h, dth, n, dg1, dyb, dci, dli, dst);
+    if (rch) return rch;
+    DYB_CUDA(sgh.finish());
+    return DYB_OK;
+  }
   int rc = reserve_batch(h, n);
   if (rc) return rc;
   Stager sg(h->stream);
@@ -526,6 +544,8 @@ int dyb_state_space_batch(dyb_handle* h, const double* theta, int64_t n, double*
   if (n == 0) return DYB_OK;
   DYB_CUDA(cudaSetDevice(h->device));
   const dyb_model_dims& d = h->dims;
+  if (!h->ops->register_solver)
+    return fail(DYB_ERR_UNSUPPORTED, "dyb_state_space_batch: not available for models beyond the register-resident kernels (use dyb_first_order_batch / dyb_loglik_batch)");
   int rc = reserve_batch(h, n);
   if (rc) return rc;
   Stager sg(h->stream);

@@ -473,10 +473,8 @@ int dyb_set_kalman_variant(int32_t variant) {
   return DYB_OK;
 }
 
-// ---- handle from index sets alone --------------------------------------------------------------------------------
-int dyb_create_generic(const dyb_model_desc* md, int device, dyb_handle** out) {
-  if (!out) return fail(DYB_ERR_ARG, "out is null");
-  *out = nullptr;
+// ---- the run-time description (index arrays on the device, shared-memory plan) on an existing handle -----------------------
+static int generic_build(dyb_handle* h, const dyb_model_desc* md, dyb_model_dims* dims_out) {
   if (!md || md->n < 1 || md->nx < 1 || md->ny < 1 || md->n_static < 0 || md->n_bkwrd_b < 0 || md->n_fwrd_b < 0 ||
       md->n_static >= md->n || md->ny > 64 || (md->n_static > 0 && !md->i_static) || (md->n_bkwrd_b > 0 && !md->i_bkwrd_b) ||
       (md->n_fwrd_b > 0 && !md->i_fwrd_b) || !md->obs_idx)
@@ -517,47 +515,59 @@ int dyb_create_generic(const dyb_model_desc* md, int device, dyb_handle** out) {
   for (int i = 0; i < ny; ++i) obs_state[i] = pos_in_states(md->obs_idx[i]);
   for (int j = 0; j < k; ++j) lagged[j] = pos_in_states(md->i_bkwrd_b[j]);
 
-  int ndev = 0;
-  DYB_CUDA(cudaGetDeviceCount(&ndev));
-  if (device < 0 || device >= ndev) return fail(DYB_ERR_ARG, "no such CUDA device");
-  DYB_CUDA(cudaSetDevice(device));
+  DYB_CUDA(cudaSetDevice(h->device));
   int max_smem = 0;
-  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
   const size_t smem = sizeof(double) * generic_solve_smem_doubles(n, nx, ny, s, k, nf, ns);
   if (smem + 1024 > (size_t)max_smem)
     return fail(DYB_ERR_UNSUPPORTED, "model too large for the shared-memory generic solver (" + std::to_string(smem / 1024) + " KB per draw)");
-
-  dyb_handle* h = new dyb_handle();
-  h->device = device;
-  h->dims = dyb_model_dims{n, nx, 0, k, nf, s, ncol, ns, ny, 0, 0, 0};
-  h->hs.np = 0;
-  h->hs.opt.cr_tol = 1e-8; h->hs.opt.cr_maxit = 100; h->hs.opt.steady_tol = std::cbrt(2.220446049250313e-16);
-  h->hs.opt.lyap_tol = 1e-16; h->hs.opt.lyap_maxit = 60; h->hs.opt.presample = 0; h->hs.opt.solver = 0; h->hs.opt.filter_lanes = 0;
-  cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
-  h->stream = h->own_stream;
-  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
   GenericHost* gh = new GenericHost();
-  h->generic = gh;
   // pack the index arrays into one device buffer
   std::vector<int> pack;
   auto push = [&](const std::vector<int>& v) { const size_t off = pack.size(); pack.insert(pack.end(), v.begin(), v.end()); return off; };
   const size_t o_jperm = push(jperm), o_bk = push(bk), o_fw = push(fw), o_vs = push(var_static), o_vp = push(var_pos),
                o_sid = push(state_ids), o_ov = push(obs_var), o_lag = push(lagged);
-  if (e == cudaSuccess) e = gh->d_idx.reserve(sizeof(int) * pack.size());
+  cudaError_t e = gh->d_idx.reserve(sizeof(int) * pack.size());
   if (e == cudaSuccess) e = cudaMemcpy(gh->d_idx.p, pack.data(), sizeof(int) * pack.size(), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { dyb_destroy(h); return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
   const int* base = gh->d_idx.as<int>();
   gh->gm = GenericModel{n, nx, ny, s, k, nf, m, ncol, ns, base + o_jperm, base + o_bk, base + o_fw, base + o_vs, base + o_vp,
                         base + o_sid, base + o_ov, base + o_lag};
   gh->obs_state = obs_state;
   gh->smem = smem;
   gh->warp_groups = smem <= 24 * 1024;
-  if (gh->warp_groups) {
-    if (4 * smem > 48 * 1024) e = cudaFuncSetAttribute(solve_generic_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * smem));
-  } else if (smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(solve_generic_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    if (gh->warp_groups) {
+      if (4 * smem > 48 * 1024) e = cudaFuncSetAttribute(solve_generic_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * smem));
+    } else if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(solve_generic_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
   }
+  if (e != cudaSuccess) { gh->d_idx.release(); delete gh; return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
+  h->generic = gh;
+  if (dims_out) *dims_out = dyb_model_dims{n, nx, 0, k, nf, s, ncol, ns, ny, 0, 0, 0};
+  return DYB_OK;
+}
+
+// ---- handle from index sets alone --------------------------------------------------------------------------------
+int dyb_create_generic(const dyb_model_desc* md, int device, dyb_handle** out) {
+  if (!out) return fail(DYB_ERR_ARG, "out is null");
+  *out = nullptr;
+  int ndev = 0;
+  DYB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(DYB_ERR_ARG, "no such CUDA device");
+  DYB_CUDA(cudaSetDevice(device));
+  dyb_handle* h = new dyb_handle();
+  h->device = device;
+  h->hs.np = 0;
+  h->hs.opt.cr_tol = 1e-8; h->hs.opt.cr_maxit = 100; h->hs.opt.steady_tol = std::cbrt(2.220446049250313e-16);
+  h->hs.opt.lyap_tol = 1e-16; h->hs.opt.lyap_maxit = 60; h->hs.opt.presample = 0; h->hs.opt.solver = 0; h->hs.opt.filter_lanes = 0;
+  h->hs.opt.univariate_fallback = 0;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  h->stream = h->own_stream;
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
   if (e != cudaSuccess) { dyb_destroy(h); return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
+  const int rc = generic_build(h, md, &h->dims);
+  if (rc) { dyb_destroy(h); return rc; }
   *out = h;
   return DYB_OK;
 }
@@ -606,19 +616,61 @@ int dyb_first_order_from_jacobian_batch(dyb_handle* h, const double* jac, const 
   return DYB_OK;
 }
 
+// solve + dense filter from device-resident Jacobians (shared by dyb_loglik_from_jacobian_batch and the generated-model path
+// for models beyond the register-resident solver), in chunks that bound the working set of dense state spaces
+static int loglik_from_device_jacobians(dyb_handle* h, const double* djac, const double* dyb_, const double* dse, bool se_per_draw,
+                                        const double* dsm, bool sm_per_draw, const int* dsi, long long n, double* dll, int* dst,
+                                        Stager& sg) {
+  const dyb_model_dims& d = h->dims;
+  GenericHost* gh = h->generic;
+  const size_t ns2 = (size_t)d.ns * d.ns;
+  const long long chunk = std::max<long long>(1, std::min<long long>(n, (long long)((1ULL << 30) / (sizeof(double) * (3 * ns2 + d.ny * (d.ny + 1))))));
+  DYB_CUDA(gh->bT.reserve(sizeof(double) * ns2 * chunk)); DYB_CUDA(gh->bQ.reserve(sizeof(double) * ns2 * chunk));
+  DYB_CUDA(gh->bP.reserve(sizeof(double) * ns2 * chunk)); DYB_CUDA(gh->byo.reserve(sizeof(double) * d.ny * chunk));
+  DYB_CUDA(gh->bH.reserve(sizeof(double) * d.ny * d.ny * chunk)); DYB_CUDA(gh->bst.reserve(sizeof(int) * chunk));
+  DYB_CUDA(gh->bz.reserve(sizeof(int) * d.ny));
+  double* dT = gh->bT.as<double>(); double* dQ = gh->bQ.as<double>(); double* dP = gh->bP.as<double>();
+  double* dyo = gh->byo.as<double>(); double* dH = gh->bH.as<double>();
+  int* dst1 = gh->bst.as<int>();
+  int* dz = gh->bz.as<int>();
+  DYB_CUDA(cudaMemcpyAsync(dz, gh->obs_state.data(), sizeof(int) * d.ny, cudaMemcpyHostToDevice, h->stream));
+  for (long long lo = 0; lo < n; lo += chunk) {
+    const long long c = std::min<long long>(chunk, n - lo);
+    GenericSolveArgs a{};
+    a.jac = djac + (size_t)lo * d.n * d.ncol;
+    a.ybar = dyb_ ? dyb_ + (size_t)lo * d.n : nullptr;
+    a.sigma_e = dse + (se_per_draw ? (size_t)lo * d.nx * d.nx : 0);
+    a.stride_se = se_per_draw ? (long long)d.nx * d.nx : 0;
+    a.sigma_m = dsm ? dsm + (sm_per_draw ? (size_t)lo * d.ny * d.ny : 0) : nullptr;
+    a.stride_sm = sm_per_draw ? (long long)d.ny * d.ny : 0;
+    a.status_in = dsi ? dsi + lo : nullptr;
+    a.n_draws = c;
+    a.T = dT; a.RQR = dQ; a.P0 = dP; a.ybar_obs = dyo; a.H = dH; a.status = dst1;
+    int rc = generic_solve(h, a);
+    if (rc) return rc;
+    KalmanGenericArgs g{};
+    g.ns = d.ns; g.ny = d.ny; g.nobs = h->nobs; g.presample = h->hs.opt.presample;
+    g.z_idx = dz; g.Y = h->d_Y.as<double>(); g.T = dT; g.RQR = dQ; g.P0 = dP; g.a0 = nullptr; g.H = dH;
+    g.ybar_obs = dyo; g.status_in = dst1;
+    g.n_draws = c; g.loglik = dll + lo; g.status = dst + lo; g.scratch = nullptr;
+    DYB_CUDA(launch_kalman_generic(g, h->device, h->stream, sg));
+    if (h->hs.opt.univariate_fallback)
+      DYB_CUDA(launch_kalman_univariate(g, h->hs.opt.univariate_fallback, dst1, h->device, h->stream, h->d_uscr));
+    h->launches += 1;
+  }
+  return DYB_OK;
+}
+
 int dyb_loglik_from_jacobian_batch(dyb_handle* h, const double* jac, const double* ybar, const double* sigma_e,
                                    int32_t sigma_e_per_draw, const double* sigma_m, int32_t sigma_m_per_draw,
                                    const int32_t* status_in, int64_t n, double* loglik, int32_t* status) {
-  if (!h || !h->generic) return fail(DYB_ERR_ARG, "needs a handle made by dyb_create_generic");
+  if (!h || !h->generic || h->ops) return fail(DYB_ERR_ARG, "needs a handle made by dyb_create_generic");
   if (n < 0 || (n > 0 && (!jac || !sigma_e || !loglik || !status))) return fail(DYB_ERR_ARG, "null argument");
   if (h->d_Y.p == nullptr) return fail(DYB_ERR_STATE, "dyb_set_observations has not been called");
   if (n == 0) return DYB_OK;
   DYB_CUDA(cudaSetDevice(h->device));
   const dyb_model_dims& d = h->dims;
   GenericHost* gh = h->generic;
-  const size_t ns2 = (size_t)d.ns * d.ns;
-  // bounded working set: the dense state spaces of one chunk of draws
-  const long long chunk = std::max<long long>(1, std::min<long long>(n, (long long)((1ULL << 30) / (sizeof(double) * (3 * ns2 + d.ny * (d.ny + 1))))));
   Stager sg(h->stream);
   const size_t N = (size_t)n;
   // inputs: device pointers are used in place, host arrays go through persistent device buffers (pinned host memory from
@@ -638,41 +690,71 @@ int dyb_loglik_from_jacobian_batch(dyb_handle* h, const double* jac, const doubl
   if (se_ != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(se_));
   double* dll = sg.out(loglik, N);
   int* dst = sg.out(status, N);
-  DYB_CUDA(gh->bT.reserve(sizeof(double) * ns2 * chunk)); DYB_CUDA(gh->bQ.reserve(sizeof(double) * ns2 * chunk));
-  DYB_CUDA(gh->bP.reserve(sizeof(double) * ns2 * chunk)); DYB_CUDA(gh->byo.reserve(sizeof(double) * d.ny * chunk));
-  DYB_CUDA(gh->bH.reserve(sizeof(double) * d.ny * d.ny * chunk)); DYB_CUDA(gh->bst.reserve(sizeof(int) * chunk));
-  DYB_CUDA(gh->bz.reserve(sizeof(int) * d.ny));
-  double* dT = gh->bT.as<double>(); double* dQ = gh->bQ.as<double>(); double* dP = gh->bP.as<double>();
-  double* dyo = gh->byo.as<double>(); double* dH = gh->bH.as<double>();
-  int* dst1 = gh->bst.as<int>();
-  int* dz = gh->bz.as<int>();
   if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
-  DYB_CUDA(cudaMemcpyAsync(dz, gh->obs_state.data(), sizeof(int) * d.ny, cudaMemcpyHostToDevice, h->stream));
-  for (long long lo = 0; lo < n; lo += chunk) {
-    const long long c = std::min<long long>(chunk, n - lo);
-    GenericSolveArgs a{};
-    a.jac = djac + (size_t)lo * d.n * d.ncol;
-    a.ybar = dyb_ ? dyb_ + (size_t)lo * d.n : nullptr;
-    a.sigma_e = dse + (sigma_e_per_draw ? (size_t)lo * d.nx * d.nx : 0);
-    a.stride_se = sigma_e_per_draw ? (long long)d.nx * d.nx : 0;
-    a.sigma_m = dsm ? dsm + (sigma_m_per_draw ? (size_t)lo * d.ny * d.ny : 0) : nullptr;
-    a.stride_sm = sigma_m_per_draw ? (long long)d.ny * d.ny : 0;
-    a.status_in = dsi ? dsi + lo : nullptr;
-    a.n_draws = c;
-    a.T = dT; a.RQR = dQ; a.P0 = dP; a.ybar_obs = dyo; a.H = dH; a.status = dst1;
-    int rc = generic_solve(h, a);
-    if (rc) return rc;
-    KalmanGenericArgs g{};
-    g.ns = d.ns; g.ny = d.ny; g.nobs = h->nobs; g.presample = h->hs.opt.presample;
-    g.z_idx = dz; g.Y = h->d_Y.as<double>(); g.T = dT; g.RQR = dQ; g.P0 = dP; g.a0 = nullptr; g.H = dH;
-    g.ybar_obs = dyo; g.status_in = dst1;
-    g.n_draws = c; g.loglik = dll + lo; g.status = dst + lo; g.scratch = nullptr;
-    DYB_CUDA(launch_kalman_generic(g, h->device, h->stream, sg));
-    h->launches += 1;
-  }
+  int rc = loglik_from_device_jacobians(h, djac, dyb_, dse, sigma_e_per_draw != 0, dsm, sigma_m_per_draw != 0, dsi, n, dll, dst, sg);
+  if (rc) return rc;
   DYB_CUDA(sg.finish());
   return DYB_OK;
 }
+
+// ---- generated models beyond the register-resident solver: model function -> Jacobians on the device -> the path above ----
+static int hybrid_prepare(dyb_handle* h, const double* d_theta, long long n) {
+  const dyb_model_dims& d = h->dims;
+  if (!h->generic) {
+    std::vector<int> is((size_t)d.s), ib((size_t)d.k), ifw((size_t)d.nf), io((size_t)d.ny);
+    h->ops->static_indices(is.data()); h->ops->bkwrd_indices(ib.data()); h->ops->fwrd_indices(ifw.data()); h->ops->obs_indices(io.data());
+    dyb_model_desc md{d.n, d.nx, d.ny, d.s, d.k, d.nf, is.data(), ib.data(), ifw.data(), io.data()};
+    int rc = generic_build(h, &md, nullptr);
+    if (rc) return rc;
+  }
+  GenericHost* gh = h->generic;
+  const size_t N = (size_t)n;
+  DYB_CUDA(gh->bJ.reserve(sizeof(double) * d.n * d.ncol * N)); DYB_CUDA(gh->byb.reserve(sizeof(double) * d.n * N));
+  DYB_CUDA(gh->bse.reserve(sizeof(double) * d.nx * d.nx * N)); DYB_CUDA(gh->bsm.reserve(sizeof(double) * d.ny * d.ny * N));
+  DYB_CUDA(gh->bsi.reserve(sizeof(int) * N));
+  DYB_CUDA(h->ops->jacobian_batch(h->hs, d_theta, n, gh->bJ.as<double>(), gh->byb.as<double>(), gh->bse.as<double>(),
+                                  gh->bsm.as<double>(), gh->bsi.as<int>(), h->stream));
+  h->launches += 1;
+  return DYB_OK;
+}
+
+}  // extern "C"
+
+namespace dyb {
+int hybrid_loglik(dyb_handle* h, const double* d_theta, long long n, double* d_loglik, int* d_status) {
+  int rc = hybrid_prepare(h, d_theta, n);
+  if (rc) return rc;
+  GenericHost* gh = h->generic;
+  Stager sg(h->stream);
+  rc = loglik_from_device_jacobians(h, gh->bJ.as<double>(), gh->byb.as<double>(), gh->bse.as<double>(), true,
+                                    gh->bsm.as<double>(), true, gh->bsi.as<int>(), n, d_loglik, d_status, sg);
+  if (rc) return rc;
+  if (!sg.temps.empty()) DYB_CUDA(sg.finish());      // scratch of the large-state filter: released after the stream has drained
+  return DYB_OK;
+}
+
+// LRE.first_order_solver! for such a model: g1, ybar (may be null), iteration counts, status; device pointers
+int hybrid_first_order(dyb_handle* h, const double* d_theta, long long n, double* d_g1, double* d_ybar, int* d_cr_iters,
+                       int* d_lyap_iters, int* d_status) {
+  int rc = hybrid_prepare(h, d_theta, n);
+  if (rc) return rc;
+  const dyb_model_dims& d = h->dims;
+  GenericHost* gh = h->generic;
+  GenericSolveArgs a{};
+  a.jac = gh->bJ.as<double>(); a.ybar = gh->byb.as<double>();
+  a.sigma_e = gh->bse.as<double>(); a.stride_se = (long long)d.nx * d.nx;
+  a.sigma_m = gh->bsm.as<double>(); a.stride_sm = (long long)d.ny * d.ny;
+  a.status_in = gh->bsi.as<int>(); a.n_draws = n;
+  a.g1 = d_g1; a.status = d_status; a.cr_iters = d_cr_iters; a.lyap_iters = d_lyap_iters;
+  if (d_g1) DYB_CUDA(cudaMemsetAsync(d_g1, 0, sizeof(double) * (size_t)d.n * (d.k + d.nx) * (size_t)n, h->stream));
+  rc = generic_solve(h, a);
+  if (rc) return rc;
+  if (d_ybar) DYB_CUDA(cudaMemcpyAsync(d_ybar, gh->byb.p, sizeof(double) * (size_t)d.n * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+  return DYB_OK;
+}
+}  // namespace dyb
+
+extern "C" {
 
 int dyb_prior_predictive_batch(dyb_handle* h, const double* theta, int64_t n, int32_t periods, double* ybar, double* stdev,
                                 double* irfs, int32_t* status) {

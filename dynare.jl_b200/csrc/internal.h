@@ -139,6 +139,10 @@ struct Comm;        // NCCL communicator wrapper (sampler.cu)
 struct GenericHost; // run-time model description (generic.cu)
 void generic_release(dyb_handle* h);
 // dyb_options.univariate_fallback for the model-specific path: re-evaluates flagged draws from the hand-off buffer (generic.cu)
+// generated models beyond the register-resident solver (ModelOps::register_solver == false): generic.cu
+int hybrid_loglik(dyb_handle* h, const double* d_theta, long long n, double* d_loglik, int* d_status);
+int hybrid_first_order(dyb_handle* h, const double* d_theta, long long n, double* d_g1, double* d_ybar, int* d_cr_iters,
+                       int* d_lyap_iters, int* d_status);
 int univariate_fallback_from_handoff(dyb_handle* h, long long n, const int* d_status_solve, double* d_loglik, int* d_status);
 }  // namespace dyb
 

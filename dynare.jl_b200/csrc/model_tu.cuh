@@ -28,10 +28,16 @@ void mt_defaults(HostState& hs) {
 }
 
 constexpr bool mt_coop_fits = (MT::M <= 12) && (MT::K >= 1) && (MT::NF >= 1);
-int mt_solve_launches(const HostState& hs) { return (mt_coop_fits && hs.opt.solver != 1) ? 3 : 1; }
+// Models beyond the per-thread / register-resident kernels (dynamic block > 12 or more than 16 Kalman states): none of
+// the model-templated solve / filter kernels is instantiated (their unrolled code would take tens of minutes to compile
+// and could not launch); the generated model function feeds the run-time-size solver and the dense tensor-core filter
+// instead (ModelOps::jacobian_batch, generic.cu).
+constexpr bool mt_big = (MT::M > 12) || (MT::NS > 16);
+int mt_solve_launches(const HostState& hs) { return mt_big ? 2 : ((mt_coop_fits && hs.opt.solver != 1) ? 3 : 1); }
 
 cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, SolveOut out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
+  if constexpr (mt_big) { return cudaErrorNotSupported; } else {
   SolveParams<MT> prm;
   for (int i = 0; i < MT::NPAR; ++i) prm.params0[i] = hs.params[i];
   for (int i = 0; i < MT::NX * MT::NX; ++i) prm.sigma_e0[i] = hs.sigma_e[i];
@@ -44,7 +50,7 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
   const long long grid = (n + block - 1) / block;
   constexpr int G = CrCfg<MT>::G;
   const bool coop = mt_coop_fits && hs.opt.solver != 1;
-  if (coop) {
+  if constexpr (mt_coop_fits) { if (coop) {
     model_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.mid, out.status, out.ybar);
     if (out.ev_after_model) cudaEventRecord(out.ev_after_model, st);
     const long long gridc = (n * G + CrCfg<MT>::BLOCK - 1) / CrCfg<MT>::BLOCK;
@@ -53,17 +59,20 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
     if (out.ev_after_cr) cudaEventRecord(out.ev_after_cr, st);
     assemble_kernel<MT><<<(unsigned)grid, block, 0, st>>>(out.mid, n, hs.opt.lyap_tol, hs.opt.lyap_maxit, out.ss,
                                                           out.status, out.g1, out.lyap_iters);
-  } else {
-    SolveExtra ex{out.g1, out.ybar, out.cr_iters, out.lyap_iters};
-    solve_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.ss, out.status, ex);
-  }
+    return cudaGetLastError();
+  } }
+  (void)coop;
+  SolveExtra ex{out.g1, out.ybar, out.cr_iters, out.lyap_iters};
+  solve_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.ss, out.status, ex);
   return cudaGetLastError();
+  }
 }
 
 // G lanes per draw for small batches (kalman_sublanes.cuh)
 template <int G>
 cudaError_t mt_kalman_sub(const double* d_ss, long long n, const double* d_Y, int nobs, int presample,
                           const int* d_status_in, double* d_loglik, int* d_status_out, cudaStream_t st) {
+  if constexpr (!KalmanSubCfg<MT, G>::FITS) { return cudaErrorNotSupported; } else {
   using C = KalmanSubCfg<MT, G>;
   const size_t smem = C::smem_bytes(nobs);
   if (smem > 48 * 1024) {
@@ -73,6 +82,7 @@ cudaError_t mt_kalman_sub(const double* d_ss, long long n, const double* d_Y, in
   const long long grid = (n * G + C::BLOCK - 1) / C::BLOCK;
   kalman_sublanes_kernel<MT, G><<<(unsigned)grid, C::BLOCK, smem, st>>>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out);
   return cudaGetLastError();
+  }
 }
 
 // lanes per draw of the filter: 1 = one thread per draw (throughput kernel), 4 / 8 = shared-tile kernel for batches that
@@ -88,6 +98,7 @@ int mt_kalman_lanes(long long n, int nobs, int want) {
 cudaError_t mt_kalman(const double* d_ss, long long n, const double* d_Y, int nobs, int presample, int want_lanes,
                       const int* d_status_in, double* d_loglik, int* d_status_out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
+  if constexpr (mt_big) { return cudaErrorNotSupported; } else {
   const int lanes = mt_kalman_lanes(n, nobs, want_lanes);
   if (lanes == 8) return mt_kalman_sub<8>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out, st);
   if (lanes == 4) return mt_kalman_sub<4>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out, st);
@@ -101,6 +112,7 @@ cudaError_t mt_kalman(const double* d_ss, long long n, const double* d_Y, int no
   }
   kalman_kernel<MT><<<(unsigned)grid, block, smem, st>>>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out);
   return cudaGetLastError();
+  }
 }
 
 __global__ void mt_unpack_kernel(const double* __restrict__ ss, long long n, double* T, double* RQR, double* P0,
@@ -123,6 +135,7 @@ __global__ void mt_unpack_kernel(const double* __restrict__ ss, long long n, dou
 
 cudaError_t mt_unpack(const double* d_ss, long long n, double* T, double* RQR, double* P0, double* yb, double* H, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
+  if (mt_big) return cudaErrorNotSupported;
   const int block = 128;
   mt_unpack_kernel<<<(unsigned)((n + block - 1) / block), block, 0, st>>>(d_ss, n, T, RQR, P0, yb, H);
   return cudaGetLastError();
@@ -132,6 +145,75 @@ void mt_bkwrd_indices(int* out) { for (int i = 0; i < MT::K; ++i) out[i] = MT::i
 
 void mt_obs_indices(int* out) { for (int i = 0; i < MT::NY; ++i) out[i] = MT::state_ids(MT::obs_idx_state(i)); }
 
+void mt_static_indices(int* out) { for (int i = 0; i < MT::S; ++i) out[i] = MT::i_static(i); }
+void mt_fwrd_indices(int* out) { for (int i = 0; i < MT::NF; ++i) out[i] = MT::i_fwrd_b(i); }
+
+// theta -> dense compressed Jacobian, steady state, Sigma_e, Sigma_m, status: one thread per draw (K1-K2 of solve_draw with
+// the Jacobian written out instead of consumed); feeds solve_generic_kernel for models beyond the register-resident solver
+struct JacDense {
+  double* w;
+  DYB_D double& operator[](int idx) const { return w[idx]; }
+};
+__global__ void __launch_bounds__(128)
+mt_jacobian_kernel(const SolveParams<MT> prm, const double* __restrict__ theta, long long n_draws, double* __restrict__ jac,
+                   double* __restrict__ ybar, double* __restrict__ sigma_e, double* __restrict__ sigma_m, int* __restrict__ status) {
+  constexpr int N = MT::N, NX = MT::NX, NY = MT::NY, NCOL = MT::NCOL;
+  const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_draws) return;
+  const double* th = theta + d * (long long)prm.np;
+  double p[MT::NPAR > 0 ? MT::NPAR : 1];
+  double* Se = sigma_e + d * NX * NX;
+  double* Sm = sigma_m + d * NY * NY;
+  for (int i = 0; i < MT::NPAR; ++i) p[i] = prm.params0[i];
+  for (int i = 0; i < NX * NX; ++i) Se[i] = prm.sigma_e0[i];
+  for (int i = 0; i < NY * NY; ++i) Sm[i] = prm.sigma_m0[i];
+  for (int q = 0; q < prm.np; ++q) {
+    const double v = th[q];
+    const int ty = prm.est_type[q], i = prm.est_i[q], j = prm.est_j[q];
+    switch (ty) {
+      case EST_PARAM: p[i] = v; break;
+      case EST_SD_SHOCK: Se[i + NX * j] = v * v; break;
+      case EST_VAR_SHOCK: Se[i + NX * j] = v; break;
+      case EST_CORR_SHOCK: { const double c = v * sqrt(Se[i + NX * i] * Se[j + NX * j]); Se[i + NX * j] = c; Se[j + NX * i] = c; } break;
+      case EST_SD_MEAS: Sm[i + NY * j] = v * v; break;
+      case EST_VAR_MEAS: Sm[i + NY * j] = v; break;
+      case EST_CORR_MEAS: { const double c = v * sqrt(Sm[i + NY * i] * Sm[j + NY * j]); Sm[i + NY * j] = c; Sm[j + NY * i] = c; } break;
+      default: break;
+    }
+  }
+  double* y = ybar + d * N;
+  MT::steady_state(p, y);
+  bool ok = true;
+  for (int i = 0; i < N; ++i) ok = ok && isfinite(y[i]);
+  if (ok) ok = MT::static_resid_ss(p, y) <= prm.steady_tol * prm.steady_tol;      // SteadyState.jl:476-482
+  double* J = jac + d * (long long)(N * NCOL);
+  for (int e = 0; e < N * NCOL; ++e) J[e] = 0.0;
+  int st = ok ? ST_OK : ST_STEADY;
+  if (ok) {
+    JacDense acc{J};
+    MT::jacobian(p, y, acc);
+    double chk = 0.0;
+    for (int e = 0; e < N * NCOL; ++e) chk = fma(J[e], 0.0, chk);
+    if (!(chk == 0.0)) st = ST_STEADY;                  // NaN / Inf in the Jacobian
+  }
+  status[d] = st;
+}
+
+cudaError_t mt_jacobian_batch(const HostState& hs, const double* d_theta, long long n, double* d_jac, double* d_ybar,
+                              double* d_se, double* d_sm, int* d_status, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  SolveParams<MT> prm;
+  for (int i = 0; i < MT::NPAR; ++i) prm.params0[i] = hs.params[i];
+  for (int i = 0; i < MT::NX * MT::NX; ++i) prm.sigma_e0[i] = hs.sigma_e[i];
+  for (int i = 0; i < MT::NY * MT::NY; ++i) prm.sigma_m0[i] = hs.sigma_m[i];
+  prm.np = hs.np;
+  for (int i = 0; i < MAX_EST; ++i) { prm.est_type[i] = hs.est_type[i]; prm.est_i[i] = hs.est_i[i]; prm.est_j[i] = hs.est_j[i]; }
+  prm.cr_tol = hs.opt.cr_tol; prm.cr_maxit = hs.opt.cr_maxit; prm.steady_tol = hs.opt.steady_tol;
+  prm.lyap_tol = hs.opt.lyap_tol; prm.lyap_maxit = hs.opt.lyap_maxit;
+  mt_jacobian_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(prm, d_theta, n, d_jac, d_ybar, d_se, d_sm, d_status);
+  return cudaGetLastError();
+}
+
 void mt_obs_state_positions(int* out) { for (int i = 0; i < MT::NY; ++i) out[i] = MT::obs_idx_state(i); }
 
 const ModelOps mt_ops = {
@@ -139,7 +221,7 @@ const ModelOps mt_ops = {
   {MT::N, MT::NX, MT::NPAR, MT::K, MT::NF, MT::S, MT::NCOL, MT::NS, MT::NY, MT::NP_DEFAULT, SSLayout<MT>::SIZE, MidLayout<MT>::SIZE},
   MidLayout<MT>::SIZE,
   mt_defaults, mt_solve_launches, mt_solve, mt_kalman, mt_unpack, mt_bkwrd_indices, mt_obs_indices,
-  mt_obs_state_positions
+  mt_obs_state_positions, !mt_big, mt_static_indices, mt_fwrd_indices, mt_jacobian_batch
 };
 
 struct Registrar { Registrar() { register_model(&mt_ops); } } mt_registrar;

@@ -43,6 +43,14 @@ struct ModelOps {
   void (*bkwrd_indices)(int* i_bkwrd_b /* dims.k */);   // variables with a lag, 0-based (Model.i_bkwrd_b)
   void (*obs_indices)(int* obs_idx /* dims.ny */);      // observed variable of each row of Y, 0-based
   void (*obs_state_positions)(int* z_idx /* dims.ny */);   // position of each observable in the Kalman state (SSWs.obs_idx_state)
+  // ---- models whose dynamic block does not fit the register-resident solver (m > 12): the generated model function
+  // feeds the run-time-size solver and the dense filter (generic.cu) on the device, no host hop
+  bool register_solver;                                 // the three-kernel register-resident path exists for this model
+  void (*static_indices)(int* i_static /* dims.s */);
+  void (*fwrd_indices)(int* i_fwrd_b /* dims.nf */);
+  // theta -> per draw: compressed Jacobian n x ncol (column-major), steady state n, Sigma_e nx x nx, Sigma_m ny x ny, status
+  cudaError_t (*jacobian_batch)(const HostState&, const double* d_theta, long long n, double* d_jac, double* d_ybar,
+                                double* d_sigma_e, double* d_sigma_m, int* d_status, cudaStream_t);
 };
 
 const std::vector<const ModelOps*>& registry();

@@ -278,5 +278,62 @@ class HSNK(HandModel):
         ])
 
 
+class MC4(HandModel):
+    """Four linked Lubik-Schorfheide economies (dynare.jl_b200/models/src/mc4.mod, written for this repository as the
+    medium-scale fixture: 44 endogenous variables, 20 shocks, 7 observables): the ls2003 block once per country, the foreign
+    output of country c loaded on the lagged output of the three others.  Transcribed by hand from the equations."""
+    name = "mc4"
+    linear = True
+    C = 4
+    endo = [f"{v}{c}" for c in range(1, 5) for v in ("y", "ys", "R", "pie", "dq", "pies", "de", "A", "yobs", "pieobs", "Robs")]
+    exo = [f"{v}{c}" for c in range(1, 5) for v in ("eR", "eq", "eys", "epies", "eA")]
+    params = ["psi1", "psi2", "psi3", "rho_R", "tau", "alpha", "rr", "k", "rho_q", "rho_A", "rho_ys", "rho_pies", "spill"]
+    params0 = np.array([0.54, 0.25, 0.25, 0.5, 0.5, 0.3, 2.51, 0.5, 0.4, 0.2, 0.8, 0.7, 0.1])
+    sigma_e0 = np.diag(np.tile(np.array([1.25, 2.5, 1.37, 1.37, 1.37]) ** 2, 4))
+    varobs = ["yobs1", "pieobs1", "Robs1", "yobs2", "pieobs2", "Robs2", "dq1"]
+    lagged = [f"{v}{c}" for c in range(1, 5) for v in ("y", "ys", "R", "dq", "pies", "A")]
+    led = [f"{v}{c}" for c in range(1, 5) for v in ("y", "ys", "pie", "dq", "A")]
+    est = ([("param", p) for p in ("psi1", "psi2", "psi3", "rho_R", "alpha", "rr", "k", "tau", "rho_q", "rho_A", "rho_ys",
+                                   "rho_pies", "spill")]
+           + [("stderr", f"{v}{c}") for c in range(1, 5) for v in ("eR", "eq", "eys", "epies", "eA")])
+
+    @property
+    def theta_mode(self):
+        return np.concatenate([[0.54, 0.25, 0.25, 0.5, 0.3, 2.51, 0.5, 0.5, 0.4, 0.2, 0.8, 0.7, 0.1],
+                               np.tile([1.25, 2.5, 1.37, 1.37, 1.37], 4)])
+
+    def steady_state(self, p):
+        return np.zeros(44)
+
+    def dynamic_resid(self, ym, y_, yp, u, p):
+        psi1, psi2, psi3, rho_R, tau, alpha, rr, k, rho_q, rho_A, rho_ys, rho_pies, spill = p
+        om = tau + alpha * (2 - alpha) * (1 - tau)
+        r = []
+        ylag = [ym[11 * c] for c in range(4)]
+        for c in range(4):
+            b = 11 * c
+            y, ys, R, pie, dq, pies, de, A, yobs, pieobs, Robs = y_[b:b + 11]
+            y_1, ys_1, R_1, dq_1, pies_1, A_1 = ym[b], ym[b + 1], ym[b + 2], ym[b + 4], ym[b + 5], ym[b + 7]
+            y1, ys1, pie1, dq1, A1 = yp[b], yp[b + 1], yp[b + 3], yp[b + 4], yp[b + 7]
+            eR, eq, eys, epies, eA = u[5 * c:5 * c + 5]
+            others = sum(ylag[o] for o in range(4) if o != c)
+            r += [
+                y - (y1 - om * (R - pie1) - alpha * om * dq1 + alpha * (2 - alpha) * ((1 - tau) / tau) * (ys - ys1) - A1),
+                pie - (np.exp(-rr / 400) * pie1 + alpha * np.exp(-rr / 400) * dq1 - alpha * dq + (k / om) * y
+                       + alpha * (2 - alpha) * (1 - tau) / (tau * om) * ys),
+                pie - (de + (1 - alpha) * dq + pies),
+                R - (rho_R * R_1 + (1 - rho_R) * ((1 + psi1) * pie + psi2 * (y + alpha * (2 - alpha) * ((1 - tau) / tau) * ys)
+                                                  + psi3 * de) + eR),
+                dq - (rho_q * dq_1 + eq),
+                ys - (rho_ys * ys_1 + (spill / 3) * others + eys),
+                pies - (rho_pies * pies_1 + epies),
+                A - (rho_A * A_1 + eA),
+                yobs - (y - y_1 + A),
+                pieobs - 4 * pie,
+                Robs - 4 * R,
+            ]
+        return np.array(r)
+
+
 def get_model(name: str) -> HandModel:
-    return {"fs2000": FS2000, "ls2003": LS2003, "hs_nk": HSNK}[name]()
+    return {"fs2000": FS2000, "ls2003": LS2003, "hs_nk": HSNK, "mc4": MC4}[name]()

@@ -28,12 +28,22 @@ MODELS = {
 }
 
 
+# models written for this repository (sources under dynare.jl_b200/models/src): mc4 = four linked Lubik-Schorfheide economies,
+# 44 variables / 20 shocks / 7 observables -- the medium-scale fixture (BASELINE configs[3]) for the path beyond m = 12
+OWN_MODELS = {"mc4": os.path.join(ROOT, "dynare.jl_b200", "models", "src", "mc4.mod")}
+
+
 def main():
     gen = os.path.join(ROOT, "dynare.jl_b200", "csrc", "generated")
     os.makedirs(gen, exist_ok=True)
     os.makedirs(os.path.join(ROOT, "oracle", "c"), exist_ok=True)
-    for name, rel in MODELS.items():
-        spec = modelgen.spec_from_file(name, os.path.join(REF, rel))
+    sources = {name: os.path.join(REF, rel) for name, rel in MODELS.items()}
+    sources.update(OWN_MODELS)
+    only = set(sys.argv[1:])
+    for name, path in sources.items():
+        if only and name not in only:
+            continue
+        spec = modelgen.spec_from_file(name, path)
         with open(os.path.join(gen, f"model_{name}.cuh"), "w") as f:
             f.write(modelgen.emit_cuda(spec))
         with open(os.path.join(gen, f"model_{name}.cu"), "w") as f:
@@ -46,6 +56,8 @@ def main():
         print(f"{name}: n={spec.n} k={spec.k} nf={spec.nf} s={spec.s} ns={spec.ns} ny={spec.ny} "
               f"np={spec.np_est} jac nnz={len(spec.jac)}")
 
+    if only and "ls2003" not in only:
+        return
     # ls2003 data: reference test/models/ls2003/data_ca1.csv, estimation(first_obs=8, nobs=79)
     import csv
     with open(os.path.join(REF, "test/models/ls2003/data_ca1.csv")) as f:

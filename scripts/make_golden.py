@@ -48,6 +48,10 @@ def main():
     if not only or "ls2003" in only:
         Yls = np.load(os.path.join(GOLD, "ls2003_data.npy"))
         make("ls2003", Yls, 256, 1)
+    if not only or "mc4" in only:
+        # mc4: four linked Lubik-Schorfheide economies (dynare.jl_b200/models/src/mc4.mod), 200 synthetic quarters
+        mc = models.get_model("mc4")
+        make("mc4", pl.simulate_observations(mc, mc.theta_mode, 200, 20260103), 128, 1)
     if only and "hs_nk" not in only:
         return
     # hs_nk: the reference's data file (dsge1_data.csv) is not in the tree; 80 synthetic quarters at the

@@ -29,7 +29,7 @@ def test_version_and_registry(lib):
     from dynare_jl_b200 import _lib
     assert lib.dyb_version() == 100
     names = [lib.dyb_model_name(i).decode() for i in range(lib.dyb_model_count())]
-    assert sorted(names) == ["fs2000", "hs_nk", "ls2003"]
+    assert sorted(names) == ["fs2000", "hs_nk", "ls2003", "mc4"]
     for nm in names:
         d = _lib.ModelDims()
         assert lib.dyb_model_get_dims(nm.encode(), C.byref(d)) == 0

@@ -362,6 +362,7 @@ def run_ours(args):
             extra["config4"] = BL.dense_filter_leg(local, 40, 7, 200, 32768, 64, 2, 2, dpk)
             extra["config5"] = BL.dense_filter_leg(local, 200, 20, 500, args.config5_draws, 8, 3, 1, dpk)
             extra["config5"]["projected_seconds_262144_draws_8gpu"] = 32768 / extra["config5"]["evals_per_s"]
+            extra["config4_model"] = BL.medium_model_leg(local)
         barrier()
         smc_a = BL.smc_leg(local, rank, world, gloo, 16384, 400)
         smc_b = BL.smc_leg(local, rank, world, gloo, 131072, 100)

@@ -77,6 +77,33 @@ def dense_filter_leg(local, ns, ny, nobs, n, pool, seed, reps, dmma_peak):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def medium_model_leg(local, chains=32768, sweeps=10):
+    """BASELINE configs[3] WITH the model solve: mc4 (44 variables, m = 28, 30 states, 7 observables, T = 200), parallel
+    RWMH chains: proposal, transformation, prior, first-order solve, dense tensor-core filter, accept -- all on the device."""
+    import torch
+    from dynare_jl_b200.engine import BatchSSWs, model_description
+    from dynare_jl_b200.priors import PriorSet
+    from dynare_jl_b200.samplers import rwmh
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "mc4_golden.npz")))
+    d = model_description("mc4")
+    pri = PriorSet.from_description(d["priors"])
+    ws = BatchSSWs("mc4", g["Y"], device=local)
+    ws.set_priors(pri)
+    x0 = np.array(d["theta_init"])
+    y0 = ws.transform(x0[None, :], inverse=True)[0]
+    cov = np.diag(np.full(ws.np, 0.01 ** 2))
+    rwmh(ws, pri, y0, cov, mcmc_replic=2, mcmc_chains=chains, seed=1)                    # warm-up (buffers, attributes)
+    torch.cuda.synchronize(local)
+    t = time.perf_counter()
+    out = rwmh(ws, pri, y0, cov, mcmc_replic=sweeps, mcmc_chains=chains, seed=2)          # synchronous call
+    dt = time.perf_counter() - t
+    ws.close()
+    return {"workload": f"mc4 (44 variables, dynamic block 28, 30 Kalman states, 7 observables, T=200): {chains} RWMH chains x "
+                        f"{sweeps} sweeps, model solve + filter per proposal", "seconds": dt, "ms_per_sweep": 1e3 * dt / sweeps,
+            "posterior_evals_per_s": chains * sweeps / dt, "projected_seconds_100_sweeps": 100 * dt / sweeps,
+            "acceptance_rate": float(out["accepted"].mean() / sweeps)}
+
+
 def smc_leg(local, rank, world, gloo, npart, nphi, seed=3, check=True, profile=True):
     """One full SMC recursion on ls2003 with `npart` particles over `world` GPUs; rank 0 returns the record."""
     import torch.distributed as dist

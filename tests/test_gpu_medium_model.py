@@ -44,5 +44,5 @@ def test_mc4_samplers_run_on_the_device(golden):
     r = est.rwmh_compute(ctx, data=g["Y"], initial_values=x0, transformed_covariance=np.diag(np.full(33, 0.02 ** 2)),
                          mcmc_chains=128, mcmc_replic=12, mcmc_jscale=1.0, seed=4)
     assert r["chains"].shape == (12, 128, 33) and np.all(np.isfinite(r["chains"])) and 0.0 < r["acceptance_rate"].mean() < 1.0
-    out = est.smc_compute(ctx, data=g["Y"], npart=1024, nphi=8, seed=2)
+    out = est.smc_compute(ctx, data=g["Y"], npart=8192, nphi=60, seed=2)
     assert np.isfinite(out["logmdd"]) and abs(out["w"].sum() - 1) < 1e-12 and np.all(np.isfinite(out["loglh"]))

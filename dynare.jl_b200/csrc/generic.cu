@@ -11,6 +11,7 @@
 #include "kalman_dmma_large.cuh"
 #include "kalman_lanes.cuh"
 #include "solve_generic.cuh"
+#include "solve_block.cuh"
 #include "kalman_smoother.cuh"
 #include "kalman_diffuse.cuh"
 
@@ -22,6 +23,8 @@ struct GenericHost {
   std::vector<int> obs_state;  // ny: Kalman state observed by each row of Y
   size_t smem = 0;             // bytes of shared memory per draw
   bool warp_groups = false;    // one warp per draw (small models) instead of one CTA per draw
+  bool block = false;          // medium models: register-blocked CTA-per-draw kernel (solve_block.cuh)
+  SbLayout sbl{};              // its shared-memory layout
   DevBuf bT, bQ, bP, byo, bH, bst, bz;   // persistent work buffers of dyb_loglik_from_jacobian_batch
   DevBuf bJ, byb, bse, bsm, bsi;         // persistent staging of its host inputs
 };
@@ -535,6 +538,15 @@ static int generic_build(dyb_handle* h, const dyb_model_desc* md, dyb_model_dims
   gh->obs_state = obs_state;
   gh->smem = smem;
   gh->warp_groups = smem <= 24 * 1024;
+  // medium models (more than 12 dynamic variables, up to 32): register-blocked kernel, instantiation <4, 6>
+  if (!gh->warp_groups && m > 12 && m <= 32 && m + k + nf <= 96 && m + nx <= 96 && k + nf <= 64) {
+    gh->sbl = sb_layout(n, nx, s, k, nf, ns, 32, 96);
+    const size_t sb = sizeof(double) * (size_t)gh->sbl.total;
+    if (sb + 1024 <= (size_t)max_smem) {
+      gh->block = true;
+      if (sb > 48 * 1024) e = cudaFuncSetAttribute(solve_block_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+    }
+  }
   if (e == cudaSuccess) {
     if (gh->warp_groups) {
       if (4 * smem > 48 * 1024) e = cudaFuncSetAttribute(solve_generic_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * smem));
@@ -576,7 +588,11 @@ static int generic_solve(dyb_handle* h, GenericSolveArgs a) {
   GenericHost* gh = h->generic;
   a.cr_tol = h->hs.opt.cr_tol; a.cr_maxit = h->hs.opt.cr_maxit; a.lyap_tol = h->hs.opt.lyap_tol; a.lyap_maxit = h->hs.opt.lyap_maxit;
   const int per_draw = (int)(gh->smem / sizeof(double));
-  if (gh->warp_groups) {                 // small model: one warp per draw, four draws per CTA
+  if (gh->block && h->hs.opt.solver != 1) {      // medium model: one CTA per draw, algebra in registers (solve_block.cuh)
+    long long grid = a.n_draws;
+    if (grid > 148LL * 64) grid = 148LL * 64;
+    solve_block_kernel<4, 6><<<(unsigned)grid, SB_THREADS, sizeof(double) * (size_t)gh->sbl.total, h->stream>>>(gh->gm, a, gh->sbl);
+  } else if (gh->warp_groups) {                 // small model: one warp per draw, four draws per CTA
     long long grid = (a.n_draws + 3) / 4;
     if (grid > 148LL * 64) grid = 148LL * 64;
     solve_generic_kernel<32><<<(unsigned)grid, 128, 4 * gh->smem, h->stream>>>(gh->gm, a, per_draw);

@@ -46,3 +46,28 @@ def test_mc4_samplers_run_on_the_device(golden):
     assert r["chains"].shape == (12, 128, 33) and np.all(np.isfinite(r["chains"])) and 0.0 < r["acceptance_rate"].mean() < 1.0
     out = est.smc_compute(ctx, data=g["Y"], npart=8192, nphi=60, seed=2)
     assert np.isfinite(out["logmdd"]) and abs(out["w"].sum() - 1) < 1e-12 and np.all(np.isfinite(out["loglh"]))
+
+
+def test_mc4_register_blocked_solver_matches_the_shared_memory_solver(golden):
+    """solve_block_kernel (Gauss-Jordan with implicit pivoting in registers) against solve_generic_kernel (pivoted LU in
+    shared memory): same status for every draw, policy matrices and likelihood to rounding; failing draws included."""
+    from dynare_jl_b200.engine import BatchSSWs, model_description
+    from dynare_jl_b200.priors import PriorSet
+    g = golden("mc4")
+    pri = PriorSet.from_description(model_description("mc4")["priors"])
+    th = np.concatenate([g["theta"], pri.sample(np.random.default_rng(7), 600)])
+    ws = BatchSSWs("mc4", g["Y"])
+    out = {}
+    for solver in (0, 1):
+        ws.set_options(solver=solver)
+        ll, st = ws.loglikelihood(th)
+        fo = ws.first_order(th)
+        out[solver] = (ll, st, fo)
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2]["status"], out[1][2]["status"])
+    assert (out[0][1] != 0).sum() >= 5
+    ok = out[0][1] == 0
+    assert np.max(np.abs(out[0][0][ok] - out[1][0][ok]) / np.abs(out[1][0][ok])) <= 1e-9
+    for k in ("g1_1", "g1_2"):
+        assert np.abs(out[0][2][k][ok] - out[1][2][k][ok]).max() <= 1e-10
+    assert np.array_equal(out[0][2]["cr_iters"][ok], out[1][2]["cr_iters"][ok])
+    ws.close()

@@ -8,6 +8,7 @@
 #include "kalman_univariate.cuh"
 #include "kalman_generic.cuh"
 #include "kalman_dmma.cuh"
+#include "kalman_dmma_fold.cuh"
 #include "kalman_dmma_large.cuh"
 #include "kalman_lanes.cuh"
 #include "solve_generic.cuh"
@@ -44,7 +45,8 @@ void generic_release(dyb_handle* h) {
 // from-Jacobian likelihood); scratch (2 ns^2 doubles per CTA) only when P and T P do not fit in shared memory
 // PROCESS-WIDE A/B switches set by dyb_set_kalman_variant (every handle, device and thread reads them; atomics so that
 // a concurrent reader sees a consistent value -- a test that toggles them changes the kernel other handles use)
-static std::atomic<int> g_kalman_variant{0};      // 0 auto, 1 scalar (kalman_generic.cuh), 2 tensor-core (kalman_dmma.cuh)
+static std::atomic<int> g_kalman_variant{0};      // 0 auto, 1 scalar (kalman_generic.cuh), 2 tensor-core (kalman_dmma*.cuh)
+static std::atomic<int> g_kalman_fold{1};         // ns <= 88: correction folded behind the products + scalar warp (kalman_dmma_fold.cuh)
 static std::atomic<int> g_kalman_lanes_max{16};   // auto choice: sub-warp kernel up to this many states
 static std::atomic<int> g_kalman_bulk{1};         // large-ns kernel: stage the GEMM panels with cp.async.bulk when alignment allows
 
@@ -74,6 +76,33 @@ static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaSt
     const KalmanDmmaGeom q = kalman_dmma_geom(g.ns, g.ny);
     const size_t smem = sizeof(double) * kalman_dmma_smem_doubles(g.ns, g.ny);
     const bool fits = q.nsp / 8 <= DMMA_MAX_TILES && smem + 1024 <= (size_t)max_smem;
+    const size_t smem_f = sizeof(double) * kalman_fold_smem_doubles(g.ns, g.ny);
+    if (fits && g_kalman_variant != 1 && g_kalman_fold && g.ny <= 32 && smem_f + 1024 <= (size_t)max_smem) {
+      long long grid = g.n_draws < (long long)dev_sms * 32 ? g.n_draws : (long long)dev_sms * 32;
+      g.scratch = nullptr;
+      const int ntile = q.nsp / 8;
+      auto launch = [&](auto kern) -> cudaError_t {
+        if (smem_f > 48 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+          if (e != cudaSuccess) return e;
+        }
+        kern<<<(unsigned)grid, 32 * (ntile + 1), smem_f, st>>>(g, q);
+        return cudaGetLastError();
+      };
+      switch (ntile) {
+        case 1: return launch(kalman_dmma_fold_kernel<1>);
+        case 2: return launch(kalman_dmma_fold_kernel<2>);
+        case 3: return launch(kalman_dmma_fold_kernel<3>);
+        case 4: return launch(kalman_dmma_fold_kernel<4>);
+        case 5: return launch(kalman_dmma_fold_kernel<5>);
+        case 6: return launch(kalman_dmma_fold_kernel<6>);
+        case 7: return launch(kalman_dmma_fold_kernel<7>);
+        case 8: return launch(kalman_dmma_fold_kernel<8>);
+        case 9: return launch(kalman_dmma_fold_kernel<9>);
+        case 10: return launch(kalman_dmma_fold_kernel<10>);
+        default: return launch(kalman_dmma_fold_kernel<DMMA_MAX_TILES>);
+      }
+    }
     if (fits && g_kalman_variant != 1) {
       long long grid = g.n_draws < (long long)dev_sms * 32 ? g.n_draws : (long long)dev_sms * 32;
       g.scratch = nullptr;
@@ -469,10 +498,11 @@ int dyb_kalman_batch_fallback(int device, int32_t ns, int32_t ny, int32_t nobs, 
 }
 
 int dyb_set_kalman_variant(int32_t variant) {
-  if (variant < 0 || variant > 4)
-    return fail(DYB_ERR_ARG, "variant must be 0 (auto), 1 (scalar), 2 (tensor-core), 3 (tensor-core, no bulk copies) or 4 (sub-warp, ns <= 16)");
+  if (variant < 0 || variant > 5)
+    return fail(DYB_ERR_ARG, "variant must be 0 (auto), 1 (scalar), 2 (tensor-core), 3 (tensor-core, no bulk copies), 4 (sub-warp, ns <= 16) or 5 (tensor-core, unfolded ns <= 88 kernel)");
   g_kalman_bulk = variant != 3;
-  g_kalman_variant = variant == 3 ? 2 : variant;
+  g_kalman_fold = variant != 5;
+  g_kalman_variant = (variant == 3 || variant == 5) ? 2 : variant;
   return DYB_OK;
 }
 

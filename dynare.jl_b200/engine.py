@@ -477,7 +477,7 @@ def fp64_peak_dmma(shape=0, device=0) -> float:
 
 def set_kalman_variant(variant: int):
     """0 auto, 1 scalar dense filter kernel, 2 tensor-core (DMMA) kernel, 3 DMMA without bulk copies, 4 four lanes per draw
-    (ns <= 16, ny <= 8)."""
+    (ns <= 16, ny <= 8), 5 DMMA with the unfolded ns <= 88 kernel."""
     L.check(L.load().dyb_set_kalman_variant(variant))
 
 

@@ -237,7 +237,8 @@ int dyb_kalman_batch_fallback(int device, int32_t ns, int32_t ny, int32_t nobs, 
 /* which dense filter kernel dyb_kalman_batch / dyb_loglik_from_jacobian_batch use: 0 auto (four / eight lanes per draw up to
  * ns = 16 and ny = 8, tensor-core kernels up to ns = 256, scalar kernel beyond), 1 scalar, 2 tensor-core (fp64 mma.sync),
  * 3 tensor-core with the large-ns kernel's cp.async.bulk panel staging switched off, 4 lanes-per-draw kernel (ns <= 16,
- * ny <= 8 only); process-wide, for A/B tests */
+ * ny <= 8 only), 5 tensor-core with the earlier ns <= 88 kernel (rank-ny downdate before the products, kalman_dmma.cuh)
+ * instead of the folded one (kalman_dmma_fold.cuh); process-wide, for A/B tests */
 int dyb_set_kalman_variant(int32_t variant);
 
 /* ---- models without a generated device function -----------------------------------------------------------

@@ -56,12 +56,111 @@ DYB_D double fold_gain_row(int s, int ny, int ld, int ldu, unsigned miss, const 
   return xa;
 }
 
+DYB_D void fold_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+struct FoldScalarArgs {
+  const double* Ps; const double* Hs; const double* abuf; double* F; double* w; double* rdv; int* miss_sh; const int* zi;
+  const double* Y; const double* ybar_obs_d;      // observations (ny x nobs), steady state of the observables of this draw or null
+  int nsp, ld, nobs, presample;
+  double* loglik_d; int* status_d;
+};
+
+// Scalar role of kalman_dmma_fold_kernel for NY <= 8 observables, all periods of one draw, executed by ONE warp:
+// lane i owns row i of F = P[z,z] + H in registers; Cholesky and w = L^-1 v by shuffles; the lane's share of the
+// quadratic form and of det(L) (a running product with its exponent split off) is accumulated per lane, so that no
+// cross-lane reduction, logarithm or division is on the per-period path.  Straight-line code for the exact NY.
+// Meets the tensor-core warps at the CTA barrier three times per period.
+template <int NY>
+__device__ __noinline__ void fold_scalar_role(const FoldScalarArgs A) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < NY;
+  int poff[NY];                  // offsets of this lane's row of P[z, z]
+  {
+    const int zme = act ? A.zi[lane] : 0;
+#pragma unroll
+    for (int j = 0; j < NY; ++j) poff[j] = zme + A.ld * A.zi[j];
+  }
+  const double* hrow = A.Hs + (act ? lane : 0);
+  const int aoff = act ? A.zi[lane] : 0;
+  const double ybi = (act && A.ybar_obs_d) ? A.ybar_obs_d[lane] : 0.0;
+  double ynext = (act && A.nobs > 0) ? A.Y[lane] : 0.0;
+  double qacc = 0.0, pr = 1.0;
+  int nseen = 0, eacc = 0;
+  bool okall = true;
+#pragma unroll 1
+  for (int t = 0; t < A.nobs; ++t) {
+    const double* a = A.abuf + (t & 1) * A.nsp;
+    const bool last = (t == A.nobs - 1);
+    const double yi = ynext;
+    if (act && !last) ynext = A.Y[(size_t)(t + 1) * NY + lane];
+    const unsigned miss = __ballot_sync(FULL, act && isnan(yi));
+    if (lane == 0) *A.miss_sh = (int)miss;
+    const bool mi = (miss >> lane) & 1u;
+    double x = (act && !mi) ? (yi - ybi) - a[aoff] : 0.0;
+    double f[NY];
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+      double val = (j == lane) ? 1.0 : 0.0;                 // rows beyond NY and missing observations: identity
+      if (act && j <= lane && !(mi || ((miss >> j) & 1u))) val = A.Ps[poff[j]] + hrow[NY * j];
+      f[j] = val;
+    }
+    double rd = 1.0, ldiag = 1.0;
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+      const double dj = __shfl_sync(FULL, f[j], j);
+      okall = okall && (dj > 0.0);
+      const double r = fast_rsqrt(dj);
+      const double lij = (lane == j) ? dj * r : f[j] * r;
+      f[j] = lij;
+      if (lane == j) { rd = r; ldiag = lij; }
+#pragma unroll
+      for (int cc = j + 1; cc < NY; ++cc) {
+        const double lcj = __shfl_sync(FULL, lij, cc);
+        f[cc] = fma(-lij, lcj, f[cc]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+      const double wj = __shfl_sync(FULL, x * rd, j);
+      if (lane > j) x = fma(-f[j], wj, x);
+    }
+    const double wi = x * rd;
+    if (act) {
+      A.w[lane] = wi;
+      A.rdv[lane] = rd;
+#pragma unroll
+      for (int j = 0; j < NY; ++j) if (j <= lane) A.F[lane + NY * j] = f[j];
+      if (t >= A.presample) {
+        qacc = fma(wi, wi, qacc);
+        pr *= ldiag;
+        const int hi = __double2hiint(pr);
+        const int ex = ((hi >> 20) & 0x7ff) - 1023;
+        eacc += ex;
+        pr = __hiloint2double(hi - (ex << 20), __double2loint(pr));
+      }
+    }
+    if (t >= A.presample) nseen += NY - __popc(miss);
+    if (last) break;
+    fold_bar();                                      // M, L and the missing-data pattern are ready
+    fold_bar();                                      // V and V w are ready
+    fold_bar();                                      // P' and a' are ready
+  }
+  double tot = act ? fma(2.0, fma((double)eacc, 0.6931471805599453, log(pr)), qacc) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+  if (lane == 0) {
+    const double ll = -0.5 * (nseen * 1.8378770664093453 + tot);
+    if (!okall || !isfinite(ll)) { *A.loglik_d = -INFINITY; *A.status_d = ST_F_NOT_PD; }
+    else { *A.loglik_d = ll; *A.status_d = ST_OK; }
+  }
+}
+
 // blockDim.x = 32 * (NT + 1): warps 0 .. NT - 1 issue the tensor-core products, the last warp does the scalar work.
 // NT = nsp / 8 is a template parameter: every fragment address is then base + immediate (the run-time-size version spent
 // 11 instructions per DMMA on address arithmetic and predicates; ncu: 6 % of the issued instructions were DMMAs).
 // The two roles run their own period loops and meet at the CTA barrier three times per period (bar.sync 0 from two
 // program locations); their register sets do not add up.
-DYB_D void fold_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 template <int NT>
 __global__ void __launch_bounds__(32 * (NT + 1), (NT <= 3 ? 6 : (NT <= 5 ? 4 : (NT <= 8 ? 2 : 1))))
@@ -115,86 +214,32 @@ kalman_dmma_fold_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
 
     if (scalar_warp) {
       // ================= scalar role: innovation, F = P[z,z] + H, L = chol(F), w = L^-1 v, likelihood terms =================
-      // ny <= 8 keeps everything per lane (row `lane` of F in registers, the lane's share of the quadratic form and of
-      // det(L) as a running product with its exponent split off): no cross-lane reduction inside the period loop
-      double acc = 0.0, qacc = 0.0, pr = 1.0;
-      int nseen = 0, bad = 0, eacc = 0;
-      const int zme = lane < ny ? zi[lane] : 0;
-      int zj[8];
-      double hrow[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        zj[j] = j < ny ? zi[j] : 0;
-        hrow[j] = (small && lane < ny && j <= lane) ? Hs[lane + ny * j] : 0.0;
-      }
-      const double ybi = (lane < ny && g.ybar_obs) ? g.ybar_obs[(size_t)d * ny + lane] : 0.0;
-      double ynext = (lane < ny && g.nobs > 0) ? g.Y[lane] : 0.0;
+      if (small) {
+        FoldScalarArgs A{Ps, Hs, abuf, F, w, rdv, &miss_sh, zi, g.Y, g.ybar_obs ? g.ybar_obs + (size_t)d * ny : nullptr,
+                         NSP, LD, g.nobs, g.presample, g.loglik + d, g.status + d};
+        switch (ny) {
+          case 1: fold_scalar_role<1>(A); break;
+          case 2: fold_scalar_role<2>(A); break;
+          case 3: fold_scalar_role<3>(A); break;
+          case 4: fold_scalar_role<4>(A); break;
+          case 5: fold_scalar_role<5>(A); break;
+          case 6: fold_scalar_role<6>(A); break;
+          case 7: fold_scalar_role<7>(A); break;
+          default: fold_scalar_role<8>(A); break;
+        }
+      } else {
+        double acc = 0.0;
+        int nseen = 0, bad = 0;
+        const double ybi = (lane < ny && g.ybar_obs) ? g.ybar_obs[(size_t)d * ny + lane] : 0.0;
+        double ynext = (lane < ny && g.nobs > 0) ? g.Y[lane] : 0.0;
 #pragma unroll 1
-      for (int t = 0; t < g.nobs; ++t) {
-        const double* a = abuf + (t & 1) * NSP;
-        const bool last = (t == g.nobs - 1);
-        const double yi = ynext;
-        if (lane < ny && !last) ynext = g.Y[(size_t)(t + 1) * ny + lane];
-        const unsigned miss = __ballot_sync(FULL, lane < ny && isnan(yi));
-        if (lane == 0) miss_sh = (int)miss;
-        if (small) {
-          const bool mi = (miss >> lane) & 1u;
-          double x = (lane < ny && !mi) ? (yi - ybi) - a[zme] : 0.0;
-          double f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            double val = 0.0;
-            if (lane < ny && j <= lane) {
-              val = Ps[zme + LD * zj[j]] + hrow[j];
-              if (mi || ((miss >> j) & 1u)) val = (j == lane) ? 1.0 : 0.0;
-            }
-            f[j] = val;
-          }
-          double rd = 1.0, ldiag = 1.0;
-          bool okc = true;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (j < ny) {
-              const double dj = __shfl_sync(FULL, f[j], j);
-              okc = okc && (dj > 0.0);
-              const double r = fast_rsqrt(dj);
-              const double lij = (lane == j) ? dj * r : f[j] * r;
-              f[j] = lij;
-              if (lane == j) { rd = r; ldiag = lij; }
-#pragma unroll
-              for (int cc = j + 1; cc < 8; ++cc) {
-                if (cc < ny) {
-                  const double lcj = __shfl_sync(FULL, lij, cc);
-                  f[cc] = fma(-lij, lcj, f[cc]);
-                }
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (j < ny) {
-              const double wj = __shfl_sync(FULL, x * rd, j);
-              if (lane > j) x = fma(-f[j], wj, x);
-            }
-          }
-          const double wi = x * rd;
-          if (lane < ny) {
-            w[lane] = wi;
-            rdv[lane] = rd;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) if (j <= lane) F[lane + ny * j] = f[j];
-            if (t >= g.presample) {
-              qacc = fma(wi, wi, qacc);
-              pr *= ldiag;
-              const int hi = __double2hiint(pr);
-              const int ex = ((hi >> 20) & 0x7ff) - 1023;
-              eacc += ex;
-              pr = __hiloint2double(hi - (ex << 20), __double2loint(pr));
-            }
-          }
-          if (!okc) bad = 1;
-          if (t >= g.presample) nseen += ny - __popc(miss);
-        } else {
+        for (int t = 0; t < g.nobs; ++t) {
+          const double* a = abuf + (t & 1) * NSP;
+          const bool last = (t == g.nobs - 1);
+          const double yi = ynext;
+          if (lane < ny && !last) ynext = g.Y[(size_t)(t + 1) * ny + lane];
+          const unsigned miss = __ballot_sync(FULL, lane < ny && isnan(yi));
+          if (lane == 0) miss_sh = (int)miss;
           if (lane < ny) v[lane] = isnan(yi) ? 0.0 : (yi - ybi) - a[zi[lane]];
           for (int e0 = 0; e0 < ny * ny; e0 += 32) {
             const int e = e0 + lane;
@@ -213,22 +258,16 @@ kalman_dmma_fold_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
           else okc = chol_warp_call<32>(F, ny, v, w, rdv, ql);
           if (!okc) bad = 1;
           if (t >= g.presample) { acc += 2.0 * ql[1] + ql[0]; nseen += ny - __popc(miss); }
+          if (last) break;
+          fold_bar();                                      // M, L and the missing-data pattern are ready
+          fold_bar();                                      // V and V w are ready
+          fold_bar();                                      // P' and a' are ready
         }
-        if (last) break;
-        fold_bar();                                      // M, L and the missing-data pattern are ready
-        fold_bar();                                      // V and V w are ready
-        fold_bar();                                      // P' and a' are ready
-      }
-      if (small) {
-        double tot = lane < ny ? fma(2.0, fma((double)eacc, 0.6931471805599453, log(pr)), qacc) : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-        acc = tot;
-      }
-      if (lane == 0) {
-        const double ll = -0.5 * (nseen * 1.8378770664093453 + acc);
-        if (bad || !isfinite(ll)) { g.loglik[d] = -INFINITY; g.status[d] = ST_F_NOT_PD; }
-        else { g.loglik[d] = ll; g.status[d] = ST_OK; }
+        if (lane == 0) {
+          const double ll = -0.5 * (nseen * 1.8378770664093453 + acc);
+          if (bad || !isfinite(ll)) { g.loglik[d] = -INFINITY; g.status[d] = ST_F_NOT_PD; }
+          else { g.loglik[d] = ll; g.status[d] = ST_OK; }
+        }
       }
     } else {
       // ================= tensor-core role ======================================================================================

@@ -27,7 +27,7 @@ void mt_defaults(HostState& hs) {
   }
 }
 
-constexpr bool mt_coop_fits = (MT::M <= 12) && (MT::K >= 1) && (MT::NF >= 1);
+constexpr bool mt_coop_fits = CrCfg<MT>::FITS;
 // Models beyond the per-thread / register-resident kernels (dynamic block > 12 or more than 16 Kalman states): none of
 // the model-templated solve / filter kernels is instantiated (their unrolled code would take tens of minutes to compile
 // and could not launch); the generated model function feeds the run-time-size solver and the dense tensor-core filter

@@ -202,17 +202,89 @@ DYB_D bool qr_solve(double (&A)[(MM + G - 1) / G][MM], double (&B)[NR][MM], int 
   return ok;
 }
 
+// Gauss-Jordan elimination with COLUMN pivoting on the same distributed layout:  B <- A^-1 B up to a row permutation.
+// Step p works on ROW p: the pivot is the largest |A[p][c]| over the columns c not used yet (a 32-bit key -- upper word of
+// |a| with the column number in its four low bits -- maximised over the G lanes by two shuffles), the pivot column is
+// broadcast from its owner and every lane eliminates it from all other rows of its own columns.  Rows stay where they are
+// (every register index is a compile-time constant) and only the owner of the pivot column depends on the data, so what
+// comes out is row p of B = row pc[p] of the solution; the caller undoes the permutation through shared memory.
+// (MM - 1) FMAs per column and step against 2 (MM - p) + back-substitution for the Householder variant: 0.7 x the
+// arithmetic at MM = 9 with 3 + 3 slots, and no serial backward phase.  Returns false on a zero / non-finite pivot.
+template <int MM, int G, int NR>
+DYB_D bool gj_solve(double (&A)[(MM + G - 1) / G][MM], double (&B)[NR][MM], int lg, unsigned mask, int (&pc)[MM]) {
+  constexpr int SL = (MM + G - 1) / G;
+  static_assert(MM <= 16, "column number must fit the four key bits");
+  unsigned used = 0u;                               // bit sl: own column sl * G + lg has served as a pivot
+  bool ok = true;
+#pragma unroll
+  for (int p = 0; p < MM; ++p) {
+    unsigned key = 0u;
+    int msl = 0;
+#pragma unroll
+    for (int sl = 0; sl < SL; ++sl) {
+      const int col = sl * G + lg;
+      const unsigned k = (((unsigned)__double2hiint(A[sl][p]) & 0x7ffffff0u) + 16u) | (unsigned)col;
+      const bool cand = (col < MM) && !((used >> sl) & 1u);
+      if (cand && k > key) { key = k; msl = sl; }
+    }
+    double v[MM];
+#pragma unroll
+    for (int r = 0; r < MM; ++r) {
+      double t = A[0][r];
+#pragma unroll
+      for (int sl = 1; sl < SL; ++sl) t = (msl == sl) ? A[sl][r] : t;
+      v[r] = t;
+    }
+    unsigned kb = key;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) kb = max(kb, __shfl_xor_sync(mask, kb, o, G));
+    const int pcol = (int)(kb & 15u);
+    const int pl = pcol % G;
+    pc[p] = pcol;
+    if (lg == pl) used |= 1u << msl;
+    double x[MM];
+#pragma unroll
+    for (int r = 0; r < MM; ++r) x[r] = gshfl<G>(mask, v[r], pl);
+    const double ap = fabs(x[p]);
+    ok = ok && (ap > 0.0) && (ap < 1e150);
+    const double ip = fast_rcp(x[p]);
+#pragma unroll
+    for (int sl = 0; sl < SL; ++sl) A[sl][p] *= ip;
+#pragma unroll
+    for (int sl = 0; sl < NR; ++sl) B[sl][p] *= ip;
+#pragma unroll
+    for (int r = 0; r < MM; ++r) {
+      if (r == p) continue;
+#pragma unroll
+      for (int sl = 0; sl < SL; ++sl) A[sl][r] = fma(-x[r], A[sl][p], A[sl][r]);
+#pragma unroll
+      for (int sl = 0; sl < NR; ++sl) B[sl][r] = fma(-x[r], B[sl][p], B[sl][r]);
+    }
+  }
+  return ok;
+}
+
+// m x m solver of cr_kernel: 0 = Householder QR (default), 1 = Gauss-Jordan with column pivoting.  Measured on B200
+// (profiles/r02_d_cr_solver_ab.txt, 65 536 draws): fs2000 0.410 ms (QR) against 0.485 ms (GJ), ls2003 0.324 / 0.360,
+// hs_nk 0.159 / 0.155 -- the pivoted variant executes 0.71 x the fp64 instructions (881 against 1 243 per iteration at
+// MM = 9) but 331 FSEL + LDS / STS for the dynamic slot and the un-permutation make its loop 2 165 instructions against
+// 1 894, and the kernel's time follows the instruction count, not the fp64 count.
+#ifndef DYB_CR_SOLVER
+#define DYB_CR_SOLVER 0
+#endif
+
 struct CrOptions { double cr_tol; int cr_maxit; };
 
 #ifndef DYB_CR_LANES
 #define DYB_CR_LANES 4
 #endif
 #ifndef DYB_CR_MIN_CTAS
-#define DYB_CR_MIN_CTAS 6
+#define DYB_CR_MIN_CTAS (DYB_CR_SOLVER ? 5 : 6)
 #endif
 
 // Geometry of cr_kernel: G lanes per draw, CTAs of BLOCK threads, one shared-memory tile per draw holding
-// A1 (MM x MM) | acc_hat (MM x K) | A0 (MM x K) | A2 (MM x NF), column-major.  The tile stride is padded to
+// A1 (MM x MM) | acc_hat (MM x K) | A0 (MM x K) | A2 (MM x NF) | X (MM x (K + NF), the un-permuting buffer of the
+// Gauss-Jordan solver), column-major.  The tile stride is padded to
 // 4 (mod 16) doubles so that the "own column" accesses of a half-warp (4 draws x 4 lanes, column stride MM)
 // fall into 16 distinct 8-byte banks when MM is odd.
 template <class M>
@@ -220,11 +292,34 @@ struct CrCfg {
   static constexpr int G = DYB_CR_LANES, BLOCK = 64, GROUPS = BLOCK / G;
   static constexpr int MM = M::M, K = M::K, NF = M::NF;
   static constexpr int OFF_A1 = 0, OFF_ACC = MM * MM, OFF_A0 = OFF_ACC + MM * K, OFF_A2 = OFF_A0 + MM * K;
-  static constexpr int TILE_RAW = OFF_A2 + MM * NF;
+  static constexpr int OFF_X = OFF_A2 + MM * NF;
+  static constexpr int TILE_RAW = OFF_X + (DYB_CR_SOLVER ? MM * (K + NF) : 0);
   static constexpr int PAD_TO = (G == 4) ? 4 : 8;       // tile stride mod 16 that spreads a half-warp over 16 banks
   static constexpr int TILE = TILE_RAW + ((PAD_TO - TILE_RAW % 16) + 16) % 16;
   static constexpr int MIN_CTAS = DYB_CR_MIN_CTAS;
+  static constexpr int MAX_REGS = (65536 / (BLOCK * MIN_CTAS)) / 8 * 8;
+  static constexpr bool FITS = (MM <= 12) && (K >= 1) && (NF >= 1) && (NF + K >= M::NX) &&
+                               (sizeof(double) * GROUPS * TILE <= 48 * 1024);
 };
+
+// B (own columns, rows in pivot order pc) -> natural row order through the draw's X buffer.  Slot s of the lane is
+// column xcol[s] of the buffer (negative: a padding slot, nothing stored, whatever read); same thread writes and reads.
+template <int MM, int NR>
+DYB_D void unpermute_rows(double (&B)[NR][MM], const int (&pc)[MM], double* Xs, const int (&xcol)[NR]) {
+#pragma unroll
+  for (int s = 0; s < NR; ++s) {
+    if (xcol[s] >= 0) {
+#pragma unroll
+      for (int p = 0; p < MM; ++p) Xs[pc[p] + MM * xcol[s]] = B[s][p];
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NR; ++s) {
+    const double* xs = Xs + MM * (xcol[s] >= 0 ? xcol[s] : 0);
+#pragma unroll
+    for (int r = 0; r < MM; ++r) B[s][r] = xs[r];
+  }
+}
 
 // All 32 lanes of a warp (8 draws) run the SAME instruction stream: shuffles use the full mask (a partial mask costs
 // a WARPSYNC / BSSY / BSYNC sequence per shuffle), the iteration runs until every draw of the warp has stopped, and a
@@ -232,7 +327,7 @@ struct CrCfg {
 // result does not depend on its neighbours.  Between iterations the whole state of a draw lives in its shared tile;
 // registers only hold the transient copies of one iteration (A1 and [X0 | X2] by column, then the GEMM accumulators).
 template <class M, int G>
-__global__ void __launch_bounds__(CrCfg<M>::BLOCK, CrCfg<M>::MIN_CTAS)
+__global__ void __launch_bounds__(CrCfg<M>::BLOCK) __maxnreg__(CrCfg<M>::MAX_REGS)
 cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
           int* __restrict__ status, int* __restrict__ cr_iters) {
   using C = CrCfg<M>;
@@ -252,6 +347,8 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
   double* accs = A1s + (C::OFF_ACC - C::OFF_A1);
   double* A0s = A1s + (C::OFF_A0 - C::OFF_A1);
   double* A2s = A1s + (C::OFF_A2 - C::OFF_A1);
+  [[maybe_unused]] double* Xs = A1s + (C::OFF_X - C::OFF_A1);
+  [[maybe_unused]] int pc[MM];
   const double* md = mid + d;
   const long long st = n_draws;
   const int st_in = status[d];
@@ -301,7 +398,19 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
       for (int r = 0; r < MM; ++r) XB[SL0 + s][r] = (col < NF) ? A2s[r + MM * col] : 0.0;
     }
     // [X0 | X2] = A1^-1 [A0 | A2]
+#if DYB_CR_SOLVER
+    const bool okq = gj_solve<MM, G, NR>(A1w, XB, lg, FULL, pc);
+    {
+      int xcol[NR];
+#pragma unroll
+      for (int s = 0; s < SL0; ++s) xcol[s] = (s * G + lg < K) ? s * G + lg : -1;
+#pragma unroll
+      for (int s = 0; s < SL2; ++s) xcol[SL0 + s] = (s * G + lg < NF) ? K + s * G + lg : -1;
+      unpermute_rows<MM, NR>(XB, pc, Xs, xcol);
+    }
+#else
     const bool okq = qr_solve<MM, G, NR>(A1w, XB, lg, FULL);
+#endif
     const bool commit = active && okq;
 
     // pass 1: own columns j of [W00 | W01] = A0 * X[bk, j], columns of A0 broadcast from the tile
@@ -447,7 +556,18 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
 #pragma unroll
     for (int r = 0; r < MM; ++r) Gc[s][r] = (col < K) ? -A0s[r + MM * col] : 0.0;
   }
-  bool okq = qr_solve<MM, G, SL0>(A1h, Gc, lg, FULL);         // Gc now holds G's own columns
+#if DYB_CR_SOLVER
+  bool okq = gj_solve<MM, G, SL0>(A1h, Gc, lg, FULL, pc);
+  {
+    int xcol[SL0];
+#pragma unroll
+    for (int s = 0; s < SL0; ++s) xcol[s] = (s * G + lg < K) ? s * G + lg : -1;
+    unpermute_rows<MM, SL0>(Gc, pc, Xs, xcol);
+  }
+#else
+  bool okq = qr_solve<MM, G, SL0>(A1h, Gc, lg, FULL);
+#endif
+  // Gc now holds G's own columns
   // ---- g_u = -(A1(0) + A2(0) G[fw, :])^-1 F_u ---------------------------------------------------------------------------
   double w[SL0][MM];
 #pragma unroll
@@ -497,7 +617,18 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
       if (lg == cu % G) U[cu / G][rr] = -md[(L::OFF_RED + e) * st];
     }
   }
+#if DYB_CR_SOLVER
+  okq = gj_solve<MM, G, SLU>(A1h, U, lg, FULL, pc) && okq;
+  {
+    static_assert(NX <= K + NF, "X buffer holds the shock columns");
+    int xcol[SLU];
+#pragma unroll
+    for (int s = 0; s < SLU; ++s) xcol[s] = (s * G + lg < NX) ? s * G + lg : -1;
+    unpermute_rows<MM, SLU>(U, pc, Xs, xcol);
+  }
+#else
   okq = qr_solve<MM, G, SLU>(A1h, U, lg, FULL) && okq;
+#endif
   if (result == ST_OK && !okq) result = ST_SOLVER;
   if (real && result == ST_OK) {
 #pragma unroll

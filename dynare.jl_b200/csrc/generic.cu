@@ -1,6 +1,7 @@
 // Run-time-size entry points (include/dynare_b200.h, "models without a generated device function"): a handle built
 // from index sets alone, the solve / likelihood from host-evaluated Jacobians, the batched doubling Lyapunov
 // solver and the generic dense Kalman filter.
+#include <cstdlib>
 #include <algorithm>
 
 #include <atomic>
@@ -133,6 +134,7 @@ static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaSt
                       (size_t)8 * threads >= (size_t)q.nsp * DL_BK + (size_t)DL_BK * 8 * DL_NTP;
     if (fits && g_kalman_variant != 1 && g.ns > 8 * DMMA_MAX_TILES) {
       long long grid = g.n_draws < dev_sms ? g.n_draws : dev_sms;
+      if (const char* e = getenv("DYB_KL_GRID")) { const long long c = atoll(e); if (c > 0 && c < grid) grid = c; }   // experiments only
       g.scratch = sg.temp<double>(kalman_large_scratch_doubles(g.ns, g.ny) * (size_t)grid);
       if (sg.err != cudaSuccess) return sg.err;
       auto launch = [&](auto kern) -> cudaError_t {

@@ -86,10 +86,11 @@ cudaError_t mt_kalman_sub(const double* d_ss, long long n, const double* d_Y, in
 }
 
 // lanes per draw of the filter: 1 = one thread per draw (throughput kernel), 4 / 8 = shared-tile kernel for batches that
-// leave schedulers idle; `want` = dyb_options.filter_lanes (0 = choose by batch width)
+// leave schedulers idle; `want` = dyb_options.filter_lanes (0 = choose by batch width: 8 lanes up to 2 048 draws, 4 up to
+// 4 096, one thread per draw beyond -- ls2003 filter at 2 048 / 4 096 / 8 192 draws: 0.164 / 0.189 / 0.229 ms with 8 / 4 / 1 lanes)
 int mt_kalman_lanes(long long n, int nobs, int want) {
   int g = want;
-  if (g != 1 && g != 4 && g != 8) g = (n <= 4096) ? 8 : 1;
+  if (g != 1 && g != 4 && g != 8) g = (n <= 2048) ? 8 : ((n <= 4096) ? 4 : 1);     // measured: profiles/r02_f_small_batch_lanes.txt
   if (g == 4 && (!KalmanSubCfg<MT, 4>::FITS || KalmanSubCfg<MT, 4>::smem_bytes(nobs) > 200 * 1024)) g = 8;
   if (g == 8 && (!KalmanSubCfg<MT, 8>::FITS || KalmanSubCfg<MT, 8>::smem_bytes(nobs) > 200 * 1024)) g = 1;
   return g;

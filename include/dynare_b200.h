@@ -80,8 +80,8 @@ typedef struct dyb_options {
   int32_t presample;        /* periods excluded from the likelihood sum (default 0) */
   int32_t solver;           /* 0 auto; 1 one thread per draw (any size; for run-time-size and medium models: the shared-memory
                                kernel instead of the register-blocked one); 2 cooperative register-resident (m <= 12) */
-  int32_t filter_lanes;     /* lanes per draw of the model-specific Kalman kernel: 0 auto (8 up to 4 096 draws per call, else
-                             * 1), 1 = one thread per draw (throughput kernel), 4, 8 = shared-tile kernel for batches that
+  int32_t filter_lanes;     /* lanes per draw of the model-specific Kalman kernel: 0 auto (8 up to 2 048 draws per call, 4 up to
+                             * 4 096, else 1), 1 = one thread per draw (throughput kernel), 4, 8 = shared-tile kernel for batches that
                              * leave schedulers idle (an SMC stage on a shard); same sums in the same order */
   int32_t univariate_fallback; /* what a period whose innovation covariance F fails its Cholesky factorisation does:
                              * 0 (default) the draw is rejected (status 6, loglik -Inf); 1 the period is processed one observation

@@ -104,6 +104,7 @@ SIGNATURES = {
     "dyb_smc_resample_multinomial": (C.c_int, [C.c_int, _D, _D, C.c_int64, _I64, C.POINTER(C.c_int64)]),
     "dyb_smc_resample_systematic": (C.c_int, [C.c_int, _D, C.c_double, C.c_int64, _I64, C.POINTER(C.c_int64)]),
     "dyb_smc_moments": (C.c_int, [C.c_int, _D, _D, C.c_int64, C.c_int32, _D, _D]),
+    "dyb_smc_covariance_factor": (C.c_int, [C.c_int, _D, C.c_int32, _D, _D, C.POINTER(C.c_int32)]),
     "dyb_set_kalman_variant": (C.c_int, [C.c_int32]),
     "dyb_create_generic": (C.c_int, [C.POINTER(ModelDesc), C.c_int, C.POINTER(_P)]),
     "dyb_first_order_from_jacobian_batch": (C.c_int, [_P, _D, _D, C.c_int32, C.c_int64, _D, _D, _D, _D, _I32, _I32, _I32]),
@@ -121,6 +122,8 @@ SIGNATURES = {
     "dyb_smc_local_range": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dyb_smc_transport": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dyb_smc_init": (C.c_int, [_P, _D, _I32]),
+    "dyb_smc_init_from_prior": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_int64)]),
+    "dyb_prior_draw": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_int32, _D]),
     "dyb_smc_run": (C.c_int, [_P, C.c_int32]),
     "dyb_smc_stages_done": (C.c_int, [_P]),
     "dyb_smc_set_profiling": (C.c_int, [_P, C.c_int32]),

@@ -265,6 +265,34 @@ int dyb_smc_moments(int device, const double* para, const double* w, int64_t n, 
   return DYB_OK;
 }
 
+int dyb_smc_covariance_factor(int device, const double* R, int32_t np, double* Rpsd, double* L, int32_t* projected) {
+  if (np <= 0 || np > MAX_EST || !R || !Rpsd || !L || !projected) return fail(DYB_ERR_ARG, "bad argument");
+  DYB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = device_stream(device);
+  Stager sg(st);
+  const size_t n2 = (size_t)np * np;
+  const double* dRin = sg.in(R, n2);
+  double* dR = sg.out(Rpsd, n2);
+  double* dL = sg.out(L, n2);
+  double* drd = sg.temp<double>((size_t)np);
+  double* daux = sg.temp<double>(4);
+  double* dwork = sg.temp<double>(2 * n2);
+  int* derr = sg.temp<int>(1);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  DYB_CUDA(cudaMemcpyAsync(dR, dRin, 8 * n2, cudaMemcpyDeviceToDevice, st));
+  DYB_CUDA(cudaMemsetAsync(daux, 0, 32, st));
+  DYB_CUDA(cudaMemsetAsync(derr, 0, 4, st));
+  smc_covariance_factor_kernel<<<1, 32, 8 * n2, st>>>(dR, np, dL, drd, daux, dwork, derr);
+  DYB_CUDA(cudaGetLastError());
+  double aux1[4] = {0, 0, 0, 0};
+  int err1 = 0;
+  DYB_CUDA(cudaMemcpyAsync(aux1, daux, 32, cudaMemcpyDeviceToHost, st));
+  DYB_CUDA(cudaMemcpyAsync(&err1, derr, 4, cudaMemcpyDeviceToHost, st));
+  DYB_CUDA(sg.finish());
+  *projected = err1 ? 2 : (aux1[2] > 0.0 ? 1 : 0);
+  return DYB_OK;
+}
+
 // ---- communicator ------------------------------------------------------------------------------------
 int dyb_comm_unique_id(void* id) {
   if (!id) return fail(DYB_ERR_ARG, "null argument");
@@ -525,7 +553,7 @@ int dyb_smc_create(dyb_handle* h, const dyb_smc_options* o, const double* phi, d
   R(s->ctl, sizeof(SmcCtl)); R(s->phi_d, 8 * (size_t)o->nphi);
   R(s->w_g, 8 * N); R(s->wt_g, 8 * N); R(s->cwl, 8 * N); R(s->bt, 8 * nb); R(s->bt2, 8 * nb); R(s->btw, 8 * nb); R(s->offs, 8 * nb);
   R(s->idx, 8 * N); R(s->xsel, 8 * N * (np + 2)); R(s->part1, 8 * nb * np); R(s->part2, 8 * nb * np * np);
-  R(s->mu, 8 * np); R(s->R, 8 * np * np); R(s->L, 8 * np * np); R(s->rdiag, 8 * np); R(s->aux, 16);
+  R(s->mu, 8 * np); R(s->R, 8 * np * np); R(s->L, 8 * np * np); R(s->rdiag, 8 * np); R(s->aux, 32 + 16 * np * np);     // aux: 4 scalars + the 2 np^2 workspace of the PSD projection
   R(s->prop, 8 * np * n); R(s->qx, 8 * n); R(s->q0, 8 * n); R(s->lx, 8 * n); R(s->st, 4 * n); R(s->priorx, 8 * n);
   R(s->stats, 8 * SMC_STATS * (size_t)o->nphi);
   R(s->tmp_para, 8 * np * n); R(s->tmp_ll, 8 * n); R(s->tmp_lp, 8 * n);
@@ -536,7 +564,7 @@ int dyb_smc_create(dyb_handle* h, const dyb_smc_options* o, const double* phi, d
     CK(cudaMemsetAsync(s->slab.p, 0, s->slab_bytes, h->stream));
     CK(cudaMemsetAsync(s->ctl.p, 0, sizeof(SmcCtl), h->stream));
     CK(cudaMemsetAsync(s->stats.p, 0, 8 * SMC_STATS * (size_t)o->nphi, h->stream));
-    CK(cudaMemsetAsync(s->aux.p, 0, 16, h->stream));
+    CK(cudaMemsetAsync(s->aux.p, 0, 32, h->stream));
     CK(cudaMemcpyAsync(s->phi_d.p, s->phi.data(), 8 * (size_t)o->nphi, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
@@ -581,6 +609,26 @@ int dyb_smc_transport(const dyb_smc* s, int32_t* peer_stores, int32_t* cuda_grap
   return DYB_OK;
 }
 
+// prior density, packing into the payload, initial weights / control block / records: what follows the likelihood of the
+// initial particles (which is in s->lx / s->st for the draws in s->prop)
+static int smc_init_finish(dyb_smc* s, const PriorSetDev& ps) {
+  dyb_handle* h = s->h;
+  const long long n = s->n_local;
+  cudaStream_t st = h->stream;
+  logprior_kernel<<<nblk(n, 128), 128, 0, st>>>(ps, s->prop.as<double>(), n, s->priorx.as<double>());
+  const SmcStageArgs a = stage_args(s);
+  smc_init_pack_kernel<<<nblk(n, 256), 256, 0, st>>>(a, s->prop.as<double>(), s->lx.as<double>(), s->priorx.as<double>(), s->phi[0]);
+  smc_fill_kernel<<<nblk(s->npart, 256), 256, 0, st>>>(s->w_g.as<double>(), s->npart, 1.0 / (double)s->npart);
+  SmcCtl c0{};
+  c0.stage = 1; c0.tune = SmcTune{s->c0, s->acpt0};
+  DYB_CUDA(cudaMemcpyAsync(s->ctl.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, st));
+  const double st0[SMC_STATS] = {1.0, (double)s->npart, 0.0, 0.0, 0.0, 0.0};
+  DYB_CUDA(cudaMemcpyAsync(s->stats.p, st0, sizeof(st0), cudaMemcpyHostToDevice, st));
+  DYB_CUDA(cudaGetLastError());
+  h->launches += 3;
+  return DYB_OK;
+}
+
 // initial particles (smc.jl:84-101): the caller draws them from the prior; the likelihood, the prior density and
 // logpost = phi[1] * loglh + logprior are evaluated here.  status[i] != 0 marks draws the reference would reject
 // (obj = -Inf): replace them and call again.  Local to the rank (no collective).
@@ -596,21 +644,70 @@ int dyb_smc_init(dyb_smc* s, const double* para_local, int32_t* status) {
   DYB_CUDA(cudaMemcpyAsync(s->prop.p, para_local, 8 * (size_t)s->np * n, cudaMemcpyDefault, st));
   rc = dyb_loglik_batch_device(h, s->prop.as<double>(), n, s->lx.as<double>(), s->st.as<int>());
   if (rc) return rc;
-  logprior_kernel<<<nblk(n, 128), 128, 0, st>>>(ps, s->prop.as<double>(), n, s->priorx.as<double>());
-  const SmcStageArgs a = stage_args(s);
-  smc_init_pack_kernel<<<nblk(n, 256), 256, 0, st>>>(a, s->prop.as<double>(), s->lx.as<double>(), s->priorx.as<double>(), s->phi[0]);
-  smc_fill_kernel<<<nblk(s->npart, 256), 256, 0, st>>>(s->w_g.as<double>(), s->npart, 1.0 / (double)s->npart);
-  SmcCtl c0{};
-  c0.stage = 1; c0.tune = SmcTune{s->c0, s->acpt0};
-  DYB_CUDA(cudaMemcpyAsync(s->ctl.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, st));
-  const double st0[SMC_STATS] = {1.0, (double)s->npart, 0.0, 0.0, 0.0, 0.0};
-  DYB_CUDA(cudaMemcpyAsync(s->stats.p, st0, sizeof(st0), cudaMemcpyHostToDevice, st));
-  DYB_CUDA(cudaGetLastError());
-  h->launches += 3;
+  rc = smc_init_finish(s, ps);
+  if (rc) return rc;
   if (status) DYB_CUDA(cudaMemcpyAsync(status, s->st.p, 4 * (size_t)n, cudaMemcpyDefault, st));
   DYB_CUDA(cudaStreamSynchronize(st));
   s->stage = 1;
   s->published = false;
+  return DYB_OK;
+}
+
+// the same with the prior draws made on the device (prior_draw!, estimation.jl:329-335, inside the rejection loop of
+// smc.jl:87-101): round 0 draws every local particle, round r > 0 re-draws the ones whose likelihood was not finite; the host
+// only reads one counter per round.  The draw of global particle j in round r depends on (seed, j, r) alone, so the initial
+// cloud does not depend on the number of GPUs.
+int dyb_smc_init_from_prior(dyb_smc* s, uint64_t seed, int32_t max_rounds, int64_t* n_draws) {
+  if (!s || max_rounds < 1) return fail(DYB_ERR_ARG, "bad argument");
+  dyb_handle* h = s->h;
+  DYB_CUDA(cudaSetDevice(h->device));
+  PriorSetDev ps;
+  int rc = prior_set(h, &ps);
+  if (rc) return rc;
+  const long long n = s->n_local;
+  cudaStream_t st = h->stream;
+  unsigned long long* cnt = s->idx.as<unsigned long long>();          // free until the first selection step
+  DYB_CUDA(cudaMemsetAsync(cnt, 0, 8, st));
+  unsigned long long total = 0;
+  bool done = false;
+  for (int r = 0; r < max_rounds && !done; ++r) {
+    prior_draw_kernel<<<nblk(n, 128), 128, 0, st>>>(ps, seed, s->first, n, (unsigned)r, r == 0 ? nullptr : s->st.as<int>(),
+                                                     s->prop.as<double>(), cnt);
+    DYB_CUDA(cudaGetLastError());
+    h->launches += 1;
+    unsigned long long now = 0;
+    DYB_CUDA(cudaMemcpyAsync(&now, cnt, 8, cudaMemcpyDeviceToHost, st));
+    DYB_CUDA(cudaStreamSynchronize(st));
+    if (now == total) { done = true; break; }                         // nothing was re-drawn: every particle is finite
+    total = now;
+    rc = dyb_loglik_batch_device(h, s->prop.as<double>(), n, s->lx.as<double>(), s->st.as<int>());
+    if (rc) return rc;
+  }
+  if (n_draws) *n_draws = (int64_t)total;
+  if (!done) return fail(DYB_ERR_STATE, "could not draw initial particles with a finite likelihood within max_rounds");
+  rc = smc_init_finish(s, ps);
+  if (rc) return rc;
+  DYB_CUDA(cudaStreamSynchronize(st));
+  s->stage = 1;
+  s->published = false;
+  return DYB_OK;
+}
+
+// prior draws on their own: para np x n (draw-major), draw i = particle first + i of round `round`
+int dyb_prior_draw(dyb_handle* h, int64_t n, int64_t first, uint64_t seed, int32_t round, double* para) {
+  if (!h || n < 0 || round < 0 || (n > 0 && !para)) return fail(DYB_ERR_ARG, "bad argument");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  PriorSetDev ps;
+  int rc = prior_set(h, &ps);
+  if (rc) return rc;
+  Stager sg(h->stream);
+  double* d = sg.out(para, (size_t)n * ps.np);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  prior_draw_kernel<<<nblk(n, 128), 128, 0, h->stream>>>(ps, seed, first, n, (unsigned)round, nullptr, d, nullptr);
+  DYB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  DYB_CUDA(sg.finish());
   return DYB_OK;
 }
 

@@ -21,7 +21,7 @@ namespace dyb {
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10
 // ------------------------------------------------------------------------------------------------
-enum RngStream : unsigned { RNG_RESAMPLE = 0, RNG_MIX = 1, RNG_ACCEPT = 2, RNG_NORMAL = 3, RNG_USER = 4 };
+enum RngStream : unsigned { RNG_RESAMPLE = 0, RNG_MIX = 1, RNG_ACCEPT = 2, RNG_NORMAL = 3, RNG_USER = 4, RNG_PRIOR = 5 };
 
 DYB_HD void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
                           unsigned out[4]) {
@@ -147,6 +147,58 @@ DYB_D double transform_from_param(const PriorDevK& p, double x) {
     case 3: { const double u = (x - p.a) / (p.b - p.a); return log(u / (1.0 - u)); }
     default: return x;
   }
+}
+
+// ---- prior draws (prior_draw!, estimation.jl:329-335: pdraw[i] = rand(prior_i)) -------------------------------------------
+// Counter layout of stream RNG_PRIOR: (draw index, round, block) with block = k << 12 | attempt << 2 | sub for parameter k:
+// attempt t < 512 of a rejection sampler uses the normal pair of sub 0 / 2 and the uniform of sub 1 / 3 (first / second
+// Gamma variate of the parameter), attempt 512 + g holds the uniform of the shape-below-one boost of variate g.
+// Gamma(a, 1) by Marsaglia & Tsang (2000): d = a - 1/3, c = 1 / sqrt(9 d), v = (1 + c z)^3, accept when
+// log u < z^2 / 2 + d - d v + d log v; a < 1: Gamma(a + 1, 1) u^(1/a).  oracle/sampler.py restates it in numpy.
+DYB_D double rng_gamma(unsigned long long seed, unsigned long long idx, unsigned round, unsigned kbase, int g, double a) {
+  double boost = 1.0;
+  if (a < 1.0) {
+    const double u = rng_uniform(seed, idx, round, RNG_PRIOR, kbase | ((512u + (unsigned)g) << 2));
+    boost = pow(1.0 - u, 1.0 / a);                     // 1 - u in (0, 1]
+    a += 1.0;
+  }
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (unsigned t = 0; t < 512u; ++t) {
+    double z, z1;
+    rng_normal_pair(seed, idx, round, RNG_PRIOR, kbase | (t << 2) | (unsigned)(2 * g), z, z1);
+    double v = 1.0 + c * z;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    const double u = 1.0 - rng_uniform(seed, idx, round, RNG_PRIOR, kbase | (t << 2) | (unsigned)(2 * g + 1));
+    if (log(u) < 0.5 * z * z + d - d * v + d * log(v)) return d * v * boost;
+  }
+  return d * boost;
+}
+
+DYB_D double prior_draw(const PriorDevK& p, unsigned long long seed, unsigned long long idx, unsigned round, int k) {
+  const unsigned kbase = (unsigned)k << 12;
+  switch (p.shape) {
+    case 1: { const double x = rng_gamma(seed, idx, round, kbase, 0, p.a), y = rng_gamma(seed, idx, round, kbase, 1, p.b);
+              return x / (x + y); }
+    case 2: return p.b * rng_gamma(seed, idx, round, kbase, 0, p.a);
+    case 3: { double z, z1; rng_normal_pair(seed, idx, round, RNG_PRIOR, kbase, z, z1); return p.a + p.b * z; }
+    case 4: return sqrt(p.b / rng_gamma(seed, idx, round, kbase, 0, p.a));       // sqrt of InverseGamma(a, b) (inversegamma1.jl:167)
+    case 5: return p.a + (p.b - p.a) * rng_uniform(seed, idx, round, RNG_PRIOR, kbase);
+    case 6: return p.b / rng_gamma(seed, idx, round, kbase, 0, p.a);
+    case 8: return p.b * pow(-log(1.0 - rng_uniform(seed, idx, round, RNG_PRIOR, kbase)), 1.0 / p.a);
+    default: return NAN;
+  }
+}
+
+// para[:, i] = a draw from the priors for every i < n whose status is non-zero (status null: every i); the draw of particle
+// first + i in round r depends on (seed, first + i, r) only
+__global__ void prior_draw_kernel(PriorSetDev ps, unsigned long long seed, long long first, long long n, unsigned round,
+                                  const int* __restrict__ status, double* __restrict__ para, unsigned long long* __restrict__ n_drawn) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (status && status[i] == 0) return;
+  for (int k = 0; k < ps.np; ++k) para[i * ps.np + k] = prior_draw(ps.p[k], seed, (unsigned long long)(first + i), round, k);
+  if (n_drawn) atomicAdd(n_drawn, 1ULL);
 }
 
 // logprior[i] = sum_k logpdf(prior_k, theta[k, i])   (estimation.jl:455-462; left-to-right sum)

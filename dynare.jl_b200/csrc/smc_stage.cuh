@@ -237,9 +237,63 @@ __global__ void __launch_bounds__(256) smc_select_take_kernel(SmcStageArgs a) {
   }
 }
 
-// Cholesky factor of the particle covariance by one warp (smc.jl:161-165); A: np*np doubles of shared memory
-DYB_D void smc_chol_warp(const double* __restrict__ R, int np, double* A, double* __restrict__ L,
-                         double* __restrict__ rdiag, double* __restrict__ aux, int* __restrict__ err, int lane) {
+// prox!(RPSD, IndPSD(), R) (smc.jl:163; ProximalOperators' IndPSD: symmetric eigen-decomposition, negative eigenvalues set
+// to zero): cyclic Jacobi by one warp on the full symmetric matrix W (np x np), eigenvectors accumulated in V, eigenvalues
+// left in lam; on return W = V max(Lambda, 0) V'.  Only reached when the Cholesky factorisation of R has failed -- on a
+// positive-definite matrix the projection is the identity and is skipped.  W, V, lam: global or shared memory.
+DYB_D void smc_psd_project_warp(double* W, double* V, double* lam, int np, int lane) {
+  for (int e = lane; e < np * np; e += 32) V[e] = (e % np == e / np) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int e = lane; e < np * np; e += 32) {
+      const double v = W[e];
+      if (e % np == e / np) dg = fma(v, v, dg); else off = fma(v, v, off);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dg += __shfl_xor_sync(0xffffffffu, dg, o); }
+    if (!(off > 1e-32 * dg)) break;                      // also leaves on NaN
+    for (int p = 0; p < np - 1; ++p) {
+      for (int q = p + 1; q < np; ++q) {
+        const double apq = W[p + np * q];
+        if (apq == 0.0) continue;                         // the same value in every lane
+        const double theta = (W[q + np * q] - W[p + np * p]) / (2.0 * apq);
+        const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+        const double c = rsqrt(fma(t, t, 1.0)), sn = t * c;
+        __syncwarp();
+        for (int k = lane; k < np; k += 32) {             // W <- W J, V <- V J
+          const double wp = W[k + np * p], wq = W[k + np * q];
+          W[k + np * p] = c * wp - sn * wq; W[k + np * q] = sn * wp + c * wq;
+          const double vp = V[k + np * p], vq = V[k + np * q];
+          V[k + np * p] = c * vp - sn * vq; V[k + np * q] = sn * vp + c * vq;
+        }
+        __syncwarp();
+        for (int k = lane; k < np; k += 32) {             // W <- J' W
+          const double wp = W[p + np * k], wq = W[q + np * k];
+          W[p + np * k] = c * wp - sn * wq; W[q + np * k] = sn * wp + c * wq;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  for (int k = lane; k < np; k += 32) lam[k] = W[k + np * k];
+  __syncwarp();
+  for (int e = lane; e < np * np; e += 32) {
+    const int i = e % np, j = e / np;
+    double sacc = 0.0;
+    for (int k = 0; k < np; ++k) sacc = fma(V[i + np * k] * fmax(lam[k], 0.0), V[j + np * k], sacc);
+    W[e] = sacc;
+  }
+  __syncwarp();
+  for (int e = lane; e < np * np; e += 32) {              // exactly symmetric
+    const int i = e % np, j = e / np;
+    if (i > j) { const double m = 0.5 * (W[i + np * j] + W[j + np * i]); W[i + np * j] = m; W[j + np * i] = m; }
+  }
+  __syncwarp();
+}
+
+// lower Cholesky factor of R (lower triangle read) in A (np*np doubles of shared memory); true when a pivot is not positive
+DYB_D bool smc_chol_try(const double* R, int np, double* A, int lane) {
   for (int e = lane; e < np * np; e += 32) {
     const int i = e % np, j = e / np;
     A[e] = (i >= j) ? R[i + np * j] : 0.0;
@@ -260,6 +314,31 @@ DYB_D void smc_chol_warp(const double* __restrict__ R, int np, double* A, double
     for (int i = j + lane; i < np; i += 32) A[i + np * j] = (i == j) ? ljj : A[i + np * j] / ljj;
     __syncwarp();
   }
+  return bad;
+}
+
+// Covariance of the particles -> RPSD, its diagonal and its Cholesky factor by one warp (smc.jl:161-165):
+//     prox!(tune.RPSD, IndPSD(), tune.R); tune.Rdiag = diag(tune.RPSD); tune.Rchol .= cholesky(tune.RPSD).L
+// R is factorised directly; only if that fails is it replaced by its projection on the positive semi-definite cone and
+// factorised again (a matrix that is STILL not positive definite makes the reference's `cholesky` throw: *err = 1).
+// A: np*np doubles of shared memory; work: 2 np*np doubles (global); aux[0..1] log-determinant terms, aux[2] counts the
+// projections.  R may be overwritten by RPSD.
+DYB_D void smc_chol_warp(double* R, int np, double* A, double* __restrict__ L, double* __restrict__ rdiag,
+                         double* __restrict__ aux, double* work, int* __restrict__ err, int lane) {
+  bool bad = smc_chol_try(R, np, A, lane);
+  if (bad && work) {
+    double* W = work; double* V = work + np * np;
+    for (int e = lane; e < np * np; e += 32) {
+      const int i = e % np, j = e / np;
+      W[e] = (i >= j) ? R[i + np * j] : R[j + np * i];
+    }
+    __syncwarp();
+    smc_psd_project_warp(W, V, rdiag, np, lane);
+    for (int e = lane; e < np * np; e += 32) R[e] = W[e];
+    __syncwarp();
+    bad = smc_chol_try(R, np, A, lane);
+    if (lane == 0) aux[2] += 1.0;
+  }
   for (int e = lane; e < np * np; e += 32) L[e] = A[e];
   for (int k = lane; k < np; k += 32) rdiag[k] = R[k + np * k];
   if (lane == 0) {
@@ -268,6 +347,17 @@ DYB_D void smc_chol_warp(const double* __restrict__ R, int np, double* A, double
     aux[0] = s0; aux[1] = s1;
     if (bad) *err = 1;
   }
+}
+
+// stand-alone entry (dyb_smc_covariance_factor): <<<1, 32, np*np doubles>>>; R np x np in/out, work 2 np*np, out3 = aux
+__global__ void smc_covariance_factor_kernel(double* R, int np, double* L, double* rdiag, double* aux, double* work, int* err) {
+  extern __shared__ double sm_cf[];
+  for (int e = threadIdx.x; e < np * np; e += 32) {     // only the lower triangle of the input is meaningful
+    const int i = e % np, j = e / np;
+    if (i < j) R[e] = R[j + np * i];
+  }
+  __syncwarp();
+  smc_chol_warp(R, np, sm_cf, L, rdiag, aux, work, err, threadIdx.x);
 }
 
 // ---- K4 / K5: particle mean (smc.jl:154) and covariance (:155-160) of the selected particles in the canonical order.
@@ -340,7 +430,7 @@ __global__ void __launch_bounds__(32 * SMC_MOM_WARPS) smc_moments_kernel(SmcStag
     }
     if (SECOND) {
       __syncthreads();
-      if (threadIdx.y == 0) smc_chol_warp(a.R, np, sm_mom, a.L, a.rdiag, a.aux, &a.ctl->err, lane);
+      if (threadIdx.y == 0) smc_chol_warp(a.R, np, sm_mom, a.L, a.rdiag, a.aux, a.aux + 4, &a.ctl->err, lane);
     }
   }
 }

@@ -222,6 +222,13 @@ class BatchSSWs:
         L.check(self.lib.dyb_set_priors(self._h, self.np, L.ptr(code), L.ptr(a), L.ptr(b)))
         self.priors = priors
 
+    def prior_draw(self, n, seed=0, first=0, round=0):
+        """(n, np) draws from the priors on the device (prior_draw!, estimation.jl:329-335); draw i is particle first + i of
+        the counter-based stream, so a shard of a larger cloud is reproducible on its own."""
+        out = np.empty((int(n), self.np))
+        L.check(self.lib.dyb_prior_draw(self._h, int(n), int(first), int(seed), int(round), L.ptr(out)))
+        return out
+
     def logprior(self, Theta):
         Theta = self._theta(Theta)
         out = np.empty(Theta.shape[0])
@@ -623,3 +630,16 @@ def smc_moments(para, w, device=0):
     mu = np.empty(np_); R = np.empty((np_, np_))
     L.check(lib.dyb_smc_moments(device, L.ptr(para), L.ptr(w), n, np_, L.ptr(mu), L.ptr(R)))
     return mu, R.T.copy()      # library writes column-major
+
+
+def smc_covariance_factor(R, device=0):
+    """`prox!(RPSD, IndPSD(), R)`, `cholesky(RPSD).L` of the SMC mutation step (src/estimation/smc.jl:161-165) on the device.
+    Returns (RPSD, L, projected): projected = 0 when R was positive definite (RPSD = R), 1 when it had to be projected on the
+    positive semi-definite cone first, 2 when even the projection cannot be factorised (the reference's cholesky throws)."""
+    lib = L.load()
+    R = np.asfortranarray(np.asarray(R, dtype=np.float64))
+    np_ = R.shape[0]
+    Rp = np.empty((np_, np_), order="F"); Lc = np.empty((np_, np_), order="F")
+    flag = C.c_int32()
+    L.check(lib.dyb_smc_covariance_factor(device, L.ptr(R), np_, L.ptr(Rp), L.ptr(Lc), C.byref(flag)))
+    return Rp, Lc, flag.value

@@ -80,6 +80,7 @@ class SMC:
         o.npart, o.nphi, o.lam, o.c0, o.acpt0, o.trgt, o.alp = npart, nphi, lam, c, acpt, trgt, alp
         o.resampling = {"multinomial": 0, "systematic": 1}[resampling]
         o.seed = seed
+        self._seed = seed
         self.phi = tempering_schedule(nphi, lam) if phi is None else np.ascontiguousarray(phi, dtype=np.float64)
         if self.phi.shape != (nphi,):
             raise ValueError("phi must have nphi entries")
@@ -92,9 +93,21 @@ class SMC:
         self.npart, self.nphi, self.np = npart, nphi, ssws.np
         self.prior_draws = 0
 
-    def initialise(self, rng: np.random.Generator, para: Optional[np.ndarray] = None, max_rounds=1000):
-        """Draw the initial particles from the prior until every one has a finite likelihood (smc.jl:84-101)."""
+    def initialise(self, rng: Optional[np.random.Generator] = None, para: Optional[np.ndarray] = None, max_rounds=1000,
+                   seed: Optional[int] = None):
+        """Draw the initial particles from the prior until every one has a finite likelihood (smc.jl:84-101).
+        Without ``rng`` and ``para`` the draws and the rejection loop run on the device (dyb_smc_init_from_prior; Philox
+        stream keyed by ``seed``, default the sampler's seed); with ``rng`` they are numpy draws on the host; ``para`` are
+        caller-supplied particles (rejected ones are replaced from ``rng``)."""
         n = self.n_local
+        if rng is None and para is None:
+            nd = C.c_int64()
+            L.check(self.ssws.lib.dyb_smc_init_from_prior(self._s, int(self._seed if seed is None else seed), int(max_rounds),
+                                                          C.byref(nd)))
+            self.prior_draws += nd.value
+            return None
+        if rng is None:
+            rng = np.random.default_rng(self._seed if seed is None else seed)
         if para is None:
             para = self.priors.sample(rng, n)
             self.prior_draws += n
@@ -161,7 +174,7 @@ class SMC:
 def smc(ssws: BatchSSWs, priors: PriorSet, rng: Optional[np.random.Generator] = None, **tune):
     """Run the whole recursion; returns (particles dict, stats dict)."""
     s = SMC(ssws, priors, **tune)
-    s.initialise(rng or np.random.default_rng(tune.get("seed", 0)))
+    s.initialise(rng)             # rng None: prior draws and the rejection loop on the device
     s.run()
     out = s.particles(), s.stats()
     s.close()

@@ -293,6 +293,14 @@ int dyb_smc_resample_systematic(int device, const double* w, double u0, int64_t 
  * (np x n column-major), mu np, R np x np */
 int dyb_smc_moments(int device, const double* para, const double* w, int64_t n, int32_t np,
                     double* mu, double* R);
+/* covariance of the particles -> what the mutation step uses (smc.jl:161-165): `prox!(RPSD, IndPSD(), R)` (projection on
+ * the positive semi-definite cone: symmetric eigen-decomposition, negative eigenvalues set to zero), `Rdiag = diag(RPSD)`,
+ * `Rchol = cholesky(RPSD).L`.  R np x np symmetric (lower triangle read); Rpsd, L np x np column-major.  The projection is
+ * the identity on a positive-definite matrix and is only carried out when the factorisation of R itself fails:
+ * *projected = 0 (R positive definite, Rpsd = R), 1 (projected, then factorised), 2 (still not positive definite after
+ * the projection: the reference's `cholesky` throws PosDefException; L is not usable).  The device routine is the one the
+ * SMC stage runs (csrc/smc_stage.cuh). */
+int dyb_smc_covariance_factor(int device, const double* R, int32_t np, double* Rpsd, double* L, int32_t* projected);
 
 /* ---- samplers around the batched likelihood ---------------------------------------------------------------
  * Priors: the `prior` vector of EstimatedParameters (src/dynare_containers.jl:800-841).  shape[k] uses the
@@ -346,6 +354,16 @@ int dyb_smc_transport(const dyb_smc* s, int32_t* peer_stores, int32_t* cuda_grap
  * likelihood and the prior; status[i] != 0 marks draws the reference rejects (replace them and call again).  Local to
  * the rank: ranks may call it a different number of times before the (collective) dyb_smc_run. */
 int dyb_smc_init(dyb_smc* s, const double* para_local, int32_t* status);
+/* the same with the prior draws made on the device: `prior_draw!` (src/estimation/estimation.jl:329-335, pdraw[i] =
+ * rand(prior_i)) inside the rejection loop of smc.jl:87-101 -- every local particle is drawn, the ones whose likelihood is
+ * not finite are re-drawn, until none is left (at most max_rounds rounds, else DYB_ERR_STATE).  Philox stream keyed by
+ * (seed, global particle index, round): the initial cloud does not depend on the number of GPUs.  *n_draws (may be NULL):
+ * prior draws used by this rank.  Gamma variates by Marsaglia-Tsang, Beta as a ratio of Gammas, InverseGamma(1) as
+ * (square roots of) reciprocal Gammas, Weibull / Uniform by inversion, Normal by Box-Muller. */
+int dyb_smc_init_from_prior(dyb_smc* s, uint64_t seed, int32_t max_rounds, int64_t* n_draws);
+/* prior draws on their own: para np x n_draws column-major (host or device), draw i = particle first + i of round `round`
+ * of the stream above; needs dyb_set_priors */
+int dyb_prior_draw(dyb_handle* h, int64_t n_draws, int64_t first, uint64_t seed, int32_t round, double* para);
 /* the next n_stages tempering stages: correction, selection, mutation (smc.jl:110-243); asynchronous.  With several
  * ranks this is a collective call: every rank runs the same number of stages.  A stage is seven fused kernels around the
  * likelihood batch (csrc/smc_stage.cuh), replayed as a CUDA graph; its one exchange -- the mutated particles -- is

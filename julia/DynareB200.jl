@@ -84,6 +84,15 @@ function smc_reweight!(wout, w, loglh, dphi; device = 0)
                 device, w, loglh, dphi, length(w), wout, z, e))
     return z[], e[]
 end
+# prox!(RPSD, IndPSD(), R); cholesky(RPSD).L (src/estimation/smc.jl:161-165); flag 0: R was positive definite, 1: projected
+# first, 2: the reference's cholesky would throw
+function covariance_factor(R::Matrix{Float64}; device = 0)
+    np = size(R, 1); RPSD = similar(R); L = similar(R); flag = Ref{Int32}(0)
+    check(ccall((:dyb_smc_covariance_factor, LIB), Cint, (Cint, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ref{Int32}),
+                device, R, np, RPSD, L, flag))
+    flag[] == 2 && throw(PosDefException(1))
+    return RPSD, LowerTriangular(L), Int(flag[])
+end
 function multinomial_resampling(w::Vector{Float64}, u::Vector{Float64}; device = 0)
     idx = Vector{Int64}(undef, length(w)); nc = Ref{Int64}(0)
     check(ccall((:dyb_smc_resample_multinomial, LIB), Cint, (Cint, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Ref{Int64}),
@@ -102,6 +111,12 @@ function set_priors!(ws::BatchSSWs, priors::Vector)
     check(ccall((:dyb_set_priors, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
                 ws.handle, length(shape), shape, a, b))
 end
+"`prior_draw!` (src/estimation/estimation.jl:329-335) for n draws at once on the device: np × n, column j = particle first + j."
+function prior_draw(ws::BatchSSWs, n::Integer; seed = 0, first = 0, round = 0)
+    para = Matrix{Float64}(undef, ws.np, n)
+    check(ccall((:dyb_prior_draw, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, UInt64, Int32, Ptr{Float64}), ws.handle, n, first, seed, round, para))
+    return para
+end
 "Batched `(problem::DSGELogPosteriorDensity)(θ)`: one column of Θ per draw, `-Inf` for failed draws."
 function logposterior!(out::Vector{Float64}, Θ::Matrix{Float64}, ws::BatchSSWs)
     GC.@preserve out Θ check(ccall((:dyb_logposterior_batch, LIB), Cint,
@@ -114,16 +129,20 @@ struct SmcOptions          # mirrors dyb_smc_options; defaults = Tune (smc.jl:13
     npart::Int64; nphi::Int32; lam::Float64; c0::Float64; acpt0::Float64; trgt::Float64; alp::Float64
     resampling::Int32; seed::UInt64
 end
-function smc(ws::BatchSSWs, pdraw!::Function; npart = 1000, nphi = 400, lam = 2.0, seed = 0)
+function smc(ws::BatchSSWs, pdraw!::Union{Function, Nothing} = nothing; npart = 1000, nphi = 400, lam = 2.0, seed = 0)
     opt = Ref(SmcOptions(npart, nphi, lam, 0.5, 0.25, 0.25, 0.9, 0, seed))
     s = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:dyb_smc_create, LIB), Cint, (Ptr{Cvoid}, Ref{SmcOptions}, Ptr{Float64}, Ref{Ptr{Cvoid}}), ws.handle, opt, C_NULL, s))
     first = Ref{Int64}(0); nloc = Ref{Int64}(0)
     check(ccall((:dyb_smc_local_range, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), s[], first, nloc))
     para = Matrix{Float64}(undef, ws.np, nloc[]); st = ones(Int32, nloc[]); θ = Vector{Float64}(undef, ws.np)
-    while any(!=(0), st)                                   # smc.jl:84-101: redraw until the likelihood is finite
-        for j in findall(!=(0), st); pdraw!(θ); para[:, j] .= θ; end
-        check(ccall((:dyb_smc_init, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}), s[], para, st))
+    if pdraw! === nothing                                  # prior draws + rejection loop on the device (needs set_priors!)
+        check(ccall((:dyb_smc_init_from_prior, LIB), Cint, (Ptr{Cvoid}, UInt64, Int32, Ptr{Int64}), s[], seed, 1000, C_NULL))
+    else
+        while any(!=(0), st)                               # smc.jl:84-101: redraw until the likelihood is finite
+            for j in findall(!=(0), st); pdraw!(θ); para[:, j] .= θ; end
+            check(ccall((:dyb_smc_init, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}), s[], para, st))
+        end
     end
     check(ccall((:dyb_smc_run, LIB), Cint, (Ptr{Cvoid}, Int32), s[], nphi))      # all stages, asynchronous
     stats = Matrix{Float64}(undef, 6, nphi); mu = Vector{Float64}(undef, ws.np); R = Matrix{Float64}(undef, ws.np, ws.np)

@@ -194,3 +194,32 @@ def rwmh_chain(y0, Lchol, n_iter, z, u, logtarget):
                 y, lp = yp, lpx; acc += 1
         hist[t] = y; hlp[t] = lp
     return hist, hlp, acc
+
+
+def prior_draws(codes, a, b, seed, first, n, rnd=0):
+    """prior_draw! (src/estimation/estimation.jl:329-335: pdraw[i] = rand(prior_i)) with the engine's counter-based stream
+    (sampler_kernels.cuh prior_draw): (n, np) draws of particles first .. first + n - 1 in round `rnd`.  codes: the
+    reference's shape codes (1 Beta, 2 Gamma, 3 Normal, 4 InverseGamma1, 5 Uniform, 6 InverseGamma, 8 Weibull)."""
+    from . import rng as R
+    idx = np.arange(first, first + n, dtype=np.uint64)
+    out = np.empty((n, len(codes)))
+    for k, (code, ak, bk) in enumerate(zip(codes, a, b)):
+        kbase = k << 12
+        if code == 1:
+            x = R.gamma_mt(seed, idx, rnd, k, 0, ak); y = R.gamma_mt(seed, idx, rnd, k, 1, bk)
+            out[:, k] = x / (x + y)
+        elif code == 2:
+            out[:, k] = bk * R.gamma_mt(seed, idx, rnd, k, 0, ak)
+        elif code == 3:
+            out[:, k] = ak + bk * R.normal_first(seed, idx, rnd, R.STREAM_PRIOR, kbase)
+        elif code == 4:
+            out[:, k] = np.sqrt(bk / R.gamma_mt(seed, idx, rnd, k, 0, ak))
+        elif code == 5:
+            out[:, k] = ak + (bk - ak) * R.uniform(seed, idx, rnd, R.STREAM_PRIOR, kbase)
+        elif code == 6:
+            out[:, k] = bk / R.gamma_mt(seed, idx, rnd, k, 0, ak)
+        elif code == 8:
+            out[:, k] = bk * (-np.log(1.0 - R.uniform(seed, idx, rnd, R.STREAM_PRIOR, kbase))) ** (1.0 / ak)
+        else:
+            raise ValueError(code)
+    return out

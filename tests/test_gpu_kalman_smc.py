@@ -96,6 +96,35 @@ def test_resampling_indices_bit_exact(n):
     assert np.array_equal(idx, ref) and ncl == rcl
 
 
+def test_covariance_factor_projects_on_the_psd_cone():
+    """smc.jl:161-165: prox!(RPSD, IndPSD(), R) + cholesky, against the oracle's eigen-decomposition (oracle/sampler.py)."""
+    from dynare_jl_b200.engine import smc_covariance_factor
+    from oracle.sampler import project_psd
+    rng = np.random.default_rng(4)
+    for np_ in (1, 5, 13, 36):
+        A = rng.normal(size=(np_, np_ + 3))
+        R = A @ A.T / (np_ + 3)
+        Rp, Lc, flag = smc_covariance_factor(R)                      # positive definite: untouched, plain Cholesky
+        assert flag == 0 and np.array_equal(Rp, R)
+        assert np.allclose(Lc, np.linalg.cholesky(R), rtol=1e-12, atol=1e-14)
+        if np_ == 1:
+            continue
+        # indefinite: two eigenvalues pushed below zero -> set to zero; the projection is singular, so its Cholesky factorisation
+        # fails as the reference's would (flag 2), but RPSD itself must be the oracle's
+        lam, V = np.linalg.eigh(R)
+        lam2 = lam.copy(); lam2[0] = -0.3 * lam[-1]; lam2[1] = -1e-3 * lam[-1]
+        Rind = (V * lam2) @ V.T
+        Rind = 0.5 * (Rind + Rind.T)
+        Rp, Lc, flag = smc_covariance_factor(Rind)
+        ref = project_psd(Rind)
+        assert flag in (1, 2)           # 1 if rounding left every pivot of the singular projection positive
+        assert np.allclose(Rp, ref, rtol=0, atol=1e-12 * lam[-1])
+        assert np.linalg.eigvalsh(Rp).min() >= -1e-12 * lam[-1]
+        # projecting the projection changes nothing
+        Rp2, _, _ = smc_covariance_factor(Rp)
+        assert np.allclose(Rp2, Rp, rtol=0, atol=1e-12 * lam[-1])
+
+
 def test_reweight_ess_and_moments():
     from dynare_jl_b200.engine import smc_reweight, smc_moments
     rng = np.random.default_rng(9)

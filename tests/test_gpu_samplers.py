@@ -62,6 +62,65 @@ def test_logprior_and_transform_all_shapes(golden):
     ws.close()
 
 
+def test_prior_draws_on_device_match_oracle(golden):
+    """prior_draw! on the device (dyb_prior_draw) against its numpy restatement, all seven shapes incl. Gamma / Beta shapes
+    below one; the distributions themselves are checked against scipy.stats in tests/test_sampler_oracle.py."""
+    from dynare_jl_b200.engine import BatchSSWs
+    from dynare_jl_b200.priors import PriorSet, Prior, make_prior
+    ps = PriorSet([make_prior(*p) for p in ALL])
+    ps.priors[0] = Prior("beta", 0.6, 0.8)                # both Gammas of the ratio take the boost path
+    ps.priors[1] = Prior("gamma", 0.4, 2.0)
+    g = golden("fs2000")
+    ws = BatchSSWs("fs2000", g["Y"])
+    ws.set_estimated_params(np.zeros(8, dtype=np.int32), np.arange(8) % 7, np.zeros(8))
+    ws.set_priors(ps)
+    code, a, b = ps.abi_arrays()
+    for first, n, rnd, seed in [(0, 5000, 0, 7), (123456789012, 257, 3, 99)]:
+        x = ws.prior_draw(n, seed=seed, first=first, round=rnd)
+        ref = osam.prior_draws(code.tolist(), a.tolist(), b.tolist(), seed, first, n, rnd)
+        assert x.shape == ref.shape and np.all(np.isfinite(x))
+        assert np.allclose(x, ref, rtol=1e-11, atol=0), np.abs(x / ref - 1).max()
+        assert np.all(np.isfinite(ws.logprior(x)))         # every draw lies inside its support
+    # a shard of the cloud is the same draws
+    assert np.array_equal(ws.prior_draw(100, seed=7, first=1000), ws.prior_draw(5000, seed=7)[1000:1100])
+    ws.close()
+
+
+def test_smc_initialised_on_the_device(golden):
+    """smc.jl:84-101 on the device: every initial particle has a finite likelihood, is an oracle prior draw of SOME round, and
+    the run is reproducible."""
+    from dynare_jl_b200.engine import BatchSSWs
+    from dynare_jl_b200.samplers import SMC
+    g = golden("ls2003")
+    ps = _model_priors("ls2003")
+    ws = BatchSSWs("ls2003", g["Y"])
+    code, a, b = ps.abi_arrays()
+    outs = []
+    for _ in range(2):
+        s = SMC(ws, ps, npart=2048, nphi=6, seed=11)
+        s.initialise()
+        draws = s.prior_draws
+        p0 = s.particles()
+        s.run()
+        outs.append((p0, s.particles(), s.stats()["logmdd"]))
+        s.close()
+    p0 = outs[0][0]
+    assert draws >= 2048 and np.all(np.isfinite(p0["loglh"])) and np.all(np.isfinite(p0["logpost"]))
+    ll, st = ws.loglikelihood(p0["para"])
+    assert np.all(st == 0) and np.allclose(ll, p0["loglh"], rtol=1e-12, atol=0)
+    rounds = [osam.prior_draws(code.tolist(), a.tolist(), b.tolist(), 11, 0, 2048, r) for r in range(8)]
+    hit = np.zeros(2048, dtype=bool)
+    for r in rounds:
+        hit |= np.all(np.isclose(p0["para"], r, rtol=1e-11, atol=0), axis=1)
+    assert hit.all()
+    # round 0 is kept wherever its likelihood is finite
+    ll0, st0 = ws.loglikelihood(rounds[0])
+    keep = st0 == 0
+    assert np.allclose(p0["para"][keep], rounds[0][keep], rtol=1e-11, atol=0)
+    assert np.array_equal(outs[0][1]["para"], outs[1][1]["para"]) and outs[0][2] == outs[1][2]
+    ws.close()
+
+
 @pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_logposterior_matches_oracle(name, golden):
     from dynare_jl_b200.engine import BatchSSWs, DSGELogPosteriorDensity

@@ -103,8 +103,11 @@ def smc_compute(context: EstimationContext, datafile: str = "", data=None, first
     comm = Communicator.from_torch_distributed(ws, group=communicator_group) if communicator_group is not None else None
     seed = int(tune.pop("seed", 0))
     s = SMC(ws, context.priors, seed=seed, **tune)
-    rng = rng or np.random.default_rng(seed)
-    if comm is not None:                                     # every rank draws the same stream and keeps its slice
+    if rng is None:
+        # prior draws and the rejection loop of smc.jl:87-101 on the device; the stream is keyed by the global particle
+        # index, so the initial cloud is the same however the particles are sharded
+        s.initialise()
+    elif comm is not None:                                   # every rank draws the same host stream and keeps its slice
         para = context.priors.sample(rng, s.npart)[s.first:s.first + s.n_local]
         s.initialise(np.random.default_rng(seed + 1 + comm.rank), para=para)
     else:

@@ -57,6 +57,24 @@ def solve_flops_per_eval(d, cr_it, lyap_it):
     return sum(solve_flops_split(d, cr_it, lyap_it))
 
 
+def ncu_executed(kernel):
+    """Executed-instruction view of `kernel` from the committed ncu capture: fp64-pipe and issue-slot utilisation.  The
+    algorithmic TFLOP/s of a kernel uses the dense formulas of SURVEY.md section 8(d); a kernel that skips structural zeros
+    (kalman_kernel) is over-credited by them, so the pipe utilisation ncu measured is reported next to it."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            for name, v in d.get("kernels", {}).items():
+                if name.startswith(kernel.split("<")[0]) and "fp64_pipe_active_pct" in v:
+                    return {"fp64_pipe_active_pct": v["fp64_pipe_active_pct"], "issue_active_pct": v.get("issue_active_pct"),
+                            "registers": v.get("registers"), "source": os.path.relpath(path, ROOT)}
+        except Exception:
+            continue
+    return None
+
+
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/*_ncu_summary.json)."""
     import glob
@@ -398,6 +416,8 @@ def run_ours(args):
             kern(f"assemble_kernel<{MODEL}>", asm_ms, fl_asm, mid * 8 + d["ss_doubles"] * 8 + 4),
             kern(f"kalman_kernel<{MODEL}>", filter_ms, fl_kal, d["ss_doubles"] * 8 + 4 + 12),
         ]
+        for kx in kernels:
+            kx["executed"] = ncu_executed(kx["name"])
         if cr_ms == 0.0:      # one-kernel solver path
             kernels = [kern(f"solve_kernel<{MODEL}>", solve_ms, fl_sol, npar * 8 + d["ss_doubles"] * 8 + 4), kernels[3]]
         dom = max(kernels, key=lambda kx: kx["ms_per_launch"])
@@ -411,6 +431,7 @@ def run_ours(args):
             "hbm": {"achieved": dom["hbm_bytes_per_launch"] / (dom["ms_per_launch"] * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
                     "frac": dom["hbm_bytes_per_launch"] / (dom["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak},
+            "executed": ncu_executed(dom["name"]),
             "kernels": kernels,
             "kernel_share_of_step": {kx["name"]: kx["ms_per_launch"] / serial_ms for kx in kernels},
             "kernel_timing": f"CUDA events around each kernel in a separate pass of {ksteps} steps on ONE stream right after the "

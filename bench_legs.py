@@ -153,6 +153,7 @@ def smc_leg(local, rank, world, gloo, npart, nphi, seed=3, check=True, profile=T
             out["ms_per_stage"] = 1e3 * dt / (nphi - 1)
             out["logmdd"] = st["logmdd"]
             out["resamples"] = int(st["resampled"].sum())
+            out["transport"] = s.transport()
             part = s.particles()
             stats_main = st["stats"].copy()
         else:

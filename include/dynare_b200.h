@@ -118,7 +118,10 @@ int dyb_set_calibration(dyb_handle* h, const double* params /* npar */,
 int dyb_set_estimated_params(dyb_handle* h, int32_t np, const int32_t* kind,
                              const int32_t* index1, const int32_t* index2);
 /* observations: ny x nobs column-major, NaN = missing (the Matrix{Union{Missing,Float64}} of
- * src/estimation/estimation.jl:603-608 after get_transposed_data!, src/data.jl:107-140) */
+ * src/estimation/estimation.jl:603-608 after get_transposed_data!, src/data.jl:107-140).  Only the steady state of the
+ * observed variables is removed on the device (estimation.jl:660-663); the reference's other detrending variants -- linear
+ * trends, `prefilter`, log / first-difference transformations of the data file (src/data.jl:169-208, 332-353) -- are data
+ * preparation done ONCE per estimation and stay with the caller: pass the prepared Y. */
 int dyb_set_observations(dyb_handle* h, const double* Y, int32_t ny, int32_t nobs);
 
 /* ---- the hot path: loglikelihood(theta, context, observations, ssws) for N draws ---------------
@@ -196,7 +199,11 @@ int dyb_kalman_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, in
  * max diag(Pinf) > tol (the reference passes 1e-8, kalman.jl:211).  loglik is the diffuse log-likelihood
  * (Durbin & Koopman 2012, eq. 7.3), n_diffuse the number of diffuse periods; other arguments and outputs as in
  * dyb_kalman_smoother_batch; ybar_obs ny per draw (NULL = 0) is subtracted from the observations; with Pinf0 = 0 the
- * results are those of dyb_kalman_smoother_batch. */
+ * results are those of dyb_kalman_smoother_batch.
+ * NOT batched on the device: the ordered real Schur decomposition that yields Z1, Z2 (LAPACK gees per draw, as the
+ * reference calls it) runs on the HOST, one draw after another (the Python mirror's diffuse_initial_covariances, the
+ * Julia shim's schur!), and the stable block's Lyapunov equation goes through dyb_lyapunov_batch; this smoother path
+ * is a post-estimation call on a handful of draws, not part of the per-draw likelihood. */
 int dyb_kalman_diffuse_smoother_batch(int device, int32_t ns, int32_t ny, int32_t nx, int32_t nobs, const int32_t* z_idx,
                                       const double* Y, const double* T, const double* R, const double* Q,
                                       const double* Pinf0, const double* Pstar0, const double* a0, const double* Hdiag,

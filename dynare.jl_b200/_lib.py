@@ -83,6 +83,7 @@ SIGNATURES = {
     "dyb_kernel_timers_reset": (C.c_int, [_P]),
     "dyb_kernel_timers_read": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "dyb_kernel_timers_read_solve_split": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "dyb_solver_redo_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "dyb_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "dyb_fp64_peak_dmma": (C.c_int, [C.c_int, C.c_int32, C.POINTER(C.c_double)]),
     "dyb_state_space_batch": (C.c_int, [_P, _D, C.c_int64, _D, _D, _D, _D, _D, _I32]),

@@ -146,6 +146,7 @@ int dyb_destroy(dyb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   comm_release(h);
   generic_release(h);
+  h->hs.crp.release();
   h->d_uT.release(); h->d_uQ.release(); h->d_uP.release(); h->d_uyb.release(); h->d_uH.release(); h->d_uz.release(); h->d_uscr.release();
   h->d_theta.release(); h->d_ss.release(); h->d_st1.release(); h->d_ll.release(); h->d_st2.release(); h->d_Y.release(); h->d_mid.release();
   h->h_in.release(); h->h_out.release();
@@ -406,7 +407,7 @@ int dyb_kernel_timers_read_solve_split(dyb_handle* h, float* model_ms_total, flo
   DYB_CUDA(cudaSetDevice(h->device));
   DYB_CUDA(cudaStreamSynchronize(h->stream));
   float m = 0, c = 0, s = 0;
-  if (h->ops && h->ops->solve_launches(h->hs) == 3) {
+  if (h->ops && h->ops->solve_launches(h->hs) >= 3) {
     for (int i = 0; i < h->timer_n; ++i) {
       float x = 0, y = 0, z = 0;
       DYB_CUDA(cudaEventElapsedTime(&x, h->timer_ev[5 * i], h->timer_ev[5 * i + 3]));
@@ -418,6 +419,16 @@ int dyb_kernel_timers_read_solve_split(dyb_handle* h, float* model_ms_total, flo
   if (model_ms_total) *model_ms_total = m;
   if (cr_ms_total) *cr_ms_total = c;
   if (assemble_ms_total) *assemble_ms_total = s;
+  return DYB_OK;
+}
+
+int dyb_solver_redo_count(dyb_handle* h, int64_t* n_redone) {
+  if (!h || !n_redone) return fail(DYB_ERR_ARG, "null argument");
+  DYB_CUDA(cudaSetDevice(h->device));
+  DYB_CUDA(cudaStreamSynchronize(h->stream));
+  unsigned long long v = 0;
+  if (h->hs.crp.d_redo) DYB_CUDA(cudaMemcpy(&v, h->hs.crp.d_redo, sizeof(v), cudaMemcpyDeviceToHost));
+  *n_redone = (int64_t)v;
   return DYB_OK;
 }
 

@@ -23,7 +23,8 @@ enum EstKind : int {
 // per-draw status (include/dynare_b200.h DYB_ST_*)
 enum DrawStatus : int {
   ST_OK = 0, ST_STEADY = 1, ST_INDETERMINATE = 2, ST_UNSTABLE = 3, ST_SOLVER = 4,
-  ST_NONSTATIONARY = 5, ST_F_NOT_PD = 6
+  ST_NONSTATIONARY = 5, ST_F_NOT_PD = 6,
+  ST_REDO = 64          // internal to the solver: the fast pass could not verify this draw, the Householder pass takes it
 };
 
 constexpr int MAX_EST = 64;

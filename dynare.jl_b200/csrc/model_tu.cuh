@@ -3,6 +3,8 @@
 //   #define DYB_MODEL dyb::Model_<name>
 //   #include "model_tu.cuh"
 // Instantiates the solve / filter kernels for the model and registers its launchers.
+#include <cstdio>
+#include <cstdlib>
 #include "registry.h"
 #include "solve_kernel.cuh"
 #include "solve_coop.cuh"
@@ -33,7 +35,19 @@ constexpr bool mt_coop_fits = CrCfg<MT>::FITS;
 // and could not launch); the generated model function feeds the run-time-size solver and the dense tensor-core filter
 // instead (ModelOps::jacobian_batch, generic.cu).
 constexpr bool mt_big = (MT::M > 12) || (MT::NS > 16);
-int mt_solve_launches(const HostState& hs) { return mt_big ? 2 : ((mt_coop_fits && hs.opt.solver != 1) ? 3 : 1); }
+constexpr bool mt_fast_fits = CrCfg<MT>::FITS_LU;
+int mt_solve_launches(const HostState& hs) {
+  return mt_big ? 2 : ((mt_coop_fits && hs.opt.solver != 1) ? ((mt_fast_fits && hs.opt.solver == 0) ? 4 : 3) : 1);
+}
+
+// FNV-1a over what the calibration draw of the pivot order depends on
+unsigned long long mt_perm_key(const HostState& hs) {
+  unsigned long long k = 1469598103934665603ULL;
+  auto mix = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { k ^= b[i]; k *= 1099511628211ULL; } };
+  mix(hs.params.data(), 8 * hs.params.size()); mix(hs.sigma_e.data(), 8 * hs.sigma_e.size()); mix(hs.sigma_m.data(), 8 * hs.sigma_m.size());
+  mix(&hs.opt.steady_tol, 8);
+  return k | 1ULL;
+}
 
 cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, SolveOut out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
@@ -55,7 +69,48 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
     if (out.ev_after_model) cudaEventRecord(out.ev_after_model, st);
     const long long gridc = (n * G + CrCfg<MT>::BLOCK - 1) / CrCfg<MT>::BLOCK;
     CrOptions co{hs.opt.cr_tol, hs.opt.cr_maxit};
-    cr_kernel<MT, G><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters);
+    bool fast = false;
+    if constexpr (mt_fast_fits) {
+      // fast pass (no pivoting, verified) + Householder pass on what it could not verify; needs the pivot order of the
+      // calibration point, derived once per configuration (not inside a stream capture: it allocates)
+      CrPermCache& c = hs.crp;
+      fast = hs.opt.solver == 0;
+      const unsigned long long key = mt_perm_key(hs);
+      if (fast && !(c.valid && c.key == key)) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        if (cap != cudaStreamCaptureStatusNone && !c.d_perm) fast = false;
+        else {
+          if (!c.d_perm) {
+            if (cudaMalloc(&c.d_perm, sizeof(int) * MT::M) != cudaSuccess || cudaMalloc(&c.d_mid1, sizeof(double) * MidLayout<MT>::SIZE) != cudaSuccess ||
+                cudaMalloc(&c.d_st1, sizeof(int)) != cudaSuccess || cudaMalloc(&c.d_redo, sizeof(unsigned long long)) != cudaSuccess) {
+              c.release(); cudaGetLastError(); fast = false;
+            } else cudaMemsetAsync(c.d_redo, 0, sizeof(unsigned long long), st);
+          }
+          if (fast) {
+            SolveParams<MT> prm0 = prm;
+            prm0.np = 0;                              // the calibration itself: no estimated parameter overrides it
+            model_kernel<MT><<<1, 32, 0, st>>>(prm0, nullptr, 1, c.d_mid1, c.d_st1, nullptr);
+            cr_perm_kernel<MT><<<1, 32, 0, st>>>(c.d_mid1, c.d_st1, c.d_perm);
+            if (cap == cudaStreamCaptureStatusNone) { c.key = key; c.valid = true; }    // a captured launch has not run yet
+            if (cap == cudaStreamCaptureStatusNone && getenv("DYB_DEBUG_PERM")) {
+              int hp[MT::M], hst = -1;
+              cudaStreamSynchronize(st);
+              cudaMemcpy(hp, c.d_perm, sizeof(hp), cudaMemcpyDeviceToHost); cudaMemcpy(&hst, c.d_st1, sizeof(int), cudaMemcpyDeviceToHost);
+              fprintf(stderr, "[dyb] %s: calibration status %d, equation order", MT::name, hst);
+              for (int r = 0; r < MT::M; ++r) fprintf(stderr, " %d", hp[r]);
+              fprintf(stderr, "\n");
+            }
+          }
+        }
+      }
+      if (fast) {
+        cr_kernel<MT, G, CR_LU, false><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, c.d_perm, nullptr);
+        cr_kernel<MT, G, CR_QR, true><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, nullptr, c.d_redo);
+      }
+    }
+    if (!fast)
+      cr_kernel<MT, G, (DYB_CR_SOLVER == 1 ? CR_GJ : CR_QR), false><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, nullptr, nullptr);
     if (out.ev_after_cr) cudaEventRecord(out.ev_after_cr, st);
     assemble_kernel<MT><<<(unsigned)grid, block, 0, st>>>(out.mid, n, hs.opt.lyap_tol, hs.opt.lyap_maxit, out.ss,
                                                           out.status, out.g1, out.lyap_iters);

@@ -9,11 +9,31 @@
 namespace dyb {
 
 // everything the solve kernel needs from the host besides theta
+// device-side cache of the cooperative solver's fast pass (solve_coop.cuh): the pivot order of the equations found at the
+// calibration point, re-derived when params / sigma_e / sigma_m change (key), and the count of draws the fast pass handed
+// to the Householder pass.  Owned by the handle (released in dyb_destroy); never copied.
+struct CrPermCache {
+  int* d_perm = nullptr;                // MM ints
+  double* d_mid1 = nullptr;             // mid buffer of the one calibration draw
+  int* d_st1 = nullptr;
+  unsigned long long* d_redo = nullptr; // draws redone by the Householder pass since creation
+  unsigned long long key = 0;
+  bool valid = false;
+  void release() {
+    if (d_perm) cudaFree(d_perm); if (d_mid1) cudaFree(d_mid1); if (d_st1) cudaFree(d_st1); if (d_redo) cudaFree(d_redo);
+    d_perm = nullptr; d_mid1 = nullptr; d_st1 = nullptr; d_redo = nullptr; valid = false;
+  }
+};
+
 struct HostState {
   std::vector<double> params, sigma_e, sigma_m;
   int np = 0;
   int est_type[MAX_EST], est_i[MAX_EST], est_j[MAX_EST];
   dyb_options opt;
+  mutable CrPermCache crp;
+  HostState() = default;
+  HostState(const HostState&) = delete;
+  HostState& operator=(const HostState&) = delete;
 };
 
 struct SolveOut {

@@ -264,6 +264,54 @@ DYB_D bool gj_solve(double (&A)[(MM + G - 1) / G][MM], double (&B)[NR][MM], int 
   return ok;
 }
 
+// Gaussian elimination WITHOUT pivoting on the same layout: half the multiply-adds of the Householder variant, the same
+// shuffles, every index static (1 368 instructions per cyclic-reduction iteration at MM = 9 against 1 894).  The rows have
+// been put in the pivot order of the calibration point by the caller; nothing here bounds the element growth, so the
+// caller verifies the residual of what it finally returns (cr_kernel, CR_VERIFY_TOL).
+template <int MM, int G, int NR>
+DYB_D bool lu_solve_static(double (&A)[(MM + G - 1) / G][MM], double (&B)[NR][MM], int lg, unsigned mask) {
+  constexpr int SL = (MM + G - 1) / G;
+  double ipv[MM];
+  bool ok = true;
+#pragma unroll
+  for (int p = 0; p < MM; ++p) {
+    double x[MM];
+#pragma unroll
+    for (int r = p; r < MM; ++r) x[r] = gshfl<G>(mask, A[p / G][r], p % G);
+    const double ap = fabs(x[p]);
+    ok = ok && (ap > 0.0) && (ap < 1e150);
+    const double ip = fast_rcp(x[p]);
+    ipv[p] = ip;
+    double l[MM];
+#pragma unroll
+    for (int r = p + 1; r < MM; ++r) l[r] = x[r] * ip;
+#pragma unroll
+    for (int sl = p / G; sl < SL; ++sl) {
+#pragma unroll
+      for (int r = p + 1; r < MM; ++r) A[sl][r] = fma(-l[r], A[sl][p], A[sl][r]);
+    }
+#pragma unroll
+    for (int sl = 0; sl < NR; ++sl) {
+#pragma unroll
+      for (int r = p + 1; r < MM; ++r) B[sl][r] = fma(-l[r], B[sl][p], B[sl][r]);
+    }
+  }
+#pragma unroll
+  for (int p = MM - 1; p >= 0; --p) {
+    double rc[MM];
+#pragma unroll
+    for (int r = 0; r < p; ++r) rc[r] = gshfl<G>(mask, A[p / G][r], p % G);
+#pragma unroll
+    for (int sl = 0; sl < NR; ++sl) {
+      const double yp = B[sl][p] * ipv[p];
+      B[sl][p] = yp;
+#pragma unroll
+      for (int r = 0; r < p; ++r) B[sl][r] = fma(-rc[r], yp, B[sl][r]);
+    }
+  }
+  return ok;
+}
+
 // m x m solver of cr_kernel: 0 = Householder QR (default), 1 = Gauss-Jordan with column pivoting.  Measured on B200
 // (profiles/r02_d_cr_solver_ab.txt, 65 536 draws): fs2000 0.410 ms (QR) against 0.485 ms (GJ), ls2003 0.324 / 0.360,
 // hs_nk 0.159 / 0.155 -- the pivoted variant executes 0.71 x the fp64 instructions (881 against 1 243 per iteration at
@@ -279,7 +327,7 @@ struct CrOptions { double cr_tol; int cr_maxit; };
 #define DYB_CR_LANES 4
 #endif
 #ifndef DYB_CR_MIN_CTAS
-#define DYB_CR_MIN_CTAS (DYB_CR_SOLVER ? 5 : 6)
+#define DYB_CR_MIN_CTAS (DYB_CR_SOLVER == 1 ? 5 : 6)
 #endif
 
 // Geometry of cr_kernel: G lanes per draw, CTAs of BLOCK threads, one shared-memory tile per draw holding
@@ -293,13 +341,14 @@ struct CrCfg {
   static constexpr int MM = M::M, K = M::K, NF = M::NF;
   static constexpr int OFF_A1 = 0, OFF_ACC = MM * MM, OFF_A0 = OFF_ACC + MM * K, OFF_A2 = OFF_A0 + MM * K;
   static constexpr int OFF_X = OFF_A2 + MM * NF;
-  static constexpr int TILE_RAW = OFF_X + (DYB_CR_SOLVER ? MM * (K + NF) : 0);
+  static constexpr int TILE_RAW = OFF_X + (DYB_CR_SOLVER == 1 ? MM * (K + NF) : 0);
   static constexpr int PAD_TO = (G == 4) ? 4 : 8;       // tile stride mod 16 that spreads a half-warp over 16 banks
   static constexpr int TILE = TILE_RAW + ((PAD_TO - TILE_RAW % 16) + 16) % 16;
   static constexpr int MIN_CTAS = DYB_CR_MIN_CTAS;
   static constexpr int MAX_REGS = (65536 / (BLOCK * MIN_CTAS)) / 8 * 8;
   static constexpr bool FITS = (MM <= 12) && (K >= 1) && (NF >= 1) && (NF + K >= M::NX) &&
                                (sizeof(double) * GROUPS * TILE <= 48 * 1024);
+  static constexpr bool FITS_LU = FITS && (M::NX <= 2 * K);          // F_u staged over the acc_hat | A0 regions of the tile
 };
 
 // B (own columns, rows in pivot order pc) -> natural row order through the draw's X buffer.  Slot s of the lane is
@@ -326,12 +375,22 @@ DYB_D void unpermute_rows(double (&B)[NR][MM], const int (&pc)[MM], double* Xs, 
 // draw that has stopped is frozen by predicating its commits (short divergent sections without shuffles), so its
 // result does not depend on its neighbours.  Between iterations the whole state of a draw lives in its shared tile;
 // registers only hold the transient copies of one iteration (A1 and [X0 | X2] by column, then the GEMM accumulators).
-template <class M, int G>
+// SOLVER: the m x m solver (CR_QR Householder, CR_GJ Gauss-Jordan with column pivoting, CR_LU Gaussian elimination without
+// pivoting on rows pre-ordered by `row_perm`).  The CR_LU pass is the fast one: it does not pivot, so it VERIFIES what it
+// returns -- the residuals of A0 + (A1 + A2 G[fw,:] E_bk') G = 0 and of (A1 + A2 G[fw,:] E_bk') g_u = -F_u against their own
+// scale -- and hands every draw it cannot vouch for (residual above CR_VERIFY_TOL, zero pivot, no convergence) to a second
+// launch with REDO = true and SOLVER = CR_QR, which only touches draws marked ST_REDO (warps without one return at once).
+constexpr int CR_QR = 0, CR_GJ = 1, CR_LU = 2;
+constexpr double CR_VERIFY_TOL = 1e-12;
+
+template <class M, int G, int SOLVER, bool REDO>
 __global__ void __launch_bounds__(CrCfg<M>::BLOCK) __maxnreg__(CrCfg<M>::MAX_REGS)
 cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
-          int* __restrict__ status, int* __restrict__ cr_iters) {
+          int* __restrict__ status, int* __restrict__ cr_iters, const int* __restrict__ row_perm,
+          unsigned long long* __restrict__ redo_count) {
   using C = CrCfg<M>;
   static_assert(G == C::G, "lane count");
+  static_assert(SOLVER != CR_GJ || DYB_CR_SOLVER == 1, "the Gauss-Jordan variant needs the X buffer of a -DDYB_CR_SOLVER=1 build");
   constexpr int MM = M::M, K = M::K, NF = M::NF, NX = M::NX;
   constexpr int SL1 = (MM + G - 1) / G, SL0 = (K + G - 1) / G, SL2 = (NF + G - 1) / G, SLU = (NX + G - 1) / G;
   constexpr int NR = SL0 + SL2;
@@ -351,7 +410,18 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
   [[maybe_unused]] int pc[MM];
   const double* md = mid + d;
   const long long st = n_draws;
-  const int st_in = status[d];
+  int st_in = status[d];
+  bool skip = false;                                  // REDO pass: a draw the fast pass has already settled
+  if constexpr (REDO) {
+    if (!__any_sync(FULL, real && st_in == ST_REDO)) return;          // the whole warp leaves (no block-level barrier below)
+    skip = st_in != ST_REDO;
+    if (!skip) st_in = ST_OK;
+    if (real && !skip && lg == 0 && redo_count) atomicAdd(redo_count, 1ULL);
+  }
+  // tile row of equation r: the pivot order found once at the calibration (cr_perm_kernel), identity otherwise
+  int prow[MM];
+#pragma unroll
+  for (int r = 0; r < MM; ++r) prow[r] = (SOLVER == CR_LU && row_perm) ? row_perm[r] : r;
 
   // (re)load A1(0), A0(0), A2(0) of the draw into the tile; acc_hat is left alone unless zero_acc
   auto load_tile = [&](bool zero_acc) {
@@ -362,7 +432,7 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
 #pragma unroll
     for (int e = 0; e < M::RED_NNZ; ++e) {
       if (e % G != lg) continue;
-      const int rr = M::red_row(e), c = M::red_col(e);
+      const int rr = prow[M::red_row(e)], c = M::red_col(e);
       if (c < K) A0s[rr + MM * c] = md[(L::OFF_RED + e) * st];
       else if (c < K + MM) A1s[rr + MM * (c - K)] = md[(L::OFF_RED + e) * st];
       else if (c < K + MM + NF) A2s[rr + MM * (c - K - MM)] = md[(L::OFF_RED + e) * st];
@@ -373,7 +443,7 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
 
   int it = 0;
   int result = st_in;                 // draws that already failed are frozen from the start
-  bool active = (st_in == ST_OK), conv = false, stalled = false;
+  bool active = (st_in == ST_OK) && !skip, conv = false, stalled = false;
   double n0 = 0.0, n2 = 0.0;
   for (int iter = 1; iter <= opt.cr_maxit; ++iter) {
     if (!__any_sync(FULL, active)) break;
@@ -398,19 +468,24 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
       for (int r = 0; r < MM; ++r) XB[SL0 + s][r] = (col < NF) ? A2s[r + MM * col] : 0.0;
     }
     // [X0 | X2] = A1^-1 [A0 | A2]
-#if DYB_CR_SOLVER
-    const bool okq = gj_solve<MM, G, NR>(A1w, XB, lg, FULL, pc);
-    {
+    bool okq;
+    if constexpr (SOLVER == CR_LU) {
+      okq = lu_solve_static<MM, G, NR>(A1w, XB, lg, FULL);
+    } else if constexpr (SOLVER == CR_GJ) {
+#if DYB_CR_SOLVER == 1
+      okq = gj_solve<MM, G, NR>(A1w, XB, lg, FULL, pc);
       int xcol[NR];
 #pragma unroll
       for (int s = 0; s < SL0; ++s) xcol[s] = (s * G + lg < K) ? s * G + lg : -1;
 #pragma unroll
       for (int s = 0; s < SL2; ++s) xcol[SL0 + s] = (s * G + lg < NF) ? K + s * G + lg : -1;
       unpermute_rows<MM, NR>(XB, pc, Xs, xcol);
-    }
 #else
-    const bool okq = qr_solve<MM, G, NR>(A1w, XB, lg, FULL);
+      okq = false;
 #endif
+    } else {
+      okq = qr_solve<MM, G, NR>(A1w, XB, lg, FULL);
+    }
     const bool commit = active && okq;
 
     // pass 1: own columns j of [W00 | W01] = A0 * X[bk, j], columns of A0 broadcast from the tile
@@ -556,17 +631,22 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
 #pragma unroll
     for (int r = 0; r < MM; ++r) Gc[s][r] = (col < K) ? -A0s[r + MM * col] : 0.0;
   }
-#if DYB_CR_SOLVER
-  bool okq = gj_solve<MM, G, SL0>(A1h, Gc, lg, FULL, pc);
-  {
+  bool okq;
+  if constexpr (SOLVER == CR_LU) {
+    okq = lu_solve_static<MM, G, SL0>(A1h, Gc, lg, FULL);
+  } else if constexpr (SOLVER == CR_GJ) {
+#if DYB_CR_SOLVER == 1
+    okq = gj_solve<MM, G, SL0>(A1h, Gc, lg, FULL, pc);
     int xcol[SL0];
 #pragma unroll
     for (int s = 0; s < SL0; ++s) xcol[s] = (s * G + lg < K) ? s * G + lg : -1;
     unpermute_rows<MM, SL0>(Gc, pc, Xs, xcol);
-  }
 #else
-  bool okq = qr_solve<MM, G, SL0>(A1h, Gc, lg, FULL);
+    okq = false;
 #endif
+  } else {
+    okq = qr_solve<MM, G, SL0>(A1h, Gc, lg, FULL);
+  }
   // Gc now holds G's own columns
   // ---- g_u = -(A1(0) + A2(0) G[fw, :])^-1 F_u ---------------------------------------------------------------------------
   double w[SL0][MM];
@@ -598,6 +678,39 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
     }
   }
   __syncwarp(FULL);
+  // own columns c of Atilde = A1(0) + A2(0) G[fw,:] E_bk' and, per own right-hand-side column x with constant term f0, the
+  // residual f0 + Atilde x against its scale |f0| + |Atilde| |x| (largest row of each): true when within CR_VERIFY_TOL
+  [[maybe_unused]] auto verify = [&](const double* f0, const double* x) {
+    double res[MM], sc[MM];
+#pragma unroll
+    for (int r = 0; r < MM; ++r) { res[r] = f0[r]; sc[r] = fabs(f0[r]); }
+#pragma unroll
+    for (int c = 0; c < MM; ++c) {
+#pragma unroll
+      for (int r = 0; r < MM; ++r) {
+        const double a = A1s[r + MM * c];
+        res[r] = fma(a, x[c], res[r]);
+        sc[r] = fma(fabs(a), fabs(x[c]), sc[r]);
+      }
+    }
+    // norm-wise: rows that are structurally zero carry rounding residue of their own size
+    double rmax = 0.0, smax = 0.0;
+    bool finite = true;
+#pragma unroll
+    for (int r = 0; r < MM; ++r) {
+      rmax = fmax(rmax, fabs(res[r])); smax = fmax(smax, sc[r]);
+      finite = finite && (sc[r] < 1e300);               // false for NaN / Inf (fmax would drop a NaN)
+    }
+    return finite && rmax <= CR_VERIFY_TOL * smax;
+  };
+  bool verified = true;
+  if constexpr (SOLVER == CR_LU) {
+#pragma unroll
+    for (int s = 0; s < SL0; ++s) {
+      const int col = s * G + lg;
+      if (col < K) verified = verified && verify(A0s + MM * col, Gc[s]);
+    }
+  }
 #pragma unroll
   for (int s = 0; s < SL1; ++s) {
     const int col = s * G + lg;
@@ -609,28 +722,66 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
   for (int s = 0; s < SLU; ++s)
 #pragma unroll
     for (int r = 0; r < MM; ++r) U[s][r] = 0.0;
+  [[maybe_unused]] double* Fs = accs;                  // CR_LU: F_u in tile-row order, over acc_hat | A0 (both dead by now)
+  if constexpr (SOLVER == CR_LU) {
+    static_assert(NX <= 2 * K, "F_u is staged over the acc_hat and A0 regions of the tile");
+    __syncwarp(FULL);                                  // the verification above has read A0
+    for (int e = lg; e < MM * NX; e += G) Fs[e] = 0.0;
+    __syncwarp(FULL);
 #pragma unroll
-  for (int e = 0; e < M::RED_NNZ; ++e) {
-    const int rr = M::red_row(e), c = M::red_col(e);
-    if (c >= K + MM + NF) {
-      const int cu = c - K - MM - NF;
-      if (lg == cu % G) U[cu / G][rr] = -md[(L::OFF_RED + e) * st];
+    for (int e = 0; e < M::RED_NNZ; ++e) {
+      if (e % G != lg) continue;
+      const int rr = prow[M::red_row(e)], c = M::red_col(e);
+      if (c >= K + MM + NF) Fs[rr + MM * (c - K - MM - NF)] = md[(L::OFF_RED + e) * st];
+    }
+    __syncwarp(FULL);
+#pragma unroll
+    for (int s = 0; s < SLU; ++s) {
+      const int col = s * G + lg;
+#pragma unroll
+      for (int r = 0; r < MM; ++r) U[s][r] = (col < NX) ? -Fs[r + MM * col] : 0.0;
+    }
+    okq = lu_solve_static<MM, G, SLU>(A1h, U, lg, FULL) && okq;
+#pragma unroll
+    for (int s = 0; s < SLU; ++s) {
+      const int col = s * G + lg;
+      if (col < NX) verified = verified && verify(Fs + MM * col, U[s]);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) verified = verified && (__shfl_xor_sync(FULL, (int)verified, o, G) != 0);
+  } else {
+#pragma unroll
+    for (int e = 0; e < M::RED_NNZ; ++e) {
+      const int rr = M::red_row(e), c = M::red_col(e);
+      if (c >= K + MM + NF) {
+        const int cu = c - K - MM - NF;
+        if (lg == cu % G) U[cu / G][rr] = -md[(L::OFF_RED + e) * st];
+      }
+    }
+    if constexpr (SOLVER == CR_GJ) {
+#if DYB_CR_SOLVER == 1
+      okq = gj_solve<MM, G, SLU>(A1h, U, lg, FULL, pc) && okq;
+      static_assert(NX <= K + NF, "X buffer holds the shock columns");
+      int xcol[SLU];
+#pragma unroll
+      for (int s = 0; s < SLU; ++s) xcol[s] = (s * G + lg < NX) ? s * G + lg : -1;
+      unpermute_rows<MM, SLU>(U, pc, Xs, xcol);
+#endif
+    } else {
+      okq = qr_solve<MM, G, SLU>(A1h, U, lg, FULL) && okq;
     }
   }
-#if DYB_CR_SOLVER
-  okq = gj_solve<MM, G, SLU>(A1h, U, lg, FULL, pc) && okq;
-  {
-    static_assert(NX <= K + NF, "X buffer holds the shock columns");
-    int xcol[SLU];
-#pragma unroll
-    for (int s = 0; s < SLU; ++s) xcol[s] = (s * G + lg < NX) ? s * G + lg : -1;
-    unpermute_rows<MM, SLU>(U, pc, Xs, xcol);
-  }
-#else
-  okq = qr_solve<MM, G, SLU>(A1h, U, lg, FULL) && okq;
+#ifdef DYB_CR_DEBUG
+  if (SOLVER == CR_LU && real && d < 2 && lg == 0)
+    printf("draw %lld: st_in %d result %d conv %d stalled %d it %d okq %d verified %d n0 %.3e n2 %.3e\n", d, st_in, result, (int)conv,
+           (int)stalled, it, (int)okq, (int)verified, n0, n2);
 #endif
   if (result == ST_OK && !okq) result = ST_SOLVER;
-  if (real && result == ST_OK) {
+  if constexpr (SOLVER == CR_LU) {
+    // the fast pass only vouches for verified successes; every other draw that entered the solver goes to the second pass
+    if (st_in == ST_OK && !(result == ST_OK && verified)) result = ST_REDO;
+  }
+  if (real && !skip && result == ST_OK) {
 #pragma unroll
     for (int s = 0; s < SL0; ++s) {
       const int col = s * G + lg;
@@ -648,10 +799,44 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
       }
     }
   }
-  if (real && lg == 0) {
+  if (real && !skip && lg == 0) {
     status[d] = result;
     if (cr_iters) cr_iters[d] = it;
   }
+}
+
+// Pivot order of the equations of the dynamic block, found ONCE per configuration at the calibration point: partial pivoting
+// on A1(0) of the draw in `mid1` (one draw, written by model_kernel with no estimated parameter), row_perm[r] = position of
+// equation r.  Identity when that draw failed -- the fast pass then hands (nearly) everything to the Householder pass.
+template <class M>
+__global__ void cr_perm_kernel(const double* __restrict__ mid1, const int* __restrict__ status1, int* __restrict__ row_perm) {
+  constexpr int MM = M::M, K = M::K;
+  using L = MidLayout<M>;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double A[MM * MM];
+  int orig[MM];
+  for (int i = 0; i < MM * MM; ++i) A[i] = 0.0;
+  for (int r = 0; r < MM; ++r) { orig[r] = r; row_perm[r] = r; }
+  if (status1[0] != ST_OK) return;
+  for (int e = 0; e < M::RED_NNZ; ++e) {
+    const int rr = M::red_row(e), c = M::red_col(e);
+    if (c >= K && c < K + MM) A[rr + MM * (c - K)] = mid1[L::OFF_RED + e];
+  }
+  for (int p = 0; p < MM; ++p) {
+    int best = p;
+    for (int r = p + 1; r < MM; ++r) if (fabs(A[r + MM * p]) > fabs(A[best + MM * p])) best = r;
+    if (best != p) {
+      for (int c = 0; c < MM; ++c) { const double t = A[p + MM * c]; A[p + MM * c] = A[best + MM * c]; A[best + MM * c] = t; }
+      const int t = orig[p]; orig[p] = orig[best]; orig[best] = t;
+    }
+    const double piv = A[p + MM * p];
+    if (!(fabs(piv) > 0.0)) { for (int r = 0; r < MM; ++r) row_perm[r] = r; return; }
+    for (int r = p + 1; r < MM; ++r) {
+      const double l = A[r + MM * p] / piv;
+      for (int c = p; c < MM; ++c) A[r + MM * c] -= l * A[p + MM * c];
+    }
+  }
+  for (int p = 0; p < MM; ++p) row_perm[orig[p]] = p;
 }
 
 // ------------------------------------------------------------------------------------------------

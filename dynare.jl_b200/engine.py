@@ -205,6 +205,12 @@ class BatchSSWs:
         L.check(self.lib.dyb_kernel_timers_read_solve_split(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def solver_redo_count(self) -> int:
+        """Draws the solver's fast pass could not verify and its Householder pass solved again (since creation)."""
+        v = C.c_int64()
+        L.check(self.lib.dyb_solver_redo_count(self._h, C.byref(v)))
+        return v.value
+
     def kernel_launches(self) -> int:
         return int(self.lib.dyb_kernel_launches(self._h))
 

@@ -78,8 +78,11 @@ typedef struct dyb_options {
   double lyap_tol;          /* relative increment at which doubling stops (default 1e-16) */
   int32_t lyap_maxit;       /* (default 60) */
   int32_t presample;        /* periods excluded from the likelihood sum (default 0) */
-  int32_t solver;           /* 0 auto; 1 one thread per draw (any size; for run-time-size and medium models: the shared-memory
-                               kernel instead of the register-blocked one); 2 cooperative register-resident (m <= 12) */
+  int32_t solver;           /* 0 auto (m <= 12: cooperative register-resident solver whose fast pass -- Gaussian elimination
+                               without pivoting on equations pre-ordered at the calibration, result verified by its residual --
+                               is followed by a Householder pass on the draws it could not verify); 1 one thread per draw (any
+                               size; for run-time-size and medium models: the shared-memory kernel instead of the register-
+                               blocked one); 2 cooperative solver, Householder pass only */
   int32_t filter_lanes;     /* lanes per draw of the model-specific Kalman kernel: 0 auto (8 up to 2 048 draws per call, 4 up to
                              * 4 096, else 1), 1 = one thread per draw (throughput kernel), 4, 8 = shared-tile kernel for batches that
                              * leave schedulers idle (an SMC stage on a shard); same sums in the same order */
@@ -155,6 +158,10 @@ int dyb_kernel_timers_read(dyb_handle* h, int32_t* n_batches, float* solve_ms_to
  * call before dyb_kernel_timers_read; zeros on the one-kernel solver path */
 int dyb_kernel_timers_read_solve_split(dyb_handle* h, float* model_ms_total, float* cr_ms_total,
                                        float* assemble_ms_total);
+/* draws that the cooperative solver's fast pass (dyb_options.solver = 0) could not verify and its Householder pass solved
+ * again, since the handle was created: the fast pass eliminates without pivoting and checks the residuals of
+ * A0 + A1 G + A2 G[fw,:] G[bk,:] = 0 and of the g_u system against 1e-12 of their own scale (csrc/solve_coop.cuh) */
+int dyb_solver_redo_count(dyb_handle* h, int64_t* n_redone);
 /* measured fp64 FMA throughput of the device (TFLOP/s) from a register-resident DFMA loop on all SMs:
  * the roofline denominator for this path, which MEASURED_PEAKS.json does not carry */
 int dyb_fp64_peak(int device, double* tflops);

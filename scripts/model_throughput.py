@@ -28,4 +28,5 @@ m, c, a = ws.timers_read_solve_split()
 k, s, f = ws.timers_read()
 dev = (s + f) / k
 print(f"{name} {n} draws: host-call {dt * 1e3:.3f} ms; kernels ms: model {m / k:.3f} cr {c / k:.3f} assemble {a / k:.3f} "
-      f"filter {f / k:.3f} -> {n / dev / 1e3:.1f} M evals/s device-side; ok {(st == 0).sum()}")
+      f"filter {f / k:.3f} -> {n / dev / 1e3:.1f} M evals/s device-side; ok {(st == 0).sum()}; redone by the Householder pass "
+      f"{ws.solver_redo_count()} of {7 * n} draw evaluations")

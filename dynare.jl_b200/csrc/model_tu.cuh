@@ -83,9 +83,9 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
         else {
           if (!c.d_perm) {
             if (cudaMalloc(&c.d_perm, sizeof(int) * MT::M) != cudaSuccess || cudaMalloc(&c.d_mid1, sizeof(double) * MidLayout<MT>::SIZE) != cudaSuccess ||
-                cudaMalloc(&c.d_st1, sizeof(int)) != cudaSuccess || cudaMalloc(&c.d_redo, sizeof(unsigned long long)) != cudaSuccess) {
+                cudaMalloc(&c.d_st1, sizeof(int)) != cudaSuccess || cudaMalloc(&c.d_redo, 2 * sizeof(unsigned long long)) != cudaSuccess) {
               c.release(); cudaGetLastError(); fast = false;
-            } else cudaMemsetAsync(c.d_redo, 0, sizeof(unsigned long long), st);
+            } else cudaMemsetAsync(c.d_redo, 0, 2 * sizeof(unsigned long long), st);
           }
           if (fast) {
             SolveParams<MT> prm0 = prm;
@@ -104,13 +104,26 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
           }
         }
       }
+      if (fast && c.list_cap < n) {                   // the list of draws for the second pass grows with the widest batch seen
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        if (cap != cudaStreamCaptureStatusNone) fast = false;
+        else {
+          cudaStreamSynchronize(st);                  // a previous call may still be using the old list
+          if (c.d_list) cudaFree(c.d_list);
+          c.d_list = nullptr; c.list_cap = 0;
+          if (cudaMalloc(&c.d_list, sizeof(long long) * (size_t)n) == cudaSuccess) c.list_cap = n;
+          else { cudaGetLastError(); fast = false; }
+        }
+      }
       if (fast) {
-        cr_kernel<MT, G, CR_LU, false><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, c.d_perm, nullptr);
-        cr_kernel<MT, G, CR_QR, true><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, nullptr, c.d_redo);
+        cudaMemsetAsync(c.d_redo + 1, 0, sizeof(unsigned long long), st);
+        cr_kernel<MT, G, CR_LU, false><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, c.d_perm, c.d_redo, c.d_list);
+        cr_kernel<MT, G, CR_QR, true><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, nullptr, c.d_redo, c.d_list);
       }
     }
     if (!fast)
-      cr_kernel<MT, G, (DYB_CR_SOLVER == 1 ? CR_GJ : CR_QR), false><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, nullptr, nullptr);
+      cr_kernel<MT, G, (DYB_CR_SOLVER == 1 ? CR_GJ : CR_QR), false><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, nullptr, nullptr, nullptr);
     if (out.ev_after_cr) cudaEventRecord(out.ev_after_cr, st);
     assemble_kernel<MT><<<(unsigned)grid, block, 0, st>>>(out.mid, n, hs.opt.lyap_tol, hs.opt.lyap_maxit, out.ss,
                                                           out.status, out.g1, out.lyap_iters);

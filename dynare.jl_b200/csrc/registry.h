@@ -16,12 +16,15 @@ struct CrPermCache {
   int* d_perm = nullptr;                // MM ints
   double* d_mid1 = nullptr;             // mid buffer of the one calibration draw
   int* d_st1 = nullptr;
-  unsigned long long* d_redo = nullptr; // draws redone by the Householder pass since creation
+  unsigned long long* d_redo = nullptr; // [0] draws redone by the Householder pass since creation, [1] those of the current call
+  long long* d_list = nullptr;          // the current call's draws for the Householder pass, densely packed (list_cap entries)
+  long long list_cap = 0;
   unsigned long long key = 0;
   bool valid = false;
   void release() {
     if (d_perm) cudaFree(d_perm); if (d_mid1) cudaFree(d_mid1); if (d_st1) cudaFree(d_st1); if (d_redo) cudaFree(d_redo);
-    d_perm = nullptr; d_mid1 = nullptr; d_st1 = nullptr; d_redo = nullptr; valid = false;
+    if (d_list) cudaFree(d_list);
+    d_perm = nullptr; d_mid1 = nullptr; d_st1 = nullptr; d_redo = nullptr; d_list = nullptr; list_cap = 0; valid = false;
   }
 };
 

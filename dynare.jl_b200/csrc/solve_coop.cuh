@@ -387,7 +387,7 @@ template <class M, int G, int SOLVER, bool REDO>
 __global__ void __launch_bounds__(CrCfg<M>::BLOCK) __maxnreg__(CrCfg<M>::MAX_REGS)
 cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
           int* __restrict__ status, int* __restrict__ cr_iters, const int* __restrict__ row_perm,
-          unsigned long long* __restrict__ redo_count) {
+          unsigned long long* __restrict__ redo_count, long long* __restrict__ redo_list) {
   using C = CrCfg<M>;
   static_assert(G == C::G, "lane count");
   static_assert(SOLVER != CR_GJ || DYB_CR_SOLVER == 1, "the Gauss-Jordan variant needs the X buffer of a -DDYB_CR_SOLVER=1 build");
@@ -400,7 +400,15 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
 
   const int lg = threadIdx.x % G;
   long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const bool real = d < n_draws;
+  bool real = d < n_draws;
+  if constexpr (REDO) {
+    // second pass: group g takes entry g of the list the fast pass packed (redo_count[1] entries); warps beyond it leave at
+    // once (the whole warp: there is no block-level barrier below)
+    const long long nred = (long long)redo_count[1];
+    if ((d / (32 / G)) * (32 / G) >= nred) return;
+    real = d < nred;
+    d = redo_list[real ? d : nred - 1];
+  }
   if (!real) d = n_draws - 1;                       // tail groups recompute the last draw and store nothing
   double* A1s = tile + (threadIdx.x / G) * C::TILE + C::OFF_A1;
   double* accs = A1s + (C::OFF_ACC - C::OFF_A1);
@@ -411,12 +419,10 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
   const double* md = mid + d;
   const long long st = n_draws;
   int st_in = status[d];
-  bool skip = false;                                  // REDO pass: a draw the fast pass has already settled
+  constexpr bool skip = false;
   if constexpr (REDO) {
-    if (!__any_sync(FULL, real && st_in == ST_REDO)) return;          // the whole warp leaves (no block-level barrier below)
-    skip = st_in != ST_REDO;
-    if (!skip) st_in = ST_OK;
-    if (real && !skip && lg == 0 && redo_count) atomicAdd(redo_count, 1ULL);
+    st_in = ST_OK;                                    // listed draws entered the fast pass with ST_OK
+    if (real && lg == 0) atomicAdd(redo_count, 1ULL);
   }
   // tile row of equation r: the pivot order found once at the calibration (cr_perm_kernel), identity otherwise
   int prow[MM];
@@ -779,7 +785,10 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
   if (result == ST_OK && !okq) result = ST_SOLVER;
   if constexpr (SOLVER == CR_LU) {
     // the fast pass only vouches for verified successes; every other draw that entered the solver goes to the second pass
-    if (st_in == ST_OK && !(result == ST_OK && verified)) result = ST_REDO;
+    if (st_in == ST_OK && !(result == ST_OK && verified)) {
+      result = ST_REDO;
+      if (real && lg == 0) redo_list[atomicAdd(redo_count + 1, 1ULL)] = d;
+    }
   }
   if (real && !skip && result == ST_OK) {
 #pragma unroll

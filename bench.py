@@ -432,6 +432,11 @@ def run_ours(args):
                     "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
                     "frac": dom["hbm_bytes_per_launch"] / (dom["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak},
             "executed": ncu_executed(dom["name"]),
+            "frac_executed": (ncu_executed(dom["name"]) or {}).get("fp64_pipe_active_pct", 0.0) / 100.0 or None,
+            "frac_note": "achieved / frac credit the DENSE flop formulas of SURVEY.md section 8(d) (the reference's algorithm); "
+                         "kalman_kernel skips the structural zeros of Z (a selection) and T (k lagged-state columns) and executes "
+                         "about 0.47 x those flops, so its algorithmic frac exceeds 1; frac_executed is the fp64-pipe utilisation "
+                         "ncu measured for the same kernel (profiles/*_ncu_summary.json)",
             "kernels": kernels,
             "kernel_share_of_step": {kx["name"]: kx["ms_per_launch"] / serial_ms for kx in kernels},
             "kernel_timing": f"CUDA events around each kernel in a separate pass of {ksteps} steps on ONE stream right after the "

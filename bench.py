@@ -377,10 +377,22 @@ def run_ours(args):
         extra["sustained"] = sus
         if rank == 0:                                             # per-GPU figures (no collective): rank 0 measures
             dpk = fp64_peak_dmma(0, local)
-            extra["config4"] = BL.dense_filter_leg(local, 40, 7, 200, 32768, 64, 2, 2, dpk)
-            extra["config5"] = BL.dense_filter_leg(local, 200, 20, 500, args.config5_draws, 8, 3, 1, dpk)
+
+            def with_clocks(fn, *a):
+                """SM clock, power and throttle reasons sampled while the leg runs: the tensor-core legs draw close to the
+                board's power limit and the clock under them is NOT the 1 965 MHz of the headline -- recorded, not hidden."""
+                smp = ClockSampler(local)
+                smp.start()
+                time.sleep(0.15)
+                t0_ = time.time()
+                out_ = fn(*a)
+                t1_ = time.time()
+                out_["clocks"] = smp.stop(t0_, t1_)
+                return out_
+            extra["config4"] = with_clocks(BL.dense_filter_leg, local, 40, 7, 200, 32768, 64, 2, 2, dpk)
+            extra["config5"] = with_clocks(BL.dense_filter_leg, local, 200, 20, 500, args.config5_draws, 8, 3, 1, dpk)
             extra["config5"]["projected_seconds_262144_draws_8gpu"] = 32768 / extra["config5"]["evals_per_s"]
-            extra["config4_model"] = BL.medium_model_leg(local)
+            extra["config4_model"] = with_clocks(BL.medium_model_leg, local)
         barrier()
         smc_a = BL.smc_leg(local, rank, world, gloo, 16384, 400)
         smc_b = BL.smc_leg(local, rank, world, gloo, 131072, 100)

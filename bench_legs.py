@@ -94,14 +94,17 @@ def medium_model_leg(local, chains=32768, sweeps=10):
     cov = np.diag(np.full(ws.np, 0.01 ** 2))
     rwmh(ws, pri, y0, cov, mcmc_replic=2, mcmc_chains=chains, seed=1)                    # warm-up (buffers, attributes)
     torch.cuda.synchronize(local)
-    t = time.perf_counter()
-    out = rwmh(ws, pri, y0, cov, mcmc_replic=sweeps, mcmc_chains=chains, seed=2)          # synchronous call
-    dt = time.perf_counter() - t
+    runs = []
+    for _ in range(2):               # the board's power state differs between consecutive heavy runs: both are reported
+        t = time.perf_counter()
+        out = rwmh(ws, pri, y0, cov, mcmc_replic=sweeps, mcmc_chains=chains, seed=2)      # synchronous call
+        runs.append(time.perf_counter() - t)
+    dt = min(runs)
     ws.close()
     return {"workload": f"mc4 (44 variables, dynamic block 28, 30 Kalman states, 7 observables, T=200): {chains} RWMH chains x "
                         f"{sweeps} sweeps, model solve + filter per proposal", "seconds": dt, "ms_per_sweep": 1e3 * dt / sweeps,
             "posterior_evals_per_s": chains * sweeps / dt, "projected_seconds_100_sweeps": 100 * dt / sweeps,
-            "acceptance_rate": float(out["accepted"].mean() / sweeps)}
+            "acceptance_rate": float(out["accepted"].mean() / sweeps), "seconds_each_run": runs}
 
 
 def smc_leg(local, rank, world, gloo, npart, nphi, seed=3, check=True, profile=True):

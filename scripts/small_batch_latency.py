@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--sizes", default="2048,4096,8192,16384,65536")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--lanes", type=int, default=0, help="dyb_options.filter_lanes (0 = automatic)")
+    ap.add_argument("--solver", type=int, default=0, help="dyb_options.solver (0 = fast pass + Householder pass, 2 = Householder only)")
     a = ap.parse_args()
     import torch
     from dynare_jl_b200.engine import BatchSSWs, model_description
@@ -25,9 +26,9 @@ def main():
     g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{a.model}_golden.npz")))
     pri = PriorSet.from_description(model_description(a.model)["priors"])
     ws = BatchSSWs(a.model, g["Y"])
-    ws.set_options(filter_lanes=a.lanes)
+    ws.set_options(filter_lanes=a.lanes, solver=a.solver)
     dev = torch.device("cuda", 0)
-    out = {"model": a.model, "filter_lanes": a.lanes, "rows": []}
+    out = {"model": a.model, "filter_lanes": a.lanes, "solver": a.solver, "rows": []}
     for n in [int(x) for x in a.sizes.split(",")]:
         th = torch.from_numpy(np.ascontiguousarray(pri.sample(np.random.default_rng(1), n))).to(dev)
         ll = torch.empty(n, dtype=torch.float64, device=dev); st = torch.empty(n, dtype=torch.int32, device=dev)

@@ -424,7 +424,7 @@ def run_ours(args):
                     "tflops": flop * n / (ms * 1e-3) / 1e12 if ms > 0 else None, "hbm_bytes_per_launch": n * bytes_}
         kernels = [
             kern(f"model_kernel<{MODEL}>", model_ms, fl_static, npar * 8 + mid * 8 + 4),
-            kern(f"cr_kernel<{MODEL},4>", cr_ms, fl_cr, mid * 8 + 4),
+            kern(f"cr_kernel<{MODEL},4,LU>+<{MODEL},4,QR,redo>", cr_ms, fl_cr, mid * 8 + 4),   # fast pass + Householder pass
             kern(f"assemble_kernel<{MODEL}>", asm_ms, fl_asm, mid * 8 + d["ss_doubles"] * 8 + 4),
             kern(f"kalman_kernel<{MODEL}>", filter_ms, fl_kal, d["ss_doubles"] * 8 + 4 + 12),
         ]

@@ -65,7 +65,7 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
   constexpr int G = CrCfg<MT>::G;
   const bool coop = mt_coop_fits && hs.opt.solver != 1;
   if constexpr (mt_coop_fits) { if (coop) {
-    model_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.mid, out.status, out.ybar);
+    model_kernel<MT><<<(unsigned)((n + DYB_MODEL_BLOCK - 1) / DYB_MODEL_BLOCK), DYB_MODEL_BLOCK, 0, st>>>(prm, d_theta, n, out.mid, out.status, out.ybar);
     if (out.ev_after_model) cudaEventRecord(out.ev_after_model, st);
     const long long gridc = (n * G + CrCfg<MT>::BLOCK - 1) / CrCfg<MT>::BLOCK;
     CrOptions co{hs.opt.cr_tol, hs.opt.cr_maxit};
@@ -125,7 +125,7 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
     if (!fast)
       cr_kernel<MT, G, (DYB_CR_SOLVER == 1 ? CR_GJ : CR_QR), false><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, nullptr, nullptr, nullptr);
     if (out.ev_after_cr) cudaEventRecord(out.ev_after_cr, st);
-    assemble_kernel<MT><<<(unsigned)grid, block, 0, st>>>(out.mid, n, hs.opt.lyap_tol, hs.opt.lyap_maxit, out.ss,
+    assemble_kernel<MT><<<(unsigned)((n + DYB_ASM_BLOCK - 1) / DYB_ASM_BLOCK), DYB_ASM_BLOCK, 0, st>>>(out.mid, n, hs.opt.lyap_tol, hs.opt.lyap_maxit, out.ss,
                                                           out.status, out.g1, out.lyap_iters);
     return cudaGetLastError();
   } }

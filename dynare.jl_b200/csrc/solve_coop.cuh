@@ -41,8 +41,22 @@ struct StridedOut {
 };
 
 // ------------------------------------------------------------------------------------------------
+// launch geometry of the two one-thread-per-draw kernels: at 65 536 draws on 148 SMs a kernel needs >= 443 resident threads per
+// SM to finish in ONE wave (a second, nearly empty wave costs a full thread latency); DYB_*_MINB bounds the registers for that
+#ifndef DYB_MODEL_BLOCK
+#define DYB_MODEL_BLOCK 128
+#endif
+#ifndef DYB_MODEL_MINB
+#define DYB_MODEL_MINB 4
+#endif
+#ifndef DYB_ASM_BLOCK
+#define DYB_ASM_BLOCK 128
+#endif
+#ifndef DYB_ASM_MINB
+#define DYB_ASM_MINB 1
+#endif
 template <class M>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DYB_MODEL_BLOCK, DYB_MODEL_MINB)
 model_kernel(const SolveParams<M> prm, const double* __restrict__ theta, long long n_draws,
              double* __restrict__ mid, int* __restrict__ status, double* __restrict__ ybar_out) {
   constexpr int N = M::N, NX = M::NX, NY = M::NY;
@@ -850,7 +864,7 @@ __global__ void cr_perm_kernel(const double* __restrict__ mid1, const int* __res
 
 // ------------------------------------------------------------------------------------------------
 template <class M>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DYB_ASM_BLOCK, DYB_ASM_MINB)
 assemble_kernel(const double* __restrict__ mid, long long n_draws, double lyap_tol, int lyap_maxit,
                 double* __restrict__ ss, int* __restrict__ status, double* __restrict__ g1_out,
                 int* __restrict__ lyap_iters) {

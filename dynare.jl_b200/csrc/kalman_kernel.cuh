@@ -87,7 +87,8 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
 #pragma unroll
   for (int i = 0; i < NS; ++i) a[i] = 0.0;
 
-  double acc = 0.0, detp = 1.0;
+  double acc = 0.0;
+  LogDetAcc detp;
   int nseen = 0;
   bool bad = false;
 
@@ -144,9 +145,8 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
       quad = fma(w[i], w[i], quad);
     }
     if (t >= presample) {
-      // sum_t log det F_t is accumulated as a running product, folded into the sum whenever it leaves a safe range
-      detp *= det;
-      if (!(detp > 1e-200 && detp < 1e200)) { acc += log(detp); detp = 1.0; }
+      // sum_t log det F_t: running product with its exponent split off (LogDetAcc), one logarithm at the end
+      detp.mul(det);
       acc += quad;
       nseen += nobs_t;
     }
@@ -206,7 +206,7 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
       if (Cfg::P_SMEM) asm volatile("" ::: "memory");   // keep the shared-memory loads of row s inside its iteration
     }
   }
-  acc += log(detp);
+  acc += detp.value();
   const double ll = -0.5 * (nseen * 1.8378770664093453 + acc);     // log(2 pi)
   if (bad || !isfinite(ll)) {
     loglik[d] = -INFINITY;

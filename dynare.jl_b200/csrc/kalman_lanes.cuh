@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(KLN_THREADS) kalman_lanes_kernel(KalmanGeneric
     for (int e = lg; e < KLN_NY * NSMAX; e += KLN_G) U[e] = 0.0;
     for (int i = lg; i < NSMAX; i += KLN_G) { a[i] = (g.a0 && i < ns) ? g.a0[(size_t)dd * ns + i] : 0.0; au[i] = 0.0; }
     __syncwarp(FULL);
-    double acc = 0.0, detp = 1.0;
+    double acc = 0.0;
+    LogDetAcc detp;
     int nseen = 0;
     bool bad = false;
 
@@ -130,8 +131,7 @@ __global__ void __launch_bounds__(KLN_THREADS) kalman_lanes_kernel(KalmanGeneric
         quad = fma(w[i], w[i], quad);
       }
       if (t >= g.presample) {
-        detp *= det;
-        if (!(detp > 1e-200 && detp < 1e200)) { acc += log(detp); detp = 1.0; }
+        detp.mul(det);
         acc += quad;
         nseen += nobs_t;
       }
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(KLN_THREADS) kalman_lanes_kernel(KalmanGeneric
       if (skip) {
         g.loglik[d] = -INFINITY; g.status[d] = g.status_in[d];
       } else {
-        acc += log(detp);
+        acc += detp.value();
         const double ll = -0.5 * (nseen * 1.8378770664093453 + acc);
         if (bad || !isfinite(ll)) { g.loglik[d] = -INFINITY; g.status[d] = ST_F_NOT_PD; }
         else { g.loglik[d] = ll; g.status[d] = ST_OK; }

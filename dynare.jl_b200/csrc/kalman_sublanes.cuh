@@ -69,7 +69,8 @@ kalman_sublanes_kernel(const double* __restrict__ ss, long long n_draws, const d
   for (int i = 0; i < NY * (NY + 1) / 2; ++i) H[i] = (st_in == ST_OK) ? s_[(L::OFF_H + i) * st] : 0.0;
   __syncthreads();
 
-  double acc = 0.0, detp = 1.0;
+  double acc = 0.0;
+  LogDetAcc detp;
   int nseen = 0;
   bool bad = false;
   for (int t = 0; t < nobs; ++t) {
@@ -121,8 +122,7 @@ kalman_sublanes_kernel(const double* __restrict__ ss, long long n_draws, const d
       quad = fma(w[i], w[i], quad);
     }
     if (t >= presample) {
-      detp *= det;
-      if (!(detp > 1e-200 && detp < 1e200)) { acc += log(detp); detp = 1.0; }
+      detp.mul(det);
       acc += quad;
       nseen += nobs_t;
     }
@@ -187,7 +187,7 @@ kalman_sublanes_kernel(const double* __restrict__ ss, long long n_draws, const d
     }
     __syncwarp(FULL);
   }
-  acc += log(detp);
+  acc += detp.value();
   const double ll = -0.5 * (nseen * 1.8378770664093453 + acc);
   if (real && lg == 0) {
     if (st_in != ST_OK) { loglik[d] = -INFINITY; status_out[d] = st_in; }

@@ -128,6 +128,24 @@ DYB_D double fast_rsqrt(double x) {
   return y;
 }
 
+// Running product of the innovation determinants with its binary exponent split off after every factor, so that the
+// T-step recursion takes no logarithm: prod = m 2^e with m in [1, 2), log(prod) = log(m) + e log 2 at the end.  A zero,
+// denormal or non-finite product (never for a positive-definite F) is folded by a logarithm as it always was, which keeps
+// the -Inf / NaN outcome of such a draw.  (The threshold-triggered log this replaces ran whenever ANY lane of the warp
+// left [1e-200, 1e200]: 36 % of the periods of fs2000, 158 instructions each.)
+struct LogDetAcc {
+  double m = 1.0, extra = 0.0;
+  int e = 0;
+  DYB_D void mul(double det) {
+    m *= det;
+    const int hi = __double2hiint(m);
+    const int ef = (hi >> 20) & 0x7ff;
+    if (ef == 0 || ef == 0x7ff) { extra += log(m); m = 1.0; }
+    else { e += ef - 1023; m = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(m)); }
+  }
+  DYB_D double value() const { return extra + (log(m) + (double)e * 0.6931471805599453); }
+};
+
 // fast fp64 reciprocal: hardware seed (MUFU.RCP64H) + two Newton steps; callers guard zero / non-finite arguments
 DYB_D double fast_rcp(double x) {
   double y;

@@ -335,7 +335,34 @@ DYB_D bool lu_solve_static(double (&A)[(MM + G - 1) / G][MM], double (&B)[NR][MM
 #define DYB_CR_SOLVER 0
 #endif
 
+#ifndef DYB_CR_BATCH_RMW
+#define DYB_CR_BATCH_RMW 1
+#endif
+#ifndef DYB_CR_TREE_NORM
+#define DYB_CR_TREE_NORM 1
+#endif
 struct CrOptions { double cr_tol; int cr_maxit; };
+
+// sum_r |v[r]| by pairs (depth log2 MM instead of a chain of MM dependent additions; only the stopping norms use it)
+template <int MM>
+DYB_D double abs_sum_tree(const double (&v)[MM]) {
+#if !DYB_CR_TREE_NORM
+  double cs = 0.0;
+#pragma unroll
+  for (int i = 0; i < MM; ++i) cs += fabs(v[i]);
+  return cs;
+#endif
+  double t[MM];
+#pragma unroll
+  for (int i = 0; i < MM; ++i) t[i] = fabs(v[i]);
+#pragma unroll
+  for (int n = MM; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) t[i] = t[2 * i] + t[2 * i + 1];
+    if (n & 1) t[n / 2] = t[n - 1];
+  }
+  return t[0];
+}
 
 #ifndef DYB_CR_LANES
 #define DYB_CR_LANES 4
@@ -528,12 +555,7 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
     }
     double m0 = 0.0;
 #pragma unroll
-    for (int s = 0; s < SL0; ++s) {
-      double cs = 0.0;
-#pragma unroll
-      for (int r = 0; r < MM; ++r) cs += fabs(acc[s][r]);
-      m0 = fmax(m0, cs);
-    }
+    for (int s = 0; s < SL0; ++s) m0 = fmax(m0, abs_sum_tree<MM>(acc[s]));
     __syncwarp(FULL);                               // every lane has read A0 before anybody overwrites it
     if (commit) {
       // A0 <- -W00 (own columns) ; A1[:, fw(j)] -= W01[:, j]
@@ -545,6 +567,27 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
           for (int r = 0; r < MM; ++r) A0s[r + MM * col] = -acc[s][r];
         }
       }
+      // read-modify-write of the tile in two sweeps (all loads, then all stores): the regions alias as far as the compiler
+      // knows, and load -> add -> store chains per element stalled on the shared-memory latency
+#if DYB_CR_BATCH_RMW
+      double old1[SL2][MM];
+#pragma unroll
+      for (int s = 0; s < SL2; ++s) {
+        const int col = s * G + lg;
+        const int tc = M::fwrd_in_dyn(col < NF ? col : 0);
+#pragma unroll
+        for (int r = 0; r < MM; ++r) old1[s][r] = A1s[r + MM * tc];
+      }
+#pragma unroll
+      for (int s = 0; s < SL2; ++s) {
+        const int col = s * G + lg;
+        if (col < NF) {
+          const int tc = M::fwrd_in_dyn(col);
+#pragma unroll
+          for (int r = 0; r < MM; ++r) A1s[r + MM * tc] = old1[s][r] - acc[SL0 + s][r];
+        }
+      }
+#else
 #pragma unroll
       for (int s = 0; s < SL2; ++s) {
         const int col = s * G + lg;
@@ -554,6 +597,7 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
           for (int r = 0; r < MM; ++r) A1s[r + MM * tc] -= acc[SL0 + s][r];
         }
       }
+#endif
     }
     __syncwarp(FULL);
     // pass 2: own columns j of [W10 | W11] = A2 * X[fw, j]
@@ -575,12 +619,7 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
     }
     double m2 = 0.0;
 #pragma unroll
-    for (int s = 0; s < SL2; ++s) {
-      double cs = 0.0;
-#pragma unroll
-      for (int r = 0; r < MM; ++r) cs += fabs(acc[SL0 + s][r]);
-      m2 = fmax(m2, cs);
-    }
+    for (int s = 0; s < SL2; ++s) m2 = fmax(m2, abs_sum_tree<MM>(acc[SL0 + s]));
     __syncwarp(FULL);
     if (commit) {
 #pragma unroll
@@ -591,6 +630,25 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
           for (int r = 0; r < MM; ++r) A2s[r + MM * col] = -acc[SL0 + s][r];
         }
       }
+#if DYB_CR_BATCH_RMW
+      double old1[SL0][MM], olda[SL0][MM];
+#pragma unroll
+      for (int s = 0; s < SL0; ++s) {
+        const int col = (s * G + lg < K) ? s * G + lg : 0;
+        const int tc = M::bkwrd_in_dyn(col);
+#pragma unroll
+        for (int r = 0; r < MM; ++r) { old1[s][r] = A1s[r + MM * tc]; olda[s][r] = accs[r + MM * col]; }
+      }
+#pragma unroll
+      for (int s = 0; s < SL0; ++s) {
+        const int col = s * G + lg;
+        if (col < K) {
+          const int tc = M::bkwrd_in_dyn(col);
+#pragma unroll
+          for (int r = 0; r < MM; ++r) { A1s[r + MM * tc] = old1[s][r] - acc[s][r]; accs[r + MM * col] = olda[s][r] + acc[s][r]; }
+        }
+      }
+#else
 #pragma unroll
       for (int s = 0; s < SL0; ++s) {
         const int col = s * G + lg;
@@ -600,6 +658,7 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
           for (int r = 0; r < MM; ++r) { A1s[r + MM * tc] -= acc[s][r]; accs[r + MM * col] += acc[s][r]; }
         }
       }
+#endif
     }
     __syncwarp(FULL);
     m0 = gmax<G>(FULL, m0);

@@ -82,7 +82,7 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
         if (cap != cudaStreamCaptureStatusNone && !c.d_perm) fast = false;
         else {
           if (!c.d_perm) {
-            if (cudaMalloc(&c.d_perm, sizeof(int) * MT::M) != cudaSuccess || cudaMalloc(&c.d_mid1, sizeof(double) * MidLayout<MT>::SIZE) != cudaSuccess ||
+            if (cudaMalloc(&c.d_perm, sizeof(int) * (MT::M + 1)) != cudaSuccess || cudaMalloc(&c.d_mid1, sizeof(double) * MidLayout<MT>::SIZE) != cudaSuccess ||
                 cudaMalloc(&c.d_st1, sizeof(int)) != cudaSuccess || cudaMalloc(&c.d_redo, 2 * sizeof(unsigned long long)) != cudaSuccess) {
               c.release(); cudaGetLastError(); fast = false;
             } else cudaMemsetAsync(c.d_redo, 0, 2 * sizeof(unsigned long long), st);

@@ -461,6 +461,14 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
   const long long st = n_draws;
   int st_in = status[d];
   constexpr bool skip = false;
+  if constexpr (SOLVER == CR_LU) {
+    // no usable pivot order (the calibration point itself failed): nothing to gain from eliminating in the natural order,
+    // every draw goes straight to the Householder pass
+    if (row_perm[MM] == 0) {
+      if (real && lg == 0 && st_in == ST_OK) { status[d] = ST_REDO; redo_list[atomicAdd(redo_count + 1, 1ULL)] = d; }
+      return;
+    }
+  }
   if constexpr (REDO) {
     st_in = ST_OK;                                    // listed draws entered the fast pass with ST_OK
     if (real && lg == 0) atomicAdd(redo_count, 1ULL);
@@ -889,7 +897,7 @@ cr_kernel(double* __restrict__ mid, long long n_draws, CrOptions opt,
 
 // Pivot order of the equations of the dynamic block, found ONCE per configuration at the calibration point: partial pivoting
 // on A1(0) of the draw in `mid1` (one draw, written by model_kernel with no estimated parameter), row_perm[r] = position of
-// equation r.  Identity when that draw failed -- the fast pass then hands (nearly) everything to the Householder pass.
+// equation r, row_perm[M] = 1.  When that draw fails row_perm[M] = 0 and the fast pass hands every draw to the Householder pass.
 template <class M>
 __global__ void cr_perm_kernel(const double* __restrict__ mid1, const int* __restrict__ status1, int* __restrict__ row_perm) {
   constexpr int MM = M::M, K = M::K;
@@ -899,6 +907,7 @@ __global__ void cr_perm_kernel(const double* __restrict__ mid1, const int* __res
   int orig[MM];
   for (int i = 0; i < MM * MM; ++i) A[i] = 0.0;
   for (int r = 0; r < MM; ++r) { orig[r] = r; row_perm[r] = r; }
+  row_perm[MM] = 0;                                  // [MM]: 1 once a pivot order has been found
   if (status1[0] != ST_OK) return;
   for (int e = 0; e < M::RED_NNZ; ++e) {
     const int rr = M::red_row(e), c = M::red_col(e);
@@ -919,6 +928,7 @@ __global__ void cr_perm_kernel(const double* __restrict__ mid1, const int* __res
     }
   }
   for (int p = 0; p < MM; ++p) row_perm[orig[p]] = p;
+  row_perm[MM] = 1;
 }
 
 // ------------------------------------------------------------------------------------------------

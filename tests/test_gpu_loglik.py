@@ -276,6 +276,32 @@ def test_fast_pass_hands_over_what_it_cannot_verify(name, golden, ws_factory):
     assert 2 * bk_failures <= redo0 <= 2 * (bk_failures + solver_failures) + n // 5
 
 
+def test_fast_pass_without_a_pivot_order(golden, ws_factory):
+    """The fast pass orders the equations by partial pivoting at the CALIBRATION point.  When that point itself has no steady
+    state (here: an estimated parameter calibrated to a value outside its domain, which every draw overrides) there is no
+    order to use: every draw must go to the Householder pass and come back with the same results as solver = 2."""
+    from dynare_jl_b200.engine import model_description
+    g = golden("fs2000")
+    ws = ws_factory("fs2000", g["Y"])
+    d = model_description("fs2000")
+    p = np.array(d["param_values"], dtype=float)
+    est = [i for t, i in zip(d["est_type"], d["est_i"]) if t == 0]
+    p[est[0]] = -5.0                                         # alp < 0: the steady state of the calibration is not finite
+    ws.set_calibration(p)
+    out = {}
+    for variant in (2, 0):
+        ws.set_options(solver=variant)
+        r0 = ws.solver_redo_count()
+        ll, st = ws.loglikelihood(g["theta"])
+        out[variant] = (ll, st, ws.solver_redo_count() - r0)
+    ws.set_options(solver=0)
+    assert np.array_equal(out[0][1], g["status"]) and np.array_equal(out[2][1], g["status"])
+    assert np.array_equal(out[0][0], out[2][0])              # the same kernel solved them: identical bits
+    assert out[0][2] == int((g["status"] != 1).sum()) and out[2][2] == 0
+    ok = g["status"] == 0
+    assert np.max(np.abs(out[0][0][ok] - g["loglik"][ok]) / np.abs(g["loglik"][ok])) <= RTOL_LOGLIK
+
+
 @pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
 def test_prior_predictive_moments_and_irfs(name, golden, ws_factory):
     """run_simulations (priorprediction.jl:64-98): steady state, robustsqrt(diag(variance)) and the 40-period responses of

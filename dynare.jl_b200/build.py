@@ -81,5 +81,39 @@ def build_model_library(name: str, mod_path: str, out_dir: str, spec=None) -> st
     return lib
 
 
+def build_sizes_library(n: int, nx: int, i_static, i_bkwrd_b, i_fwrd_b, obs_idx, out_dir: str, name: str = None) -> tuple:
+    """Compile the register-resident kernels for the SIZES and index sets of a model whose steady state and Jacobian stay on
+    the host (``engine.GenericSSWs(..., compile=True)``): modelgen.emit_cuda_jacobian_fed -> nvcc ->
+    <out_dir>/libdynare_b200_model_<name>.so, self-registering like any compiled model.  The name defaults to a hash of the
+    sizes and index sets, so that equal models share one library.  Returns (library path, model name)."""
+    import hashlib
+    from . import modelgen
+    build_library()
+    key = repr((int(n), int(nx), [int(v) for v in i_static], [int(v) for v in i_bkwrd_b], [int(v) for v in i_fwrd_b],
+                [int(v) for v in obs_idx]))
+    if name is None:
+        name = "jf_" + hashlib.sha1(key.encode()).hexdigest()[:12]
+    os.makedirs(out_dir, exist_ok=True)
+    lib = os.path.join(out_dir, f"libdynare_b200_model_{name}.so")
+    cuh = os.path.join(out_dir, f"model_{name}.cuh")
+    text = modelgen.emit_cuda_jacobian_fed(name, n, nx, i_static, i_bkwrd_b, i_fwrd_b, obs_idx).replace(
+        '#include "../model_traits.cuh"', '#include "model_traits.cuh"')
+    newest = max(os.path.getmtime(p) for p in _deps())
+    if os.path.exists(lib) and os.path.exists(cuh) and open(cuh).read() == text and os.path.getmtime(lib) >= newest:
+        return lib, name
+    with open(cuh, "w") as f:
+        f.write(text)
+    cu = os.path.join(out_dir, f"model_{name}.cu")
+    with open(cu, "w") as f:
+        f.write(f"// GENERATED -- instantiates the solve and filter kernels for the sizes of '{name}'.\n"
+                f"#include \"model_{name}.cuh\"\n#define DYB_MODEL dyb::Model_{name}\n#include \"model_tu.cuh\"\n")
+    cmd = [NVCC, *FLAGS, "-I", CSRC, "-I", out_dir, "-shared", "-o", lib, cu, "-L", PKG, "-l:libdynare_b200.so",
+           "-Xlinker", f"-rpath={PKG}", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {cu}:\n{r.stdout}\n{r.stderr}")
+    return lib, name
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -147,6 +147,7 @@ int dyb_destroy(dyb_handle* h) {
   comm_release(h);
   generic_release(h);
   h->hs.crp.release();
+  h->d_jfJ.release(); h->d_jfyb.release(); h->d_jfse.release(); h->d_jfsm.release(); h->d_jfsi.release();
   h->d_uT.release(); h->d_uQ.release(); h->d_uP.release(); h->d_uyb.release(); h->d_uH.release(); h->d_uz.release(); h->d_uscr.release();
   h->d_theta.release(); h->d_ss.release(); h->d_st1.release(); h->d_ll.release(); h->d_st2.release(); h->d_Y.release(); h->d_mid.release();
   h->h_in.release(); h->h_out.release();
@@ -422,6 +423,99 @@ int dyb_kernel_timers_read_solve_split(dyb_handle* h, float* model_ms_total, flo
   return DYB_OK;
 }
 
+}  // extern "C"
+
+namespace dyb {
+// host or device inputs of a sizes-only model -> device (persistent buffers; device pointers are used in place)
+struct JfInputs { const double *jac, *ybar, *se, *sm; const int* si; };
+static int jacfed_stage(dyb_handle* h, const double* jac, const double* ybar, const double* sigma_e, int se_pd,
+                        const double* sigma_m, int sm_pd, const int* status_in, long long n, JfInputs* o) {
+  const dyb_model_dims& d = h->dims;
+  const size_t N = (size_t)n;
+  cudaError_t e = cudaSuccess;
+  auto stage = [&](DevBuf& b, const void* p, size_t bytes) -> const void* {
+    if (!p || is_device_ptr(p)) return p;
+    if (e == cudaSuccess) e = b.reserve(bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b.p, p, bytes, cudaMemcpyHostToDevice, h->stream);
+    return b.p;
+  };
+  o->jac = static_cast<const double*>(stage(h->d_jfJ, jac, sizeof(double) * d.n * d.ncol * N));
+  o->ybar = static_cast<const double*>(stage(h->d_jfyb, ybar, sizeof(double) * d.n * N));
+  o->se = static_cast<const double*>(stage(h->d_jfse, sigma_e, sizeof(double) * d.nx * d.nx * (se_pd ? N : 1)));
+  o->sm = static_cast<const double*>(stage(h->d_jfsm, sigma_m, sizeof(double) * d.ny * d.ny * (sm_pd ? N : 1)));
+  o->si = static_cast<const int*>(stage(h->d_jfsi, status_in, sizeof(int) * N));
+  if (e != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(e));
+  return DYB_OK;
+}
+
+int jacfed_loglik(dyb_handle* h, const double* jac, const double* ybar, const double* sigma_e, int se_pd,
+                  const double* sigma_m, int sm_pd, const int* status_in, long long n, double* loglik, int* status) {
+  if (n < 0 || (n > 0 && (!jac || !sigma_e || !loglik || !status))) return fail(DYB_ERR_ARG, "null argument");
+  if (h->d_Y.p == nullptr) return fail(DYB_ERR_STATE, "dyb_set_observations has not been called");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  int rc = reserve_batch(h, n);
+  if (rc) return rc;
+  JfInputs in{};
+  rc = jacfed_stage(h, jac, ybar, sigma_e, se_pd, sigma_m, sm_pd, status_in, n, &in);
+  if (rc) return rc;
+  Stager sg(h->stream);
+  double* dll = sg.out(loglik, (size_t)n);
+  int* dst = sg.out(status, (size_t)n);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  SolveOut so{h->d_ss.as<double>(), h->d_st1.as<int>(), nullptr, nullptr, nullptr, nullptr, h->d_mid.as<double>()};
+  cudaEvent_t* ev = h->timers_armed ? timer_slot(h) : nullptr;
+  if (ev) { h->timer_n += 1; so.ev_after_model = ev[3]; so.ev_after_cr = ev[4]; } else ev = h->ev;
+  DYB_CUDA(cudaEventRecord(ev[0], h->stream));
+  DYB_CUDA(h->ops->solve_from_jacobian(h->hs, in.jac, in.ybar, in.se, se_pd, in.sm, sm_pd, in.si, n, so, h->stream));
+  DYB_CUDA(cudaEventRecord(ev[1], h->stream));
+  DYB_CUDA(h->ops->kalman(h->d_ss.as<double>(), n, h->d_Y.as<double>(), h->nobs, h->hs.opt.presample, h->hs.opt.filter_lanes,
+                          h->d_st1.as<int>(), dll, dst, h->stream));
+  DYB_CUDA(cudaEventRecord(ev[2], h->stream));
+  h->ev_valid = (ev == h->ev);
+  h->launches += 4;
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+
+int jacfed_first_order(dyb_handle* h, const double* jac, const double* sigma_e, int se_pd, long long n, double* g1,
+                       double* T, double* RQR, double* P0, int* cr_iters, int* lyap_iters, int* status) {
+  if (n < 0 || (n > 0 && (!jac || !sigma_e || !status))) return fail(DYB_ERR_ARG, "null argument");
+  if (n == 0) return DYB_OK;
+  DYB_CUDA(cudaSetDevice(h->device));
+  const dyb_model_dims& d = h->dims;
+  int rc = reserve_batch(h, n);
+  if (rc) return rc;
+  JfInputs in{};
+  rc = jacfed_stage(h, jac, nullptr, sigma_e, se_pd, nullptr, 0, nullptr, n, &in);
+  if (rc) return rc;
+  Stager sg(h->stream);
+  const size_t N = (size_t)n, ns2 = (size_t)d.ns * d.ns;
+  SolveOut so;
+  so.ss = h->d_ss.as<double>();
+  so.status = sg.out(status, N);
+  so.g1 = sg.out(g1, (size_t)d.n * (d.k + d.nx) * N);
+  so.ybar = nullptr;
+  so.cr_iters = sg.out(cr_iters, N);
+  so.lyap_iters = sg.out(lyap_iters, N);
+  so.mid = h->d_mid.as<double>();
+  double* dT = sg.out(T, ns2 * N); double* dQ = sg.out(RQR, ns2 * N); double* dP = sg.out(P0, ns2 * N);
+  if (sg.err != cudaSuccess) return fail(DYB_ERR_CUDA, cudaGetErrorString(sg.err));
+  if (so.g1) DYB_CUDA(cudaMemsetAsync(so.g1, 0, sizeof(double) * (size_t)d.n * (d.k + d.nx) * N, h->stream));
+  if (so.cr_iters) DYB_CUDA(cudaMemsetAsync(so.cr_iters, 0, sizeof(int) * N, h->stream));
+  if (so.lyap_iters) DYB_CUDA(cudaMemsetAsync(so.lyap_iters, 0, sizeof(int) * N, h->stream));
+  if (dT) DYB_CUDA(cudaMemsetAsync(dT, 0, sizeof(double) * ns2 * N, h->stream));
+  if (dQ) DYB_CUDA(cudaMemsetAsync(dQ, 0, sizeof(double) * ns2 * N, h->stream));
+  if (dP) DYB_CUDA(cudaMemsetAsync(dP, 0, sizeof(double) * ns2 * N, h->stream));
+  DYB_CUDA(h->ops->solve_from_jacobian(h->hs, in.jac, nullptr, in.se, se_pd, nullptr, 0, nullptr, n, so, h->stream));
+  if (dT || dQ || dP) DYB_CUDA(h->ops->unpack(h->d_ss.as<double>(), n, dT, dQ, dP, nullptr, nullptr, h->stream));
+  h->launches += 4;
+  DYB_CUDA(sg.finish());
+  return DYB_OK;
+}
+}  // namespace dyb
+
+extern "C" {
 int dyb_solver_redo_count(dyb_handle* h, int64_t* n_redone) {
   if (!h || !n_redone) return fail(DYB_ERR_ARG, "null argument");
   DYB_CUDA(cudaSetDevice(h->device));

@@ -641,6 +641,8 @@ static int generic_solve(dyb_handle* h, GenericSolveArgs a) {
 int dyb_first_order_from_jacobian_batch(dyb_handle* h, const double* jac, const double* sigma_e, int32_t sigma_e_per_draw,
                                         int64_t n, double* g1, double* T, double* RQR, double* P0,
                                         int32_t* cr_iters, int32_t* lyap_iters, int32_t* status) {
+  if (h && h->ops && h->ops->solve_from_jacobian)       // a compiled sizes-only model: the register-resident kernels
+    return jacfed_first_order(h, jac, sigma_e, sigma_e_per_draw, n, g1, T, RQR, P0, cr_iters, lyap_iters, status);
   if (!h || !h->generic) return fail(DYB_ERR_ARG, "needs a handle made by dyb_create_generic");
   if (n < 0 || (n > 0 && (!jac || !sigma_e || !status))) return fail(DYB_ERR_ARG, "null argument");
   if (n == 0) return DYB_OK;
@@ -712,6 +714,8 @@ static int loglik_from_device_jacobians(dyb_handle* h, const double* djac, const
 int dyb_loglik_from_jacobian_batch(dyb_handle* h, const double* jac, const double* ybar, const double* sigma_e,
                                    int32_t sigma_e_per_draw, const double* sigma_m, int32_t sigma_m_per_draw,
                                    const int32_t* status_in, int64_t n, double* loglik, int32_t* status) {
+  if (h && h->ops && h->ops->solve_from_jacobian)       // a compiled sizes-only model: the register-resident kernels
+    return jacfed_loglik(h, jac, ybar, sigma_e, sigma_e_per_draw, sigma_m, sigma_m_per_draw, status_in, n, loglik, status);
   if (!h || !h->generic || h->ops) return fail(DYB_ERR_ARG, "needs a handle made by dyb_create_generic");
   if (n < 0 || (n > 0 && (!jac || !sigma_e || !loglik || !status))) return fail(DYB_ERR_ARG, "null argument");
   if (h->d_Y.p == nullptr) return fail(DYB_ERR_STATE, "dyb_set_observations has not been called");

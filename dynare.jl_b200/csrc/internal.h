@@ -141,6 +141,11 @@ void generic_release(dyb_handle* h);
 // dyb_options.univariate_fallback for the model-specific path: re-evaluates flagged draws from the hand-off buffer (generic.cu)
 // generated models beyond the register-resident solver (ModelOps::register_solver == false): generic.cu
 int hybrid_loglik(dyb_handle* h, const double* d_theta, long long n, double* d_loglik, int* d_status);
+// sizes-only models (ModelOps::solve_from_jacobian): the register-resident kernels on host-evaluated Jacobians (api.cu)
+int jacfed_loglik(dyb_handle* h, const double* jac, const double* ybar, const double* sigma_e, int sigma_e_per_draw,
+                  const double* sigma_m, int sigma_m_per_draw, const int* status_in, long long n, double* loglik, int* status);
+int jacfed_first_order(dyb_handle* h, const double* jac, const double* sigma_e, int sigma_e_per_draw, long long n, double* g1,
+                       double* T, double* RQR, double* P0, int* cr_iters, int* lyap_iters, int* status);
 int hybrid_first_order(dyb_handle* h, const double* d_theta, long long n, double* d_g1, double* d_ybar, int* d_cr_iters,
                        int* d_lyap_iters, int* d_status);
 int univariate_fallback_from_handoff(dyb_handle* h, long long n, const int* d_status_solve, double* d_loglik, int* d_status);
@@ -161,6 +166,7 @@ struct dyb_handle {
   dyb::HostState hs;
   dyb::DevBuf d_theta, d_ss, d_st1, d_ll, d_st2, d_Y, d_mid;
   dyb::DevBuf d_uT, d_uQ, d_uP, d_uyb, d_uH, d_uz, d_uscr;     // dense state spaces of the univariate fallback (generic.cu)
+  dyb::DevBuf d_jfJ, d_jfyb, d_jfse, d_jfsm, d_jfsi;           // staged inputs of a sizes-only model (jacfed_*, api.cu)
   dyb::PinBuf h_in, h_out;
   int ny_obs = 0, nobs = 0;
   int64_t launches = 0;

@@ -35,7 +35,8 @@ constexpr bool mt_coop_fits = CrCfg<MT>::FITS;
 // and could not launch); the generated model function feeds the run-time-size solver and the dense tensor-core filter
 // instead (ModelOps::jacobian_batch, generic.cu).
 constexpr bool mt_big = (MT::M > 12) || (MT::NS > 16);
-constexpr bool mt_fast_fits = CrCfg<MT>::FITS_LU;
+constexpr bool mt_jac_fed = is_jac_fed<MT>::value;      // sizes-only model: Jacobians come from the host (modelgen.emit_cuda_jacobian_fed)
+constexpr bool mt_fast_fits = CrCfg<MT>::FITS_LU && !mt_jac_fed;
 int mt_solve_launches(const HostState& hs) {
   return mt_big ? 2 : ((mt_coop_fits && hs.opt.solver != 1) ? ((mt_fast_fits && hs.opt.solver == 0) ? 4 : 3) : 1);
 }
@@ -51,7 +52,7 @@ unsigned long long mt_perm_key(const HostState& hs) {
 
 cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, SolveOut out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  if constexpr (mt_big) { return cudaErrorNotSupported; } else {
+  if constexpr (mt_big || mt_jac_fed) { return cudaErrorNotSupported; } else {
   SolveParams<MT> prm;
   for (int i = 0; i < MT::NPAR; ++i) prm.params0[i] = hs.params[i];
   for (int i = 0; i < MT::NX * MT::NX; ++i) prm.sigma_e0[i] = hs.sigma_e[i];
@@ -132,6 +133,26 @@ cudaError_t mt_solve(const HostState& hs, const double* d_theta, long long n, So
   (void)coop;
   SolveExtra ex{out.g1, out.ybar, out.cr_iters, out.lyap_iters};
   solve_kernel<MT><<<(unsigned)grid, block, 0, st>>>(prm, d_theta, n, out.ss, out.status, ex);
+  return cudaGetLastError();
+  }
+}
+
+// sizes-only models: host-evaluated Jacobians -> static elimination -> the Householder cyclic reduction -> assembly
+cudaError_t mt_solve_from_jacobian(const HostState& hs, const double* d_jac, const double* d_ybar, const double* d_se,
+                                   int se_per_draw, const double* d_sm, int sm_per_draw, const int* d_status_in,
+                                   long long n, SolveOut out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  if constexpr (!(mt_jac_fed && mt_coop_fits)) { return cudaErrorNotSupported; } else {
+  constexpr int G = CrCfg<MT>::G;
+  jac_model_kernel<MT><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_jac, d_ybar, d_se, se_per_draw, d_sm, sm_per_draw,
+                                                                     d_status_in, n, out.mid, out.status);
+  if (out.ev_after_model) cudaEventRecord(out.ev_after_model, st);
+  const long long gridc = (n * G + CrCfg<MT>::BLOCK - 1) / CrCfg<MT>::BLOCK;
+  CrOptions co{hs.opt.cr_tol, hs.opt.cr_maxit};
+  cr_kernel<MT, G, CR_QR, false><<<(unsigned)gridc, CrCfg<MT>::BLOCK, 0, st>>>(out.mid, n, co, out.status, out.cr_iters, nullptr, nullptr, nullptr);
+  if (out.ev_after_cr) cudaEventRecord(out.ev_after_cr, st);
+  assemble_kernel<MT><<<(unsigned)((n + DYB_ASM_BLOCK - 1) / DYB_ASM_BLOCK), DYB_ASM_BLOCK, 0, st>>>(out.mid, n, hs.opt.lyap_tol, hs.opt.lyap_maxit, out.ss,
+                                                                                                   out.status, out.g1, out.lyap_iters);
   return cudaGetLastError();
   }
 }
@@ -290,7 +311,8 @@ const ModelOps mt_ops = {
   {MT::N, MT::NX, MT::NPAR, MT::K, MT::NF, MT::S, MT::NCOL, MT::NS, MT::NY, MT::NP_DEFAULT, SSLayout<MT>::SIZE, MidLayout<MT>::SIZE},
   MidLayout<MT>::SIZE,
   mt_defaults, mt_solve_launches, mt_solve, mt_kalman, mt_unpack, mt_bkwrd_indices, mt_obs_indices,
-  mt_obs_state_positions, !mt_big, mt_static_indices, mt_fwrd_indices, mt_jacobian_batch
+  mt_obs_state_positions, !mt_big, mt_static_indices, mt_fwrd_indices, mt_jacobian_batch,
+  (mt_jac_fed && mt_coop_fits) ? mt_solve_from_jacobian : nullptr
 };
 
 struct Registrar { Registrar() { register_model(&mt_ops); } } mt_registrar;

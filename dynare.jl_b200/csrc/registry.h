@@ -74,6 +74,12 @@ struct ModelOps {
   // theta -> per draw: compressed Jacobian n x ncol (column-major), steady state n, Sigma_e nx x nx, Sigma_m ny x ny, status
   cudaError_t (*jacobian_batch)(const HostState&, const double* d_theta, long long n, double* d_jac, double* d_ybar,
                                 double* d_sigma_e, double* d_sigma_m, int* d_status, cudaStream_t);
+  // ---- "sizes-only" models (modelgen.emit_cuda_jacobian_fed): no model function, the HOST evaluates steady state and
+  // compressed Jacobian per draw and the register-resident kernels, compiled for the model's sizes and index sets, do the
+  // rest.  Null for models with a generated model function.  Inputs as dyb_loglik_from_jacobian_batch (device pointers).
+  cudaError_t (*solve_from_jacobian)(const HostState&, const double* d_jac, const double* d_ybar, const double* d_sigma_e,
+                                     int sigma_e_per_draw, const double* d_sigma_m, int sigma_m_per_draw,
+                                     const int* d_status_in, long long n, SolveOut out, cudaStream_t);
 };
 
 const std::vector<const ModelOps*>& registry();

@@ -18,6 +18,7 @@
 // Reference stages replaced: LRE.first_order_solver! (src/perturbations.jl:663-664), compute_variance!
 // (src/estimation/estimation.jl:630), state-space assembly (estimation.jl:640-658).
 #pragma once
+#include <type_traits>
 #include "model_traits.cuh"
 #include "solve_kernel.cuh"
 
@@ -138,6 +139,91 @@ model_kernel(const SolveParams<M> prm, const double* __restrict__ theta, long lo
     for (int j = 0; j <= i; ++j) out[L::OFF_H + tri(i, j)] = Sm[i + NY * j];
   status[d] = st;
 }
+
+// ------------------------------------------------------------------------------------------------
+// model_kernel's counterpart for "sizes-only" models (M::JAC_FED): the host has evaluated the steady state and the compressed
+// dynamic Jacobian of every draw (as the reference does per draw, src/perturbations.jl:526-561, 616-635); this kernel does
+// the static elimination -- a dense Householder QR on the S static columns, applied to every column of the working matrix
+// [static | lags | dynamic current | leads | shocks] -- and writes the same hand-off (`mid`) as model_kernel: the reduced rows
+// (dense: RED_NNZ = M x (NCOL - S)), the S pivot rows (TOP_NNZ = S x NCOL), ybar of the observables, Sigma_e, H.
+// One thread per draw, the working matrix in local memory (run-time loops: the sizes are compile-time constants but the
+// code stays small).  jac: N x NCOL per draw, column-major, columns [lags of i_bkwrd_b | N current | leads of i_fwrd_b | NX].
+template <class M>
+__global__ void __launch_bounds__(128)
+jac_model_kernel(const double* __restrict__ jac, const double* __restrict__ ybar, const double* __restrict__ sigma_e,
+                 int se_per_draw, const double* __restrict__ sigma_m, int sm_per_draw, const int* __restrict__ status_in,
+                 long long n_draws, double* __restrict__ mid, int* __restrict__ status) {
+  constexpr int N = M::N, NX = M::NX, NY = M::NY, NCOL = M::NCOL, S = M::S, W = NCOL - S;
+  using L = MidLayout<M>;
+  static_assert(M::RED_NNZ == M::M * W && M::TOP_NNZ == S * NCOL, "dense hand-off pattern");
+  const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_draws) return;
+  int st = status_in ? status_in[d] : ST_OK;
+  StridedOut out{mid + d, n_draws};
+  double Wm[N * NCOL];
+  const double* J = jac + d * (long long)(N * NCOL);
+  double chk = 0.0;
+#pragma unroll 1
+  for (int c = 0; c < NCOL; ++c) {
+    const int wc = M::jperm(c);
+#pragma unroll 1
+    for (int r = 0; r < N; ++r) { const double v = J[r + N * c]; Wm[r + N * wc] = v; chk = fma(v, 0.0, chk); }
+  }
+  if (st == ST_OK && !(chk == 0.0)) st = ST_STEADY;          // NaN / Inf in the Jacobian
+  bool nonsing = true;
+#pragma unroll 1
+  for (int q = 0; q < S; ++q) {
+    double s2 = 0.0;
+#pragma unroll 1
+    for (int r = q + 1; r < N; ++r) s2 = fma(Wm[r + N * q], Wm[r + N * q], s2);
+    const double xq = Wm[q + N * q];
+    const double nrm = sqrt(fma(xq, xq, s2));
+    if (!(nrm > 0.0)) { nonsing = false; break; }
+    const double alpha = xq >= 0.0 ? -nrm : nrm;
+    const double vq = xq - alpha;
+    const double beta = 1.0 / (-alpha * vq);                 // 2 / (v'v)
+    Wm[q + N * q] = alpha;
+#pragma unroll 1
+    for (int c = q + 1; c < NCOL; ++c) {
+      double dt = vq * Wm[q + N * c];
+#pragma unroll 1
+      for (int r = q + 1; r < N; ++r) dt = fma(Wm[r + N * q], Wm[r + N * c], dt);
+      dt *= beta;
+      Wm[q + N * c] = fma(-dt, vq, Wm[q + N * c]);
+#pragma unroll 1
+      for (int r = q + 1; r < N; ++r) Wm[r + N * c] = fma(-dt, Wm[r + N * q], Wm[r + N * c]);
+    }
+#pragma unroll 1
+    for (int r = q + 1; r < N; ++r) Wm[r + N * q] = 0.0;
+  }
+  if (st == ST_OK && !nonsing) st = ST_SOLVER;
+  if (st == ST_OK) {
+#pragma unroll 1
+    for (int r = 0; r < M::M; ++r)
+#pragma unroll 1
+      for (int c = 0; c < W; ++c) out[L::OFF_RED + r * W + c] = Wm[(S + r) + N * (S + c)];
+#pragma unroll 1
+    for (int q = 0; q < S; ++q)
+#pragma unroll 1
+      for (int c = 0; c < NCOL; ++c) out[L::OFF_TOP + q * NCOL + c] = Wm[q + N * c];
+  }
+  const double* yb = ybar ? ybar + d * N : nullptr;
+#pragma unroll 1
+  for (int i = 0; i < NY; ++i) out[L::OFF_YB + i] = yb ? yb[M::state_ids(M::obs_idx_state(i))] : 0.0;
+  const double* Se = sigma_e + (se_per_draw ? d * (long long)(NX * NX) : 0);
+#pragma unroll 1
+  for (int i = 0; i < NX * NX; ++i) out[L::OFF_SE + i] = Se[i];
+  const double* Sm = sigma_m ? sigma_m + (sm_per_draw ? d * (long long)(NY * NY) : 0) : nullptr;
+#pragma unroll 1
+  for (int i = 0; i < NY; ++i)
+#pragma unroll 1
+    for (int j = 0; j <= i; ++j) out[L::OFF_H + tri(i, j)] = Sm ? Sm[i + NY * j] : 0.0;
+  status[d] = st;
+}
+
+// detection of sizes-only models
+template <class T, class = void> struct is_jac_fed : std::false_type {};
+template <class T> struct is_jac_fed<T, std::void_t<decltype(T::JAC_FED)>> : std::integral_constant<bool, T::JAC_FED> {};
 
 // ------------------------------------------------------------------------------------------------
 // cyclic reduction, G lanes per draw

@@ -378,14 +378,30 @@ class GenericSSWs:
     Jacobian per draw (as the reference does, src/perturbations.jl:533-561) and this class runs everything after
     that on the GPU.  Index sets are 0-based, as ``Model`` holds them (src/dynare_containers.jl:110-131)."""
 
-    def __init__(self, n, nx, i_static, i_bkwrd_b, i_fwrd_b, obs_idx, observations=None, device=0):
+    def __init__(self, n, nx, i_static, i_bkwrd_b, i_fwrd_b, obs_idx, observations=None, device=0, compile=False,
+                 build_dir=None):
+        """``compile=True``: the register-resident kernels of the generated-model path are compiled (nvcc, once per set of
+        sizes and index sets, cached in ``build_dir``) for THIS model's sizes -- a "sizes-only" model without a model
+        function (build.build_sizes_library) -- and used instead of the run-time-size kernels: the same calls, an order of
+        magnitude faster for small models (dynamic block <= 12).  Falls back to the run-time-size kernels when the model
+        does not fit them."""
         self.lib = L.load()
         self._idx = [np.ascontiguousarray(a, dtype=np.int32) for a in (i_static, i_bkwrd_b, i_fwrd_b, obs_idx)]
-        d = L.ModelDesc(n, nx, len(self._idx[3]), len(self._idx[0]), len(self._idx[1]), len(self._idx[2]),
-                        *[a.ctypes.data if a.size else None for a in self._idx])
+        self.compiled = False
         h = C.c_void_p()
-        L.check(self.lib.dyb_create_generic(C.byref(d), device, C.byref(h)))
+        if compile and n - len(self._idx[0]) <= 12:
+            from . import build as _build
+            bdir = build_dir or os.path.join(L.PACKAGE_DIR, "models", "_sizes")      # in-tree: travels with the built library
+            lib, name = _build.build_sizes_library(n, nx, *[a.tolist() for a in self._idx], bdir)
+            load_model_library(lib)
+            L.check(self.lib.dyb_create(name.encode(), device, C.byref(h)))
+            self.compiled = True
+        else:
+            d = L.ModelDesc(n, nx, len(self._idx[3]), len(self._idx[0]), len(self._idx[1]), len(self._idx[2]),
+                            *[a.ctypes.data if a.size else None for a in self._idx])
+            L.check(self.lib.dyb_create_generic(C.byref(d), device, C.byref(h)))
         self._h = h
+        self.nobs = 0
         dm = L.ModelDims()
         L.check(self.lib.dyb_get_dims(self._h, C.byref(dm)))
         self.dims = dm.asdict()
@@ -397,6 +413,9 @@ class GenericSSWs:
     set_options = BatchSSWs.set_options
     close = BatchSSWs.close
     __del__ = BatchSSWs.__del__
+    timers_reset = BatchSSWs.timers_reset
+    timers_read = BatchSSWs.timers_read
+    timers_read_solve_split = BatchSSWs.timers_read_solve_split
 
     def _jac(self, jac):
         """(N, n, ncol) numpy -> per-draw column-major."""

@@ -791,6 +791,76 @@ def emit_cuda(spec: ModelSpec) -> str:
     return "\n".join(L) + "\n"
 
 
+def emit_cuda_jacobian_fed(name: str, n: int, nx: int, i_static, i_bkwrd_b, i_fwrd_b, obs_idx) -> str:
+    """CUDA header of a SIZES-ONLY model: the traits struct the register-resident kernels are templated on -- compile-time
+    sizes and the reference's index sets (``Model.i_static / i_bkwrd_b / i_fwrd_b``, src/dynare_containers.jl:110-131,
+    0-based) -- with NO model function: the host keeps evaluating steady state and compressed Jacobian per draw (as the
+    reference does, src/perturbations.jl:526-561, 616-635) and ``jac_model_kernel`` (csrc/solve_coop.cuh) takes them from
+    memory.  The hand-off patterns are dense (RED_NNZ = M (NCOL - S), TOP_NNZ = S NCOL).  ``JAC_FED`` marks the struct."""
+    i_static = [int(v) for v in i_static]; i_bkwrd_b = [int(v) for v in i_bkwrd_b]
+    i_fwrd_b = [int(v) for v in i_fwrd_b]; obs_idx = [int(v) for v in obs_idx]
+    if sorted(set(i_static) | set(i_bkwrd_b) | set(i_fwrd_b)) != list(range(n)) or set(i_static) & (set(i_bkwrd_b) | set(i_fwrd_b)):
+        raise ValueError("i_static, i_bkwrd_b and i_fwrd_b must cover 0..n-1, the static set disjoint from the other two")
+    i_dyn = [v for v in range(n) if v not in set(i_static)]
+    s_, k, nf, m = len(i_static), len(i_bkwrd_b), len(i_fwrd_b), len(i_dyn)
+    ncol = k + n + nf + nx
+    state_ids = sorted(set(obs_idx) | set(i_bkwrd_b))
+    obs_idx_state = [state_ids.index(i) for i in obs_idx]
+    lagged_state_ids = [p for p, i in enumerate(state_ids) if i in set(i_bkwrd_b)]
+    pos_in_dyn = {v: i for i, v in enumerate(i_dyn)}
+    pos_in_static = {v: i for i, v in enumerate(i_static)}
+    ny, ns = len(obs_idx), len(state_ids)
+    L = []
+    A = L.append
+    A(f"// GENERATED by dynare_jl_b200.modelgen.emit_cuda_jacobian_fed for '{name}' -- do not edit.")
+    A("// Sizes and index sets only: steady state and Jacobian are evaluated by the host and uploaded per draw.")
+    A("#pragma once")
+    A("#include \"../model_traits.cuh\"")
+    A("namespace dyb {")
+    A(f"struct Model_{name} {{")
+    A(f"  static constexpr const char* name = \"{name}\";")
+    A("  static constexpr bool JAC_FED = true;")
+    for nm, val in [("N", n), ("NX", nx), ("NPAR", 0), ("K", k), ("NF", nf), ("S", s_), ("M", m), ("NCOL", ncol),
+                    ("NS", ns), ("NY", ny), ("NL", len(lagged_state_ids)), ("NP_DEFAULT", 0)]:
+        A(f"  static constexpr int {nm} = {val};")
+    A("  static constexpr bool LINEAR = true;")
+
+    def arr(nm, v):
+        v = list(v)
+        A(f"  DYB_HD static constexpr int {nm}(int i) {{ constexpr int a[{max(len(v), 1)}] = {_int_list(v)}; return a[i]; }}")
+    arr("i_bkwrd_b", i_bkwrd_b); arr("i_fwrd_b", i_fwrd_b); arr("i_static", i_static); arr("i_dyn", i_dyn)
+    arr("bkwrd_in_dyn", [pos_in_dyn[v] for v in i_bkwrd_b]); arr("fwrd_in_dyn", [pos_in_dyn[v] for v in i_fwrd_b])
+    arr("state_ids", state_ids); arr("obs_idx_state", obs_idx_state); arr("lagged_state_ids", lagged_state_ids)
+    arr("lagged_in_bkwrd", [i_bkwrd_b.index(state_ids[p]) for p in lagged_state_ids])
+    arr("var_static", [1 if v in pos_in_static else 0 for v in range(n)])
+    arr("var_pos", [pos_in_static[v] if v in pos_in_static else pos_in_dyn[v] for v in range(n)])
+    jperm = [s_ + j for j in range(k)]
+    jperm += [pos_in_static[v] if v in pos_in_static else s_ + k + pos_in_dyn[v] for v in range(n)]
+    jperm += [s_ + k + m + j for j in range(nf)]
+    jperm += [s_ + k + m + nf + j for j in range(nx)]
+    arr("jperm", jperm)
+    arr("est_type0", []); arr("est_i0", []); arr("est_j0", [])
+    A("  DYB_HD static constexpr double param0(int) { return 0.0; }")
+    A("  DYB_HD static constexpr double sigma_e0(int) { return 0.0; }")
+    A("  DYB_HD static constexpr double sigma_m0(int) { return 0.0; }")
+    A("  // no model function: these exist so that the shared translation unit compiles; they are never launched")
+    A("  DYB_HD static void steady_state(const double*, double* y) { for (int i = 0; i < N; ++i) y[i] = 0.0; }")
+    A("  DYB_HD static double static_resid_ss(const double*, const double*) { return 0.0; }")
+    A("  template <class JT> DYB_HD static void jacobian(const double*, const double*, JT&) {}")
+    A("  static constexpr int JAC_NNZ = 0;")
+    A(f"  static constexpr int RED_NNZ = {m * (ncol - s_)};")
+    A(f"  static constexpr int TOP_NNZ = {s_ * ncol};")
+    A(f"  DYB_HD static constexpr int red_row(int i) {{ return i / {ncol - s_}; }}")
+    A(f"  DYB_HD static constexpr int red_col(int i) {{ return i % {ncol - s_}; }}")
+    A(f"  DYB_HD static constexpr int top_row(int i) {{ return i / {ncol}; }}")
+    A(f"  DYB_HD static constexpr int top_col(int i) {{ return i % {ncol}; }}")
+    A("  template <class OT> DYB_HD static bool static_elim(const double*, const double*, OT&) { return false; }")
+    A("  static constexpr int STATIC_ELIM_FMA = 0;")
+    A("};")
+    A("}  // namespace dyb")
+    return "\n".join(L) + "\n"
+
+
 def emit_c(spec: ModelSpec) -> str:
     if spec.ss_numeric:
         raise NotImplementedError("the C restatement covers models with a closed-form steady state only")

@@ -272,6 +272,12 @@ typedef struct dyb_model_desc {
 /* a handle with run-time sizes; dyb_set_observations / dyb_set_options / dyb_get_dims / dyb_destroy apply, the
  * theta-based entry points return DYB_ERR_UNSUPPORTED */
 int dyb_create_generic(const dyb_model_desc* desc, int device, dyb_handle** out);
+/* The two *_from_jacobian entry points below also accept a handle made by dyb_create(name) for a "SIZES-ONLY" model: a
+ * translation unit that instantiates the register-resident kernels of the generated-model path for the model's sizes and
+ * index sets, without a model function (host side: modelgen.emit_cuda_jacobian_fed + build.build_sizes_library, i.e.
+ * engine.GenericSSWs(..., compile = True); a dynamic block of at most 12 variables).  Same arguments, same results to
+ * solver accuracy; ls2003 with device-resident Jacobians: 30 M evaluations/s against 5.9 M for the run-time-size kernels
+ * (fs2000 22.9 M, hs_nk 80 M; from pinned host memory the 1.2 - 3.7 KB per draw of PCIe traffic bound it at 9 - 26 M). */
 /* LRE.first_order_solver! + compute_variance! + state-space assembly from compressed Jacobians
  * (n x ncol per draw, column-major, columns [lags of i_bkwrd_b | all n current | leads of i_fwrd_b | nx shocks]).
  * sigma_e: nx x nx, one per draw (sigma_e_per_draw != 0) or shared.  Outputs per draw (any may be NULL):

@@ -12,8 +12,10 @@ sys.path.insert(0, ROOT)
 from dynare_jl_b200.engine import GenericSSWs          # noqa: E402
 from oracle import models, pipeline as pl              # noqa: E402
 
-name = sys.argv[1] if len(sys.argv) > 1 else "fs2000"
-N = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+COMPILE = "--compile" in sys.argv            # the register-resident kernels compiled for the model's sizes (sizes-only model)
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+name = argv[0] if len(argv) > 0 else "fs2000"
+N = int(argv[1]) if len(argv) > 1 else 16384
 g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{name}_golden.npz")))
 m = models.get_model(name)
 ok = np.flatnonzero(g["status"] == 0)[:64]
@@ -24,7 +26,8 @@ for t in g["theta"][ok]:
 rep = (N + len(J) - 1) // len(J)
 J = np.tile(np.array(J), (rep, 1, 1))[:N]; yb = np.tile(np.array(yb), (rep, 1))[:N]
 Se = np.tile(np.array(Se), (rep, 1, 1))[:N]; Sm = np.tile(np.array(Sm), (rep, 1, 1))[:N]
-ws = GenericSSWs(m.n, m.nx, m.i_static, m.i_bkwrd_b, m.i_fwrd_b, m.obs_idx, observations=g["Y"])
+ws = GenericSSWs(m.n, m.nx, m.i_static, m.i_bkwrd_b, m.i_fwrd_b, m.obs_idx, observations=g["Y"], compile=COMPILE)
+print("compiled sizes-only model:", ws.compiled)
 ll, st = ws.loglikelihood(J, yb, Se, Sm)
 ref = np.tile(g["loglik"][ok], rep)[:N]
 assert np.all(st == 0) and np.allclose(ll, ref, rtol=1e-8)

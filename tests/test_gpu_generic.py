@@ -27,14 +27,18 @@ def _host_side(m, theta):
     return J, yb, Se, Sm, st
 
 
+@pytest.mark.parametrize("compiled", [False, True])
 @pytest.mark.parametrize("name", ["fs2000", "ls2003", "hs_nk"])
-def test_generic_path_matches_oracle(name, golden):
+def test_generic_path_matches_oracle(name, compiled, golden):
+    """compiled = False: the run-time-size kernels; True: the register-resident kernels compiled for the model's sizes and
+    index sets alone (a "sizes-only" model, build.build_sizes_library), fed with the same host-evaluated Jacobians."""
     from dynare_jl_b200.engine import GenericSSWs
     g = golden(name)
     m = models.get_model(name)
     theta = g["theta"][:96]
     J, yb, Se, Sm, st_host = _host_side(m, theta)
-    ws = GenericSSWs(m.n, m.nx, m.i_static, m.i_bkwrd_b, m.i_fwrd_b, m.obs_idx, observations=g["Y"])
+    ws = GenericSSWs(m.n, m.nx, m.i_static, m.i_bkwrd_b, m.i_fwrd_b, m.obs_idx, observations=g["Y"], compile=compiled)
+    assert ws.compiled == compiled
     assert ws.dims["ns"] == m.ns and ws.dims["k"] == m.k and ws.dims["ncol"] == J.shape[2]
     fo = ws.first_order(J, Se)
     ll, st = ws.loglikelihood(J, yb, Se, Sm, status_in=st_host)
@@ -49,7 +53,8 @@ def test_generic_path_matches_oracle(name, golden):
         assert np.abs(fo["g1_2"][i] - d["sol"]["g1_2"]).max() < 1e-10
         ss = d["ss"]
         assert np.abs(fo["T"][i] - ss["T"]).max() < 1e-10
-        assert np.allclose(fo["RQR"][i], ss["R"] @ ss["Q"] @ ss["R"].T, rtol=1e-9, atol=1e-14)
+        rqr = ss["R"] @ ss["Q"] @ ss["R"].T
+        assert np.allclose(fo["RQR"][i], rqr, rtol=1e-9, atol=1e-13 * max(1.0, np.abs(rqr).max()))
         sc = max(1.0, np.abs(ss["P0"]).max())
         assert np.abs(fo["P0"][i] - ss["P0"]).max() <= 1e-9 * sc
         assert abs(ll[i] - g["loglik"][i]) <= 1e-8 * abs(g["loglik"][i])

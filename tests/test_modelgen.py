@@ -90,3 +90,24 @@ def test_aux_variables_for_long_leads_and_lags():
     spec = modelgen.build_spec("toy", parse_mod(txt))
     assert spec.endo == ["x", "z", "AUX_ENDO_LAG_x_1", "AUX_ENDO_LEAD_z_1", "AUX_ENDO_LEAD_z_2"]
     assert spec.n == 5 and spec.k == 3 and spec.nf == 3
+
+
+def test_sizes_only_header():
+    """modelgen.emit_cuda_jacobian_fed: traits of a model whose steady state and Jacobian stay on the host -- sizes, the
+    reference's index sets (src/dynare_containers.jl:110-131) and the dense hand-off patterns, no model function."""
+    from dynare_jl_b200 import modelgen
+    from oracle import models
+    m = models.get_model("ls2003")
+    txt = modelgen.emit_cuda_jacobian_fed("jf_test", m.n, m.nx, m.i_static, m.i_bkwrd_b, m.i_fwrd_b, m.obs_idx)
+    s, k, nf, mm = len(m.i_static), m.k, m.nf, m.n - len(m.i_static)
+    ncol = k + m.n + nf + m.nx
+    assert "static constexpr bool JAC_FED = true;" in txt and "struct Model_jf_test" in txt
+    assert f"static constexpr int RED_NNZ = {mm * (ncol - s)};" in txt and f"static constexpr int TOP_NNZ = {s * ncol};" in txt
+    assert f"static constexpr int NS = {m.ns};" in txt and f"static constexpr int NCOL = {ncol};" in txt
+    # the working-matrix permutation is a permutation, static columns first
+    import re
+    jp = [int(x) for x in re.search(r"jperm\(int i\) \{ constexpr int a\[\d+\] = \{([^}]*)\}", txt).group(1).split(",")]
+    assert sorted(jp) == list(range(ncol))
+    assert sorted(jp[k + v] for v in m.i_static) == list(range(s))
+    with pytest.raises(ValueError):
+        modelgen.emit_cuda_jacobian_fed("bad", 4, 1, [0, 1], [1], [2], [0])        # a static variable cannot have a lag

@@ -172,7 +172,8 @@ int dyb_set_options(dyb_handle* h, const dyb_options* opt) {
   if (!h || !opt) return fail(DYB_ERR_ARG, "null argument");
   if (!(opt->cr_tol > 0) || opt->cr_maxit < 1 || !(opt->steady_tol > 0) || !(opt->lyap_tol >= 0) ||
       opt->lyap_maxit < 1 || opt->presample < 0 || opt->solver < 0 || opt->solver > 2 ||
-      !(opt->filter_lanes == 0 || opt->filter_lanes == 1 || opt->filter_lanes == 4 || opt->filter_lanes == 8) ||
+      !(opt->filter_lanes == 0 || opt->filter_lanes == 1 || opt->filter_lanes == 4 || opt->filter_lanes == 8 ||
+        opt->filter_lanes == 16 || opt->filter_lanes == 32) ||
       opt->univariate_fallback < 0 || opt->univariate_fallback > 2)
     return fail(DYB_ERR_ARG, "invalid option value");
   h->hs.opt = *opt;

@@ -10,6 +10,7 @@
 #include "solve_coop.cuh"
 #include "kalman_kernel.cuh"
 #include "kalman_sublanes.cuh"
+#include "kalman_coop.cuh"
 
 namespace dyb {
 namespace {
@@ -174,12 +175,45 @@ cudaError_t mt_kalman_sub(const double* d_ss, long long n, const double* d_Y, in
   }
 }
 
-// lanes per draw of the filter: 1 = one thread per draw (throughput kernel), 4 / 8 = shared-tile kernel for batches that
-// leave schedulers idle; `want` = dyb_options.filter_lanes (0 = choose by batch width: 8 lanes up to 2 048 draws, 4 up to
-// 4 096, one thread per draw beyond -- ls2003 filter at 2 048 / 4 096 / 8 192 draws: 0.164 / 0.189 / 0.229 ms with 8 / 4 / 1 lanes)
+// G = 16 / 32 lanes per draw for the smallest batches (kalman_coop.cuh)
+template <int G>
+cudaError_t mt_kalman_coop(const double* d_ss, long long n, const double* d_Y, int nobs, int presample,
+                           const int* d_status_in, double* d_loglik, int* d_status_out, cudaStream_t st) {
+  if constexpr (!KalmanCoopCfg<MT, G>::FITS) { return cudaErrorNotSupported; } else {
+  using C = KalmanCoopCfg<MT, G>;
+  const size_t smem = C::smem_bytes(nobs);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kalman_coop_kernel<MT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const long long grid = (n + C::DRAWS - 1) / C::DRAWS;
+  kalman_coop_kernel<MT, G><<<(unsigned)grid, C::BLOCK, smem, st>>>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out);
+  return cudaGetLastError();
+  }
+}
+
+// lanes per draw of the filter: 1 = one thread per draw (throughput kernel), 4 / 8 = shared-tile kernel with the time update
+// dealt over the lanes, 16 / 32 = every stage of a period dealt over the lanes (kalman_coop.cuh), for batches that leave
+// schedulers idle; `want` = dyb_options.filter_lanes (0 = choose by batch width).  Measured with scripts/small_batch_latency.py
+// (profiles/r02_n_small_batch_coop.txt), ls2003 filter at 2 048 draws: 0.107 ms with 16 lanes, 0.129 with 32, 0.170 with 8,
+// 0.226 with one thread per draw; the 16-lane kernel keeps 2 368 draws resident (242 registers), beyond that a second wave
+// starts and the 4-lane kernel is the faster one (4 096 draws: 0.189 against 0.202 ms)
+#ifndef DYB_COOP32_MAX
+#define DYB_COOP32_MAX 0
+#endif
+#ifndef DYB_COOP16_MAX
+#define DYB_COOP16_MAX 2304
+#endif
 int mt_kalman_lanes(long long n, int nobs, int want) {
+  const bool fits32 = KalmanCoopCfg<MT, 32>::FITS && KalmanCoopCfg<MT, 32>::smem_bytes(nobs) <= 200 * 1024;
+  const bool fits16 = KalmanCoopCfg<MT, 16>::FITS && KalmanCoopCfg<MT, 16>::smem_bytes(nobs) <= 200 * 1024;
   int g = want;
-  if (g != 1 && g != 4 && g != 8) g = (n <= 2048) ? 8 : ((n <= 4096) ? 4 : 1);     // measured: profiles/r02_f_small_batch_lanes.txt
+  if (g != 1 && g != 4 && g != 8 && g != 16 && g != 32) {
+    if (n <= DYB_COOP32_MAX && fits32) g = 32;
+    else if (n <= DYB_COOP16_MAX && fits16) g = 16;
+    else g = (n <= 2048) ? 8 : ((n <= 4096) ? 4 : 1);
+  }
+  if ((g == 32 && !fits32) || (g == 16 && !fits16)) g = 1;
   if (g == 4 && (!KalmanSubCfg<MT, 4>::FITS || KalmanSubCfg<MT, 4>::smem_bytes(nobs) > 200 * 1024)) g = 8;
   if (g == 8 && (!KalmanSubCfg<MT, 8>::FITS || KalmanSubCfg<MT, 8>::smem_bytes(nobs) > 200 * 1024)) g = 1;
   return g;
@@ -190,6 +224,8 @@ cudaError_t mt_kalman(const double* d_ss, long long n, const double* d_Y, int no
   if (n <= 0) return cudaSuccess;
   if constexpr (mt_big) { return cudaErrorNotSupported; } else {
   const int lanes = mt_kalman_lanes(n, nobs, want_lanes);
+  if (lanes == 32) return mt_kalman_coop<32>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out, st);
+  if (lanes == 16) return mt_kalman_coop<16>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out, st);
   if (lanes == 8) return mt_kalman_sub<8>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out, st);
   if (lanes == 4) return mt_kalman_sub<4>(d_ss, n, d_Y, nobs, presample, d_status_in, d_loglik, d_status_out, st);
   using Cfg = KalmanCfg<MT>;

@@ -83,9 +83,11 @@ typedef struct dyb_options {
                                is followed by a Householder pass on the draws it could not verify); 1 one thread per draw (any
                                size; for run-time-size and medium models: the shared-memory kernel instead of the register-
                                blocked one); 2 cooperative solver, Householder pass only */
-  int32_t filter_lanes;     /* lanes per draw of the model-specific Kalman kernel: 0 auto (8 up to 2 048 draws per call, 4 up to
-                             * 4 096, else 1), 1 = one thread per draw (throughput kernel), 4, 8 = shared-tile kernel for batches that
-                             * leave schedulers idle (an SMC stage on a shard); same sums in the same order */
+  int32_t filter_lanes;     /* lanes per draw of the model-specific Kalman kernel: 0 auto (16 up to 2 304 draws per call, 4 up to
+                             * 4 096, else 1), 1 = one thread per draw (throughput kernel), 4, 8 = shared-tile kernel with the time
+                             * update dealt over the lanes, 16, 32 = every stage of a period dealt over the lanes; the small-batch
+                             * kernels are for calls that leave schedulers idle (an SMC stage on a shard); same sums in the same
+                             * order: every variant returns the same bits */
   int32_t univariate_fallback; /* what a period whose innovation covariance F fails its Cholesky factorisation does:
                              * 0 (default) the draw is rejected (status 6, loglik -Inf); 1 the period is processed one observation
                              * at a time, observations with conditional variance <= 1e-10 skipped -- the behaviour of

@@ -38,21 +38,16 @@ struct KalmanCfg {
   static constexpr int MIN_CTAS = DYB_KF_MIN_CTAS;
 };
 
-template <class M>
-__global__ void __launch_bounds__(KalmanCfg<M>::BLOCK, KalmanCfg<M>::MIN_CTAS)
-kalman_kernel(const double* __restrict__ ss, long long n_draws,
-              const double* __restrict__ Y,            // NY x nobs, column-major, NaN = missing
-              int nobs, int presample,
-              const int* __restrict__ status_in,
-              double* __restrict__ loglik, int* __restrict__ status_out) {
+// the recursion of one draw; MISS = false is the instantiation for data without a single missing observation (the pattern
+// is shared by every draw, so the choice is uniform): the neutralising selects of the measurement update are compiled out
+template <class M, bool MISS>
+DYB_D void kalman_draw(const double* __restrict__ ss, long long n_draws, const double* ysh, int nobs, int presample,
+                       const int* __restrict__ status_in, double* __restrict__ loglik, int* __restrict__ status_out) {
   constexpr int NS = M::NS, K = M::K, NY = M::NY;
   using L = SSLayout<M>;
   using Cfg = KalmanCfg<M>;
-  extern __shared__ double ysh[];                      // NY * nobs, then (optionally) QQ_N * BLOCK
-  for (int i = threadIdx.x; i < NY * nobs; i += blockDim.x) ysh[i] = Y[i];
-  double* qsh = ysh + NY * nobs + threadIdx.x;          // this thread's column of the R Q R' tile
+  double* qsh = const_cast<double*>(ysh) + NY * nobs + threadIdx.x;   // this thread's column of the R Q R' tile
   double* psh = qsh + Cfg::QQ_N * Cfg::BLOCK;           // ... and of the P tile (P_SMEM only)
-  __syncthreads();
 
   const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n_draws) return;
@@ -100,7 +95,7 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
 #pragma unroll
     for (int i = 0; i < NY; ++i) {
       const double yi = ysh[i + NY * t];
-      miss[i] = isnan(yi);
+      miss[i] = MISS && isnan(yi);
       nobs_t += miss[i] ? 0 : 1;
       v[i] = miss[i] ? 0.0 : (yi - yb[i] - a[M::obs_idx_state(i)]);
     }
@@ -215,6 +210,21 @@ kalman_kernel(const double* __restrict__ ss, long long n_draws,
     loglik[d] = ll;
     status_out[d] = ST_OK;
   }
+}
+
+template <class M>
+__global__ void __launch_bounds__(KalmanCfg<M>::BLOCK, KalmanCfg<M>::MIN_CTAS)
+kalman_kernel(const double* __restrict__ ss, long long n_draws,
+              const double* __restrict__ Y,            // NY x nobs, column-major, NaN = missing
+              int nobs, int presample,
+              const int* __restrict__ status_in,
+              double* __restrict__ loglik, int* __restrict__ status_out) {
+  extern __shared__ double ysh[];                      // NY * nobs, then (optionally) QQ_N * BLOCK
+  int nan_seen = 0;
+  for (int i = threadIdx.x; i < M::NY * nobs; i += blockDim.x) { const double y = Y[i]; ysh[i] = y; nan_seen |= isnan(y) ? 1 : 0; }
+  const int any_missing = __syncthreads_or(nan_seen);
+  if (any_missing) kalman_draw<M, true>(ss, n_draws, ysh, nobs, presample, status_in, loglik, status_out);
+  else kalman_draw<M, false>(ss, n_draws, ysh, nobs, presample, status_in, loglik, status_out);
 }
 
 }  // namespace dyb

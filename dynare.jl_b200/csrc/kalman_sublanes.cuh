@@ -32,19 +32,18 @@ struct KalmanSubCfg {
   static constexpr size_t smem_bytes(int nobs) { return sizeof(double) * ((size_t)NY * nobs + (size_t)DRAWS * TILE); }
 };
 
-template <class M, int G>
-__global__ void __launch_bounds__(KalmanSubCfg<M, G>::BLOCK)
-kalman_sublanes_kernel(const double* __restrict__ ss, long long n_draws, const double* __restrict__ Y, int nobs,
-                       int presample, const int* __restrict__ status_in, double* __restrict__ loglik,
-                       int* __restrict__ status_out) {
+// the recursion of the CTA's draws; MISS = false: data without a single missing observation (uniform: the pattern is shared
+// by every draw), the neutralising selects of the measurement update compiled out -- as kalman_draw<M, MISS>
+template <class M, int G, bool MISS>
+DYB_D void kalman_sublanes_draws(const double* __restrict__ ss, long long n_draws, double* sm_ks, int nobs,
+                                 int presample, const int* __restrict__ status_in, double* __restrict__ loglik,
+                                 int* __restrict__ status_out) {
   using C = KalmanSubCfg<M, G>;
   using L = SSLayout<M>;
   constexpr int NS = M::NS, K = M::K, NY = M::NY, QQ_N = C::QQ_N, KK_N = C::KK_N;
   constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ double sm_ks[];
-  double* ysh = sm_ks;                                        // NY x nobs
+  double* ysh = sm_ks;                                        // NY x nobs, filled by the kernel
   double* tiles = ysh + (size_t)NY * nobs;
-  for (int i = threadIdx.x; i < NY * nobs; i += blockDim.x) ysh[i] = Y[i];
 
   const int lg = threadIdx.x % G;
   long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -81,7 +80,7 @@ kalman_sublanes_kernel(const double* __restrict__ ss, long long n_draws, const d
 #pragma unroll
     for (int i = 0; i < NY; ++i) {
       const double yi = ysh[i + NY * t];
-      miss[i] = isnan(yi);
+      miss[i] = MISS && isnan(yi);
       nobs_t += miss[i] ? 0 : 1;
       v[i] = miss[i] ? 0.0 : (yi - yb[i] - as[M::obs_idx_state(i)]);
     }
@@ -194,6 +193,19 @@ kalman_sublanes_kernel(const double* __restrict__ ss, long long n_draws, const d
     else if (bad || !isfinite(ll)) { loglik[d] = -INFINITY; status_out[d] = ST_F_NOT_PD; }
     else { loglik[d] = ll; status_out[d] = ST_OK; }
   }
+}
+
+template <class M, int G>
+__global__ void __launch_bounds__(KalmanSubCfg<M, G>::BLOCK)
+kalman_sublanes_kernel(const double* __restrict__ ss, long long n_draws, const double* __restrict__ Y, int nobs,
+                       int presample, const int* __restrict__ status_in, double* __restrict__ loglik,
+                       int* __restrict__ status_out) {
+  extern __shared__ double sm_ks[];
+  int nan_seen = 0;
+  for (int i = threadIdx.x; i < M::NY * nobs; i += blockDim.x) { const double y = Y[i]; sm_ks[i] = y; nan_seen |= isnan(y) ? 1 : 0; }
+  const int any_missing = __syncthreads_or(nan_seen);
+  if (any_missing) kalman_sublanes_draws<M, G, true>(ss, n_draws, sm_ks, nobs, presample, status_in, loglik, status_out);
+  else kalman_sublanes_draws<M, G, false>(ss, n_draws, sm_ks, nobs, presample, status_in, loglik, status_out);
 }
 
 }  // namespace dyb

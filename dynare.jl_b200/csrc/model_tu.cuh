@@ -195,9 +195,9 @@ cudaError_t mt_kalman_coop(const double* d_ss, long long n, const double* d_Y, i
 // lanes per draw of the filter: 1 = one thread per draw (throughput kernel), 4 / 8 = shared-tile kernel with the time update
 // dealt over the lanes, 16 / 32 = every stage of a period dealt over the lanes (kalman_coop.cuh), for batches that leave
 // schedulers idle; `want` = dyb_options.filter_lanes (0 = choose by batch width).  Measured with scripts/small_batch_latency.py
-// (profiles/r02_n_small_batch_coop.txt), ls2003 filter at 2 048 draws: 0.107 ms with 16 lanes, 0.129 with 32, 0.170 with 8,
-// 0.226 with one thread per draw; the 16-lane kernel keeps 2 368 draws resident (242 registers), beyond that a second wave
-// starts and the 4-lane kernel is the faster one (4 096 draws: 0.189 against 0.202 ms)
+// (profiles/r02_n_small_batch_coop.txt), ls2003 filter at 2 048 draws without missing observations: 0.107 ms with 16 lanes,
+// 0.129 with 32, 0.146 with 8, 0.154 with one thread per draw; the 16-lane kernel keeps 2 368 draws resident (242 registers),
+// beyond that a second wave starts (4 096 draws: 0.203 ms) and one thread per draw is the fastest (0.154 ms up to 16 384)
 #ifndef DYB_COOP32_MAX
 #define DYB_COOP32_MAX 0
 #endif
@@ -211,7 +211,7 @@ int mt_kalman_lanes(long long n, int nobs, int want) {
   if (g != 1 && g != 4 && g != 8 && g != 16 && g != 32) {
     if (n <= DYB_COOP32_MAX && fits32) g = 32;
     else if (n <= DYB_COOP16_MAX && fits16) g = 16;
-    else g = (n <= 2048) ? 8 : ((n <= 4096) ? 4 : 1);
+    else g = 1;      // without missing observations one thread per draw (0.154 ms up to 16 384 ls2003 draws) beats 4 / 8 lanes
   }
   if ((g == 32 && !fits32) || (g == 16 && !fits16)) g = 1;
   if (g == 4 && (!KalmanSubCfg<MT, 4>::FITS || KalmanSubCfg<MT, 4>::smem_bytes(nobs) > 200 * 1024)) g = 8;

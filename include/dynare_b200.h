@@ -83,8 +83,7 @@ typedef struct dyb_options {
                                is followed by a Householder pass on the draws it could not verify); 1 one thread per draw (any
                                size; for run-time-size and medium models: the shared-memory kernel instead of the register-
                                blocked one); 2 cooperative solver, Householder pass only */
-  int32_t filter_lanes;     /* lanes per draw of the model-specific Kalman kernel: 0 auto (16 up to 2 304 draws per call, 4 up to
-                             * 4 096, else 1), 1 = one thread per draw (throughput kernel), 4, 8 = shared-tile kernel with the time
+  int32_t filter_lanes;     /* lanes per draw of the model-specific Kalman kernel: 0 auto (16 up to 2 304 draws per call, else 1), 1 = one thread per draw (throughput kernel), 4, 8 = shared-tile kernel with the time
                              * update dealt over the lanes, 16, 32 = every stage of a period dealt over the lanes; the small-batch
                              * kernels are for calls that leave schedulers idle (an SMC stage on a shard); same sums in the same
                              * order: every variant returns the same bits */

@@ -27,6 +27,7 @@ struct GenericHost {
   bool warp_groups = false;    // one warp per draw (small models) instead of one CTA per draw
   bool block = false;          // medium models: register-blocked CTA-per-draw kernel (solve_block.cuh)
   SbLayout sbl{};              // its shared-memory layout
+  bool block_small = false;    // ... and the narrower instantiation fits (m + k + nf <= 80, m + nx <= 80, k + nf <= 48)
   DevBuf bT, bQ, bP, byo, bH, bst, bz;   // persistent work buffers of dyb_loglik_from_jacobian_batch
   DevBuf bJ, byb, bse, bsm, bsi;         // persistent staging of its host inputs
 };
@@ -576,7 +577,11 @@ static int generic_build(dyb_handle* h, const dyb_model_desc* md, dyb_model_dims
     const size_t sb = sizeof(double) * (size_t)gh->sbl.total;
     if (sb + 1024 <= (size_t)max_smem) {
       gh->block = true;
-      if (sb > 48 * 1024) e = cudaFuncSetAttribute(solve_block_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+      gh->block_small = (m + k + nf <= 80) && (m + nx <= 80) && (k + nf <= 48);
+      if (sb > 48 * 1024) {
+        e = cudaFuncSetAttribute(solve_block_kernel<4, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_block_kernel<4, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+      }
     }
   }
   if (e == cudaSuccess) {
@@ -623,7 +628,9 @@ static int generic_solve(dyb_handle* h, GenericSolveArgs a) {
   if (gh->block && h->hs.opt.solver != 1) {      // medium model: one CTA per draw, algebra in registers (solve_block.cuh)
     long long grid = a.n_draws;
     if (grid > 148LL * 64) grid = 148LL * 64;
-    solve_block_kernel<4, 6><<<(unsigned)grid, SB_THREADS, sizeof(double) * (size_t)gh->sbl.total, h->stream>>>(gh->gm, a, gh->sbl);
+    const size_t sb = sizeof(double) * (size_t)gh->sbl.total;
+    if (gh->block_small) solve_block_kernel<4, 5, 3><<<(unsigned)grid, SB_THREADS, sb, h->stream>>>(gh->gm, a, gh->sbl);
+    else solve_block_kernel<4, 6, 4><<<(unsigned)grid, SB_THREADS, sb, h->stream>>>(gh->gm, a, gh->sbl);
   } else if (gh->warp_groups) {                 // small model: one warp per draw, four draws per CTA
     long long grid = (a.n_draws + 3) / 4;
     if (grid > 148LL * 64) grid = 148LL * 64;

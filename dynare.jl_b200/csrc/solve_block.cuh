@@ -94,17 +94,20 @@ DYB_D void sb_block_max3(double& a, double& b, double& c, double* red, int warp,
 }
 
 // Gauss-Jordan elimination with implicit row pivoting of the m x nc array R = [A | B] (A = first m columns), element
-// (ti + 8a, tj + 16b) in R[a][b]; rows >= m and columns >= nc must hold zeros.  On exit the B part of row r holds row
-// dest[a] of A^-1 B.  colbuf: 2 x 8 RPT doubles, prow: 16 CPT doubles.  Returns false (uniformly) on a zero / non-finite
-// pivot.  Ends with a barrier.
+// (ti + 8a, tj + 16b) in R[a][b]; rows >= m and columns >= nc must hold zeros.  A pivot row is NOT normalised when it is
+// used (its multiplier is simply zero in its own step): it stays a multiple of the solution row through the later
+// eliminations and is scaled by rinv[a] = 1 / pivot when it is read out, so the rank-one update of a step is RPT x CPT
+// plain multiply-adds per thread without a select.  Columns already eliminated (c <= p) are updated too: they are never
+// read again.  On exit the B part of row r, times rinv[a], holds row dest[a] of A^-1 B.  colbuf: 2 x 8 RPT doubles,
+// prow: 16 CPT doubles.  Returns false (uniformly) on a zero / non-finite pivot.  Ends with a barrier.
 template <int RPT, int CPT>
-DYB_D bool sb_gauss_jordan(double (&R)[RPT][CPT], int (&dest)[RPT], int m, int nc, double* colbuf, double* prow,
-                           int ti, int tj, int lane) {
+DYB_D bool sb_gauss_jordan(double (&R)[RPT][CPT], int (&dest)[RPT], double (&rinv)[RPT], int m, int nc, double* colbuf,
+                           double* prow, int ti, int tj, int lane) {
   constexpr int MAXM = 8 * RPT;
   unsigned long long used = 0;
   bool ok = true;
 #pragma unroll
-  for (int a = 0; a < RPT; ++a) dest[a] = 0;
+  for (int a = 0; a < RPT; ++a) { dest[a] = 0; rinv[a] = 0.0; }
   if (tj == 0) {
 #pragma unroll
     for (int a = 0; a < RPT; ++a) colbuf[ti + 8 * a] = R[a][0];
@@ -135,35 +138,30 @@ DYB_D bool sb_gauss_jordan(double (&R)[RPT][CPT], int (&dest)[RPT], int m, int n
       const int rs = 63 - (int)(key & 63u);
       const double inv = fast_rcp(cb[rs]);
       used |= 1ull << rs;
-      const int as = rs >> 3;
+      const int as = rs >> 3;                                             // uniform over the CTA
       const bool mine = (ti == (rs & 7));
       if (mine) {
 #pragma unroll
-        for (int b = b0; b < CPT; ++b) {
-          double v = R[0][b];
+        for (int a = 0; a < RPT; ++a) {
+          if (as == a) {
 #pragma unroll
-          for (int a = 1; a < RPT; ++a) v = (as == a) ? R[a][b] : v;
-          prow[tj + 16 * b] = v;
+            for (int b = b0; b < CPT; ++b) prow[tj + 16 * b] = R[a][b];
+          }
         }
       }
       double l[RPT];
-      bool isp[RPT];
 #pragma unroll
       for (int a = 0; a < RPT; ++a) {
-        isp[a] = mine && (as == a);
-        if (isp[a]) dest[a] = p;
-        l[a] = -cb[ti + 8 * a] * inv;
+        const bool isp = mine && (as == a);
+        if (isp) { dest[a] = p; rinv[a] = inv; }
+        l[a] = isp ? 0.0 : -cb[ti + 8 * a] * inv;
       }
       __syncthreads();
 #pragma unroll
       for (int b = b0; b < CPT; ++b) {
-        const int c = tj + 16 * b;
-        if ((b > b0 || tj > pp) && c < nc) {
-          const double pr = prow[c];
-          const double prs = pr * inv;
+        const double pr = prow[tj + 16 * b];
 #pragma unroll
-          for (int a = 0; a < RPT; ++a) R[a][b] = isp[a] ? prs : fma(l[a], pr, R[a][b]);
-        }
+        for (int a = 0; a < RPT; ++a) R[a][b] = fma(l[a], pr, R[a][b]);
       }
       // next pivot column for the following step
       if (p + 1 < m) {
@@ -337,11 +335,12 @@ DYB_D int sb_lyapunov(double* Ak, double* Sg, double* Tm, int k, int ldk, double
   return conv;
 }
 
-template <int RPT, int CPT>
+// RPT / CPT: row / column slots of the Gauss-Jordan array (m <= 8 RPT, m + k + nf <= 16 CPT, m + nx <= 16 CPT); XCB: column
+// slots of the k + nf wide products (k + nf <= 16 XCB); all three are checked on the host, which picks the smallest instantiation
+template <int RPT, int CPT, int XCB>
 __global__ void __launch_bounds__(SB_THREADS, 3)
 solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
   extern __shared__ double sm[];
-  constexpr int XCB = (CPT + 1) / 2 + 1;        // column slots of the k + nf wide products (k + nf <= 16 XCB is checked on the host)
   constexpr int LCB = (RPT + 1) / 2;            // column slots of k x k blocks (k <= 8 RPT)
   const int tid = threadIdx.x, nt = SB_THREADS, lane = tid & 31, warp = tid >> 5;
   const int ti = tid >> 4, tj = tid & 15;
@@ -379,14 +378,23 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
     if (tid == 0) okflag = 1;
     __syncthreads();
     double chk = 0.0;
+    {
+      // eight coalesced loads in flight per thread (the Jacobian is the one large global read of a draw: n x ncol doubles)
+      const int tot = n * NCOL;
 #pragma unroll 1
-    for (int c = warp; c < NCOL; c += 4) {
-      const int wc = gm.jperm[c];
-#pragma unroll 1
-      for (int r = lane; r < n; r += 32) {
-        const double v = J[r + n * c];
-        chk = fma(v, 0.0, chk);
-        W[r + ldw * wc] = v;
+      for (int e0 = tid; e0 < tot; e0 += 8 * nt) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int e = e0 + u * nt; v[u] = e < tot ? J[e] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * nt;
+          if (e < tot) {
+            const int c = e / n, r = e - c * n;
+            chk = fma(v[u], 0.0, chk);
+            W[r + ldw * gm.jperm[c]] = v[u];
+          }
+        }
       }
     }
 #pragma unroll 1
@@ -445,6 +453,7 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
       for (it = 1; it <= a.cr_maxit; ++it) {
         double R[RPT][CPT];
         int dest[RPT];
+        double rinv[RPT];
 #pragma unroll
         for (int q = 0; q < RPT; ++q)
 #pragma unroll
@@ -458,7 +467,7 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
             }
             R[q][b] = v;
           }
-        const bool okq = sb_gauss_jordan<RPT, CPT>(R, dest, MM, nc, colbuf, prow, ti, tj, lane);
+        const bool okq = sb_gauss_jordan<RPT, CPT>(R, dest, rinv, MM, nc, colbuf, prow, ti, tj, lane);
         if (!okq) { if (it == 1) status = ST_SOLVER; else stalled = true; break; }
         // X = A1^-1 [A0 | A2], rows back in order
 #pragma unroll
@@ -466,7 +475,7 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
 #pragma unroll
           for (int b = 0; b < CPT; ++b) {
             const int r = ti + 8 * q, c = tj + 16 * b;
-            if (r < MM && c >= MM && c < nc) X[dest[q] + ldm * (c - MM)] = R[q][b];
+            if (r < MM && c >= MM && c < nc) X[dest[q] + ldm * (c - MM)] = R[q][b] * rinv[q];
           }
         __syncthreads();
         // [W00 | W01] = A0 X[bk, :],  [W10 | W11] = A2 X[fw, :]
@@ -530,6 +539,7 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
       // ---- G (dynamic rows, backward columns) = -A1hat^-1 A0(0),  A1hat = A1(0) - acc_hat on the backward columns ------
       double R[RPT][CPT];
       int dest[RPT];
+      double rinv[RPT];
       const int nc = MM + K;
 #pragma unroll
       for (int q = 0; q < RPT; ++q)
@@ -543,14 +553,14 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
           }
           R[q][b] = v;
         }
-      if (!sb_gauss_jordan<RPT, CPT>(R, dest, MM, nc, colbuf, prow, ti, tj, lane)) status = ST_SOLVER;
+      if (!sb_gauss_jordan<RPT, CPT>(R, dest, rinv, MM, nc, colbuf, prow, ti, tj, lane)) status = ST_SOLVER;
       else {
 #pragma unroll
         for (int q = 0; q < RPT; ++q)
 #pragma unroll
           for (int b = 0; b < CPT; ++b) {
             const int r = ti + 8 * q, c = tj + 16 * b;
-            if (r < MM && c >= MM && c < nc) Gd[dest[q] + ldm * (c - MM)] = R[q][b];
+            if (r < MM && c >= MM && c < nc) Gd[dest[q] + ldm * (c - MM)] = R[q][b] * rinv[q];
           }
       }
     }
@@ -569,6 +579,7 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
       __syncthreads();
       double R[RPT][CPT];
       int dest[RPT];
+      double rinv[RPT];
       const int nc = MM + nx;
 #pragma unroll
       for (int q = 0; q < RPT; ++q)
@@ -582,14 +593,14 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
           }
           R[q][b] = v;
         }
-      if (!sb_gauss_jordan<RPT, CPT>(R, dest, MM, nc, colbuf, prow, ti, tj, lane)) status = ST_SOLVER;
+      if (!sb_gauss_jordan<RPT, CPT>(R, dest, rinv, MM, nc, colbuf, prow, ti, tj, lane)) status = ST_SOLVER;
       else {
 #pragma unroll
         for (int q = 0; q < RPT; ++q)
 #pragma unroll
           for (int b = 0; b < CPT; ++b) {
             const int r = ti + 8 * q, c = tj + 16 * b;
-            if (r < MM && c >= MM && c < nc) gud[dest[q] + ldm * (c - MM)] = R[q][b];
+            if (r < MM && c >= MM && c < nc) gud[dest[q] + ldm * (c - MM)] = R[q][b] * rinv[q];
           }
       }
     }

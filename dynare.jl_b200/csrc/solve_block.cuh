@@ -121,22 +121,32 @@ DYB_D bool sb_gauss_jordan(double (&R)[RPT][CPT], int (&dest)[RPT], double (&rin
       if (p >= m || !ok) break;
       const double* cb = colbuf + (p & 1) * MAXM;
       double* cbn = colbuf + ((p + 1) & 1) * MAXM;
-      // pivot row: largest magnitude among the rows not used yet (top 25 bits of |x|, row index in the low 6 bits of the key)
+      // pivot row: largest magnitude among the rows not used yet (top 25 bits of |x|, row index in the low 6 bits of the key).
+      // Every lane also takes the reciprocal of ITS candidate while the keys are being reduced, so that the winner's
+      // reciprocal is one shuffle away instead of a dependent load + MUFU + two Newton steps after the reduction
       unsigned key = 0;
+      double cand[(MAXM + 31) / 32], cinv[(MAXM + 31) / 32];
 #pragma unroll
       for (int h = 0; h < (MAXM + 31) / 32; ++h) {
         const int r = lane + 32 * h;
+        cand[h] = r < m ? cb[r] : 1.0;
+        cinv[h] = fast_rcp(cand[h]);
         if (r < m && !((used >> r) & 1ull)) {
-          const unsigned hi = (unsigned)__double2hiint(cb[r]) & 0x7fffffffu;
+          const unsigned hi = (unsigned)__double2hiint(cand[h]) & 0x7fffffffu;
           const unsigned kk = (hi & ~63u) | (unsigned)(63 - r);
           key = kk > key ? kk : key;
         }
       }
+      double lraw[RPT];
+#pragma unroll
+      for (int a = 0; a < RPT; ++a) lraw[a] = -cb[ti + 8 * a];
       key = __reduce_max_sync(0xffffffffu, key);
       const unsigned expo = key >> 20;
       if (expo == 0u || expo >= 0x7ffu) { ok = false; break; }          // zero / subnormal / Inf / NaN pivot column
       const int rs = 63 - (int)(key & 63u);
-      const double inv = fast_rcp(cb[rs]);
+      double inv = __shfl_sync(0xffffffffu, cinv[0], rs & 31);
+#pragma unroll
+      for (int h = 1; h < (MAXM + 31) / 32; ++h) { const double o = __shfl_sync(0xffffffffu, cinv[h], rs & 31); if ((rs >> 5) == h) inv = o; }
       used |= 1ull << rs;
       const int as = rs >> 3;                                             // uniform over the CTA
       const bool mine = (ti == (rs & 7));
@@ -154,7 +164,7 @@ DYB_D bool sb_gauss_jordan(double (&R)[RPT][CPT], int (&dest)[RPT], double (&rin
       for (int a = 0; a < RPT; ++a) {
         const bool isp = mine && (as == a);
         if (isp) { dest[a] = p; rinv[a] = inv; }
-        l[a] = isp ? 0.0 : -cb[ti + 8 * a] * inv;
+        l[a] = isp ? 0.0 : lraw[a] * inv;
       }
       __syncthreads();
 #pragma unroll

@@ -438,8 +438,16 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
         for (int i = j + 1; i < n; ++i) dot = fma(col[i], x[i], dot);
         dot *= beta;
         x[j] = fma(-dot, vj, x[j]);
-#pragma unroll 4
-        for (int i = j + 1; i < n; ++i) x[i] = fma(-dot, col[i], x[i]);
+        // eight elements at a time, loads before stores: x and col are one array to the compiler, so a store to x[i]
+        // inside the loop orders the loads of x[i + 1], col[i + 1] behind it (one shared-memory round trip per element)
+#pragma unroll 1
+        for (int i0 = j + 1; i0 < n; i0 += 8) {
+          double xv[8], cv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const int ii = i0 + u < n ? i0 + u : n - 1; xv[u] = x[ii]; cv[u] = col[ii]; }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) if (i0 + u < n) x[i0 + u] = fma(-dot, cv[u], xv[u]);
+        }
       }
       __syncthreads();
       if (tid == 0) col[j] = alpha;

@@ -28,6 +28,7 @@ struct GenericHost {
   bool block = false;          // medium models: register-blocked CTA-per-draw kernel (solve_block.cuh)
   SbLayout sbl{};              // its shared-memory layout
   bool block_small = false;    // ... and the narrower instantiation fits (m + k + nf <= 80, m + nx <= 80, k + nf <= 48)
+  DevBuf wscr;                 // its global scratch: the working Jacobian after the static elimination, SB_GRID CTAs
   DevBuf bT, bQ, bP, byo, bH, bst, bz;   // persistent work buffers of dyb_loglik_from_jacobian_batch
   DevBuf bJ, byb, bse, bsm, bsi;         // persistent staging of its host inputs
 };
@@ -35,6 +36,7 @@ struct GenericHost {
 void generic_release(dyb_handle* h) {
   if (h && h->generic) {
     h->generic->d_idx.release();
+    h->generic->wscr.release();
     DevBuf* all[] = {&h->generic->bT, &h->generic->bQ, &h->generic->bP, &h->generic->byo, &h->generic->bH, &h->generic->bst,
                      &h->generic->bz, &h->generic->bJ, &h->generic->byb, &h->generic->bse, &h->generic->bsm, &h->generic->bsi};
     for (DevBuf* b : all) b->release();
@@ -577,8 +579,9 @@ static int generic_build(dyb_handle* h, const dyb_model_desc* md, dyb_model_dims
     const size_t sb = sizeof(double) * (size_t)gh->sbl.total;
     if (sb + 1024 <= (size_t)max_smem) {
       gh->block = true;
+      e = gh->wscr.reserve(sizeof(double) * (size_t)gh->sbl.wdoubles * SB_GRID);
       gh->block_small = (m + k + nf <= 80) && (m + nx <= 80) && (k + nf <= 48);
-      if (sb > 48 * 1024) {
+      if (e == cudaSuccess && sb > 48 * 1024) {
         e = cudaFuncSetAttribute(solve_block_kernel<4, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_block_kernel<4, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
       }
@@ -591,7 +594,7 @@ static int generic_build(dyb_handle* h, const dyb_model_desc* md, dyb_model_dims
       e = cudaFuncSetAttribute(solve_generic_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
   }
-  if (e != cudaSuccess) { gh->d_idx.release(); delete gh; return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { gh->d_idx.release(); gh->wscr.release(); delete gh; return fail(DYB_ERR_CUDA, cudaGetErrorString(e)); }
   h->generic = gh;
   if (dims_out) *dims_out = dyb_model_dims{n, nx, 0, k, nf, s, ncol, ns, ny, 0, 0, 0};
   return DYB_OK;
@@ -627,7 +630,8 @@ static int generic_solve(dyb_handle* h, GenericSolveArgs a) {
   const int per_draw = (int)(gh->smem / sizeof(double));
   if (gh->block && h->hs.opt.solver != 1) {      // medium model: one CTA per draw, algebra in registers (solve_block.cuh)
     long long grid = a.n_draws;
-    if (grid > 148LL * 64) grid = 148LL * 64;
+    if (grid > SB_GRID) grid = SB_GRID;
+    a.wscratch = gh->wscr.as<double>();
     const size_t sb = sizeof(double) * (size_t)gh->sbl.total;
     if (gh->block_small) solve_block_kernel<4, 5, 3><<<(unsigned)grid, SB_THREADS, sb, h->stream>>>(gh->gm, a, gh->sbl);
     else solve_block_kernel<4, 6, 4><<<(unsigned)grid, SB_THREADS, sb, h->stream>>>(gh->gm, a, gh->sbl);

@@ -19,24 +19,32 @@
 namespace dyb {
 
 constexpr int SB_THREADS = 128;      // 8 x 16 thread grid
+constexpr int SB_GRID = 148 * 6;     // CTAs of a launch (each walks over its draws); sizes the global scratch
 
 struct SbLayout {
   int ldw, ldm, lds, ldk, ldn;                                   // odd leading dimensions
-  int oW, oU, oGd, oGud, oGst, oGG, oSe, oCol, oRow, oRed, oInt; // offsets in doubles
+  int oW, oU, oGd, oGud, oGst, oSe, oCol, oRow, oRed, oInt;      // offsets in doubles (oW == oU: one region, three lives)
   int uA1, uA0, uA2, uACC, uX;                                   // inside U while the cyclic reduction runs
+  int uWt, uGG;                                                  // inside U for the static rows: top S rows of W, G[fw,:] [G | g_u]
   int uAk, uSg, uTm, uBs, uBQ, uG1s, uGS, uG2s, uRQ;             // inside U afterwards
   int total;                                                     // doubles
+  int wdoubles;                                                  // global scratch per CTA: the working Jacobian after the QR
 };
 
 DYB_HD int sb_odd(int x) { return x | 1; }
 
-// maxm = 8 RPT, maxc = 16 CPT of the instantiation that will run
+// maxm = 8 RPT, maxc = 16 CPT of the instantiation that will run.
+// The working Jacobian W (n x ncol) is in shared memory only while it is read in and reduced by the Householder QR on the
+// static columns; it is then written to a per-CTA global scratch (L2-resident: 39 KB per CTA for mc4) and the same region
+// holds, in turn, the cyclic-reduction state, the top rows of W for the static back-substitution and the Lyapunov / state-space
+// work arrays.  112 -> 66 KB per draw for mc4, i.e. three CTAs per SM instead of two for a kernel that is latency-bound.
 inline __host__ __device__ SbLayout sb_layout(int n, int nx, int s, int k, int nf, int ns, int maxm, int maxc) {
   SbLayout L;
   const int m = n - s, ncol = s + k + m + nf + nx;
   L.ldw = sb_odd(n); L.ldm = sb_odd(m); L.lds = sb_odd(s > 0 ? s : 1); L.ldk = sb_odd(k); L.ldn = sb_odd(ns);
+  L.wdoubles = L.ldw * ncol;
   int o = 0;
-  L.oW = o; o += L.ldw * ncol;
+  L.oW = o;
   L.oU = o;
   {
     int u = 0;
@@ -47,6 +55,10 @@ inline __host__ __device__ SbLayout sb_layout(int n, int nx, int s, int k, int n
     L.uX = u; u += L.ldm * (k + nf);
     const int cr = u;
     u = 0;
+    L.uWt = u; u += L.lds * ncol;
+    L.uGG = u; u += (nf > 0 ? nf : 1) * (k + nx);
+    const int st = u;
+    u = 0;
     L.uAk = u; u += L.ldk * k;
     L.uSg = u; u += L.ldk * k;
     L.uTm = u; u += L.ldk * k;
@@ -56,12 +68,13 @@ inline __host__ __device__ SbLayout sb_layout(int n, int nx, int s, int k, int n
     L.uGS = u; u += L.ldn * k;
     L.uG2s = u; u += L.ldn * nx;
     L.uRQ = u; u += L.ldn * nx;
-    o += cr > u ? cr : u;
+    int x = L.wdoubles;
+    x = cr > x ? cr : x; x = st > x ? st : x; x = u > x ? u : x;
+    o += x;
   }
   L.oGd = o; o += L.ldm * k;
   L.oGud = o; o += L.ldm * nx;
   L.oGst = o; o += L.lds * (k + nx);
-  L.oGG = o; o += (nf > 0 ? nf : 1) * (k + nx);
   L.oSe = o; o += nx * nx;
   L.oCol = o; o += 2 * maxm;
   L.oRow = o; o += maxc;
@@ -362,7 +375,9 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
   double* A1 = U + L.uA1; double* A0 = U + L.uA0; double* A2 = U + L.uA2; double* ACC = U + L.uACC; double* X = U + L.uX;
   double* Ak = U + L.uAk; double* Sg = U + L.uSg; double* Tm = U + L.uTm; double* Bs = U + L.uBs; double* BQ = U + L.uBQ;
   double* g1s = U + L.uG1s; double* GS = U + L.uGS; double* g2s = U + L.uG2s; double* RQ = U + L.uRQ;
-  double* Gd = sm + L.oGd; double* gud = sm + L.oGud; double* gst = sm + L.oGst; double* GG = sm + L.oGG;
+  double* Gd = sm + L.oGd; double* gud = sm + L.oGud; double* gst = sm + L.oGst; double* GG = U + L.uGG;
+  double* Wt = U + L.uWt;                       // top S rows of W (leading dimension lds) while the static rows are solved
+  double* Wg = a.wscratch + (size_t)blockIdx.x * L.wdoubles;    // W after the QR (leading dimension ldw)
   double* Se = sm + L.oSe; double* colbuf = sm + L.oCol; double* prow = sm + L.oRow; double* red = sm + L.oRed;
   int* bk = reinterpret_cast<int*>(sm + L.oInt);
   int* fw = bk + K;
@@ -453,16 +468,22 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
       if (tid == 0) col[j] = alpha;
     }
     __syncthreads();
+    // W leaves shared memory: its region is the cyclic reduction's from here on
+    if (status == ST_OK) {
+#pragma unroll 4
+      for (int e = tid; e < L.wdoubles; e += nt) Wg[e] = W[e];
+    }
+    __syncthreads();
 
     // ---- cyclic reduction on the MM x MM dynamic block --------------------------------------------------------
     int it = 0;
     if (status == ST_OK) {
 #pragma unroll 1
-      for (int e = tid; e < MM * K; e += nt) { const int r = e % MM, j = e / MM; A0[r + ldm * j] = W[S + r + ldw * (cC + j)]; ACC[r + ldm * j] = 0.0; }
+      for (int e = tid; e < MM * K; e += nt) { const int r = e % MM, j = e / MM; A0[r + ldm * j] = Wg[S + r + ldw * (cC + j)]; ACC[r + ldm * j] = 0.0; }
 #pragma unroll 1
-      for (int e = tid; e < MM * NF; e += nt) { const int r = e % MM, j = e / MM; A2[r + ldm * j] = W[S + r + ldw * (cA + j)]; }
+      for (int e = tid; e < MM * NF; e += nt) { const int r = e % MM, j = e / MM; A2[r + ldm * j] = Wg[S + r + ldw * (cA + j)]; }
 #pragma unroll 1
-      for (int e = tid; e < MM * MM; e += nt) { const int r = e % MM, c = e / MM; A1[r + ldm * c] = W[S + r + ldw * (cB + c)]; }
+      for (int e = tid; e < MM * MM; e += nt) { const int r = e % MM, c = e / MM; A1[r + ldm * c] = Wg[S + r + ldw * (cB + c)]; }
       __syncthreads();
       bool conv = false, stalled = false;
       double n0 = 0.0, n2 = 0.0;
@@ -566,8 +587,8 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
           const int r = ti + 8 * q, c = tj + 16 * b;
           double v = 0.0;
           if (r < MM) {
-            if (c < MM) { v = W[S + r + ldw * (cB + c)]; const int jb = bkof[c]; if (jb >= 0) v -= ACC[r + ldm * jb]; }
-            else if (c < nc) v = -W[S + r + ldw * (cC + (c - MM))];
+            if (c < MM) { v = Wg[S + r + ldw * (cB + c)]; const int jb = bkof[c]; if (jb >= 0) v -= ACC[r + ldm * jb]; }
+            else if (c < nc) v = -Wg[S + r + ldw * (cC + (c - MM))];
           }
           R[q][b] = v;
         }
@@ -586,7 +607,7 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
     if (status == ST_OK) {
       // ---- g_u = -(A G + B)^-1 F_u on the dynamic block ---------------------------------------------------------
       double t[RPT][LCB];
-      sb_gemm<RPT, LCB>(t, W + S + ldw * cA, ldw, Gd, ldm, fw, NF, MM, K, ti, tj);       // A2(0) G[fw, :] -> X as staging
+      sb_gemm<RPT, LCB>(t, Wg + S + ldw * cA, ldw, Gd, ldm, fw, NF, MM, K, ti, tj);       // A2(0) G[fw, :] -> X as staging
 #pragma unroll
       for (int q = 0; q < RPT; ++q)
 #pragma unroll
@@ -606,8 +627,8 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
           const int r = ti + 8 * q, c = tj + 16 * b;
           double v = 0.0;
           if (r < MM) {
-            if (c < MM) { v = W[S + r + ldw * (cB + c)]; const int jb = bkof[c]; if (jb >= 0) v += X[r + ldm * jb]; }
-            else if (c < nc) v = -W[S + r + ldw * (cU + (c - MM))];
+            if (c < MM) { v = Wg[S + r + ldw * (cB + c)]; const int jb = bkof[c]; if (jb >= 0) v += X[r + ldm * jb]; }
+            else if (c < nc) v = -Wg[S + r + ldw * (cU + (c - MM))];
           }
           R[q][b] = v;
         }
@@ -625,6 +646,9 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
     __syncthreads();
     if (status == ST_OK && S > 0) {
       // ---- static rows by back-substitution: R_s y_s + B_top y_d + A_top y_f(+1) + C_top y_b(-1) + Fu_top u = 0 ---
+      // the top S rows of W come back from the scratch into the region the cyclic reduction has left
+#pragma unroll 4
+      for (int e = tid; e < S * NCOL; e += nt) { const int q = e % S, c = e / S; Wt[q + lds * c] = Wg[q + ldw * c]; }
 #pragma unroll 1
       for (int e = tid; e < NF * (K + nx); e += nt) {
         const int i = e % NF, c = e / NF;
@@ -641,11 +665,11 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
       for (int e = tid; e < S * (K + nx); e += nt) {
         const int q = e % S, c = e / S;
         const double* gcol = (c < K) ? (Gd + ldm * c) : (gud + ldm * (c - K));
-        double s = (c < K) ? W[q + ldw * (cC + c)] : W[q + ldw * (cU + (c - K))];
+        double s = (c < K) ? Wt[q + lds * (cC + c)] : Wt[q + lds * (cU + (c - K))];
 #pragma unroll 4
-        for (int dd = 0; dd < MM; ++dd) s = fma(W[q + ldw * (cB + dd)], gcol[dd], s);
+        for (int dd = 0; dd < MM; ++dd) s = fma(Wt[q + lds * (cB + dd)], gcol[dd], s);
 #pragma unroll 4
-        for (int i = 0; i < NF; ++i) s = fma(W[q + ldw * (cA + i)], GG[i + NF * c], s);
+        for (int i = 0; i < NF; ++i) s = fma(Wt[q + lds * (cA + i)], GG[i + NF * c], s);
         gst[q + lds * c] = -s;
       }
       __syncthreads();
@@ -655,8 +679,8 @@ solve_block_kernel(GenericModel gm, GenericSolveArgs a, SbLayout L) {
         for (int q = S - 1; q >= 0; --q) {
           double s = gst[q + lds * c];
 #pragma unroll 1
-          for (int r = q + 1; r < S; ++r) s = fma(-W[q + ldw * r], gst[r + lds * c], s);
-          const double dg = W[q + ldw * q];
+          for (int r = q + 1; r < S; ++r) s = fma(-Wt[q + lds * r], gst[r + lds * c], s);
+          const double dg = Wt[q + lds * q];
           if (dg == 0.0) okflag = 0;
           gst[q + lds * c] = s / dg;
         }

@@ -38,6 +38,7 @@ struct GenericSolveArgs {
   double* T; double* RQR; double* P0; double* ybar_obs; double* H;   // per draw ns*ns, ns*ns, ns*ns, ny, ny*ny
   double* g1;                // n x (k+nx) per draw
   int* status; int* cr_iters; int* lyap_iters;
+  double* wscratch;          // solve_block_kernel only: SbLayout::wdoubles per CTA (set by the launcher)
 };
 
 // A draw is worked on by a GROUP of GSZ threads: one warp (GSZ = 32, several draws per CTA, __syncwarp between phases)

@@ -90,6 +90,9 @@ static cudaError_t launch_kalman_generic(KalmanGenericArgs g, int device, cudaSt
           cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
           if (e != cudaSuccess) return e;
         }
+        // up to four tiles (five CTAs per SM by registers): the whole L1 / shared array as shared memory, the default carve-out
+        // stops at four CTAs (ns = 30: 12.9 -> 12.6 ms per 8 192 draws; larger CTAs keep the L1: ns = 40 measured 2 % slower without)
+        if (ntile <= 4) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         kern<<<(unsigned)grid, 32 * (ntile + 1), smem_f, st>>>(g, q);
         return cudaGetLastError();
       };

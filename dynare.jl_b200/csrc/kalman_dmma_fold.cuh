@@ -163,7 +163,7 @@ __device__ __noinline__ void fold_scalar_role(const FoldScalarArgs A) {
 // program locations); their register sets do not add up.
 
 template <int NT>
-__global__ void __launch_bounds__(32 * (NT + 1), (NT <= 3 ? 6 : (NT <= 5 ? 4 : (NT <= 8 ? 2 : 1))))
+__global__ void __launch_bounds__(32 * (NT + 1), (NT <= 3 ? 6 : (NT <= 4 ? 5 : (NT <= 5 ? 4 : (NT <= 8 ? 2 : 1)))))
 kalman_dmma_fold_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
   extern __shared__ double sm[];
   constexpr unsigned FULL = 0xffffffffu;

@@ -271,7 +271,11 @@ kalman_dmma_fold_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
       }
     } else {
       // ================= tensor-core role ======================================================================================
-      const int gq = lane >> 2, tq = lane & 3, i0 = 8 * warp;
+      // strip of this warp: rotated with the CTA index, so that the warps with the most tiles of the triangular second
+      // product (strip NT - 1: NT tiles, strip 0: one) do not all sit on the same SM sub-partition (warp w of every CTA does)
+      const int ws = __reduce_max_sync(FULL, (warp + (int)(blockIdx.x % NT)) % NT);
+      const int gq = lane >> 2, tq = lane & 3, i0 = 8 * ws;
+      const int vtid = 32 * ws + lane;                  // rows of V: the strips with the fewest tiles first
       const double* aT = Ts + (i0 + gq) + LD * tq;      // A fragment of T:  aT[LD k0]
       const double* bP = Ps + tq + LD * gq;             // B fragment of P:  bP[k0 + 8 LD jt]
       const double* aM = Ms + (i0 + gq) + LD * tq;      // A fragment of M:  aM[LD k0]
@@ -304,7 +308,7 @@ kalman_dmma_fold_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
 #pragma unroll
         for (int jt = 0; jt < NT; ++jt) {
           c[jt][0] = 0.0; c[jt][1] = 0.0;
-          if (jt <= wu) {
+          if (jt <= ws) {
             const int j = 8 * jt + qj;
             if (qi < ns && j < ns) c[jt][0] = qp[(size_t)ns * (8 * jt)];
             if (qi < ns && j + 1 < ns) c[jt][1] = qp[(size_t)ns * (8 * jt + 1)];
@@ -312,11 +316,11 @@ kalman_dmma_fold_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
         }
         fold_bar();                                      // M, L and the missing-data pattern are ready
         // ---- V = M[:, z] L^-T: thread s < ns, i.e. the warps with the fewest tiles of the second product --------------------
-        if (tid < ns) {
+        if (vtid < ns) {
           const unsigned ms = (unsigned)miss_sh;
-          const double xa = small ? fold_gain_row<8>(tid, ny, LD, ldu, ms, zi, Ms, F, rdv, w, V)
-                                  : fold_gain_row<0>(tid, ny, LD, ldu, ms, zi, Ms, F, rdv, w, V);
-          anew[tid] = xa;
+          const double xa = small ? fold_gain_row<8>(vtid, ny, LD, ldu, ms, zi, Ms, F, rdv, w, V)
+                                  : fold_gain_row<0>(vtid, ny, LD, ldu, ms, zi, Ms, F, rdv, w, V);
+          anew[vtid] = xa;
         }
         // ---- T a: four lanes per row ----------------------------------------------------------------------------------------
         double ta = 0.0;
@@ -330,7 +334,7 @@ kalman_dmma_fold_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
           const double av = aM[LD * k0];
 #pragma unroll
           for (int jt = 0; jt < NT; ++jt)
-            if (jt <= wu) dmma884(c[jt][0], c[jt][1], av, bT[8 * jt + LD * k0]);
+            if (jt <= ws) dmma884(c[jt][0], c[jt][1], av, bT[8 * jt + LD * k0]);
         }
         fold_bar();                                      // V and V w are ready
         if ((tid & 3) == 0 && (tid >> 2) < ns) anew[tid >> 2] += ta;
@@ -339,12 +343,12 @@ kalman_dmma_fold_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
           const double av = -vA[k0];
 #pragma unroll
           for (int jt = 0; jt < NT; ++jt)
-            if (jt <= wu) dmma884(c[jt][0], c[jt][1], av, vB[k0 + 8 * ldu * jt]);
+            if (jt <= ws) dmma884(c[jt][0], c[jt][1], av, vB[k0 + 8 * ldu * jt]);
         }
 #pragma unroll
         for (int jt = 0; jt < NT; ++jt)
-          if (jt <= wu) {
-            if (jt < wu) {
+          if (jt <= ws) {
+            if (jt < ws) {
               sP[8 * LD * jt] = c[jt][0]; sP[8 * LD * jt + LD] = c[jt][1];
               sPm[8 * jt] = c[jt][0]; sPm[8 * jt + 1] = c[jt][1];
             } else {                            // diagonal tile: keep the lower triangle, mirror it

@@ -114,16 +114,14 @@ __device__ __noinline__ void fold_scalar_role(const FoldScalarArgs A) {
       const double lij = (lane == j) ? dj * r : f[j] * r;
       f[j] = lij;
       if (lane == j) { rd = r; ldiag = lij; }
+      // forward substitution w = L^-1 v in step with the factorisation (lane j's x is final at step j): off the critical path
+      const double wj = __shfl_sync(FULL, x * r, j);
+      if (lane > j) x = fma(-lij, wj, x);
 #pragma unroll
       for (int cc = j + 1; cc < NY; ++cc) {
         const double lcj = __shfl_sync(FULL, lij, cc);
         f[cc] = fma(-lij, lcj, f[cc]);
       }
-    }
-#pragma unroll
-    for (int j = 0; j < NY; ++j) {
-      const double wj = __shfl_sync(FULL, x * rd, j);
-      if (lane > j) x = fma(-f[j], wj, x);
     }
     const double wi = x * rd;
     if (act) {

@@ -269,9 +269,11 @@ kalman_dmma_fold_kernel(KalmanGenericArgs g, KalmanDmmaGeom q) {
       }
     } else {
       // ================= tensor-core role ======================================================================================
-      // strip of this warp: rotated with the CTA index, so that the warps with the most tiles of the triangular second
-      // product (strip NT - 1: NT tiles, strip 0: one) do not all sit on the same SM sub-partition (warp w of every CTA does)
-      const int ws = __reduce_max_sync(FULL, (warp + (int)(blockIdx.x % NT)) % NT);
+      // strip of this warp: for NT <= 4 rotated with the CTA index, so that the warps with the most tiles of the triangular
+      // second product (strip NT - 1: NT tiles, strip 0: one) do not all sit on the same SM sub-partition (warp w of every
+      // CTA does); measured: ns = 24 / 30 6 % / 3 % faster, ns = 40 (NT = 5: five tensor warps already straddle the four
+      // sub-partitions) 1.4 % slower, hence the limit
+      const int ws = __reduce_max_sync(FULL, NT <= 4 ? (warp + (int)(blockIdx.x % NT)) % NT : warp);
       const int gq = lane >> 2, tq = lane & 3, i0 = 8 * ws;
       const int vtid = 32 * ws + lane;                  // rows of V: the strips with the fewest tiles first
       const double* aT = Ts + (i0 + gq) + LD * tq;      // A fragment of T:  aT[LD k0]

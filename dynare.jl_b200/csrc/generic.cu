@@ -584,6 +584,8 @@ static int generic_build(dyb_handle* h, const dyb_model_desc* md, dyb_model_dims
       gh->block = true;
       e = gh->wscr.reserve(sizeof(double) * (size_t)gh->sbl.wdoubles * SB_GRID);
       gh->block_small = (m + k + nf <= 80) && (m + nx <= 80) && (k + nf <= 48);
+      // test hook: DYB_SB_WIDE=1 in the environment when the handle is built forces the wide instantiation <4, 6, 4>
+      if (const char* wide = std::getenv("DYB_SB_WIDE")) { if (wide[0] == '1') gh->block_small = false; }
       if (e == cudaSuccess && sb > 48 * 1024) {
         e = cudaFuncSetAttribute(solve_block_kernel<4, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_block_kernel<4, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);

@@ -71,3 +71,25 @@ def test_mc4_register_blocked_solver_matches_the_shared_memory_solver(golden):
         assert np.abs(out[0][2][k][ok] - out[1][2][k][ok]).max() <= 1e-10
     assert np.array_equal(out[0][2]["cr_iters"][ok], out[1][2]["cr_iters"][ok])
     ws.close()
+
+
+def test_mc4_wide_instantiation_of_the_register_blocked_solver(golden, monkeypatch):
+    """mc4 fits the narrow instantiation solve_block_kernel<4,5,3>; the wide one <4,6,4> (models with m + k + nf > 80 or
+    k + nf > 48) is forced through the library's test hook and must return the same bits: every element of the Gauss-Jordan
+    array and of the products sees the same operations, only the number of (zero) padding columns differs."""
+    from dynare_jl_b200.engine import BatchSSWs
+    g = golden("mc4")
+    ws = BatchSSWs("mc4", g["Y"])
+    ll0, st0 = ws.loglikelihood(g["theta"])
+    fo0 = ws.first_order(g["theta"])
+    ws.close()
+    monkeypatch.setenv("DYB_SB_WIDE", "1")
+    ws = BatchSSWs("mc4", g["Y"])
+    ll1, st1 = ws.loglikelihood(g["theta"])
+    fo1 = ws.first_order(g["theta"])
+    ws.close()
+    assert np.array_equal(st0, st1) and np.array_equal(st0, g["status"])
+    ok = st0 == 0
+    assert np.array_equal(ll0[ok], ll1[ok])
+    for k in ("g1_1", "g1_2"):
+        assert np.array_equal(fo0[k][ok], fo1[k][ok])

@@ -151,7 +151,7 @@ __global__ void smc_moment_kernel(const double* __restrict__ para, const double*
 // Particle e of the block sits at column e + e / 32, so that the 32 lanes of a warp (runs 32 apart) hit distinct banks.
 // launch <<<dim3(blocks, groups), dim3(32, SMC_MOM_TILE), smc_moment2_smem_bytes(np)>>>; group g owns components
 // c = g, g + groups, ... spread over the CTA's warps.
-constexpr int SMC_MOM_LD = SMC_BLOCK + SMC_BLOCK / 32;
+constexpr int SMC_MOM_LD = SMC_BLOCK + SMC_BLOCK / 32 + 1;     // odd: the staging stores of one particle's components (stride LD) hit distinct banks (an even LD made them np-way conflicts)
 inline size_t smc_moment2_smem_bytes(int np) { return sizeof(double) * (size_t)(np + 1) * SMC_MOM_LD; }
 __global__ void smc_moment2_staged_kernel(const double* __restrict__ para, const double* __restrict__ w,
                                           const double* __restrict__ mu, long long n, int np,

@@ -20,16 +20,19 @@
 
 namespace dyb {
 
+// minimum CTAs per SM the register allocation aims at.  Measured on the headline (bench.py, two batches in flight) after
+// the no-missing-observation instantiation: 8 -> 104.4, 7 -> 103.7-104.4, 6 -> 107.0, 5 -> 107.7 M evals/s; at 7 and 8
+// the kernel spills (200+ bytes per thread, re-read every period) and holds the whole register file while it runs;
+// hs_nk filter per 65 536 draws: 0.324 ms at 7, 0.195 ms at 5; ls2003 (P in shared memory, one-warp CTAs) unchanged
 #ifndef DYB_KF_MIN_CTAS
-#define DYB_KF_MIN_CTAS 7
+#define DYB_KF_MIN_CTAS 5
 #endif
 
 template <class M>
 struct KalmanCfg {
-  // packed R Q R' goes to shared memory ([element][thread], conflict-free) to keep the register count low
-  // enough for 7 CTAs per SM (one wave for 65 536 draws on 148 SMs).  Models whose packed covariance would not
-  // fit the register file beside T_l (ls2003: 55 + 55 + 60 doubles) keep P in shared memory as well and use
-  // one-warp CTAs so that 7 of them still fit an SM.
+  // packed R Q R' goes to shared memory ([element][thread], conflict-free) to keep the register count low.  Models whose
+  // packed covariance would not fit the register file beside T_l (ls2003: 55 + 55 + 60 doubles) keep P in shared memory as
+  // well and use one-warp CTAs.
   static constexpr int QQ_N = M::NS * (M::NS + 1) / 2;
   static constexpr bool P_SMEM = (QQ_N + M::NS * M::K > 96);
   static constexpr int BLOCK = P_SMEM ? 32 : 64;

@@ -453,6 +453,8 @@ DYB_D double abs_sum_tree(const double (&v)[MM]) {
 #ifndef DYB_CR_LANES
 #define DYB_CR_LANES 4
 #endif
+// (6 CTAs per SM = 168 registers with 128 bytes of spills in the fast pass; 5 CTAs = 200 registers, no spills, measured SLOWER:
+// cr stage 0.313 -> 0.328 ms, headline 107.7 -> 105.7 M evals/s -- unlike the filter, this kernel gains more from the twelfth warp)
 #ifndef DYB_CR_MIN_CTAS
 #define DYB_CR_MIN_CTAS (DYB_CR_SOLVER == 1 ? 5 : 6)
 #endif
